@@ -1,0 +1,218 @@
+"""The BASELINE.json benchmark configurations, built through the g3a_*/g3l_* mirror API.
+
+Model structure and parameter settings follow the reference vignettes line by line; the observation
+tables are synthetic draws (numpy default_rng(123)) with the distributions the vignettes use, because
+the vignettes' own data are unstored R ``rnorm``/``runif`` draws.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import (g3_areas, g3_fleet, g3_init_val, g3_stock, g3_timeareadata, g3_to_cuda, g3a_age,
+               g3a_grow_impl_bbinom, g3a_growmature, g3a_initialconditions_normalcv,
+               g3a_mature_continuous, g3a_naturalmortality, g3a_predate_catchability_totalfleet,
+               g3a_predate_fleet, g3a_renewal_normalcv, g3a_report_detail, g3a_time,
+               g3l_abundancedistribution, g3l_bounds_penalty, g3l_catchdistribution,
+               g3l_distribution_sumofsquares, g3l_distribution_surveyindices_log, g3l_understocking,
+               g3s_age, g3s_livesonareas, g3_suitability_exponentiall50)
+
+
+def _cut(x, breaks):
+    """cut(x, breaks = c(breaks, Inf), right = FALSE) labels."""
+    edges = list(breaks) + [np.inf]
+    idx = np.searchsorted(edges, x, side="right") - 1
+    lab = ["[%g,%s)" % (edges[i], "Inf" if np.isinf(edges[i + 1]) else "%g" % edges[i + 1])
+           for i in range(len(edges) - 1)]
+    return [lab[i] if i >= 0 else None for i in idx]
+
+
+def _count(cols: dict, keys):
+    """group_by(keys) |> summarise(number = n())."""
+    n = len(cols[keys[0]])
+    tab = {}
+    for i in range(n):
+        k = tuple(cols[c][i] for c in keys)
+        if any(v is None for v in k):
+            continue
+        tab[k] = tab.get(k, 0) + 1
+    out = {c: [] for c in keys}
+    out["number"] = []
+    for k in sorted(tab, key=lambda t: tuple(str(v) if isinstance(v, str) else v for v in t)):
+        for c, v in zip(keys, k):
+            out[c].append(v)
+        out["number"].append(tab[k])
+    return out
+
+
+def _fleet_data(rng, years, landings_mean, landings_sd, n_ldist, len_breaks, n_al, age_fn, al_mean_fn,
+                maturity=False):
+    ny = len(years)
+    landings = dict(year=list(years), step=[2] * ny, area=["IXa"] * ny,
+                    weight=list(rng.normal(landings_mean, landings_sd, ny)))
+    yy = np.repeat(years, n_ldist)
+    ln = rng.normal(50, 20, len(yy))
+    ldist = _count(dict(year=[int(y) for y in yy], step=[2] * len(yy), length=_cut(ln, len_breaks)),
+                   ["year", "step", "length"])
+    yy = np.repeat(years, n_al)
+    ages = age_fn(rng, len(yy))
+    ln = rng.normal(al_mean_fn(ages), 20, len(yy))
+    raw = dict(year=[int(y) for y in yy], step=[2] * len(yy), age=[int(a) for a in ages],
+               length=_cut(ln, len_breaks))
+    aldist = _count(raw, ["year", "step", "age", "length"])
+    out = dict(landings=landings, ldist=ldist, aldist=aldist)
+    if maturity:
+        mat = np.asarray(aldist["age"]) > rng.uniform(3, 5, len(aldist["age"]))
+        m = dict(year=aldist["year"], step=aldist["step"], length=aldist["length"],
+                 stock=["mat" if x else "imm" for x in mat], number=aldist["number"])
+        # duplicate (year, step, length, stock) rows are summed, as merge()/xtabs would
+        agg = {}
+        for i in range(len(m["year"])):
+            k = (m["year"][i], m["step"][i], m["length"][i], m["stock"][i])
+            agg[k] = agg.get(k, 0) + m["number"][i]
+        ks = list(agg.keys())
+        out["matp"] = dict(year=[k[0] for k in ks], step=[k[1] for k in ks], length=[k[2] for k in ks],
+                           stock=[k[3] for k in ks], number=[agg[k] for k in ks])
+    si = dict(year=list(years), step=[3] * ny, area=["IXa"] * ny,
+              weight=list(rng.uniform(10000, 100000, ny)))
+    out["si"] = si
+    return out
+
+
+def build_c1(seed=123):
+    """introduction-single-stock (vignettes/introduction-single-stock.Rmd:116-596, 666-701)."""
+    rng = np.random.default_rng(seed)
+    years = list(range(1990, 2024))
+    area_names = g3_areas(["IXa", "IXb"])
+    ixa = {"IXa": area_names["IXa"]}
+    fish = g3s_age(g3s_livesonareas(g3_stock("fish", range(10, 101, 10)), ixa), 1, 5)
+    d = _fleet_data(rng, years, 1000, 100, 100, range(0, 81, 20), 10000,
+                    lambda r, n: np.floor(r.uniform(1, 5, n)), lambda a: 30 + a * 10)
+    f_surv = g3s_livesonareas(g3_fleet("f_surv"), ixa)
+    actions = [
+        g3a_time(1990, 2023, [3, 3, 3, 3]),
+        g3a_growmature(fish, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4)),
+        g3a_naturalmortality(fish),
+        g3a_initialconditions_normalcv(fish),
+        g3a_renewal_normalcv(fish, run_step=2),
+        g3a_age(fish),
+        g3l_understocking([fish], nll_breakdown=True),
+        g3a_predate_fleet(f_surv, [fish], suitabilities=g3_suitability_exponentiall50(),
+                          catchability_f=g3a_predate_catchability_totalfleet(
+                              g3_timeareadata("landings_f_surv", d["landings"], "weight", areas=area_names))),
+        g3l_catchdistribution("ldist_f_surv", d["ldist"], fleets=[f_surv], stocks=[fish],
+                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              report=True, nll_breakdown=True),
+        g3l_catchdistribution("aldist_f_surv", d["aldist"], fleets=[f_surv], stocks=[fish],
+                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              report=True, nll_breakdown=True),
+        g3l_abundancedistribution("dist_si_cpue", d["si"], stocks=[fish],
+                                  function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
+                                  area_group=area_names, report=True, nll_breakdown=True),
+    ]
+    actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    midlen = fish.midlen
+    est_l50 = midlen[len(midlen) // 2 - 1]
+    est_linf = max(midlen)
+    est_t0 = fish.minage - 0.8
+    p = model.parameter_template
+    p = g3_init_val(p, "*.rec|init.scalar", 1, optimise=False)
+    p = g3_init_val(p, "*.init.#", 10, lower=0.001, upper=30)
+    p = g3_init_val(p, "*.rec.#", 1e-4, lower=1e-6, upper=1e-2)
+    p = g3_init_val(p, "*.rec.proj", 0.002)
+    p = g3_init_val(p, "init.F", 0.5, lower=0.1, upper=1)
+    p = g3_init_val(p, "*.M.#", 0.15, lower=0.001, upper=10)
+    p = g3_init_val(p, "*.Linf", est_linf, spread=0.2)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.04, upper=1.2)
+    p = g3_init_val(p, "*.t0", est_t0, spread=2)
+    p = g3_init_val(p, "*.walpha", 0.01, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.*.alpha", 0.07, lower=0.01, upper=0.2)
+    p = g3_init_val(p, "*.*.l50", est_l50, spread=0.25)
+    p = g3_init_val(p, "*.bbin", 1, lower=1e-05, upper=10)
+    return model, p
+
+
+def build_c2(seed=123):
+    """multiple-substocks (vignettes/multiple-substocks.Rmd:59-439)."""
+    rng = np.random.default_rng(seed)
+    years = list(range(1990, 2024))
+    area_names = g3_areas(["IXa", "IXb"])
+    ixa = {"IXa": area_names["IXa"]}
+    st_imm = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "imm"}, range(5, 101, 5)), 1, 5), ixa)
+    st_mat = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "mat"}, range(5, 101, 5)), 3, 10), ixa)
+    stocks = [st_imm, st_mat]
+    d = _fleet_data(rng, years, 1e5, 10, 1000, range(0, 111, 5), 10000,
+                    lambda r, n: np.floor(np.minimum(r.normal(6, 1, n), 10)), lambda a: 30 + a * 2,
+                    maturity=True)
+    f_surv = g3s_livesonareas(g3_fleet("f_surv"), ixa)
+    actions = [
+        g3a_time(1990, 2023, [3, 3, 3, 3]),
+        g3a_growmature(st_imm, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4),
+                       maturity_f=g3a_mature_continuous(), output_stocks=[st_mat], transition_f=True),
+        g3a_naturalmortality(st_imm),
+        g3a_initialconditions_normalcv(st_imm),
+        g3a_renewal_normalcv(st_imm),
+        g3a_age(st_imm, output_stocks=[st_mat]),
+        g3a_growmature(st_mat, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4)),
+        g3a_naturalmortality(st_mat),
+        g3a_initialconditions_normalcv(st_mat),
+        g3a_age(st_mat),
+        g3l_understocking(stocks, nll_breakdown=True),
+        g3a_predate_fleet(f_surv, stocks,
+                          suitabilities=g3_suitability_exponentiall50(by_stock="species"),
+                          catchability_f=g3a_predate_catchability_totalfleet(
+                              g3_timeareadata("landings_f_surv", d["landings"], "weight", areas=area_names))),
+        g3l_catchdistribution("ldist_f_surv", d["ldist"], fleets=[f_surv], stocks=stocks,
+                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              report=True, nll_breakdown=True),
+        g3l_catchdistribution("aldist_f_surv", d["aldist"], fleets=[f_surv], stocks=stocks,
+                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              report=True, nll_breakdown=True),
+        g3l_catchdistribution("matp_f_surv", d["matp"], fleets=[f_surv], stocks=stocks,
+                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              report=True, nll_breakdown=True),
+        g3l_abundancedistribution("dist_si_cpue", d["si"], stocks=stocks,
+                                  function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
+                                  area_group=area_names, report=True, nll_breakdown=True),
+    ]
+    actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    midlen = st_imm.midlen
+    est_l50 = midlen[len(midlen) // 2 - 1]
+    est_linf = midlen[-3]
+    est_t0 = st_imm.minage - 0.8
+    p = model.parameter_template
+    p = g3_init_val(p, "*.rec|init.scalar", 1000, optimise=False)
+    p = g3_init_val(p, "*.init.#", 10, lower=0.001, upper=10)
+    p = g3_init_val(p, "*.rec.#", 100, lower=1e-6, upper=1000)
+    p = g3_init_val(p, "*.rec.proj", 0.002)
+    p = g3_init_val(p, "*.M.#", 0.15, lower=0.001, upper=10)
+    p = g3_init_val(p, "init.F", 0.5, lower=0.1, upper=10)
+    p = g3_init_val(p, "*.Linf", est_linf, spread=2)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.04, upper=1.2)
+    p = g3_init_val(p, "*.t0", est_t0, optimise=False)
+    p = g3_init_val(p, "*.walpha", 0.01, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.*.alpha", 0.07, lower=0.01, upper=1.8)
+    p = g3_init_val(p, "*.*.l50", est_l50, spread=1.5)
+    p = g3_init_val(p, "*.mat.alpha", 0.07, lower=0.0001, upper=1.8)
+    p = g3_init_val(p, "*.mat.l50", est_l50, spread=3.5)
+    p = g3_init_val(p, "*.bbin", 100, lower=1e-05, upper=1500)
+    return model, p
+
+
+def parameter_batch(params, B, seed=2026, width=0.10):
+    """Synthetic parameter batch: each optimised parameter is the template
+    value perturbed uniformly within +-width of (upper - lower), clipped to the bounds; fixed
+    parameters stay at their template values. Returns B x n_optimised."""
+    rng = np.random.default_rng(seed)
+    idx = params.optimised_indices()
+    v = params.values()[idx]
+    lo = np.asarray(params.lower)[idx]
+    up = np.asarray(params.upper)[idx]
+    P = v[None, :] + rng.uniform(-width, width, (B, len(idx))) * (up - lo)[None, :]
+    return np.clip(P, lo[None, :], up[None, :])
+
+
+CONFIGS = {"C1": build_c1, "C2": build_c2}

@@ -1,0 +1,617 @@
+"""g3_to_cuda(): lower an action list into the packed spec; g3_cuda_adfun(): bind it to the GPU.
+
+Sits beside the reference's ``g3_to_r()`` / ``g3_to_tmb()`` (R/run_r.R:11, R/run_tmb.R:709) and
+``g3_tmb_adfun()`` (R/run_tmb.R:1118): same inputs (action list, parameter template), same outputs
+(``$par``, ``$fn``, ``$gr``, ``$report``) plus the batched entry points. Models outside the supported
+action subset raise :class:`G3Unsupported`; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+from . import actions as A
+from . import likelihood as LK
+from .formula import Ctx, G3Unsupported, Lowerer, ParameterTemplate, g3_parameterized, wrap
+from .spec import K, SpecBuilder
+from .stock import Stock
+
+
+def _flatten(actions):
+    out = []
+    for a in actions:
+        if a is None:
+            continue
+        if isinstance(a, (list, tuple)):
+            out.extend(_flatten(a))
+        else:
+            out.append(a)
+    return out
+
+
+def _lgmatrix(src: Stock, dst: Stock):
+    """stock_reshape() length-regrouping matrix (R/step.R:249-282); None when grids are equal."""
+    s_lg, d_lg = list(src.minlen), list(dst.minlen)
+    if len(s_lg) == len(d_lg) and np.allclose(s_lg, d_lg):
+        return None
+    s_up = src.upperlen if math.isfinite(src.upperlen) else s_lg[-1] + 1
+    d_up = dst.upperlen if math.isfinite(dst.upperlen) else max(s_lg[-1], d_lg[-1]) + 1
+    M = np.zeros((len(d_lg), len(s_lg)))
+    for di in range(len(d_lg)):
+        lo_d = d_lg[di]
+        up_d = d_up if di >= len(d_lg) - 1 else d_lg[di + 1]
+        for si in range(len(s_lg)):
+            lo_s = s_lg[si]
+            up_s = s_up if si >= len(s_lg) - 1 else s_lg[si + 1]
+            inter = min(up_s, up_d) - max(lo_s, lo_d)
+            M[di, si] = inter / (up_s - lo_s) if inter > 0 else 0.0
+    return M
+
+
+class G3CudaModel:
+    """Result of g3_to_cuda(): carries the same attributes g3_to_tmb() attaches
+    (``actions``, ``parameter_template``) plus the packed spec."""
+
+    def __init__(self):
+        self.actions = None
+        self.parameter_template = None
+        self._builder = None
+        self.stock_names, self.stock_shapes, self.stock_dims = [], [], []
+        self.comp_names, self.comp_shapes, self.comp_units = [], [], []
+        self.nll_names = []
+        self.n_steps = 0
+        self.time_labels = []
+        self.has_bounds = None
+
+    def pack(self, parameters: ParameterTemplate = None):
+        """Final (ints, reals): adds the g3l_bounds_penalty section from the template's lower/upper,
+        as g3_tmb_adfun fills the __lower/__upper DATA_SCALARs (R/run_tmb.R:1234-1235)."""
+        pt = self.parameter_template if parameters is None else parameters
+        if list(pt.switch) != list(self.parameter_template.switch):
+            raise ValueError("Parameters not in expected order")   # R/run_tmb.R:1156-1158
+        b = SpecBuilder()
+        b.ints = list(self._builder.ints)
+        b.reals = list(self._builder.reals)
+        idx, lu = [], []
+        if self.has_bounds is not None:
+            for name in sorted(pt.switch):   # radix / C-locale order of step ids (R/run.R:67-69)
+                i = pt.index(name)
+                lo, up = pt.lower[i], pt.upper[i]
+                if math.isfinite(lo) and math.isfinite(up):
+                    idx.append(i)
+                    lu += [lo, up]
+            ws = [self.has_bounds.weight, self.has_bounds.scale]
+        else:
+            ws = [0.0, 0.0]
+        b.ints[K["G3H_NBOUND"]] = len(idx)
+        b.ints[K["G3H_BOUND_OFF"]] = b.alloc_ints(idx)
+        b.ints[K["G3H_BOUND_ROFF"]] = b.alloc_reals(lu)
+        b.ints[K["G3H_BOUND_WS_ROFF"]] = b.alloc_reals(ws)
+        return b.finish()
+
+
+def g3_to_cuda(actions, strict=False) -> G3CudaModel:
+    acts = _flatten(actions)
+    by_kind = {}
+    for a in acts:
+        if not isinstance(a, A.Action):
+            raise G3Unsupported(f"unsupported action object {a!r}")
+        by_kind.setdefault(a.kind, []).append(a)
+
+    times = by_kind.get("time", [])
+    if len(times) != 1:
+        raise ValueError("exactly one g3a_time() action is required")
+    tm = times[0]
+    S = len(tm.step_lengths)
+    if S > 31:
+        raise G3Unsupported("more than 31 steps per year")
+    n_years = tm.end_year - tm.start_year + 1
+    NT = S * n_years
+    dt0 = tm.step_lengths[0] / 12.0
+
+    # ---- stocks (alphabetical = step_id radix order, R/step.R:523-543) and fleets
+    stocks = OrderedDict()
+    preds = OrderedDict()
+
+    def note_stock(s):
+        if s.lengthgroups is None:
+            raise G3Unsupported(f"{s.name} has no length dimension")
+        if s.minage is None or s.areas is None:
+            raise G3Unsupported(f"stock {s.name} must have age and area dimensions")
+        stocks.setdefault(s.name, s)
+
+    for k in ("init", "renewal", "naturalmortality", "growmature", "age", "migrate"):
+        for a in by_kind.get(k, []):
+            note_stock(a.stock)
+    for a in by_kind.get("growmature", []) + by_kind.get("age", []):
+        for o in a.output_stocks:
+            note_stock(o)
+    for a in by_kind.get("predate", []):
+        for p in a.prey_stocks:
+            note_stock(p)
+        preds.setdefault(a.predstock.name, a)
+        if a.predstock.lengthgroups is not None:
+            note_stock(a.predstock)
+    for a in by_kind.get("distribution", []):
+        for p in a.stocks:
+            note_stock(p)
+    for a in by_kind.get("understocking", []):
+        for p in a.prey_stocks:
+            note_stock(p)
+    stocks = OrderedDict(sorted(stocks.items()))
+    sidx = {n: i for i, n in enumerate(stocks)}
+    preds = OrderedDict(sorted(preds.items()))
+
+    model_areas = sorted({v for s in stocks.values() for v in s.areas.values()})
+
+    b = SpecBuilder()
+    H = b.ints
+    tmpl = ParameterTemplate()
+    low = Lowerer(b, tmpl, tm.start_year, tm.end_year, S)
+
+    H[K["G3H_START_YEAR"]], H[K["G3H_END_YEAR"]] = tm.start_year, tm.end_year
+    H[K["G3H_NSTEPS"]] = S
+    H[K["G3H_STEPLEN_OFF"]] = b.alloc_ints(tm.step_lengths)
+    H[K["G3H_NT"]] = NT
+    H[K["G3H_NAREA"]] = len(model_areas)
+
+    # parameter order follows first appearance in the collated code (R/run_tmb.R:715):
+    H[K["G3H_PAR_RETRO"]] = tmpl.add("retro_years", 0.0, optimise=False)
+
+    # ---- stock records
+    cell_off = 0
+    srec = {}
+    for name, s in stocks.items():
+        r = [0] * K["G3S_LEN"]
+        r[K["G3S_L"]], r[K["G3S_MINAGE"]], r[K["G3S_NAGE"]] = s.L, s.minage, s.nage
+        r[K["G3S_NAREA"]] = len(s.areas)
+        r[K["G3S_AREA_OFF"]] = b.alloc_ints(s.areas.values())
+        r[K["G3S_CELL_OFF"]] = cell_off
+        r[K["G3S_MIDLEN_ROFF"]] = b.alloc_reals(s.midlen)
+        r[K["G3S_PLUSDL_ROFF"]] = b.alloc_reals([s.plusdl])
+        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF"):
+            r[K[f]] = -1
+        dims = [d for d in s.dims if d != "length"]
+        r[K["G3S_DIMORDER"]] = 0 if dims == ["age", "area"] else 1
+        s._cell_off = cell_off
+        cell_off += s.L * s.nage * len(s.areas)
+        srec[name] = r
+    ncell = cell_off
+    H[K["G3H_NCELL"]] = ncell
+
+    def columns(s):
+        for ri, (an, aid) in enumerate(s.areas.items()):
+            for ai in range(s.nage):
+                yield ri, an, aid, ai, s.minage + ai
+
+    def one_per_stock(kind, label):
+        out = {}
+        for a in by_kind.get(kind, []):
+            if a.stock.name in out:
+                raise G3Unsupported(f"more than one {label} action for {a.stock.name}")
+            out[a.stock.name] = a
+        return out
+
+    # ---- initial conditions (order -1)
+    inits = one_per_stock("init", "g3a_initialconditions")
+    for name, s in stocks.items():
+        a = inits.get(name)
+        if a is None:
+            continue
+        tab = []
+        for ri, an, aid, ai, ag in columns(s):
+            c = Ctx(stock=s, age=ag, area=aid, area_name=an, cur_year=tm.start_year, cur_step=1,
+                    cur_step_size=dt0)
+            tab += [low.slot(a.mean_f, c), low.slot(a.stddev_f, c), low.slot(a.factor_f, c),
+                    low.slot(a.alpha_f, c), low.slot(a.beta_f, c)]
+        srec[name][K["G3S_INIT_OFF"]] = b.alloc_ints(tab)
+
+    if by_kind.get("report_detail"):
+        tmpl.add("report_detail", 1.0, optimise=False)
+
+    # ---- predation (order 3): predators by name, prey by name
+    pred_recs, pp_recs, pp_index = [], [], {}
+    for pname, a in preds.items():
+        pr = [0] * K["G3P_LEN"]
+        ps = a.predstock
+        if ps.areas is None:
+            raise G3Unsupported(f"predator {pname} must live on areas")
+        cat = a.catchability_f
+        if cat.kind == "totalfleet":
+            if ps.lengthgroups is not None:
+                raise G3Unsupported("totalfleet catchability on a stock predator")
+            pr[K["G3P_KIND"]] = K["G3PRED_TOTALFLEET"]
+            E = []
+            for t in range(NT):
+                y, st = tm.start_year + t // S, t % S + 1
+                for aid in ps.areas.values():
+                    E.append(cat.E.lookup(y, st, aid))
+            pr[K["G3P_E_ROFF"]] = b.alloc_reals(E)
+            pr[K["G3P_STOCK"]] = -1
+            pr[K["G3P_SLOT_OFF"]] = -1
+        else:
+            raise G3Unsupported(f"catchability {cat.kind}")
+        pr[K["G3P_NAREA"]] = len(ps.areas)
+        pr[K["G3P_AREA_OFF"]] = b.alloc_ints(ps.areas.values())
+        pr[K["G3P_PP_FIRST"]] = len(pp_recs)
+        for prey in sorted(a.prey_stocks, key=lambda x: x.name):
+            su = a.suit_for(prey)
+            c = Ctx(stock=prey, predstock=ps)
+            q = [0] * K["G3PP_LEN"]
+            q[K["G3PP_PRED"]], q[K["G3PP_PREY"]] = len(pred_recs), sidx[prey.name]
+            q[K["G3PP_SUIT_KIND"]] = {"expl50": K["G3SUIT_EXPL50"], "andersen": K["G3SUIT_ANDERSEN"],
+                                      "constant": K["G3SUIT_CONSTANT"]}[su.kind]
+            slots = [low.slot(x, c) for x in su.args]
+            q[K["G3PP_SUIT_OFF"]] = b.alloc_ints(slots + [-1] * (6 - len(slots)))
+            q[K["G3PP_ENERGY"]] = q[K["G3PP_PREF"]] = -1
+            pp_index[(pname, prey.name)] = len(pp_recs)
+            pp_recs.append(q)
+        pr[K["G3P_N_PP"]] = len(pp_recs) - pr[K["G3P_PP_FIRST"]]
+        pred_recs.append(pr)
+
+    # ---- natural mortality (order 4)
+    for name, a in one_per_stock("naturalmortality", "g3a_naturalmortality").items():
+        s = stocks[name]
+        tab = [low.slot(a.param_f, Ctx(stock=s, age=ag, area=aid, area_name=an))
+               for ri, an, aid, ai, ag in columns(s)]
+        srec[name][K["G3S_MORT_OFF"]] = b.alloc_ints(tab)
+
+    # ---- growth + maturity (order 5 / 7)
+    maxn = 0
+
+    def out_table(s, outs, ratios):
+        tab = []
+        for o, rt in zip(outs, ratios):
+            if not np.allclose(o.minlen, s.minlen) or o.L != s.L:
+                raise G3Unsupported(f"moving {s.name} into {o.name}: length groups differ")
+            tab += [sidx[o.name], low.slot(wrap(rt), Ctx(stock=s))]
+        return b.alloc_ints(tab)
+
+    for name, a in one_per_stock("growmature", "g3a_growmature").items():
+        s, r, im = stocks[name], srec[name], a.impl_f
+        c = Ctx(stock=s)
+        r[K["G3S_GROW_N"]] = im.maxlengthgroupgrowth
+        maxn = max(maxn, im.maxlengthgroupgrowth)
+        r[K["G3S_GROW_OFF"]] = b.alloc_ints([
+            low.slot(im.delta_len_f.linf_f, c), low.slot(im.delta_len_f.kappa_f, c),
+            low.slot(im.beta_f, c), low.slot(im.delta_wgt_f.alpha_f, c), low.slot(im.delta_wgt_f.beta_f, c)])
+        m = a.maturity_f
+        if m is not None:
+            r[K["G3S_MAT_KIND"]] = K["G3MAT_CONTINUOUS"] if m.kind == "continuous" else K["G3MAT_CONSTANT"]
+            r[K["G3S_MAT_OFF"]] = b.alloc_ints(
+                [(-1 if x is None else low.slot(x, c)) for x in (m.alpha, m.l50, m.beta, m.a50)])
+            if m.kind == "continuous" and (m.alpha is None or m.l50 is None):
+                raise G3Unsupported("g3a_mature_continuous needs alpha and l50")
+            if (m.alpha is None) != (m.l50 is None) or (m.beta is None) != (m.a50 is None):
+                raise ValueError("l50 must be supplied if alpha is supplied (and a50 with beta)")
+            tf = a.transition_f
+            if tf == "cur_step_final":
+                mask = 1 << (S - 1)
+            elif tf is True:
+                mask = (1 << S) - 1
+            else:
+                mask = 0
+                for st in tf:
+                    mask |= 1 << (int(st) - 1)
+            r[K["G3S_TRANS_MASK"]] = mask
+            r[K["G3S_N_OUT"]] = len(a.output_stocks)
+            r[K["G3S_OUT_OFF"]] = out_table(s, a.output_stocks, a.output_ratios)
+            omap = []
+            for o in a.output_stocks:
+                for ri, an, aid, ai, ag in columns(s):
+                    ok = (o.minage <= ag <= o.maxage) and (aid in o.areas.values())
+                    if ok:
+                        ro = list(o.areas.values()).index(aid)
+                        base = o._cell_off + (ro * o.nage + (ag - o.minage)) * o.L
+                    for l in range(s.L):
+                        omap.append(base + l if ok else -1)
+            r[K["G3S_OUT_MAP_OFF"]] = b.alloc_ints(omap)
+
+    # ---- renewal (order 8)
+    for name, s in stocks.items():
+        recs = []
+        for a in by_kind.get("renewal", []):
+            if a.stock.name != name:
+                continue
+            if a.run_age is None:
+                raise G3Unsupported("g3a_renewal: run_age = NULL")
+            if not (s.minage <= a.run_age <= s.maxage):
+                continue
+            q = [0] * K["G3R_LEN"]
+            q[K["G3R_RUN_STEP"]] = 0 if a.run_step is None else int(a.run_step)
+            q[K["G3R_AGE_IDX"]] = a.run_age - s.minage
+            an0, aid0 = next(iter(s.areas.items()))
+            c = Ctx(stock=s, age=a.run_age, area=aid0, area_name=an0)
+            q[K["G3R_MEAN"]], q[K["G3R_SD"]] = low.slot(a.mean_f, c), low.slot(a.stddev_f, c)
+            q[K["G3R_WALPHA"]], q[K["G3R_WBETA"]] = low.slot(a.alpha_f, c), low.slot(a.beta_f, c)
+            ftab = []
+            for y in range(tm.start_year, tm.end_year + 1):
+                for an, aid in s.areas.items():
+                    cy = Ctx(stock=s, age=a.run_age, area=aid, area_name=an, cur_year=y,
+                             cur_step=(a.run_step or 1))
+                    ftab.append(low.slot(a.factor_f, cy))
+            q[K["G3R_FACTOR_OFF"]] = b.alloc_ints(ftab)
+            recs.append(q)
+        srec[name][K["G3S_N_RENEW"]] = len(recs)
+        srec[name][K["G3S_RENEW_OFF"]] = b.alloc_ints([x for q in recs for x in q])
+
+    # ---- ageing (order 12)
+    for name, a in one_per_stock("age", "g3a_age").items():
+        s, r = stocks[name], srec[name]
+        r[K["G3S_AGE_ENABLE"]] = 1
+        r[K["G3S_AGE_N_OUT"]] = len(a.output_stocks)
+        r[K["G3S_AGE_OUT_OFF"]] = out_table(s, a.output_stocks, a.output_ratios)
+        amap = []
+        for o in a.output_stocks:
+            ag = s.maxage + 1
+            for an, aid in s.areas.items():
+                ok = (o.minage <= ag <= o.maxage) and (aid in o.areas.values())
+                if ok:
+                    ro = list(o.areas.values()).index(aid)
+                    base = o._cell_off + (ro * o.nage + (ag - o.minage)) * o.L
+                for l in range(s.L):
+                    amap.append(base + l if ok else -1)
+        r[K["G3S_AGE_MAP_OFF"]] = b.alloc_ints(amap)
+
+    if by_kind.get("migrate"):
+        raise G3Unsupported("g3a_migrate is not lowered yet")
+
+    # ---- likelihood components (order 10), by generated name
+    comps = sorted(by_kind.get("distribution", []), key=lambda a: a.nll_name)
+    xbufs, xbuf_index, comp_recs = [], {}, []
+    model = G3CudaModel()
+    for a in comps:
+        ld = a.ld
+        wslot_ctx = Ctx()
+        wcode = low._lower(a.weight, wslot_ctx)
+        if wcode[0] != "x" or len(wcode[1]) != 2 or wcode[1][0] != K["G3OP_PARAM"]:
+            raise G3Unsupported("likelihood weight must be a plain parameter")
+        q = [0] * K["G3C_LEN"]
+        fn = a.function_f
+        q[K["G3C_FUNC"]] = {"sumofsquares": K["G3F_SUMOFSQUARES"], "multinomial": K["G3F_MULTINOMIAL"],
+                            "surveyindices_log": K["G3F_SI_LOG"],
+                            "surveyindices_linear": K["G3F_SI_LINEAR"]}[fn.name]
+        q[K["G3C_WEIGHT_PAR"]] = wcode[1][1]
+        st_sorted = sorted(a.stocks, key=lambda x: x.name)
+        if a.fleets:
+            pps = []
+            for f in sorted(a.fleets, key=lambda x: x.name):
+                for p in st_sorted:
+                    if (f.name, p.name) not in pp_index:
+                        raise G3Unsupported(f"{a.nll_name}: no g3a_predate for {f.name} on {p.name}")
+                    pps.append(pp_index[(f.name, p.name)])
+            key = ("catch", ld.unit, tuple(pps))
+        else:
+            pps = []
+            key = ("abund", ld.unit, tuple(sidx[p.name] for p in st_sorted))
+        # destination of every cell
+        entries = [[] for _ in range(ld.n_dest)]
+        cell_dest = [-1] * ncell
+        cell_coef = [0.0] * ncell
+        for p in st_sorted:
+            sg = 0
+            if ld.stock_map is not None:
+                sg = ld.stock_map[p.name]
+                if sg < 0:
+                    continue
+            M = _lgmatrix(p, ld.lenstock)
+            for ri, an, aid, ai, ag in columns(p):
+                if ld.area_group is not None:
+                    hit = [i for i, v in enumerate(ld.area_group.values()) if int(v) == aid]
+                    if not hit:
+                        continue
+                    areag = hit[0]
+                else:
+                    areag = 0
+                if ld.minage is not None:
+                    if not (ld.minage <= ag <= ld.maxage):
+                        continue
+                    ageg = ag - ld.minage
+                else:
+                    ageg = 0
+                for l in range(p.L):
+                    cell = p._cell_off + (ri * p.nage + ai) * p.L + l
+                    for bi in range(ld.n_bins):
+                        coef = (1.0 if bi == l else 0.0) if M is None else M[bi, l]
+                        if coef != 0.0:
+                            e = ld.dest(areag, sg, ageg, bi)
+                            entries[e].append((cell, coef))
+                            cell_dest[cell], cell_coef[cell] = e, coef
+        mode = 1 if ld.n_bins == 1 else 0
+        q[K["G3C_MODE"]] = mode
+        q[K["G3C_N_DEST"]], q[K["G3C_N_BINS"]] = ld.n_dest, ld.n_bins
+        q[K["G3C_N_SLICES"]], q[K["G3C_N_AREAG"]] = ld.n_slices, ld.n_areag
+        if mode == 0:
+            ptr, idx, coef = [0], [], []
+            for e in entries:
+                for cell, cf in e:
+                    idx.append(cell)
+                    coef.append(cf)
+                ptr.append(len(idx))
+            q[K["G3C_CSR_PTR_OFF"]] = b.alloc_ints(ptr)
+            q[K["G3C_CSR_IDX_OFF"]] = b.alloc_ints(idx)
+            q[K["G3C_CSR_COEF_ROFF"]] = b.alloc_reals(coef)
+            q[K["G3C_CELL_DEST_OFF"]] = q[K["G3C_CELL_COEF_ROFF"]] = -1
+        else:
+            q[K["G3C_CELL_DEST_OFF"]] = b.alloc_ints(cell_dest)
+            q[K["G3C_CELL_COEF_ROFF"]] = b.alloc_reals(cell_coef)
+            q[K["G3C_CSR_PTR_OFF"]] = q[K["G3C_CSR_IDX_OFF"]] = q[K["G3C_CSR_COEF_ROFF"]] = -1
+        tkey = {t: i for i, t in enumerate(ld.times)}
+        tidx, cmp_ = [], []
+        for t in range(NT):
+            y, st = tm.start_year + t // S, t % S + 1
+            tidx.append(tkey.get(y * 100 + (st if ld.has_step else 0), -1))
+            cmp_.append(1 if (ld.has_step or st == S) else 0)
+        q[K["G3C_TIDX_OFF"]], q[K["G3C_CMP_OFF"]] = b.alloc_ints(tidx), b.alloc_ints(cmp_)
+        q[K["G3C_N_TIMES"]] = len(ld.times)
+        q[K["G3C_OBS_ROFF"]] = b.alloc_reals(ld.obs)
+        if fn.name.startswith("surveyindices"):
+            al, be = fn.kw["alpha"], fn.kw["beta"]
+            q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([float("nan") if al is None else float(al),
+                                                    float("nan") if be is None else float(be)])
+        elif fn.name == "multinomial":
+            q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([fn.kw["epsilon"], 0.0])
+        else:
+            q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([0.0, 0.0])
+        if key not in xbuf_index:
+            xbuf_index[key] = len(xbufs)
+            xbufs.append(dict(kind=0 if key[0] == "catch" else 1, unit=0 if ld.unit == "num" else 1,
+                              pps=list(pps), active=[0] * NT))
+        xb = xbufs[xbuf_index[key]]
+        q[K["G3C_XBUF"]] = xbuf_index[key]
+        for t in range(NT):
+            if tidx[t] >= 0:
+                xb["active"][t] = 1
+        comp_recs.append(q)
+        model.comp_names.append(a.nll_name)
+        model.comp_units.append(ld.unit)
+        model.comp_shapes.append(dict(n_times=len(ld.times), n_areag=ld.n_areag, n_stockg=ld.n_stockg,
+                                      n_age=ld.n_age, n_bins=ld.n_bins, times=list(ld.times)))
+
+    xrecs = []
+    for xb in xbufs:
+        x = [0] * K["G3X_LEN"]
+        x[K["G3X_KIND"]], x[K["G3X_UNIT"]] = xb["kind"], xb["unit"]
+        x[K["G3X_N_PP"]], x[K["G3X_PP_OFF"]] = len(xb["pps"]), b.alloc_ints(xb["pps"])
+        x[K["G3X_ACTIVE_OFF"]] = b.alloc_ints(xb["active"])
+        xrecs.append(x)
+
+    # ---- understocking
+    us = by_kind.get("understocking", [])
+    if len(us) > 1:
+        raise G3Unsupported("more than one g3l_understocking")
+    if us:
+        H[K["G3H_US_N"]] = len(us[0].prey_stocks)
+        H[K["G3H_US_OFF"]] = b.alloc_ints(sorted(sidx[p.name] for p in us[0].prey_stocks))
+        H[K["G3H_US_ROFF"]] = b.alloc_reals([us[0].power, us[0].weight])
+    else:
+        H[K["G3H_US_N"]], H[K["G3H_US_OFF"]] = 0, 0
+        H[K["G3H_US_ROFF"]] = b.alloc_reals([2.0, 0.0])
+
+    H[K["G3H_PAR_PROJECT"]] = tmpl.add("project_years", 0.0, optimise=False)
+
+    # ---- write record tables
+    H[K["G3H_NSTOCK"]] = len(stocks)
+    H[K["G3H_STOCK_OFF"]] = b.alloc_ints([x for n in stocks for x in srec[n]])
+    H[K["G3H_NPRED"]] = len(pred_recs)
+    H[K["G3H_PRED_OFF"]] = b.alloc_ints([x for r in pred_recs for x in r])
+    H[K["G3H_NPP"]] = len(pp_recs)
+    H[K["G3H_PP_OFF"]] = b.alloc_ints([x for r in pp_recs for x in r])
+    H[K["G3H_NCOMP"]] = len(comp_recs)
+    H[K["G3H_COMP_OFF"]] = b.alloc_ints([x for r in comp_recs for x in r])
+    H[K["G3H_NXBUF"]] = len(xrecs)
+    H[K["G3H_XBUF_OFF"]] = b.alloc_ints([x for r in xrecs for x in r])
+    H[K["G3H_NSLOT"]], H[K["G3H_SLOT_OFF"]] = low.finish()
+    H[K["G3H_NPAR"]] = len(tmpl)
+    H[K["G3H_MAXL"]] = max(s.L for s in stocks.values())
+    H[K["G3H_MAXN"]] = maxn
+    H[K["G3H_NNLL"]] = len(comp_recs) + 2
+
+    model.actions = acts
+    model.parameter_template = tmpl
+    model._builder = b
+    bp = by_kind.get("bounds_penalty", [])
+    model.has_bounds = bp[0] if bp else None
+    for n, s in stocks.items():
+        model.stock_names.append(n)
+        model.stock_shapes.append((s.L, s.nage, len(s.areas)))
+        model.stock_dims.append(list(s.dims))
+    model.nll_names = list(model.comp_names) + ["understocking", "bounds"]
+    model.n_steps = NT
+    model.time_labels = ["%d-%02d" % (tm.start_year + t // S, t % S + 1) for t in range(NT)]
+    return model
+
+
+# --------------------------------------------------------------------------- binding
+class G3CudaADFun:
+    """Mirror of the list g3_tmb_adfun() returns (R/run_tmb.R:1254-1325): ``par``, ``fn``, ``gr``,
+    ``report`` -- plus batched ``fn_batch`` / ``gr_batch`` / ``nll_components_batch``."""
+
+    def __init__(self, model: G3CudaModel, parameters: ParameterTemplate = None, device=0):
+        from ._lib import Handle
+        self.model = model
+        self.parameters = (model.parameter_template if parameters is None else parameters).copy()
+        ints, reals = model.pack(self.parameters)
+        self.opt_idx = self.parameters.optimised_indices()
+        if len(self.opt_idx) == 0:
+            raise ValueError("No parameters with optimise=TRUE set")    # R/run_tmb.R:1166-1168
+        self.par_names = [self.parameters.switch[i] for i in self.opt_idx]
+        self.par = self.parameters.values()[self.opt_idx].copy()
+        self._full = self.parameters.values()
+        self.handle = Handle(ints, reals, device)
+        self.last_par = self.par.copy()
+
+    # full PARAMETER matrix from optimiser-facing vectors
+    def full_par(self, P) -> np.ndarray:
+        P = np.atleast_2d(np.asarray(P, dtype=np.float64))
+        if P.shape[1] != len(self.opt_idx):
+            raise ValueError(f"expected {len(self.opt_idx)} parameters per vector, got {P.shape[1]}")
+        out = np.tile(self._full, (P.shape[0], 1))
+        out[:, self.opt_idx] = P
+        return out
+
+    def fn(self, par=None) -> float:
+        par = self.par if par is None else np.asarray(par, dtype=np.float64)
+        self.last_par = par.copy()
+        return float(self.fn_batch(par[None, :])[0])
+
+    def gr(self, par=None) -> np.ndarray:
+        par = self.par if par is None else np.asarray(par, dtype=np.float64)
+        self.last_par = par.copy()
+        return self.gr_batch(par[None, :])[1]          # 1 x n matrix, like TMB
+
+    def fn_batch(self, P) -> np.ndarray:
+        return self.handle.eval_batch(self.full_par(P))[0]
+
+    def nll_components_batch(self, P):
+        nll, comp, _ = self.handle.eval_batch(self.full_par(P), want_comp=True)
+        return nll, comp
+
+    def gr_batch(self, P):
+        nll, _, grad = self.handle.eval_batch(self.full_par(P), tangent_idx=self.opt_idx)
+        return nll, grad
+
+    def report(self, par=None) -> dict:
+        par = self.par if par is None else np.asarray(par, dtype=np.float64)
+        raw = self.handle.report(self.full_par(par[None, :])[0])
+        return unpack_report(self.model, raw)
+
+
+def unpack_report(model: G3CudaModel, raw: np.ndarray) -> dict:
+    """Split the flat g3cuda_report() buffer into named arrays in the model's own dimension order
+    (names as in the reference's REPORT()s, baseline/multiple-substocks.cpp:763-862)."""
+    NT = model.n_steps
+    out = OrderedDict()
+    pos = 0
+    out["nll"] = float(raw[pos]); pos += 1
+    nn = len(model.nll_names)
+    br = raw[pos:pos + nn * NT].reshape(nn, NT); pos += nn * NT
+    for i, n in enumerate(model.comp_names):
+        out[f"nll_{n}__{model.comp_units[i]}"] = br[i].copy()
+    out["nll_understocking__wgt"] = br[nn - 2].copy()
+    out["nll_bounds"] = br[nn - 1].copy()
+    for n, (L, A_, R), dims in zip(model.stock_names, model.stock_shapes, model.stock_dims):
+        nc = L * A_ * R
+        for what in ("num", "wgt"):
+            a = raw[pos:pos + NT * nc].reshape(NT, R, A_, L); pos += NT * nc
+            order = [d for d in dims if d != "length"]
+            # canonical (time, area, age, length) -> model order with length fastest, time last
+            if order == ["age", "area"]:
+                arr = a.transpose(3, 2, 1, 0)     # length, age, area, time
+            else:
+                arr = a.transpose(3, 1, 2, 0)     # length, area, age, time
+            out[f"dstart_{n}__{what}"] = np.ascontiguousarray(arr)
+    for n, u, sh in zip(model.comp_names, model.comp_units, model.comp_shapes):
+        nd = sh["n_areag"] * sh["n_stockg"] * sh["n_age"] * sh["n_bins"]
+        a = raw[pos:pos + sh["n_times"] * nd]; pos += sh["n_times"] * nd
+        out[f"{n}_model__{u}"] = a.reshape(sh["n_times"], sh["n_areag"], sh["n_stockg"], sh["n_age"],
+                                            sh["n_bins"]).copy()
+    for n in model.comp_names:
+        out[f"{n}_model__params"] = raw[pos:pos + 2].copy(); pos += 2
+    return out
+
+
+def g3_cuda_adfun(model: G3CudaModel, parameters: ParameterTemplate = None, device=0) -> G3CudaADFun:
+    return G3CudaADFun(model, parameters, device)

@@ -1,0 +1,112 @@
+/*
+ * g3cuda.h -- C ABI of the B200 batched objective evaluator for gadget3 models.
+ *
+ * This is the drop-in boundary: what a reference-side binding (R .Call shim,
+ * see INTEGRATION.md) links against in place of the TMB-compiled objective.
+ * Every entry point cites the reference interface it stands in for
+ * (paths relative to the gadget3 source tree).
+ *
+ * Conventions: plain pointers and sizes, no torch/R types. All functions
+ * return 0 on success or a negative G3CUDA_E* code; the message is available
+ * from g3cuda_last_error(). A NaN objective is a VALUE, not an error (it
+ * mirrors assert_msg()/return NaN in R/aab_env.R:98-107, R/action_time.R:78).
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with G3CUDA_ENODEVICE.
+ */
+#ifndef G3CUDA_H
+#define G3CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G3CUDA_OK          0
+#define G3CUDA_EINVAL     -1   /* malformed spec / bad argument */
+#define G3CUDA_ENODEVICE  -2   /* no usable CUDA device */
+#define G3CUDA_ECUDA      -3   /* CUDA runtime error */
+#define G3CUDA_EUNSUPP    -4   /* model outside the supported action subset */
+#define G3CUDA_ENOMEM     -5
+
+/* Packed model specification; layout in g3cuda_spec.h.
+ * Replaces: the generated TMB translation unit + model_data environment
+ * returned by g3_to_tmb() (R/run_tmb.R:1076-1091). */
+typedef struct g3cuda_spec {
+    int32_t        version;   /* G3CUDA_SPEC_VERSION */
+    int64_t        n_ints;
+    const int32_t* ints;
+    int64_t        n_reals;
+    const double*  reals;
+} g3cuda_spec;
+
+typedef struct g3cuda_model g3cuda_model;
+
+/* Build a model handle: validates the spec, copies it to the device
+ * (device = CUDA ordinal), precomputes parameter-independent tables.
+ * The caller keeps ownership of `spec`.
+ * Replaces: g3_tmb_adfun() -> TMB::compile + dyn.load + TMB::MakeADFun
+ * (R/run_tmb.R:1118-1260). */
+int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out);
+
+/* Free a handle. Replaces: the ADFun external pointer finalizer. */
+void g3cuda_model_free(g3cuda_model* m);
+
+/* Model dimensions, for callers sizing buffers. */
+int32_t g3cuda_n_par(const g3cuda_model* m);    /* full PARAMETER vector length */
+int32_t g3cuda_n_nll(const g3cuda_model* m);    /* rows of nll_comp: one per g3l_distribution
+                                                   component (run order), then understocking, then bounds */
+int32_t g3cuda_n_steps(const g3cuda_model* m);  /* allocated model steps (total_steps + 1 at retro_years = 0) */
+int64_t g3cuda_report_len(const g3cuda_model* m); /* doubles written by g3cuda_report() */
+
+/* Evaluate the objective for a batch of B independent parameter vectors.
+ *   par         B x n_par, row-major, HOST memory; full PARAMETER order
+ *               (fixed parameters included), i.e. obj$env$last.par order.
+ *   tangent_idx K parameter indices to differentiate with respect to, or NULL
+ *   nll         out, B
+ *   nll_comp    out, B x n_nll (unweighted per-component sums over time;
+ *               understocking = sum of nll_understocking__wgt; bounds = penalty sum), or NULL
+ *   grad        out, B x K forward-mode d nll / d par[tangent_idx[k]], or NULL
+ * Replaces: obj$fn(par), obj$gr(par) of the TMB ADFun (R/run_tmb.R:1254-1260,
+ * man/run_tmb.Rd:233-242), called once per vector by nlminb/optim. */
+int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B,
+                      const int32_t* tangent_idx, int32_t K,
+                      double* nll, double* nll_comp, double* grad);
+
+/* Same computation with DEVICE pointers, asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = default stream). Used by callers
+ * that keep parameter batches resident in HBM (bench.py `value`). */
+int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B,
+                             const int32_t* d_tangent_idx, int32_t K,
+                             double* d_nll, double* d_nll_comp, double* d_grad,
+                             void* stream);
+
+/* Number of kernels launched by this handle so far (bench.py gpu_launches). */
+int64_t g3cuda_launch_count(const g3cuda_model* m);
+
+/* Milliseconds spent in the last g3cuda_eval_batch[_device] kernel(s),
+ * measured with CUDA events on the launching stream (synchronises). */
+float g3cuda_last_kernel_ms(g3cuda_model* m);
+
+/* Single-vector report run: fills `out` (g3cuda_report_len doubles, HOST) with
+ *   [0]                       nll
+ *   [1 .. 1+n_nll*NT)         per-step unweighted nll values, row-major [n_nll][NT]
+ *                             (nll_<comp>__num/wgt, nll_understocking__wgt; bounds row: step 0 only)
+ *   then per stock, in stock order: dstart num [NT][cells of stock], dstart wgt [NT][cells]
+ *   (state at the start of each step, canonical cell layout, as dstart_<stock>__num/wgt
+ *   of g3a_report_detail, R/action_report.R:177-213)
+ *   then per component: model array [n_times][n_dest] (canonical dest layout)
+ *   then per component: 2 doubles (surveyindices alpha, beta; NaN otherwise)
+ * Replaces: obj$report(par) (R/run_tmb.R:1277-1321). */
+int g3cuda_report(g3cuda_model* m, const double* par, double* out);
+
+/* Last error message of the calling thread. */
+const char* g3cuda_last_error(void);
+
+/* Library/ABI version: G3CUDA_SPEC_VERSION the library was built for. */
+int32_t g3cuda_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G3CUDA_H */
