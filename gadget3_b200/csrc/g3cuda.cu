@@ -1,0 +1,481 @@
+// g3cuda.cu -- C ABI (include/g3cuda.h) over the evaluation kernel: spec validation, derived
+// device tables, shared-memory layout, launches. No CPU evaluation path exists in this library:
+// without a CUDA device every compute entry point returns G3CUDA_ENODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/g3cuda.h"
+#include "g3_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(G3CUDA_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
+
+constexpr int NTAN = 4;                 // tangent directions per gradient pass
+using DualT = g3::Dual<NTAN>;
+
+double h_avoid_zero(double a) {         // R/aab_env.R:24-31 on the host, for parameter-independent terms
+    double p = a * 1000.0;
+    return (std::fmax(p, 0.0) + std::log1p(std::exp(-std::fabs(p)))) / 1000.0;
+}
+
+template <class T> T* dev_copy(const std::vector<T>& v) {
+    T* d = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    if (cudaMalloc(&d, n) != cudaSuccess) return nullptr;
+    if (!v.empty() && cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    return d;
+}
+
+}  // namespace
+
+struct g3cuda_model {
+    int device = 0;
+    std::vector<int32_t> I; std::vector<double> R;
+    g3::KArgs base{};                   // everything except per-call pointers and the smem layout
+    std::vector<void*> owned;           // device allocations
+    int nthreads = 0;
+    int num_sms = 0;
+    int64_t report_len = 0;
+    int64_t launches = 0;
+    // per-call scratch (grow-only)
+    double* d_par = nullptr; double* d_nll = nullptr; double* d_comp = nullptr; double* d_grad = nullptr;
+    int32_t* d_tidx = nullptr; double* d_report = nullptr;
+    size_t cap_par = 0, cap_nll = 0, cap_comp = 0, cap_grad = 0, cap_tidx = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    // smem element counts
+    int sm_elems = 0;
+};
+
+namespace {
+
+struct Layout { g3::KArgs a; size_t bytes; };
+
+// Shared-memory layout for scalar type of `tsize` bytes.
+Layout make_layout(const g3cuda_model* m, size_t tsize) {
+    using namespace g3;
+    Layout out; out.a = m->base;
+    KArgs& A = out.a;
+    const int32_t* I = m->I.data();
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += n; return o; };
+    A.sm_par_bytes = (int)(((size_t)A.NPAR * 8 + 15) / 16 * 16);
+    A.o_slot = take(A.NSLOT);
+    A.o_num = take(A.NC); A.o_wgt = take(A.NC); A.o_tn = take(A.NC); A.o_tw = take(A.NC);
+    A.o_alt = A.any_const_mat ? take(A.NC) : A.o_tn;
+    for (int x = 0; x < MAXX; x++) A.o_xslot[x] = -1;
+    for (int c = 0; c < A.NCOMP; c++) {
+        const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+        if (C[G3C_MODE] == 0 && A.o_xslot[C[G3C_XBUF]] < 0) A.o_xslot[C[G3C_XBUF]] = take(A.NC);
+    }
+    A.o_xg = 0;
+    A.o_pw = off;
+    for (int s = 0; s < A.NS; s++) A.o_pws[s] = take(I[I[G3H_STOCK_OFF] + s * G3S_LEN + G3S_L]);
+    A.o_suit = take(A.NPP * A.maxL);
+    int maxg = 0;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        int n = St[G3S_GROW_N], L = St[G3S_L];
+        if (n < 0) { A.o_g[s] = A.o_gr[s] = A.o_gn[s] = 0; continue; }
+        int g = (n + 1) * L; maxg = std::max(maxg, g);
+        A.o_g[s] = take(g);
+        if (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0) { A.o_gr[s] = take(g); A.o_gn[s] = take(g); }
+        else { A.o_gr[s] = A.o_gn[s] = A.o_g[s]; }
+    }
+    A.o_gscr = take(3 * maxg);
+    int rd0 = off;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        A.o_rd[s] = take(St[G3S_N_RENEW] * St[G3S_L]);
+    }
+    A.o_rwt = take(off - rd0);
+    for (int c = 0; c < A.NCOMP; c++) {
+        const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+        bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+        A.o_ms[c] = take(C[G3C_N_DEST] * (si ? C[G3C_N_TIMES] : 1));
+    }
+    A.o_red = take((NRED + MAXTS + 2) * 32);
+    out.bytes = (size_t)A.sm_par_bytes + (size_t)off * tsize;
+    return out;
+}
+
+template <class T, int MAXT>
+int launch_variant(g3cuda_model* m, const Layout& lay, int nblocks_hint, cudaStream_t st) {
+    auto kern = g3::eval_kernel<T, MAXT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lay.bytes));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, m->nthreads, lay.bytes));
+    if (per_sm < 1) return fail(G3CUDA_EUNSUPP, "model does not fit one SM: %zu bytes of shared memory, %d threads", lay.bytes, m->nthreads);
+    long long grid = std::min<long long>(nblocks_hint, (long long)per_sm * m->num_sms);
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, m->nthreads, lay.bytes, st>>>(lay.a);
+    CUDA_TRY(cudaGetLastError());
+    m->launches++;
+    return G3CUDA_OK;
+}
+
+template <class T>
+int launch(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStream_t st) {
+    Layout lay = make_layout(m, sizeof(T));
+    // per-call fields
+    lay.a.par = call.par; lay.a.B = call.B; lay.a.tangent_idx = call.tangent_idx; lay.a.K = call.K;
+    lay.a.nll = call.nll; lay.a.comp = call.comp; lay.a.grad = call.grad; lay.a.report = call.report;
+    int hint = (int)std::min<long long>(work, 1 << 30);
+    int n = m->nthreads;
+    if (n <= 128) return launch_variant<T, 128>(m, lay, hint, st);
+    if (n <= 320) return launch_variant<T, 320>(m, lay, hint, st);
+    if (n <= 704) return launch_variant<T, 704>(m, lay, hint, st);
+    return launch_variant<T, 1024>(m, lay, hint, st);
+}
+
+template <class T> int ensure(T** p, size_t* cap, size_t n) {
+    if (n <= *cap) return G3CUDA_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    if (cudaMalloc(p, n * sizeof(T)) != cudaSuccess) return fail(G3CUDA_ENOMEM, "cudaMalloc of %zu bytes failed", n * sizeof(T));
+    *cap = n;
+    return G3CUDA_OK;
+}
+
+int check_spec(const g3cuda_spec* spec) {
+    if (!spec || !spec->ints || !spec->reals) return fail(G3CUDA_EINVAL, "null spec");
+    if (spec->version != G3CUDA_SPEC_VERSION || spec->n_ints < G3H_LEN || spec->ints[G3H_VERSION] != G3CUDA_SPEC_VERSION)
+        return fail(G3CUDA_EINVAL, "spec version mismatch (library built for %d)", G3CUDA_SPEC_VERSION);
+    const int32_t* I = spec->ints;
+    auto in_i = [&](int64_t off, int64_t n) { return off >= 0 && off + n <= spec->n_ints; };
+    if (!in_i(I[G3H_STOCK_OFF], (int64_t)I[G3H_NSTOCK] * G3S_LEN) || !in_i(I[G3H_COMP_OFF], (int64_t)I[G3H_NCOMP] * G3C_LEN) ||
+        !in_i(I[G3H_PP_OFF], (int64_t)I[G3H_NPP] * G3PP_LEN) || !in_i(I[G3H_PRED_OFF], (int64_t)I[G3H_NPRED] * G3P_LEN) ||
+        !in_i(I[G3H_SLOT_OFF], 2LL * I[G3H_NSLOT]) || !in_i(I[G3H_XBUF_OFF], (int64_t)I[G3H_NXBUF] * G3X_LEN))
+        return fail(G3CUDA_EINVAL, "spec section offsets out of range");
+    if (I[G3H_NSTOCK] < 1 || I[G3H_NSTOCK] > g3::MAXS) return fail(G3CUDA_EUNSUPP, "number of stocks %d outside 1..%d", I[G3H_NSTOCK], g3::MAXS);
+    if (I[G3H_NCOMP] > g3::MAXC) return fail(G3CUDA_EUNSUPP, "more than %d likelihood components", g3::MAXC);
+    if (I[G3H_NXBUF] > g3::MAXX) return fail(G3CUDA_EUNSUPP, "more than %d collect vectors", g3::MAXX);
+    if (I[G3H_NCELL] > 1024) return fail(G3CUDA_EUNSUPP, "%d stock cells: more than 1024 are not supported yet", I[G3H_NCELL]);
+    if (I[G3H_NSTEPS] > 31) return fail(G3CUDA_EUNSUPP, "more than 31 steps per year");
+    return G3CUDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* g3cuda_last_error(void) { return g_err.c_str(); }
+int32_t g3cuda_abi_version(void) { return G3CUDA_SPEC_VERSION; }
+int32_t g3cuda_n_par(const g3cuda_model* m) { return m ? m->base.NPAR : 0; }
+int32_t g3cuda_n_nll(const g3cuda_model* m) { return m ? m->base.NNLL : 0; }
+int32_t g3cuda_n_steps(const g3cuda_model* m) { return m ? m->base.NT : 0; }
+int64_t g3cuda_report_len(const g3cuda_model* m) { return m ? m->report_len : 0; }
+int64_t g3cuda_launch_count(const g3cuda_model* m) { return m ? m->launches : 0; }
+
+void g3cuda_model_free(g3cuda_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (void* p : m->owned) cudaFree(p);
+    for (void* p : {(void*)m->d_par, (void*)m->d_nll, (void*)m->d_comp, (void*)m->d_grad, (void*)m->d_tidx, (void*)m->d_report})
+        if (p) cudaFree(p);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out) {
+    using namespace g3;
+    if (!out) return fail(G3CUDA_EINVAL, "null out pointer");
+    *out = nullptr;
+    int rc = check_spec(spec);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(G3CUDA_ENODEVICE, "no usable CUDA device (requested %d, found %d); this library has no CPU fallback", device, ndev);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    g3cuda_model* m = new g3cuda_model();
+    m->device = device;
+    m->I.assign(spec->ints, spec->ints + spec->n_ints);
+    m->R.assign(spec->reals, spec->reals + spec->n_reals);
+    const int32_t* I = m->I.data();
+    const double* R = m->R.data();
+    KArgs& A = m->base;
+    A.NC = I[G3H_NCELL]; A.NS = I[G3H_NSTOCK]; A.NPP = I[G3H_NPP]; A.NCOMP = I[G3H_NCOMP]; A.NX = I[G3H_NXBUF];
+    A.NSLOT = I[G3H_NSLOT]; A.NPAR = I[G3H_NPAR]; A.NT = I[G3H_NT]; A.NSTEPS = I[G3H_NSTEPS]; A.NNLL = I[G3H_NNLL];
+    A.NBOUND = I[G3H_NBOUND]; A.maxL = I[G3H_MAXL];
+    auto stock = [&](int s) { return I + I[G3H_STOCK_OFF] + s * G3S_LEN; };
+    auto bail = [&](int code) { g3cuda_model_free(m); return code; };
+
+    // ---- per-cell tables
+    int maxnarea = 1;
+    std::vector<int4> cell(A.NC);
+    std::vector<int32_t> inc_src(A.NC, -1), inc_slot(A.NC, -1), inc_mask(A.NC, 0), age_src(A.NC, -1), age_slot(A.NC, -1);
+    std::vector<int32_t> rem_off(A.NC, 0), rem_slots;
+    A.any_const_mat = 0;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = stock(s);
+        int L = St[G3S_L], nage = St[G3S_NAGE], narea = St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+        maxnarea = std::max(maxnarea, narea);
+        if (St[G3S_N_RENEW] > MAXRN) return bail(fail(G3CUDA_EUNSUPP, "more than %d renewal actions on one stock", MAXRN));
+        if (St[G3S_MIGRATE_OFF] >= 0) return bail(fail(G3CUDA_EUNSUPP, "g3a_migrate is not supported yet"));
+        if (St[G3S_GROW_N] >= 0 && St[G3S_MAT_KIND] == G3MAT_CONSTANT && St[G3S_N_OUT] > 0) A.any_const_mat = 1;
+        if (St[G3S_GROW_N] >= 0 && St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0 && I[St[G3S_MAT_OFF] + 2] >= 0)
+            return bail(fail(G3CUDA_EUNSUPP, "g3a_mature_continuous with a beta/a50 (age) term is not supported yet"));
+        for (int r = 0; r < narea; r++) for (int a = 0; a < nage; a++) for (int l = 0; l < L; l++)
+            cell[c0 + (r * nage + a) * L + l] = make_int4(s, l, r * nage + a, r);
+        int ncell = L * nage * narea;
+        // maturation: destination cells learn their source; sources learn which ratios have a destination
+        bool trans = St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0;
+        for (int i = 0; i < ncell; i++) {
+            rem_off[c0 + i] = (int)rem_slots.size();
+            if (trans) for (int o = 0; o < St[G3S_N_OUT]; o++) {
+                int d = I[St[G3S_OUT_MAP_OFF] + o * ncell + i];
+                if (d < 0) continue;
+                int slot = I[St[G3S_OUT_OFF] + 2 * o + 1];
+                if (inc_src[d] >= 0) return bail(fail(G3CUDA_EUNSUPP, "a cell receives maturing fish from more than one source"));
+                inc_src[d] = c0 + i; inc_slot[d] = slot; inc_mask[d] = St[G3S_TRANS_MASK];
+                rem_slots.push_back(slot);
+            }
+            rem_slots.push_back(-1);
+        }
+        if (St[G3S_AGE_ENABLE]) for (int o = 0; o < St[G3S_AGE_N_OUT]; o++) for (int r = 0; r < narea; r++) for (int l = 0; l < L; l++) {
+            int d = I[St[G3S_AGE_MAP_OFF] + (o * narea + r) * L + l];
+            if (d < 0) continue;
+            if (age_src[d] >= 0) return bail(fail(G3CUDA_EUNSUPP, "a cell receives ageing fish from more than one source"));
+            age_src[d] = c0 + (r * nage + nage - 1) * L + l;
+            age_slot[d] = I[St[G3S_AGE_OUT_OFF] + 2 * o + 1];
+        }
+    }
+    A.maxnarea = maxnarea;
+    for (int st = 0; st < 32; st++) {
+        A.trans_any[st] = 0;
+        for (int s = 0; s < A.NS; s++) {
+            const int32_t* St = stock(s);
+            if (St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0 && ((St[G3S_TRANS_MASK] >> st) & 1)) A.trans_any[st] = 1;
+        }
+    }
+    // ---- predation tables
+    std::vector<int32_t> tsid((size_t)std::max(A.NPP, 1) * maxnarea, -1), eoff(tsid.size(), 0), estr(tsid.size(), 0);
+    std::vector<int> ts_of_pred_area;   // accumulator id per (pred, pred area idx)
+    int nts = 0;
+    std::vector<int> pred_ts_base(I[G3H_NPRED], 0);
+    for (int p = 0; p < I[G3H_NPRED]; p++) {
+        const int32_t* P = I + I[G3H_PRED_OFF] + p * G3P_LEN;
+        if (P[G3P_KIND] != G3PRED_TOTALFLEET) return bail(fail(G3CUDA_EUNSUPP, "predator kind %d is not supported yet", P[G3P_KIND]));
+        pred_ts_base[p] = nts; nts += P[G3P_NAREA];
+    }
+    if (nts > MAXTS) return bail(fail(G3CUDA_EUNSUPP, "more than %d (predator, area) pairs", MAXTS));
+    A.NTS = nts;
+    std::vector<std::vector<int>> pp_of_stock(A.NS);
+    for (int q = 0; q < A.NPP; q++) {
+        const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+        const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
+        const int32_t* St = stock(Q[G3PP_PREY]);
+        if (Q[G3PP_SUIT_KIND] != G3SUIT_EXPL50 && Q[G3PP_SUIT_KIND] != G3SUIT_CONSTANT)
+            return bail(fail(G3CUDA_EUNSUPP, "suitability kind %d is not supported yet", Q[G3PP_SUIT_KIND]));
+        pp_of_stock[Q[G3PP_PREY]].push_back(q);
+        for (int r = 0; r < St[G3S_NAREA]; r++) {
+            int area = I[St[G3S_AREA_OFF] + r];
+            for (int k = 0; k < P[G3P_NAREA]; k++) if (I[P[G3P_AREA_OFF] + k] == area) {
+                tsid[(size_t)q * maxnarea + r] = pred_ts_base[Q[G3PP_PRED]] + k;
+                eoff[(size_t)q * maxnarea + r] = P[G3P_E_ROFF] + k;
+                estr[(size_t)q * maxnarea + r] = P[G3P_NAREA];
+            }
+        }
+    }
+    int ppo = 0;
+    for (int s = 0; s < A.NS; s++) {
+        A.stock_pp_off[s] = ppo;
+        if ((int)pp_of_stock[s].size() > MAXQ) return bail(fail(G3CUDA_EUNSUPP, "more than %d predators on one stock", MAXQ));
+        for (int q : pp_of_stock[s]) A.stock_pp[ppo++] = q;
+        A.us_flag[s] = 0;
+    }
+    A.stock_pp_off[A.NS] = ppo;
+    for (int i = 0; i < I[G3H_US_N]; i++) A.us_flag[I[I[G3H_US_OFF] + i]] = 1;
+
+    // ---- observation terms that do not depend on parameters
+    std::vector<double> obsprop, obsconst;
+    int maxnd = 0, maxnt = 0;
+    for (int c = 0; c < A.NCOMP; c++) {
+        const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+        int nd = C[G3C_N_DEST], nt = C[G3C_N_TIMES], nb = C[G3C_N_BINS], nsl = C[G3C_N_SLICES], nag = C[G3C_N_AREAG];
+        maxnd = std::max(maxnd, nd);
+        A.obs_off[c] = (int)obsprop.size(); A.obsconst_off[c] = (int)obsconst.size();
+        const double* obs = R + C[G3C_OBS_ROFF];
+        bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+        if (si) maxnt = std::max(maxnt, nt);
+        if (C[G3C_MODE] == 1 && nd > 32) return bail(fail(G3CUDA_EUNSUPP, "reduce-mode component with %d destinations", nd));
+        for (int t = 0; t < nt; t++) {
+            double cst = 0.0;
+            for (int ag = 0; ag < nag; ag++) {
+                double tot = 0.0;
+                for (int i = 0; i < nsl * nb; i++) tot += obs[(size_t)t * nd + ag * nsl * nb + i];
+                double az = h_avoid_zero(tot);
+                for (int i = 0; i < nsl * nb; i++) {
+                    double o = obs[(size_t)t * nd + ag * nsl * nb + i];
+                    double v = o;
+                    if (C[G3C_FUNC] == G3F_SUMOFSQUARES) v = o / az;                // R/likelihood_distribution.R:12-27
+                    else if (C[G3C_FUNC] == G3F_SI_LOG) v = std::log(h_avoid_zero(o));  // R/likelihood_distribution.R:86
+                    obsprop.push_back(v);
+                }
+                if (C[G3C_FUNC] == G3F_MULTINOMIAL)
+                    for (int sl = 0; sl < nsl; sl++) {      // sum(lgamma(1 + data)) - lgamma(1 + sum(data))
+                        double so = 0, slg = 0;
+                        for (int b = 0; b < nb; b++) { double o = obs[(size_t)t * nd + (ag * nsl + sl) * nb + b]; so += o; slg += std::lgamma(1 + o); }
+                        cst += slg - std::lgamma(1 + so);
+                    }
+            }
+            obsconst.push_back(cst);
+        }
+    }
+    // ---- report layout (include/g3cuda.h)
+    int64_t pos = 1 + (int64_t)A.NNLL * A.NT;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = stock(s);
+        A.rep_dstart[s] = pos;
+        pos += 2LL * A.NT * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+    }
+    for (int c = 0; c < A.NCOMP; c++) {
+        const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+        A.rep_model[c] = pos; pos += (int64_t)C[G3C_N_TIMES] * C[G3C_N_DEST];
+    }
+    A.rep_params = pos; pos += 2LL * A.NCOMP;
+    m->report_len = pos;
+
+    int need = std::max({A.NC, maxnd, maxnt, A.maxL, 32});
+    m->nthreads = (need + 31) / 32 * 32;
+    if (m->nthreads > 1024) return bail(fail(G3CUDA_EUNSUPP, "model needs %d threads per evaluation (> 1024)", m->nthreads));
+
+    // ---- upload
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    m->num_sms = prop.multiProcessorCount;
+    auto up = [&](auto& vec) { auto* d = dev_copy(vec); if (d) m->owned.push_back((void*)d); return d; };
+    A.I = up(m->I); A.R = up(m->R); A.cell = up(cell);
+    A.inc_src = up(inc_src); A.inc_slot = up(inc_slot); A.inc_mask = up(inc_mask);
+    A.age_src = up(age_src); A.age_slot = up(age_slot); A.rem_off = up(rem_off); A.rem_slots = up(rem_slots);
+    A.pp_tsid = up(tsid); A.pp_eoff = up(eoff); A.pp_estride = up(estr);
+    A.obsprop = up(obsprop); A.obsconst = up(obsconst);
+    if (!A.I || !A.R || !A.cell || !A.inc_src || !A.inc_slot || !A.inc_mask || !A.age_src || !A.age_slot || !A.rem_off ||
+        !A.rem_slots || !A.pp_tsid || !A.pp_eoff || !A.pp_estride || !A.obsprop || !A.obsconst)
+        return bail(fail(G3CUDA_ENOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
+        return bail(fail(G3CUDA_ECUDA, "stream/event creation failed"));
+    Layout lay = make_layout(m, sizeof(DualT));
+    if (lay.bytes > (size_t)prop.sharedMemPerBlockOptin)
+        return bail(fail(G3CUDA_EUNSUPP, "model needs %zu bytes of shared memory per evaluation (limit %zu)", lay.bytes, (size_t)prop.sharedMemPerBlockOptin));
+    *out = m;
+    return G3CUDA_OK;
+}
+
+int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B, const int32_t* d_tangent_idx, int32_t K,
+                             double* d_nll, double* d_comp, double* d_grad, void* stream) {
+    if (!m || !d_par || !d_nll || B < 0) return fail(G3CUDA_EINVAL, "bad argument");
+    if (B == 0) return G3CUDA_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    g3::KArgs call{};
+    call.par = d_par; call.B = B; call.nll = d_nll; call.comp = d_comp; call.report = nullptr;
+    m->timed = true;
+    CUDA_TRY(cudaEventRecord(m->ev0, st));
+    int rc;
+    if (d_grad && K > 0) {
+        if (!d_tangent_idx) return fail(G3CUDA_EINVAL, "grad requested without tangent_idx");
+        // value + per-component sums from the double kernel, gradients from the dual kernel
+        call.tangent_idx = nullptr; call.K = 0; call.grad = nullptr;
+        rc = launch<double>(m, call, B, st);
+        if (rc) return rc;
+        g3::KArgs g = call;
+        g.tangent_idx = d_tangent_idx; g.K = K; g.grad = d_grad; g.comp = nullptr;
+        // the dual kernel also writes nll (tile 0); keep the double kernel's value: write duals' nll into scratch
+        rc = ensure(&m->d_nll, &m->cap_nll, (size_t)B);
+        if (rc) return rc;
+        g.nll = m->d_nll;
+        long long ntiles = (K + NTAN - 1) / NTAN;
+        rc = launch<DualT>(m, g, B * ntiles, st);
+    } else {
+        call.tangent_idx = nullptr; call.K = 0; call.grad = nullptr;
+        rc = launch<double>(m, call, B, st);
+    }
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(m->ev1, st));
+    return G3CUDA_OK;
+}
+
+int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B, const int32_t* tangent_idx, int32_t K,
+                      double* nll, double* nll_comp, double* grad) {
+    if (!m || !par || !nll || B < 0) return fail(G3CUDA_EINVAL, "bad argument");
+    if (B == 0) return G3CUDA_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    const int P = m->base.NPAR, NN = m->base.NNLL;
+    int rc;
+    double* d_out_nll = nullptr; size_t cap_out = 0;
+    if ((rc = ensure(&m->d_par, &m->cap_par, (size_t)B * P))) return rc;
+    if ((rc = ensure(&d_out_nll, &cap_out, (size_t)B))) return rc;
+    if (nll_comp && (rc = ensure(&m->d_comp, &m->cap_comp, (size_t)B * NN))) { cudaFree(d_out_nll); return rc; }
+    bool want_grad = grad && K > 0;
+    if (want_grad) {
+        if (!tangent_idx) { cudaFree(d_out_nll); return fail(G3CUDA_EINVAL, "grad requested without tangent_idx"); }
+        if ((rc = ensure(&m->d_grad, &m->cap_grad, (size_t)B * K)) || (rc = ensure(&m->d_tidx, &m->cap_tidx, (size_t)K))) { cudaFree(d_out_nll); return rc; }
+        cudaMemcpyAsync(m->d_tidx, tangent_idx, sizeof(int32_t) * K, cudaMemcpyHostToDevice, m->stream);
+    }
+    cudaMemcpyAsync(m->d_par, par, sizeof(double) * B * P, cudaMemcpyHostToDevice, m->stream);
+    rc = g3cuda_eval_batch_device(m, m->d_par, B, want_grad ? m->d_tidx : nullptr, want_grad ? K : 0, d_out_nll,
+                                  nll_comp ? m->d_comp : nullptr, want_grad ? m->d_grad : nullptr, m->stream);
+    if (rc) { cudaFree(d_out_nll); return rc; }
+    cudaMemcpyAsync(nll, d_out_nll, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream);
+    if (nll_comp) cudaMemcpyAsync(nll_comp, m->d_comp, sizeof(double) * B * NN, cudaMemcpyDeviceToHost, m->stream);
+    if (want_grad) cudaMemcpyAsync(grad, m->d_grad, sizeof(double) * B * K, cudaMemcpyDeviceToHost, m->stream);
+    cudaError_t e = cudaStreamSynchronize(m->stream);
+    cudaFree(d_out_nll);
+    if (e != cudaSuccess) return fail(G3CUDA_ECUDA, "evaluation failed: %s", cudaGetErrorString(e));
+    return G3CUDA_OK;
+}
+
+float g3cuda_last_kernel_ms(g3cuda_model* m) {
+    if (!m || !m->timed) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(m->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, m->ev0, m->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+int g3cuda_report(g3cuda_model* m, const double* par, double* out) {
+    if (!m || !par || !out) return fail(G3CUDA_EINVAL, "bad argument");
+    CUDA_TRY(cudaSetDevice(m->device));
+    int rc;
+    size_t cap = 0; double* d_rep = nullptr; double* d_nll = nullptr; size_t cap2 = 0;
+    if ((rc = ensure(&m->d_par, &m->cap_par, (size_t)m->base.NPAR))) return rc;
+    if ((rc = ensure(&d_rep, &cap, (size_t)m->report_len))) return rc;
+    if ((rc = ensure(&d_nll, &cap2, 1))) { cudaFree(d_rep); return rc; }
+    cudaMemsetAsync(d_rep, 0, sizeof(double) * m->report_len, m->stream);
+    cudaMemcpyAsync(m->d_par, par, sizeof(double) * m->base.NPAR, cudaMemcpyHostToDevice, m->stream);
+    g3::KArgs call{};
+    call.par = m->d_par; call.B = 1; call.nll = d_nll; call.report = d_rep;
+    rc = launch<double>(m, call, 1, m->stream);
+    if (!rc) {
+        cudaMemcpyAsync(out, d_rep, sizeof(double) * m->report_len, cudaMemcpyDeviceToHost, m->stream);
+        cudaError_t e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) rc = fail(G3CUDA_ECUDA, "report failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_rep); cudaFree(d_nll);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,814 @@
+/*
+ * g3oracle.cpp -- CPU restatement of gadget3's generated objective function.
+ *
+ * TEST INFRASTRUCTURE ONLY. Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / reported baseline.
+ *
+ * What it restates: the body of `objective_function<Type>::operator()` that
+ * g3_to_tmb() generates (reference: baseline/multiple-substocks.cpp:692-2161,
+ * baseline/introduction-single-stock.cpp:542-1389, inttest/codegeneration/ling.cpp),
+ * statement by statement and in the same order, driven by the packed spec of
+ * include/g3cuda_spec.h instead of being hard-coded per model. It deliberately keeps
+ * the reference's formulation (dense L x L growth matrices, nine-lgamma beta-binomial,
+ * every avoid_zero evaluated in full with libm exp/log1p, per-age recomputation) so
+ * that it is an independent check of the restructured CUDA path.
+ *
+ * Parity pin: see oracle/README.md -- known-answer vectors from the reference's unit
+ * tests (tests/test-action_grow.R etc.) and, where buildable, the reference's own
+ * generated C++ compiled against oracle/tmb_shim (oracle/_ref).
+ *
+ * Scalar type T is double or Dual<K> (forward-mode tangents) so the same
+ * restatement is the gradient oracle.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+#include "../include/g3cuda_spec.h"
+
+namespace {
+
+// ------------------------------------------------------------------ dual numbers
+template <int K>
+struct Dual {
+    double v;
+    double d[K];
+    Dual() : v(0) { for (int i = 0; i < K; i++) d[i] = 0; }
+    Dual(double x) : v(x) { for (int i = 0; i < K; i++) d[i] = 0; }
+};
+template <int K> Dual<K> operator+(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v + b.v; for (int i = 0; i < K; i++) r.d[i] = a.d[i] + b.d[i]; return r; }
+template <int K> Dual<K> operator-(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v - b.v; for (int i = 0; i < K; i++) r.d[i] = a.d[i] - b.d[i]; return r; }
+template <int K> Dual<K> operator-(const Dual<K>& a) { Dual<K> r; r.v = -a.v; for (int i = 0; i < K; i++) r.d[i] = -a.d[i]; return r; }
+template <int K> Dual<K> operator*(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v * b.v; for (int i = 0; i < K; i++) r.d[i] = a.d[i] * b.v + a.v * b.d[i]; return r; }
+template <int K> Dual<K> operator/(const Dual<K>& a, const Dual<K>& b) { Dual<K> r; r.v = a.v / b.v; for (int i = 0; i < K; i++) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v; return r; }
+template <int K> Dual<K> operator+(const Dual<K>& a, double b) { return a + Dual<K>(b); }
+template <int K> Dual<K> operator+(double a, const Dual<K>& b) { return Dual<K>(a) + b; }
+template <int K> Dual<K> operator-(const Dual<K>& a, double b) { return a - Dual<K>(b); }
+template <int K> Dual<K> operator-(double a, const Dual<K>& b) { return Dual<K>(a) - b; }
+template <int K> Dual<K> operator*(const Dual<K>& a, double b) { Dual<K> r; r.v = a.v * b; for (int i = 0; i < K; i++) r.d[i] = a.d[i] * b; return r; }
+template <int K> Dual<K> operator*(double a, const Dual<K>& b) { return b * a; }
+template <int K> Dual<K> operator/(const Dual<K>& a, double b) { return a / Dual<K>(b); }
+template <int K> Dual<K> operator/(double a, const Dual<K>& b) { return Dual<K>(a) / b; }
+template <int K> Dual<K>& operator+=(Dual<K>& a, const Dual<K>& b) { a = a + b; return a; }
+template <int K> Dual<K>& operator-=(Dual<K>& a, const Dual<K>& b) { a = a - b; return a; }
+template <int K> Dual<K>& operator*=(Dual<K>& a, const Dual<K>& b) { a = a * b; return a; }
+
+inline double val(double x) { return x; }
+template <int K> double val(const Dual<K>& x) { return x.v; }
+
+template <int K, class F> Dual<K> chain(const Dual<K>& a, double f, F dfda) {
+    Dual<K> r; r.v = f; double g = dfda; for (int i = 0; i < K; i++) r.d[i] = g * a.d[i]; return r;
+}
+inline double xexp(double a) { return std::exp(a); }
+inline double xlog(double a) { return std::log(a); }
+inline double xlog1p(double a) { return std::log1p(a); }
+inline double xsqrt(double a) { return std::sqrt(a); }
+inline double xpow(double a, double b) { return std::pow(a, b); }
+inline double xlgamma(double a) { return std::lgamma(a); }
+template <int K> Dual<K> xexp(const Dual<K>& a) { double f = std::exp(a.v); return chain(a, f, f); }
+template <int K> Dual<K> xlog(const Dual<K>& a) { return chain(a, std::log(a.v), 1.0 / a.v); }
+template <int K> Dual<K> xlog1p(const Dual<K>& a) { return chain(a, std::log1p(a.v), 1.0 / (1.0 + a.v)); }
+template <int K> Dual<K> xsqrt(const Dual<K>& a) { double f = std::sqrt(a.v); return chain(a, f, 0.5 / f); }
+template <int K> Dual<K> xpow(const Dual<K>& a, const Dual<K>& b) {
+    double f = std::pow(a.v, b.v);
+    Dual<K> r; r.v = f;
+    double da = (b.v == 0.0) ? 0.0 : b.v * std::pow(a.v, b.v - 1.0);
+    bool bconst = true; for (int i = 0; i < K; i++) if (b.d[i] != 0.0) bconst = false;
+    double db = bconst ? 0.0 : f * std::log(a.v);
+    for (int i = 0; i < K; i++) r.d[i] = da * a.d[i] + (bconst ? 0.0 : db * b.d[i]);
+    return r;
+}
+template <int K> Dual<K> xpow(double a, const Dual<K>& b) { return xpow(Dual<K>(a), b); }
+template <int K> Dual<K> xpow(const Dual<K>& a, double b) { return xpow(a, Dual<K>(b)); }
+// digamma for the lgamma tangent (asymptotic series after upward recurrence)
+inline double digamma(double x) {
+    double r = 0;
+    if (x <= 0 && std::floor(x) == x) return std::numeric_limits<double>::quiet_NaN();
+    if (x < 0) return digamma(1 - x) - M_PI / std::tan(M_PI * x);
+    while (x < 10) { r -= 1 / x; x += 1; }
+    double f = 1 / (x * x);
+    return r + std::log(x) - 0.5 / x -
+           f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132 - f * (691.0 / 32760 - f / 12))))));
+}
+template <int K> Dual<K> xlgamma(const Dual<K>& a) { return chain(a, std::lgamma(a.v), digamma(a.v)); }
+
+// ------------------------------------------------------------------ g3_env primitives
+// logspace_add: R/aab_env.R:16-19 (TMB's logspace_add, Rmath form)
+template <class T> T logspace_add(const T& a, const T& b) {
+    if (val(a) < val(b)) return b + xlog1p(xexp(a - b));
+    return a + xlog1p(xexp(b - a));
+}
+// dif_pmax: R/env_dif.R:1-35 ; scale < 0 gives the smooth minimum (dif_pmin, R/env_dif.R:37-47)
+template <class T> T dif_pmax(const T& a, double b, double scale) {
+    return logspace_add(a * scale, T(b * scale)) / scale;
+}
+template <class T> T dif_pmin(const T& a, double b, double scale) { return dif_pmax(a, b, -scale); }
+// avoid_zero: R/aab_env.R:24-31
+template <class T> T avoid_zero(const T& a) { return dif_pmax(a, 0.0, 1e3); }
+// dif_pminmax: R/env_dif.R:49-67
+template <class T> T dif_pminmax(const T& a, double lower, double upper, double scale) {
+    T out = dif_pmax(a, upper, -scale);
+    return dif_pmax(out, lower, scale);
+}
+// TMB dnorm (density form used by R/action_renewal.R:66)
+template <class T> T dnorm(double x, const T& mean, const T& sd) {
+    T resid = (T(x) - mean) / sd;
+    T logans = T(-std::log(std::sqrt(2 * M_PI))) - xlog(sd) - 0.5 * resid * resid;
+    return xexp(logans);
+}
+// ratio_add_pop: R/aab_env.R:133-153
+template <class T> T ratio_add_pop(const T& ov, const T& oa, const T& nv, const T& na) {
+    return (ov * oa + nv * na) / avoid_zero(oa + na);
+}
+
+// ------------------------------------------------------------------ spec view
+struct Spec {
+    const int32_t* I; const double* R;
+    int h(int k) const { return I[k]; }
+    const int32_t* stock(int s) const { return I + I[G3H_STOCK_OFF] + s * G3S_LEN; }
+    const int32_t* pred(int p) const { return I + I[G3H_PRED_OFF] + p * G3P_LEN; }
+    const int32_t* pp(int p) const { return I + I[G3H_PP_OFF] + p * G3PP_LEN; }
+    const int32_t* comp(int c) const { return I + I[G3H_COMP_OFF] + c * G3C_LEN; }
+    const int32_t* xbuf(int x) const { return I + I[G3H_XBUF_OFF] + x * G3X_LEN; }
+};
+
+template <class T> struct ParVec {
+    const double* p; const int32_t* tidx; int K;   // tangent seeds for Dual
+};
+inline double mkpar(const ParVec<double>& pv, int i) { return pv.p[i]; }
+template <int K> Dual<K> mkpar(const ParVec<Dual<K>>& pv, int i) {
+    Dual<K> r(pv.p[i]);
+    for (int k = 0; k < pv.K && k < K; k++) if (pv.tidx[k] == i) r.d[k] = 1.0;
+    return r;
+}
+
+// slot programs (include/g3cuda_spec.h G3OP_*)
+template <class T> T eval_slot(const Spec& S, const ParVec<T>& pv, int slot) {
+    const int32_t* tab = S.I + S.h(G3H_SLOT_OFF) + 2 * slot;
+    const int32_t* c = S.I + tab[0];
+    int n = tab[1];
+    T st[G3_SLOT_STACK]; int sp = 0;
+    for (int i = 0; i < n; i++) {
+        switch (c[i]) {
+        case G3OP_CONST: st[sp++] = T(S.R[c[++i]]); break;
+        case G3OP_PARAM: st[sp++] = mkpar(pv, c[++i]); break;
+        case G3OP_NAN:   st[sp++] = T(std::numeric_limits<double>::quiet_NaN()); break;
+        case G3OP_ADD: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+        case G3OP_SUB: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
+        case G3OP_MUL: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+        case G3OP_DIV: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
+        case G3OP_POW: sp--; st[sp - 1] = xpow(st[sp - 1], st[sp]); break;
+        case G3OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+        case G3OP_EXP: st[sp - 1] = xexp(st[sp - 1]); break;
+        case G3OP_LOG: st[sp - 1] = xlog(st[sp - 1]); break;
+        case G3OP_SQRT: st[sp - 1] = xsqrt(st[sp - 1]); break;
+        case G3OP_AVOID_ZERO: st[sp - 1] = avoid_zero(st[sp - 1]); break;
+        }
+    }
+    return st[0];
+}
+
+// ------------------------------------------------------------------ growth natives
+// growth_bbinom: R/action_grow.R:155-213. out[l + L*x], column-major L x (n+1)
+template <class T> void growth_bbinom(const std::vector<T>& delt_l, int binn, const T& beta, std::vector<T>& out) {
+    int na = (int)delt_l.size(), n = binn;
+    out.assign((size_t)na * (n + 1), T(0.0));
+    for (int i = 0; i < na * (n + 1); i++) {
+        T alpha = (beta * delt_l[i % na]) / (double(binn) - delt_l[i % na]);
+        double x = double(i / na);
+        out[i] = xexp(T(std::lgamma(double(n) + 1)) + xlgamma(alpha + beta) + xlgamma(T(n - x) + beta) + xlgamma(T(x) + alpha) -
+                      T(std::lgamma(n - x + 1)) - T(std::lgamma(x + 1)) - xlgamma(T(double(n)) + alpha + beta) - xlgamma(beta) - xlgamma(alpha));
+    }
+}
+// g3a_grow_matrix_len: R/action_grow.R:233-271. delta L x D (col-major) -> dense L x L (row lg, col dest)
+template <class T> void grow_matrix_len(const std::vector<T>& delta, int L, int D, std::vector<T>& M) {
+    M.assign((size_t)L * L, T(0.0));
+    for (int lg = 0; lg < L; lg++) {
+        if (lg == L - 1) {
+            T s(0.0); for (int x = 0; x < D; x++) s = s + delta[lg + L * x];
+            M[lg + L * lg] = s;
+        } else if (lg + D > L) {
+            for (int x = 0; x < L - lg; x++) M[lg + L * (lg + x)] = delta[lg + L * x];
+            T s(0.0); for (int x = L - lg - 1; x < D; x++) s = s + delta[lg + L * x];   // tail(total_deltas - (L - lg) + 1)
+            M[lg + L * (L - 1)] = s;
+        } else {
+            for (int x = 0; x < D; x++) M[lg + L * (lg + x)] = delta[lg + L * x];
+        }
+    }
+}
+// g3a_grow_matrix_wgt: R/action_grow.R:273-307
+template <class T> void grow_matrix_wgt(const std::vector<T>& delta, int L, int D, std::vector<T>& M) {
+    M.assign((size_t)L * L, T(0.0));
+    for (int lg = 0; lg < L; lg++) {
+        int w = (lg == L - 1 || lg + D > L) ? L - lg : D;
+        for (int x = 0; x < w; x++) M[lg + L * (lg + x)] = delta[lg + L * x];
+    }
+}
+// g3a_grow_apply: R/action_grow.R:309-335
+template <class T> void grow_apply(const std::vector<T>& G, const std::vector<T>& W, int L, const T* num, const T* wgt,
+                                   std::vector<T>& out_num, std::vector<T>& out_wgt) {
+    std::vector<T> g((size_t)L * L), w((size_t)L * L);
+    for (int j = 0; j < L; j++) for (int l = 0; l < L; l++) {
+        g[l + L * j] = G[l + L * j] * num[l];
+        w[l + L * j] = (W[l + L * j] + wgt[l]) * g[l + L * j];
+    }
+    out_num.assign(L, T(0.0)); out_wgt.assign(L, T(0.0));
+    for (int j = 0; j < L; j++) {
+        T sn(0.0), sw(0.0);
+        for (int l = 0; l < L; l++) { sn = sn + g[l + L * j]; sw = sw + w[l + L * j]; }
+        out_num[j] = sn;
+        out_wgt[j] = sw / avoid_zero(sn);
+    }
+}
+
+// ------------------------------------------------------------------ the model run
+struct ReportSink {
+    double* nll;          // 1
+    double* steps;        // [n_nll][NT]
+    std::vector<double*> dstart_num, dstart_wgt;   // per stock [NT][cells]
+    std::vector<double*> model;                    // per comp [n_times][n_dest]
+    std::vector<double*> params;                   // per comp [2]
+};
+
+template <class T>
+T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null*/, ReportSink* rep) {
+    const double NaN = std::numeric_limits<double>::quiet_NaN();
+    const int NS = S.h(G3H_NSTOCK), NC = S.h(G3H_NCELL), NP = S.h(G3H_NPRED), NPP = S.h(G3H_NPP);
+    const int NCOMP = S.h(G3H_NCOMP), NX = S.h(G3H_NXBUF), NSTEP = S.h(G3H_NSTEPS), NT = S.h(G3H_NT);
+    const int NNLL = S.h(G3H_NNLL);
+    const int32_t* steplen = S.I + S.h(G3H_STEPLEN_OFF);
+    auto slot = [&](int id) { return eval_slot<T>(S, pv, id); };
+
+    // g3a_time (R/action_time.R:75-91)
+    double retro = S.h(G3H_PAR_RETRO) >= 0 ? pv.p[S.h(G3H_PAR_RETRO)] : 0.0;
+    double proj = S.h(G3H_PAR_PROJECT) >= 0 ? pv.p[S.h(G3H_PAR_PROJECT)] : 0.0;
+    if (!(retro >= 0) || !(proj >= 0)) return T(NaN);
+    int total_steps = NSTEP * (S.h(G3H_END_YEAR) - (int)std::floor(retro) - S.h(G3H_START_YEAR) + (int)std::floor(proj)) + NSTEP - 1;
+    if (total_steps + 1 > NT) return T(NaN);   // projections need tables beyond the packed range
+
+    std::vector<T> num(NC, T(0.0)), wgt(NC, T(1.0));
+    std::vector<T> totalpredate(NC), consratio(NC), consconv(NC);
+    std::vector<std::vector<T>> suit(NPP, std::vector<T>(NC, T(0.0))), cons(NPP, std::vector<T>(NC, T(0.0)));
+    std::vector<T> overcons(NS, T(0.0));
+    std::vector<std::vector<T>> trans_num(NS), trans_wgt(NS), growth_l(NS), growth_w(NS);
+    std::vector<int> lastcalc(NS, -1);
+    std::vector<std::vector<T>> mv_num(NS), mv_wgt(NS);
+    std::vector<std::vector<T>> model(NCOMP);
+    std::vector<double> nllsteps((size_t)NNLL * NT, 0.0);
+    std::vector<T> comp_tot(NNLL, T(0.0));
+    for (int c = 0; c < NCOMP; c++) {
+        const int32_t* C = S.comp(c);
+        bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+        model[c].assign((size_t)C[G3C_N_DEST] * (si || rep ? C[G3C_N_TIMES] : 1), T(0.0));
+    }
+    std::vector<std::vector<T>> si_params(NCOMP, std::vector<T>(2, T(0.0)));
+    T nll(0.0);
+
+    for (int cur_time = 0;; cur_time++) {
+        int cur_year = S.h(G3H_START_YEAR) + cur_time / NSTEP;
+        int cur_step = cur_time % NSTEP + 1;
+        double cur_step_size = steplen[cur_step - 1] / 12.0;
+        bool cur_step_final = cur_step == NSTEP;
+        int yidx = cur_year - S.h(G3H_START_YEAR);
+
+        // ---- g3a_initialconditions (R/action_renewal.R:83-103), cur_time == 0
+        if (cur_time == 0) for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            if (St[G3S_INIT_OFF] < 0) continue;
+            int L = St[G3S_L]; const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
+            for (int col = 0; col < St[G3S_NAREA] * St[G3S_NAGE]; col++) {
+                const int32_t* sl = S.I + St[G3S_INIT_OFF] + col * 5;
+                T mean = slot(sl[0]), sd = avoid_zero(slot(sl[1])), factor = slot(sl[2]), wa = slot(sl[3]), wb = slot(sl[4]);
+                std::vector<T> d(L); T tot(0.0);
+                for (int l = 0; l < L; l++) { d[l] = dnorm(midlen[l], mean, sd); tot = tot + d[l]; }
+                T den = avoid_zero(tot);                                    // normalize_vec, R/aab_env.R:37-41
+                for (int l = 0; l < L; l++) {
+                    int c = St[G3S_CELL_OFF] + col * L + l;
+                    num[c] = d[l] / den * 10000.0 * factor;
+                    wgt[c] = wa * xpow(midlen[l], wb);
+                }
+            }
+        }
+        // ---- report dstart_* (R/action_report.R:177-213)
+        if (rep && cur_time <= total_steps) for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            int n = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+            for (int i = 0; i < n; i++) {
+                rep->dstart_num[s][(size_t)cur_time * n + i] = val(num[St[G3S_CELL_OFF] + i]);
+                rep->dstart_wgt[s][(size_t)cur_time * n + i] = val(wgt[St[G3S_CELL_OFF] + i]);
+            }
+        }
+        if (cur_time > total_steps) break;
+
+        // ---- g3a_predate (R/action_predate.R:240-420)
+        std::fill(totalpredate.begin(), totalpredate.end(), T(0.0));
+        std::vector<std::vector<T>> totalsuit(NP);
+        for (int p = 0; p < NP; p++) totalsuit[p].assign(S.pred(p)[G3P_NAREA], T(0.0));
+        std::vector<char> is_prey(NS, 0);
+        for (int q = 0; q < NPP; q++) {     // step 1: collect suitable biomass
+            const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
+            is_prey[Q[G3PP_PREY]] = 1;
+            int L = St[G3S_L]; const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
+            const int32_t* ss = S.I + Q[G3PP_SUIT_OFF];
+            std::vector<T> suitability(L);
+            for (int l = 0; l < L; l++) {
+                if (Q[G3PP_SUIT_KIND] == G3SUIT_EXPL50)          // R/suitability.R:10
+                    suitability[l] = 1.0 / (1.0 + xexp(-slot(ss[0]) * (T(midlen[l]) - slot(ss[1]))));
+                else if (Q[G3PP_SUIT_KIND] == G3SUIT_CONSTANT)
+                    suitability[l] = slot(ss[0]);
+                else return T(NaN);
+            }
+            std::fill(suit[q].begin(), suit[q].end(), T(0.0));
+            for (int r = 0; r < St[G3S_NAREA]; r++) {
+                int area = S.I[St[G3S_AREA_OFF] + r], pr = -1;
+                for (int k = 0; k < P[G3P_NAREA]; k++) if (S.I[P[G3P_AREA_OFF] + k] == area) pr = k;
+                if (pr < 0) continue;
+                for (int a = 0; a < St[G3S_NAGE]; a++) {
+                    T colsum(0.0);
+                    for (int l = 0; l < L; l++) {
+                        int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
+                        suit[q][c] = suitability[l] * num[c] * wgt[c];
+                        colsum = colsum + suit[q][c];
+                    }
+                    totalsuit[Q[G3PP_PRED]][pr] = totalsuit[Q[G3PP_PRED]][pr] + colsum;
+                }
+            }
+        }
+        for (int q = 0; q < NPP; q++) {     // step 2: scale by total expected catch
+            const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
+            int L = St[G3S_L];
+            std::fill(cons[q].begin(), cons[q].end(), T(0.0));
+            for (int r = 0; r < St[G3S_NAREA]; r++) {
+                int area = S.I[St[G3S_AREA_OFF] + r], pr = -1;
+                for (int k = 0; k < P[G3P_NAREA]; k++) if (S.I[P[G3P_AREA_OFF] + k] == area) pr = k;
+                if (pr < 0) continue;
+                double E = S.R[P[G3P_E_ROFF] + (size_t)cur_time * P[G3P_NAREA] + pr];
+                for (int a = 0; a < St[G3S_NAGE]; a++) for (int l = 0; l < L; l++) {
+                    int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
+                    cons[q][c] = E * (suit[q][c] / totalsuit[Q[G3PP_PRED]][pr]);
+                    totalpredate[c] = totalpredate[c] + cons[q][c];
+                }
+            }
+        }
+        for (int s = 0; s < NS; s++) {      // step 4: overconsumption (R/action_predate.R:381-406)
+            if (!is_prey[s]) continue;
+            const int32_t* St = S.stock(s);
+            int c0 = St[G3S_CELL_OFF], n = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+            T o(0.0), o2(0.0);
+            for (int c = c0; c < c0 + n; c++) {
+                consratio[c] = totalpredate[c] / avoid_zero(num[c] * wgt[c]);
+                consratio[c] = dif_pmin(consratio[c], 0.95, 1e3);
+            }
+            for (int c = c0; c < c0 + n; c++) o = o + totalpredate[c];
+            for (int c = c0; c < c0 + n; c++) {
+                consconv[c] = 1.0 / avoid_zero(totalpredate[c]);
+                totalpredate[c] = (num[c] * wgt[c]) * consratio[c];
+            }
+            for (int c = c0; c < c0 + n; c++) o2 = o2 + totalpredate[c];
+            overcons[s] = o - o2;
+            for (int c = c0; c < c0 + n; c++) {
+                consconv[c] = consconv[c] * totalpredate[c];
+                num[c] = num[c] * (1.0 - consratio[c]);
+            }
+        }
+        for (int q = 0; q < NPP; q++) {     // step 5
+            const int32_t* St = S.stock(S.pp(q)[G3PP_PREY]);
+            int c0 = St[G3S_CELL_OFF], n = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+            for (int c = c0; c < c0 + n; c++) cons[q][c] = cons[q][c] * consconv[c];
+        }
+
+        // ---- g3a_naturalmortality (R/action_naturalmortality.R:26)
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            if (St[G3S_MORT_OFF] < 0) continue;
+            int L = St[G3S_L];
+            for (int col = 0; col < St[G3S_NAREA] * St[G3S_NAGE]; col++) {
+                T f = xexp(-slot(S.I[St[G3S_MORT_OFF] + col]) * cur_step_size);
+                for (int l = 0; l < L; l++) { int c = St[G3S_CELL_OFF] + col * L + l; num[c] = num[c] * f; }
+            }
+        }
+
+        // ---- g3a_growmature (R/action_grow.R:340-497)
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            int n = St[G3S_GROW_N];
+            if (n < 0) continue;
+            int L = St[G3S_L], D = n + 1, ncell = L * St[G3S_NAGE] * St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+            const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
+            double plusdl = S.R[St[G3S_PLUSDL_ROFF]];
+            bool transition = St[G3S_N_OUT] > 0 && ((St[G3S_TRANS_MASK] >> (cur_step - 1)) & 1);
+            if (transition) {       // "Reset transitioning arrays" (R/action_grow.R:376-381)
+                trans_num[s].assign(ncell, T(0.0));
+                trans_wgt[s].assign(wgt.begin() + c0, wgt.begin() + c0 + ncell);
+            }
+            const int32_t* gs = S.I + St[G3S_GROW_OFF];
+            int calc = (int)std::floor(cur_step_size * 12);
+            if (lastcalc[s] != calc) {
+                T linf = slot(gs[0]), kappa = slot(gs[1]), beta = slot(gs[2]), wa = slot(gs[3]), wb = slot(gs[4]);
+                std::vector<T> dl(L);
+                for (int l = 0; l < L; l++)     // g3a_grow_lengthvbsimple + bbinom wrapper (R/action_grow.R:54,220)
+                    dl[l] = avoid_zero(avoid_zero((linf - midlen[l]) * (1.0 - xexp(-(kappa) * cur_step_size))) / plusdl);
+                growth_bbinom(dl, n, avoid_zero(beta), growth_l[s]);
+                growth_w[s].assign((size_t)L * D, T(0.0));
+                std::vector<T> pw(L);
+                for (int l = 0; l < L; l++) pw[l] = xpow(midlen[l], wb);
+                for (int l = 0; l < L; l++) for (int x = 0; x < D; x++)     // vec_rotate - vec_extrude (R/action_grow.R:1-41,67-70)
+                    growth_w[s][l + L * x] = (pw[(l + x < L) ? l + x : L - 1] - pw[l]) * wa;
+            }
+            std::vector<T> Wm; grow_matrix_wgt(growth_w[s], L, D, Wm);
+            const int32_t* ms = St[G3S_MAT_KIND] != G3MAT_NONE ? S.I + St[G3S_MAT_OFF] : nullptr;
+            std::vector<T> on, ow;
+            for (int col = 0; col < St[G3S_NAREA] * St[G3S_NAGE]; col++) {
+                int age = St[G3S_MINAGE] + col % St[G3S_NAGE];
+                T* cn = &num[c0 + col * L]; T* cw = &wgt[c0 + col * L];
+                if (transition && St[G3S_MAT_KIND] == G3MAT_CONTINUOUS) {
+                    // maturity_ratio depends on growth_delta_l: two applies (R/action_grow.R:420-437)
+                    T alpha = slot(ms[0]), l50 = slot(ms[1]);
+                    T beta = ms[2] >= 0 ? slot(ms[2]) : T(0.0);
+                    std::vector<T> gm((size_t)L * D), gi((size_t)L * D);
+                    for (int l = 0; l < L; l++) {
+                        T inner = T(0.0) - alpha * (T(midlen[l]) - l50);         // g3a_mature_constant (R/action_mature.R:46-72)
+                        if (ms[2] >= 0) inner = inner - beta * (T(double(age)) - slot(ms[3]));
+                        T m0 = 1.0 / (1.0 + xexp(inner));
+                        for (int x = 0; x < D; x++) {
+                            T ratio = dif_pminmax(m0 * (alpha * (plusdl * x) + beta * cur_step_size), 0.0, 1.0, 1e5);
+                            gm[l + L * x] = growth_l[s][l + L * x] * ratio;
+                            gi[l + L * x] = growth_l[s][l + L * x] * (1.0 - ratio);
+                        }
+                    }
+                    std::vector<T> Gm, Gi; grow_matrix_len(gm, L, D, Gm); grow_matrix_len(gi, L, D, Gi);
+                    std::vector<T> tn, tw;
+                    grow_apply(Gm, Wm, L, cn, cw, tn, tw);
+                    grow_apply(Gi, Wm, L, cn, cw, on, ow);
+                    for (int l = 0; l < L; l++) { trans_num[s][col * L + l] = tn[l]; trans_wgt[s][col * L + l] = tw[l]; cn[l] = on[l]; cw[l] = ow[l]; }
+                } else if (transition && St[G3S_MAT_KIND] == G3MAT_CONSTANT) {
+                    // num * ratio / num * (1 - ratio) with one growth matrix (R/action_grow.R:438-457)
+                    std::vector<T> G; grow_matrix_len(growth_l[s], L, D, G);
+                    std::vector<T> nm(L), ni(L);
+                    for (int l = 0; l < L; l++) {
+                        T inner(0.0);
+                        if (ms[0] >= 0) inner = inner - slot(ms[0]) * (T(midlen[l]) - slot(ms[1]));
+                        if (ms[2] >= 0) inner = inner - slot(ms[2]) * (T(double(age)) - slot(ms[3]));
+                        T ratio = 1.0 / (1.0 + xexp(inner));
+                        nm[l] = cn[l] * ratio; ni[l] = cn[l] * (1.0 - ratio);
+                    }
+                    std::vector<T> tn, tw;
+                    grow_apply(G, Wm, L, nm.data(), cw, tn, tw);
+                    grow_apply(G, Wm, L, ni.data(), cw, on, ow);
+                    for (int l = 0; l < L; l++) { trans_num[s][col * L + l] = tn[l]; trans_wgt[s][col * L + l] = tw[l]; cn[l] = on[l]; cw[l] = ow[l]; }
+                } else {
+                    std::vector<T> G; grow_matrix_len(growth_l[s], L, D, G);
+                    grow_apply(G, Wm, L, cn, cw, on, ow);
+                    for (int l = 0; l < L; l++) { cn[l] = on[l]; cw[l] = ow[l]; }
+                }
+            }
+            lastcalc[s] = calc;
+        }
+        // ---- g3a_step_transition after growth (R/action_mature.R:78-134)
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            if (St[G3S_GROW_N] < 0 || St[G3S_N_OUT] == 0) continue;
+            if (!((St[G3S_TRANS_MASK] >> (cur_step - 1)) & 1)) continue;
+            int ncell = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+            std::vector<T> rem(trans_num[s]);
+            for (int o = 0; o < St[G3S_N_OUT]; o++) {
+                T ratio = slot(S.I[St[G3S_OUT_OFF] + 2 * o + 1]);
+                const int32_t* map = S.I + St[G3S_OUT_MAP_OFF] + o * ncell;
+                for (int i = 0; i < ncell; i++) {
+                    int d = map[i]; if (d < 0) continue;
+                    T moved = trans_num[s][i] * ratio;
+                    wgt[d] = ratio_add_pop(wgt[d], num[d], trans_wgt[s][i], moved);
+                    num[d] = num[d] + moved;
+                    rem[i] = rem[i] - moved;
+                }
+            }
+            for (int i = 0; i < ncell; i++) num[c0 + i] = num[c0 + i] + rem[i];
+        }
+
+        // ---- g3a_renewal (R/action_renewal.R:166-188)
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            int L = St[G3S_L]; const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
+            for (int k = 0; k < St[G3S_N_RENEW]; k++) {
+                const int32_t* Rn = S.I + St[G3S_RENEW_OFF] + k * G3R_LEN;
+                if (Rn[G3R_RUN_STEP] != 0 && Rn[G3R_RUN_STEP] != cur_step) continue;
+                for (int r = 0; r < St[G3S_NAREA]; r++) {
+                    int fs = S.I[Rn[G3R_FACTOR_OFF] + yidx * St[G3S_NAREA] + r];
+                    if (fs < 0) continue;
+                    T factor = slot(fs), mean = slot(Rn[G3R_MEAN]), sd = avoid_zero(slot(Rn[G3R_SD]));
+                    T wa = slot(Rn[G3R_WALPHA]), wb = slot(Rn[G3R_WBETA]);
+                    std::vector<T> d(L); T tot(0.0);
+                    for (int l = 0; l < L; l++) { d[l] = dnorm(midlen[l], mean, sd); tot = tot + d[l]; }
+                    T den = avoid_zero(tot);
+                    for (int l = 0; l < L; l++) {
+                        int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + Rn[G3R_AGE_IDX]) * L + l;
+                        T rn = d[l] / den * 10000.0 * factor, rw = wa * xpow(midlen[l], wb);
+                        wgt[c] = ratio_add_pop(wgt[c], num[c], rw, rn);
+                        num[c] = num[c] + rn;
+                    }
+                }
+            }
+        }
+
+        // ---- g3l_bounds_penalty (R/likelihood_bounds.R:13-16)
+        if (cur_time == 0) {
+            double bw = S.R[S.h(G3H_BOUND_WS_ROFF)], bs = S.R[S.h(G3H_BOUND_WS_ROFF) + 1];
+            for (int i = 0; i < S.h(G3H_NBOUND); i++) {
+                T p = mkpar(pv, S.I[S.h(G3H_BOUND_OFF) + i]);
+                double lo = S.R[S.h(G3H_BOUND_ROFF) + 2 * i], up = S.R[S.h(G3H_BOUND_ROFF) + 2 * i + 1];
+                T a = logspace_add(bs * (p - up) / (up - lo), T(0.0)) + logspace_add(bs * (lo - p) / (up - lo), T(0.0));
+                T pen = a * a;
+                nll = nll + bw * pen;
+                comp_tot[NNLL - 1] = comp_tot[NNLL - 1] + pen;
+                nllsteps[(size_t)(NNLL - 1) * NT + 0] += val(pen);
+            }
+        }
+        // ---- g3l_distribution (R/likelihood_distribution.R:275-394)
+        std::vector<std::vector<T>> xb(NX);
+        for (int c = 0; c < NCOMP; c++) {
+            const int32_t* C = S.comp(c);
+            if (!(pv.p[C[G3C_WEIGHT_PAR]] > 0)) continue;
+            T weight = mkpar(pv, C[G3C_WEIGHT_PAR]);
+            int ti = S.I[C[G3C_TIDX_OFF] + cur_time];
+            if (ti < 0) continue;
+            int x = C[G3C_XBUF];
+            if (xb[x].empty()) {            // collect vector: R/likelihood_distribution.R:275-287
+                const int32_t* X = S.xbuf(x);
+                xb[x].assign(NC, T(0.0));
+                if (X[G3X_KIND] == 0) {
+                    for (int k = 0; k < X[G3X_N_PP]; k++) {
+                        int q = S.I[X[G3X_PP_OFF] + k];
+                        const int32_t* St = S.stock(S.pp(q)[G3PP_PREY]);
+                        int c0 = St[G3S_CELL_OFF], n = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+                        for (int i = c0; i < c0 + n; i++)
+                            xb[x][i] = xb[x][i] + (X[G3X_UNIT] == 0 ? cons[q][i] / avoid_zero(wgt[i]) : cons[q][i]);
+                    }
+                } else {
+                    for (int i = 0; i < NC; i++) xb[x][i] = X[G3X_UNIT] == 0 ? num[i] : num[i] * wgt[i];
+                }
+            }
+            bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+            int nd = C[G3C_N_DEST], nt = C[G3C_N_TIMES];
+            T* m = model[c].data() + ((si || rep) ? (size_t)ti * nd : 0);
+            if (C[G3C_MODE] == 0) {
+                const int32_t* ptr = S.I + C[G3C_CSR_PTR_OFF]; const int32_t* idx = S.I + C[G3C_CSR_IDX_OFF];
+                const double* cf = S.R + C[G3C_CSR_COEF_ROFF];
+                for (int e = 0; e < nd; e++) for (int j = ptr[e]; j < ptr[e + 1]; j++) m[e] = m[e] + cf[j] * xb[x][idx[j]];
+            } else {
+                const int32_t* cd = S.I + C[G3C_CELL_DEST_OFF]; const double* cf = S.R + C[G3C_CELL_COEF_ROFF];
+                for (int i = 0; i < NC; i++) if (cd[i] >= 0) m[cd[i]] = m[cd[i]] + cf[i] * xb[x][i];
+            }
+            if (!S.I[C[G3C_CMP_OFF] + cur_time]) continue;
+            const double* obs = S.R + C[G3C_OBS_ROFF] + (size_t)ti * nd;
+            int nb = C[G3C_N_BINS], nsl = C[G3C_N_SLICES], nag = C[G3C_N_AREAG];
+            T cnll(0.0);
+            if (C[G3C_FUNC] == G3F_SUMOFSQUARES) {          // R/likelihood_distribution.R:3-39
+                for (int ag = 0; ag < nag; ag++) {
+                    T tm(0.0); double to = 0.0;
+                    for (int i = 0; i < nsl * nb; i++) { tm = tm + m[ag * nsl * nb + i]; to += obs[ag * nsl * nb + i]; }
+                    T atm = avoid_zero(tm); double ato = avoid_zero(to);
+                    for (int sl = 0; sl < nsl; sl++) {
+                        T v(0.0);
+                        for (int b = 0; b < nb; b++) {
+                            int e = (ag * nsl + sl) * nb + b;
+                            T dlt = m[e] / atm - obs[e] / ato;
+                            v = v + dlt * dlt;
+                        }
+                        cnll = cnll + v;
+                    }
+                }
+            } else if (C[G3C_FUNC] == G3F_MULTINOMIAL) {    // R/likelihood_distribution.R:41-60
+                double eps = S.R[C[G3C_PARAM_ROFF]];
+                for (int ag = 0; ag < nag; ag++) for (int sl = 0; sl < nsl; sl++) {
+                    const T* mm = m + (ag * nsl + sl) * nb; const double* oo = obs + (ag * nsl + sl) * nb;
+                    T tm(0.0); double so = 0.0, slg = 0.0;
+                    for (int b = 0; b < nb; b++) { tm = tm + mm[b]; so += oo[b]; slg += std::lgamma(1 + oo[b]); }
+                    T atm = avoid_zero(tm);
+                    T likely(0.0);
+                    for (int b = 0; b < nb; b++) likely = likely + oo[b] * xlog(dif_pmax(mm[b] / atm, 1.0 / (nb * eps), 1e4));
+                    cnll = cnll + 2.0 * (-likely + (slg - std::lgamma(1 + so)));
+                }
+            } else if (ti == nt - 1) {                      // surveyindices: R/likelihood_distribution.R:82-125
+                double fa = S.R[C[G3C_PARAM_ROFF]], fb = S.R[C[G3C_PARAM_ROFF] + 1];
+                bool lg = C[G3C_FUNC] == G3F_SI_LOG;
+                for (int e = 0; e < nd; e++) {
+                    std::vector<T> N(nt), I(nt); T mN(0.0), mI(0.0);
+                    for (int t = 0; t < nt; t++) {
+                        T mv = model[c][(size_t)t * nd + e]; double ov = S.R[C[G3C_OBS_ROFF] + (size_t)t * nd + e];
+                        N[t] = lg ? xlog(avoid_zero(mv)) : mv;
+                        I[t] = lg ? T(std::log(avoid_zero(ov))) : T(ov);
+                        mN = mN + N[t]; mI = mI + I[t];
+                    }
+                    mN = mN / double(nt); mI = mI / double(nt);
+                    T beta, alpha;
+                    if (std::isnan(fb)) {
+                        T sxy(0.0), sxx(0.0);
+                        for (int t = 0; t < nt; t++) { sxy = sxy + (I[t] - mI) * (N[t] - mN); sxx = sxx + (N[t] - mN) * (N[t] - mN); }
+                        beta = sxy / avoid_zero(sxx);
+                    } else beta = T(fb);
+                    alpha = std::isnan(fa) ? mI - beta * mN : T(fa);
+                    si_params[c][0] = alpha; si_params[c][1] = beta;
+                    T v(0.0);
+                    for (int t = 0; t < nt; t++) { T r = alpha + beta * N[t] - I[t]; v = v + r * r; }
+                    cnll = cnll + v;
+                }
+            }
+            nll = nll + weight * cnll;
+            comp_tot[c] = comp_tot[c] + cnll;
+            nllsteps[(size_t)c * NT + cur_time] += val(cnll);
+            if (!si && !rep) std::fill(model[c].begin(), model[c].end(), T(0.0));
+        }
+        // ---- g3l_understocking (R/likelihood_understocking.R:36-46)
+        if (S.h(G3H_US_N) > 0) {
+            T tot(0.0);
+            for (int i = 0; i < S.h(G3H_US_N); i++) tot = tot + overcons[S.I[S.h(G3H_US_OFF) + i]];
+            double power = S.R[S.h(G3H_US_ROFF)], w = S.R[S.h(G3H_US_ROFF) + 1];
+            T u = (power == 2.0) ? tot * tot : xpow(tot, power);
+            nll = nll + w * u;
+            comp_tot[NNLL - 2] = comp_tot[NNLL - 2] + u;
+            nllsteps[(size_t)(NNLL - 2) * NT + cur_time] += val(u);
+        }
+
+        // ---- g3a_age (R/action_age.R:51-85), then movement hand-off (R/action_mature.R:78-134, move_remainder = FALSE)
+        if (cur_step_final) {
+            for (int s = 0; s < NS; s++) {
+                const int32_t* St = S.stock(s);
+                if (!St[G3S_AGE_ENABLE]) continue;
+                int L = St[G3S_L], A = St[G3S_NAGE], NR = St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+                mv_num[s].assign((size_t)NR * L, T(0.0)); mv_wgt[s].assign((size_t)NR * L, T(0.0));
+                if (A == 1) {
+                    if (St[G3S_AGE_N_OUT] == 0) continue;
+                    for (int r = 0; r < NR; r++) for (int l = 0; l < L; l++) {
+                        int c = c0 + r * L + l;
+                        mv_num[s][r * L + l] = num[c]; mv_wgt[s][r * L + l] = wgt[c]; num[c] = T(0.0);
+                    }
+                    continue;
+                }
+                for (int r = 0; r < NR; r++) for (int a = A - 1; a >= 0; a--) for (int l = 0; l < L; l++) {
+                    int c = c0 + (r * A + a) * L + l, cp = c - L;
+                    if (a == A - 1) {
+                        if (St[G3S_AGE_N_OUT] > 0) {
+                            mv_num[s][r * L + l] = num[c]; mv_wgt[s][r * L + l] = wgt[c];
+                            num[c] = num[cp]; wgt[c] = wgt[cp];
+                        } else {
+                            wgt[c] = ratio_add_pop(wgt[c], num[c], wgt[cp], num[cp]);
+                            num[c] = num[c] + num[cp];
+                        }
+                    } else if (a == 0) {
+                        num[c] = T(0.0);
+                    } else {
+                        num[c] = num[cp]; wgt[c] = wgt[cp];
+                    }
+                }
+            }
+            for (int s = 0; s < NS; s++) {
+                const int32_t* St = S.stock(s);
+                if (!St[G3S_AGE_ENABLE] || St[G3S_AGE_N_OUT] == 0) continue;
+                int L = St[G3S_L], NR = St[G3S_NAREA];
+                for (int o = 0; o < St[G3S_AGE_N_OUT]; o++) {
+                    T ratio = slot(S.I[St[G3S_AGE_OUT_OFF] + 2 * o + 1]);
+                    const int32_t* map = S.I + St[G3S_AGE_MAP_OFF] + o * NR * L;
+                    for (int i = 0; i < NR * L; i++) {
+                        int d = map[i]; if (d < 0) continue;
+                        T moved = mv_num[s][i] * ratio;
+                        wgt[d] = ratio_add_pop(wgt[d], num[d], mv_wgt[s][i], moved);
+                        num[d] = num[d] + moved;
+                    }
+                }
+            }
+        }
+    }
+
+    if (comp_out) for (int i = 0; i < NNLL; i++) comp_out[i] = val(comp_tot[i]);
+    if (rep) {
+        rep->nll[0] = val(nll);
+        std::memcpy(rep->steps, nllsteps.data(), sizeof(double) * nllsteps.size());
+        for (int c = 0; c < NCOMP; c++) {
+            for (size_t i = 0; i < model[c].size(); i++) rep->model[c][i] = val(model[c][i]);
+            const int32_t* C = S.comp(c);
+            bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+            rep->params[c][0] = si ? val(si_params[c][0]) : NaN;
+            rep->params[c][1] = si ? val(si_params[c][1]) : NaN;
+        }
+    }
+    return nll;
+}
+
+int64_t report_len(const Spec& S) {
+    int64_t n = 1 + (int64_t)S.h(G3H_NNLL) * S.h(G3H_NT);
+    for (int s = 0; s < S.h(G3H_NSTOCK); s++) {
+        const int32_t* St = S.stock(s);
+        n += 2LL * S.h(G3H_NT) * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+    }
+    for (int c = 0; c < S.h(G3H_NCOMP); c++) n += (int64_t)S.comp(c)[G3C_N_TIMES] * S.comp(c)[G3C_N_DEST] + 2;
+    return n;
+}
+
+constexpr int KT = 8;   // tangents per Dual pass
+
+void eval_range(const Spec& S, const double* par, int64_t b0, int64_t b1, const int32_t* tidx, int K,
+                double* nll, double* comp, double* grad) {
+    int P = S.h(G3H_NPAR), NN = S.h(G3H_NNLL);
+    for (int64_t b = b0; b < b1; b++) {
+        const double* p = par + b * P;
+        ParVec<double> pv{p, nullptr, 0};
+        double v = run_model<double>(S, pv, comp ? comp + b * NN : nullptr, nullptr);
+        if (nll) nll[b] = v;
+        if (grad && K > 0) {
+            for (int k0 = 0; k0 < K; k0 += KT) {
+                ParVec<Dual<KT>> dv{p, tidx + k0, std::min(KT, K - k0)};
+                Dual<KT> r = run_model<Dual<KT>>(S, dv, nullptr, nullptr);
+                for (int k = 0; k < std::min(KT, K - k0); k++) grad[b * K + k0 + k] = r.d[k];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t g3oracle_report_len(const int32_t* ints, const double* reals) {
+    Spec S{ints, reals};
+    return report_len(S);
+}
+
+// Batched evaluation on `nthreads` host threads (one std::thread per contiguous block).
+int g3oracle_eval(const int32_t* ints, const double* reals, const double* par, int64_t B,
+                  const int32_t* tangent_idx, int32_t K, double* nll, double* nll_comp, double* grad,
+                  int32_t nthreads) {
+    Spec S{ints, reals};
+    if (S.h(G3H_VERSION) != G3CUDA_SPEC_VERSION) return -1;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads == 1 || B < 2) { eval_range(S, par, 0, B, tangent_idx, K, nll, nll_comp, grad); return 0; }
+    std::vector<std::thread> th;
+    int64_t per = (B + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; t++) {
+        int64_t b0 = t * per, b1 = std::min<int64_t>(B, b0 + per);
+        if (b0 >= b1) break;
+        th.emplace_back([=, &S] { eval_range(S, par, b0, b1, tangent_idx, K, nll, nll_comp, grad); });
+    }
+    for (auto& t : th) t.join();
+    return 0;
+}
+
+// Single-vector report, same buffer layout as g3cuda_report() (include/g3cuda.h).
+int g3oracle_report(const int32_t* ints, const double* reals, const double* par, double* out) {
+    Spec S{ints, reals};
+    if (S.h(G3H_VERSION) != G3CUDA_SPEC_VERSION) return -1;
+    int NT = S.h(G3H_NT);
+    ReportSink rep;
+    double* p = out;
+    rep.nll = p; p += 1;
+    rep.steps = p; p += (size_t)S.h(G3H_NNLL) * NT;
+    for (int s = 0; s < S.h(G3H_NSTOCK); s++) {
+        const int32_t* St = S.stock(s);
+        size_t n = (size_t)NT * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+        rep.dstart_num.push_back(p); p += n;
+        rep.dstart_wgt.push_back(p); p += n;
+    }
+    for (int c = 0; c < S.h(G3H_NCOMP); c++) { rep.model.push_back(p); p += (size_t)S.comp(c)[G3C_N_TIMES] * S.comp(c)[G3C_N_DEST]; }
+    for (int c = 0; c < S.h(G3H_NCOMP); c++) { rep.params.push_back(p); p += 2; }
+    std::fill(out, p, 0.0);
+    ParVec<double> pv{par, nullptr, 0};
+    run_model<double>(S, pv, nullptr, &rep);
+    return 0;
+}
+
+// ---- primitives exposed for the known-answer tests (tests/test_oracle_kat.py) ----
+void g3oracle_growth_bbinom(const double* delt_l, int32_t na, int32_t binn, double beta, double* out) {
+    std::vector<double> d(delt_l, delt_l + na), o;
+    growth_bbinom<double>(d, binn, beta, o);
+    std::copy(o.begin(), o.end(), out);
+}
+void g3oracle_grow_matrix_len(const double* delta, int32_t L, int32_t D, double* out) {
+    std::vector<double> d(delta, delta + (size_t)L * D), o;
+    grow_matrix_len<double>(d, L, D, o);
+    std::copy(o.begin(), o.end(), out);
+}
+void g3oracle_grow_matrix_wgt(const double* delta, int32_t L, int32_t D, double* out) {
+    std::vector<double> d(delta, delta + (size_t)L * D), o;
+    grow_matrix_wgt<double>(d, L, D, o);
+    std::copy(o.begin(), o.end(), out);
+}
+void g3oracle_grow_apply(const double* G, const double* W, int32_t L, const double* num, const double* wgt,
+                         double* out_num, double* out_wgt) {
+    std::vector<double> g(G, G + (size_t)L * L), w(W, W + (size_t)L * L), on, ow;
+    grow_apply<double>(g, w, L, num, wgt, on, ow);
+    std::copy(on.begin(), on.end(), out_num);
+    std::copy(ow.begin(), ow.end(), out_wgt);
+}
+double g3oracle_avoid_zero(double a) { return avoid_zero<double>(a); }
+double g3oracle_logspace_add(double a, double b) { return logspace_add<double>(a, b); }
+double g3oracle_dif_pmin(double a, double b, double s) { return dif_pmin<double>(a, b, s); }
+double g3oracle_dif_pminmax(double a, double lo, double hi, double s) { return dif_pminmax<double>(a, lo, hi, s); }
+double g3oracle_dnorm(double x, double m, double s) { return dnorm<double>(x, m, s); }
+double g3oracle_ratio_add_pop(double ov, double oa, double nv, double na) { return ratio_add_pop<double>(ov, oa, nv, na); }
+double g3oracle_digamma(double x) { return digamma(x); }
+
+}  // extern "C"
