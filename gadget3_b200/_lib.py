@@ -59,13 +59,16 @@ def load():
     lib.g3cuda_report.restype = C.c_int
     lib.g3cuda_last_error.restype = C.c_char_p
     lib.g3cuda_abi_version.restype = C.c_int32
+    lib.g3cuda_fp64_peak_tflops.argtypes = [C.c_int]
+    lib.g3cuda_fp64_peak_tflops.restype = C.c_double
     _LIB = lib
     return lib
 
 
 EXPORTED = ["g3cuda_model_create", "g3cuda_model_free", "g3cuda_n_par", "g3cuda_n_nll", "g3cuda_n_steps",
             "g3cuda_report_len", "g3cuda_eval_batch", "g3cuda_eval_batch_device", "g3cuda_launch_count",
-            "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version"]
+            "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version",
+            "g3cuda_fp64_peak_tflops"]
 
 
 def _dp(a):

@@ -174,7 +174,43 @@ int check_spec(const g3cuda_spec* spec) {
 
 }  // namespace
 
+// DFMA-chain microbenchmark: the fp64 roofline denominator (MEASURED_PEAKS.json has no fp64 entry).
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 extern "C" {
+
+double g3cuda_fp64_peak_tflops(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1.0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int threads = 512, blocks = prop.multiProcessorCount * 4, iters = 20000;
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * threads * blocks) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 2.0 * 64.0 * iters * (double)threads * blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return best;
+}
 
 const char* g3cuda_last_error(void) { return g_err.c_str(); }
 int32_t g3cuda_abi_version(void) { return G3CUDA_SPEC_VERSION; }

@@ -100,6 +100,10 @@ float g3cuda_last_kernel_ms(g3cuda_model* m);
  * Replaces: obj$report(par) (R/run_tmb.R:1277-1321). */
 int g3cuda_report(g3cuda_model* m, const double* par, double* out);
 
+/* Measured fp64 FMA throughput of `device` in TFLOP/s (DFMA-chain microbenchmark; the roofline
+ * denominator bench.py reports against). Negative on failure. */
+double g3cuda_fp64_peak_tflops(int device);
+
 /* Last error message of the calling thread. */
 const char* g3cuda_last_error(void);
 
