@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- objective evaluations per second of a gadget3 model on N B200s.
+
+One "step" = one pass of the hot path over one batch of synthetic parameter vectors per GPU
+(BASELINE.json configs[1]: multiple-substocks, 65,536 vectors, nll only). Prints ONE JSON line.
+
+  value      evals/s with the parameter batches already resident in HBM (device pointers through
+             g3cuda_eval_batch_device), CUDA events on the launching stream, max over ranks
+  e2e        evals/s through the reference-facing call (g3_cuda_adfun(...).fn_batch -> g3cuda_eval_batch)
+             with HOST buffers: pinned host -> device copy of the parameters and device -> host read of
+             the nll vector inside the timed region
+  roofline   fp64-pipe roofline of the evaluation kernel: algorithmic flop per evaluation (SURVEY.md
+             section 8d) x evaluations per launch / mean launch duration, against the DFMA
+             throughput measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry)
+  cpu_baseline  the CPU restatement of the reference objective (oracle/, or oracle/_ref when the
+             reference's generated code was compiled) on the box's host cores, bounded sample
+
+`--impl reference` times that CPU implementation alone (all host threads) and prints the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "objective_evals_per_sec"
+UNIT = "evals/s"
+# Algorithmic flop per evaluation, reference semantics (DESIGN.md "flop model")
+ALG_FLOP = {"C1": 4.39e6, "C2": 2.60e7}
+WORKLOAD = {"C1": "introduction-single-stock, nll only", "C2": "multiple-substocks imm/mat, nll only"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(ALG_FLOP))
+    ap.add_argument("--batch", type=int, default=65536, help="parameter vectors per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [ln.split(", ") for ts, ln in self.lines if t0 <= ts <= t1 + 0.2] or [ln.split(", ") for _, ln in self.lines]
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference(model, params, config, batch_fn, seconds_target=12.0):
+    """Time the CPU implementation of the path on all host cores over a bounded sample."""
+    from oracle import oracle_lib as ol
+    kind, lib = "port", None
+    try:
+        lib = ol.load(ol.build(native=True))          # -O3 -march=native, like TMB's default flags
+    except Exception:
+        lib = ol.load()
+    orc = ol.Oracle(*model.pack(params), lib=lib)
+    cores = os.cpu_count() or 1
+    probe = batch_fn(4 * cores, 99)
+    t = time.perf_counter(); orc.eval_batch(probe, nthreads=cores); per = (time.perf_counter() - t) / len(probe)
+    n = int(min(max(seconds_target / max(per, 1e-9), 8 * cores), 1 << 16))
+    n = max(cores, n // cores * cores)
+    sample = batch_fn(n, 7)
+    t = time.perf_counter(); nll, _, _ = orc.eval_batch(sample, nthreads=cores); dt = time.perf_counter() - t
+    assert np.isfinite(nll).all()
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n} vectors of the {config} batch, {cores} threads, {dt:.1f} s wall"}, orc
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from gadget3_b200.configs import CONFIGS, parameter_batch
+    model, params = CONFIGS[a.config]()
+    opt = params.optimised_indices()
+    base = params.values()
+
+    def batch_fn(n, seed):
+        full = np.tile(base, (n, 1))
+        full[:, opt] = parameter_batch(params, n, seed=seed)
+        return full
+
+    cfg = {"workload": f"{a.config}: {WORKLOAD[a.config]}, {a.batch} parameter vectors per GPU per step",
+           "n_par": int(len(base)), "n_optimised": int(len(opt)), "batch_per_gpu": a.batch,
+           "steps_per_eval": model.n_steps, "parallelism": f"batch-sharded x{world}"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        from oracle import oracle_lib as ol
+        try:
+            lib = ol.load(ol.build(native=True))
+        except Exception:
+            lib = ol.load()
+        orc = ol.Oracle(*model.pack(params), lib=lib)
+        probe = batch_fn(4 * cores, 99)
+        t = time.perf_counter(); orc.eval_batch(probe, nthreads=cores); per = (time.perf_counter() - t) / len(probe)
+        n = int(min(max(4.0 / max(per, 1e-9), 8 * cores), a.batch))     # ~4 s per step
+        n = max(cores, n // cores * cores)
+        sample = batch_fn(n, 7)
+        for _ in range(a.warmup):
+            orc.eval_batch(sample[: max(cores, n // 8)], nthreads=cores)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            orc.eval_batch(sample, nthreads=cores)
+        dt = time.perf_counter() - t0
+        v = n * a.steps / dt
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} vectors per step ({a.config}), {cores} threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gadget3_b200.run_cuda import g3_cuda_adfun
+    fn = g3_cuda_adfun(model, params, device=local)
+    h = fn.handle
+    B, P = a.batch, h.n_par
+
+    # ---- inputs: NB distinct batches so that the parameter stream (NB x B x P x 8 B) exceeds the 126 MB L2
+    nb = max(2, int(np.ceil(140e6 / (B * P * 8))))
+    host = [torch.from_numpy(batch_fn(B, 1000 + 17 * rank + i)).pin_memory() for i in range(nb)]
+    d_par = [x.to(dev, non_blocking=True) for x in host]
+    d_nll = torch.empty(B, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    peak_tflops = h.lib.g3cuda_fp64_peak_tflops(local)
+
+    def step_device(i):
+        h.eval_batch_device(d_par[i % nb].data_ptr(), B, d_nll.data_ptr(), stream=stream.cuda_stream)
+
+    for i in range(a.warmup):
+        step_device(i)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.25)
+    launches0 = h.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    barrier()
+    tc0 = time.perf_counter()
+    evs[0].record(stream)
+    for i in range(a.steps):
+        step_device(i)
+        evs[i + 1].record(stream)
+    barrier()
+    tc1 = time.perf_counter()
+    launches = h.launch_count() - launches0
+    total_ms = evs[0].elapsed_time(evs[-1])
+    kern_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(a.steps)]
+    clk = clocks.stop(tc0, tc1)
+    assert torch.isfinite(d_nll).all().item(), "non-finite nll in the timed batch"
+
+    # ---- end to end: host buffers in, host buffers out, through the public API
+    P_opt = [np.ascontiguousarray(x.numpy()[:, opt]) for x in host]
+
+    def step_e2e(i):
+        full = host[i % nb].numpy()                       # pinned; the H2D copy happens inside eval_batch
+        nll, _, _ = h.eval_batch(full)
+        if world > 1:                                     # every rank ends up with the whole job's nll vector
+            t = torch.from_numpy(nll).to(dev)
+            out = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(out, t)
+            nll = torch.cat(out).cpu().numpy()
+        return nll
+
+    for i in range(min(a.warmup, 2)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks
+    tt = torch.tensor([total_ms, e2e_s, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(tt[0]), float(tt[1])
+
+    value = world * B * a.steps / (total_ms * 1e-3)
+    e2e = world * B * a.steps / e2e_s
+    kms = float(np.mean(kern_ms))
+    flop = ALG_FLOP[a.config]
+    achieved = flop * B / (kms * 1e-3) / 1e12
+    hbm_bytes = B * (P * 8 + 8)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": dict(cfg, l2="inputs larger than L2: %d distinct parameter batches (%.0f MB) rotate" % (nb, nb * B * P * 8 / 1e6)),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * P * 8), "d2h_bytes_per_step": int(B * 8)},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "fp64", "kernel": "g3::eval_kernel<double>", "achieved": achieved, "peak": peak_tflops,
+                     "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops > 0 else None,
+                     "peak_source": "DFMA-chain microbenchmark run live on this GPU (g3cuda_fp64_peak_tflops); "
+                                    "MEASURED_PEAKS.json has no fp64 entry",
+                     "alg_flop_per_eval": flop, "evals_per_launch": B, "launch_ms": kms,
+                     "hbm": {"achieved": hbm_bytes / (kms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                             "alg_bytes_per_eval": P * 8 + 8},
+                     "traffic": None},
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cb, orc = cpu_reference(model, params, a.config, batch_fn)
+        # spot-check the timed batch against the checker (not part of any timed region)
+        chk = host[(a.steps - 1) % nb].numpy()[:64]
+        o = orc.eval_batch(chk, nthreads=cb["cores"])[0]
+        rel = float(np.max(np.abs(d_nll[:64].cpu().numpy() - o) / np.abs(o)))
+        out["cpu_baseline"] = cb
+        out["parity_spot_check"] = {"vectors": 64, "max_rel_err_nll": rel}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -408,9 +408,11 @@ __global__ void __launch_bounds__(MAXT) eval_kernel(const __grid_constant__ KArg
                         T delta = avoid_zero(dl / pdl);
                         T beta = avoid_zero(slotv[gs[2]]);
                         T alpha = (beta * delta) / ((double)n2 - delta);
-                        // P(x) = C(n,x) prod_{i<x}(alpha+i) prod_{j<n-x}(beta+j) / prod_{k<n}(alpha+beta+k)
+                        // P(x) = C(n,x) prod_{i<x}|alpha+i| prod_{j<n-x}(beta+j) / prod_{k<n}|alpha+beta+k|
+                        // (the reference's lgamma is log|Gamma|, so a mean jump beyond n -- alpha < 0 --
+                        // yields absolute values, tests/test-action_grow.R:34-62; beta > 0 always)
                         T g = T(1.0);
-                        for (int j = 0; j < n2; j++) g = g * ((beta + (double)j) / (alpha + beta + (double)j));
+                        for (int j = 0; j < n2; j++) g = g * ((beta + (double)j) / xabs(alpha + beta + (double)j));
                         T m0(0.0), malpha(0.0);
                         if (cont) {
                             const int32_t* ms = I + S2[G3S_MAT_OFF];
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(MAXT) eval_kernel(const __grid_constant__ KArg
                                 scr[2 * gsz + x * L2 + tid] = g * (1.0 - ratio);
                             }
                             if (x < n2)
-                                g = g * ((double)(n2 - x) / (double)(x + 1)) * ((alpha + (double)x) / (beta + (double)(n2 - x - 1)));
+                                g = g * ((double)(n2 - x) / (double)(x + 1)) * (xabs(alpha + (double)x) / (beta + (double)(n2 - x - 1)));
                         }
                     }
                     __syncthreads();

@@ -55,8 +55,8 @@ struct g3cuda_model {
     int64_t launches = 0;
     // per-call scratch (grow-only)
     double* d_par = nullptr; double* d_nll = nullptr; double* d_comp = nullptr; double* d_grad = nullptr;
-    int32_t* d_tidx = nullptr; double* d_report = nullptr;
-    size_t cap_par = 0, cap_nll = 0, cap_comp = 0, cap_grad = 0, cap_tidx = 0;
+    int32_t* d_tidx = nullptr; double* d_report = nullptr; double* d_out = nullptr;
+    size_t cap_par = 0, cap_nll = 0, cap_comp = 0, cap_grad = 0, cap_tidx = 0, cap_out = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -224,7 +224,7 @@ void g3cuda_model_free(g3cuda_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (void* p : m->owned) cudaFree(p);
-    for (void* p : {(void*)m->d_par, (void*)m->d_nll, (void*)m->d_comp, (void*)m->d_grad, (void*)m->d_tidx, (void*)m->d_report})
+    for (void* p : {(void*)m->d_par, (void*)m->d_nll, (void*)m->d_comp, (void*)m->d_grad, (void*)m->d_tidx, (void*)m->d_report, (void*)m->d_out})
         if (p) cudaFree(p);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
@@ -461,25 +461,23 @@ int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B, const int32
     CUDA_TRY(cudaSetDevice(m->device));
     const int P = m->base.NPAR, NN = m->base.NNLL;
     int rc;
-    double* d_out_nll = nullptr; size_t cap_out = 0;
     if ((rc = ensure(&m->d_par, &m->cap_par, (size_t)B * P))) return rc;
-    if ((rc = ensure(&d_out_nll, &cap_out, (size_t)B))) return rc;
-    if (nll_comp && (rc = ensure(&m->d_comp, &m->cap_comp, (size_t)B * NN))) { cudaFree(d_out_nll); return rc; }
+    if ((rc = ensure(&m->d_out, &m->cap_out, (size_t)B))) return rc;
+    if (nll_comp && (rc = ensure(&m->d_comp, &m->cap_comp, (size_t)B * NN))) return rc;
     bool want_grad = grad && K > 0;
     if (want_grad) {
-        if (!tangent_idx) { cudaFree(d_out_nll); return fail(G3CUDA_EINVAL, "grad requested without tangent_idx"); }
-        if ((rc = ensure(&m->d_grad, &m->cap_grad, (size_t)B * K)) || (rc = ensure(&m->d_tidx, &m->cap_tidx, (size_t)K))) { cudaFree(d_out_nll); return rc; }
-        cudaMemcpyAsync(m->d_tidx, tangent_idx, sizeof(int32_t) * K, cudaMemcpyHostToDevice, m->stream);
+        if (!tangent_idx) return fail(G3CUDA_EINVAL, "grad requested without tangent_idx");
+        if ((rc = ensure(&m->d_grad, &m->cap_grad, (size_t)B * K)) || (rc = ensure(&m->d_tidx, &m->cap_tidx, (size_t)K))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(m->d_tidx, tangent_idx, sizeof(int32_t) * K, cudaMemcpyHostToDevice, m->stream));
     }
-    cudaMemcpyAsync(m->d_par, par, sizeof(double) * B * P, cudaMemcpyHostToDevice, m->stream);
-    rc = g3cuda_eval_batch_device(m, m->d_par, B, want_grad ? m->d_tidx : nullptr, want_grad ? K : 0, d_out_nll,
+    CUDA_TRY(cudaMemcpyAsync(m->d_par, par, sizeof(double) * B * P, cudaMemcpyHostToDevice, m->stream));
+    rc = g3cuda_eval_batch_device(m, m->d_par, B, want_grad ? m->d_tidx : nullptr, want_grad ? K : 0, m->d_out,
                                   nll_comp ? m->d_comp : nullptr, want_grad ? m->d_grad : nullptr, m->stream);
-    if (rc) { cudaFree(d_out_nll); return rc; }
-    cudaMemcpyAsync(nll, d_out_nll, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream);
-    if (nll_comp) cudaMemcpyAsync(nll_comp, m->d_comp, sizeof(double) * B * NN, cudaMemcpyDeviceToHost, m->stream);
-    if (want_grad) cudaMemcpyAsync(grad, m->d_grad, sizeof(double) * B * K, cudaMemcpyDeviceToHost, m->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(nll, m->d_out, sizeof(double) * B, cudaMemcpyDeviceToHost, m->stream));
+    if (nll_comp) CUDA_TRY(cudaMemcpyAsync(nll_comp, m->d_comp, sizeof(double) * B * NN, cudaMemcpyDeviceToHost, m->stream));
+    if (want_grad) CUDA_TRY(cudaMemcpyAsync(grad, m->d_grad, sizeof(double) * B * K, cudaMemcpyDeviceToHost, m->stream));
     cudaError_t e = cudaStreamSynchronize(m->stream);
-    cudaFree(d_out_nll);
     if (e != cudaSuccess) return fail(G3CUDA_ECUDA, "evaluation failed: %s", cudaGetErrorString(e));
     return G3CUDA_OK;
 }
@@ -509,6 +507,11 @@ int g3cuda_report(g3cuda_model* m, const double* par, double* out) {
         cudaMemcpyAsync(out, d_rep, sizeof(double) * m->report_len, cudaMemcpyDeviceToHost, m->stream);
         cudaError_t e = cudaStreamSynchronize(m->stream);
         if (e != cudaSuccess) rc = fail(G3CUDA_ECUDA, "report failed: %s", cudaGetErrorString(e));
+        const int32_t* I = m->I.data();
+        for (int c = 0; c < m->base.NCOMP && !rc; c++) {     // regression parameters exist for survey indices only
+            int f = I[I[G3H_COMP_OFF] + c * G3C_LEN + G3C_FUNC];
+            if (f != G3F_SI_LOG && f != G3F_SI_LINEAR) out[m->base.rep_params + 2 * c] = out[m->base.rep_params + 2 * c + 1] = std::nan("");
+        }
     }
     cudaFree(d_rep); cudaFree(d_nll);
     return rc;

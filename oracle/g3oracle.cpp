@@ -174,10 +174,33 @@ template <class T> T eval_slot(const Spec& S, const ParVec<T>& pv, int slot) {
 }
 
 // ------------------------------------------------------------------ growth natives
+// g3a_grow_lengthvbsimple: R/action_grow.R:44-55
+template <class T> T grow_lengthvbsimple(const T& linf, const T& kappa, double midlen, double cur_step_size) {
+    return avoid_zero((linf - midlen) * (1.0 - xexp(-(kappa) * cur_step_size)));
+}
+// Diagnostic switch (tests only): evaluate growth_bbinom in the lgamma-free product form the CUDA
+// kernel uses, to measure how far the two formulations are apart.
+int g_bbinom_product = 0;
+inline double xabs(double a) { return std::fabs(a); }
+template <int K> Dual<K> xabs(const Dual<K>& a) { return chain(a, std::fabs(a.v), a.v < 0 ? -1.0 : 1.0); }
+
 // growth_bbinom: R/action_grow.R:155-213. out[l + L*x], column-major L x (n+1)
 template <class T> void growth_bbinom(const std::vector<T>& delt_l, int binn, const T& beta, std::vector<T>& out) {
     int na = (int)delt_l.size(), n = binn;
     out.assign((size_t)na * (n + 1), T(0.0));
+    if (g_bbinom_product) {
+        // C(n,x) prod_{i<x}|alpha+i| prod_{j<n-x}(beta+j) / prod_{k<n}|alpha+beta+k|
+        for (int l = 0; l < na; l++) {
+            T alpha = (beta * delt_l[l]) / (double(binn) - delt_l[l]);
+            T g(1.0);
+            for (int j = 0; j < n; j++) g = g * ((beta + double(j)) / xabs(alpha + beta + double(j)));
+            for (int x = 0; x <= n; x++) {
+                out[l + na * x] = g;
+                if (x < n) g = g * (double(n - x) / double(x + 1)) * (xabs(alpha + double(x)) / (beta + double(n - x - 1)));
+            }
+        }
+        return;
+    }
     for (int i = 0; i < na * (n + 1); i++) {
         T alpha = (beta * delt_l[i % na]) / (double(binn) - delt_l[i % na]);
         double x = double(i / na);
@@ -412,7 +435,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                 T linf = slot(gs[0]), kappa = slot(gs[1]), beta = slot(gs[2]), wa = slot(gs[3]), wb = slot(gs[4]);
                 std::vector<T> dl(L);
                 for (int l = 0; l < L; l++)     // g3a_grow_lengthvbsimple + bbinom wrapper (R/action_grow.R:54,220)
-                    dl[l] = avoid_zero(avoid_zero((linf - midlen[l]) * (1.0 - xexp(-(kappa) * cur_step_size))) / plusdl);
+                    dl[l] = avoid_zero(grow_lengthvbsimple(linf, kappa, midlen[l], cur_step_size) / plusdl);
                 growth_bbinom(dl, n, avoid_zero(beta), growth_l[s]);
                 growth_w[s].assign((size_t)L * D, T(0.0));
                 std::vector<T> pw(L);
@@ -803,6 +826,10 @@ void g3oracle_grow_apply(const double* G, const double* W, int32_t L, const doub
     std::copy(on.begin(), on.end(), out_num);
     std::copy(ow.begin(), ow.end(), out_wgt);
 }
+double g3oracle_grow_lengthvbsimple(double linf, double kappa, double midlen, double dt) {
+    return grow_lengthvbsimple<double>(linf, kappa, midlen, dt);
+}
+void g3oracle_set_bbinom_product(int32_t on) { g_bbinom_product = on; }
 double g3oracle_avoid_zero(double a) { return avoid_zero<double>(a); }
 double g3oracle_logspace_add(double a, double b) { return logspace_add<double>(a, b); }
 double g3oracle_dif_pmin(double a, double b, double s) { return dif_pmin<double>(a, b, s); }

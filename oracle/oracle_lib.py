@@ -38,7 +38,7 @@ def load(path=None):
     lib.g3oracle_report_len.argtypes = [ip, dp]
     lib.g3oracle_report_len.restype = C.c_int64
     for n, k in (("avoid_zero", 1), ("logspace_add", 2), ("dif_pmin", 3), ("dif_pminmax", 4), ("dnorm", 3),
-                 ("ratio_add_pop", 4), ("digamma", 1)):
+                 ("ratio_add_pop", 4), ("digamma", 1), ("grow_lengthvbsimple", 4)):
         f = getattr(lib, "g3oracle_" + n)
         f.argtypes = [C.c_double] * k
         f.restype = C.c_double

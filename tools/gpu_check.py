@@ -18,13 +18,16 @@ def main():
         fn = g3_cuda_adfun(model, params)
         ints, reals = model.pack(params)
         orc = Oracle(ints, reals)
-        P = np.vstack([fn.par[None, :], parameter_batch(params, 63)])
+        P = np.vstack([fn.par[None, :], parameter_batch(params, 255)])
         full = fn.full_par(P)
         t = time.time(); o_nll, o_comp, _ = orc.eval_batch(full, want_comp=True, nthreads=8); to = time.time() - t
         t = time.time(); g_nll, g_comp, _ = fn.handle.eval_batch(full, want_comp=True); tg = time.time() - t
         rel = np.abs(g_nll - o_nll) / np.maximum(np.abs(o_nll), 1e-300)
         print(f"{name}: oracle {to*1e3:.1f} ms, gpu {tg*1e3:.1f} ms (kernel {fn.handle.last_kernel_ms():.3f} ms), max rel err nll {rel.max():.3e}")
         print("  nll[:4] gpu", g_nll[:4], "oracle", o_nll[:4])
+        wo_g, wo_o = g_nll - 1e8 * g_comp[:, -2], o_nll - 1e8 * o_comp[:, -2]
+        print("  max rel err nll without understocking", (np.abs(wo_g - wo_o) / np.abs(o_nll)).max(),
+              " us share of nll at worst vector", (1e8 * o_comp[:, -2] / o_nll)[int(np.argmax(rel))])
         crel = np.abs(g_comp - o_comp) / np.maximum(np.abs(o_comp), 1e-12)
         print("  comp max rel err per row", crel.max(axis=0))
         if rel.max() > 1e-10:
