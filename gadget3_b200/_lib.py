@@ -59,6 +59,8 @@ def load():
     lib.g3cuda_report.restype = C.c_int
     lib.g3cuda_last_error.restype = C.c_char_p
     lib.g3cuda_abi_version.restype = C.c_int32
+    lib.g3cuda_set_kernel.argtypes = [vp, C.c_int]
+    lib.g3cuda_set_kernel.restype = C.c_int
     lib.g3cuda_fp64_peak_tflops.argtypes = [C.c_int]
     lib.g3cuda_fp64_peak_tflops.restype = C.c_double
     _LIB = lib
@@ -68,7 +70,7 @@ def load():
 EXPORTED = ["g3cuda_model_create", "g3cuda_model_free", "g3cuda_n_par", "g3cuda_n_nll", "g3cuda_n_steps",
             "g3cuda_report_len", "g3cuda_eval_batch", "g3cuda_eval_batch_device", "g3cuda_launch_count",
             "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version",
-            "g3cuda_fp64_peak_tflops"]
+            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel"]
 
 
 def _dp(a):
@@ -134,6 +136,10 @@ class Handle:
         rc = self.lib.g3cuda_eval_batch_device(self.h, d_par, int(B), d_tidx or None, int(K), d_nll,
                                                d_comp or None, d_grad or None, stream or None)
         self._check(rc, "g3cuda_eval_batch_device")
+
+    def set_kernel(self, which: int):
+        """0 = automatic, 1 = CTA-, 2 = warp-, 3 = thread-per-evaluation kernel."""
+        self._check(self.lib.g3cuda_set_kernel(self.h, int(which)), "g3cuda_set_kernel")
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.g3cuda_last_kernel_ms(self.h))

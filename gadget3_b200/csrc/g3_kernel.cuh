@@ -55,6 +55,23 @@ struct KArgs {
     int o_g[MAXS], o_gr[MAXS], o_gn[MAXS], o_pws[MAXS], o_rd[MAXS], o_ms[MAXC], o_xslot[MAXX];
     int maxL;
     long long rep_dstart[MAXS]; long long rep_model[MAXC]; long long rep_params;
+    // ---- warp-per-evaluation kernel (g3_warp_kernel.cuh)
+    int w_warp_bytes;                       // shared memory per warp
+    int w_G[MAXS], w_ntile[MAXS];           // columns per tile, tiles per stock
+    int w_ndt, w_dt_len[4], w_step_idt[32]; // distinct step lengths (months) and the one each step uses
+    const unsigned char* w_pred_active;     // [NT] some landing is non-zero at t
+    int w_o_mort, w_o_tot, w_o_mv;
+    int w_mort_off[MAXS], w_o_dw[MAXS], w_o_rw[MAXS], w_tr_off[MAXS], w_mv_off[MAXS], w_inc_steps[MAXS];
+    int w_ts_eoff[MAXTS], w_ts_estr[MAXTS]; // landings table of each (predator, area) accumulator
+    int w_x_kind[MAXX], w_x_unit[MAXX]; unsigned w_x_ppmask[MAXX];
+    const int32_t* w_inc_tr;                // per cell: compact index of its maturation source in s_tn/s_tw, or -1
+    int w_n_agedst; const int4* w_agedst;
+    // ---- thread-per-evaluation kernel (g3_thread_kernel.cuh): workspace entries, [entry][thread]
+    void* t_ws;
+    int t_slot, t_num, t_wgt, t_tn, t_tw, t_mv, t_suit, t_scr, t_ctot;
+    int t_mort[MAXS], t_pw[MAXS], t_g[MAXS], t_gr[MAXS], t_gn[MAXS], t_rd[MAXS], t_rw[MAXS], t_ms[MAXC];
+    const int32_t* t_cellptr;               // [NCOMP][NC + 1] cell-oriented CSR of the collect step
+    const int32_t* t_celldst; const double* t_cellcoef;   // ageing movement: (destination cell, stash index num, stash index wgt, ratio slot)
 };
 
 template <class T> __device__ __forceinline__ T mkpar(const double* spar, const int* seed, int i) {

@@ -1,0 +1,650 @@
+// g3_thread_kernel.cuh -- one THREAD per parameter vector: the production evaluation kernel.
+//
+// Mapping. A lane is an independent evaluation: the 32 lanes of a warp walk the SAME cell of the
+// SAME time step of 32 different parameter vectors. Everything the reference's objective
+// (baseline/multiple-substocks.cpp:692-2161) does for one vector becomes straight scalar code per
+// thread, so
+//   * control flow is warp-uniform by construction (every branch depends on model structure and
+//     the step, never on the lane) and no lane is ever padding;
+//   * nothing is exchanged between lanes: no shuffles, no barriers, no shared-memory staging;
+//     reductions over length/age/stock are serial sums in the reference's own order;
+//   * the data-dependent tiers of logspace_add (g3_math.cuh) rarely diverge, because the 32 lanes
+//     look at the same cell of near-identical populations.
+// State. The per-evaluation working set (stock state, transition buffers, growth/suitability
+// tables, likelihood slabs: a few thousand doubles) lives in a global-memory workspace laid out
+// [entry][thread], so that every access of a warp is one coalesced 256-byte line; it is streamed
+// once per time step: per cell and step the kernel moves ~6 doubles against ~150 fp64
+// instructions, i.e. it is bound by the fp64 pipe, not by HBM (DESIGN.md "roofline").
+// Per step there is ONE fused pass over the cells (predation -> natural mortality -> banded
+// growth with the maturing split -> maturation hand-over -> renewal -> likelihood collection),
+// possible because length growth only looks down the length axis (a register window of n+1
+// source cells per column) and maturation sources are processed before their destinations;
+// plus a totals pre-pass on steps with landings and the ageing pass at the end of a year.
+#pragma once
+#include "g3_kernel.cuh"
+
+namespace g3 {
+
+template <class T> __device__ __forceinline__ T mkpar_g(const double* __restrict__ prow, const int* seed, int i) {
+    T r(prow[i]);
+    if constexpr (Tan<T>::n > 0) {
+#pragma unroll
+        for (int k = 0; k < Tan<T>::n; k++) if (seed[k] == i) r.d[k] = 1.0;
+    }
+    return r;
+}
+
+// slot programs (include/g3cuda_spec.h G3OP_*), parameters read from the vector's row in global memory
+template <class T> __device__ __noinline__ T eval_slot_g(const int32_t* __restrict__ I, const double* __restrict__ R,
+                                                         const double* __restrict__ prow, const int* seed, int slot) {
+    const int32_t* tab = I + I[G3H_SLOT_OFF] + 2 * slot;
+    const int32_t* c = I + tab[0];
+    int n = tab[1];
+    T st[G3_SLOT_STACK];
+    int sp = 0;
+    for (int i = 0; i < n; i++) {
+        int op = c[i];
+        switch (op) {
+        case G3OP_CONST: st[sp++] = T(R[c[++i]]); break;
+        case G3OP_PARAM: st[sp++] = mkpar_g<T>(prow, seed, c[++i]); break;
+        case G3OP_NAN: st[sp++] = T(nan("")); break;
+        case G3OP_ADD: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
+        case G3OP_SUB: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
+        case G3OP_MUL: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
+        case G3OP_DIV: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
+        case G3OP_POW: sp--; st[sp - 1] = xpow(st[sp - 1], st[sp]); break;
+        case G3OP_NEG: st[sp - 1] = -st[sp - 1]; break;
+        case G3OP_EXP: st[sp - 1] = xexp(st[sp - 1]); break;
+        case G3OP_LOG: st[sp - 1] = xlog(st[sp - 1]); break;
+        case G3OP_SQRT: st[sp - 1] = xsqrt(st[sp - 1]); break;
+        case G3OP_AVOID_ZERO: st[sp - 1] = avoid_zero(st[sp - 1]); break;
+        default: break;
+        }
+    }
+    return st[0];
+}
+
+constexpr int TPB = 128;        // threads per block of the thread-per-evaluation kernel
+
+// CB: columns processed side by side (shared table loads, CB independent dependency chains)
+// NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
+// CONSTMAT: some stock matures with g3a_mature_constant (needs a third register window)
+template <class T, int CB, int NW, bool CONSTMAT>
+__global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant__ KArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int32_t* __restrict__ I = A.I;
+    const double* __restrict__ R = A.R;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long NTH = (long long)gridDim.x * blockDim.x;
+    T* __restrict__ ws = reinterpret_cast<T*>(A.t_ws) + gtid;
+#define W(e) ws[(size_t)(e) * (size_t)NTH]
+    T* s_eot = reinterpret_cast<T*>(smem_raw) + threadIdx.x;      // [MAXTS][TPB]: landings / total suitable biomass
+#define EOT(k) s_eot[(k) * TPB]
+
+    const int NS = A.NS, NSTEPS = A.NSTEPS, NT = A.NT;
+    constexpr int NTAN = Tan<T>::n;
+    const int ntiles = NTAN > 0 ? (A.K + NTAN - 1) / NTAN : 1;
+    const double us_power = R[I[G3H_US_ROFF]], us_weight = R[I[G3H_US_ROFF] + 1];
+    const bool have_us = I[G3H_US_N] > 0;
+
+    for (long long work = gtid; work < A.B * ntiles; work += NTH) {
+        const long long b = work / ntiles;
+        const int tile_t = (int)(work - b * ntiles);
+        int seed[NTAN > 0 ? NTAN : 1];
+#pragma unroll
+        for (int k = 0; k < (NTAN > 0 ? NTAN : 1); k++) {
+            int g = tile_t * NTAN + k;
+            seed[k] = (NTAN > 0 && g < A.K) ? A.tangent_idx[g] : -1;
+        }
+        const double* __restrict__ prow = A.par + b * A.NPAR;
+
+        // ---- g3a_time (R/action_time.R:75-91)
+        const double retro = I[G3H_PAR_RETRO] >= 0 ? prow[I[G3H_PAR_RETRO]] : 0.0;
+        const double proj = I[G3H_PAR_PROJECT] >= 0 ? prow[I[G3H_PAR_PROJECT]] : 0.0;
+        const int total_steps = NSTEPS * (I[G3H_END_YEAR] - (int)floor(retro) - I[G3H_START_YEAR] + (int)floor(proj)) + NSTEPS - 1;
+        const bool bad_time = !(retro >= 0.0) || !(proj >= 0.0) || total_steps + 1 > NT;
+
+        for (int i = 0; i < A.NSLOT; i++) W(A.t_slot + i) = eval_slot_g<T>(I, R, prow, seed, i);
+#define SLOT(i) W(A.t_slot + (i))
+
+        // ================= per-evaluation tables
+        for (int q = 0; q < A.NPP; q++) {           // suitability (R/suitability.R:5-13)
+            const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+            const int32_t* Ps = I + I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN;
+            const int32_t* ss = I + Q[G3PP_SUIT_OFF];
+            if (Q[G3PP_SUIT_KIND] == G3SUIT_EXPL50) {
+                const T al = SLOT(ss[0]), l50 = SLOT(ss[1]);
+                for (int l = 0; l < Ps[G3S_L]; l++)
+                    W(A.t_suit + q * A.maxL + l) = 1.0 / (1.0 + xexp(-al * (R[Ps[G3S_MIDLEN_ROFF] + l] - l50)));
+            } else {
+                const T v = SLOT(ss[0]);
+                for (int l = 0; l < Ps[G3S_L]; l++) W(A.t_suit + q * A.maxL + l) = v;
+            }
+        }
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+            const int L = St[G3S_L], ncol = St[G3S_NAGE] * St[G3S_NAREA];
+            const double* midlen = R + St[G3S_MIDLEN_ROFF];
+            const double pdl = R[St[G3S_PLUSDL_ROFF]];
+            // natural mortality factor per column and distinct step length (R/action_naturalmortality.R:26)
+            if (St[G3S_MORT_OFF] >= 0)
+                for (int idt = 0; idt < A.w_ndt; idt++)
+                    for (int col = 0; col < ncol; col++)
+                        W(A.t_mort[s] + idt * ncol + col) = xexp(-SLOT(I[St[G3S_MORT_OFF] + col]) * (A.w_dt_len[idt] / 12.0));
+            // renewal length distribution, normalised, and weight (R/action_renewal.R:56-80)
+            for (int k = 0; k < St[G3S_N_RENEW]; k++) {
+                const int32_t* Rn = I + St[G3S_RENEW_OFF] + k * G3R_LEN;
+                const T mean = SLOT(Rn[G3R_MEAN]), sd = avoid_zero(SLOT(Rn[G3R_SD]));
+                const T wa = SLOT(Rn[G3R_WALPHA]), wb = SLOT(Rn[G3R_WBETA]);
+                T tot(0.0);
+                for (int l = 0; l < L; l++) { T d = dnorm(midlen[l], mean, sd); W(A.t_rd[s] + k * L + l) = d; tot = tot + d; }
+                const T den = avoid_zero(tot);
+                for (int l = 0; l < L; l++) {
+                    W(A.t_rd[s] + k * L + l) = W(A.t_rd[s] + k * L + l) / den * 10000.0;
+                    W(A.t_rw[s] + k * L + l) = wa * xpow(midlen[l], wb);
+                }
+            }
+            const int n2 = St[G3S_GROW_N];
+            if (n2 < 0) continue;
+            const int32_t* gs = I + St[G3S_GROW_OFF];
+            const bool cont = St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0;
+            const int gsz = (n2 + 1) * L;
+            {
+                const T wb = SLOT(gs[4]);
+                for (int l = 0; l < L; l++) W(A.t_pw[s] + l) = xpow(midlen[l], wb);
+            }
+            for (int idt = 0; idt < A.w_ndt; idt++) {
+                const double dt = A.w_dt_len[idt] / 12.0;
+                const T linf = SLOT(gs[0]), kk = 1.0 - xexp(-(SLOT(gs[1])) * dt), beta = avoid_zero(SLOT(gs[2]));
+                T malpha(0.0), ml50(0.0);
+                if (cont) { const int32_t* ms = I + St[G3S_MAT_OFF]; malpha = SLOT(ms[0]); ml50 = SLOT(ms[1]); }
+                // source-oriented band in scratch: [v][x * L + l], v = 0 all, 1 maturing, 2 staying
+                for (int l = 0; l < L; l++) {
+                    // g3a_grow_lengthvbsimple (R/action_grow.R:54) inside the bbinom wrapper (R/action_grow.R:220)
+                    T dl = avoid_zero((linf - midlen[l]) * kk);
+                    T delta = avoid_zero(dl / pdl);
+                    T alpha = (beta * delta) / ((double)n2 - delta);
+                    // growth_bbinom in product form, see g3_kernel.cuh
+                    T g = T(1.0);
+                    for (int j = 0; j < n2; j++) g = g * ((beta + (double)j) / xabs(alpha + beta + (double)j));
+                    T m0(0.0);
+                    if (cont) m0 = 1.0 / (1.0 + xexp(0.0 - malpha * (midlen[l] - ml50)));      // R/action_mature.R:46-72
+                    for (int x = 0; x <= n2; x++) {
+                        W(A.t_scr + x * L + l) = g;
+                        if (cont) {     // g3a_mature_continuous (R/action_mature.R:1-42), beta = 0
+                            T ratio = dif_pminmax_c(m0 * (malpha * (pdl * x)), 0.0, 1.0, 1e5);
+                            W(A.t_scr + gsz + x * L + l) = g * ratio;
+                            W(A.t_scr + 2 * gsz + x * L + l) = g * (1.0 - ratio);
+                        }
+                        if (x < n2)
+                            g = g * ((double)(n2 - x) / (double)(x + 1)) * (xabs(alpha + (double)x) / (beta + (double)(n2 - x - 1)));
+                    }
+                }
+                // destination-oriented band [d][l] = P(l - d -> l), plus-group tail sums folded in (R/action_grow.R:233-271)
+                for (int v = 0; v < (cont ? 3 : 1); v++) {
+                    const int o = (v == 0 ? A.t_g[s] : (v == 1 ? A.t_gr[s] : A.t_gn[s])) + idt * gsz;
+                    for (int d = 0; d <= n2; d++)
+                        for (int j = 0; j < L; j++) {
+                            const int src = j - d;
+                            T g(0.0);
+                            if (src >= 0) {
+                                if (j < L - 1) g = W(A.t_scr + v * gsz + d * L + src);
+                                else for (int x = d; x <= n2; x++) g = g + W(A.t_scr + v * gsz + x * L + src);
+                            }
+                            W(o + d * L + j) = g;
+                        }
+                }
+            }
+        }
+
+        // ================= g3a_initialconditions (R/action_renewal.R:83-163)
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+            const int L = St[G3S_L], c0 = St[G3S_CELL_OFF], ncol = St[G3S_NAGE] * St[G3S_NAREA];
+            const double* midlen = R + St[G3S_MIDLEN_ROFF];
+            for (int col = 0; col < ncol; col++) {
+                if (St[G3S_INIT_OFF] < 0) {
+                    for (int l = 0; l < L; l++) { W(A.t_num + c0 + col * L + l) = T(0.0); W(A.t_wgt + c0 + col * L + l) = T(1.0); }
+                    continue;
+                }
+                const int32_t* sl = I + St[G3S_INIT_OFF] + col * 5;
+                const T mean = SLOT(sl[0]), sd = avoid_zero(SLOT(sl[1])), factor = SLOT(sl[2]), wa = SLOT(sl[3]), wb = SLOT(sl[4]);
+                T tot(0.0);
+                for (int l = 0; l < L; l++) { T d = dnorm(midlen[l], mean, sd); W(A.t_num + c0 + col * L + l) = d; tot = tot + d; }
+                const T den = avoid_zero(tot);                           // normalize_vec, R/aab_env.R:37-41
+                for (int l = 0; l < L; l++) {
+                    const int cell = c0 + col * L + l;
+                    W(A.t_num + cell) = W(A.t_num + cell) / den * 10000.0 * factor;
+                    W(A.t_wgt + cell) = wa * xpow(midlen[l], wb);
+                }
+            }
+        }
+
+        T nll(0.0);
+        for (int i = 0; i < A.NNLL; i++) W(A.t_ctot + i) = T(0.0);
+        // ---- g3l_bounds_penalty (R/likelihood_bounds.R:13-16), cur_time == 0
+        if (A.NBOUND > 0) {
+            T pen(0.0);
+            const double bw = R[I[G3H_BOUND_WS_ROFF]], bs = R[I[G3H_BOUND_WS_ROFF] + 1];
+            for (int i = 0; i < A.NBOUND; i++) {
+                T p = mkpar_g<T>(prow, seed, I[I[G3H_BOUND_OFF] + i]);
+                double lo = R[I[G3H_BOUND_ROFF] + 2 * i], up = R[I[G3H_BOUND_ROFF] + 2 * i + 1];
+                T a = lsa_c(bs * (p - up) / (up - lo), 0.0) + lsa_c(bs * (lo - p) / (up - lo), 0.0);
+                pen = pen + a * a;
+            }
+            nll = nll + bw * pen;
+            W(A.t_ctot + A.NNLL - 1) = pen;
+        }
+        for (int c = 0; c < A.NCOMP; c++) {         // zero the likelihood slabs
+            const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+            bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+            int n = C[G3C_N_DEST] * (si ? C[G3C_N_TIMES] : 1);
+            for (int i = 0; i < n; i++) W(A.t_ms[c] + i) = T(0.0);
+        }
+
+        for (int t = 0; t <= total_steps && !bad_time; t++) {
+            const int step = t % NSTEPS, yidx = t / NSTEPS;
+            const int idt = A.w_step_idt[step];
+            const bool final_step = step == NSTEPS - 1;
+            const bool pred_now = A.w_pred_active[t] != 0;
+            // components collecting at this step (bit c), and whether any of them reads a catch
+            unsigned cact = 0;
+            bool any_catch = false;
+            for (int c = 0; c < A.NCOMP; c++) {
+                const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+                if (I[C[G3C_TIDX_OFF] + t] >= 0 && prow[C[G3C_WEIGHT_PAR]] > 0.0) {
+                    cact |= 1u << c;
+                    if (A.w_x_kind[C[G3C_XBUF]] == 0) any_catch = true;
+                }
+            }
+
+            // ================= g3a_predate step 1: suitable biomass per (predator, area) (R/action_predate.R:314-333)
+            if (pred_now) {
+#pragma unroll
+                for (int k = 0; k < MAXTS; k++) if (k < A.NTS) EOT(k) = T(0.0);
+                for (int s = 0; s < NS; s++) {
+                    const int nq = A.stock_pp_off[s + 1] - A.stock_pp_off[s];
+                    if (nq == 0) continue;
+                    const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+                    const int L = St[G3S_L], nage = St[G3S_NAGE], c0 = St[G3S_CELL_OFF], ncol = nage * St[G3S_NAREA];
+                    for (int col = 0; col < ncol; col++) {
+                        const int ridx = col / nage;
+                        T cs[MAXQ];
+#pragma unroll
+                        for (int j = 0; j < MAXQ; j++) cs[j] = T(0.0);
+                        for (int l = 0; l < L; l++) {
+                            const int cell = c0 + col * L + l;
+                            const T B0 = W(A.t_num + cell) * W(A.t_wgt + cell);
+#pragma unroll
+                            for (int j = 0; j < MAXQ; j++)
+                                if (j < nq) cs[j] = cs[j] + W(A.t_suit + A.stock_pp[A.stock_pp_off[s] + j] * A.maxL + l) * B0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < MAXQ; j++)
+                            if (j < nq) {
+                                const int ts = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + j] * A.maxnarea + ridx];
+                                if (ts >= 0) EOT(ts) = EOT(ts) + cs[j];
+                            }
+                    }
+                }
+                // landings over total suitable biomass: cons = E * (suit / totalsuit)
+#pragma unroll
+                for (int k = 0; k < MAXTS; k++)
+                    if (k < A.NTS) EOT(k) = R[A.w_ts_eoff[k] + (size_t)t * A.w_ts_estr[k]] / EOT(k);
+            }
+
+            // ================= the fused pass, stock by stock, CB columns side by side
+            T us_tot(0.0);
+            for (int s = 0; s < NS; s++) {
+                const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+                const int L = St[G3S_L], nage = St[G3S_NAGE], narea = St[G3S_NAREA], c0 = St[G3S_CELL_OFF], ncol = nage * narea;
+                const int nq = A.stock_pp_off[s + 1] - A.stock_pp_off[s];
+                const bool prey_now = pred_now && nq > 0;
+                const bool is_us = A.us_flag[s] != 0;
+                const int grow_n = St[G3S_GROW_N], mat_kind = St[G3S_MAT_KIND];
+                const bool trans_now = grow_n >= 0 && St[G3S_N_OUT] > 0 && ((St[G3S_TRANS_MASK] >> step) & 1);
+                const bool cont_now = trans_now && mat_kind == G3MAT_CONTINUOUS;
+                const bool const_now = CONSTMAT && trans_now && mat_kind == G3MAT_CONSTANT;
+                const bool has_mort = St[G3S_MORT_OFF] >= 0;
+                const bool inc_now = (A.w_inc_steps[s] >> step) & 1;
+                const int n_renew = St[G3S_N_RENEW];
+                bool ren_now = false;
+                for (int k = 0; k < n_renew; k++) {
+                    int rs = I[St[G3S_RENEW_OFF] + k * G3R_LEN + G3R_RUN_STEP];
+                    ren_now = ren_now || rs == 0 || rs == step + 1;
+                }
+                const bool catch_now = any_catch && nq > 0;
+                if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_now && cact == 0) continue;
+                const int gsz = (grow_n + 1) * L;
+                const int og = (cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz;      // staying part
+                const int ogr = A.t_gr[s] + idt * gsz;                              // maturing part (continuous)
+                const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
+                const int32_t* msl = I + St[G3S_MAT_OFF];
+                T o1(0.0), o2(0.0);
+
+                for (int col0 = 0; col0 < ncol; col0 += CB) {
+                    T wn[CB][NW], ww[CB][NW], wm[CONSTMAT ? CB : 1][CONSTMAT ? NW : 1];       // windows: staying numbers, weights, maturing numbers (constant maturity)
+                    T pwv[NW];
+                    T mortf[CB], agec[CB];
+                    int ridx[CB], aidx[CB];
+                    bool cv[CB];
+#pragma unroll
+                    for (int j = 0; j < CB; j++) {
+                        const int col = col0 + j;
+                        cv[j] = col < ncol;
+                        const int cc = cv[j] ? col : ncol - 1;
+                        ridx[j] = cc / nage; aidx[j] = cc - ridx[j] * nage;
+                        mortf[j] = has_mort ? W(A.t_mort[s] + idt * ncol + cc) : T(1.0);
+                        agec[j] = T(0.0);
+                        if (const_now && msl[2] >= 0) agec[j] = SLOT(msl[2]) * ((double)(St[G3S_MINAGE] + aidx[j]) - SLOT(msl[3]));
+#pragma unroll
+                        for (int d = 0; d < NW; d++) { wn[j][d] = T(0.0); ww[j][d] = T(0.0); if constexpr (CONSTMAT) wm[j][d] = T(0.0); }
+                    }
+#pragma unroll
+                    for (int d = 0; d < NW; d++) pwv[d] = T(0.0);
+
+                    for (int l = 0; l < L; l++) {
+                        // ---- per-length tables, shared by the CB columns
+                        T gt[NW], grt[NW], sq[MAXQ];
+#pragma unroll
+                        for (int d = NW - 1; d > 0; d--) pwv[d] = pwv[d - 1];
+                        if (grow_n >= 0) {
+                            pwv[0] = W(A.t_pw[s] + l);
+#pragma unroll
+                            for (int d = 0; d < NW; d++) {
+                                gt[d] = T(0.0); grt[d] = T(0.0);
+                                if (d <= grow_n && d <= l) {
+                                    gt[d] = W(og + d * L + l);
+                                    if (cont_now) grt[d] = W(ogr + d * L + l);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < MAXQ; j++)
+                            sq[j] = (prey_now && j < nq) ? W(A.t_suit + A.stock_pp[A.stock_pp_off[s] + j] * A.maxL + l) : T(0.0);
+                        T mat_l(0.0);
+                        if (const_now && msl[0] >= 0) mat_l = SLOT(msl[0]) * (R[St[G3S_MIDLEN_ROFF] + l] - SLOT(msl[1]));
+
+#pragma unroll
+                        for (int j = 0; j < CB; j++) {
+                            if (!cv[j]) continue;
+                            const int cell = c0 + (col0 + j) * L + l;
+                            T num = W(A.t_num + cell), wgt = W(A.t_wgt + cell);
+                            T cons[MAXX];
+#pragma unroll
+                            for (int x = 0; x < MAXX; x++) cons[x] = T(0.0);
+                            if (prey_now) {     // R/action_predate.R:335-406
+                                const T B0 = num * wgt;
+                                T tp(0.0), fx[MAXX];
+#pragma unroll
+                                for (int x = 0; x < MAXX; x++) fx[x] = T(0.0);
+#pragma unroll
+                                for (int k = 0; k < MAXQ; k++)
+                                    if (k < nq) {
+                                        const int q = A.stock_pp[A.stock_pp_off[s] + k];
+                                        const int ts = A.pp_tsid[q * A.maxnarea + ridx[j]];
+                                        if (ts >= 0) {
+                                            const T cf = sq[k] * EOT(ts);
+                                            tp = tp + cf * B0;
+                                            if (catch_now) {
+#pragma unroll
+                                                for (int x = 0; x < MAXX; x++) if (x < A.NX && ((A.w_x_ppmask[x] >> q) & 1)) fx[x] = fx[x] + cf;
+                                            }
+                                        }
+                                    }
+                                T cr = tp / avoid_zero(B0);
+                                cr = dif_pmax_c(cr, 0.95, -1e3);
+                                const T tpn = B0 * cr;
+                                num = num * (1.0 - cr);
+                                if (is_us) { o1 = o1 + tp; o2 = o2 + tpn; }
+                                if (catch_now) {
+                                    const T cc = 1.0 / avoid_zero(tp) * tpn * B0;      // consconv * B0
+#pragma unroll
+                                    for (int x = 0; x < MAXX; x++) cons[x] = fx[x] * cc;
+                                }
+                            }
+                            num = num * mortf[j];
+                            T tn(0.0), tw(0.0);
+                            if (grow_n >= 0) {
+                                // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d
+#pragma unroll
+                                for (int d = NW - 1; d > 0; d--) { wn[j][d] = wn[j][d - 1]; ww[j][d] = ww[j][d - 1]; if constexpr (CONSTMAT) wm[j][d] = wm[j][d - 1]; }
+                                ww[j][0] = wgt;
+                                wn[j][0] = num;
+                                if constexpr (CONSTMAT) {
+                                    wm[j][0] = T(0.0);
+                                    if (const_now) {
+                                        // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
+                                        T ratio = 1.0 / (1.0 + xexp(T(0.0) - mat_l - agec[j]));
+                                        wn[j][0] = num * (1.0 - ratio);
+                                        wm[j][0] = num * ratio;
+                                    }
+                                }
+                                T an(0.0), aw(0.0), bn(0.0), bw(0.0);
+#pragma unroll
+                                for (int d = 0; d < NW; d++) {
+                                    const T wsrc = wal * (pwv[0] - pwv[d]) + ww[j][d];
+                                    if (cont_now) {
+                                        const T w = wsrc * wn[j][d];
+                                        an = an + grt[d] * wn[j][d]; aw = aw + grt[d] * w;
+                                        bn = bn + gt[d] * wn[j][d]; bw = bw + gt[d] * w;
+                                    } else if (CONSTMAT && const_now) {
+                                        const T n1 = wm[CONSTMAT ? j : 0][CONSTMAT ? d : 0] * gt[d], n2 = wn[j][d] * gt[d];
+                                        an = an + n1; aw = aw + wsrc * n1;
+                                        bn = bn + n2; bw = bw + wsrc * n2;
+                                    } else {
+                                        const T n2 = wn[j][d] * gt[d];
+                                        bn = bn + n2; bw = bw + wsrc * n2;
+                                    }
+                                }
+                                num = bn; wgt = bw / avoid_zero(bn);
+                                if (trans_now) {
+                                    tn = an; tw = aw / avoid_zero(an);
+                                    W(A.t_tn + A.w_tr_off[s] + cell - c0) = tn;
+                                    W(A.t_tw + A.w_tr_off[s] + cell - c0) = tw;
+                                }
+                            }
+                            // ---- g3a_step_transition (R/action_mature.R:78-134)
+                            if (inc_now) {
+                                const int src = A.w_inc_tr[cell];
+                                if (src >= 0 && ((A.inc_mask[cell] >> step) & 1)) {
+                                    const T moved = W(A.t_tn + src) * SLOT(A.inc_slot[cell]);
+                                    wgt = ratio_add_pop(wgt, num, W(A.t_tw + src), moved);
+                                    num = num + moved;
+                                }
+                            }
+                            if (trans_now) {      // unclaimed remainder moves back (move_remainder = TRUE)
+                                T rem = tn;
+                                for (int k = A.rem_off[cell]; A.rem_slots[k] >= 0; k++) rem = rem - tn * SLOT(A.rem_slots[k]);
+                                num = num + rem;
+                            }
+                            // ---- g3a_renewal (R/action_renewal.R:166-188)
+                            if (ren_now)
+                                for (int r = 0; r < n_renew; r++) {
+                                    const int32_t* Rn = I + St[G3S_RENEW_OFF] + r * G3R_LEN;
+                                    if (aidx[j] == Rn[G3R_AGE_IDX] && (Rn[G3R_RUN_STEP] == 0 || Rn[G3R_RUN_STEP] == step + 1)) {
+                                        const int fs = I[Rn[G3R_FACTOR_OFF] + yidx * narea + ridx[j]];
+                                        if (fs >= 0) {
+                                            const T rn = W(A.t_rd[s] + r * L + l) * SLOT(fs);
+                                            wgt = ratio_add_pop(wgt, num, W(A.t_rw[s] + r * L + l), rn);
+                                            num = num + rn;
+                                        }
+                                    }
+                                }
+                            W(A.t_num + cell) = num; W(A.t_wgt + cell) = wgt;
+                            // ---- g3l_distribution collect (R/likelihood_distribution.R:275-364): scatter this cell
+                            if (cact) {
+                                T xval[MAXX];
+#pragma unroll
+                                for (int x = 0; x < MAXX; x++) {
+                                    xval[x] = T(0.0);
+                                    if (x < A.NX) {
+                                        if (A.w_x_kind[x] == 0) { if (catch_now) xval[x] = A.w_x_unit[x] == 0 ? cons[x] / avoid_zero(wgt) : cons[x]; }
+                                        else xval[x] = A.w_x_unit[x] == 0 ? num : num * wgt;
+                                    }
+                                }
+                                for (int c = 0; c < A.NCOMP; c++) {
+                                    if (!((cact >> c) & 1)) continue;
+                                    const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+                                    const int xb = C[G3C_XBUF];
+                                    T xv(0.0);
+#pragma unroll
+                                    for (int x = 0; x < MAXX; x++) if (x == xb) xv = xval[x];
+                                    const bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+                                    const int base = A.t_ms[c] + (si ? I[C[G3C_TIDX_OFF] + t] * C[G3C_N_DEST] : 0);
+                                    const int32_t* cp = A.t_cellptr + (size_t)c * (A.NC + 1);
+                                    for (int k = cp[cell]; k < cp[cell + 1]; k++)
+                                        W(base + A.t_celldst[k]) = W(base + A.t_celldst[k]) + A.t_cellcoef[k] * xv;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (is_us && prey_now) us_tot = us_tot + (o1 - o2);
+            }
+
+            // ================= g3l_distribution compare (R/likelihood_distribution.R:375-394)
+            for (int c = 0; c < A.NCOMP; c++) {
+                if (!((cact >> c) & 1)) continue;
+                const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+                if (!I[C[G3C_CMP_OFF] + t]) continue;
+                const int ti = I[C[G3C_TIDX_OFF] + t];
+                const int func = C[G3C_FUNC], nd = C[G3C_N_DEST], nt = C[G3C_N_TIMES];
+                const bool si = func == G3F_SI_LOG || func == G3F_SI_LINEAR;
+                const int ms = A.t_ms[c] + (si ? ti * nd : 0);
+                const T weight = mkpar_g<T>(prow, seed, C[G3C_WEIGHT_PAR]);
+                const int nb = C[G3C_N_BINS], nsl = C[G3C_N_SLICES], nag = C[G3C_N_AREAG];
+                T cnll(0.0);
+                bool scored = false;
+                if (func == G3F_SUMOFSQUARES) {     // R/likelihood_distribution.R:3-39
+                    const int per = nsl * nb;
+                    const double* op = A.obsprop + A.obs_off[c] + (size_t)ti * nd;
+                    for (int ag = 0; ag < nag; ag++) {
+                        T tot(0.0);
+                        for (int e = 0; e < per; e++) tot = tot + W(ms + ag * per + e);
+                        const T rt = 1.0 / avoid_zero(tot);
+                        for (int sl = 0; sl < nsl; sl++) {
+                            T v(0.0);
+                            for (int e = 0; e < nb; e++) {
+                                const int i = ag * per + sl * nb + e;
+                                T dlt = W(ms + i) * rt - op[i];
+                                v = v + dlt * dlt;
+                            }
+                            cnll = cnll + v;
+                        }
+                    }
+                    scored = true;
+                } else if (func == G3F_MULTINOMIAL) {   // R/likelihood_distribution.R:41-60
+                    const double eps = R[C[G3C_PARAM_ROFF]];
+                    const double* op = A.obsprop + A.obs_off[c] + (size_t)ti * nd;
+                    T likely(0.0);
+                    for (int sl = 0; sl < nag * nsl; sl++) {
+                        T tot(0.0);
+                        for (int e = 0; e < nb; e++) tot = tot + W(ms + sl * nb + e);
+                        const T at = avoid_zero(tot);
+                        for (int e = 0; e < nb; e++)
+                            likely = likely + op[sl * nb + e] * xlog(dif_pmax_c(W(ms + sl * nb + e) / at, 1.0 / (nb * eps), 1e4));
+                    }
+                    cnll = 2.0 * (-likely + A.obsconst[A.obsconst_off[c] + ti]);
+                    scored = true;
+                } else if (ti == nt - 1) {              // surveyindices: R/likelihood_distribution.R:82-125
+                    const double fa = R[C[G3C_PARAM_ROFF]], fb = R[C[G3C_PARAM_ROFF] + 1];
+                    const int series = A.t_ms[c];
+                    const double* op = A.obsprop + A.obs_off[c];
+                    for (int e = 0; e < nd; e++) {
+                        T sN(0.0); double sI = 0.0;
+                        for (int i = 0; i < nt; i++) {
+                            T mv = W(series + i * nd + e);
+                            sN = sN + (func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv);
+                            sI += op[(size_t)i * nd + e];
+                        }
+                        const T mN = sN / (double)nt;
+                        const double mI = sI / (double)nt;
+                        T beta(fb), alpha(fa);
+                        if (isnan(fb)) {
+                            T sxy(0.0), sxx(0.0);
+                            for (int i = 0; i < nt; i++) {
+                                T mv = W(series + i * nd + e);
+                                T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
+                                sxy = sxy + (op[(size_t)i * nd + e] - mI) * (N - mN); sxx = sxx + (N - mN) * (N - mN);
+                            }
+                            beta = sxy / avoid_zero(sxx);
+                        }
+                        if (isnan(fa)) alpha = mI - beta * mN;
+                        for (int i = 0; i < nt; i++) {
+                            T mv = W(series + i * nd + e);
+                            T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
+                            T r = alpha + beta * N - op[(size_t)i * nd + e];
+                            cnll = cnll + r * r;
+                        }
+                    }
+                    scored = true;
+                }
+                if (scored) {
+                    nll = nll + weight * cnll;
+                    W(A.t_ctot + c) = W(A.t_ctot + c) + cnll;
+                }
+                if (!si) for (int e = 0; e < nd; e++) W(ms + e) = T(0.0);     // zero counters for the next period
+            }
+            // ================= g3l_understocking (R/likelihood_understocking.R:36-46)
+            if (have_us) {
+                T u = (us_power == 2.0) ? us_tot * us_tot : xpow(us_tot, T(us_power));
+                nll = nll + us_weight * u;
+                W(A.t_ctot + A.NNLL - 2) = W(A.t_ctot + A.NNLL - 2) + u;
+            }
+
+            // ================= g3a_age (R/action_age.R:51-85) + movement hand-off
+            if (final_step) {
+                for (int s = 0; s < NS; s++) {
+                    const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+                    if (!St[G3S_AGE_ENABLE]) continue;
+                    const int L = St[G3S_L], nage = St[G3S_NAGE], narea = St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+                    const int age_n_out = St[G3S_AGE_N_OUT];
+                    for (int r = 0; r < narea; r++)
+                        for (int l = 0; l < L; l++) {
+                            const int i = r * L + l;
+                            const int base = c0 + r * nage * L + l;
+                            const int top = base + (nage - 1) * L;
+                            if (age_n_out > 0) { W(A.t_mv + A.w_mv_off[s] + i) = W(A.t_num + top); W(A.t_mv + A.w_mv_off[s] + narea * L + i) = W(A.t_wgt + top); }
+                            if (nage == 1) {
+                                if (age_n_out > 0) W(A.t_num + top) = T(0.0);
+                                continue;
+                            }
+                            if (age_n_out > 0) { W(A.t_num + top) = W(A.t_num + top - L); W(A.t_wgt + top) = W(A.t_wgt + top - L); }
+                            else {
+                                const T n0 = W(A.t_num + top), n1 = W(A.t_num + top - L);
+                                W(A.t_wgt + top) = ratio_add_pop(W(A.t_wgt + top), n0, W(A.t_wgt + top - L), n1);
+                                W(A.t_num + top) = n0 + n1;
+                            }
+                            for (int a = nage - 2; a >= 1; a--) {
+                                W(A.t_num + base + a * L) = W(A.t_num + base + (a - 1) * L);
+                                W(A.t_wgt + base + a * L) = W(A.t_wgt + base + (a - 1) * L);
+                            }
+                            W(A.t_num + base) = T(0.0);
+                        }
+                }
+                for (int i = 0; i < A.w_n_agedst; i++) {
+                    const int4 e = A.w_agedst[i];
+                    const T n0 = W(A.t_num + e.x);
+                    const T moved = W(A.t_mv + e.y) * SLOT(e.w);
+                    W(A.t_wgt + e.x) = ratio_add_pop(W(A.t_wgt + e.x), n0, W(A.t_mv + e.z), moved);
+                    W(A.t_num + e.x) = n0 + moved;
+                }
+            }
+        }   // time loop
+
+        const T out = bad_time ? T(nan("")) : nll;
+        if (tile_t == 0) {
+            A.nll[b] = val(out);
+            if (A.comp) for (int c = 0; c < A.NNLL; c++) A.comp[b * A.NNLL + c] = bad_time ? nan("") : val(W(A.t_ctot + c));
+        }
+        if (NTAN > 0 && A.grad)
+            for (int k = 0; k < NTAN; k++)
+                if (tile_t * NTAN + k < A.K) A.grad[b * A.K + tile_t * NTAN + k] = tan_of(out, k);
+    }
+#undef W
+#undef EOT
+#undef SLOT
+}
+
+}  // namespace g3

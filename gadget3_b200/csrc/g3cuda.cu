@@ -9,10 +9,13 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/g3cuda.h"
 #include "g3_kernel.cuh"
+#include "g3_warp_kernel.cuh"
+#include "g3_thread_kernel.cuh"
 
 namespace {
 
@@ -62,6 +65,12 @@ struct g3cuda_model {
     bool timed = false;
     // smem element counts
     int sm_elems = 0;
+    size_t smem_optin = 0;
+    bool thread_ok = false;             // model fits the thread-per-evaluation kernel
+    int t_entries = 0, t_maxn = 0;      // workspace entries per thread; widest growth band
+    void* t_ws = nullptr; size_t t_ws_bytes = 0;
+    bool warp_ok = false;               // model fits the warp-per-evaluation kernel
+    int force_kernel = 0;               // 0 = automatic, 1 = CTA-per-evaluation kernel, 2 = warp kernel (debug / tests)
 };
 
 namespace {
@@ -116,6 +125,154 @@ Layout make_layout(const g3cuda_model* m, size_t tsize) {
     return out;
 }
 
+// Shared-memory layout of ONE warp's slice for the warp-per-evaluation kernel.
+Layout make_wlayout(const g3cuda_model* m, size_t tsize) {
+    using namespace g3;
+    Layout out; out.a = m->base;
+    KArgs& A = out.a;
+    const int32_t* I = m->I.data();
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += n; return o; };
+    A.sm_par_bytes = (int)(((size_t)A.NPAR * 8 + 15) / 16 * 16);
+    A.o_slot = take(A.NSLOT);
+    A.o_num = take(A.NC); A.o_wgt = take(A.NC);
+    int ntr = 0, nmv = 0, nmort = 0, maxg = 0;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        int ncell = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+        A.w_tr_off[s] = ntr;                 // (same numbering as w_inc_tr, built at model_create)
+        if (St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0) ntr += ncell;
+        A.w_mv_off[s] = nmv;
+        if (St[G3S_AGE_ENABLE] && St[G3S_AGE_N_OUT] > 0) nmv += 2 * St[G3S_NAREA] * St[G3S_L];
+        A.w_mort_off[s] = nmort;
+        if (St[G3S_MORT_OFF] >= 0) nmort += St[G3S_NAGE] * St[G3S_NAREA] * A.w_ndt;
+    }
+    A.o_tn = take(ntr); A.o_tw = take(ntr);
+    A.o_alt = A.any_const_mat ? take(A.NC) : A.o_tn;
+    A.w_o_mv = take(nmv);
+    A.w_o_mort = take(nmort);
+    for (int x = 0; x < MAXX; x++) A.o_xslot[x] = x < A.NX ? take(A.NC) : -1;
+    for (int s = 0; s < A.NS; s++) A.o_pws[s] = take(I[I[G3H_STOCK_OFF] + s * G3S_LEN + G3S_L]);
+    A.o_suit = take(A.NPP * A.maxL);
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        int n = St[G3S_GROW_N], L = St[G3S_L];
+        A.o_rd[s] = take(St[G3S_N_RENEW] * L);
+        A.w_o_rw[s] = take(St[G3S_N_RENEW] * L);
+        if (n < 0) { A.o_g[s] = A.o_gr[s] = A.o_gn[s] = A.w_o_dw[s] = 0; continue; }
+        int g = (n + 1) * L; maxg = std::max(maxg, g);
+        A.w_o_dw[s] = take(g);
+        A.o_g[s] = take(g * A.w_ndt);
+        if (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0) { A.o_gr[s] = take(g * A.w_ndt); A.o_gn[s] = take(g * A.w_ndt); }
+        else { A.o_gr[s] = A.o_gn[s] = A.o_g[s]; }
+    }
+    A.o_gscr = take(std::max(3 * maxg, 32));
+    for (int c = 0; c < A.NCOMP; c++) {
+        const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+        bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+        A.o_ms[c] = take(C[G3C_N_DEST] * (si ? C[G3C_N_TIMES] : 1));
+    }
+    A.w_o_tot = take(MAXTS + A.NNLL);
+    out.bytes = ((size_t)A.sm_par_bytes + (size_t)off * tsize + 15) / 16 * 16;
+    A.w_warp_bytes = (int)out.bytes;
+    return out;
+}
+
+// Workspace entries of the thread-per-evaluation kernel (one T per entry per thread).
+int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
+    using namespace g3;
+    const int32_t* I = m->I.data();
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += n; return o; };
+    A.t_slot = take(A.NSLOT);
+    A.t_num = take(A.NC); A.t_wgt = take(A.NC);
+    int ntr = 0, nmv = 0, maxg = 0;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        int ncell = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+        A.w_tr_off[s] = ntr;
+        if (St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0) ntr += ncell;
+        A.w_mv_off[s] = nmv;
+        if (St[G3S_AGE_ENABLE] && St[G3S_AGE_N_OUT] > 0) nmv += 2 * St[G3S_NAREA] * St[G3S_L];
+    }
+    A.t_tn = take(ntr); A.t_tw = take(ntr); A.t_mv = take(nmv);
+    A.t_suit = take(A.NPP * A.maxL);
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        int n = St[G3S_GROW_N], L = St[G3S_L];
+        A.t_mort[s] = take(St[G3S_MORT_OFF] >= 0 ? St[G3S_NAGE] * St[G3S_NAREA] * A.w_ndt : 0);
+        A.t_rd[s] = take(St[G3S_N_RENEW] * L);
+        A.t_rw[s] = take(St[G3S_N_RENEW] * L);
+        A.t_pw[s] = take(n >= 0 ? L : 0);
+        if (n < 0) { A.t_g[s] = A.t_gr[s] = A.t_gn[s] = 0; continue; }
+        int g = (n + 1) * L; maxg = std::max(maxg, g);
+        A.t_g[s] = take(g * A.w_ndt);
+        if (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0) { A.t_gr[s] = take(g * A.w_ndt); A.t_gn[s] = take(g * A.w_ndt); }
+        else { A.t_gr[s] = A.t_gn[s] = A.t_g[s]; }
+    }
+    A.t_scr = take(3 * maxg);
+    for (int c = 0; c < A.NCOMP; c++) {
+        const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+        bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+        A.t_ms[c] = take(C[G3C_N_DEST] * (si ? C[G3C_N_TIMES] : 1));
+    }
+    A.t_ctot = take(A.NNLL);
+    return off;
+}
+
+template <class T, int CB, int NW, bool CM>
+int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStream_t st) {
+    auto kern = g3::eval_thread_kernel<T, CB, NW, CM>;
+    const size_t smem = sizeof(T) * g3::MAXTS * g3::TPB;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g3::TPB, smem));
+    if (per_sm < 1) return fail(G3CUDA_EUNSUPP, "thread kernel does not fit one SM");
+    long long grid = std::min<long long>((work + g3::TPB - 1) / g3::TPB, (long long)per_sm * m->num_sms);
+    if (grid < 1) grid = 1;
+    const size_t need = (size_t)m->t_entries * sizeof(T) * (size_t)grid * g3::TPB;
+    if (need > m->t_ws_bytes) {
+        // the workspace may still be in use by an earlier asynchronous launch on another stream
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (m->t_ws) cudaFree(m->t_ws);
+        m->t_ws = nullptr; m->t_ws_bytes = 0;
+        if (cudaMalloc(&m->t_ws, need) != cudaSuccess) { cudaGetLastError(); return fail(G3CUDA_ENOMEM, "cudaMalloc of the %zu-byte evaluation workspace failed", need); }
+        m->t_ws_bytes = need;
+    }
+    A.t_ws = m->t_ws;
+    kern<<<(unsigned)grid, g3::TPB, smem, st>>>(A);
+    CUDA_TRY(cudaGetLastError());
+    m->launches++;
+    return G3CUDA_OK;
+}
+
+template <class T>
+int launch_thread(g3cuda_model* m, g3::KArgs& A, long long work, cudaStream_t st) {
+    const bool cm = A.any_const_mat != 0;
+    if (m->t_maxn <= 4) {
+        if (cm) return launch_thread_variant<T, 1, 5, true>(m, A, work, st);
+        return launch_thread_variant<T, 1, 5, false>(m, A, work, st);
+    }
+    if (cm) return launch_thread_variant<T, 1, 16, true>(m, A, work, st);
+    return launch_thread_variant<T, 1, 16, false>(m, A, work, st);
+}
+
+template <class T, int WPC>
+int launch_warp_variant(g3cuda_model* m, const Layout& lay, long long work, cudaStream_t st) {
+    auto kern = g3::eval_warp_kernel<T, WPC>;
+    size_t bytes = lay.bytes * WPC;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WPC * 32, bytes));
+    if (per_sm < 1) return fail(G3CUDA_EUNSUPP, "warp kernel does not fit one SM: %zu bytes of shared memory per CTA", bytes);
+    long long grid = std::min<long long>((work + WPC - 1) / WPC, (long long)per_sm * m->num_sms);
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, WPC * 32, bytes, st>>>(lay.a);
+    CUDA_TRY(cudaGetLastError());
+    m->launches++;
+    return G3CUDA_OK;
+}
+
 template <class T, int MAXT>
 int launch_variant(g3cuda_model* m, const Layout& lay, int nblocks_hint, cudaStream_t st) {
     auto kern = g3::eval_kernel<T, MAXT>;
@@ -133,6 +290,22 @@ int launch_variant(g3cuda_model* m, const Layout& lay, int nblocks_hint, cudaStr
 
 template <class T>
 int launch(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStream_t st) {
+    const bool is_double = std::is_same<T, double>::value;
+    if (m->thread_ok && !call.report && (m->force_kernel == 0 || m->force_kernel == 3) && (is_double || m->force_kernel == 3)) {
+        g3::KArgs a = m->base;
+        a.par = call.par; a.B = call.B; a.tangent_idx = call.tangent_idx; a.K = call.K;
+        a.nll = call.nll; a.comp = call.comp; a.grad = call.grad; a.report = nullptr;
+        return launch_thread<T>(m, a, work, st);
+    }
+    if (m->warp_ok && !call.report && m->force_kernel != 1 && (is_double || m->force_kernel == 2)) {
+        Layout lay = make_wlayout(m, sizeof(T));
+        lay.a.par = call.par; lay.a.B = call.B; lay.a.tangent_idx = call.tangent_idx; lay.a.K = call.K;
+        lay.a.nll = call.nll; lay.a.comp = call.comp; lay.a.grad = call.grad; lay.a.report = nullptr;
+        if (lay.bytes * 2 <= m->smem_optin) {
+            if (lay.bytes * 4 <= m->smem_optin / 2) return launch_warp_variant<T, 4>(m, lay, work, st);
+            return launch_warp_variant<T, 2>(m, lay, work, st);
+        }
+    }
     Layout lay = make_layout(m, sizeof(T));
     // per-call fields
     lay.a.par = call.par; lay.a.B = call.B; lay.a.tangent_idx = call.tangent_idx; lay.a.K = call.K;
@@ -224,7 +397,7 @@ void g3cuda_model_free(g3cuda_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (void* p : m->owned) cudaFree(p);
-    for (void* p : {(void*)m->d_par, (void*)m->d_nll, (void*)m->d_comp, (void*)m->d_grad, (void*)m->d_tidx, (void*)m->d_report, (void*)m->d_out})
+    for (void* p : {(void*)m->d_par, (void*)m->d_nll, (void*)m->d_comp, (void*)m->d_grad, (void*)m->d_tidx, (void*)m->d_report, (void*)m->d_out, m->t_ws})
         if (p) cudaFree(p);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
@@ -344,6 +517,98 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     A.stock_pp_off[A.NS] = ppo;
     for (int i = 0; i < I[G3H_US_N]; i++) A.us_flag[I[I[G3H_US_OFF] + i]] = 1;
 
+    // ---- warp-per-evaluation kernel: tiling, distinct step lengths, compact hand-over tables
+    m->warp_ok = A.NPP <= 32;
+    {
+        A.w_ndt = 0;
+        for (int st = 0; st < A.NSTEPS; st++) {
+            int len = I[I[G3H_STEPLEN_OFF] + st], k = 0;
+            while (k < A.w_ndt && A.w_dt_len[k] != len) k++;
+            if (k == A.w_ndt) { if (A.w_ndt < 4) A.w_dt_len[A.w_ndt++] = len; else { m->warp_ok = false; k = 0; } }
+            A.w_step_idt[st] = k;
+        }
+        std::vector<int32_t> tr_of_cell(A.NC, -1), inc_tr(A.NC, -1);
+        int ntr = 0, nmv = 0;
+        std::vector<int> mv_off(A.NS, 0);
+        for (int s = 0; s < A.NS; s++) {
+            const int32_t* St = stock(s);
+            int L = St[G3S_L], ncell = L * St[G3S_NAGE] * St[G3S_NAREA];
+            if (L > 32) { m->warp_ok = false; A.w_G[s] = 1; A.w_ntile[s] = 0; }
+            else { A.w_G[s] = 32 / L; A.w_ntile[s] = (St[G3S_NAGE] * St[G3S_NAREA] + A.w_G[s] - 1) / A.w_G[s]; }
+            if (St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0) { for (int i = 0; i < ncell; i++) tr_of_cell[St[G3S_CELL_OFF] + i] = ntr + i; ntr += ncell; }
+            mv_off[s] = nmv;
+            if (St[G3S_AGE_ENABLE] && St[G3S_AGE_N_OUT] > 0) nmv += 2 * St[G3S_NAREA] * L;
+            A.w_inc_steps[s] = 0;
+        }
+        for (int c = 0; c < A.NC; c++) if (inc_src[c] >= 0) {
+            inc_tr[c] = tr_of_cell[inc_src[c]];
+            A.w_inc_steps[cell[c].x] |= inc_mask[c];
+        }
+        std::vector<int4> agedst;
+        for (int c = 0; c < A.NC; c++) if (age_src[c] >= 0) {
+            int src = age_src[c], ss = cell[src].x;
+            const int32_t* St = stock(ss);
+            int L = St[G3S_L], i = cell[src].w * L + cell[src].y;       // (area idx, l) of the oldest column
+            agedst.push_back(make_int4(c, mv_off[ss] + i, mv_off[ss] + St[G3S_NAREA] * L + i, age_slot[c]));
+        }
+        A.w_n_agedst = (int)agedst.size();
+        int4* d_agedst = dev_copy(agedst); int32_t* d_inc_tr = dev_copy(inc_tr);
+        if (!d_agedst || !d_inc_tr) return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
+        m->owned.push_back(d_agedst); m->owned.push_back(d_inc_tr);
+        A.w_agedst = d_agedst; A.w_inc_tr = d_inc_tr;
+        // accumulators of (predator, area): where their landings live
+        std::vector<unsigned char> pact(A.NT, 0);
+        for (int p = 0; p < I[G3H_NPRED]; p++) {
+            const int32_t* P = I + I[G3H_PRED_OFF] + p * G3P_LEN;
+            for (int k = 0; k < P[G3P_NAREA]; k++) {
+                A.w_ts_eoff[pred_ts_base[p] + k] = P[G3P_E_ROFF] + k;
+                A.w_ts_estr[pred_ts_base[p] + k] = P[G3P_NAREA];
+                for (int t = 0; t < A.NT; t++) if (R[P[G3P_E_ROFF] + (size_t)t * P[G3P_NAREA] + k] != 0.0) pact[t] = 1;
+            }
+        }
+        unsigned char* d_pact = dev_copy(pact);
+        if (!d_pact) return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
+        m->owned.push_back(d_pact); A.w_pred_active = d_pact;
+        for (int x = 0; x < A.NX; x++) {
+            const int32_t* X = I + I[G3H_XBUF_OFF] + x * G3X_LEN;
+            A.w_x_kind[x] = X[G3X_KIND]; A.w_x_unit[x] = X[G3X_UNIT]; A.w_x_ppmask[x] = 0;
+            for (int j = 0; j < X[G3X_N_PP]; j++) { int q = I[X[G3X_PP_OFF] + j]; if (q < 32) A.w_x_ppmask[x] |= 1u << q; }
+        }
+    }
+
+    // ---- thread-per-evaluation kernel: workspace layout, cell-oriented collect CSR, ordering check
+    {
+        m->thread_ok = A.NPP <= 32 && A.w_ndt <= 4 && A.NCOMP <= 32;
+        m->t_maxn = 0;
+        for (int s = 0; s < A.NS; s++) m->t_maxn = std::max(m->t_maxn, stock(s)[G3S_GROW_N]);
+        if (m->t_maxn > 15) m->thread_ok = false;
+        // the fused pass hands maturing fish over within one sweep: sources must come before destinations
+        for (int c = 0; c < A.NC; c++) if (inc_src[c] >= 0 && cell[inc_src[c]].x >= cell[c].x) m->thread_ok = false;
+        m->t_entries = make_tlayout(m, A);
+        std::vector<int32_t> cptr, cdst; std::vector<double> ccoef;
+        for (int c = 0; c < A.NCOMP; c++) {
+            const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+            std::vector<std::vector<std::pair<int, double>>> per_cell(A.NC);
+            if (C[G3C_MODE] == 0) {
+                const int32_t* ptr = I + C[G3C_CSR_PTR_OFF]; const int32_t* idx = I + C[G3C_CSR_IDX_OFF];
+                const double* cf = R + C[G3C_CSR_COEF_ROFF];
+                for (int e = 0; e < C[G3C_N_DEST]; e++) for (int j = ptr[e]; j < ptr[e + 1]; j++) per_cell[idx[j]].push_back({e, cf[j]});
+            } else {
+                const int32_t* cd = I + C[G3C_CELL_DEST_OFF]; const double* cf = R + C[G3C_CELL_COEF_ROFF];
+                for (int i = 0; i < A.NC; i++) if (cd[i] >= 0) per_cell[i].push_back({cd[i], cf[i]});
+            }
+            for (int i = 0; i < A.NC; i++) {
+                cptr.push_back((int32_t)cdst.size());
+                for (auto& pr : per_cell[i]) { cdst.push_back(pr.first); ccoef.push_back(pr.second); }
+            }
+            cptr.push_back((int32_t)cdst.size());
+        }
+        int32_t* d_cptr = dev_copy(cptr); int32_t* d_cdst = dev_copy(cdst); double* d_ccoef = dev_copy(ccoef);
+        if (!d_cptr || !d_cdst || !d_ccoef) return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
+        m->owned.push_back(d_cptr); m->owned.push_back(d_cdst); m->owned.push_back(d_ccoef);
+        A.t_cellptr = d_cptr; A.t_celldst = d_cdst; A.t_cellcoef = d_ccoef;
+    }
+
     // ---- observation terms that do not depend on parameters
     std::vector<double> obsprop, obsconst;
     int maxnd = 0, maxnt = 0;
@@ -401,6 +666,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     m->num_sms = prop.multiProcessorCount;
+    m->smem_optin = prop.sharedMemPerBlockOptin;
     auto up = [&](auto& vec) { auto* d = dev_copy(vec); if (d) m->owned.push_back((void*)d); return d; };
     A.I = up(m->I); A.R = up(m->R); A.cell = up(cell);
     A.inc_src = up(inc_src); A.inc_slot = up(inc_slot); A.inc_mask = up(inc_mask);
@@ -479,6 +745,14 @@ int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B, const int32
     if (want_grad) CUDA_TRY(cudaMemcpyAsync(grad, m->d_grad, sizeof(double) * B * K, cudaMemcpyDeviceToHost, m->stream));
     cudaError_t e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) return fail(G3CUDA_ECUDA, "evaluation failed: %s", cudaGetErrorString(e));
+    return G3CUDA_OK;
+}
+
+int g3cuda_set_kernel(g3cuda_model* m, int which) {
+    if (!m || which < 0 || which > 3) return fail(G3CUDA_EINVAL, "bad argument");
+    if (which == 3 && !m->thread_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the thread-per-evaluation kernel");
+    if (which == 2 && !m->warp_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the warp-per-evaluation kernel");
+    m->force_kernel = which;
     return G3CUDA_OK;
 }
 

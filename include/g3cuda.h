@@ -81,6 +81,12 @@ int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B,
                              double* d_nll, double* d_nll_comp, double* d_grad,
                              void* stream);
 
+/* Kernel selection, for tests and profiling: 0 = automatic (default), 1 = CTA-per-evaluation
+ * kernel, 2 = warp-per-evaluation kernel, 3 = thread-per-evaluation kernel (G3CUDA_EUNSUPP if
+ * the model does not fit the requested one).
+ * Both are CUDA; there is no CPU path to select. */
+int g3cuda_set_kernel(g3cuda_model* m, int which);
+
 /* Number of kernels launched by this handle so far (bench.py gpu_launches). */
 int64_t g3cuda_launch_count(const g3cuda_model* m);
 
