@@ -64,10 +64,13 @@ template <class T> __device__ __noinline__ T eval_slot_g(const int32_t* __restri
     return st[0];
 }
 
-constexpr int TPB = 128;        // threads per block of the thread-per-evaluation kernel
+#ifndef G3_TPB
+#define G3_TPB 512
+#endif
+constexpr int TPB = G3_TPB;     // LARGEST block of the thread-per-evaluation kernel (one block per SM; the launch
+                                // picks blockDim <= TPB so that the batch splits into equally full waves)
 
-// CB: columns processed side by side (shared table loads, CB independent dependency chains)
-// NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
+// CB: unused (kept for the launch table); NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
 // CONSTMAT: some stock matures with g3a_mature_constant (needs a third register window)
 template <class T, int CB, int NW, bool CONSTMAT>
 __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant__ KArgs A) {
@@ -78,8 +81,8 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
     const long long NTH = (long long)gridDim.x * blockDim.x;
     T* __restrict__ ws = reinterpret_cast<T*>(A.t_ws) + gtid;
 #define W(e) ws[(size_t)(e) * (size_t)NTH]
-    T* s_eot = reinterpret_cast<T*>(smem_raw) + threadIdx.x;      // [MAXTS][TPB]: landings / total suitable biomass
-#define EOT(k) s_eot[(k) * TPB]
+    T* s_eot = reinterpret_cast<T*>(smem_raw) + threadIdx.x;      // [MAXTS][blockDim]: landings / total suitable biomass
+#define EOT(k) s_eot[(k) * blockDim.x]
 
     const int NS = A.NS, NSTEPS = A.NSTEPS, NT = A.NT;
     constexpr int NTAN = Tan<T>::n;
@@ -87,7 +90,12 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
     const double us_power = R[I[G3H_US_ROFF]], us_weight = R[I[G3H_US_ROFF] + 1];
     const bool have_us = I[G3H_US_N] > 0;
 
-    for (long long work = gtid; work < A.B * ntiles; work += NTH) {
+    // Every thread of a block runs the same trip counts (threads past the end of the batch redo
+    // vector 0 without writing), so that the block can re-align its warps once per time step:
+    // warps that execute the same code at the same time share instruction fetches.
+    for (long long base0 = (long long)blockIdx.x * blockDim.x; base0 < A.B * ntiles; base0 += NTH) {
+        const bool live = base0 + threadIdx.x < A.B * ntiles;
+        const long long work = live ? base0 + threadIdx.x : 0;
         const long long b = work / ntiles;
         const int tile_t = (int)(work - b * ntiles);
         int seed[NTAN > 0 ? NTAN : 1];
@@ -242,7 +250,9 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
             for (int i = 0; i < n; i++) W(A.t_ms[c] + i) = T(0.0);
         }
 
-        for (int t = 0; t <= total_steps && !bad_time; t++) {
+        for (int t = 0; t < NT; t++) {
+            __syncthreads();
+            if (t > total_steps || bad_time) continue;
             const int step = t % NSTEPS, yidx = t / NSTEPS;
             const int idt = A.w_step_idt[step];
             const bool final_step = step == NSTEPS - 1;
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                     if (k < A.NTS) EOT(k) = R[A.w_ts_eoff[k] + (size_t)t * A.w_ts_estr[k]] / EOT(k);
             }
 
-            // ================= the fused pass, stock by stock, CB columns side by side
+            // ================= the fused pass, stock by stock, column by column, up the length axis
             T us_tot(0.0);
             for (int s = 0; s < NS; s++) {
                 const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
@@ -308,194 +318,173 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                 const bool has_mort = St[G3S_MORT_OFF] >= 0;
                 const bool inc_now = (A.w_inc_steps[s] >> step) & 1;
                 const int n_renew = St[G3S_N_RENEW];
-                bool ren_now = false;
+                int ren_mask = 0;       // renewal records that run at this step
                 for (int k = 0; k < n_renew; k++) {
                     int rs = I[St[G3S_RENEW_OFF] + k * G3R_LEN + G3R_RUN_STEP];
-                    ren_now = ren_now || rs == 0 || rs == step + 1;
+                    if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
                 }
                 const bool catch_now = any_catch && nq > 0;
-                if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_now && cact == 0) continue;
+                if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_mask && cact == 0) continue;
                 const int gsz = (grow_n + 1) * L;
-                const int og = (cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz;      // staying part
-                const int ogr = A.t_gr[s] + idt * gsz;                              // maturing part (continuous)
                 const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
                 const int32_t* msl = I + St[G3S_MAT_OFF];
+                const size_t LN = (size_t)L * NTH;
+                const T* const gbase = ws + (size_t)((cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz) * NTH;    // staying part
+                const T* const grbase = ws + (size_t)(A.t_gr[s] + idt * gsz) * NTH;                             // maturing part
+                // collect vectors fed by each predator of this stock
+                unsigned kx[MAXQ];
+#pragma unroll
+                for (int k = 0; k < MAXQ; k++) {
+                    kx[k] = 0;
+                    if (k < nq) for (int x = 0; x < A.NX; x++) if ((A.w_x_ppmask[x] >> A.stock_pp[A.stock_pp_off[s] + k]) & 1) kx[k] |= 1u << x;
+                }
                 T o1(0.0), o2(0.0);
 
-                for (int col0 = 0; col0 < ncol; col0 += CB) {
-                    T wn[CB][NW], ww[CB][NW], wm[CONSTMAT ? CB : 1][CONSTMAT ? NW : 1];       // windows: staying numbers, weights, maturing numbers (constant maturity)
-                    T pwv[NW];
-                    T mortf[CB], agec[CB];
-                    int ridx[CB], aidx[CB];
-                    bool cv[CB];
+                for (int col = 0; col < ncol; col++) {
+                    const int ridx = col / nage, aidx = col - ridx * nage;
+                    const T mortf = has_mort ? W(A.t_mort[s] + idt * ncol + col) : T(1.0);
+                    T agec(0.0);
+                    if (const_now && msl[2] >= 0) agec = SLOT(msl[2]) * ((double)(St[G3S_MINAGE] + aidx) - SLOT(msl[3]));
+                    int tsk[MAXQ];
 #pragma unroll
-                    for (int j = 0; j < CB; j++) {
-                        const int col = col0 + j;
-                        cv[j] = col < ncol;
-                        const int cc = cv[j] ? col : ncol - 1;
-                        ridx[j] = cc / nage; aidx[j] = cc - ridx[j] * nage;
-                        mortf[j] = has_mort ? W(A.t_mort[s] + idt * ncol + cc) : T(1.0);
-                        agec[j] = T(0.0);
-                        if (const_now && msl[2] >= 0) agec[j] = SLOT(msl[2]) * ((double)(St[G3S_MINAGE] + aidx[j]) - SLOT(msl[3]));
+                    for (int k = 0; k < MAXQ; k++) tsk[k] = (prey_now && k < nq) ? A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx] : -1;
+                    // renewal into this column at this step: record and factor
+                    int ren_r = -1; T ren_f(0.0);
+                    for (int r = 0; r < n_renew; r++)
+                        if (((ren_mask >> r) & 1) && aidx == I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_AGE_IDX]) {
+                            const int fs = I[I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * narea + ridx];
+                            if (fs >= 0) { ren_r = r; ren_f = SLOT(fs); }    // (one renewal per column and step)
+                        }
+                    T wn[NW], ww[NW], wm[CONSTMAT ? NW : 1], pwv[NW];   // windows: staying numbers, weights, maturing numbers, l^wbeta
 #pragma unroll
-                        for (int d = 0; d < NW; d++) { wn[j][d] = T(0.0); ww[j][d] = T(0.0); if constexpr (CONSTMAT) wm[j][d] = T(0.0); }
-                    }
-#pragma unroll
-                    for (int d = 0; d < NW; d++) pwv[d] = T(0.0);
+                    for (int d = 0; d < NW; d++) { wn[d] = T(0.0); ww[d] = T(0.0); pwv[d] = T(0.0); if constexpr (CONSTMAT) wm[d] = T(0.0); }
+                    const int cell0 = c0 + col * L;
+                    T* pn = ws + (size_t)(A.t_num + cell0) * NTH;
+                    T* pw_ = ws + (size_t)(A.t_wgt + cell0) * NTH;
+                    T* ptn = ws + (size_t)(A.t_tn + A.w_tr_off[s] + col * L) * NTH;
+                    T* ptw = ws + (size_t)(A.t_tw + A.w_tr_off[s] + col * L) * NTH;
+                    const T* ppw = ws + (size_t)A.t_pw[s] * NTH;
+                    const T* pg = gbase;
+                    const T* pgr = grbase;
 
-                    for (int l = 0; l < L; l++) {
-                        // ---- per-length tables, shared by the CB columns
-                        T gt[NW], grt[NW], sq[MAXQ];
+                    for (int l = 0; l < L; l++, pn += NTH, pw_ += NTH, ptn += NTH, ptw += NTH, ppw += NTH, pg += NTH, pgr += NTH) {
+                        const int cell = cell0 + l;
+                        T num = *pn, wgt = *pw_;
+                        T cons[MAXX];
 #pragma unroll
-                        for (int d = NW - 1; d > 0; d--) pwv[d] = pwv[d - 1];
-                        if (grow_n >= 0) {
-                            pwv[0] = W(A.t_pw[s] + l);
+                        for (int x = 0; x < MAXX; x++) cons[x] = T(0.0);
+                        if (prey_now) {     // R/action_predate.R:335-406
+                            const T B0 = num * wgt;
+                            T tp(0.0), fx[MAXX];
 #pragma unroll
-                            for (int d = 0; d < NW; d++) {
-                                gt[d] = T(0.0); grt[d] = T(0.0);
-                                if (d <= grow_n && d <= l) {
-                                    gt[d] = W(og + d * L + l);
-                                    if (cont_now) grt[d] = W(ogr + d * L + l);
+                            for (int x = 0; x < MAXX; x++) fx[x] = T(0.0);
+#pragma unroll
+                            for (int k = 0; k < MAXQ; k++)
+                                if (tsk[k] >= 0) {
+                                    const T cf = W(A.t_suit + A.stock_pp[A.stock_pp_off[s] + k] * A.maxL + l) * EOT(tsk[k]);
+                                    tp = tp + cf * B0;
+                                    if (catch_now) {
+#pragma unroll
+                                        for (int x = 0; x < MAXX; x++) if ((kx[k] >> x) & 1) fx[x] = fx[x] + cf;
+                                    }
                                 }
+                            T cr = tp / avoid_zero(B0);
+                            cr = dif_pmax_c(cr, 0.95, -1e3);
+                            const T tpn = B0 * cr;
+                            num = num * (1.0 - cr);
+                            if (is_us) { o1 = o1 + tp; o2 = o2 + tpn; }
+                            if (catch_now) {
+                                const T cc = 1.0 / avoid_zero(tp) * tpn * B0;      // consconv * B0
+#pragma unroll
+                                for (int x = 0; x < MAXX; x++) cons[x] = fx[x] * cc;
                             }
                         }
+                        num = num * mortf;
+                        T tn(0.0);
+                        if (grow_n >= 0) {
+                            // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d
 #pragma unroll
-                        for (int j = 0; j < MAXQ; j++)
-                            sq[j] = (prey_now && j < nq) ? W(A.t_suit + A.stock_pp[A.stock_pp_off[s] + j] * A.maxL + l) : T(0.0);
-                        T mat_l(0.0);
-                        if (const_now && msl[0] >= 0) mat_l = SLOT(msl[0]) * (R[St[G3S_MIDLEN_ROFF] + l] - SLOT(msl[1]));
-
-#pragma unroll
-                        for (int j = 0; j < CB; j++) {
-                            if (!cv[j]) continue;
-                            const int cell = c0 + (col0 + j) * L + l;
-                            T num = W(A.t_num + cell), wgt = W(A.t_wgt + cell);
-                            T cons[MAXX];
-#pragma unroll
-                            for (int x = 0; x < MAXX; x++) cons[x] = T(0.0);
-                            if (prey_now) {     // R/action_predate.R:335-406
-                                const T B0 = num * wgt;
-                                T tp(0.0), fx[MAXX];
-#pragma unroll
-                                for (int x = 0; x < MAXX; x++) fx[x] = T(0.0);
-#pragma unroll
-                                for (int k = 0; k < MAXQ; k++)
-                                    if (k < nq) {
-                                        const int q = A.stock_pp[A.stock_pp_off[s] + k];
-                                        const int ts = A.pp_tsid[q * A.maxnarea + ridx[j]];
-                                        if (ts >= 0) {
-                                            const T cf = sq[k] * EOT(ts);
-                                            tp = tp + cf * B0;
-                                            if (catch_now) {
-#pragma unroll
-                                                for (int x = 0; x < MAXX; x++) if (x < A.NX && ((A.w_x_ppmask[x] >> q) & 1)) fx[x] = fx[x] + cf;
-                                            }
-                                        }
-                                    }
-                                T cr = tp / avoid_zero(B0);
-                                cr = dif_pmax_c(cr, 0.95, -1e3);
-                                const T tpn = B0 * cr;
-                                num = num * (1.0 - cr);
-                                if (is_us) { o1 = o1 + tp; o2 = o2 + tpn; }
-                                if (catch_now) {
-                                    const T cc = 1.0 / avoid_zero(tp) * tpn * B0;      // consconv * B0
-#pragma unroll
-                                    for (int x = 0; x < MAXX; x++) cons[x] = fx[x] * cc;
+                            for (int d = NW - 1; d > 0; d--) { wn[d] = wn[d - 1]; ww[d] = ww[d - 1]; pwv[d] = pwv[d - 1]; if constexpr (CONSTMAT) wm[d] = wm[d - 1]; }
+                            ww[0] = wgt; wn[0] = num; pwv[0] = *ppw;
+                            if constexpr (CONSTMAT) {
+                                wm[0] = T(0.0);
+                                if (const_now) {
+                                    // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
+                                    T mat_l(0.0);
+                                    if (msl[0] >= 0) mat_l = SLOT(msl[0]) * (R[St[G3S_MIDLEN_ROFF] + l] - SLOT(msl[1]));
+                                    T ratio = 1.0 / (1.0 + xexp(T(0.0) - mat_l - agec));
+                                    wn[0] = num * (1.0 - ratio);
+                                    wm[0] = num * ratio;
                                 }
                             }
-                            num = num * mortf[j];
-                            T tn(0.0), tw(0.0);
-                            if (grow_n >= 0) {
-                                // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d
+                            T an(0.0), aw(0.0), bn(0.0), bw(0.0);
 #pragma unroll
-                                for (int d = NW - 1; d > 0; d--) { wn[j][d] = wn[j][d - 1]; ww[j][d] = ww[j][d - 1]; if constexpr (CONSTMAT) wm[j][d] = wm[j][d - 1]; }
-                                ww[j][0] = wgt;
-                                wn[j][0] = num;
-                                if constexpr (CONSTMAT) {
-                                    wm[j][0] = T(0.0);
-                                    if (const_now) {
-                                        // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
-                                        T ratio = 1.0 / (1.0 + xexp(T(0.0) - mat_l - agec[j]));
-                                        wn[j][0] = num * (1.0 - ratio);
-                                        wm[j][0] = num * ratio;
-                                    }
-                                }
-                                T an(0.0), aw(0.0), bn(0.0), bw(0.0);
-#pragma unroll
-                                for (int d = 0; d < NW; d++) {
-                                    const T wsrc = wal * (pwv[0] - pwv[d]) + ww[j][d];
+                            for (int d = 0; d < NW; d++) {
+                                if (d <= grow_n && d <= l) {
+                                    const T g = pg[d * LN];
+                                    const T wsrc = wal * (pwv[0] - pwv[d]) + ww[d];
                                     if (cont_now) {
-                                        const T w = wsrc * wn[j][d];
-                                        an = an + grt[d] * wn[j][d]; aw = aw + grt[d] * w;
-                                        bn = bn + gt[d] * wn[j][d]; bw = bw + gt[d] * w;
+                                        const T gr = pgr[d * LN];
+                                        const T w = wsrc * wn[d];
+                                        an = an + gr * wn[d]; aw = aw + gr * w;
+                                        bn = bn + g * wn[d]; bw = bw + g * w;
                                     } else if (CONSTMAT && const_now) {
-                                        const T n1 = wm[CONSTMAT ? j : 0][CONSTMAT ? d : 0] * gt[d], n2 = wn[j][d] * gt[d];
+                                        const T n1 = wm[CONSTMAT ? d : 0] * g, n2 = wn[d] * g;
                                         an = an + n1; aw = aw + wsrc * n1;
                                         bn = bn + n2; bw = bw + wsrc * n2;
                                     } else {
-                                        const T n2 = wn[j][d] * gt[d];
+                                        const T n2 = wn[d] * g;
                                         bn = bn + n2; bw = bw + wsrc * n2;
                                     }
                                 }
-                                num = bn; wgt = bw / avoid_zero(bn);
-                                if (trans_now) {
-                                    tn = an; tw = aw / avoid_zero(an);
-                                    W(A.t_tn + A.w_tr_off[s] + cell - c0) = tn;
-                                    W(A.t_tw + A.w_tr_off[s] + cell - c0) = tw;
-                                }
                             }
-                            // ---- g3a_step_transition (R/action_mature.R:78-134)
-                            if (inc_now) {
-                                const int src = A.w_inc_tr[cell];
-                                if (src >= 0 && ((A.inc_mask[cell] >> step) & 1)) {
-                                    const T moved = W(A.t_tn + src) * SLOT(A.inc_slot[cell]);
-                                    wgt = ratio_add_pop(wgt, num, W(A.t_tw + src), moved);
-                                    num = num + moved;
-                                }
-                            }
-                            if (trans_now) {      // unclaimed remainder moves back (move_remainder = TRUE)
+                            num = bn; wgt = bw / avoid_zero(bn);
+                            if (trans_now) {
+                                tn = an;
+                                *ptn = an; *ptw = aw / avoid_zero(an);
+                                // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
                                 T rem = tn;
                                 for (int k = A.rem_off[cell]; A.rem_slots[k] >= 0; k++) rem = rem - tn * SLOT(A.rem_slots[k]);
                                 num = num + rem;
                             }
-                            // ---- g3a_renewal (R/action_renewal.R:166-188)
-                            if (ren_now)
-                                for (int r = 0; r < n_renew; r++) {
-                                    const int32_t* Rn = I + St[G3S_RENEW_OFF] + r * G3R_LEN;
-                                    if (aidx[j] == Rn[G3R_AGE_IDX] && (Rn[G3R_RUN_STEP] == 0 || Rn[G3R_RUN_STEP] == step + 1)) {
-                                        const int fs = I[Rn[G3R_FACTOR_OFF] + yidx * narea + ridx[j]];
-                                        if (fs >= 0) {
-                                            const T rn = W(A.t_rd[s] + r * L + l) * SLOT(fs);
-                                            wgt = ratio_add_pop(wgt, num, W(A.t_rw[s] + r * L + l), rn);
-                                            num = num + rn;
-                                        }
-                                    }
-                                }
-                            W(A.t_num + cell) = num; W(A.t_wgt + cell) = wgt;
-                            // ---- g3l_distribution collect (R/likelihood_distribution.R:275-364): scatter this cell
-                            if (cact) {
-                                T xval[MAXX];
+                        }
+                        // ---- g3a_step_transition (R/action_mature.R:78-134)
+                        if (inc_now) {
+                            const int src = A.w_inc_tr[cell];
+                            if (src >= 0 && ((A.inc_mask[cell] >> step) & 1)) {
+                                const T moved = W(A.t_tn + src) * SLOT(A.inc_slot[cell]);
+                                wgt = ratio_add_pop(wgt, num, W(A.t_tw + src), moved);
+                                num = num + moved;
+                            }
+                        }
+                        // ---- g3a_renewal (R/action_renewal.R:166-188)
+                        if (ren_r >= 0) {
+                            const T rn = W(A.t_rd[s] + ren_r * L + l) * ren_f;
+                            wgt = ratio_add_pop(wgt, num, W(A.t_rw[s] + ren_r * L + l), rn);
+                            num = num + rn;
+                        }
+                        *pn = num; *pw_ = wgt;
+                        // ---- g3l_distribution collect (R/likelihood_distribution.R:275-364): scatter this cell
+                        if (cact) {
+                            T inv_w(0.0);
+                            if (catch_now) inv_w = 1.0 / avoid_zero(wgt);
+                            for (int c = 0; c < A.NCOMP; c++) {
+                                if (!((cact >> c) & 1)) continue;
+                                const int32_t* cp = A.t_cellptr + (size_t)c * (A.NC + 1);
+                                const int k0 = cp[cell], k1 = cp[cell + 1];
+                                if (k0 == k1) continue;
+                                const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+                                const int xb = C[G3C_XBUF];
+                                T xv(0.0);
+                                if (A.w_x_kind[xb] == 0) {
 #pragma unroll
-                                for (int x = 0; x < MAXX; x++) {
-                                    xval[x] = T(0.0);
-                                    if (x < A.NX) {
-                                        if (A.w_x_kind[x] == 0) { if (catch_now) xval[x] = A.w_x_unit[x] == 0 ? cons[x] / avoid_zero(wgt) : cons[x]; }
-                                        else xval[x] = A.w_x_unit[x] == 0 ? num : num * wgt;
-                                    }
-                                }
-                                for (int c = 0; c < A.NCOMP; c++) {
-                                    if (!((cact >> c) & 1)) continue;
-                                    const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
-                                    const int xb = C[G3C_XBUF];
-                                    T xv(0.0);
-#pragma unroll
-                                    for (int x = 0; x < MAXX; x++) if (x == xb) xv = xval[x];
-                                    const bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
-                                    const int base = A.t_ms[c] + (si ? I[C[G3C_TIDX_OFF] + t] * C[G3C_N_DEST] : 0);
-                                    const int32_t* cp = A.t_cellptr + (size_t)c * (A.NC + 1);
-                                    for (int k = cp[cell]; k < cp[cell + 1]; k++)
-                                        W(base + A.t_celldst[k]) = W(base + A.t_celldst[k]) + A.t_cellcoef[k] * xv;
-                                }
+                                    for (int x = 0; x < MAXX; x++) if (x == xb) xv = cons[x];
+                                    if (A.w_x_unit[xb] == 0) xv = xv * inv_w;
+                                } else xv = A.w_x_unit[xb] == 0 ? num : num * wgt;
+                                const bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+                                const int base = A.t_ms[c] + (si ? I[C[G3C_TIDX_OFF] + t] * C[G3C_N_DEST] : 0);
+                                for (int k = k0; k < k1; k++)
+                                    W(base + A.t_celldst[k]) = W(base + A.t_celldst[k]) + A.t_cellcoef[k] * xv;
                             }
                         }
                     }
@@ -634,6 +623,7 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
         }   // time loop
 
         const T out = bad_time ? T(nan("")) : nll;
+        if (!live) continue;
         if (tile_t == 0) {
             A.nll[b] = val(out);
             if (A.comp) for (int c = 0; c < A.NNLL; c++) A.comp[b * A.NNLL + c] = bad_time ? nan("") : val(W(A.t_ctot + c));

@@ -228,9 +228,16 @@ int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStr
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g3::TPB, smem));
     if (per_sm < 1) return fail(G3CUDA_EUNSUPP, "thread kernel does not fit one SM");
-    long long grid = std::min<long long>((work + g3::TPB - 1) / g3::TPB, (long long)per_sm * m->num_sms);
+    // One block per SM, sized so that the batch splits into equally full waves: an evaluation is
+    // one thread for its whole life, so a ragged last wave would idle most of the machine.
+    const long long slots = (long long)g3::TPB * m->num_sms;
+    const long long waves = (work + slots - 1) / slots;
+    long long per_wave = (work + waves - 1) / waves;
+    long long grid = std::min<long long>(m->num_sms, (per_wave + 31) / 32);
     if (grid < 1) grid = 1;
-    const size_t need = (size_t)m->t_entries * sizeof(T) * (size_t)grid * g3::TPB;
+    int block = (int)(((per_wave + grid - 1) / grid + 31) / 32 * 32);
+    block = std::max(32, std::min(block, g3::TPB));
+    const size_t need = (size_t)m->t_entries * sizeof(T) * (size_t)grid * block;
     if (need > m->t_ws_bytes) {
         // the workspace may still be in use by an earlier asynchronous launch on another stream
         CUDA_TRY(cudaDeviceSynchronize());
@@ -240,7 +247,7 @@ int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStr
         m->t_ws_bytes = need;
     }
     A.t_ws = m->t_ws;
-    kern<<<(unsigned)grid, g3::TPB, smem, st>>>(A);
+    kern<<<(unsigned)grid, block, smem, st>>>(A);
     CUDA_TRY(cudaGetLastError());
     m->launches++;
     return G3CUDA_OK;
