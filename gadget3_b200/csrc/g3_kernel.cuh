@@ -70,8 +70,7 @@ struct KArgs {
     void* t_ws;
     int t_slot, t_num, t_wgt, t_tn, t_tw, t_mv, t_suit, t_scr, t_ctot;
     int t_mort[MAXS], t_pw[MAXS], t_g[MAXS], t_gr[MAXS], t_gn[MAXS], t_rd[MAXS], t_rw[MAXS], t_ms[MAXC];
-    const int32_t* t_cellptr;               // [NCOMP][NC + 1] cell-oriented CSR of the collect step
-    const int32_t* t_celldst; const double* t_cellcoef;   // ageing movement: (destination cell, stash index num, stash index wgt, ratio slot)
+    int t_x[MAXX];                          // collect vectors   // ageing movement: (destination cell, stash index num, stash index wgt, ratio slot)
 };
 
 template <class T> __device__ __forceinline__ T mkpar(const double* spar, const int* seed, int i) {

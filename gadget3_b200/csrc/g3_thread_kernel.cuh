@@ -67,6 +67,7 @@ template <class T> __device__ __noinline__ T eval_slot_g(const int32_t* __restri
 #ifndef G3_TPB
 #define G3_TPB 512
 #endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 constexpr int TPB = G3_TPB;     // LARGEST block of the thread-per-evaluation kernel (one block per SM; the launch
                                 // picks blockDim <= TPB so that the batch splits into equally full waves)
 
@@ -77,10 +78,10 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long NTH = (long long)gridDim.x * blockDim.x;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned NTH = gridDim.x * blockDim.x;        // (entries x NTH < 2^32 is checked at launch)
     T* __restrict__ ws = reinterpret_cast<T*>(A.t_ws) + gtid;
-#define W(e) ws[(size_t)(e) * (size_t)NTH]
+#define W(e) ws[(unsigned)(e) * NTH]
     T* s_eot = reinterpret_cast<T*>(smem_raw) + threadIdx.x;      // [MAXTS][blockDim]: landings / total suitable biomass
 #define EOT(k) s_eot[(k) * blockDim.x]
 
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
     // Every thread of a block runs the same trip counts (threads past the end of the batch redo
     // vector 0 without writing), so that the block can re-align its warps once per time step:
     // warps that execute the same code at the same time share instruction fetches.
-    for (long long base0 = (long long)blockIdx.x * blockDim.x; base0 < A.B * ntiles; base0 += NTH) {
+    for (long long base0 = (long long)blockIdx.x * blockDim.x; base0 < A.B * ntiles; base0 += (long long)NTH) {
         const bool live = base0 + threadIdx.x < A.B * ntiles;
         const long long work = live ? base0 + threadIdx.x : 0;
         const long long b = work / ntiles;
@@ -258,12 +259,13 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
             const bool final_step = step == NSTEPS - 1;
             const bool pred_now = A.w_pred_active[t] != 0;
             // components collecting at this step (bit c), and whether any of them reads a catch
-            unsigned cact = 0;
+            unsigned cact = 0, xact = 0;
             bool any_catch = false;
             for (int c = 0; c < A.NCOMP; c++) {
                 const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
                 if (I[C[G3C_TIDX_OFF] + t] >= 0 && prow[C[G3C_WEIGHT_PAR]] > 0.0) {
                     cact |= 1u << c;
+                    xact |= 1u << C[G3C_XBUF];
                     if (A.w_x_kind[C[G3C_XBUF]] == 0) any_catch = true;
                 }
             }
@@ -324,19 +326,23 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                     if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
                 }
                 const bool catch_now = any_catch && nq > 0;
-                if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_mask && cact == 0) continue;
+                if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0) continue;
                 const int gsz = (grow_n + 1) * L;
                 const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
                 const int32_t* msl = I + St[G3S_MAT_OFF];
-                const size_t LN = (size_t)L * NTH;
-                const T* const gbase = ws + (size_t)((cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz) * NTH;    // staying part
-                const T* const grbase = ws + (size_t)(A.t_gr[s] + idt * gsz) * NTH;                             // maturing part
-                // collect vectors fed by each predator of this stock
-                unsigned kx[MAXQ];
+                const unsigned LN = (unsigned)L * NTH;
+                const T* const gbase = ws + (unsigned)((cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz) * NTH;    // staying part
+                const T* const grbase = ws + (unsigned)(A.t_gr[s] + idt * gsz) * NTH;                             // maturing part
+                // predators of this stock: suitability table and the collect vectors they feed
+                unsigned kx[MAXQ], ksuit[MAXQ];
 #pragma unroll
                 for (int k = 0; k < MAXQ; k++) {
-                    kx[k] = 0;
-                    if (k < nq) for (int x = 0; x < A.NX; x++) if ((A.w_x_ppmask[x] >> A.stock_pp[A.stock_pp_off[s] + k]) & 1) kx[k] |= 1u << x;
+                    kx[k] = 0; ksuit[k] = 0;
+                    if (k < nq) {
+                        const int q = A.stock_pp[A.stock_pp_off[s] + k];
+                        ksuit[k] = (unsigned)(A.t_suit + q * A.maxL) * NTH;
+                        for (int x = 0; x < A.NX; x++) if ((A.w_x_ppmask[x] >> q) & 1) kx[k] |= 1u << x;
+                    }
                 }
                 T o1(0.0), o2(0.0);
 
@@ -345,31 +351,49 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                     const T mortf = has_mort ? W(A.t_mort[s] + idt * ncol + col) : T(1.0);
                     T agec(0.0);
                     if (const_now && msl[2] >= 0) agec = SLOT(msl[2]) * ((double)(St[G3S_MINAGE] + aidx) - SLOT(msl[3]));
-                    int tsk[MAXQ];
+                    T eotk[MAXQ];           // landings / total suitable biomass of each predator in this column's area
+                    bool anyk = false;
 #pragma unroll
-                    for (int k = 0; k < MAXQ; k++) tsk[k] = (prey_now && k < nq) ? A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx] : -1;
+                    for (int k = 0; k < MAXQ; k++) {
+                        eotk[k] = T(0.0);
+                        if (prey_now && k < nq) {
+                            const int ts = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx];
+                            if (ts >= 0) { eotk[k] = EOT(ts); anyk = true; }
+                        }
+                    }
+                    (void)anyk;
                     // renewal into this column at this step: record and factor
                     int ren_r = -1; T ren_f(0.0);
                     for (int r = 0; r < n_renew; r++)
                         if (((ren_mask >> r) & 1) && aidx == I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_AGE_IDX]) {
                             const int fs = I[I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * narea + ridx];
-                            if (fs >= 0) { ren_r = r; ren_f = SLOT(fs); }    // (one renewal per column and step)
+                            if (fs >= 0) { ren_r = r; ren_f = SLOT(fs); }    // (one renewal per column and step, checked at model_create)
                         }
                     T wn[NW], ww[NW], wm[CONSTMAT ? NW : 1], pwv[NW];   // windows: staying numbers, weights, maturing numbers, l^wbeta
 #pragma unroll
                     for (int d = 0; d < NW; d++) { wn[d] = T(0.0); ww[d] = T(0.0); pwv[d] = T(0.0); if constexpr (CONSTMAT) wm[d] = T(0.0); }
                     const int cell0 = c0 + col * L;
-                    T* pn = ws + (size_t)(A.t_num + cell0) * NTH;
-                    T* pw_ = ws + (size_t)(A.t_wgt + cell0) * NTH;
-                    T* ptn = ws + (size_t)(A.t_tn + A.w_tr_off[s] + col * L) * NTH;
-                    T* ptw = ws + (size_t)(A.t_tw + A.w_tr_off[s] + col * L) * NTH;
-                    const T* ppw = ws + (size_t)A.t_pw[s] * NTH;
+                    T* pn = ws + (unsigned)(A.t_num + cell0) * NTH;
+                    T* pw_ = ws + (unsigned)(A.t_wgt + cell0) * NTH;
+                    T* ptn = ws + (unsigned)(A.t_tn + A.w_tr_off[s] + col * L) * NTH;
+                    T* ptw = ws + (unsigned)(A.t_tw + A.w_tr_off[s] + col * L) * NTH;
+                    const T* ppw = ws + (unsigned)A.t_pw[s] * NTH;
                     const T* pg = gbase;
                     const T* pgr = grbase;
+                    unsigned lN = 0;        // l * NTH
 
-                    for (int l = 0; l < L; l++, pn += NTH, pw_ += NTH, ptn += NTH, ptw += NTH, ppw += NTH, pg += NTH, pgr += NTH) {
+                    for (int l = 0; l < L; l++, pn += NTH, pw_ += NTH, ptn += NTH, ptw += NTH, ppw += NTH, pg += NTH, pgr += NTH, lN += NTH) {
                         const int cell = cell0 + l;
                         T num = *pn, wgt = *pw_;
+                        if (l + 1 < L) {    // next cell's lines on their way while this one is computed
+                            prefetch_l1(pn + NTH); prefetch_l1(pw_ + NTH);
+                            if (grow_n >= 0) {
+                                prefetch_l1(ppw + NTH);
+#pragma unroll
+                                for (int d = 0; d < NW; d++)
+                                    if (d <= grow_n && d <= l + 1) { prefetch_l1(pg + NTH + d * LN); if (cont_now) prefetch_l1(pgr + NTH + d * LN); }
+                            }
+                        }
                         T cons[MAXX];
 #pragma unroll
                         for (int x = 0; x < MAXX; x++) cons[x] = T(0.0);
@@ -380,8 +404,8 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                             for (int x = 0; x < MAXX; x++) fx[x] = T(0.0);
 #pragma unroll
                             for (int k = 0; k < MAXQ; k++)
-                                if (tsk[k] >= 0) {
-                                    const T cf = W(A.t_suit + A.stock_pp[A.stock_pp_off[s] + k] * A.maxL + l) * EOT(tsk[k]);
+                                if (k < nq) {
+                                    const T cf = ws[ksuit[k] + lN] * eotk[k];
                                     tp = tp + cf * B0;
                                     if (catch_now) {
 #pragma unroll
@@ -400,7 +424,6 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                             }
                         }
                         num = num * mortf;
-                        T tn(0.0);
                         if (grow_n >= 0) {
                             // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d
 #pragma unroll
@@ -440,11 +463,10 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                             }
                             num = bn; wgt = bw / avoid_zero(bn);
                             if (trans_now) {
-                                tn = an;
                                 *ptn = an; *ptw = aw / avoid_zero(an);
                                 // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
-                                T rem = tn;
-                                for (int k = A.rem_off[cell]; A.rem_slots[k] >= 0; k++) rem = rem - tn * SLOT(A.rem_slots[k]);
+                                T rem = an;
+                                for (int k = A.rem_off[cell]; A.rem_slots[k] >= 0; k++) rem = rem - an * SLOT(A.rem_slots[k]);
                                 num = num + rem;
                             }
                         }
@@ -464,32 +486,52 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                             num = num + rn;
                         }
                         *pn = num; *pw_ = wgt;
-                        // ---- g3l_distribution collect (R/likelihood_distribution.R:275-364): scatter this cell
-                        if (cact) {
+                        // ---- collect vectors for g3l_distribution (R/likelihood_distribution.R:275-287)
+                        if (xact) {
                             T inv_w(0.0);
                             if (catch_now) inv_w = 1.0 / avoid_zero(wgt);
-                            for (int c = 0; c < A.NCOMP; c++) {
-                                if (!((cact >> c) & 1)) continue;
-                                const int32_t* cp = A.t_cellptr + (size_t)c * (A.NC + 1);
-                                const int k0 = cp[cell], k1 = cp[cell + 1];
-                                if (k0 == k1) continue;
-                                const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
-                                const int xb = C[G3C_XBUF];
-                                T xv(0.0);
-                                if (A.w_x_kind[xb] == 0) {
 #pragma unroll
-                                    for (int x = 0; x < MAXX; x++) if (x == xb) xv = cons[x];
-                                    if (A.w_x_unit[xb] == 0) xv = xv * inv_w;
-                                } else xv = A.w_x_unit[xb] == 0 ? num : num * wgt;
-                                const bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
-                                const int base = A.t_ms[c] + (si ? I[C[G3C_TIDX_OFF] + t] * C[G3C_N_DEST] : 0);
-                                for (int k = k0; k < k1; k++)
-                                    W(base + A.t_celldst[k]) = W(base + A.t_celldst[k]) + A.t_cellcoef[k] * xv;
-                            }
+                            for (int x = 0; x < MAXX; x++)
+                                if ((xact >> x) & 1) {
+                                    T xv;
+                                    if (A.w_x_kind[x] == 0) xv = A.w_x_unit[x] == 0 ? cons[x] * inv_w : cons[x];
+                                    else xv = A.w_x_unit[x] == 0 ? num : num * wgt;
+                                    W(A.t_x[x] + cell) = xv;
+                                }
                         }
                     }
                 }
                 if (is_us && prey_now) us_tot = us_tot + (o1 - o2);
+            }
+
+            // ================= g3l_distribution collect: model[dest] += lgmatrix . x (R/likelihood_distribution.R:288-364)
+            for (int c = 0; c < A.NCOMP; c++) {
+                if (!((cact >> c) & 1)) continue;
+                const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+                const int nd = C[G3C_N_DEST];
+                const bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
+                const int ms = A.t_ms[c] + (si ? I[C[G3C_TIDX_OFF] + t] * nd : 0);
+                const int xs = A.t_x[C[G3C_XBUF]];
+                if (C[G3C_MODE] == 0) {
+                    const int32_t* ptr = I + C[G3C_CSR_PTR_OFF];
+                    const int32_t* idx = I + C[G3C_CSR_IDX_OFF];
+                    const double* cf = R + C[G3C_CSR_COEF_ROFF];
+                    for (int e = 0; e < nd; e++) {
+                        T acc = W(ms + e);
+                        for (int j = ptr[e]; j < ptr[e + 1]; j++) acc = acc + cf[j] * W(xs + idx[j]);
+                        W(ms + e) = acc;
+                    }
+                } else {
+                    const int32_t* cd = I + C[G3C_CELL_DEST_OFF];
+                    const double* cf = R + C[G3C_CELL_COEF_ROFF];
+                    if (nd == 1) {
+                        T acc = W(ms);
+                        for (int i = 0; i < A.NC; i++) if (cd[i] == 0) acc = acc + cf[i] * W(xs + i);
+                        W(ms) = acc;
+                    } else {
+                        for (int i = 0; i < A.NC; i++) if (cd[i] >= 0) W(ms + cd[i]) = W(ms + cd[i]) + cf[i] * W(xs + i);
+                    }
+                }
             }
 
             // ================= g3l_distribution compare (R/likelihood_distribution.R:375-394)

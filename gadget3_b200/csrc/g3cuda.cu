@@ -217,6 +217,7 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
         A.t_ms[c] = take(C[G3C_N_DEST] * (si ? C[G3C_N_TIMES] : 1));
     }
     A.t_ctot = take(A.NNLL);
+    for (int x = 0; x < MAXX; x++) A.t_x[x] = x < A.NX ? take(A.NC) : 0;
     return off;
 }
 
@@ -237,6 +238,8 @@ int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStr
     if (grid < 1) grid = 1;
     int block = (int)(((per_wave + grid - 1) / grid + 31) / 32 * 32);
     block = std::max(32, std::min(block, g3::TPB));
+    if ((double)m->t_entries * (double)grid * block >= 4294967295.0)
+        return fail(G3CUDA_EUNSUPP, "evaluation workspace too large for 32-bit element indexing (%d entries)", m->t_entries);
     const size_t need = (size_t)m->t_entries * sizeof(T) * (size_t)grid * block;
     if (need > m->t_ws_bytes) {
         // the workspace may still be in use by an earlier asynchronous launch on another stream
@@ -592,28 +595,15 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         // the fused pass hands maturing fish over within one sweep: sources must come before destinations
         for (int c = 0; c < A.NC; c++) if (inc_src[c] >= 0 && cell[inc_src[c]].x >= cell[c].x) m->thread_ok = false;
         m->t_entries = make_tlayout(m, A);
-        std::vector<int32_t> cptr, cdst; std::vector<double> ccoef;
-        for (int c = 0; c < A.NCOMP; c++) {
-            const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
-            std::vector<std::vector<std::pair<int, double>>> per_cell(A.NC);
-            if (C[G3C_MODE] == 0) {
-                const int32_t* ptr = I + C[G3C_CSR_PTR_OFF]; const int32_t* idx = I + C[G3C_CSR_IDX_OFF];
-                const double* cf = R + C[G3C_CSR_COEF_ROFF];
-                for (int e = 0; e < C[G3C_N_DEST]; e++) for (int j = ptr[e]; j < ptr[e + 1]; j++) per_cell[idx[j]].push_back({e, cf[j]});
-            } else {
-                const int32_t* cd = I + C[G3C_CELL_DEST_OFF]; const double* cf = R + C[G3C_CELL_COEF_ROFF];
-                for (int i = 0; i < A.NC; i++) if (cd[i] >= 0) per_cell[i].push_back({cd[i], cf[i]});
+        // one renewal per (column, step) is what the fused pass applies
+        for (int s = 0; s < A.NS; s++) {
+            const int32_t* St = stock(s);
+            for (int k = 0; k < St[G3S_N_RENEW]; k++) for (int k2 = k + 1; k2 < St[G3S_N_RENEW]; k2++) {
+                const int32_t* Ra = I + St[G3S_RENEW_OFF] + k * G3R_LEN; const int32_t* Rb = I + St[G3S_RENEW_OFF] + k2 * G3R_LEN;
+                if (Ra[G3R_AGE_IDX] == Rb[G3R_AGE_IDX] && (Ra[G3R_RUN_STEP] == 0 || Rb[G3R_RUN_STEP] == 0 || Ra[G3R_RUN_STEP] == Rb[G3R_RUN_STEP]))
+                    m->thread_ok = false;
             }
-            for (int i = 0; i < A.NC; i++) {
-                cptr.push_back((int32_t)cdst.size());
-                for (auto& pr : per_cell[i]) { cdst.push_back(pr.first); ccoef.push_back(pr.second); }
-            }
-            cptr.push_back((int32_t)cdst.size());
         }
-        int32_t* d_cptr = dev_copy(cptr); int32_t* d_cdst = dev_copy(cdst); double* d_ccoef = dev_copy(ccoef);
-        if (!d_cptr || !d_cdst || !d_ccoef) return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
-        m->owned.push_back(d_cptr); m->owned.push_back(d_cdst); m->owned.push_back(d_ccoef);
-        A.t_cellptr = d_cptr; A.t_celldst = d_cdst; A.t_cellcoef = d_ccoef;
     }
 
     // ---- observation terms that do not depend on parameters
