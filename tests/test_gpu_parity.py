@@ -85,9 +85,18 @@ def _check_nll_and_components(model, p, fn, orc):
     assert np.median(_rel(g_nll, o_nll)) < 1e-12
 
 
+@pytest.mark.parametrize("kernel", [1, 3], ids=["cta_kernel", "thread_kernel"])
 @pytest.mark.parametrize("name", ["C1", "C2"])
-def test_gradients(setups, name):
+def test_gradients(setups, name, kernel):
     model, p, fn, orc = setups[name]
+    fn.handle.set_kernel(kernel)
+    try:
+        _check_gradients(model, p, fn, orc)
+    finally:
+        fn.handle.set_kernel(0)
+
+
+def _check_gradients(model, p, fn, orc):
     P = parameter_batch(p, 6, seed=77)
     full = fn.full_par(P)
     g_nll, g_grad = fn.gr_batch(P)
