@@ -14,9 +14,11 @@
  * every avoid_zero evaluated in full with libm exp/log1p, per-age recomputation) so
  * that it is an independent check of the restructured CUDA path.
  *
- * Parity pin: see oracle/README.md -- known-answer vectors from the reference's unit
- * tests (tests/test-action_grow.R etc.) and, where buildable, the reference's own
- * generated C++ compiled against oracle/tmb_shim (oracle/_ref).
+ * Parity pin: (1) the known-answer vectors of the reference's unit tests
+ * (tests/test_oracle_kat.py <- tests/test-action_grow.R etc.); (2) the reference's own
+ * generated C++ (baseline/*.cpp) compiled unmodified against oracle/tmb_shim into
+ * oracle/_ref -- whole-model nll and reports agree to ~1e-16..2e-12
+ * (tests/test_reference_golden.py, tests/golden/reference_c{1,2}.npz).
  *
  * Scalar type T is double or Dual<K> (forward-mode tangents) so the same
  * restatement is the gradient oracle.

@@ -1,0 +1,35 @@
+"""Shared helpers of the parity tests."""
+import numpy as np
+
+US_WEIGHT = 1e8      # g3l_understocking default weight (R/likelihood_understocking.R:7)
+
+
+def us_tolerance(model, params, comp_us):
+    """Conditioning of g3l_understocking. Per step it adds weight * (sum(tp) - sum(tp'))^2 where both
+    sums are ~ the landings E of that step (R/action_predate.R:393-398): a one-ulp difference in any
+    exp/log1p underneath moves the DIFFERENCE by delta ~ 64 eps E, i.e. the squared term by
+    2 sqrt(u_t) delta + delta^2. The reference's own backends (R sums in long double, TMB in Eigen's
+    packet order) differ by this much, so this term is compared against that bound, and everything
+    else at 1e-10 relative. Over T steps: sum_t 2 sqrt(u_t) delta <= 2 delta sqrt(T * sum_t u_t)."""
+    from gadget3_b200.spec import K
+    ints, reals = model.pack(params)
+    emax = 0.0
+    for pr in range(ints[K["G3H_NPRED"]]):
+        rec = ints[K["G3H_PRED_OFF"]] + pr * K["G3P_LEN"]
+        n = ints[K["G3H_NT"]] * ints[rec + K["G3P_NAREA"]]
+        if ints[rec + K["G3P_E_ROFF"]] >= 0 and ints[rec + K["G3P_KIND"]] != K["G3PRED_STOCK"]:
+            emax = max(emax, np.abs(reals[ints[rec + K["G3P_E_ROFF"]]:ints[rec + K["G3P_E_ROFF"]] + n]).max())
+    delta = 64 * np.finfo(float).eps * emax
+    T = model.n_steps
+    return 2 * delta * np.sqrt(T * np.abs(comp_us)) + T * delta * delta
+
+
+def golden(name):
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"reference_{name.lower()}.npz")
+    return np.load(path)
+
+
+def report_to_reference_layout(model, rep, key):
+    """Our unpack_report() arrays -> the dimension order of the reference's REPORT()ed arrays."""
+    return rep[key]

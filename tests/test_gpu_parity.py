@@ -30,28 +30,11 @@ def _rel(a, b, floor=0.0):
     return np.abs(a - b) / np.maximum(np.abs(b), floor if floor > 0 else 1e-300)
 
 
+from _util import US_WEIGHT, golden, us_tolerance as _us_tolerance  # noqa: E402
+
+
 def _us_weight(model):
-    return 1e8                                             # g3l_understocking default weight (R/likelihood_understocking.R:7)
-
-
-def _us_tolerance(model, params, comp_us):
-    """Conditioning of g3l_understocking. Per step it adds weight * (sum(tp) - sum(tp'))^2 where both
-    sums are ~ the landings E of that step (R/action_predate.R:393-398): a one-ulp difference in any
-    exp/log1p underneath moves the DIFFERENCE by delta ~ 64 eps E, i.e. the squared term by
-    2 sqrt(u_t) delta + delta^2. The reference's own backends (R sums in long double, TMB in Eigen's
-    packet order) differ by this much, so this term is compared against that bound, and everything
-    else at 1e-10 relative. Over T steps: sum_t 2 sqrt(u_t) delta <= 2 delta sqrt(T * sum_t u_t)."""
-    from gadget3_b200.spec import K
-    ints, reals = model.pack(params)
-    emax = 0.0
-    for pr in range(ints[K["G3H_NPRED"]]):
-        rec = ints[K["G3H_PRED_OFF"]] + pr * K["G3P_LEN"]
-        n = ints[K["G3H_NT"]] * ints[rec + K["G3P_NAREA"]]
-        if ints[rec + K["G3P_E_ROFF"]] >= 0 and ints[rec + K["G3P_KIND"]] != K["G3PRED_STOCK"]:
-            emax = max(emax, np.abs(reals[ints[rec + K["G3P_E_ROFF"]]:ints[rec + K["G3P_E_ROFF"]] + n]).max())
-    delta = 64 * np.finfo(float).eps * emax
-    T = model.n_steps
-    return 2 * delta * np.sqrt(T * np.abs(comp_us)) + T * delta * delta
+    return US_WEIGHT
 
 
 @pytest.mark.parametrize("kernel", [1, 2, 3], ids=["cta_kernel", "warp_kernel", "thread_kernel"])
@@ -208,3 +191,21 @@ def test_growth_beyond_maxlengthgroupgrowth(setups):
     ok = np.isfinite(o)          # lgamma poles (alpha + x a non-positive integer) make the reference NaN
     assert ok.sum() >= 2
     assert _rel(g[ok], o[ok]).max() < 1e-9
+
+
+@pytest.mark.parametrize("kernel", [1, 3], ids=["cta_kernel", "thread_kernel"])
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_against_reference_generated_code(setups, name, kernel):
+    """CUDA nll vs the reference's OWN generated objective (baseline/*.cpp compiled against
+    oracle/tmb_shim; vectors and results in tests/golden/reference_*.npz, tools/make_golden_reference.py)."""
+    model, p, fn, orc = setups[name]
+    g = golden(name)
+    assert list(g["switch"]) == list(p.switch)
+    fn.handle.set_kernel(kernel)
+    try:
+        nll, comp, _ = fn.handle.eval_batch(g["par"], want_comp=True)
+    finally:
+        fn.handle.set_kernel(0)
+    tol = NLL_RTOL * np.abs(g["nll"]) + US_WEIGHT * _us_tolerance(model, p, comp[:, -2])
+    assert (np.abs(nll - g["nll"]) <= tol).all()
+    assert np.median(_rel(nll, g["nll"])) < 1e-12
