@@ -267,7 +267,7 @@ def main():
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * P * 8), "d2h_bytes_per_step": int(B * 8)},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "fp64", "kernel": "g3::eval_kernel<double>", "achieved": achieved, "peak": peak_tflops,
+        "roofline": {"bound": "fp64", "kernel": "g3::eval_thread_kernel<double>", "achieved": achieved, "peak": peak_tflops,
                      "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops > 0 else None,
                      "peak_source": "DFMA-chain microbenchmark run live on this GPU (g3cuda_fp64_peak_tflops); "
                                     "MEASURED_PEAKS.json has no fp64 entry",
