@@ -70,7 +70,9 @@ struct KArgs {
     void* t_ws;
     int t_slot, t_num, t_wgt, t_tn, t_tw, t_mv, t_suit, t_scr, t_ctot;
     int t_mort[MAXS], t_pw[MAXS], t_g[MAXS], t_gr[MAXS], t_gn[MAXS], t_rd[MAXS], t_rw[MAXS], t_ms[MAXC];
-    int t_x[MAXX];                          // collect vectors   // ageing movement: (destination cell, stash index num, stash index wgt, ratio slot)
+    int t_x[MAXX];                          // collect vectors
+    int t_remf, t_colbase[MAXS], t_cmat[MAXS];      // per global column: unclaimed share; first global column; constant-maturity ratios
+    const int4* t_colinc;                   // per global column: (compact index of the source column's first cell or -1, ratio slot, step mask, 0)   // ageing movement: (destination cell, stash index num, stash index wgt, ratio slot)
 };
 
 template <class T> __device__ __forceinline__ T mkpar(const double* spar, const int* seed, int i) {

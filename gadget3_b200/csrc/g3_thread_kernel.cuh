@@ -68,7 +68,8 @@ template <class T> __device__ __noinline__ T eval_slot_g(const int32_t* __restri
 #define G3_TPB 512
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-constexpr int TPB = G3_TPB;     // LARGEST block of the thread-per-evaluation kernel (one block per SM; the launch
+constexpr int TPB = G3_TPB;
+constexpr unsigned WS_STRIDE = 152u * G3_TPB;   // workspace stride in threads: room for 152 SMs x the largest block     // LARGEST block of the thread-per-evaluation kernel (one block per SM; the launch
                                 // picks blockDim <= TPB so that the batch splits into equally full waves)
 
 // CB: unused (kept for the launch table); NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
@@ -79,7 +80,10 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned NTH = gridDim.x * blockDim.x;        // (entries x NTH < 2^32 is checked at launch)
+    // The thread stride of the workspace is a COMPILE-TIME constant (>= the launched threads), so that
+    // neighbouring entries sit at immediate offsets from a running pointer: no address arithmetic
+    // in the inner loops. (entries x WS_STRIDE < 2^32 is checked at launch.)
+    constexpr unsigned NTH = WS_STRIDE;
     T* __restrict__ ws = reinterpret_cast<T*>(A.t_ws) + gtid;
 #define W(e) ws[(unsigned)(e) * NTH]
     T* s_eot = reinterpret_cast<T*>(smem_raw) + threadIdx.x;      // [MAXTS][blockDim]: landings / total suitable biomass
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
     // Every thread of a block runs the same trip counts (threads past the end of the batch redo
     // vector 0 without writing), so that the block can re-align its warps once per time step:
     // warps that execute the same code at the same time share instruction fetches.
-    for (long long base0 = (long long)blockIdx.x * blockDim.x; base0 < A.B * ntiles; base0 += (long long)NTH) {
+    for (long long base0 = (long long)blockIdx.x * blockDim.x; base0 < A.B * ntiles; base0 += (long long)gridDim.x * blockDim.x) {
         const bool live = base0 + threadIdx.x < A.B * ntiles;
         const long long work = live ? base0 + threadIdx.x : 0;
         const long long b = work / ntiles;
@@ -229,6 +233,29 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
             }
         }
 
+        // maturation: share of the maturing fish of a column that no output stock claims (R/action_mature.R:126-131),
+        // and the g3a_mature_constant ratio per (column, length) (R/action_mature.R:44-74)
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+            if (St[G3S_GROW_N] < 0 || St[G3S_N_OUT] == 0) continue;
+            const int L = St[G3S_L], nage = St[G3S_NAGE], ncol = nage * St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+            for (int col = 0; col < ncol; col++) {
+                T remf(1.0);
+                for (int k = A.rem_off[c0 + col * L]; A.rem_slots[k] >= 0; k++) remf = remf - SLOT(A.rem_slots[k]);
+                W(A.t_remf + A.t_colbase[s] + col) = remf;
+                if (CONSTMAT && St[G3S_MAT_KIND] == G3MAT_CONSTANT) {
+                    const int32_t* msl = I + St[G3S_MAT_OFF];
+                    const int aidx = col % nage;
+                    for (int l = 0; l < L; l++) {
+                        T inner(0.0);
+                        if (msl[0] >= 0) inner = inner - SLOT(msl[0]) * (R[St[G3S_MIDLEN_ROFF] + l] - SLOT(msl[1]));
+                        if (msl[2] >= 0) inner = inner - SLOT(msl[2]) * ((double)(St[G3S_MINAGE] + aidx) - SLOT(msl[3]));
+                        W(A.t_cmat[s] + col * L + l) = 1.0 / (1.0 + xexp(inner));
+                    }
+                }
+            }
+        }
+
         T nll(0.0);
         for (int i = 0; i < A.NNLL; i++) W(A.t_ctot + i) = T(0.0);
         // ---- g3l_bounds_penalty (R/likelihood_bounds.R:13-16), cur_time == 0
@@ -305,7 +332,7 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                     if (k < A.NTS) EOT(k) = R[A.w_ts_eoff[k] + (size_t)t * A.w_ts_estr[k]] / EOT(k);
             }
 
-            // ================= the fused pass, stock by stock, column by column, up the length axis
+            // ================= stock by stock
             T us_tot(0.0);
             for (int s = 0; s < NS; s++) {
                 const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
@@ -327,78 +354,38 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                 }
                 const bool catch_now = any_catch && nq > 0;
                 if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0) continue;
-                const int gsz = (grow_n + 1) * L;
-                const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
-                const int32_t* msl = I + St[G3S_MAT_OFF];
-                const unsigned LN = (unsigned)L * NTH;
-                const T* const gbase = ws + (unsigned)((cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz) * NTH;    // staying part
-                const T* const grbase = ws + (unsigned)(A.t_gr[s] + idt * gsz) * NTH;                             // maturing part
-                // predators of this stock: suitability table and the collect vectors they feed
-                unsigned kx[MAXQ], ksuit[MAXQ];
-#pragma unroll
-                for (int k = 0; k < MAXQ; k++) {
-                    kx[k] = 0; ksuit[k] = 0;
-                    if (k < nq) {
-                        const int q = A.stock_pp[A.stock_pp_off[s] + k];
-                        ksuit[k] = (unsigned)(A.t_suit + q * A.maxL) * NTH;
-                        for (int x = 0; x < A.NX; x++) if ((A.w_x_ppmask[x] >> q) & 1) kx[k] |= 1u << x;
-                    }
-                }
-                T o1(0.0), o2(0.0);
+                const unsigned LWS = (unsigned)L * NTH;
 
-                for (int col = 0; col < ncol; col++) {
-                    const int ridx = col / nage, aidx = col - ridx * nage;
-                    const T mortf = has_mort ? W(A.t_mort[s] + idt * ncol + col) : T(1.0);
-                    T agec(0.0);
-                    if (const_now && msl[2] >= 0) agec = SLOT(msl[2]) * ((double)(St[G3S_MINAGE] + aidx) - SLOT(msl[3]));
-                    T eotk[MAXQ];           // landings / total suitable biomass of each predator in this column's area
-                    bool anyk = false;
+                // ---------- g3a_predate (R/action_predate.R:335-406): cell order, as the reference sums
+                if (prey_now) {
+                    unsigned kx[MAXQ], ksuit[MAXQ];     // per predator: collect vectors it feeds, suitability table
 #pragma unroll
                     for (int k = 0; k < MAXQ; k++) {
-                        eotk[k] = T(0.0);
-                        if (prey_now && k < nq) {
-                            const int ts = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx];
-                            if (ts >= 0) { eotk[k] = EOT(ts); anyk = true; }
+                        kx[k] = 0; ksuit[k] = 0;
+                        if (k < nq) {
+                            const int q = A.stock_pp[A.stock_pp_off[s] + k];
+                            ksuit[k] = (unsigned)(A.t_suit + q * A.maxL) * NTH;
+                            for (int x = 0; x < A.NX; x++) if ((A.w_x_ppmask[x] >> q) & 1) kx[k] |= 1u << x;
                         }
                     }
-                    (void)anyk;
-                    // renewal into this column at this step: record and factor
-                    int ren_r = -1; T ren_f(0.0);
-                    for (int r = 0; r < n_renew; r++)
-                        if (((ren_mask >> r) & 1) && aidx == I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_AGE_IDX]) {
-                            const int fs = I[I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * narea + ridx];
-                            if (fs >= 0) { ren_r = r; ren_f = SLOT(fs); }    // (one renewal per column and step, checked at model_create)
-                        }
-                    T wn[NW], ww[NW], wm[CONSTMAT ? NW : 1], pwv[NW];   // windows: staying numbers, weights, maturing numbers, l^wbeta
+                    T o1(0.0), o2(0.0);
+                    T* pn = ws + (unsigned)(A.t_num + c0) * NTH;
+                    const T* pw_ = ws + (unsigned)(A.t_wgt + c0) * NTH;
+                    for (int col = 0; col < ncol; col++) {
+                        const int ridx = col / nage;
+                        T eotk[MAXQ];       // landings / total suitable biomass of each predator in this column's area
 #pragma unroll
-                    for (int d = 0; d < NW; d++) { wn[d] = T(0.0); ww[d] = T(0.0); pwv[d] = T(0.0); if constexpr (CONSTMAT) wm[d] = T(0.0); }
-                    const int cell0 = c0 + col * L;
-                    T* pn = ws + (unsigned)(A.t_num + cell0) * NTH;
-                    T* pw_ = ws + (unsigned)(A.t_wgt + cell0) * NTH;
-                    T* ptn = ws + (unsigned)(A.t_tn + A.w_tr_off[s] + col * L) * NTH;
-                    T* ptw = ws + (unsigned)(A.t_tw + A.w_tr_off[s] + col * L) * NTH;
-                    const T* ppw = ws + (unsigned)A.t_pw[s] * NTH;
-                    const T* pg = gbase;
-                    const T* pgr = grbase;
-                    unsigned lN = 0;        // l * NTH
-
-                    for (int l = 0; l < L; l++, pn += NTH, pw_ += NTH, ptn += NTH, ptw += NTH, ppw += NTH, pg += NTH, pgr += NTH, lN += NTH) {
-                        const int cell = cell0 + l;
-                        T num = *pn, wgt = *pw_;
-                        if (l + 1 < L) {    // next cell's lines on their way while this one is computed
-                            prefetch_l1(pn + NTH); prefetch_l1(pw_ + NTH);
-                            if (grow_n >= 0) {
-                                prefetch_l1(ppw + NTH);
-#pragma unroll
-                                for (int d = 0; d < NW; d++)
-                                    if (d <= grow_n && d <= l + 1) { prefetch_l1(pg + NTH + d * LN); if (cont_now) prefetch_l1(pgr + NTH + d * LN); }
+                        for (int k = 0; k < MAXQ; k++) {
+                            eotk[k] = T(0.0);
+                            if (k < nq) {
+                                const int ts = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx];
+                                if (ts >= 0) eotk[k] = EOT(ts);
                             }
                         }
-                        T cons[MAXX];
-#pragma unroll
-                        for (int x = 0; x < MAXX; x++) cons[x] = T(0.0);
-                        if (prey_now) {     // R/action_predate.R:335-406
-                            const T B0 = num * wgt;
+                        unsigned lN = 0;
+                        for (int l = 0; l < L; l++, pn += NTH, pw_ += NTH, lN += NTH) {
+                            const T num = *pn;
+                            const T B0 = num * *pw_;
                             T tp(0.0), fx[MAXX];
 #pragma unroll
                             for (int x = 0; x < MAXX; x++) fx[x] = T(0.0);
@@ -415,48 +402,74 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                             T cr = tp / avoid_zero(B0);
                             cr = dif_pmax_c(cr, 0.95, -1e3);
                             const T tpn = B0 * cr;
-                            num = num * (1.0 - cr);
+                            *pn = num * (1.0 - cr);
                             if (is_us) { o1 = o1 + tp; o2 = o2 + tpn; }
                             if (catch_now) {
                                 const T cc = 1.0 / avoid_zero(tp) * tpn * B0;      // consconv * B0
 #pragma unroll
-                                for (int x = 0; x < MAXX; x++) cons[x] = fx[x] * cc;
+                                for (int x = 0; x < MAXX; x++)
+                                    if (((xact >> x) & 1) && A.w_x_kind[x] == 0) W(A.t_x[x] + c0 + col * L + l) = fx[x] * cc;
                             }
                         }
-                        num = num * mortf;
+                    }
+                    if (is_us) us_tot = us_tot + (o1 - o2);
+                } else if (catch_now) {
+                    for (int x = 0; x < A.NX; x++)
+                        if (((xact >> x) & 1) && A.w_x_kind[x] == 0)
+                            for (int i = 0; i < ncol * L; i++) W(A.t_x[x] + c0 + i) = T(0.0);       // no landings: cons = 0
+                }
+                if (!has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0) continue;
+
+                // ---------- natural mortality, growth (+ maturing split), hand-over, renewal, collect vectors.
+                // Length growth only looks DOWN the length axis, so walking l from the top the update is in
+                // place: every source l - d is still the old value when l is rebuilt. Columns are the inner
+                // loop: the band P(l - d -> l) and the weight gains are loaded once per l for all columns.
+                const int gsz = (grow_n + 1) * L;
+                const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
+                const T* pg = ws + (unsigned)((cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz + (L - 1)) * NTH;     // staying part, [d][l]
+                const T* pgr = ws + (unsigned)(A.t_gr[s] + idt * gsz + (L - 1)) * NTH;                              // maturing part
+                const T* ppw = ws + (unsigned)(A.t_pw[s] + (L - 1)) * NTH;
+                const T* pmort = ws + (unsigned)(A.t_mort[s] + idt * ncol) * NTH;
+                const int4* cinc = A.t_colinc + A.t_colbase[s];
+                for (int l = L - 1; l >= 0; l--, pg -= NTH, pgr -= NTH, ppw -= NTH) {
+                    T gt[NW], grt[NW], dwt[NW];
+#pragma unroll
+                    for (int d = 0; d < NW; d++) {
+                        gt[d] = T(0.0); grt[d] = T(0.0); dwt[d] = T(0.0);
+                        if (d <= grow_n && d <= l) {
+                            gt[d] = pg[d * LWS];
+                            if (cont_now) grt[d] = pgr[d * LWS];
+                            dwt[d] = wal * (ppw[0] - *(ppw - d * NTH));        // walpha (l^wbeta - (l-d)^wbeta), R/action_grow.R:58-71
+                        }
+                    }
+                    T* pn = ws + (unsigned)(A.t_num + c0 + l) * NTH;
+                    T* pw_ = ws + (unsigned)(A.t_wgt + c0 + l) * NTH;
+                    T* ptn = ws + (unsigned)(A.t_tn + A.w_tr_off[s] + l) * NTH;
+                    T* ptw = ws + (unsigned)(A.t_tw + A.w_tr_off[s] + l) * NTH;
+                    int aidx = 0, ridx = 0;
+                    for (int col = 0; col < ncol; col++, pn += LWS, pw_ += LWS, ptn += LWS, ptw += LWS) {
+                        const T mortf = has_mort ? pmort[col * NTH] : T(1.0);
+                        T num, wgt;
                         if (grow_n >= 0) {
                             // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d
-#pragma unroll
-                            for (int d = NW - 1; d > 0; d--) { wn[d] = wn[d - 1]; ww[d] = ww[d - 1]; pwv[d] = pwv[d - 1]; if constexpr (CONSTMAT) wm[d] = wm[d - 1]; }
-                            ww[0] = wgt; wn[0] = num; pwv[0] = *ppw;
-                            if constexpr (CONSTMAT) {
-                                wm[0] = T(0.0);
-                                if (const_now) {
-                                    // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
-                                    T mat_l(0.0);
-                                    if (msl[0] >= 0) mat_l = SLOT(msl[0]) * (R[St[G3S_MIDLEN_ROFF] + l] - SLOT(msl[1]));
-                                    T ratio = 1.0 / (1.0 + xexp(T(0.0) - mat_l - agec));
-                                    wn[0] = num * (1.0 - ratio);
-                                    wm[0] = num * ratio;
-                                }
-                            }
                             T an(0.0), aw(0.0), bn(0.0), bw(0.0);
 #pragma unroll
                             for (int d = 0; d < NW; d++) {
                                 if (d <= grow_n && d <= l) {
-                                    const T g = pg[d * LN];
-                                    const T wsrc = wal * (pwv[0] - pwv[d]) + ww[d];
+                                    const T ns = *(pn - d * NTH) * mortf;
+                                    const T wsrc = dwt[d] + *(pw_ - d * NTH);
                                     if (cont_now) {
-                                        const T gr = pgr[d * LN];
-                                        const T w = wsrc * wn[d];
-                                        an = an + gr * wn[d]; aw = aw + gr * w;
-                                        bn = bn + g * wn[d]; bw = bw + g * w;
+                                        const T w = wsrc * ns;
+                                        an = an + grt[d] * ns; aw = aw + grt[d] * w;
+                                        bn = bn + gt[d] * ns; bw = bw + gt[d] * w;
                                     } else if (CONSTMAT && const_now) {
-                                        const T n1 = wm[CONSTMAT ? d : 0] * g, n2 = wn[d] * g;
+                                        // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
+                                        const T ratio = W(A.t_cmat[s] + col * L + l - d);
+                                        const T n1 = (ns * ratio) * gt[d], n2 = (ns * (1.0 - ratio)) * gt[d];
                                         an = an + n1; aw = aw + wsrc * n1;
                                         bn = bn + n2; bw = bw + wsrc * n2;
                                     } else {
-                                        const T n2 = wn[d] * g;
+                                        const T n2 = ns * gt[d];
                                         bn = bn + n2; bw = bw + wsrc * n2;
                                     }
                                 }
@@ -465,43 +478,45 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                             if (trans_now) {
                                 *ptn = an; *ptw = aw / avoid_zero(an);
                                 // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
-                                T rem = an;
-                                for (int k = A.rem_off[cell]; A.rem_slots[k] >= 0; k++) rem = rem - an * SLOT(A.rem_slots[k]);
-                                num = num + rem;
+                                num = num + an * W(A.t_remf + A.t_colbase[s] + col);
                             }
+                        } else {
+                            num = *pn * mortf; wgt = *pw_;
                         }
-                        // ---- g3a_step_transition (R/action_mature.R:78-134)
+                        // ---- g3a_step_transition (R/action_mature.R:78-134): maturing fish arriving from their source column
                         if (inc_now) {
-                            const int src = A.w_inc_tr[cell];
-                            if (src >= 0 && ((A.inc_mask[cell] >> step) & 1)) {
-                                const T moved = W(A.t_tn + src) * SLOT(A.inc_slot[cell]);
-                                wgt = ratio_add_pop(wgt, num, W(A.t_tw + src), moved);
+                            const int4 ci = cinc[col];
+                            if (ci.x >= 0 && ((ci.z >> step) & 1)) {
+                                const T moved = W(A.t_tn + ci.x + l) * SLOT(ci.y);
+                                wgt = ratio_add_pop(wgt, num, W(A.t_tw + ci.x + l), moved);
                                 num = num + moved;
                             }
                         }
                         // ---- g3a_renewal (R/action_renewal.R:166-188)
-                        if (ren_r >= 0) {
-                            const T rn = W(A.t_rd[s] + ren_r * L + l) * ren_f;
-                            wgt = ratio_add_pop(wgt, num, W(A.t_rw[s] + ren_r * L + l), rn);
-                            num = num + rn;
-                        }
+                        if (ren_mask)
+                            for (int r = 0; r < n_renew; r++)
+                                if (((ren_mask >> r) & 1) && aidx == I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_AGE_IDX]) {
+                                    const int fs = I[I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * narea + ridx];
+                                    if (fs >= 0) {
+                                        const T rn = W(A.t_rd[s] + r * L + l) * SLOT(fs);
+                                        wgt = ratio_add_pop(wgt, num, W(A.t_rw[s] + r * L + l), rn);
+                                        num = num + rn;
+                                    }
+                                }
                         *pn = num; *pw_ = wgt;
                         // ---- collect vectors for g3l_distribution (R/likelihood_distribution.R:275-287)
                         if (xact) {
-                            T inv_w(0.0);
-                            if (catch_now) inv_w = 1.0 / avoid_zero(wgt);
+                            const int cell = c0 + col * L + l;
 #pragma unroll
                             for (int x = 0; x < MAXX; x++)
                                 if ((xact >> x) & 1) {
-                                    T xv;
-                                    if (A.w_x_kind[x] == 0) xv = A.w_x_unit[x] == 0 ? cons[x] * inv_w : cons[x];
-                                    else xv = A.w_x_unit[x] == 0 ? num : num * wgt;
-                                    W(A.t_x[x] + cell) = xv;
+                                    if (A.w_x_kind[x] == 0) { if (A.w_x_unit[x] == 0 && nq > 0) W(A.t_x[x] + cell) = W(A.t_x[x] + cell) / avoid_zero(wgt); }
+                                    else W(A.t_x[x] + cell) = A.w_x_unit[x] == 0 ? num : num * wgt;
                                 }
                         }
+                        if (++aidx == nage) { aidx = 0; ridx++; }
                     }
                 }
-                if (is_us && prey_now) us_tot = us_tot + (o1 - o2);
             }
 
             // ================= g3l_distribution collect: model[dest] += lgmatrix . x (R/likelihood_distribution.R:288-364)

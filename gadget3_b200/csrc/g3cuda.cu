@@ -218,6 +218,13 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
     }
     A.t_ctot = take(A.NNLL);
     for (int x = 0; x < MAXX; x++) A.t_x[x] = x < A.NX ? take(A.NC) : 0;
+    int ncolg = 0;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        A.t_colbase[s] = ncolg; ncolg += St[G3S_NAGE] * St[G3S_NAREA];
+        A.t_cmat[s] = (St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0 && St[G3S_MAT_KIND] == G3MAT_CONSTANT) ? take(St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA]) : 0;
+    }
+    A.t_remf = take(ncolg);
     return off;
 }
 
@@ -231,16 +238,17 @@ int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStr
     if (per_sm < 1) return fail(G3CUDA_EUNSUPP, "thread kernel does not fit one SM");
     // One block per SM, sized so that the batch splits into equally full waves: an evaluation is
     // one thread for its whole life, so a ragged last wave would idle most of the machine.
-    const long long slots = (long long)g3::TPB * m->num_sms;
+    const int sms = std::min<int>(m->num_sms, (int)(g3::WS_STRIDE / g3::TPB));
+    const long long slots = (long long)g3::TPB * sms;
     const long long waves = (work + slots - 1) / slots;
     long long per_wave = (work + waves - 1) / waves;
-    long long grid = std::min<long long>(m->num_sms, (per_wave + 31) / 32);
+    long long grid = std::min<long long>(sms, (per_wave + 31) / 32);
     if (grid < 1) grid = 1;
     int block = (int)(((per_wave + grid - 1) / grid + 31) / 32 * 32);
     block = std::max(32, std::min(block, g3::TPB));
-    if ((double)m->t_entries * (double)grid * block >= 4294967295.0)
+    if ((double)m->t_entries * (double)g3::WS_STRIDE >= 4294967295.0)
         return fail(G3CUDA_EUNSUPP, "evaluation workspace too large for 32-bit element indexing (%d entries)", m->t_entries);
-    const size_t need = (size_t)m->t_entries * sizeof(T) * (size_t)grid * block;
+    const size_t need = (size_t)m->t_entries * sizeof(T) * (size_t)g3::WS_STRIDE;
     if (need > m->t_ws_bytes) {
         // the workspace may still be in use by an earlier asynchronous launch on another stream
         CUDA_TRY(cudaDeviceSynchronize());
@@ -595,6 +603,41 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         // the fused pass hands maturing fish over within one sweep: sources must come before destinations
         for (int c = 0; c < A.NC; c++) if (inc_src[c] >= 0 && cell[inc_src[c]].x >= cell[c].x) m->thread_ok = false;
         m->t_entries = make_tlayout(m, A);
+        // hand-over per COLUMN: every cell of a destination column must be fed by the same length of one source column
+        {
+            std::vector<int4> colinc;
+            std::vector<int32_t> tr_of_cell(A.NC, -1);
+            int ntr = 0;
+            for (int s = 0; s < A.NS; s++) {
+                const int32_t* St = stock(s);
+                int ncell = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+                if (St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0) { for (int i = 0; i < ncell; i++) tr_of_cell[St[G3S_CELL_OFF] + i] = ntr + i; ntr += ncell; }
+            }
+            for (int s = 0; s < A.NS; s++) {
+                const int32_t* St = stock(s);
+                int L = St[G3S_L];
+                for (int col = 0; col < St[G3S_NAGE] * St[G3S_NAREA]; col++) {
+                    int c00 = St[G3S_CELL_OFF] + col * L;
+                    int4 e = make_int4(-1, 0, 0, 0);
+                    if (inc_src[c00] >= 0) e = make_int4(tr_of_cell[inc_src[c00]], inc_slot[c00], inc_mask[c00], 0);
+                    for (int l = 0; l < L; l++) {
+                        int c = c00 + l;
+                        bool ok = inc_src[c] < 0 ? e.x < 0 : (e.x >= 0 && tr_of_cell[inc_src[c]] == e.x + l && inc_slot[c] == e.y && inc_mask[c] == e.z);
+                        if (!ok) m->thread_ok = false;
+                        if (rem_off[c] != rem_off[c00] && l > 0) {       // remainder ratios must be the same down a column
+                            int a = rem_off[c], b = rem_off[c00];
+                            while (rem_slots[a] >= 0 && rem_slots[a] == rem_slots[b]) { a++; b++; }
+                            if (rem_slots[a] != rem_slots[b]) m->thread_ok = false;
+                        }
+                    }
+                    colinc.push_back(e);
+                }
+            }
+            int4* d_ci = dev_copy(colinc);
+            if (!d_ci) return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
+            m->owned.push_back(d_ci); A.t_colinc = d_ci;
+            m->t_entries = make_tlayout(m, A);
+        }
         // one renewal per (column, step) is what the fused pass applies
         for (int s = 0; s < A.NS; s++) {
             const int32_t* St = stock(s);
