@@ -433,6 +433,11 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                 const int4* cinc = A.t_colinc + A.t_colbase[s];
                 for (int l = L - 1; l >= 0; l--, pg -= NTH, pgr -= NTH, ppw -= NTH) {
                     T gt[NW], grt[NW], dwt[NW];
+                    if (l > 0 && grow_n >= 0) {     // next length's band on its way
+#pragma unroll
+                        for (int d = 0; d < NW; d++)
+                            if (d <= grow_n && d < l) { prefetch_l1(pg - NTH + d * LWS); if (cont_now) prefetch_l1(pgr - NTH + d * LWS); }
+                    }
 #pragma unroll
                     for (int d = 0; d < NW; d++) {
                         gt[d] = T(0.0); grt[d] = T(0.0); dwt[d] = T(0.0);
@@ -447,7 +452,19 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                     T* ptn = ws + (unsigned)(A.t_tn + A.w_tr_off[s] + l) * NTH;
                     T* ptw = ws + (unsigned)(A.t_tw + A.w_tr_off[s] + l) * NTH;
                     int aidx = 0, ridx = 0;
+                    T* const pn_first = pn; T* const pw_first = pw_;
                     for (int col = 0; col < ncol; col++, pn += LWS, pw_ += LWS, ptn += LWS, ptw += LWS) {
+                        {   // the next column's (or, at the end of the sweep, the next length's first column's) sources on their way
+                            const T* qn = col + 1 < ncol ? pn + LWS : pn_first - NTH;
+                            const T* qw = col + 1 < ncol ? pw_ + LWS : pw_first - NTH;
+                            if (col + 1 < ncol || l > 0) {
+                                if (grow_n >= 0) {
+#pragma unroll
+                                    for (int d = 0; d < NW; d++)
+                                        if (d <= grow_n && d < l) { prefetch_l1(qn - d * NTH); prefetch_l1(qw - d * NTH); }
+                                } else { prefetch_l1(qn); prefetch_l1(qw); }
+                            }
+                        }
                         const T mortf = has_mort ? pmort[col * NTH] : T(1.0);
                         T num, wgt;
                         if (grow_n >= 0) {
