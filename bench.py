@@ -33,8 +33,12 @@ sys.path.insert(0, ROOT)
 METRIC = "objective_evals_per_sec"
 UNIT = "evals/s"
 # Algorithmic flop per evaluation, reference semantics (DESIGN.md "flop model")
-ALG_FLOP = {"C1": 4.39e6, "C2": 2.60e7}
-WORKLOAD = {"C1": "introduction-single-stock, nll only", "C2": "multiple-substocks imm/mat, nll only"}
+ALG_FLOP = {"C1": 4.39e6, "C2": 2.60e7, "C3": 2.79e9, "C4": 1.31e8}
+WORKLOAD = {"C1": "introduction-single-stock, nll only", "C2": "multiple-substocks imm/mat, nll only",
+            "C3": "multiple-substocks imm/mat, nll + forward-mode gradient over all 71 optimised parameters",
+            "C4": "ling-style: 2 stocks x 35 length groups, 3 fleets, constant maturity, 40 years quarterly, nll only"}
+MODEL_OF = {"C1": "C1", "C2": "C2", "C3": "C2", "C4": "C4"}
+DEFAULT_BATCH = {"C1": 65536, "C2": 65536, "C3": 8192, "C4": 65536}
 
 
 def parse():
@@ -44,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(ALG_FLOP))
-    ap.add_argument("--batch", type=int, default=65536, help="parameter vectors per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="parameter vectors per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -94,7 +98,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference(model, params, config, batch_fn, seconds_target=12.0):
+def cpu_reference(model, params, config, batch_fn, seconds_target=12.0, tix=None):
     """Time the CPU implementation of the path on all host cores over a bounded sample."""
     from oracle import oracle_lib as ol
     kind, lib = "port", None
@@ -104,12 +108,12 @@ def cpu_reference(model, params, config, batch_fn, seconds_target=12.0):
         lib = ol.load()
     orc = ol.Oracle(*model.pack(params), lib=lib)
     cores = os.cpu_count() or 1
-    probe = batch_fn(4 * cores, 99)
-    t = time.perf_counter(); orc.eval_batch(probe, nthreads=cores); per = (time.perf_counter() - t) / len(probe)
-    n = int(min(max(seconds_target / max(per, 1e-9), 8 * cores), 1 << 16))
+    probe = batch_fn(2 * cores, 99)
+    t = time.perf_counter(); orc.eval_batch(probe, tangent_idx=tix, nthreads=cores); per = (time.perf_counter() - t) / len(probe)
+    n = int(min(max(seconds_target / max(per, 1e-9), 2 * cores), 1 << 16))
     n = max(cores, n // cores * cores)
     sample = batch_fn(n, 7)
-    t = time.perf_counter(); nll, _, _ = orc.eval_batch(sample, nthreads=cores); dt = time.perf_counter() - t
+    t = time.perf_counter(); nll, _, _ = orc.eval_batch(sample, tangent_idx=tix, nthreads=cores); dt = time.perf_counter() - t
     assert np.isfinite(nll).all()
     return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{n} vectors of the {config} batch, {cores} threads, {dt:.1f} s wall"}, orc
@@ -122,7 +126,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     from gadget3_b200.configs import CONFIGS, parameter_batch
-    model, params = CONFIGS[a.config]()
+    if a.batch <= 0:
+        a.batch = DEFAULT_BATCH[a.config]
+    want_grad = a.config == "C3"
+    model, params = CONFIGS[MODEL_OF[a.config]]()
     opt = params.optimised_indices()
     base = params.values()
 
@@ -145,16 +152,17 @@ def main():
         except Exception:
             lib = ol.load()
         orc = ol.Oracle(*model.pack(params), lib=lib)
-        probe = batch_fn(4 * cores, 99)
-        t = time.perf_counter(); orc.eval_batch(probe, nthreads=cores); per = (time.perf_counter() - t) / len(probe)
-        n = int(min(max(4.0 / max(per, 1e-9), 8 * cores), a.batch))     # ~4 s per step
+        tix = opt.astype(np.int32) if want_grad else None
+        probe = batch_fn(2 * cores, 99)
+        t = time.perf_counter(); orc.eval_batch(probe, tangent_idx=tix, nthreads=cores); per = (time.perf_counter() - t) / len(probe)
+        n = int(min(max(4.0 / max(per, 1e-9), 2 * cores), a.batch))     # ~4 s per step
         n = max(cores, n // cores * cores)
         sample = batch_fn(n, 7)
         for _ in range(a.warmup):
-            orc.eval_batch(sample[: max(cores, n // 8)], nthreads=cores)
+            orc.eval_batch(sample[: max(cores, n // 8)], tangent_idx=tix, nthreads=cores)
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            orc.eval_batch(sample, nthreads=cores)
+            orc.eval_batch(sample, tangent_idx=tix, nthreads=cores)
         dt = time.perf_counter() - t0
         v = n * a.steps / dt
         print(json.dumps({
@@ -185,6 +193,9 @@ def main():
     host = [torch.from_numpy(batch_fn(B, 1000 + 17 * rank + i)).pin_memory() for i in range(nb)]
     d_par = [x.to(dev, non_blocking=True) for x in host]
     d_nll = torch.empty(B, dtype=torch.float64, device=dev)
+    Kt = len(opt) if want_grad else 0
+    d_tidx = torch.from_numpy(opt.astype(np.int32)).to(dev) if want_grad else None
+    d_grad = torch.empty((B, Kt), dtype=torch.float64, device=dev) if want_grad else None
     stream = torch.cuda.current_stream(dev)
     torch.cuda.synchronize(dev)
 
@@ -196,7 +207,11 @@ def main():
     peak_tflops = h.lib.g3cuda_fp64_peak_tflops(local)
 
     def step_device(i):
-        h.eval_batch_device(d_par[i % nb].data_ptr(), B, d_nll.data_ptr(), stream=stream.cuda_stream)
+        if want_grad:
+            h.eval_batch_device(d_par[i % nb].data_ptr(), B, d_nll.data_ptr(), d_tidx=d_tidx.data_ptr(), K=Kt,
+                                d_grad=d_grad.data_ptr(), stream=stream.cuda_stream)
+        else:
+            h.eval_batch_device(d_par[i % nb].data_ptr(), B, d_nll.data_ptr(), stream=stream.cuda_stream)
 
     for i in range(a.warmup):
         step_device(i)
@@ -225,7 +240,7 @@ def main():
 
     def step_e2e(i):
         full = host[i % nb].numpy()                       # pinned; the H2D copy happens inside eval_batch
-        nll, _, _ = h.eval_batch(full)
+        nll, _, grad = h.eval_batch(full, tangent_idx=opt.astype(np.int32) if want_grad else None)
         if world > 1:                                     # every rank ends up with the whole job's nll vector
             t = torch.from_numpy(nll).to(dev)
             out = [torch.empty_like(t) for _ in range(world)]
@@ -264,10 +279,10 @@ def main():
         "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": dict(cfg, l2="inputs larger than L2: %d distinct parameter batches (%.0f MB) rotate" % (nb, nb * B * P * 8 / 1e6)),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * P * 8), "d2h_bytes_per_step": int(B * 8)},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(B * P * 8), "d2h_bytes_per_step": int(B * 8 * (1 + Kt))},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "fp64", "kernel": "g3::eval_thread_kernel<double>", "achieved": achieved, "peak": peak_tflops,
+        "roofline": {"bound": "fp64", "kernel": "g3::eval_thread_kernel<Dual<4>> (+ one <double> launch for the values)" if want_grad else "g3::eval_thread_kernel<double>", "achieved": achieved, "peak": peak_tflops,
                      "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops > 0 else None,
                      "peak_source": "DFMA-chain microbenchmark run live on this GPU (g3cuda_fp64_peak_tflops); "
                                     "MEASURED_PEAKS.json has no fp64 entry",
@@ -277,7 +292,7 @@ def main():
                      "traffic": None},
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cb, orc = cpu_reference(model, params, a.config, batch_fn)
+        cb, orc = cpu_reference(model, params, a.config, batch_fn, tix=opt.astype(np.int32) if want_grad else None)
         # spot-check the timed batch against the checker (not part of any timed region)
         chk = host[(a.steps - 1) % nb].numpy()[:64]
         o = orc.eval_batch(chk, nthreads=cb["cores"])[0]

@@ -8,10 +8,12 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import (g3_areas, g3_fleet, g3_init_val, g3_stock, g3_timeareadata, g3_to_cuda, g3a_age,
-               g3a_grow_impl_bbinom, g3a_growmature, g3a_initialconditions_normalcv,
-               g3a_mature_continuous, g3a_naturalmortality, g3a_predate_catchability_totalfleet,
-               g3a_predate_fleet, g3a_renewal_normalcv, g3a_report_detail, g3a_time,
+from . import (g3_areas, g3_fleet, g3_init_val, g3_parameterized, g3_stock, g3_timeareadata, g3_to_cuda,
+               g3a_age, g3a_grow_impl_bbinom, g3a_grow_lengthvbsimple, g3a_grow_weightsimple,
+               g3a_growmature, g3a_initialconditions_normalcv, g3a_initialconditions_normalparam,
+               g3a_mature_constant, g3a_mature_continuous, g3a_naturalmortality,
+               g3a_predate_catchability_totalfleet, g3a_predate_fleet, g3a_renewal_normalcv,
+               g3a_renewal_normalparam, g3a_renewal_vonb_recl, g3a_report_detail, g3a_time,
                g3l_abundancedistribution, g3l_bounds_penalty, g3l_catchdistribution,
                g3l_distribution_sumofsquares, g3l_distribution_surveyindices_log, g3l_understocking,
                g3s_age, g3s_livesonareas, g3_suitability_exponentiall50)
@@ -215,4 +217,94 @@ def parameter_batch(params, B, seed=2026, width=0.10):
     return np.clip(P, lo[None, :], up[None, :])
 
 
-CONFIGS = {"C1": build_c1, "C2": build_c2}
+def build_c4(seed=123):
+    """Ling-style model (structure of inttest/codegeneration/run.R:17-183 as BASELINE.json config 4
+    describes it): 2 stocks on 35 length groups, maxlengthgroupgrowth 15, constant maturity with the
+    hand-over on the last step of the year, 3 total-catch fleets with exponentiall50 suitability,
+    one length distribution per fleet and two log survey indices, 40 years of quarterly steps."""
+    rng = np.random.default_rng(seed)
+    years = list(range(1979, 2019))
+    areas = g3_areas(["area1"])
+    lg = range(20, 157, 4)
+    ling_imm = g3s_livesonareas(g3s_age(g3_stock({"species": "ling", "maturity": "imm"}, lg), 3, 10), areas)
+    ling_mat = g3s_livesonareas(g3s_age(g3_stock({"species": "ling", "maturity": "mat"}, lg), 5, 15), areas)
+    stocks = [ling_imm, ling_mat]
+
+    def grow():
+        return g3a_grow_impl_bbinom(g3a_grow_lengthvbsimple(by_stock="species"), g3a_grow_weightsimple(),
+                                    beta_f=g3_parameterized("bbin", by_stock="species"), maxlengthgroupgrowth=15)
+
+    def init(st):
+        return g3a_initialconditions_normalparam(
+            st, mean_f=g3a_renewal_vonb_recl(by_stock="species"),
+            stddev_f=g3_parameterized("init.sd", by_stock=True, by_age=True, value=10, optimise=False))
+
+    actions = [
+        g3a_time(1979, 2018, [3, 3, 3, 3]),
+        init(ling_imm),
+        g3a_renewal_normalparam(ling_imm, mean_f=g3a_renewal_vonb_recl(by_stock="species"),
+                                stddev_f=g3_parameterized("rec.sd", by_stock=True, value=8, optimise=False),
+                                run_step=1),
+        g3a_growmature(ling_imm, grow(),
+                       maturity_f=g3a_mature_constant(alpha=g3_parameterized("mat1", by_stock="species") * 0.001,
+                                                      l50=g3_parameterized("mat2", by_stock="species")),
+                       output_stocks=[ling_mat]),
+        g3a_naturalmortality(ling_imm),
+        g3a_age(ling_imm, output_stocks=[ling_mat]),
+        init(ling_mat),
+        g3a_growmature(ling_mat, grow()),
+        g3a_naturalmortality(ling_mat),
+        g3a_age(ling_mat),
+        g3l_understocking(stocks, nll_breakdown=True),
+    ]
+    edges = list(range(20, 157, 4))
+    for fi, (fname, lmean) in enumerate((("lln", 90), ("bmt", 70), ("gil", 110))):
+        fleet = g3s_livesonareas(g3_fleet(fname), areas)
+        yy = np.repeat(years, 4)
+        st = np.tile([1, 2, 3, 4], len(years))
+        landings = dict(year=[int(y) for y in yy], step=[int(x) for x in st], area=["area1"] * len(yy),
+                        total_weight=list((fi + 1) * 2e3 * np.tile([1.0, 2.0, 3.0, 4.0], len(years))
+                                          * rng.uniform(0.8, 1.2, len(yy))))
+        actions.append(g3a_predate_fleet(
+            fleet, stocks, suitabilities=g3_suitability_exponentiall50(by_stock="species"),
+            catchability_f=g3a_predate_catchability_totalfleet(
+                g3_timeareadata("landings_" + fname, landings, "total_weight", areas=areas))))
+        ns = 300
+        yy2 = np.repeat(yy, ns)
+        st2 = np.repeat(st, ns)
+        ln = np.clip(rng.normal(lmean, 25, len(yy2)), 20, 400)
+        ld = _count(dict(year=[int(y) for y in yy2], step=[int(x) for x in st2], length=_cut(ln, edges)),
+                    ["year", "step", "length"])
+        actions.append(g3l_catchdistribution("ldist_" + fname, ld, fleets=[fleet], stocks=stocks,
+                                             function_f=g3l_distribution_sumofsquares(), nll_breakdown=True))
+    for nm, lab in (("si_20_52", "[20,52)"), ("si_52_inf", "[52,Inf)")):
+        si = dict(year=list(years), step=[2] * len(years), area=["area1"] * len(years), length=[lab] * len(years),
+                  weight=list(rng.uniform(1e5, 1e6, len(years))))
+        actions.append(g3l_abundancedistribution(nm, si, stocks=stocks,
+                                                 function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
+                                                 area_group=areas, nll_breakdown=True))
+    actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "*.Linf", 160, spread=0.2)
+    p = g3_init_val(p, "*.K", 0.09, lower=0.04, upper=0.2)
+    p = g3_init_val(p, "*.recl", 12, lower=8, upper=20)
+    p = g3_init_val(p, "recage", 3, optimise=False)
+    p = g3_init_val(p, "*.walpha", 2.27567436711055e-06, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3.20200445996187, optimise=False)
+    p = g3_init_val(p, "*.bbin", 60, lower=1, upper=500)
+    p = g3_init_val(p, "*.M.#", 0.15, lower=0.01, upper=1)
+    p = g3_init_val(p, "*.init.scalar", 200, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.001, upper=10)
+    p = g3_init_val(p, "init.F", 0.4, lower=0.1, upper=1)
+    p = g3_init_val(p, "*.mat1", 70, lower=10, upper=200)
+    p = g3_init_val(p, "*.mat2", 75, lower=40, upper=120)
+    p = g3_init_val(p, "*.rec.scalar", 400, optimise=False)
+    p = g3_init_val(p, "*.rec.#", 1, lower=0.001, upper=10)
+    p = g3_init_val(p, "*.rec.proj", 1)
+    p = g3_init_val(p, "*.*.alpha", 0.5, lower=0.01, upper=2)
+    p = g3_init_val(p, "*.*.l50", 50, spread=0.5)
+    return model, p
+
+
+CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4}

@@ -66,6 +66,7 @@ struct g3cuda_model {
     // smem element counts
     int sm_elems = 0;
     size_t smem_optin = 0;
+    bool cta_ok_double = false, cta_ok_dual = false;    // CTA kernel: shared-memory layout fits (values / duals)
     bool thread_ok = false;             // model fits the thread-per-evaluation kernel
     int t_entries = 0, t_maxn = 0;      // workspace entries per thread; widest growth band
     void* t_ws = nullptr; size_t t_ws_bytes = 0;
@@ -309,7 +310,7 @@ int launch_variant(g3cuda_model* m, const Layout& lay, int nblocks_hint, cudaStr
 template <class T>
 int launch(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStream_t st) {
     const bool is_double = std::is_same<T, double>::value;
-    if (m->thread_ok && !call.report && (m->force_kernel == 0 || m->force_kernel == 3) && (is_double || m->force_kernel == 3)) {
+    if (m->thread_ok && !call.report && (m->force_kernel == 0 || m->force_kernel == 3) && (is_double || m->force_kernel == 3 || work >= 16384 || !m->cta_ok_dual)) {
         g3::KArgs a = m->base;
         a.par = call.par; a.B = call.B; a.tangent_idx = call.tangent_idx; a.K = call.K;
         a.nll = call.nll; a.comp = call.comp; a.grad = call.grad; a.report = nullptr;
@@ -324,6 +325,8 @@ int launch(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStream_t 
             return launch_warp_variant<T, 2>(m, lay, work, st);
         }
     }
+    if (!(is_double ? m->cta_ok_double : m->cta_ok_dual))
+        return fail(G3CUDA_EUNSUPP, "the CTA-per-evaluation kernel does not fit this model%s", call.report ? " (needed for g3cuda_report)" : "");
     Layout lay = make_layout(m, sizeof(T));
     // per-call fields
     lay.a.par = call.par; lay.a.B = call.B; lay.a.tangent_idx = call.tangent_idx; lay.a.K = call.K;
@@ -358,7 +361,7 @@ int check_spec(const g3cuda_spec* spec) {
     if (I[G3H_NSTOCK] < 1 || I[G3H_NSTOCK] > g3::MAXS) return fail(G3CUDA_EUNSUPP, "number of stocks %d outside 1..%d", I[G3H_NSTOCK], g3::MAXS);
     if (I[G3H_NCOMP] > g3::MAXC) return fail(G3CUDA_EUNSUPP, "more than %d likelihood components", g3::MAXC);
     if (I[G3H_NXBUF] > g3::MAXX) return fail(G3CUDA_EUNSUPP, "more than %d collect vectors", g3::MAXX);
-    if (I[G3H_NCELL] > 1024) return fail(G3CUDA_EUNSUPP, "%d stock cells: more than 1024 are not supported yet", I[G3H_NCELL]);
+
     if (I[G3H_NSTEPS] > 31) return fail(G3CUDA_EUNSUPP, "more than 31 steps per year");
     return G3CUDA_OK;
 }
@@ -700,7 +703,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
 
     int need = std::max({A.NC, maxnd, maxnt, A.maxL, 32});
     m->nthreads = (need + 31) / 32 * 32;
-    if (m->nthreads > 1024) return bail(fail(G3CUDA_EUNSUPP, "model needs %d threads per evaluation (> 1024)", m->nthreads));
+    // (more than 1024 cells: the CTA kernel is unavailable; the thread kernel has no such limit)
 
     // ---- upload
     cudaDeviceProp prop;
@@ -719,9 +722,11 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
         return bail(fail(G3CUDA_ECUDA, "stream/event creation failed"));
-    Layout lay = make_layout(m, sizeof(DualT));
-    if (lay.bytes > (size_t)prop.sharedMemPerBlockOptin)
-        return bail(fail(G3CUDA_EUNSUPP, "model needs %zu bytes of shared memory per evaluation (limit %zu)", lay.bytes, (size_t)prop.sharedMemPerBlockOptin));
+    m->cta_ok_double = m->nthreads <= 1024 && make_layout(m, sizeof(double)).bytes <= (size_t)prop.sharedMemPerBlockOptin;
+    m->cta_ok_dual = m->nthreads <= 1024 && make_layout(m, sizeof(DualT)).bytes <= (size_t)prop.sharedMemPerBlockOptin;
+    if (!m->thread_ok && !m->cta_ok_double)
+        return bail(fail(G3CUDA_EUNSUPP, "model fits neither evaluation kernel (%d cells, %zu bytes of shared memory per evaluation, limit %zu)",
+                         A.NC, make_layout(m, sizeof(double)).bytes, (size_t)prop.sharedMemPerBlockOptin));
     *out = m;
     return G3CUDA_OK;
 }

@@ -19,7 +19,7 @@ GRAD_RTOL = 1e-8
 @pytest.fixture(scope="module")
 def setups(oracle_lib):
     out = {}
-    for n in ("C1", "C2"):
+    for n in ("C1", "C2", "C4"):
         model, p = CONFIGS[n]()
         fn = g3_cuda_adfun(model, p, device=0)
         out[n] = (model, p, fn, Oracle(*model.pack(p)))
@@ -38,9 +38,13 @@ def _us_weight(model):
 
 
 @pytest.mark.parametrize("kernel", [1, 2, 3], ids=["cta_kernel", "warp_kernel", "thread_kernel"])
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
 def test_nll_and_components(setups, name, kernel):
     model, p, fn, orc = setups[name]
+    if name == "C4" and kernel == 2:
+        with pytest.raises(Exception, match="does not fit"):      # 35 length groups: wider than a warp
+            fn.handle.set_kernel(kernel)
+        return
     fn.handle.set_kernel(kernel)
     try:
         _check_nll_and_components(model, p, fn, orc)
@@ -49,7 +53,8 @@ def test_nll_and_components(setups, name, kernel):
 
 
 def _check_nll_and_components(model, p, fn, orc):
-    P = np.vstack([fn.par[None, :], parameter_batch(p, 255, seed=2026)])
+    nvec = 63 if len(model.stock_names) and sum(L * A_ * R for L, A_, R in model.stock_shapes) > 400 else 255
+    P = np.vstack([fn.par[None, :], parameter_batch(p, nvec, seed=2026)])
     full = fn.full_par(P)
     g_nll, g_comp, _ = fn.handle.eval_batch(full, want_comp=True)
     o_nll, o_comp, _ = orc.eval_batch(full, want_comp=True, nthreads=8)
@@ -64,34 +69,42 @@ def _check_nll_and_components(model, p, fn, orc):
     us_tol = _us_tolerance(model, p, o_comp[:, -2])
     assert (np.abs(g_comp[:, -2] - o_comp[:, -2]) <= us_tol).all()
     assert (np.abs(g_nll - o_nll) <= NLL_RTOL * np.abs(o_nll) + w * us_tol).all()
-    # and most vectors (no active overconsumption) meet the plain 1e-10 bound outright
-    assert np.median(_rel(g_nll, o_nll)) < 1e-12
+    # away from that one ill-conditioned term the agreement is near machine precision
+    assert np.median(np.abs((g_nll - w * g_comp[:, -2]) - (o_nll - w * o_comp[:, -2])) / np.abs(o_nll)) < 1e-12
 
 
 @pytest.mark.parametrize("kernel", [1, 3], ids=["cta_kernel", "thread_kernel"])
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
 def test_gradients(setups, name, kernel):
     model, p, fn, orc = setups[name]
     fn.handle.set_kernel(kernel)
     try:
-        _check_gradients(model, p, fn, orc)
+        if name == "C4" and kernel == 1:        # Dual<4> state of 665 cells does not fit one CTA's shared memory
+            with pytest.raises(Exception, match="does not fit"):
+                fn.gr_batch(parameter_batch(p, 1, seed=77))
+        else:
+            _check_gradients(model, p, fn, orc)
     finally:
         fn.handle.set_kernel(0)
 
 
 def _check_gradients(model, p, fn, orc):
-    P = parameter_batch(p, 6, seed=77)
+    nv = 2 if sum(L * A_ * R for L, A_, R in model.stock_shapes) > 400 else 6
+    P = parameter_batch(p, nv, seed=77)
     full = fn.full_par(P)
     g_nll, g_grad = fn.gr_batch(P)
     _, _, o_grad = orc.eval_batch(full, tangent_idx=fn.opt_idx.astype(np.int32), nthreads=8)
-    o_nll = orc.eval_batch(full)[0]
-    assert g_grad.shape == (6, len(fn.opt_idx))
-    assert _rel(g_nll, o_nll).max() < 1e-9
+    o_nll, o_comp, _ = orc.eval_batch(full, want_comp=True)
+    assert g_grad.shape == (nv, len(fn.opt_idx))
+    assert (np.abs(g_nll - o_nll) <= NLL_RTOL * np.abs(o_nll) + US_WEIGHT * _us_tolerance(model, p, o_comp[:, -2])).all()
     scale = np.abs(o_grad).max(axis=1, keepdims=True)
-    assert (np.abs(g_grad - o_grad) / scale).max() < GRAD_RTOL
+    # 1e-8, plus the relative conditioning of the understocking term where it is active (its gradient is
+    # 2e8 (sum tp - sum tp') d(sum tp - sum tp'): the same difference of near-equal sums as the value)
+    gtol = GRAD_RTOL + US_WEIGHT * _us_tolerance(model, p, o_comp[:, -2]) / np.abs(o_nll)
+    assert ((np.abs(g_grad - o_grad) / scale).max(axis=1) < gtol).all()
 
 
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
 def test_report_arrays(setups, name):
     model, p, fn, orc = setups[name]
     par = parameter_batch(p, 1, seed=5)[0]
@@ -105,8 +118,9 @@ def test_report_arrays(setups, name):
         m = ~np.isnan(b)
         if not m.any():
             continue
-        if k.startswith("nll_understocking"):
-            assert (1e8 * np.abs(a - b)[m]).max() < NLL_RTOL * abs(ro["nll"]), k
+        if k.startswith("nll_understocking") or k == "nll":
+            us_tol = _us_tolerance(model, p, ro["nll_understocking__wgt"].sum())
+            assert np.abs(a - b)[m].sum() <= (NLL_RTOL * abs(ro["nll"]) if k == "nll" else 0.0) + (US_WEIGHT if k == "nll" else 1.0) * us_tol, k
         else:
             scale = np.abs(b[m]).max() if m.any() else 1.0
             assert (np.abs(a - b)[m] / np.maximum(np.abs(b[m]), 1e-12 * scale)).max() < 1e-9, k
