@@ -33,12 +33,13 @@ sys.path.insert(0, ROOT)
 METRIC = "objective_evals_per_sec"
 UNIT = "evals/s"
 # Algorithmic flop per evaluation, reference semantics (DESIGN.md "flop model")
-ALG_FLOP = {"C1": 4.39e6, "C2": 2.60e7, "C3": 2.79e9, "C4": 1.31e8}
+ALG_FLOP = {"C1": 4.39e6, "C2": 2.60e7, "C3": 2.79e9, "C4": 1.31e8, "C5": 4.9e7}
 WORKLOAD = {"C1": "introduction-single-stock, nll only", "C2": "multiple-substocks imm/mat, nll only",
             "C3": "multiple-substocks imm/mat, nll + forward-mode gradient over all 71 optimised parameters",
-            "C4": "ling-style: 2 stocks x 35 length groups, 3 fleets, constant maturity, 40 years quarterly, nll only"}
-MODEL_OF = {"C1": "C1", "C2": "C2", "C3": "C2", "C4": "C4"}
-DEFAULT_BATCH = {"C1": 65536, "C2": 65536, "C3": 8192, "C4": 65536}
+            "C4": "ling-style: 2 stocks x 35 length groups, 3 fleets, constant maturity, 40 years quarterly, nll only",
+            "C5": "4-area predator-prey with migration and a stock predator, 20 years quarterly, nll only"}
+MODEL_OF = {"C1": "C1", "C2": "C2", "C3": "C2", "C4": "C4", "C5": "C5"}
+DEFAULT_BATCH = {"C1": 65536, "C2": 65536, "C3": 8192, "C4": 65536, "C5": 131072}
 
 
 def parse():

@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import (g3_areas, g3_fleet, g3_init_val, g3_parameterized, g3_stock, g3_timeareadata, g3_to_cuda,
-               g3a_age, g3a_grow_impl_bbinom, g3a_grow_lengthvbsimple, g3a_grow_weightsimple,
+               g3a_age, g3a_migrate, g3a_predate, g3a_predate_catchability_predator, g3a_grow_impl_bbinom, g3a_grow_lengthvbsimple, g3a_grow_weightsimple,
                g3a_growmature, g3a_initialconditions_normalcv, g3a_initialconditions_normalparam,
                g3a_mature_constant, g3a_mature_continuous, g3a_naturalmortality,
                g3a_predate_catchability_totalfleet, g3a_predate_fleet, g3a_renewal_normalcv,
@@ -307,4 +307,88 @@ def build_c4(seed=123):
     return model, p
 
 
-CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4}
+def build_c5(seed=123):
+    """Four-area predator-prey model (BASELINE.json config 5): prey on 20 length
+    groups x ages 1-5 and a stock predator on 8 length groups x ages 2-7, both on areas a-d, both
+    migrating every quarter (12 off-diagonal migrate.<src>.<dst> parameters each), the predator eating
+    the prey (g3a_predate + g3a_predate_catchability_predator + exponentiall50), one total-catch fleet on
+    the predator, a length distribution for the fleet and a log survey index per area; 20 years quarterly."""
+    rng = np.random.default_rng(seed)
+    years = list(range(2000, 2020))
+    areas = g3_areas(["a", "b", "c", "d"])
+    prey = g3s_livesonareas(g3s_age(g3_stock("prey", range(5, 101, 5)), 1, 5), areas)
+    pred = g3s_livesonareas(g3s_age(g3_stock("pred", range(20, 91, 10)), 2, 7), areas)
+
+    def mig(src, dst):
+        return g3_parameterized(f"migrate.{src}.{dst}", by_stock=True, value=0.3)
+
+    fleet = g3s_livesonareas(g3_fleet("f_pred"), areas)
+    yy = np.repeat(years, 4 * 4)
+    st = np.tile(np.repeat([1, 2, 3, 4], 4), len(years))
+    ar = np.tile(["a", "b", "c", "d"], len(years) * 4)
+    landings = dict(year=[int(y) for y in yy], step=[int(x) for x in st], area=list(ar),
+                    total_weight=list(rng.uniform(20, 60, len(yy))))
+    ns = 200
+    yl = np.repeat(np.repeat(years, 4), ns)
+    sl = np.tile(np.repeat([1, 2, 3, 4], ns), len(years))
+    ln = np.clip(rng.normal(55, 15, len(yl)), 20, 200)
+    ldist = _count(dict(year=[int(y) for y in yl], step=[int(x) for x in sl], length=_cut(ln, range(20, 91, 10))),
+                   ["year", "step", "length"])
+    si = dict(year=[int(y) for y in np.repeat(years, 4)], step=[2] * (4 * len(years)),
+              area=list(np.tile(["a", "b", "c", "d"], len(years))),
+              weight=list(rng.uniform(1e4, 1e5, 4 * len(years))))
+    actions = [
+        g3a_time(2000, 2019, [3, 3, 3, 3]),
+        g3a_initialconditions_normalcv(prey), g3a_initialconditions_normalcv(pred),
+        g3a_renewal_normalcv(prey), g3a_renewal_normalcv(pred),
+        g3a_naturalmortality(prey), g3a_naturalmortality(pred),
+        g3a_growmature(prey, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4)),
+        g3a_growmature(pred, g3a_grow_impl_bbinom(maxlengthgroupgrowth=2)),
+        g3a_age(prey), g3a_age(pred),
+        g3a_migrate(prey, mig), g3a_migrate(pred, mig),
+        g3a_predate(pred, [prey], suitabilities=g3_suitability_exponentiall50(),
+                    catchability_f=g3a_predate_catchability_predator()),
+        g3a_predate_fleet(fleet, [pred], suitabilities=g3_suitability_exponentiall50(),
+                          catchability_f=g3a_predate_catchability_totalfleet(
+                              g3_timeareadata("landings_f_pred", landings, "total_weight", areas=areas))),
+        g3l_understocking([prey, pred], nll_breakdown=True),
+        g3l_catchdistribution("ldist_f_pred", ldist, fleets=[fleet], stocks=[pred],
+                              function_f=g3l_distribution_sumofsquares(), nll_breakdown=True),
+        g3l_abundancedistribution("si_prey", si, stocks=[prey],
+                                  function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
+                                  area_group=areas, nll_breakdown=True),
+    ]
+    actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "prey.Linf", 90, spread=0.2)
+    p = g3_init_val(p, "pred.Linf", 100, spread=0.2)
+    p = g3_init_val(p, "*.K", 0.25, lower=0.04, upper=1.2)
+    p = g3_init_val(p, "*.t0", -0.5, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.15, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 100, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.001, upper=10)
+    p = g3_init_val(p, "*.M.#", 0.2, lower=0.01, upper=1)
+    p = g3_init_val(p, "init.F", 0.3, lower=0.1, upper=1)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.migrate.*", 0.2, lower=0, upper=0.5)
+    p = g3_init_val(p, "*.consumption.m0", 4e-6, optimise=False)
+    p = g3_init_val(p, "*.consumption.m3", 2.0, optimise=False)
+    p = g3_init_val(p, "*.halffeeding", 1e4, lower=1e2, upper=1e6)
+    p = g3_init_val(p, "*.energycontent", 1, optimise=False)
+    p = g3_init_val(p, "*.bbin", 30, lower=1, upper=500)
+    p = g3_init_val(p, "*.rec.#", 20, lower=0.1, upper=100)
+    p = g3_init_val(p, "*.rec.scalar", 10, optimise=False)
+    p = g3_init_val(p, "pred.rec.scalar", 1, optimise=False)
+    p = g3_init_val(p, "pred.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.rec.proj", 1)
+    p = g3_init_val(p, "prey.pred.alpha", 0.15, lower=0.01, upper=1)
+    p = g3_init_val(p, "prey.pred.l50", 25, lower=5, upper=60)
+    p = g3_init_val(p, "pred.f_pred.alpha", 0.2, lower=0.01, upper=1)
+    p = g3_init_val(p, "pred.f_pred.l50", 50, lower=20, upper=90)
+    return model, p
+
+
+CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5}

@@ -68,6 +68,21 @@ template <class T> __device__ __noinline__ T eval_slot_g(const int32_t* __restri
 #define G3_TPB 512
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// g3_suitability_* of prey length `ml` for predator length `pl` (R/suitability.R:5-30); p[] = the pair's slot values
+template <class T> __device__ __forceinline__ T suitability_of(int kind, const T* p, double ml, double pl) {
+    if (kind == G3SUIT_EXPL50) return 1.0 / (1.0 + xexp(-p[0] * (ml - p[1])));
+    if (kind == G3SUIT_ANDERSEN) {
+        const T x = xlog(avoid_zero(T(pl / ml)));
+        const T d = x - p[1];
+        const T lo = 1.0 / (1.0 + xexp(1000.0 * (p[1] - x)));        // bounded_vec(., 0, 1), R/aab_env.R:51-55
+        const T hi = 1.0 / (1.0 + xexp(1000.0 * (x - p[1])));
+        const T a2 = avoid_zero(p[2]);
+        return p[0] + a2 * xexp(-(d * d) / avoid_zero(p[3])) * lo + a2 * xexp(-(d * d) / avoid_zero(p[4])) * hi;
+    }
+    return p[0];
+}
+
+constexpr int MAXMIG = 4;       // areas a migrating stock may live on
 constexpr int TPB = G3_TPB;
 constexpr unsigned WS_STRIDE = 152u * G3_TPB;   // workspace stride in threads: room for 152 SMs x the largest block     // LARGEST block of the thread-per-evaluation kernel (one block per SM; the launch
                                 // picks blockDim <= TPB so that the batch splits into equally full waves)
@@ -121,17 +136,50 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
 #define SLOT(i) W(A.t_slot + (i))
 
         // ================= per-evaluation tables
-        for (int q = 0; q < A.NPP; q++) {           // suitability (R/suitability.R:5-13)
+        for (int q = 0; q < A.NPP; q++) {           // suitability (R/suitability.R:5-30): [predator length][prey length]
             const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+            const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
             const int32_t* Ps = I + I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN;
             const int32_t* ss = I + Q[G3PP_SUIT_OFF];
-            if (Q[G3PP_SUIT_KIND] == G3SUIT_EXPL50) {
-                const T al = SLOT(ss[0]), l50 = SLOT(ss[1]);
-                for (int l = 0; l < Ps[G3S_L]; l++)
-                    W(A.t_suit + q * A.maxL + l) = 1.0 / (1.0 + xexp(-al * (R[Ps[G3S_MIDLEN_ROFF] + l] - l50)));
-            } else {
-                const T v = SLOT(ss[0]);
-                for (int l = 0; l < Ps[G3S_L]; l++) W(A.t_suit + q * A.maxL + l) = v;
+            T sp[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
+            const bool spred = P[G3P_KIND] == G3PRED_STOCK;
+            const int32_t* Pp = I + I[G3H_STOCK_OFF] + (spred ? P[G3P_STOCK] : 0) * G3S_LEN;
+            const int PL = spred ? Pp[G3S_L] : 1, L = Ps[G3S_L];
+            for (int pl = 0; pl < PL; pl++)
+                for (int l = 0; l < L; l++)
+                    W(A.t_suitq[q] + pl * L + l) = suitability_of<T>(Q[G3PP_SUIT_KIND], sp, R[Ps[G3S_MIDLEN_ROFF] + l],
+                                                                     spred ? R[Pp[G3S_MIDLEN_ROFF] + pl] : 0.0);
+        }
+        // stock predators: maximum consumption per predator length without the step length,
+        // m0 exp(m1 T - m2 T^3) l^m3 (R/action_predate.R:190-205)
+        for (int pi = 0; pi < I[G3H_NPRED]; pi++) {
+            const int32_t* P = I + I[G3H_PRED_OFF] + pi * G3P_LEN;
+            if (P[G3P_KIND] != G3PRED_STOCK) continue;
+            const int32_t* Pp = I + I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN;
+            const int32_t* ps = I + P[G3P_SLOT_OFF];
+            const T m0 = SLOT(ps[0]), m1 = SLOT(ps[1]), m2 = SLOT(ps[2]), m3 = SLOT(ps[3]), temp = SLOT(ps[5]);
+            const T tf = m0 * xexp(m1 * temp - m2 * temp * temp * temp);
+            for (int pl = 0; pl < Pp[G3S_L]; pl++) W(A.t_pmc[pi] + pl) = tf * xpow(T(R[Pp[G3S_MIDLEN_ROFF] + pl]), m3);
+        }
+        // migration matrices per step of the year: proportion moving src -> dest (R/action_migrate.R:2-15,49-56)
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+            if (St[G3S_MIGRATE_OFF] < 0) continue;
+            const int NR = St[G3S_NAREA];
+            for (int st = 0; st < NSTEPS; st++) {
+                const int32_t* mig = I + St[G3S_MIGRATE_OFF] + st * NR * NR;
+                for (int src = 0; src < NR; src++) {
+                    T tot(0.0);
+                    for (int d = 0; d < NR; d++) {
+                        T v = (d != src && mig[d * NR + src] >= 0) ? SLOT(mig[d * NR + src]) : T(0.0);
+                        v = v * v;
+                        tot = tot + v;
+                        W(A.t_mig[s] + (st * NR + d) * NR + src) = v / 1.0;
+                    }
+                    W(A.t_mig[s] + (st * NR + src) * NR + src) = (1.0 - tot) / 1.0;
+                }
             }
         }
         for (int s = 0; s < NS; s++) {
@@ -297,39 +345,92 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                 }
             }
 
-            // ================= g3a_predate step 1: suitable biomass per (predator, area) (R/action_predate.R:314-333)
+            // ================= g3a_migrate (R/action_migrate.R:17-82): every (age, length) mixes its areas in place
+            for (int s = 0; s < NS; s++) {
+                if (!((A.t_mig_steps[s] >> step) & 1)) continue;
+                const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+                const int L = St[G3S_L], nage = St[G3S_NAGE], NR = St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+                const int mo = A.t_mig[s] + step * NR * NR;
+                for (int i = 0; i < nage * L; i++) {
+                    T sn[MAXMIG], sw[MAXMIG];
+#pragma unroll
+                    for (int r = 0; r < MAXMIG; r++)
+                        if (r < NR) { sn[r] = W(A.t_num + c0 + r * nage * L + i); sw[r] = W(A.t_wgt + c0 + r * nage * L + i); }
+#pragma unroll
+                    for (int d = 0; d < MAXMIG; d++)
+                        if (d < NR) {
+                            T pn(0.0), pw(0.0);
+#pragma unroll
+                            for (int r = 0; r < MAXMIG; r++)
+                                if (r < NR) {
+                                    const T moved = sn[r] * W(mo + d * NR + r);
+                                    pw = ratio_add_pop(pw, pn, sw[r], moved);       // stock_combine_subpop
+                                    pn = pn + moved;
+                                }
+                            W(A.t_num + c0 + d * nage * L + i) = pn; W(A.t_wgt + c0 + d * nage * L + i) = pw;
+                        }
+                }
+            }
+
+            // ================= g3a_predate step 1: suitable biomass per (predator, area[, predator length]) (R/action_predate.R:314-333)
             if (pred_now) {
 #pragma unroll
                 for (int k = 0; k < MAXTS; k++) if (k < A.NTS) EOT(k) = T(0.0);
+                for (int pi = 0; pi < I[G3H_NPRED]; pi++) {
+                    const int32_t* P = I + I[G3H_PRED_OFF] + pi * G3P_LEN;
+                    if (P[G3P_KIND] != G3PRED_STOCK) continue;
+                    const int32_t* Pp = I + I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN;
+                    for (int i = 0; i < Pp[G3S_NAREA] * Pp[G3S_L]; i++) W(A.t_pts[pi] + i) = T(0.0);
+                }
                 for (int s = 0; s < NS; s++) {
                     const int nq = A.stock_pp_off[s + 1] - A.stock_pp_off[s];
                     if (nq == 0) continue;
                     const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
                     const int L = St[G3S_L], nage = St[G3S_NAGE], c0 = St[G3S_CELL_OFF], ncol = nage * St[G3S_NAREA];
-                    for (int col = 0; col < ncol; col++) {
-                        const int ridx = col / nage;
-                        T cs[MAXQ];
-#pragma unroll
-                        for (int j = 0; j < MAXQ; j++) cs[j] = T(0.0);
-                        for (int l = 0; l < L; l++) {
-                            const int cell = c0 + col * L + l;
-                            const T B0 = W(A.t_num + cell) * W(A.t_wgt + cell);
-#pragma unroll
-                            for (int j = 0; j < MAXQ; j++)
-                                if (j < nq) cs[j] = cs[j] + W(A.t_suit + A.stock_pp[A.stock_pp_off[s] + j] * A.maxL + l) * B0;
-                        }
-#pragma unroll
-                        for (int j = 0; j < MAXQ; j++)
-                            if (j < nq) {
-                                const int ts = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + j] * A.maxnarea + ridx];
-                                if (ts >= 0) EOT(ts) = EOT(ts) + cs[j];
+                    for (int j = 0; j < nq; j++) {
+                        const int q = A.stock_pp[A.stock_pp_off[s] + j];
+                        const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+                        const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
+                        const bool spred = P[G3P_KIND] == G3PRED_STOCK;
+                        const int PL = spred ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1;
+                        const T energy = spred ? SLOT(Q[G3PP_ENERGY]) : T(1.0);
+                        for (int col = 0; col < ncol; col++) {
+                            const int ts = A.pp_tsid[q * A.maxnarea + col / nage];     // accumulator (fleet) / predator area idx (stock predator)
+                            if (ts < 0) continue;
+                            for (int pl = 0; pl < PL; pl++) {
+                                T cs(0.0);
+                                for (int l = 0; l < L; l++) {
+                                    const int cell = c0 + col * L + l;
+                                    cs = cs + W(A.t_suitq[q] + pl * L + l) * (W(A.t_num + cell) * W(A.t_wgt + cell));
+                                }
+                                if (spred) W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) = W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) + cs * energy;
+                                else EOT(ts) = EOT(ts) + cs;
                             }
+                        }
                     }
                 }
                 // landings over total suitable biomass: cons = E * (suit / totalsuit)
 #pragma unroll
                 for (int k = 0; k < MAXTS; k++)
                     if (k < A.NTS) EOT(k) = R[A.w_ts_eoff[k] + (size_t)t * A.w_ts_estr[k]] / EOT(k);
+                // stock predators: predN * max_consumption * feeding_level / total_predsuit per (area, predator length)
+                // (R/action_predate.R:207-238; energycontent cancels between suit and cons)
+                for (int pi = 0; pi < I[G3H_NPRED]; pi++) {
+                    const int32_t* P = I + I[G3H_PRED_OFF] + pi * G3P_LEN;
+                    if (P[G3P_KIND] != G3PRED_STOCK) continue;
+                    const int32_t* Pp = I + I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN;
+                    const int PL = Pp[G3S_L], PA = Pp[G3S_NAGE];
+                    const double dt = A.w_dt_len[idt] / 12.0;
+                    const T hf = SLOT(I[P[G3P_SLOT_OFF] + 4]);
+                    for (int pr = 0; pr < Pp[G3S_NAREA]; pr++)
+                        for (int pl = 0; pl < PL; pl++) {
+                            const T ts = W(A.t_pts[pi] + pr * PL + pl);
+                            T predn(0.0);
+                            for (int pa = 0; pa < PA; pa++) predn = predn + W(A.t_num + Pp[G3S_CELL_OFF] + (pr * PA + pa) * PL + pl);
+                            const T feeding = ts / (hf * dt + ts);
+                            W(A.t_pts[pi] + pr * PL + pl) = predn * (W(A.t_pmc[pi] + pl) * dt) * feeding / ts;
+                        }
+                }
             }
 
             // ================= stock by stock
@@ -359,12 +460,16 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                 // ---------- g3a_predate (R/action_predate.R:335-406): cell order, as the reference sums
                 if (prey_now) {
                     unsigned kx[MAXQ], ksuit[MAXQ];     // per predator: collect vectors it feeds, suitability table
+                    int kpl[MAXQ], kpts[MAXQ];          // stock predators: predator length groups, table of their consumption factors
 #pragma unroll
                     for (int k = 0; k < MAXQ; k++) {
-                        kx[k] = 0; ksuit[k] = 0;
+                        kx[k] = 0; ksuit[k] = 0; kpl[k] = 0; kpts[k] = 0;
                         if (k < nq) {
                             const int q = A.stock_pp[A.stock_pp_off[s] + k];
-                            ksuit[k] = (unsigned)(A.t_suit + q * A.maxL) * NTH;
+                            const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+                            const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
+                            ksuit[k] = (unsigned)A.t_suitq[q] * NTH;
+                            if (P[G3P_KIND] == G3PRED_STOCK) { kpl[k] = I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L]; kpts[k] = A.t_pts[Q[G3PP_PRED]]; }
                             for (int x = 0; x < A.NX; x++) if ((A.w_x_ppmask[x] >> q) & 1) kx[k] |= 1u << x;
                         }
                     }
@@ -373,13 +478,14 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                     const T* pw_ = ws + (unsigned)(A.t_wgt + c0) * NTH;
                     for (int col = 0; col < ncol; col++) {
                         const int ridx = col / nage;
-                        T eotk[MAXQ];       // landings / total suitable biomass of each predator in this column's area
+                        T eotk[MAXQ];       // landings / total suitable biomass of each fleet in this column's area
+                        int tsk[MAXQ];
 #pragma unroll
                         for (int k = 0; k < MAXQ; k++) {
-                            eotk[k] = T(0.0);
+                            eotk[k] = T(0.0); tsk[k] = -1;
                             if (k < nq) {
-                                const int ts = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx];
-                                if (ts >= 0) eotk[k] = EOT(ts);
+                                tsk[k] = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx];
+                                if (tsk[k] >= 0 && kpl[k] == 0) eotk[k] = EOT(tsk[k]);
                             }
                         }
                         unsigned lN = 0;
@@ -391,8 +497,14 @@ __global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant_
                             for (int x = 0; x < MAXX; x++) fx[x] = T(0.0);
 #pragma unroll
                             for (int k = 0; k < MAXQ; k++)
-                                if (k < nq) {
-                                    const T cf = ws[ksuit[k] + lN] * eotk[k];
+                                if (k < nq && tsk[k] >= 0) {
+                                    T cf;
+                                    if (kpl[k] == 0) cf = ws[ksuit[k] + lN] * eotk[k];
+                                    else {      // sum over the predator's length groups of suitability x consumption factor
+                                        cf = T(0.0);
+                                        for (int pl = 0; pl < kpl[k]; pl++)
+                                            cf = cf + ws[ksuit[k] + (unsigned)(pl * L) * NTH + lN] * W(kpts[k] + tsk[k] * kpl[k] + pl);
+                                    }
                                     tp = tp + cf * B0;
                                     if (catch_now) {
 #pragma unroll

@@ -66,6 +66,7 @@ struct g3cuda_model {
     // smem element counts
     int sm_elems = 0;
     size_t smem_optin = 0;
+    bool only_thread = false;           // model uses actions only the thread kernel implements (migration, stock predators)
     bool cta_ok_double = false, cta_ok_dual = false;    // CTA kernel: shared-memory layout fits (values / duals)
     bool thread_ok = false;             // model fits the thread-per-evaluation kernel
     int t_entries = 0, t_maxn = 0;      // workspace entries per thread; widest growth band
@@ -197,7 +198,25 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
         if (St[G3S_AGE_ENABLE] && St[G3S_AGE_N_OUT] > 0) nmv += 2 * St[G3S_NAREA] * St[G3S_L];
     }
     A.t_tn = take(ntr); A.t_tw = take(ntr); A.t_mv = take(nmv);
-    A.t_suit = take(A.NPP * A.maxL);
+    A.t_suit = off;
+    for (int q = 0; q < A.NPP && q < 32; q++) {
+        const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+        const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
+        int PL = P[G3P_KIND] == G3PRED_STOCK ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1;
+        A.t_suitq[q] = take(PL * I[I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN + G3S_L]);
+    }
+    for (int p = 0; p < I[G3H_NPRED] && p < MAXS; p++) {
+        const int32_t* P = I + I[G3H_PRED_OFF] + p * G3P_LEN;
+        A.t_pts[p] = A.t_pmc[p] = 0;
+        if (P[G3P_KIND] != G3PRED_STOCK) continue;
+        const int32_t* Pp = I + I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN;
+        A.t_pts[p] = take(Pp[G3S_NAREA] * Pp[G3S_L]);
+        A.t_pmc[p] = take(Pp[G3S_L]);
+    }
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+        A.t_mig[s] = St[G3S_MIGRATE_OFF] >= 0 ? take(A.NSTEPS * St[G3S_NAREA] * St[G3S_NAREA]) : 0;
+    }
     for (int s = 0; s < A.NS; s++) {
         const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
         int n = St[G3S_GROW_N], L = St[G3S_L];
@@ -462,7 +481,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         int L = St[G3S_L], nage = St[G3S_NAGE], narea = St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
         maxnarea = std::max(maxnarea, narea);
         if (St[G3S_N_RENEW] > MAXRN) return bail(fail(G3CUDA_EUNSUPP, "more than %d renewal actions on one stock", MAXRN));
-        if (St[G3S_MIGRATE_OFF] >= 0) return bail(fail(G3CUDA_EUNSUPP, "g3a_migrate is not supported yet"));
+        if (St[G3S_MIGRATE_OFF] >= 0) m->only_thread = true;        // g3a_migrate: thread kernel only
         if (St[G3S_GROW_N] >= 0 && St[G3S_MAT_KIND] == G3MAT_CONSTANT && St[G3S_N_OUT] > 0) A.any_const_mat = 1;
         if (St[G3S_GROW_N] >= 0 && St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0 && I[St[G3S_MAT_OFF] + 2] >= 0)
             return bail(fail(G3CUDA_EUNSUPP, "g3a_mature_continuous with a beta/a50 (age) term is not supported yet"));
@@ -506,6 +525,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     std::vector<int> pred_ts_base(I[G3H_NPRED], 0);
     for (int p = 0; p < I[G3H_NPRED]; p++) {
         const int32_t* P = I + I[G3H_PRED_OFF] + p * G3P_LEN;
+        if (P[G3P_KIND] == G3PRED_STOCK) { m->only_thread = true; pred_ts_base[p] = -1; continue; }     // stock predator: thread kernel only
         if (P[G3P_KIND] != G3PRED_TOTALFLEET) return bail(fail(G3CUDA_EUNSUPP, "predator kind %d is not supported yet", P[G3P_KIND]));
         pred_ts_base[p] = nts; nts += P[G3P_NAREA];
     }
@@ -516,12 +536,15 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
         const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
         const int32_t* St = stock(Q[G3PP_PREY]);
-        if (Q[G3PP_SUIT_KIND] != G3SUIT_EXPL50 && Q[G3PP_SUIT_KIND] != G3SUIT_CONSTANT)
+        if (Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSEN) {
+            if (P[G3P_KIND] != G3PRED_STOCK) return bail(fail(G3CUDA_EUNSUPP, "g3_suitability_andersen needs a stock predator"));
+        } else if (Q[G3PP_SUIT_KIND] != G3SUIT_EXPL50 && Q[G3PP_SUIT_KIND] != G3SUIT_CONSTANT)
             return bail(fail(G3CUDA_EUNSUPP, "suitability kind %d is not supported yet", Q[G3PP_SUIT_KIND]));
         pp_of_stock[Q[G3PP_PREY]].push_back(q);
         for (int r = 0; r < St[G3S_NAREA]; r++) {
             int area = I[St[G3S_AREA_OFF] + r];
             for (int k = 0; k < P[G3P_NAREA]; k++) if (I[P[G3P_AREA_OFF] + k] == area) {
+                if (P[G3P_KIND] == G3PRED_STOCK) { tsid[(size_t)q * maxnarea + r] = k; continue; }     // predator area index
                 tsid[(size_t)q * maxnarea + r] = pred_ts_base[Q[G3PP_PRED]] + k;
                 eoff[(size_t)q * maxnarea + r] = P[G3P_E_ROFF] + k;
                 estr[(size_t)q * maxnarea + r] = P[G3P_NAREA];
@@ -581,6 +604,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         std::vector<unsigned char> pact(A.NT, 0);
         for (int p = 0; p < I[G3H_NPRED]; p++) {
             const int32_t* P = I + I[G3H_PRED_OFF] + p * G3P_LEN;
+            if (P[G3P_KIND] == G3PRED_STOCK) { std::fill(pact.begin(), pact.end(), 1); continue; }    // a stock predator eats every step
             for (int k = 0; k < P[G3P_NAREA]; k++) {
                 A.w_ts_eoff[pred_ts_base[p] + k] = P[G3P_E_ROFF] + k;
                 A.w_ts_estr[pred_ts_base[p] + k] = P[G3P_NAREA];
@@ -599,7 +623,16 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
 
     // ---- thread-per-evaluation kernel: workspace layout, cell-oriented collect CSR, ordering check
     {
-        m->thread_ok = A.NPP <= 32 && A.w_ndt <= 4 && A.NCOMP <= 32;
+        m->thread_ok = A.NPP <= 32 && A.w_ndt <= 4 && A.NCOMP <= 32 && I[G3H_NPRED] <= MAXS;
+        for (int s = 0; s < A.NS; s++) {
+            const int32_t* St = stock(s);
+            A.t_mig_steps[s] = 0;
+            if (St[G3S_MIGRATE_OFF] < 0) continue;
+            int NR = St[G3S_NAREA];
+            if (NR > MAXMIG) m->thread_ok = false;
+            for (int st = 0; st < A.NSTEPS; st++) for (int i = 0; i < NR * NR; i++)
+                if (I[St[G3S_MIGRATE_OFF] + st * NR * NR + i] >= 0) A.t_mig_steps[s] |= 1 << st;
+        }
         m->t_maxn = 0;
         for (int s = 0; s < A.NS; s++) m->t_maxn = std::max(m->t_maxn, stock(s)[G3S_GROW_N]);
         if (m->t_maxn > 15) m->thread_ok = false;
@@ -722,8 +755,9 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
         return bail(fail(G3CUDA_ECUDA, "stream/event creation failed"));
-    m->cta_ok_double = m->nthreads <= 1024 && make_layout(m, sizeof(double)).bytes <= (size_t)prop.sharedMemPerBlockOptin;
-    m->cta_ok_dual = m->nthreads <= 1024 && make_layout(m, sizeof(DualT)).bytes <= (size_t)prop.sharedMemPerBlockOptin;
+    if (m->only_thread) m->warp_ok = false;
+    m->cta_ok_double = !m->only_thread && m->nthreads <= 1024 && make_layout(m, sizeof(double)).bytes <= (size_t)prop.sharedMemPerBlockOptin;
+    m->cta_ok_dual = !m->only_thread && m->nthreads <= 1024 && make_layout(m, sizeof(DualT)).bytes <= (size_t)prop.sharedMemPerBlockOptin;
     if (!m->thread_ok && !m->cta_ok_double)
         return bail(fail(G3CUDA_EUNSUPP, "model fits neither evaluation kernel (%d cells, %zu bytes of shared memory per evaluation, limit %zu)",
                          A.NC, make_layout(m, sizeof(double)).bytes, (size_t)prop.sharedMemPerBlockOptin));

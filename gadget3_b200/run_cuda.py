@@ -211,6 +211,25 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
     if by_kind.get("report_detail"):
         tmpl.add("report_detail", 1.0, optimise=False)
 
+    # ---- migration (order 2)
+    for name, a in one_per_stock("migrate", "g3a_migrate").items():
+        s = stocks[name]
+        anames = list(s.areas.keys())
+        NR = len(anames)
+        run_steps = range(1, S + 1) if a.run_steps is None else [int(x) for x in a.run_steps]
+        tab = [-1] * (S * NR * NR)
+        for st in run_steps:
+            for di, dn in enumerate(anames):
+                for si, sn in enumerate(anames):
+                    if di == si:
+                        continue        # the stationary share balances the row (R/action_migrate.R:2-15)
+                    e = a.migrate_f(sn, dn)
+                    if isinstance(e, (int, float)) and e == 0:
+                        continue
+                    c = Ctx(stock=s, area=s.areas[sn], area_name=sn, cur_step=st)
+                    tab[((st - 1) * NR + di) * NR + si] = low.slot(wrap(e), c)
+        srec[name][K["G3S_MIGRATE_OFF"]] = b.alloc_ints(tab)
+
     # ---- predation (order 3): predators by name, prey by name
     pred_recs, pp_recs, pp_index = [], [], {}
     for pname, a in preds.items():
@@ -231,6 +250,21 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             pr[K["G3P_E_ROFF"]] = b.alloc_reals(E)
             pr[K["G3P_STOCK"]] = -1
             pr[K["G3P_SLOT_OFF"]] = -1
+        elif cat.kind == "predator":
+            # g3a_predate_catchability_predator (R/action_predate.R:207-238) for a stock predator
+            if ps.lengthgroups is None or ps.name not in sidx:
+                raise G3Unsupported("g3a_predate_catchability_predator needs a stock predator with length groups")
+            pref = cat.kw["prey_preferences"]
+            if not (isinstance(pref, (int, float)) and pref == 1):
+                raise G3Unsupported("g3a_predate_catchability_predator: prey_preferences other than 1")
+            pr[K["G3P_KIND"]] = K["G3PRED_STOCK"]
+            pr[K["G3P_E_ROFF"]] = -1
+            pr[K["G3P_STOCK"]] = sidx[ps.name]
+            mc = cat.kw["max_consumption"]
+            cp = Ctx(predstock=ps)
+            pr[K["G3P_SLOT_OFF"]] = b.alloc_ints([low.slot(mc["m0"], cp), low.slot(mc["m1"], cp), low.slot(mc["m2"], cp),
+                                                  low.slot(mc["m3"], cp), low.slot(cat.kw["half_feeding_f"], cp),
+                                                  low.slot(mc["temperature"], cp)])
         else:
             raise G3Unsupported(f"catchability {cat.kind}")
         pr[K["G3P_NAREA"]] = len(ps.areas)
@@ -246,6 +280,10 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             slots = [low.slot(x, c) for x in su.args]
             q[K["G3PP_SUIT_OFF"]] = b.alloc_ints(slots + [-1] * (6 - len(slots)))
             q[K["G3PP_ENERGY"]] = q[K["G3PP_PREF"]] = -1
+            if cat.kind == "predator":
+                q[K["G3PP_ENERGY"]] = low.slot(cat.kw["energycontent"], c)
+            elif su.kind == "andersen":
+                raise G3Unsupported("g3_suitability_andersen needs a stock predator (predator_length)")
             pp_index[(pname, prey.name)] = len(pp_recs)
             pp_recs.append(q)
         pr[K["G3P_N_PP"]] = len(pp_recs) - pr[K["G3P_PP_FIRST"]]
@@ -354,9 +392,6 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                 for l in range(s.L):
                     amap.append(base + l if ok else -1)
         r[K["G3S_AGE_MAP_OFF"]] = b.alloc_ints(amap)
-
-    if by_kind.get("migrate"):
-        raise G3Unsupported("g3a_migrate is not lowered yet")
 
     # ---- likelihood components (order 10), by generated name
     comps = sorted(by_kind.get("distribution", []), key=lambda a: a.nll_name)

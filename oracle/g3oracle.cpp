@@ -251,6 +251,31 @@ template <class T> void grow_apply(const std::vector<T>& G, const std::vector<T>
     }
 }
 
+// g3_suitability_* of prey length `ml` for predator length `pl` (R/suitability.R:5-30)
+template <class T, class F> T suitability(int kind, const int32_t* ss, F& slot, double ml, double pl, bool& ok) {
+    if (kind == G3SUIT_EXPL50) return 1.0 / (1.0 + xexp(-slot(ss[0]) * (T(ml) - slot(ss[1]))));
+    if (kind == G3SUIT_CONSTANT) return slot(ss[0]);
+    if (kind == G3SUIT_ANDERSEN) {
+        T p0 = slot(ss[0]), p1 = slot(ss[1]), p2 = slot(ss[2]), p3 = slot(ss[3]), p4 = slot(ss[4]);
+        T x = xlog(avoid_zero(T(pl / ml)));
+        T d = x - p1;
+        // bounded_vec(y, 0, 1) = 0 + (1 - 0) / (1 + exp(y))  (R/aab_env.R:51-55)
+        T lo = 1.0 / (1.0 + xexp(1000.0 * (p1 - x)));
+        T hi = 1.0 / (1.0 + xexp(1000.0 * (x - p1)));
+        return p0 + avoid_zero(p2) * xexp(-(d * d) / avoid_zero(p3)) * lo + avoid_zero(p2) * xexp(-(d * d) / avoid_zero(p4)) * hi;
+    }
+    ok = false;
+    return T(0.0);
+}
+// g3a_migrate_normalize: R/action_migrate.R:2-15 (row_total = 1)
+template <class T> void migrate_normalize(std::vector<T>& vec, int src_idx, double row_total) {
+    vec[src_idx] = T(0.0);
+    T tot(0.0);
+    for (auto& v : vec) { v = v * v; tot = tot + v; }
+    vec[src_idx] = row_total - tot;
+    for (auto& v : vec) v = v / row_total;
+}
+
 // ------------------------------------------------------------------ the model run
 struct ReportSink {
     double* nll;          // 1
@@ -330,24 +355,72 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
         }
         if (cur_time > total_steps) break;
 
+        // ---- g3a_migrate (R/action_migrate.R:17-82), action order 2
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            if (St[G3S_MIGRATE_OFF] < 0) continue;
+            int L = St[G3S_L], A = St[G3S_NAGE], NR = St[G3S_NAREA], c0 = St[G3S_CELL_OFF];
+            const int32_t* mig = S.I + St[G3S_MIGRATE_OFF] + (cur_step - 1) * NR * NR;       // [dest][src] slots
+            bool runs = false;
+            for (int i = 0; i < NR * NR; i++) if (mig[i] >= 0) runs = true;
+            if (!runs) continue;        // "Copy not-migrating stocks"
+            std::vector<T> pn((size_t)L * A * NR, T(0.0)), pw((size_t)L * A * NR, T(0.0));
+            for (int src = 0; src < NR; src++) {
+                std::vector<T> vec(NR);
+                for (int d = 0; d < NR; d++) vec[d] = mig[d * NR + src] >= 0 ? slot(mig[d * NR + src]) : T(0.0);
+                migrate_normalize(vec, src, 1.0);
+                for (int a = 0; a < A; a++) for (int d = 0; d < NR; d++) for (int l = 0; l < L; l++) {
+                    int cs = (src * A + a) * L + l, cd = (d * A + a) * L + l;
+                    T moved = num[c0 + cs] * vec[d];
+                    pw[cd] = ratio_add_pop(pw[cd], pn[cd], wgt[c0 + cs], moved);       // stock_combine_subpop
+                    pn[cd] = pn[cd] + moved;
+                }
+            }
+            for (size_t i = 0; i < pn.size(); i++) { num[c0 + i] = pn[i]; wgt[c0 + i] = pw[i]; }
+        }
+
         // ---- g3a_predate (R/action_predate.R:240-420)
         std::fill(totalpredate.begin(), totalpredate.end(), T(0.0));
         std::vector<std::vector<T>> totalsuit(NP);
         for (int p = 0; p < NP; p++) totalsuit[p].assign(S.pred(p)[G3P_NAREA], T(0.0));
         std::vector<char> is_prey(NS, 0);
+        // stock predators: total suitability per (predator area idx, predator length), R/action_predate.R:207-238
+        std::vector<std::vector<T>> ptotsuit(NP);
+        for (int p = 0; p < NP; p++)
+            if (S.pred(p)[G3P_KIND] == G3PRED_STOCK) {
+                const int32_t* Sp = S.stock(S.pred(p)[G3P_STOCK]);
+                ptotsuit[p].assign((size_t)Sp[G3S_NAREA] * Sp[G3S_L], T(0.0));
+            }
         for (int q = 0; q < NPP; q++) {     // step 1: collect suitable biomass
             const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
             is_prey[Q[G3PP_PREY]] = 1;
             int L = St[G3S_L]; const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
             const int32_t* ss = S.I + Q[G3PP_SUIT_OFF];
-            std::vector<T> suitability(L);
-            for (int l = 0; l < L; l++) {
-                if (Q[G3PP_SUIT_KIND] == G3SUIT_EXPL50)          // R/suitability.R:10
-                    suitability[l] = 1.0 / (1.0 + xexp(-slot(ss[0]) * (T(midlen[l]) - slot(ss[1]))));
-                else if (Q[G3PP_SUIT_KIND] == G3SUIT_CONSTANT)
-                    suitability[l] = slot(ss[0]);
-                else return T(NaN);
+            bool ok = true;
+            if (P[G3P_KIND] == G3PRED_STOCK) {
+                const int32_t* Sp = S.stock(P[G3P_STOCK]);
+                int PL = Sp[G3S_L]; const double* pmid = S.R + Sp[G3S_MIDLEN_ROFF];
+                T energy = slot(Q[G3PP_ENERGY]);
+                for (int r = 0; r < St[G3S_NAREA]; r++) {
+                    int area = S.I[St[G3S_AREA_OFF] + r], pr = -1;
+                    for (int k = 0; k < Sp[G3S_NAREA]; k++) if (S.I[Sp[G3S_AREA_OFF] + k] == area) pr = k;
+                    if (pr < 0) continue;
+                    for (int pl = 0; pl < PL; pl++)
+                        for (int a = 0; a < St[G3S_NAGE]; a++) {
+                            T colsum(0.0);
+                            for (int l = 0; l < L; l++) {
+                                int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
+                                colsum = colsum + suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], pmid[pl], ok) * energy * num[c] * wgt[c];
+                            }
+                            ptotsuit[Q[G3PP_PRED]][pr * PL + pl] = ptotsuit[Q[G3PP_PRED]][pr * PL + pl] + colsum;
+                        }
+                }
+                if (!ok) return T(NaN);
+                continue;
             }
+            std::vector<T> suitab(L);
+            for (int l = 0; l < L; l++) suitab[l] = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], 0.0, ok);
+            if (!ok || Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSEN) return T(NaN);
             std::fill(suit[q].begin(), suit[q].end(), T(0.0));
             for (int r = 0; r < St[G3S_NAREA]; r++) {
                 int area = S.I[St[G3S_AREA_OFF] + r], pr = -1;
@@ -357,7 +430,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                     T colsum(0.0);
                     for (int l = 0; l < L; l++) {
                         int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
-                        suit[q][c] = suitability[l] * num[c] * wgt[c];
+                        suit[q][c] = suitab[l] * num[c] * wgt[c];
                         colsum = colsum + suit[q][c];
                     }
                     totalsuit[Q[G3PP_PRED]][pr] = totalsuit[Q[G3PP_PRED]][pr] + colsum;
@@ -368,6 +441,37 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
             int L = St[G3S_L];
             std::fill(cons[q].begin(), cons[q].end(), T(0.0));
+            if (P[G3P_KIND] == G3PRED_STOCK) {
+                // cons = predN * max_consumption * feeding_level * suit / (energycontent * total_predsuit)
+                const int32_t* Sp = S.stock(P[G3P_STOCK]);
+                int PL = Sp[G3S_L], PA = Sp[G3S_NAGE]; const double* pmid = S.R + Sp[G3S_MIDLEN_ROFF];
+                const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
+                const int32_t* ss = S.I + Q[G3PP_SUIT_OFF]; const int32_t* ps = S.I + P[G3P_SLOT_OFF];
+                T energy = slot(Q[G3PP_ENERGY]);
+                T m0 = slot(ps[0]), m1 = slot(ps[1]), m2 = slot(ps[2]), m3 = slot(ps[3]), hf = slot(ps[4]), temp = slot(ps[5]);
+                bool ok = true;
+                for (int r = 0; r < St[G3S_NAREA]; r++) {
+                    int area = S.I[St[G3S_AREA_OFF] + r], pr = -1;
+                    for (int k = 0; k < Sp[G3S_NAREA]; k++) if (S.I[Sp[G3S_AREA_OFF] + k] == area) pr = k;
+                    if (pr < 0) continue;
+                    for (int pl = 0; pl < PL; pl++) {
+                        T ts = ptotsuit[Q[G3PP_PRED]][pr * PL + pl];
+                        T maxcons = m0 * cur_step_size * xexp(m1 * temp - m2 * temp * temp * temp) * xpow(T(pmid[pl]), m3);     // R/action_predate.R:190-205
+                        T feeding = ts / (hf * cur_step_size + ts);
+                        for (int pa = 0; pa < PA; pa++) {
+                            T predn = num[Sp[G3S_CELL_OFF] + (pr * PA + pa) * PL + pl];
+                            for (int a = 0; a < St[G3S_NAGE]; a++) for (int l = 0; l < L; l++) {
+                                int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
+                                T su = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], pmid[pl], ok) * energy * num[c] * wgt[c];
+                                T cn = (predn * maxcons * feeding * su) / (energy * ts);
+                                cons[q][c] = cons[q][c] + cn;
+                                totalpredate[c] = totalpredate[c] + cn;
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             for (int r = 0; r < St[G3S_NAREA]; r++) {
                 int area = S.I[St[G3S_AREA_OFF] + r], pr = -1;
                 for (int k = 0; k < P[G3P_NAREA]; k++) if (S.I[P[G3P_AREA_OFF] + k] == area) pr = k;
@@ -832,6 +936,11 @@ double g3oracle_grow_lengthvbsimple(double linf, double kappa, double midlen, do
     return grow_lengthvbsimple<double>(linf, kappa, midlen, dt);
 }
 void g3oracle_set_bbinom_product(int32_t on) { g_bbinom_product = on; }
+void g3oracle_migrate_normalize(double* vec, int32_t n, int32_t src_idx, double row_total) {
+    std::vector<double> v(vec, vec + n);
+    migrate_normalize<double>(v, src_idx, row_total);
+    std::copy(v.begin(), v.end(), vec);
+}
 double g3oracle_avoid_zero(double a) { return avoid_zero<double>(a); }
 double g3oracle_logspace_add(double a, double b) { return logspace_add<double>(a, b); }
 double g3oracle_dif_pmin(double a, double b, double s) { return dif_pmin<double>(a, b, s); }

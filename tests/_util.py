@@ -19,6 +19,16 @@ def us_tolerance(model, params, comp_us):
         n = ints[K["G3H_NT"]] * ints[rec + K["G3P_NAREA"]]
         if ints[rec + K["G3P_E_ROFF"]] >= 0 and ints[rec + K["G3P_KIND"]] != K["G3PRED_STOCK"]:
             emax = max(emax, np.abs(reals[ints[rec + K["G3P_E_ROFF"]]:ints[rec + K["G3P_E_ROFF"]] + n]).max())
+    # a stock predator's consumption is not a data table: bound it by the prey biomass it can take
+    # (0.95 x biomass, R/action_predate.R:383), from the oracle's own state history at the template values
+    if any(ints[ints[K["G3H_PRED_OFF"]] + pr * K["G3P_LEN"] + K["G3P_KIND"]] == K["G3PRED_STOCK"]
+           for pr in range(ints[K["G3H_NPRED"]])):
+        from gadget3_b200.run_cuda import unpack_report
+        from oracle.oracle_lib import Oracle
+        rep = unpack_report(model, Oracle(ints, reals).report(params.values()))
+        for sn in model.stock_names:
+            b = (rep[f"dstart_{sn}__num"] * rep[f"dstart_{sn}__wgt"])
+            emax = max(emax, float(b.reshape(-1, b.shape[-1]).sum(axis=0).max()))
     delta = 64 * np.finfo(float).eps * emax
     T = model.n_steps
     return 2 * delta * np.sqrt(T * np.abs(comp_us)) + T * delta * delta

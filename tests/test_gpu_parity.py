@@ -19,7 +19,7 @@ GRAD_RTOL = 1e-8
 @pytest.fixture(scope="module")
 def setups(oracle_lib):
     out = {}
-    for n in ("C1", "C2", "C4"):
+    for n in ("C1", "C2", "C4", "C5"):
         model, p = CONFIGS[n]()
         fn = g3_cuda_adfun(model, p, device=0)
         out[n] = (model, p, fn, Oracle(*model.pack(p)))
@@ -38,12 +38,20 @@ def _us_weight(model):
 
 
 @pytest.mark.parametrize("kernel", [1, 2, 3], ids=["cta_kernel", "warp_kernel", "thread_kernel"])
-@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C4", "C5"])
 def test_nll_and_components(setups, name, kernel):
     model, p, fn, orc = setups[name]
-    if name == "C4" and kernel == 2:
-        with pytest.raises(Exception, match="does not fit"):      # 35 length groups: wider than a warp
+    if (name == "C4" and kernel == 2) or (name == "C5" and kernel == 2):
+        with pytest.raises(Exception, match="does not fit"):      # 35 length groups: wider than a warp; C5: thread kernel only
             fn.handle.set_kernel(kernel)
+        return
+    if name == "C5" and kernel == 1:        # migration and stock predators exist in the thread kernel only
+        fn.handle.set_kernel(kernel)
+        try:
+            with pytest.raises(Exception, match="does not fit"):
+                fn.handle.eval_batch(fn.full_par(fn.par[None, :]))
+        finally:
+            fn.handle.set_kernel(0)
         return
     fn.handle.set_kernel(kernel)
     try:
@@ -74,12 +82,12 @@ def _check_nll_and_components(model, p, fn, orc):
 
 
 @pytest.mark.parametrize("kernel", [1, 3], ids=["cta_kernel", "thread_kernel"])
-@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C4", "C5"])
 def test_gradients(setups, name, kernel):
     model, p, fn, orc = setups[name]
     fn.handle.set_kernel(kernel)
     try:
-        if name == "C4" and kernel == 1:        # Dual<4> state of 665 cells does not fit one CTA's shared memory
+        if name in ("C4", "C5") and kernel == 1:        # C4: Dual<4> state of 665 cells does not fit one CTA's shared memory
             with pytest.raises(Exception, match="does not fit"):
                 fn.gr_batch(parameter_batch(p, 1, seed=77))
         else:
