@@ -391,4 +391,65 @@ def build_c5(seed=123):
     return model, p
 
 
-CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5}
+def build_mini_andersen(seed=123):
+    """Small 2-area test model: a stock predator with g3_suitability_andersen (predator-length dependent
+    suitability), migration on one step only for the predator, renewal, ageing -- exercises the code
+    paths config 5 does not (used by the parity tests, not by bench.py)."""
+    from . import g3_suitability_andersen
+    areas = g3_areas(["a", "b"])
+    prey = g3s_livesonareas(g3s_age(g3_stock("prey", range(5, 50, 5)), 1, 3), areas)
+    pred = g3s_livesonareas(g3s_age(g3_stock("pred", range(20, 70, 10)), 2, 4), areas)
+
+    def mig(src, dst):
+        return g3_parameterized(f"migrate.{src}.{dst}", by_stock=True, value=0.3)
+
+    su = g3_suitability_andersen(g3_parameterized("and.p0", value=0.0), g3_parameterized("and.p1", value=1.2),
+                                 g3_parameterized("and.p2", value=1.0), g3_parameterized("and.p3", value=0.5),
+                                 g3_parameterized("and.p4", value=0.8))
+    actions = [
+        g3a_time(2000, 2003, [3, 3, 3, 3]),
+        g3a_initialconditions_normalcv(prey), g3a_initialconditions_normalcv(pred),
+        g3a_naturalmortality(prey), g3a_naturalmortality(pred),
+        g3a_growmature(prey, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3)),
+        g3a_growmature(pred, g3a_grow_impl_bbinom(maxlengthgroupgrowth=2)),
+        g3a_renewal_normalcv(prey), g3a_age(prey), g3a_age(pred),
+        g3a_migrate(prey, mig), g3a_migrate(pred, mig, run_steps=[2]),
+        g3a_predate(pred, [prey], suitabilities=su, catchability_f=g3a_predate_catchability_predator()),
+        g3l_understocking([prey]),
+    ]
+    rng = np.random.default_rng(seed)
+    yrs = [2000, 2001, 2002, 2003]
+    for nm, stk in (("si_prey", prey), ("si_pred", pred)):
+        si = dict(year=[y for y in yrs for _ in range(2)], step=[3] * 8, area=["a", "b"] * 4,
+                  number=list(rng.uniform(1e4, 1e5, 8)))
+        actions.append(g3l_abundancedistribution(nm, si, stocks=[stk], area_group=areas,
+                                                 function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    actions += [g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "*.Linf", 60, spread=0.2)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.05, upper=1)
+    p = g3_init_val(p, "*.t0", -0.5, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.15, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, lower=0.01, upper=1)
+    p = g3_init_val(p, "init.F", 0.3, lower=0.1, upper=1)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.migrate.*", 0.3, lower=0, upper=0.7)
+    p = g3_init_val(p, "*.consumption.m0", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.consumption.m3", 1.5, optimise=False)
+    p = g3_init_val(p, "*.halffeeding", 1e3, lower=10, upper=1e5)
+    p = g3_init_val(p, "*.bbin", 10, lower=1, upper=100)
+    p = g3_init_val(p, "*.rec.#", 5, lower=0.1, upper=20)
+    p = g3_init_val(p, "*.rec.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.rec.proj", 1)
+    p = g3_init_val(p, "and.p1", 1.2, lower=0.5, upper=2)
+    p = g3_init_val(p, "and.p3", 0.5, lower=0.1, upper=2)
+    p = g3_init_val(p, "and.p4", 0.8, lower=0.1, upper=2)
+    return model, p
+
+
+CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen}

@@ -63,8 +63,10 @@ template <int K> Dual<K>& operator*=(Dual<K>& a, const Dual<K>& b) { a = a * b; 
 inline double val(double x) { return x; }
 template <int K> double val(const Dual<K>& x) { return x.v; }
 
+// A direction the argument does not depend on stays exactly zero even where the derivative
+// overflows (0 * inf): reverse-mode AD (TMBad, the reference's gradient) never forms that product.
 template <int K, class F> Dual<K> chain(const Dual<K>& a, double f, F dfda) {
-    Dual<K> r; r.v = f; double g = dfda; for (int i = 0; i < K; i++) r.d[i] = g * a.d[i]; return r;
+    Dual<K> r; r.v = f; double g = dfda; for (int i = 0; i < K; i++) r.d[i] = a.d[i] == 0.0 ? 0.0 : g * a.d[i]; return r;
 }
 inline double xexp(double a) { return std::exp(a); }
 inline double xlog(double a) { return std::log(a); }
@@ -936,6 +938,13 @@ double g3oracle_grow_lengthvbsimple(double linf, double kappa, double midlen, do
     return grow_lengthvbsimple<double>(linf, kappa, midlen, dt);
 }
 void g3oracle_set_bbinom_product(int32_t on) { g_bbinom_product = on; }
+double g3oracle_suit_andersen(double p0, double p1, double p2, double p3, double p4, double pred_len, double midlen) {
+    double par[5] = {p0, p1, p2, p3, p4};
+    int32_t ss[5] = {0, 1, 2, 3, 4};
+    auto slot = [&](int i) { return par[i]; };
+    bool ok = true;
+    return suitability<double>(G3SUIT_ANDERSEN, ss, slot, midlen, pred_len, ok);
+}
 void g3oracle_migrate_normalize(double* vec, int32_t n, int32_t src_idx, double row_total) {
     std::vector<double> v(vec, vec + n);
     migrate_normalize<double>(v, src_idx, row_total);

@@ -42,6 +42,9 @@ def load(path=None):
         f = getattr(lib, "g3oracle_" + n)
         f.argtypes = [C.c_double] * k
         f.restype = C.c_double
+    lib.g3oracle_suit_andersen.argtypes = [C.c_double] * 7
+    lib.g3oracle_suit_andersen.restype = C.c_double
+    lib.g3oracle_migrate_normalize.argtypes = [dp, C.c_int32, C.c_int32, C.c_double]
     lib.g3oracle_growth_bbinom.argtypes = [dp, C.c_int32, C.c_int32, C.c_double, dp]
     lib.g3oracle_grow_matrix_len.argtypes = [dp, C.c_int32, C.c_int32, dp]
     lib.g3oracle_grow_matrix_wgt.argtypes = [dp, C.c_int32, C.c_int32, dp]

@@ -152,3 +152,26 @@ def test_digamma_matches_lgamma_slope(lib):
         h = 1e-6 * max(1.0, x)
         fd = (math.lgamma(x + h) - math.lgamma(x - h)) / (2 * h)
         assert lib.g3oracle_digamma(x) == pytest.approx(fd, rel=1e-6)
+
+
+def test_suitability_andersen(lib):
+    """tests/test-eval.R:5-21: g3_suitability_andersen(0, 1, 2, 3, 4), predator_length = 99,
+    prey g3_stock('prey', 1:10 * 10)."""
+    expected = [1.5385642245386, 1.90781891144376, 1.99894574784489, 1.97774955212781, 1.91681934676797,
+                1.83906905397844, 1.75539377253919, 1.67124659054669, 1.58937906439558, 1.51113553695681]
+    midlen = np.arange(10, 101, 10, dtype=float) + 5.0
+    got = [lib.g3oracle_suit_andersen(0.0, 1.0, 2.0, 3.0, 4.0, 99.0, m) for m in midlen]
+    np.testing.assert_allclose(got, expected, rtol=1.5e-8)
+
+
+@pytest.mark.parametrize("vec,src,row_total,expected", [
+    ([np.sqrt(0.2), 0, np.sqrt(0.2)], 0, 1.0, [0.8, 0, 0.2]),
+    ([0, np.sqrt(0.2), 0], 1, 1.0, [0, 1, 0]),
+    ([np.sqrt(0.2), 0, 0], 2, 1.0, [0.2, 0, 0.8]),
+    ([np.sqrt(0.2), 0, np.sqrt(0.2)], 0, 10.0, [0.98, 0, 0.02]),
+])
+def test_migrate_normalize(lib, vec, src, row_total, expected):
+    """tests/test-action_migrate.R:19-31 (the selected column of array(c(sqrt(0.2), 0[, 0]), dim = c(3,3)))."""
+    v = np.array(vec, dtype=float)
+    lib.g3oracle_migrate_normalize(_dp(v), 3, src, row_total)
+    np.testing.assert_allclose(v, expected, rtol=1e-12, atol=1e-15)
