@@ -83,14 +83,16 @@ template <class T> __device__ __forceinline__ T suitability_of(int kind, const T
 }
 
 constexpr int MAXMIG = 4;       // areas a migrating stock may live on
-constexpr int TPB = G3_TPB;
-constexpr unsigned WS_STRIDE = 152u * G3_TPB;   // workspace stride in threads: room for 152 SMs x the largest block     // LARGEST block of the thread-per-evaluation kernel (one block per SM; the launch
-                                // picks blockDim <= TPB so that the batch splits into equally full waves)
+constexpr int TPB = G3_TPB;     // block-size cap of the default variant (one block per SM; the launch picks
+                                // blockDim <= the cap so that the batch splits into equally full waves)
+constexpr int TPB_BIG = 1024;   // cap of the high-occupancy variant (64 registers per thread), used for plain-double
+                                // batches larger than one 512-thread wave: more warps hide more latency
+constexpr unsigned WS_STRIDE = 152u * 1024u;    // workspace stride in threads: room for 152 SMs x the largest block
 
-// CB: unused (kept for the launch table); NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
+// CB: block-size cap the variant is compiled for (__launch_bounds__); NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
 // CONSTMAT: some stock matures with g3a_mature_constant (needs a third register window)
 template <class T, int CB, int NW, bool CONSTMAT>
-__global__ void __launch_bounds__(TPB) eval_thread_kernel(const __grid_constant__ KArgs A) {
+__global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__ KArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;

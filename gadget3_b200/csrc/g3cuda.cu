@@ -251,21 +251,21 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
 template <class T, int CB, int NW, bool CM>
 int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStream_t st) {
     auto kern = g3::eval_thread_kernel<T, CB, NW, CM>;
-    const size_t smem = sizeof(T) * g3::MAXTS * g3::TPB;
+    const size_t smem = sizeof(T) * g3::MAXTS * CB;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g3::TPB, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CB, smem));
     if (per_sm < 1) return fail(G3CUDA_EUNSUPP, "thread kernel does not fit one SM");
     // One block per SM, sized so that the batch splits into equally full waves: an evaluation is
     // one thread for its whole life, so a ragged last wave would idle most of the machine.
-    const int sms = std::min<int>(m->num_sms, (int)(g3::WS_STRIDE / g3::TPB));
-    const long long slots = (long long)g3::TPB * sms;
+    const int sms = std::min<int>(m->num_sms, (int)(g3::WS_STRIDE / CB));
+    const long long slots = (long long)CB * sms;
     const long long waves = (work + slots - 1) / slots;
     long long per_wave = (work + waves - 1) / waves;
     long long grid = std::min<long long>(sms, (per_wave + 31) / 32);
     if (grid < 1) grid = 1;
     int block = (int)(((per_wave + grid - 1) / grid + 31) / 32 * 32);
-    block = std::max(32, std::min(block, g3::TPB));
+    block = std::max(32, std::min(block, CB));
     if ((double)m->t_entries * (double)g3::WS_STRIDE >= 4294967295.0)
         return fail(G3CUDA_EUNSUPP, "evaluation workspace too large for 32-bit element indexing (%d entries)", m->t_entries);
     const size_t need = (size_t)m->t_entries * sizeof(T) * (size_t)g3::WS_STRIDE;
@@ -287,12 +287,20 @@ int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStr
 template <class T>
 int launch_thread(g3cuda_model* m, g3::KArgs& A, long long work, cudaStream_t st) {
     const bool cm = A.any_const_mat != 0;
+    // plain doubles and more work than one 512-thread wave: the 1024-thread (64-register) variant
+    const bool big = std::is_same<T, double>::value && work > (long long)g3::TPB * m->num_sms;
     if (m->t_maxn <= 4) {
-        if (cm) return launch_thread_variant<T, 1, 5, true>(m, A, work, st);
-        return launch_thread_variant<T, 1, 5, false>(m, A, work, st);
+        if (big) {
+            if constexpr (std::is_same<T, double>::value) {
+                if (cm) return launch_thread_variant<T, g3::TPB_BIG, 5, true>(m, A, work, st);
+                return launch_thread_variant<T, g3::TPB_BIG, 5, false>(m, A, work, st);
+            }
+        }
+        if (cm) return launch_thread_variant<T, g3::TPB, 5, true>(m, A, work, st);
+        return launch_thread_variant<T, g3::TPB, 5, false>(m, A, work, st);
     }
-    if (cm) return launch_thread_variant<T, 1, 16, true>(m, A, work, st);
-    return launch_thread_variant<T, 1, 16, false>(m, A, work, st);
+    if (cm) return launch_thread_variant<T, g3::TPB, 16, true>(m, A, work, st);
+    return launch_thread_variant<T, g3::TPB, 16, false>(m, A, work, st);
 }
 
 template <class T, int WPC>
