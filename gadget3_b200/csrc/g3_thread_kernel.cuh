@@ -91,7 +91,8 @@ constexpr unsigned WS_STRIDE = 152u * 1024u;    // workspace stride in threads: 
 
 // CB: block-size cap the variant is compiled for (__launch_bounds__); NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
 // CONSTMAT: some stock matures with g3a_mature_constant (needs a third register window)
-template <class T, int CB, int NW, bool CONSTMAT>
+// REPORT: single-vector report run (g3cuda_report): per-step nll rows, state histories, model arrays
+template <class T, int CB, int NW, bool CONSTMAT, bool REPORT = false>
 __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__ KArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int32_t* __restrict__ I = A.I;
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             }
             nll = nll + bw * pen;
             W(A.t_ctot + A.NNLL - 1) = pen;
+            if (REPORT && live) A.report[1 + (size_t)(A.NNLL - 1) * NT] = val(pen);
         }
         for (int c = 0; c < A.NCOMP; c++) {         // zero the likelihood slabs
             const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
@@ -335,6 +337,15 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             const int idt = A.w_step_idt[step];
             const bool final_step = step == NSTEPS - 1;
             const bool pred_now = A.w_pred_active[t] != 0;
+            if (REPORT && live)         // dstart_<stock>__num/wgt (R/action_report.R:177-213)
+                for (int s = 0; s < NS; s++) {
+                    const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+                    const size_t ncs = (size_t)St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+                    for (size_t i = 0; i < ncs; i++) {
+                        A.report[A.rep_dstart[s] + (size_t)t * ncs + i] = val(W(A.t_num + St[G3S_CELL_OFF] + i));
+                        A.report[A.rep_dstart[s] + (size_t)NT * ncs + (size_t)t * ncs + i] = val(W(A.t_wgt + St[G3S_CELL_OFF] + i));
+                    }
+                }
             // components collecting at this step (bit c), and whether any of them reads a catch
             unsigned cact = 0, xact = 0;
             bool any_catch = false;
@@ -678,6 +689,9 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                         for (int i = 0; i < A.NC; i++) if (cd[i] >= 0) W(ms + cd[i]) = W(ms + cd[i]) + cf[i] * W(xs + i);
                     }
                 }
+                if (REPORT && live)
+                    for (int e = 0; e < nd; e++)
+                        A.report[A.rep_model[c] + (size_t)I[C[G3C_TIDX_OFF] + t] * nd + e] = val(W(ms + e));
             }
 
             // ================= g3l_distribution compare (R/likelihood_distribution.R:375-394)
@@ -748,6 +762,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             beta = sxy / avoid_zero(sxx);
                         }
                         if (isnan(fa)) alpha = mI - beta * mN;
+                        if (REPORT && live) { A.report[A.rep_params + 2 * c] = val(alpha); A.report[A.rep_params + 2 * c + 1] = val(beta); }
                         for (int i = 0; i < nt; i++) {
                             T mv = W(series + i * nd + e);
                             T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
@@ -760,6 +775,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 if (scored) {
                     nll = nll + weight * cnll;
                     W(A.t_ctot + c) = W(A.t_ctot + c) + cnll;
+                    if (REPORT && live) A.report[1 + (size_t)c * NT + t] = val(cnll);
                 }
                 if (!si) for (int e = 0; e < nd; e++) W(ms + e) = T(0.0);     // zero counters for the next period
             }
@@ -768,6 +784,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 T u = (us_power == 2.0) ? us_tot * us_tot : xpow(us_tot, T(us_power));
                 nll = nll + us_weight * u;
                 W(A.t_ctot + A.NNLL - 2) = W(A.t_ctot + A.NNLL - 2) + u;
+                if (REPORT && live) A.report[1 + (size_t)(A.NNLL - 2) * NT + t] = val(u);
             }
 
             // ================= g3a_age (R/action_age.R:51-85) + movement hand-off
@@ -812,6 +829,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
 
         const T out = bad_time ? T(nan("")) : nll;
         if (!live) continue;
+        if (REPORT) A.report[0] = val(out);
         if (tile_t == 0) {
             A.nll[b] = val(out);
             if (A.comp) for (int c = 0; c < A.NNLL; c++) A.comp[b * A.NNLL + c] = bad_time ? nan("") : val(W(A.t_ctot + c));

@@ -284,9 +284,36 @@ int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStr
     return G3CUDA_OK;
 }
 
+// single-vector report run of the thread kernel (one warp; lane 0 is the evaluation)
+template <int NW, bool CM>
+int launch_thread_report(g3cuda_model* m, g3::KArgs& A, cudaStream_t st) {
+    auto kern = g3::eval_thread_kernel<double, g3::TPB, NW, CM, true>;
+    const size_t smem = sizeof(double) * g3::MAXTS * 32;
+    const size_t need = (size_t)m->t_entries * sizeof(double) * (size_t)g3::WS_STRIDE;
+    if (need > m->t_ws_bytes) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (m->t_ws) cudaFree(m->t_ws);
+        m->t_ws = nullptr; m->t_ws_bytes = 0;
+        if (cudaMalloc(&m->t_ws, need) != cudaSuccess) { cudaGetLastError(); return fail(G3CUDA_ENOMEM, "cudaMalloc of the %zu-byte evaluation workspace failed", need); }
+        m->t_ws_bytes = need;
+    }
+    A.t_ws = m->t_ws;
+    kern<<<1, 32, smem, st>>>(A);
+    CUDA_TRY(cudaGetLastError());
+    m->launches++;
+    return G3CUDA_OK;
+}
+
 template <class T>
 int launch_thread(g3cuda_model* m, g3::KArgs& A, long long work, cudaStream_t st) {
     const bool cm = A.any_const_mat != 0;
+    if (A.report) {
+        if constexpr (std::is_same<T, double>::value) {
+            if (m->t_maxn <= 4) return cm ? launch_thread_report<5, true>(m, A, st) : launch_thread_report<5, false>(m, A, st);
+            return cm ? launch_thread_report<16, true>(m, A, st) : launch_thread_report<16, false>(m, A, st);
+        }
+        return fail(G3CUDA_EINVAL, "report runs are plain-double");
+    }
     // plain doubles and more work than one 512-thread wave: the 1024-thread (64-register) variant
     const bool big = std::is_same<T, double>::value && work > (long long)g3::TPB * m->num_sms;
     if (m->t_maxn <= 4) {
@@ -337,10 +364,11 @@ int launch_variant(g3cuda_model* m, const Layout& lay, int nblocks_hint, cudaStr
 template <class T>
 int launch(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStream_t st) {
     const bool is_double = std::is_same<T, double>::value;
-    if (m->thread_ok && !call.report && (m->force_kernel == 0 || m->force_kernel == 3) && (is_double || m->force_kernel == 3 || work >= 16384 || !m->cta_ok_dual)) {
+    if (m->thread_ok && (m->force_kernel == 0 || m->force_kernel == 3) &&
+        (call.report ? (m->force_kernel == 3 || !m->cta_ok_double) : (is_double || m->force_kernel == 3 || work >= 16384 || !m->cta_ok_dual))) {
         g3::KArgs a = m->base;
         a.par = call.par; a.B = call.B; a.tangent_idx = call.tangent_idx; a.K = call.K;
-        a.nll = call.nll; a.comp = call.comp; a.grad = call.grad; a.report = nullptr;
+        a.nll = call.nll; a.comp = call.comp; a.grad = call.grad; a.report = call.report;
         return launch_thread<T>(m, a, work, st);
     }
     if (m->warp_ok && !call.report && m->force_kernel != 1 && (is_double || m->force_kernel == 2)) {

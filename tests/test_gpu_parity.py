@@ -112,11 +112,20 @@ def _check_gradients(model, p, fn, orc):
     assert ((np.abs(g_grad - o_grad) / scale).max(axis=1) < gtol).all()
 
 
-@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
-def test_report_arrays(setups, name):
+@pytest.mark.parametrize("kernel", [1, 3], ids=["cta_kernel", "thread_kernel"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C4", "C5"])
+def test_report_arrays(setups, name, kernel):
     model, p, fn, orc = setups[name]
     par = parameter_batch(p, 1, seed=5)[0]
-    rg = fn.report(par)
+    fn.handle.set_kernel(kernel)
+    try:
+        if name == "C5" and kernel == 1:
+            with pytest.raises(Exception, match="does not fit"):
+                fn.report(par)
+            return
+        rg = fn.report(par)
+    finally:
+        fn.handle.set_kernel(0)
     ro = unpack_report(model, orc.report(fn.full_par(par[None, :])[0]))
     assert set(rg) == set(ro)
     for k in ro:
@@ -131,6 +140,9 @@ def test_report_arrays(setups, name):
             assert np.abs(a - b)[m].sum() <= (NLL_RTOL * abs(ro["nll"]) if k == "nll" else 0.0) + (US_WEIGHT if k == "nll" else 1.0) * us_tol, k
         else:
             scale = np.abs(b[m]).max() if m.any() else 1.0
+            if scale == 0.0:
+                assert (a[m] == 0.0).all(), k
+                continue
             assert (np.abs(a - b)[m] / np.maximum(np.abs(b[m]), 1e-12 * scale)).max() < 1e-9, k
 
 
