@@ -93,7 +93,7 @@ constexpr unsigned WS_STRIDE = 152u * 1024u;    // workspace stride in threads: 
 // CONSTMAT: some stock matures with g3a_mature_constant (needs a third register window)
 // REPORT: single-vector report run (g3cuda_report): per-step nll rows, state histories, model arrays
 template <class T, int CB, int NW, bool CONSTMAT, bool REPORT = false>
-__global__ void __launch_bounds__(CB, 1) eval_thread_kernel(const __grid_constant__ KArgs A) {
+__global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__ KArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;
