@@ -452,4 +452,17 @@ def build_mini_andersen(seed=123):
     return model, p
 
 
+def profile_sweep(params, names, n_per_axis):
+    """Likelihood-profile grid (BASELINE.json config 5): the template everywhere except `names`, which
+    sweep their full [lower, upper] range on an n x n (x ...) grid. Returns B x n_optimised."""
+    idx = params.optimised_indices()
+    v = params.values()[idx]
+    pos = [list(idx).index(params.index(n)) for n in names]
+    axes = [np.linspace(params.lower[params.index(n)], params.upper[params.index(n)], n_per_axis) for n in names]
+    grid = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, len(names))
+    P = np.tile(v, (grid.shape[0], 1))
+    P[:, pos] = grid
+    return P
+
+
 CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen}

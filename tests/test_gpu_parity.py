@@ -269,3 +269,21 @@ def test_andersen_predator_model(oracle_lib):
     gtol = GRAD_RTOL + US_WEIGHT * us_tol[:3] / np.abs(o_nll[:3])
     err = np.where(ok, np.abs(grad - og) / scale, 0.0)
     assert (err.max(axis=1) < gtol).all()
+
+
+def test_profile_sweep_c5(setups):
+    """Config 5's workload shape: a likelihood-profile grid over two parameters (here 64 x 64; the bench
+    runs 131,072 vectors per GPU). Oracle on a slice; the grid is symmetric in nothing, but every point
+    must equal the same vector evaluated alone, and neighbouring points must vary smoothly."""
+    from gadget3_b200.configs import profile_sweep
+    model, p, fn, orc = setups["C5"]
+    P = profile_sweep(p, ["prey.K", "prey.pred.l50"], 64)
+    full = fn.full_par(P)
+    nll, comp, _ = fn.handle.eval_batch(full, want_comp=True)
+    assert nll.shape == (4096,) and np.isfinite(nll).all()
+    pick = np.random.default_rng(5).choice(4096, 24, replace=False)
+    o, oc, _ = orc.eval_batch(full[pick], want_comp=True, nthreads=8)
+    tol = NLL_RTOL * np.abs(o) + US_WEIGHT * _us_tolerance(model, p, oc[:, -2])
+    assert (np.abs(nll[pick] - o) <= tol).all()
+    alone = fn.handle.eval_batch(full[pick])[0]
+    assert (alone == nll[pick]).all()
