@@ -29,7 +29,10 @@ int fail(int code, const char* fmt, ...) {
 }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(G3CUDA_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); } while (0)
 
-constexpr int NTAN = 4;                 // tangent directions per gradient pass
+#ifndef G3_NTAN
+#define G3_NTAN 4
+#endif
+constexpr int NTAN = G3_NTAN;           // tangent directions per gradient pass
 using DualT = g3::Dual<NTAN>;
 
 double h_avoid_zero(double a) {         // R/aab_env.R:24-31 on the host, for parameter-independent terms
@@ -71,6 +74,8 @@ struct g3cuda_model {
     bool thread_ok = false;             // model fits the thread-per-evaluation kernel
     int t_entries = 0, t_maxn = 0;      // workspace entries per thread; widest growth band
     void* t_ws = nullptr; size_t t_ws_bytes = 0;
+    cudaEvent_t ws_free = nullptr;      // recorded after every launch that uses the workspace: the next one waits for it,
+                                        // whichever stream it is on (the workspace is per handle, not per stream)
     bool warp_ok = false;               // model fits the warp-per-evaluation kernel
     int force_kernel = 0;               // 0 = automatic, 1 = CTA-per-evaluation kernel, 2 = warp kernel (debug / tests)
 };
@@ -278,8 +283,11 @@ int launch_thread_variant(g3cuda_model* m, g3::KArgs& A, long long work, cudaStr
         m->t_ws_bytes = need;
     }
     A.t_ws = m->t_ws;
+    if (!m->ws_free) CUDA_TRY(cudaEventCreateWithFlags(&m->ws_free, cudaEventDisableTiming));
+    else CUDA_TRY(cudaStreamWaitEvent(st, m->ws_free, 0));
     kern<<<(unsigned)grid, block, smem, st>>>(A);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(m->ws_free, st));
     m->launches++;
     return G3CUDA_OK;
 }
@@ -298,8 +306,11 @@ int launch_thread_report(g3cuda_model* m, g3::KArgs& A, cudaStream_t st) {
         m->t_ws_bytes = need;
     }
     A.t_ws = m->t_ws;
+    if (!m->ws_free) CUDA_TRY(cudaEventCreateWithFlags(&m->ws_free, cudaEventDisableTiming));
+    else CUDA_TRY(cudaStreamWaitEvent(st, m->ws_free, 0));
     kern<<<1, 32, smem, st>>>(A);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(m->ws_free, st));
     m->launches++;
     return G3CUDA_OK;
 }
@@ -477,6 +488,7 @@ void g3cuda_model_free(g3cuda_model* m) {
         if (p) cudaFree(p);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->ws_free) cudaEventDestroy(m->ws_free);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }

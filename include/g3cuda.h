@@ -75,7 +75,10 @@ int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B,
 
 /* Same computation with DEVICE pointers, asynchronous on `stream`
  * (a cudaStream_t passed as void*; NULL = default stream). Used by callers
- * that keep parameter batches resident in HBM (bench.py `value`). */
+ * that keep parameter batches resident in HBM (bench.py `value`).
+ * A handle owns ONE evaluation workspace: launches on different streams are
+ * ordered by the library (each waits for the previous one's completion event);
+ * calls from different host threads on one handle must be serialised by the caller. */
 int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B,
                              const int32_t* d_tangent_idx, int32_t K,
                              double* d_nll, double* d_nll_comp, double* d_grad,
