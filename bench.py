@@ -119,8 +119,27 @@ def cpu_reference(model, params, config, batch_fn, seconds_target=12.0, tix=None
     sample = batch_fn(n, 7)
     t = time.perf_counter(); nll, _, _ = orc.eval_batch(sample, tangent_idx=tix, nthreads=cores); dt = time.perf_counter() - t
     assert np.isfinite(nll).all()
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{n} vectors of the {config} batch, {cores} threads, {dt:.1f} s wall"}, orc
+    out = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": f"{n} vectors of the {config} batch, {cores} threads, {dt:.1f} s wall"}
+    # for information: the reference's own generated objective (baseline/*.cpp compiled against oracle/tmb_shim,
+    # prebuilt in oracle/_ref). Its eager containers make it slower than the port, so the port stays the baseline.
+    try:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import ref_lib
+        name = MODEL_OF.get(config, config)
+        if tix is None and ref_lib.available(name):
+            refs = [ref_lib.RefModel(name, model, params) for _ in range(cores)]
+            nref = 4 * cores
+            rows = batch_fn(nref, 11)
+            t = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(lambda k: refs[k].eval_batch(rows[k::cores]), range(cores)))
+            dtr = time.perf_counter() - t
+            out["reference_generated_code"] = {"value": nref / dtr, "unit": UNIT, "cores": cores,
+                                               "what": "the reference's checked-in generated C++ under oracle/tmb_shim"}
+    except Exception as e:        # the prebuilt library is optional
+        out["reference_generated_code"] = {"unavailable": str(e)[:120]}
+    return out, orc
 
 
 def main():
