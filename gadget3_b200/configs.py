@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import (g3_areas, g3_fleet, g3_init_val, g3_parameterized, g3_stock, g3_timeareadata, g3_to_cuda,
-               g3a_age, g3a_migrate, g3a_predate, g3a_predate_catchability_predator, g3a_grow_impl_bbinom, g3a_grow_lengthvbsimple, g3a_grow_weightsimple,
+               g3a_age, g3a_migrate, g3a_naturalmortality_exp, g3a_predate, g3a_predate_catchability_predator, g3a_grow_impl_bbinom, g3a_grow_lengthvbsimple, g3a_grow_weightsimple,
                g3a_growmature, g3a_initialconditions_normalcv, g3a_initialconditions_normalparam,
                g3a_mature_constant, g3a_mature_continuous, g3a_naturalmortality,
                g3a_predate_catchability_totalfleet, g3a_predate_fleet, g3a_renewal_normalcv,
@@ -452,6 +452,103 @@ def build_mini_andersen(seed=123):
     return model, p
 
 
+LING_IMM_STDDEV = [8.25, 10.5644599516659, 12.4081745588022, 11.5741565728647, 11.0523508874244,
+                   11.3447991170274, 11.7721342759715, 13.6152275606449]
+LING_MAT_STDDEV = [12.4081745588022, 11.5741565728647, 11.0523508874244, 11.3447991170274, 11.7721342759715,
+                   13.6152275606449, 14.8004893270652, 16.2753802766344, 17.9426701121357, 19.1787817582897,
+                   15.9776436358384]
+
+
+def build_ling(seed=123):
+    """The ling model of the reference's code-generation snapshot (inttest/codegeneration/run.R:17-183,
+    generated C++ checked in as inttest/codegeneration/ling.cpp): same stocks, actions, formulas and
+    parameter names, so that the oracle can be compared with that generated code (oracle/ref_lib.py).
+    The observation table is synthetic (same shape as catchdistribution_ldist_lln.txt); the numbers in
+    ling_*_stddev and the parameter values are model DATA quoted from run.R:32-40,92-103,161-183."""
+    from .formula import Lookup, ParamExpr, age as AGE, g3_as_integer, g3_exp
+    rng = np.random.default_rng(seed)
+    areas = g3_areas(["area1"])
+    lg = range(20, 157, 4)
+    ling_imm = g3s_livesonareas(g3s_age(g3_stock({"species": "ling", "maturity": "imm"}, lg), 3, 10), areas)
+    ling_mat = g3s_livesonareas(g3s_age(g3_stock({"species": "ling", "maturity": "mat"}, lg), 5, 15), areas)
+    P = lambda n, **kw: g3_parameterized(n, **kw)         # plain g3_param("name")
+
+    def vec(name):      # g3_param_vector(name)[[as_integer(age) - minage + 1]]
+        return ParamExpr(name, False, False, False, False, True, False, None, 0.0, float("nan"), float("nan"), False, ())
+
+    def growth(wa, wb):
+        return g3a_grow_impl_bbinom(
+            g3a_grow_lengthvbsimple(linf_f=P("ling.Linf"), kappa_f=P("ling.K") * 0.001),
+            g3a_grow_weightsimple(alpha_f=P(wa), beta_f=P(wb)),
+            beta_f=P("ling.bbin") * 10, maxlengthgroupgrowth=15)
+
+    vonb = lambda: g3a_renewal_vonb_recl(by_stock="species")
+    rec_factor = P("ling.rec.scalar") * g3_parameterized("ling.rec", by_year=True)
+    igfs = g3s_livesonareas(g3_fleet("igfs"), areas)
+    years = list(range(1994, 2019))
+    yy = np.repeat(years, 4)
+    st = np.tile([1, 2, 3, 4], len(years))
+    totaldata = dict(year=[int(y) for y in yy], step=[int(x) for x in st], area=["area1"] * len(yy),
+                     total_weight=[float(x) for x in st])
+    ns = 120
+    yl, sl = np.repeat(yy, ns), np.repeat(st, ns)
+    ln = np.clip(rng.normal(80, 25, len(yl)), 20, 400)
+    obs = _count(dict(year=[int(y) for y in yl], step=[int(x) for x in sl], area=["area1"] * len(yl),
+                      length=_cut(ln, list(range(20, 157, 4)))), ["year", "step", "area", "length"])
+    actions = [
+        g3a_time(1994, 2018, [3, 3, 3, 3]),
+        # ling_mat_actions
+        g3a_initialconditions_normalparam(
+            ling_mat,
+            factor_f=P("lingmat.init.scalar") * g3_exp(-1 * (P("lingmat.M") + P("ling.init.F")) * AGE) * vec("lingmat.init"),
+            mean_f=vonb(), stddev_f=Lookup(LING_MAT_STDDEV, g3_as_integer(AGE), 5 - 1),
+            alpha_f=P("lingmat.walpha"), beta_f=P("lingmat.wbeta")),
+        g3a_growmature(ling_mat, growth("lingmat.walpha", "lingmat.wbeta")),
+        g3a_naturalmortality(ling_mat, g3a_naturalmortality_exp(P("lingmat.M"))),
+        g3a_age(ling_mat),
+        # ling_imm_actions
+        g3a_initialconditions_normalparam(
+            ling_imm,
+            factor_f=P("lingimm.init.scalar") * g3_exp(-1 * (P("lingimm.M") + P("ling.init.F")) * AGE) * vec("lingimm.init"),
+            mean_f=vonb(), stddev_f=Lookup(LING_IMM_STDDEV, g3_as_integer(AGE), 3 - 1),
+            alpha_f=P("lingimm.walpha"), beta_f=P("lingimm.wbeta")),
+        g3a_renewal_normalparam(ling_imm, factor_f=rec_factor, mean_f=vonb(),
+                                stddev_f=Lookup(LING_IMM_STDDEV, g3_as_integer(AGE), 3),
+                                alpha_f=P("lingimm.walpha"), beta_f=P("lingimm.wbeta"), run_age=3, run_step=1),
+        g3a_renewal_normalparam(ling_imm, factor_f=rec_factor, mean_f=vonb(),
+                                stddev_f=Lookup(LING_IMM_STDDEV, g3_as_integer(AGE), 3),
+                                alpha_f=P("lingimm.walpha"), beta_f=P("lingimm.wbeta"), run_age=5, run_step=1),
+        g3a_growmature(ling_imm, growth("lingimm.walpha", "lingimm.wbeta"),
+                       maturity_f=g3a_mature_constant(alpha=0.001 * P("ling.mat1"), l50=P("ling.mat2")),
+                       output_stocks=[ling_mat]),
+        g3a_naturalmortality(ling_imm, g3a_naturalmortality_exp(P("lingimm.M"))),
+        g3a_age(ling_imm, output_stocks=[ling_mat]),
+        # igfs_actions
+        g3a_predate_fleet(igfs, [ling_imm, ling_mat],
+                          suitabilities=g3_suitability_exponentiall50(P("ling.igfs.alpha"), P("ling.igfs.l50")),
+                          catchability_f=g3a_predate_catchability_totalfleet(
+                              g3_timeareadata("igfs_totaldata", totaldata, "total_weight", areas=areas))),
+        # likelihood_actions
+        g3l_understocking([ling_imm, ling_mat], nll_breakdown=True),
+        g3l_catchdistribution("ldist_lln", obs, fleets=[igfs], stocks=[ling_imm, ling_mat],
+                              function_f=g3l_distribution_sumofsquares(), area_group=areas, nll_breakdown=True),
+    ]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    for n, v in (("ling.Linf", 160), ("ling.K", 90), ("lingimm.walpha", 2.27567436711055e-06),
+                 ("lingimm.wbeta", 3.20200445996187), ("ling.bbin", 6), ("lingimm.M", 0.15),
+                 ("lingimm.init.scalar", 200), ("ling.init.F", 0.4), ("ling.recl", 12), ("ling.mat1", 70),
+                 ("ling.mat2", 75), ("ling.rec.scalar", 400), ("lingmat.M", 0.15), ("lingmat.init.scalar", 200),
+                 ("lingmat.walpha", 2.27567436711055e-06), ("lingmat.wbeta", 3.20200445996187),
+                 ("ling.igfs.alpha", 0.5), ("ling.igfs.l50", 50)):
+        p = g3_init_val(p, n, v, lower=0.5 * v, upper=1.5 * v)
+    p = g3_init_val(p, "lingimm.init.#", 1, lower=0.5, upper=1.5)
+    p = g3_init_val(p, "lingmat.init.#", 1, lower=0.5, upper=1.5)
+    p = g3_init_val(p, "ling.rec.#", 1, lower=0.5, upper=1.5)
+    p = g3_init_val(p, "recage", 0, optimise=False)
+    return model, p
+
+
 def profile_sweep(params, names, n_per_axis):
     """Likelihood-profile grid (BASELINE.json config 5): the template everywhere except `names`, which
     sweep their full [lower, upper] range on an n x n (x ...) grid. Returns B x n_optimised."""
@@ -465,4 +562,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen}
+CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen,
+           "LING": build_ling}

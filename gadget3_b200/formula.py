@@ -91,6 +91,7 @@ def g3_exp(x): return UnOp("exp", wrap(x))
 def g3_log(x): return UnOp("log", wrap(x))
 def g3_sqrt(x): return UnOp("sqrt", wrap(x))
 def g3_avoid_zero(x): return UnOp("avoid_zero", wrap(x))
+def g3_as_integer(x): return UnOp("floor", wrap(x))     # as_integer() of R/aab_env.R:9 (loop variables only)
 
 
 age = Var("age")
@@ -400,11 +401,13 @@ class Lowerer:
             if a[0] == "c":
                 v = a[1]
                 f = {"neg": lambda x: -x, "exp": math.exp, "log": math.log, "sqrt": math.sqrt,
-                     "avoid_zero": _avoid_zero}[e.op]
+                     "avoid_zero": _avoid_zero, "floor": math.floor}[e.op]
                 try:
                     return ("c", f(v))
                 except (ValueError, OverflowError):
                     return ("c", float("nan"))
+            if e.op == "floor":
+                raise G3Unsupported("as_integer() of a parameter-dependent value")
             return ("x", a[1] + [_UN[e.op]])
         if isinstance(e, BinOp):
             a, b = self._lower(e.a, ctx), self._lower(e.b, ctx)

@@ -17,7 +17,18 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(_HERE, "_ref")
-SOURCES = {"C1": "ref_c1.cpp", "C2": "ref_c2.cpp"}
+SOURCES = {"C1": "ref_c1.cpp", "C2": "ref_c2.cpp", "LING": "ref_ling.cpp"}
+
+
+def ling_extras(params):
+    """What inttest/codegeneration/ling.cpp declares beyond the generic inputs: two data vectors, two
+    PARAMETER_VECTORs (our by-age scalars lingimm.init.<age> / lingmat.init.<age>) and the dummy parameter x."""
+    from gadget3_b200.configs import LING_IMM_STDDEV, LING_MAT_STDDEV
+    return dict(
+        extra_arrays={"ling_imm_stddev": LING_IMM_STDDEV, "ling_mat_stddev": LING_MAT_STDDEV},
+        vector_params={"lingimm__init": [f"lingimm.init.{a}" for a in range(3, 11)],
+                       "lingmat__init": [f"lingmat.init.{a}" for a in range(5, 16)]},
+        extra_params={"x": 0.0})
 
 
 def lib_path(name):
@@ -39,7 +50,7 @@ def _esc(s):
 
 
 class RefModel:
-    def __init__(self, name, model, params):
+    def __init__(self, name, model, params, extra_arrays=None, vector_params=None, extra_params=None):
         from gadget3_b200.run_cuda import _lgmatrix
         self.lib = C.CDLL(lib_path(name))
         L = self.lib
@@ -58,7 +69,11 @@ class RefModel:
         self.h = C.c_void_p(L.g3ref_new())
         self.params = params
         self.model = model
+        self.vector_params = vector_params or {}
+        self.extra_params = extra_params or {}
         self._set_data(model, params, _lgmatrix)
+        for k, v in (extra_arrays or {}).items():
+            self._arr(k, v)
 
     def _arr(self, name, a, dims=None):
         a = np.asarray(a, dtype=np.float64)
@@ -120,8 +135,13 @@ class RefModel:
 
     def eval(self, full_par, reporting=False):
         self.lib.g3ref_set_scalar(self.h, b"reporting_enabled", 1.0 if reporting else 0.0)
-        for sw, v in zip(self.params.switch, np.asarray(full_par, dtype=np.float64)):
+        full_par = np.asarray(full_par, dtype=np.float64)
+        for sw, v in zip(self.params.switch, full_par):
             self.lib.g3ref_set_param(self.h, _esc(sw).encode(), float(v))
+        for vname, switches in self.vector_params.items():          # PARAMETER_VECTOR
+            self._arr(vname, [full_par[self.params.index(sw)] for sw in switches])
+        for k, v in self.extra_params.items():
+            self.lib.g3ref_set_param(self.h, k.encode(), float(v))
         nll = self.lib.g3ref_eval(self.h)
         nm = self.lib.g3ref_n_missing(self.h)
         if nm:

@@ -253,6 +253,7 @@ template <class Type> struct objective_function {
 #define DATA_UPDATE(x)
 #define DATA_INTEGER(x) int x = (int)this->get_scalar(#x);
 #define PARAMETER(x) Type x = this->get_param(#x);
+#define PARAMETER_VECTOR(x) vector<Type> x = this->template get_array<Type>(#x);
 #define DATA_VECTOR(x) vector<Type> x = this->template get_array<Type>(#x);
 #define DATA_ARRAY(x) array<Type> x = this->template get_array<Type>(#x);
 #define DATA_IVECTOR(x) vector<int> x = this->template get_array<int>(#x);

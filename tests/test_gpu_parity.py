@@ -228,6 +228,25 @@ def test_growth_beyond_maxlengthgroupgrowth(setups):
 
 
 @pytest.mark.parametrize("kernel", [1, 3], ids=["cta_kernel", "thread_kernel"])
+def test_ling_against_reference_generated_code(oracle_lib, kernel):
+    """CUDA vs inttest/codegeneration/ling.cpp (constant maturity, maxlengthgroupgrowth 15, two renewals,
+    age -> mature movement): golden nll from the reference's generated code, gradient vs the oracle."""
+    model, p = CONFIGS["LING"]()
+    fn = g3_cuda_adfun(model, p, device=0)
+    g = golden("LING")
+    assert list(g["switch"]) == list(p.switch)
+    fn.handle.set_kernel(kernel)
+    try:
+        nll, comp, _ = fn.handle.eval_batch(g["par"], want_comp=True)
+        _check_gradients(model, p, fn, Oracle(*model.pack(p)))
+    finally:
+        fn.handle.set_kernel(0)
+    tol = NLL_RTOL * np.abs(g["nll"]) + US_WEIGHT * _us_tolerance(model, p, comp[:, -2])
+    assert (np.abs(nll - g["nll"]) <= tol).all()
+    assert np.median(_rel(nll, g["nll"])) < 1e-12
+
+
+@pytest.mark.parametrize("kernel", [1, 3], ids=["cta_kernel", "thread_kernel"])
 @pytest.mark.parametrize("name", ["C1", "C2"])
 def test_against_reference_generated_code(setups, name, kernel):
     """CUDA nll vs the reference's OWN generated objective (baseline/*.cpp compiled against

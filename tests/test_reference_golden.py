@@ -1,8 +1,10 @@
 """The oracle against the REFERENCE'S OWN generated objectives.
 
-baseline/introduction-single-stock.cpp and baseline/multiple-substocks.cpp (the reference's checked-in
-g3_to_tmb() output) are compiled unmodified against oracle/tmb_shim and run on our C1/C2 model data:
-  * tests/golden/reference_c{1,2}.npz hold their nll and REPORT()ed arrays for seeded vectors
+baseline/introduction-single-stock.cpp, baseline/multiple-substocks.cpp and inttest/codegeneration/ling.cpp
+(the reference's checked-in g3_to_tmb() output) are compiled unmodified against oracle/tmb_shim and run on
+our C1/C2/LING model data (LING = configs.build_ling, the mirror of inttest/codegeneration/run.R:17-183:
+constant maturity, 15-group growth, two renewals, age -> mature movement, report = FALSE likelihood):
+  * tests/golden/reference_{c1,c2,ling}.npz hold their nll and REPORT()ed arrays for seeded vectors
     (tools/make_golden_reference.py) -- checked everywhere, including where /root/reference is absent;
   * where oracle/_ref was built (build container), fresh random vectors are compared live.
 This pins the whole-model arithmetic of the oracle (every action of SURVEY section 8a that C1/C2
@@ -20,13 +22,13 @@ from oracle.oracle_lib import Oracle
 @pytest.fixture(scope="module")
 def setups(oracle_lib):
     out = {}
-    for n in ("C1", "C2"):
+    for n in ("C1", "C2", "LING"):
         model, p = CONFIGS[n]()
         out[n] = (model, p, Oracle(*model.pack(p)))
     return out
 
 
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "LING"])
 def test_oracle_nll_matches_reference_code(setups, name):
     model, p, orc = setups[name]
     g = golden(name)
@@ -71,13 +73,24 @@ def test_oracle_reports_match_reference_code(setups, name, vi):
             np.testing.assert_allclose(mine, ref, rtol=1e-10, atol=1e-300)
 
 
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("vi", [0, 5])
+def test_oracle_ling_understocking_matches_reference_code(setups, vi):
+    """ling.cpp REPORT()s (besides two suitability vectors) only nll_understocking__wgt per step."""
+    model, p, orc = setups["LING"]
+    g = golden("LING")
+    rep = unpack_report(model, orc.report(g["par"][vi]))
+    assert rep["nll"] == pytest.approx(float(g["nll"][vi]), rel=1e-11)
+    us_ref = g[f"v{vi}__nll_understocking__wgt"]
+    assert np.abs(rep["nll_understocking__wgt"] - us_ref).sum() <= us_tolerance(model, p, us_ref.sum())
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "LING"])
 def test_live_reference_when_built(setups, name):
     from oracle import ref_lib
     if not ref_lib.available(name):
         pytest.skip("oracle/_ref not built here (needs /root/reference)")
     model, p, orc = setups[name]
-    ref = ref_lib.RefModel(name, model, p)
+    ref = ref_lib.RefModel(name, model, p, **(ref_lib.ling_extras(p) if name == "LING" else {}))
     full = np.tile(p.values(), (12, 1))
     full[:, p.optimised_indices()] = parameter_batch(p, 12, seed=777)
     o, comp, _ = orc.eval_batch(full, want_comp=True)
