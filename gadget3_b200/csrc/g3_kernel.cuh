@@ -55,6 +55,7 @@ struct KArgs {
     int o_g[MAXS], o_gr[MAXS], o_gn[MAXS], o_pws[MAXS], o_rd[MAXS], o_ms[MAXC], o_xslot[MAXX];
     int maxL;
     long long rep_dstart[MAXS]; long long rep_model[MAXC]; long long rep_params;
+    long long rep_renew[MAXS]; long long rep_pp[32];   // detail section (thread kernel): renewalnum per stock; per pair: suit report, suit, cons
     // ---- warp-per-evaluation kernel (g3_warp_kernel.cuh)
     int w_warp_bytes;                       // shared memory per warp
     int w_G[MAXS], w_ntile[MAXS];           // columns per tile, tiles per stock

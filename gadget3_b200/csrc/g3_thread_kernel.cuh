@@ -344,6 +344,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                     for (size_t i = 0; i < ncs; i++) {
                         A.report[A.rep_dstart[s] + (size_t)t * ncs + i] = val(W(A.t_num + St[G3S_CELL_OFF] + i));
                         A.report[A.rep_dstart[s] + (size_t)NT * ncs + (size_t)t * ncs + i] = val(W(A.t_wgt + St[G3S_CELL_OFF] + i));
+                        // <stock>__renewalnum keeps its last renewal until the next one overwrites it
+                        if (t > 0) A.report[A.rep_renew[s] + (size_t)t * ncs + i] = A.report[A.rep_renew[s] + (size_t)(t - 1) * ncs + i];
                     }
                 }
             // components collecting at this step (bit c), and whether any of them reads a catch
@@ -474,11 +476,13 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 if (prey_now) {
                     unsigned kx[MAXQ], ksuit[MAXQ];     // per predator: collect vectors it feeds, suitability table
                     int kpl[MAXQ], kpts[MAXQ];          // stock predators: predator length groups, table of their consumption factors
+                    int kq[MAXQ];
 #pragma unroll
                     for (int k = 0; k < MAXQ; k++) {
-                        kx[k] = 0; ksuit[k] = 0; kpl[k] = 0; kpts[k] = 0;
+                        kx[k] = 0; ksuit[k] = 0; kpl[k] = 0; kpts[k] = 0; kq[k] = 0;
                         if (k < nq) {
                             const int q = A.stock_pp[A.stock_pp_off[s] + k];
+                            kq[k] = q;
                             const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
                             const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
                             ksuit[k] = (unsigned)A.t_suitq[q] * NTH;
@@ -535,6 +539,24 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                 for (int x = 0; x < MAXX; x++)
                                     if (((xact >> x) & 1) && A.w_x_kind[x] == 0) W(A.t_x[x] + c0 + col * L + l) = fx[x] * cc;
                             }
+                            if (REPORT && live) {       // detail_<prey>_<pred>__suit / __cons (R/action_report.R:177-213)
+                                const T cc = 1.0 / avoid_zero(tp) * tpn * B0;
+                                const size_t ncs = (size_t)ncol * L, ci = (size_t)t * ncs + col * L + l;
+                                for (int k = 0; k < nq; k++)
+                                    if (tsk[k] >= 0) {
+                                        const size_t base = A.rep_pp[kq[k]] + (size_t)(kpl[k] ? kpl[k] : 1) * L;
+                                        T cf;
+                                        if (kpl[k] == 0) {
+                                            cf = ws[ksuit[k] + lN] * eotk[k];
+                                            A.report[base + ci] = val(ws[ksuit[k] + lN] * num * *pw_);
+                                        } else {
+                                            cf = T(0.0);
+                                            for (int pl = 0; pl < kpl[k]; pl++)
+                                                cf = cf + ws[ksuit[k] + (unsigned)(pl * L) * NTH + lN] * W(kpts[k] + tsk[k] * kpl[k] + pl);
+                                        }
+                                        A.report[base + (size_t)NT * ncs + ci] = val(cf * cc);
+                                    }
+                            }
                         }
                     }
                     if (is_us) us_tot = us_tot + (o1 - o2);
@@ -543,6 +565,19 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                         if (((xact >> x) & 1) && A.w_x_kind[x] == 0)
                             for (int i = 0; i < ncol * L; i++) W(A.t_x[x] + c0 + i) = T(0.0);       // no landings: cons = 0
                 }
+                if (REPORT && live && !prey_now)        // steps without landings: the fleets' suit arrays are still filled
+                    for (int k = 0; k < nq; k++) {
+                        const int q = A.stock_pp[A.stock_pp_off[s] + k];
+                        const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+                        if (I[I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN + G3P_KIND] == G3PRED_STOCK) continue;
+                        for (int col = 0; col < ncol; col++) {
+                            if (A.pp_tsid[q * A.maxnarea + col / nage] < 0) continue;
+                            for (int l = 0; l < L; l++) {
+                                const int cell = c0 + col * L + l;
+                                A.report[A.rep_pp[q] + L + ((size_t)t * ncol + col) * L + l] = val(W(A.t_suitq[q] + l) * W(A.t_num + cell) * W(A.t_wgt + cell));
+                            }
+                        }
+                    }
                 if (!has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0) continue;
 
                 // ---------- natural mortality, growth (+ maturing split), hand-over, renewal, collect vectors.
@@ -641,6 +676,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                     const int fs = I[I[St[G3S_RENEW_OFF] + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * narea + ridx];
                                     if (fs >= 0) {
                                         const T rn = W(A.t_rd[s] + r * L + l) * SLOT(fs);
+                                        if (REPORT && live) A.report[A.rep_renew[s] + ((size_t)t * ncol + col) * L + l] = val(rn);
                                         wgt = ratio_add_pop(wgt, num, W(A.t_rw[s] + r * L + l), rn);
                                         num = num + rn;
                                     }
@@ -830,6 +866,14 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
         const T out = bad_time ? T(nan("")) : nll;
         if (!live) continue;
         if (REPORT) A.report[0] = val(out);
+        if (REPORT && live)         // suit_<prey>_<pred>__report (R/action_predate.R:292-299): [predator length][prey length]
+            for (int q = 0; q < A.NPP; q++) {
+                const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+                const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
+                const int n = I[I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN + G3S_L] *
+                              (P[G3P_KIND] == G3PRED_STOCK ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1);
+                for (int i = 0; i < n; i++) A.report[A.rep_pp[q] + i] = val(W(A.t_suitq[q] + i));
+            }
         if (tile_t == 0) {
             A.nll[b] = val(out);
             if (A.comp) for (int c = 0; c < A.NNLL; c++) A.comp[b * A.NNLL + c] = bad_time ? nan("") : val(W(A.t_ctot + c));

@@ -57,7 +57,7 @@ struct g3cuda_model {
     std::vector<void*> owned;           // device allocations
     int nthreads = 0;
     int num_sms = 0;
-    int64_t report_len = 0;
+    int64_t report_len = 0, rep_detail = 0;      // rep_detail: first double of the g3a_report_detail section
     int64_t launches = 0;
     // per-call scratch (grow-only)
     double* d_par = nullptr; double* d_nll = nullptr; double* d_comp = nullptr; double* d_grad = nullptr;
@@ -376,7 +376,7 @@ template <class T>
 int launch(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStream_t st) {
     const bool is_double = std::is_same<T, double>::value;
     if (m->thread_ok && (m->force_kernel == 0 || m->force_kernel == 3) &&
-        (call.report ? (m->force_kernel == 3 || !m->cta_ok_double) : (is_double || m->force_kernel == 3 || work >= 16384 || !m->cta_ok_dual))) {
+        (call.report ? true : (is_double || m->force_kernel == 3 || work >= 16384 || !m->cta_ok_dual))) {
         g3::KArgs a = m->base;
         a.par = call.par; a.B = call.B; a.tangent_idx = call.tangent_idx; a.K = call.K;
         a.nll = call.nll; a.comp = call.comp; a.grad = call.grad; a.report = call.report;
@@ -780,6 +780,20 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         A.rep_model[c] = pos; pos += (int64_t)C[G3C_N_TIMES] * C[G3C_N_DEST];
     }
     A.rep_params = pos; pos += 2LL * A.NCOMP;
+    m->rep_detail = pos;
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = stock(s);
+        A.rep_renew[s] = pos;
+        pos += (int64_t)A.NT * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+    }
+    for (int q = 0; q < A.NPP && q < 32; q++) {
+        const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+        const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
+        const int32_t* St = stock(Q[G3PP_PREY]);
+        const int64_t PL = P[G3P_KIND] == G3PRED_STOCK ? stock(P[G3P_STOCK])[G3S_L] : 1;
+        A.rep_pp[q] = pos;
+        pos += PL * St[G3S_L] + 2LL * A.NT * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+    }
     m->report_len = pos;
 
     int need = std::max({A.NC, maxnd, maxnt, A.maxL, 32});
@@ -913,6 +927,9 @@ int g3cuda_report(g3cuda_model* m, const double* par, double* out) {
             int f = I[I[G3H_COMP_OFF] + c * G3C_LEN + G3C_FUNC];
             if (f != G3F_SI_LOG && f != G3F_SI_LINEAR) out[m->base.rep_params + 2 * c] = out[m->base.rep_params + 2 * c + 1] = std::nan("");
         }
+        // the detail_* / suit_*__report section is written by the thread kernel only
+        if (!rc && !(m->thread_ok && (m->force_kernel == 0 || m->force_kernel == 3)))
+            for (int64_t i = m->rep_detail; i < m->report_len; i++) out[i] = std::nan("");
     }
     cudaFree(d_rep); cudaFree(d_nll);
     return rc;

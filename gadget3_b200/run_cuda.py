@@ -60,6 +60,7 @@ class G3CudaModel:
         self._builder = None
         self.stock_names, self.stock_shapes, self.stock_dims = [], [], []
         self.comp_names, self.comp_shapes, self.comp_units = [], [], []
+        self.pp_info = []           # (predator name, prey name, predator length groups or 1), packed pair order
         self.nll_names = []
         self.n_steps = 0
         self.time_labels = []
@@ -231,7 +232,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         srec[name][K["G3S_MIGRATE_OFF"]] = b.alloc_ints(tab)
 
     # ---- predation (order 3): predators by name, prey by name
-    pred_recs, pp_recs, pp_index = [], [], {}
+    pred_recs, pp_recs, pp_index, pp_info = [], [], {}, []
     for pname, a in preds.items():
         pr = [0] * K["G3P_LEN"]
         ps = a.predstock
@@ -286,6 +287,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                 raise G3Unsupported("g3_suitability_andersen needs a stock predator (predator_length)")
             pp_index[(pname, prey.name)] = len(pp_recs)
             pp_recs.append(q)
+            pp_info.append((pname, prey.name, ps.L if cat.kind == "predator" else 1))
         pr[K["G3P_N_PP"]] = len(pp_recs) - pr[K["G3P_PP_FIRST"]]
         pred_recs.append(pr)
 
@@ -553,6 +555,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         model.stock_names.append(n)
         model.stock_shapes.append((s.L, s.nage, len(s.areas)))
         model.stock_dims.append(list(s.dims))
+    model.pp_info = pp_info
     model.nll_names = list(model.comp_names) + ["understocking", "bounds"]
     model.n_steps = NT
     model.time_labels = ["%d-%02d" % (tm.start_year + t // S, t % S + 1) for t in range(NT)]
@@ -645,6 +648,28 @@ def unpack_report(model: G3CudaModel, raw: np.ndarray) -> dict:
                                             sh["n_bins"]).copy()
     for n in model.comp_names:
         out[f"{n}_model__params"] = raw[pos:pos + 2].copy(); pos += 2
+
+    def detail(n_stock):            # canonical [time][area][age][length] -> the stock's own order, time last
+        L, A_, R = model.stock_shapes[n_stock]
+        nonlocal pos
+        a = raw[pos:pos + NT * L * A_ * R].reshape(NT, R, A_, L); pos += NT * L * A_ * R
+        order = [d for d in model.stock_dims[n_stock] if d != "length"]
+        return np.ascontiguousarray(a.transpose(3, 2, 1, 0) if order == ["age", "area"] else a.transpose(3, 1, 2, 0))
+
+    # g3a_report_detail's remaining arrays (R/action_report.R:177-213; baseline/multiple-substocks.cpp:598-601,2045-2065).
+    # Written by the thread-per-evaluation kernel; NaN when the report ran on the CTA kernel.
+    for i, n in enumerate(model.stock_names):
+        out[f"detail_{n}__renewalnum"] = detail(i)
+    for pred, prey, PL in model.pp_info:
+        si = model.stock_names.index(prey)
+        L = model.stock_shapes[si][0]
+        sr = raw[pos:pos + PL * L].copy(); pos += PL * L
+        out[f"suit_{prey}_{pred}__report"] = sr if PL == 1 else np.ascontiguousarray(sr.reshape(PL, L).T)
+        out[f"detail_{prey}_{pred}__suit"] = detail(si)
+        out[f"detail_{prey}_{pred}__cons"] = detail(si)
+        out[f"detail_{prey}__predby_{pred}"] = out[f"detail_{prey}_{pred}__cons"]
+    if pos != len(raw):
+        raise ValueError(f"report buffer has {len(raw)} doubles, layout needs {pos}")
     return out
 
 

@@ -106,6 +106,14 @@ float g3cuda_last_kernel_ms(g3cuda_model* m);
  *   of g3a_report_detail, R/action_report.R:177-213)
  *   then per component: model array [n_times][n_dest] (canonical dest layout)
  *   then per component: 2 doubles (surveyindices alpha, beta; NaN otherwise)
+ *   then the rest of g3a_report_detail (R/action_report.R:177-213), written by the
+ *   thread-per-evaluation kernel (NaN if the report was forced onto the CTA kernel):
+ *     per stock: renewalnum [NT][cells]                       (detail_<stock>__renewalnum)
+ *     per predator-prey pair, in packed pair order:
+ *       suitability [predator length groups (1 for a fleet)][prey L]   (suit_<prey>_<pred>__report)
+ *       suit [NT][prey cells]   (detail_<prey>_<pred>__suit; fleets only, 0 for stock predators)
+ *       cons [NT][prey cells]   (detail_<prey>_<pred>__cons == detail_<prey>__predby_<pred>,
+ *                                summed over the predator's own dimensions)
  * Replaces: obj$report(par) (R/run_tmb.R:1277-1321). */
 int g3cuda_report(g3cuda_model* m, const double* par, double* out);
 

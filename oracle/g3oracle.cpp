@@ -285,6 +285,9 @@ struct ReportSink {
     std::vector<double*> dstart_num, dstart_wgt;   // per stock [NT][cells]
     std::vector<double*> model;                    // per comp [n_times][n_dest]
     std::vector<double*> params;                   // per comp [2]
+    std::vector<double*> renewalnum;               // per stock [NT][cells]   (detail_<stock>__renewalnum)
+    std::vector<double*> suit_report;              // per predator-prey pair [predator lengths (1 for a fleet)][L]
+    std::vector<double*> dsuit, dcons;             // per pair [NT][prey cells] (detail_<prey>_<pred>__suit/__cons)
 };
 
 template <class T>
@@ -307,6 +310,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
     std::vector<T> totalpredate(NC), consratio(NC), consconv(NC);
     std::vector<std::vector<T>> suit(NPP, std::vector<T>(NC, T(0.0))), cons(NPP, std::vector<T>(NC, T(0.0)));
     std::vector<T> overcons(NS, T(0.0));
+    std::vector<T> renewalnum(NC, T(0.0));       // <stock>__renewalnum: only ever overwritten by a renewal
     std::vector<std::vector<T>> trans_num(NS), trans_wgt(NS), growth_l(NS), growth_w(NS);
     std::vector<int> lastcalc(NS, -1);
     std::vector<std::vector<T>> mv_num(NS), mv_wgt(NS);
@@ -639,9 +643,27 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                     for (int l = 0; l < L; l++) {
                         int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + Rn[G3R_AGE_IDX]) * L + l;
                         T rn = d[l] / den * 10000.0 * factor, rw = wa * xpow(midlen[l], wb);
+                        renewalnum[c] = rn;
                         wgt[c] = ratio_add_pop(wgt[c], num[c], rw, rn);
                         num[c] = num[c] + rn;
                     }
+                }
+            }
+        }
+
+        // ---- g3a_report_detail (R/action_report.R:177-213): this step's detail_* columns
+        if (rep) {
+            for (int s = 0; s < NS; s++) {
+                const int32_t* St = S.stock(s);
+                int c0 = St[G3S_CELL_OFF], n = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+                for (int i = 0; i < n; i++) rep->renewalnum[s][(size_t)cur_time * n + i] = val(renewalnum[c0 + i]);
+            }
+            for (int q = 0; q < NPP; q++) {
+                const int32_t* St = S.stock(S.pp(q)[G3PP_PREY]);
+                int c0 = St[G3S_CELL_OFF], n = St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+                for (int i = 0; i < n; i++) {
+                    rep->dsuit[q][(size_t)cur_time * n + i] = val(suit[q][c0 + i]);
+                    rep->dcons[q][(size_t)cur_time * n + i] = val(cons[q][c0 + i]);
                 }
             }
         }
@@ -826,6 +848,16 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             rep->params[c][0] = si ? val(si_params[c][0]) : NaN;
             rep->params[c][1] = si ? val(si_params[c][1]) : NaN;
         }
+        for (int q = 0; q < NPP; q++) {         // suit_<prey>_<pred>__report (R/action_predate.R:292-299)
+            const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
+            const bool sp = P[G3P_KIND] == G3PRED_STOCK;
+            const int32_t* Sp = sp ? S.stock(P[G3P_STOCK]) : nullptr;
+            int L = St[G3S_L], PL = sp ? Sp[G3S_L] : 1;
+            bool ok = true;
+            for (int pl = 0; pl < PL; pl++) for (int l = 0; l < L; l++)
+                rep->suit_report[q][pl * L + l] = val(suitability<T>(Q[G3PP_SUIT_KIND], S.I + Q[G3PP_SUIT_OFF], slot,
+                    (S.R + St[G3S_MIDLEN_ROFF])[l], sp ? (S.R + Sp[G3S_MIDLEN_ROFF])[pl] : 0.0, ok));
+        }
     }
     return nll;
 }
@@ -837,6 +869,15 @@ int64_t report_len(const Spec& S) {
         n += 2LL * S.h(G3H_NT) * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
     }
     for (int c = 0; c < S.h(G3H_NCOMP); c++) n += (int64_t)S.comp(c)[G3C_N_TIMES] * S.comp(c)[G3C_N_DEST] + 2;
+    for (int s = 0; s < S.h(G3H_NSTOCK); s++) {
+        const int32_t* St = S.stock(s);
+        n += (int64_t)S.h(G3H_NT) * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+    }
+    for (int q = 0; q < S.h(G3H_NPP); q++) {
+        const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
+        int PL = P[G3P_KIND] == G3PRED_STOCK ? S.stock(P[G3P_STOCK])[G3S_L] : 1;
+        n += (int64_t)PL * St[G3S_L] + 2LL * S.h(G3H_NT) * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+    }
     return n;
 }
 
@@ -905,6 +946,18 @@ int g3oracle_report(const int32_t* ints, const double* reals, const double* par,
     }
     for (int c = 0; c < S.h(G3H_NCOMP); c++) { rep.model.push_back(p); p += (size_t)S.comp(c)[G3C_N_TIMES] * S.comp(c)[G3C_N_DEST]; }
     for (int c = 0; c < S.h(G3H_NCOMP); c++) { rep.params.push_back(p); p += 2; }
+    for (int s = 0; s < S.h(G3H_NSTOCK); s++) {
+        const int32_t* St = S.stock(s);
+        rep.renewalnum.push_back(p); p += (size_t)NT * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+    }
+    for (int q = 0; q < S.h(G3H_NPP); q++) {
+        const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
+        size_t PL = P[G3P_KIND] == G3PRED_STOCK ? S.stock(P[G3P_STOCK])[G3S_L] : 1;
+        size_t n = (size_t)NT * St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA];
+        rep.suit_report.push_back(p); p += PL * St[G3S_L];
+        rep.dsuit.push_back(p); p += n;
+        rep.dcons.push_back(p); p += n;
+    }
     std::fill(out, p, 0.0);
     ParVec<double> pv{par, nullptr, 0};
     run_model<double>(S, pv, nullptr, &rep);

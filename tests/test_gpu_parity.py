@@ -30,7 +30,7 @@ def _rel(a, b, floor=0.0):
     return np.abs(a - b) / np.maximum(np.abs(b), floor if floor > 0 else 1e-300)
 
 
-from _util import US_WEIGHT, golden, us_tolerance as _us_tolerance  # noqa: E402
+from _util import US_WEIGHT, check_detail_reports, golden, us_tolerance as _us_tolerance  # noqa: E402
 
 
 def _us_weight(model):
@@ -131,6 +131,9 @@ def test_report_arrays(setups, name, kernel):
     for k in ro:
         a, b = np.asarray(rg[k], dtype=float), np.asarray(ro[k], dtype=float)
         assert a.shape == b.shape, k
+        if kernel == 1 and (k.startswith("detail_") or k.startswith("suit_")):
+            assert np.isnan(a).all(), k           # that section is the thread kernel's (include/g3cuda.h)
+            continue
         assert (np.isnan(a) == np.isnan(b)).all(), k
         m = ~np.isnan(b)
         if not m.any():
@@ -144,6 +147,21 @@ def test_report_arrays(setups, name, kernel):
                 assert (a[m] == 0.0).all(), k
                 continue
             assert (np.abs(a - b)[m] / np.maximum(np.abs(b[m]), 1e-12 * scale)).max() < 1e-9, k
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_detail_reports_against_reference_generated_code(setups, name):
+    """detail_*__renewalnum/suit/cons/predby and suit_*__report from g3cuda_report() vs the arrays the
+    reference's generated code REPORT()s (tests/golden/reference_*.npz)."""
+    model, p, fn, orc = setups[name]
+    g = golden(name)
+    for vi in (0, 5):
+        rep = unpack_report(model, fn.handle.report(g["par"][vi]))
+        assert check_detail_reports(model, rep, g, vi) >= 5
+        for sn in model.stock_names:
+            for what in ("num", "wgt"):
+                np.testing.assert_allclose(rep[f"dstart_{sn}__{what}"][..., g["report_times"]],
+                                           g[f"v{vi}__dstart_{sn}__{what}"], rtol=1e-9, atol=1e-300)
 
 
 def test_single_vector_fn_gr(setups):

@@ -13,7 +13,7 @@ exercise) to the reference's code, not to a re-reading of it.
 import numpy as np
 import pytest
 
-from _util import US_WEIGHT, golden, us_tolerance
+from _util import US_WEIGHT, check_detail_reports, golden, us_tolerance
 from gadget3_b200.configs import CONFIGS, parameter_batch
 from gadget3_b200.run_cuda import unpack_report
 from oracle.oracle_lib import Oracle
@@ -71,6 +71,7 @@ def test_oracle_reports_match_reference_code(setups, name, vi):
             ref = g[f"v{vi}__dstart_{sn}__{what}"]
             mine = rep[f"dstart_{sn}__{what}"][..., times]
             np.testing.assert_allclose(mine, ref, rtol=1e-10, atol=1e-300)
+    check_detail_reports(model, rep, g, vi)
 
 
 @pytest.mark.parametrize("vi", [0, 5])
@@ -82,6 +83,7 @@ def test_oracle_ling_understocking_matches_reference_code(setups, vi):
     assert rep["nll"] == pytest.approx(float(g["nll"][vi]), rel=1e-11)
     us_ref = g[f"v{vi}__nll_understocking__wgt"]
     assert np.abs(rep["nll_understocking__wgt"] - us_ref).sum() <= us_tolerance(model, p, us_ref.sum())
+    assert check_detail_reports(model, rep, g, vi) == 2          # the two suit_*__report vectors
 
 
 @pytest.mark.parametrize("name", ["C1", "C2", "LING"])

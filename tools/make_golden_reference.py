@@ -47,6 +47,15 @@ if __name__ == "__main__":
                     a = ref.report(f"dstart_{sn}__{what}")
                     if a is not None:           # (the ling model has no g3a_report_detail)
                         out[f"v{vi}__dstart_{sn}__{what}"] = a[..., REPORT_TIMES]
+                a = ref.report(f"detail_{sn}__renewalnum")
+                if a is not None:
+                    out[f"v{vi}__detail_{sn}__renewalnum"] = a[..., REPORT_TIMES]
+            for pred, prey, _ in model.pp_info:
+                for key in (f"detail_{prey}_{pred}__suit", f"detail_{prey}_{pred}__cons", f"detail_{prey}__predby_{pred}"):
+                    a = ref.report(key)
+                    if a is not None:
+                        out[f"v{vi}__{key}"] = a[..., REPORT_TIMES]
+                out[f"v{vi}__suit_{prey}_{pred}__report"] = ref.report(f"suit_{prey}_{pred}__report")
         out["report_times"] = np.array(REPORT_TIMES)
         path = os.path.join(ROOT, "tests", "golden", f"reference_{name.lower()}.npz")
         out = {k: v for k, v in out.items() if v is not None}      # (ling.cpp REPORT()s only nll_understocking__wgt)
