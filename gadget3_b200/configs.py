@@ -80,15 +80,17 @@ def _fleet_data(rng, years, landings_mean, landings_sd, n_ldist, len_breaks, n_a
     return out
 
 
-def build_c1(seed=123):
-    """introduction-single-stock (vignettes/introduction-single-stock.Rmd:116-596, 666-701)."""
+def build_c1(seed=123, data=None):
+    """introduction-single-stock (vignettes/introduction-single-stock.Rmd:116-596, 666-701).
+    `data`: the fleet tables (landings, ldist, aldist, si as column dicts) to use instead of the synthetic
+    draws -- tools/replay_tmb_bundle.py feeds the tables an R session dumped."""
     rng = np.random.default_rng(seed)
     years = list(range(1990, 2024))
     area_names = g3_areas(["IXa", "IXb"])
     ixa = {"IXa": area_names["IXa"]}
     fish = g3s_age(g3s_livesonareas(g3_stock("fish", range(10, 101, 10)), ixa), 1, 5)
-    d = _fleet_data(rng, years, 1000, 100, 100, range(0, 81, 20), 10000,
-                    lambda r, n: np.floor(r.uniform(1, 5, n)), lambda a: 30 + a * 10)
+    d = data or _fleet_data(rng, years, 1000, 100, 100, range(0, 81, 20), 10000,
+                            lambda r, n: np.floor(r.uniform(1, 5, n)), lambda a: 30 + a * 10)
     f_surv = g3s_livesonareas(g3_fleet("f_surv"), ixa)
     actions = [
         g3a_time(1990, 2023, [3, 3, 3, 3]),
@@ -135,8 +137,8 @@ def build_c1(seed=123):
     return model, p
 
 
-def build_c2(seed=123):
-    """multiple-substocks (vignettes/multiple-substocks.Rmd:59-439)."""
+def build_c2(seed=123, data=None):
+    """multiple-substocks (vignettes/multiple-substocks.Rmd:59-439). `data`: as build_c1, plus matp."""
     rng = np.random.default_rng(seed)
     years = list(range(1990, 2024))
     area_names = g3_areas(["IXa", "IXb"])
@@ -144,9 +146,9 @@ def build_c2(seed=123):
     st_imm = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "imm"}, range(5, 101, 5)), 1, 5), ixa)
     st_mat = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "mat"}, range(5, 101, 5)), 3, 10), ixa)
     stocks = [st_imm, st_mat]
-    d = _fleet_data(rng, years, 1e5, 10, 1000, range(0, 111, 5), 10000,
-                    lambda r, n: np.floor(np.minimum(r.normal(6, 1, n), 10)), lambda a: 30 + a * 2,
-                    maturity=True)
+    d = data or _fleet_data(rng, years, 1e5, 10, 1000, range(0, 111, 5), 10000,
+                            lambda r, n: np.floor(np.minimum(r.normal(6, 1, n), 10)), lambda a: 30 + a * 2,
+                            maturity=True)
     f_surv = g3s_livesonareas(g3_fleet("f_surv"), ixa)
     actions = [
         g3a_time(1990, 2023, [3, 3, 3, 3]),
