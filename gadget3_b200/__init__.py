@@ -8,8 +8,9 @@ hand-written CUDA library in ``csrc/`` reached through the C ABI in ``include/g3
 from .formula import (G3Unsupported, ParameterTemplate, Lookup, age, area, cur_step, cur_step_size,
                       cur_year, g3_as_integer, g3_avoid_zero, g3_exp, g3_init_val, g3_log, g3_parameterized, g3_sqrt)
 from .stock import (g3_areas, g3_fleet, g3_stock, g3_stock_def, g3s_age, g3s_length, g3s_livesonareas)
-from .actions import (g3_action_order, g3_suitability_andersen, g3_suitability_constant,
-                      g3_suitability_exponentiall50, g3_timeareadata, g3a_age, g3a_grow_impl_bbinom,
+from .actions import (g3_action_order, g3_suitability_andersen, g3_suitability_andersenfleet,
+                      g3_suitability_constant, g3_suitability_exponential, g3_suitability_exponentiall50,
+                      g3_suitability_gamma, g3_suitability_richards, g3_suitability_straightline, g3_timeareadata, g3a_age, g3a_grow_impl_bbinom,
                       g3a_grow_lengthvbsimple, g3a_grow_weightsimple, g3a_growmature,
                       g3a_initialconditions_normalcv, g3a_initialconditions_normalparam,
                       g3a_mature_constant, g3a_mature_continuous, g3a_migrate, g3a_naturalmortality,

@@ -333,6 +333,39 @@ def g3_suitability_constant(suit=None, by_stock=True, by_predator=True):
     return _Suitability("constant", [suit])
 
 
+def g3_suitability_andersenfleet(p0=None, p1=None, p2=None, p3=None, p4=None, by_stock=True, by_predator=True,
+                                 exponentiate=True):
+    """R/suitability.R:32-58 (p5 stays the prey's largest midlen)."""
+    import math
+    gp = g3_parameterized
+    p0 = gp("andersen.p0", value=0, optimise=False, by_stock=by_stock) if p0 is None else wrap(p0)
+    p1 = gp("andersen.p1", value=math.log(2), by_stock=by_stock, by_predator=by_predator) if p1 is None else wrap(p1)
+    p2 = gp("andersen.p2", value=1, optimise=False, by_stock=by_stock) if p2 is None else wrap(p2)
+    p3 = gp("andersen.p3", value=0.1, exponentiate=exponentiate, by_stock=by_stock, by_predator=by_predator) if p3 is None else wrap(p3)
+    p4 = gp("andersen.p4", value=0.1, exponentiate=exponentiate, by_stock=by_stock, by_predator=by_predator) if p4 is None else wrap(p4)
+    return _Suitability("andersenfleet", [p0, p1, p2, p3, p4])
+
+
+def g3_suitability_gamma(alpha, beta, gamma):
+    """R/suitability.R:60-67."""
+    return _Suitability("gamma", [wrap(alpha), wrap(beta), wrap(gamma)])
+
+
+def g3_suitability_exponential(alpha, beta, gamma, delta):
+    """R/suitability.R:69-75 (reads predator_length: stock predators only)."""
+    return _Suitability("exponential", [wrap(alpha), wrap(beta), wrap(gamma), wrap(delta)])
+
+
+def g3_suitability_straightline(alpha, beta):
+    """R/suitability.R:77-79."""
+    return _Suitability("straightline", [wrap(alpha), wrap(beta)])
+
+
+def g3_suitability_richards(p0, p1, p2, p3, p4):
+    """R/suitability.R:90-94."""
+    return _Suitability("richards", [wrap(p0), wrap(p1), wrap(p2), wrap(p3), wrap(p4)])
+
+
 class TimeAreaData:
     """g3_timeareadata (R/timedata.R:89-157): year/step/[area] -> value lookup, default 0."""
 

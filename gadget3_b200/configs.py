@@ -393,11 +393,12 @@ def build_c5(seed=123):
     return model, p
 
 
-def build_mini_andersen(seed=123):
+def build_mini_andersen(seed=123, suits=False):
     """Small 2-area test model: a stock predator with g3_suitability_andersen (predator-length dependent
     suitability), migration on one step only for the predator, renewal, ageing -- exercises the code
     paths config 5 does not (used by the parity tests, not by bench.py)."""
-    from . import g3_suitability_andersen
+    from . import (g3_suitability_andersen, g3_suitability_andersenfleet, g3_suitability_gamma,
+                   g3_suitability_richards, g3_suitability_straightline)
     areas = g3_areas(["a", "b"])
     prey = g3s_livesonareas(g3s_age(g3_stock("prey", range(5, 50, 5)), 1, 3), areas)
     pred = g3s_livesonareas(g3s_age(g3_stock("pred", range(20, 70, 10)), 2, 4), areas)
@@ -408,6 +409,10 @@ def build_mini_andersen(seed=123):
     su = g3_suitability_andersen(g3_parameterized("and.p0", value=0.0), g3_parameterized("and.p1", value=1.2),
                                  g3_parameterized("and.p2", value=1.0), g3_parameterized("and.p3", value=0.5),
                                  g3_parameterized("and.p4", value=0.8))
+    if suits:       # the other suitability forms of R/suitability.R:32-94: richards for the predator, three fleets on the prey
+        gp = g3_parameterized
+        su = g3_suitability_richards(gp("ri.p0", value=-4.0), gp("ri.p1", value=0.15), gp("ri.p2", value=0.02),
+                                     gp("ri.p3", value=0.9), gp("ri.p4", value=1.6))
     actions = [
         g3a_time(2000, 2003, [3, 3, 3, 3]),
         g3a_initialconditions_normalcv(prey), g3a_initialconditions_normalcv(pred),
@@ -421,6 +426,24 @@ def build_mini_andersen(seed=123):
     ]
     rng = np.random.default_rng(seed)
     yrs = [2000, 2001, 2002, 2003]
+    if suits:
+        gp = g3_parameterized
+        fsu = dict(f_gam=g3_suitability_gamma(gp("ga.alpha", value=3.0), gp("ga.beta", value=2.0), gp("ga.gamma", value=3.5)),
+                   f_and=g3_suitability_andersenfleet(),
+                   f_lin=g3_suitability_straightline(gp("sl.alpha", value=0.05), gp("sl.beta", value=0.01)))
+        for fname, fs in fsu.items():
+            fl = g3s_livesonareas(g3_fleet(fname), areas)
+            land = dict(year=[y for y in yrs for _ in range(2)], step=[2] * 8, area=["a", "b"] * 4,
+                        weight=list(rng.uniform(5, 20, 8)))
+            actions.append(g3a_predate_fleet(fl, [prey], suitabilities=fs,
+                                             catchability_f=g3a_predate_catchability_totalfleet(
+                                                 g3_timeareadata("landings_" + fname, land, "weight", areas=areas))))
+            if fname == "f_lin":
+                continue        # (the kernels keep at most four collect vectors: two catches + two survey indices here)
+            ld = dict(year=[y for y in yrs for _ in range(3)], step=[2] * 12,
+                      length=["[5,20)", "[20,35)", "[35,Inf)"] * 4, number=list(rng.uniform(10, 100, 12)))
+            actions.append(g3l_catchdistribution("ldist_" + fname, ld, fleets=[fl], stocks=[prey],
+                                                 function_f=g3l_distribution_sumofsquares(), area_group=None))
     for nm, stk in (("si_prey", prey), ("si_pred", pred)):
         si = dict(year=[y for y in yrs for _ in range(2)], step=[3] * 8, area=["a", "b"] * 4,
                   number=list(rng.uniform(1e4, 1e5, 8)))
@@ -448,6 +471,17 @@ def build_mini_andersen(seed=123):
     p = g3_init_val(p, "*.rec.#", 5, lower=0.1, upper=20)
     p = g3_init_val(p, "*.rec.scalar", 10, optimise=False)
     p = g3_init_val(p, "*.rec.proj", 1)
+    if suits:
+        p = g3_init_val(p, "ri.p0", -4.0, lower=-6, upper=-2)
+        p = g3_init_val(p, "ri.p1", 0.15, lower=0.05, upper=0.3)
+        p = g3_init_val(p, "ri.p4", 1.6, lower=0.8, upper=3)
+        p = g3_init_val(p, "ga.alpha", 3.0, lower=2, upper=5)
+        p = g3_init_val(p, "ga.beta", 2.0, lower=1, upper=4)
+        p = g3_init_val(p, "sl.beta", 0.01, lower=0.001, upper=0.05)
+        p = g3_init_val(p, "*.andersen.p1", np.log(2), lower=0.2, upper=1.5)
+        p = g3_init_val(p, "*.andersen.p3_exp", 0.1, lower=-1, upper=1)
+        p = g3_init_val(p, "*.andersen.p4_exp", 0.1, lower=-1, upper=1)
+        return model, p
     p = g3_init_val(p, "and.p1", 1.2, lower=0.5, upper=2)
     p = g3_init_val(p, "and.p3", 0.5, lower=0.1, upper=2)
     p = g3_init_val(p, "and.p4", 0.8, lower=0.1, upper=2)
@@ -564,5 +598,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen,
+CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True),
            "LING": build_ling}

@@ -79,6 +79,20 @@ template <class T> __device__ __forceinline__ T suitability_of(int kind, const T
         const T a2 = avoid_zero(p[2]);
         return p[0] + a2 * xexp(-(d * d) / avoid_zero(p[3])) * lo + a2 * xexp(-(d * d) / avoid_zero(p[4])) * hi;
     }
+    if (kind == G3SUIT_ANDERSENFLEET) {     // pl = the prey's largest midlen; R/suitability.R:32-58
+        const T x = xlog(T(pl / ml));
+        const T d = x - p[1];
+        const T lo = 1.0 / (1.0 + xexp(1000.0 * (p[1] - x)));
+        const T hi = 1.0 / (1.0 + xexp(1000.0 * (x - p[1])));
+        return p[0] + p[2] * xexp(-(d * d) / p[3]) * lo + p[2] * xexp(-(d * d) / p[4]) * hi;
+    }
+    if (kind == G3SUIT_GAMMA)               // R/suitability.R:60-67
+        return xpow(T(ml) / ((p[0] - 1.0) * p[1] * p[2]), p[0] - 1.0) * xexp(p[0] - 1.0 - T(ml) / (p[1] * p[2]));
+    if (kind == G3SUIT_EXPONENTIAL || kind == G3SUIT_RICHARDS) {       // R/suitability.R:69-75,90-94
+        const T e = p[3] / (1.0 + xexp(-p[0] - p[1] * ml - p[2] * pl));
+        return kind == G3SUIT_RICHARDS ? xpow(e, 1.0 / p[4]) : e;
+    }
+    if (kind == G3SUIT_STRAIGHTLINE) return p[0] + p[1] * ml;           // R/suitability.R:77-79
     return p[0];
 }
 
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             for (int pl = 0; pl < PL; pl++)
                 for (int l = 0; l < L; l++)
                     W(A.t_suitq[q] + pl * L + l) = suitability_of<T>(Q[G3PP_SUIT_KIND], sp, R[Ps[G3S_MIDLEN_ROFF] + l],
-                                                                     spred ? R[Pp[G3S_MIDLEN_ROFF] + pl] : 0.0);
+                        spred && Q[G3PP_SUIT_KIND] != G3SUIT_ANDERSENFLEET ? R[Pp[G3S_MIDLEN_ROFF] + pl] : R[Ps[G3S_MIDLEN_ROFF] + L - 1]);
         }
         // stock predators: maximum consumption per predator length without the step length,
         // m0 exp(m1 T - m2 T^3) l^m3 (R/action_predate.R:190-205)

@@ -584,10 +584,12 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
         const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
         const int32_t* St = stock(Q[G3PP_PREY]);
-        if (Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSEN) {
-            if (P[G3P_KIND] != G3PRED_STOCK) return bail(fail(G3CUDA_EUNSUPP, "g3_suitability_andersen needs a stock predator"));
-        } else if (Q[G3PP_SUIT_KIND] != G3SUIT_EXPL50 && Q[G3PP_SUIT_KIND] != G3SUIT_CONSTANT)
-            return bail(fail(G3CUDA_EUNSUPP, "suitability kind %d is not supported yet", Q[G3PP_SUIT_KIND]));
+        const int sk = Q[G3PP_SUIT_KIND];
+        if (sk == G3SUIT_ANDERSEN || sk == G3SUIT_EXPONENTIAL || sk == G3SUIT_RICHARDS) {
+            if (P[G3P_KIND] != G3PRED_STOCK) return bail(fail(G3CUDA_EUNSUPP, "suitability kind %d reads predator_length: it needs a stock predator", sk));
+        } else if (sk < 0 || sk > G3SUIT_RICHARDS)
+            return bail(fail(G3CUDA_EUNSUPP, "suitability kind %d is not supported", sk));
+        if (sk != G3SUIT_EXPL50 && sk != G3SUIT_CONSTANT) m->only_thread = true;     // the CTA / warp kernels know two forms only
         pp_of_stock[Q[G3PP_PREY]].push_back(q);
         for (int r = 0; r < St[G3S_NAREA]; r++) {
             int area = I[St[G3S_AREA_OFF] + r];

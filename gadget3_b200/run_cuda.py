@@ -276,15 +276,14 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             c = Ctx(stock=prey, predstock=ps)
             q = [0] * K["G3PP_LEN"]
             q[K["G3PP_PRED"]], q[K["G3PP_PREY"]] = len(pred_recs), sidx[prey.name]
-            q[K["G3PP_SUIT_KIND"]] = {"expl50": K["G3SUIT_EXPL50"], "andersen": K["G3SUIT_ANDERSEN"],
-                                      "constant": K["G3SUIT_CONSTANT"]}[su.kind]
+            q[K["G3PP_SUIT_KIND"]] = K["G3SUIT_" + {"expl50": "EXPL50"}.get(su.kind, su.kind.upper())]
             slots = [low.slot(x, c) for x in su.args]
             q[K["G3PP_SUIT_OFF"]] = b.alloc_ints(slots + [-1] * (6 - len(slots)))
             q[K["G3PP_ENERGY"]] = q[K["G3PP_PREF"]] = -1
             if cat.kind == "predator":
                 q[K["G3PP_ENERGY"]] = low.slot(cat.kw["energycontent"], c)
-            elif su.kind == "andersen":
-                raise G3Unsupported("g3_suitability_andersen needs a stock predator (predator_length)")
+            elif su.kind in ("andersen", "exponential", "richards"):
+                raise G3Unsupported(f"g3_suitability_{su.kind} needs a stock predator (predator_length)")
             pp_index[(pname, prey.name)] = len(pp_recs)
             pp_recs.append(q)
             pp_info.append((pname, prey.name, ps.L if cat.kind == "predator" else 1))

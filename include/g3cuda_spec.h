@@ -136,6 +136,11 @@
 #define G3SUIT_EXPL50      0   /* alpha, l50 (R/suitability.R:5) */
 #define G3SUIT_ANDERSEN    1   /* p0..p4, p5 = predator length (R/suitability.R:15) */
 #define G3SUIT_CONSTANT    2   /* value */
+#define G3SUIT_ANDERSENFLEET 3 /* p0..p4, p5 = the prey's largest midlen, no avoid_zero (R/suitability.R:32-58) */
+#define G3SUIT_GAMMA       4   /* alpha, beta, gamma (R/suitability.R:60-67) */
+#define G3SUIT_EXPONENTIAL 5   /* alpha, beta, gamma, delta; uses predator length (R/suitability.R:69-75) */
+#define G3SUIT_STRAIGHTLINE 6  /* alpha, beta (R/suitability.R:77-79) */
+#define G3SUIT_RICHARDS    7   /* p0..p3 as exponential, ^(1/p4) (R/suitability.R:90-94) */
 
 /* ---- collect vector ("xbuf") record ------------------------------------- */
 #define G3X_KIND           0   /* 0 = catch (predprey cons), 1 = abundance */

@@ -266,6 +266,24 @@ template <class T, class F> T suitability(int kind, const int32_t* ss, F& slot, 
         T hi = 1.0 / (1.0 + xexp(1000.0 * (x - p1)));
         return p0 + avoid_zero(p2) * xexp(-(d * d) / avoid_zero(p3)) * lo + avoid_zero(p2) * xexp(-(d * d) / avoid_zero(p4)) * hi;
     }
+    if (kind == G3SUIT_ANDERSENFLEET) {         // pl = the prey's largest midlen (p5 = stock__maxmidlen); R/suitability.R:32-58
+        T p0 = slot(ss[0]), p1 = slot(ss[1]), p2 = slot(ss[2]), p3 = slot(ss[3]), p4 = slot(ss[4]);
+        T x = xlog(T(pl / ml));
+        T d = x - p1;
+        T lo = 1.0 / (1.0 + xexp(1000.0 * (p1 - x)));
+        T hi = 1.0 / (1.0 + xexp(1000.0 * (x - p1)));
+        return p0 + p2 * xexp(-(d * d) / p3) * lo + p2 * xexp(-(d * d) / p4) * hi;
+    }
+    if (kind == G3SUIT_GAMMA) {                 // R/suitability.R:60-67
+        T a = slot(ss[0]), b = slot(ss[1]), g = slot(ss[2]);
+        return xpow(T(ml) / ((a - 1.0) * b * g), a - 1.0) * xexp(a - 1.0 - T(ml) / (b * g));
+    }
+    if (kind == G3SUIT_EXPONENTIAL || kind == G3SUIT_RICHARDS) {       // R/suitability.R:69-75,90-94
+        T a = slot(ss[0]), b = slot(ss[1]), g = slot(ss[2]), dl = slot(ss[3]);
+        T e = dl / (1.0 + xexp(-a - b * ml - g * pl));
+        return kind == G3SUIT_RICHARDS ? xpow(e, 1.0 / slot(ss[4])) : e;
+    }
+    if (kind == G3SUIT_STRAIGHTLINE) return slot(ss[0]) + slot(ss[1]) * ml;        // R/suitability.R:77-79
     ok = false;
     return T(0.0);
 }
@@ -416,7 +434,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                             T colsum(0.0);
                             for (int l = 0; l < L; l++) {
                                 int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
-                                colsum = colsum + suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], pmid[pl], ok) * energy * num[c] * wgt[c];
+                                colsum = colsum + suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSENFLEET ? midlen[L - 1] : pmid[pl], ok) * energy * num[c] * wgt[c];
                             }
                             ptotsuit[Q[G3PP_PRED]][pr * PL + pl] = ptotsuit[Q[G3PP_PRED]][pr * PL + pl] + colsum;
                         }
@@ -425,8 +443,9 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                 continue;
             }
             std::vector<T> suitab(L);
-            for (int l = 0; l < L; l++) suitab[l] = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], 0.0, ok);
-            if (!ok || Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSEN) return T(NaN);
+            for (int l = 0; l < L; l++) suitab[l] = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], midlen[L - 1], ok);
+            // (suitabilities that read predator_length need a predator with lengths)
+            if (!ok || Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSEN || Q[G3PP_SUIT_KIND] == G3SUIT_EXPONENTIAL || Q[G3PP_SUIT_KIND] == G3SUIT_RICHARDS) return T(NaN);
             std::fill(suit[q].begin(), suit[q].end(), T(0.0));
             for (int r = 0; r < St[G3S_NAREA]; r++) {
                 int area = S.I[St[G3S_AREA_OFF] + r], pr = -1;
@@ -468,7 +487,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                             T predn = num[Sp[G3S_CELL_OFF] + (pr * PA + pa) * PL + pl];
                             for (int a = 0; a < St[G3S_NAGE]; a++) for (int l = 0; l < L; l++) {
                                 int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
-                                T su = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], pmid[pl], ok) * energy * num[c] * wgt[c];
+                                T su = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSENFLEET ? midlen[L - 1] : pmid[pl], ok) * energy * num[c] * wgt[c];
                                 T cn = (predn * maxcons * feeding * su) / (energy * ts);
                                 cons[q][c] = cons[q][c] + cn;
                                 totalpredate[c] = totalpredate[c] + cn;
@@ -856,7 +875,8 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             bool ok = true;
             for (int pl = 0; pl < PL; pl++) for (int l = 0; l < L; l++)
                 rep->suit_report[q][pl * L + l] = val(suitability<T>(Q[G3PP_SUIT_KIND], S.I + Q[G3PP_SUIT_OFF], slot,
-                    (S.R + St[G3S_MIDLEN_ROFF])[l], sp ? (S.R + Sp[G3S_MIDLEN_ROFF])[pl] : 0.0, ok));
+                    (S.R + St[G3S_MIDLEN_ROFF])[l],
+                    sp && Q[G3PP_SUIT_KIND] != G3SUIT_ANDERSENFLEET ? (S.R + Sp[G3S_MIDLEN_ROFF])[pl] : (S.R + St[G3S_MIDLEN_ROFF])[L - 1], ok));
         }
     }
     return nll;
@@ -991,6 +1011,13 @@ double g3oracle_grow_lengthvbsimple(double linf, double kappa, double midlen, do
     return grow_lengthvbsimple<double>(linf, kappa, midlen, dt);
 }
 void g3oracle_set_bbinom_product(int32_t on) { g_bbinom_product = on; }
+double g3oracle_suitability(int32_t kind, const double* par5, double midlen, double pred_len) {
+    int32_t ss[5] = {0, 1, 2, 3, 4};
+    auto slot = [&](int i) { return par5[i]; };
+    bool ok = true;
+    double v = suitability<double>(kind, ss, slot, midlen, pred_len, ok);
+    return ok ? v : std::numeric_limits<double>::quiet_NaN();
+}
 double g3oracle_suit_andersen(double p0, double p1, double p2, double p3, double p4, double pred_len, double midlen) {
     double par[5] = {p0, p1, p2, p3, p4};
     int32_t ss[5] = {0, 1, 2, 3, 4};

@@ -44,6 +44,8 @@ def load(path=None):
         f.restype = C.c_double
     lib.g3oracle_suit_andersen.argtypes = [C.c_double] * 7
     lib.g3oracle_suit_andersen.restype = C.c_double
+    lib.g3oracle_suitability.argtypes = [C.c_int32, C.POINTER(C.c_double), C.c_double, C.c_double]
+    lib.g3oracle_suitability.restype = C.c_double
     lib.g3oracle_migrate_normalize.argtypes = [dp, C.c_int32, C.c_int32, C.c_double]
     lib.g3oracle_growth_bbinom.argtypes = [dp, C.c_int32, C.c_int32, C.c_double, dp]
     lib.g3oracle_grow_matrix_len.argtypes = [dp, C.c_int32, C.c_int32, dp]

@@ -283,9 +283,11 @@ def test_against_reference_generated_code(setups, name, kernel):
     assert np.median(_rel(nll, g["nll"])) < 1e-12
 
 
-def test_andersen_predator_model(oracle_lib):
-    """g3_suitability_andersen (predator-length dependent), one-step-only migration: thread kernel vs oracle."""
-    model, p = CONFIGS["MINI_ANDERSEN"]()
+@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_SUITS"])
+def test_andersen_predator_model(oracle_lib, name):
+    """g3_suitability_andersen (predator-length dependent), one-step-only migration: thread kernel vs oracle.
+    MINI_SUITS: richards for the predator, gamma / andersenfleet / straightline fleets, reports included."""
+    model, p = CONFIGS[name]()
     fn = g3_cuda_adfun(model, p, device=0)
     orc = Oracle(*model.pack(p))
     P = np.vstack([fn.par[None, :], parameter_batch(p, 63, seed=12)])
@@ -307,6 +309,10 @@ def test_andersen_predator_model(oracle_lib):
     gtol = GRAD_RTOL + US_WEIGHT * us_tol[:3] / np.abs(o_nll[:3])
     err = np.where(ok, np.abs(grad - og) / scale, 0.0)
     assert (err.max(axis=1) < gtol).all()
+    rg, ro = fn.report(P[1]), unpack_report(model, orc.report(full[1]))
+    for k in ro:
+        if k.startswith("suit_") or k.startswith("detail_"):
+            np.testing.assert_allclose(rg[k], ro[k], rtol=1e-9, atol=1e-12 * max(np.abs(ro[k]).max(), 1e-300), err_msg=k)
 
 
 def test_profile_sweep_c5(setups):

@@ -175,3 +175,38 @@ def test_migrate_normalize(lib, vec, src, row_total, expected):
     v = np.array(vec, dtype=float)
     lib.g3oracle_migrate_normalize(_dp(v), 3, src, row_total)
     np.testing.assert_allclose(v, expected, rtol=1e-12, atol=1e-15)
+
+
+def _suit(lib, kind, par, ml, pl=0.0):
+    p = np.zeros(5)
+    p[:len(par)] = par
+    return lib.g3oracle_suitability(kind, _dp(p), float(ml), float(pl))
+
+
+@pytest.mark.parametrize("p3_exp,p4_exp", [(0.1, 0.1), (-np.inf, 0.1), (0.1, 0.999)])
+def test_suitability_andersenfleet(lib, p3_exp, p4_exp):
+    """tests/test-suitability.R:62-108: lg = seq(100, 500, 100), defaults p0 = 0, p1 = log(2), p2 = 1,
+    p3 = exp(p3_exp), p4 = exp(p4_exp), p5 = largest midlen; against the test's non-differentiable form, 1e-6."""
+    from gadget3_b200.spec import K
+    lg = np.arange(100.0, 501.0, 100.0)
+    midlen = lg + 50.0
+    p0, p1, p2, p3, p4, p5 = 0.0, math.log(2.0), 1.0, math.exp(p3_exp), math.exp(p4_exp), midlen.max()
+    x = np.log(p5 / midlen)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        want = p0 + p2 * np.where(x <= p1, np.exp(-(x - p1) ** 2 / p4), np.exp(-(x - p1) ** 2 / p3))
+    got = [_suit(lib, K["G3SUIT_ANDERSENFLEET"], [p0, p1, p2, p3, p4], m, p5) for m in midlen]
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-12)
+
+
+def test_suitability_closed_forms(lib):
+    """R/suitability.R:60-94: gamma, exponential, straightline, richards against the formulas as documented."""
+    from gadget3_b200.spec import K
+    for ml in (12.5, 40.0, 87.5):
+        a, b, g = 3.2, 4.0, 2.5
+        assert _suit(lib, K["G3SUIT_GAMMA"], [a, b, g], ml) == pytest.approx(
+            (ml / ((a - 1) * b * g)) ** (a - 1) * math.exp(a - 1 - ml / (b * g)), rel=1e-13)
+        a, b, g, d, pl = -3.0, 0.08, 0.01, 0.9, 55.0
+        e = d / (1 + math.exp(-a - b * ml - g * pl))
+        assert _suit(lib, K["G3SUIT_EXPONENTIAL"], [a, b, g, d], ml, pl) == pytest.approx(e, rel=1e-14)
+        assert _suit(lib, K["G3SUIT_RICHARDS"], [a, b, g, d, 1.7], ml, pl) == pytest.approx(e ** (1 / 1.7), rel=1e-13)
+        assert _suit(lib, K["G3SUIT_STRAIGHTLINE"], [0.1, 0.004], ml) == pytest.approx(0.1 + 0.004 * ml, rel=1e-15)
