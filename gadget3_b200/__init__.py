@@ -15,7 +15,8 @@ from .actions import (g3_action_order, g3_suitability_andersen, g3_suitability_a
                       g3a_initialconditions_normalcv, g3a_initialconditions_normalparam,
                       g3a_mature_constant, g3a_mature_continuous, g3a_migrate, g3a_naturalmortality,
                       g3a_naturalmortality_exp, g3a_predate, g3a_predate_catchability_predator,
-                      g3a_predate_catchability_totalfleet, g3a_predate_fleet,
+                      g3a_predate_catchability_effortfleet, g3a_predate_catchability_linearfleet,
+                      g3a_predate_catchability_numberfleet, g3a_predate_catchability_totalfleet, g3a_predate_fleet,
                       g3a_predate_maxconsumption, g3a_renewal_initabund, g3a_renewal_normalcv,
                       g3a_renewal_normalparam, g3a_renewal_vonb, g3a_renewal_vonb_recl,
                       g3a_renewal_vonb_t0, g3a_report_detail, g3a_time)

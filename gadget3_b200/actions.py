@@ -418,6 +418,28 @@ def g3a_predate_catchability_totalfleet(E):
     return _Catchability("totalfleet", E)
 
 
+def _fleet_E(E, what):
+    if not isinstance(E, TimeAreaData):
+        raise G3Unsupported(f"{what}: E must be g3_timeareadata()")
+    return E
+
+
+def g3a_predate_catchability_numberfleet(E):
+    """R/action_predate.R:7-11: landings in individuals."""
+    return _Catchability("numberfleet", _fleet_E(E, "g3a_predate_catchability_numberfleet"))
+
+
+def g3a_predate_catchability_linearfleet(E):
+    """R/action_predate.R:13-18: E is a harvest rate per year, scaled by cur_step_size."""
+    return _Catchability("linearfleet", _fleet_E(E, "g3a_predate_catchability_linearfleet"))
+
+
+def g3a_predate_catchability_effortfleet(catchability_fs, E):
+    """R/action_predate.R:117-126: cons = catchability_fs[prey] * E * cur_step_size * suit.
+    ``catchability_fs``: one formula, or a dict prey stock name -> formula."""
+    return _Catchability("effortfleet", _fleet_E(E, "g3a_predate_catchability_effortfleet"), catchability_fs=catchability_fs)
+
+
 def g3a_predate_catchability_predator(prey_preferences=1, energycontent=None, half_feeding_f=None,
                                       max_consumption=None, temperature=0, by_predator=True, by_stock=True):
     """R/action_predate.R:207-238."""

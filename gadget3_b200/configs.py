@@ -488,6 +488,65 @@ def build_mini_andersen(seed=123, suits=False):
     return model, p
 
 
+def build_mini_fleets(seed=123):
+    """One stock on two areas fished by a numberfleet, a linearfleet and an effortfleet
+    (R/action_predate.R:7-18,117-126) -- parity-test model for the catchabilities bench configs do not use."""
+    from . import (g3a_predate_catchability_effortfleet, g3a_predate_catchability_linearfleet,
+                   g3a_predate_catchability_numberfleet)
+    areas = g3_areas(["a", "b"])
+    fish = g3s_livesonareas(g3s_age(g3_stock("fish", range(5, 50, 5)), 1, 3), areas)
+    rng = np.random.default_rng(seed)
+    yrs = [2000, 2001, 2002, 2003]
+
+    def table(name, lo, hi, steps):
+        n = len(yrs) * len(steps) * 2
+        d = dict(year=[y for y in yrs for _ in range(2 * len(steps))], step=[st for st in steps for _ in range(2)] * len(yrs),
+                 area=["a", "b"] * (len(yrs) * len(steps)), amount=list(rng.uniform(lo, hi, n)))
+        return g3_timeareadata(name, d, "amount", areas=areas)
+
+    fleets = dict(f_num=g3a_predate_catchability_numberfleet(table("n_f_num", 50, 200, [2])),
+                  f_lin=g3a_predate_catchability_linearfleet(table("r_f_lin", 0.1, 0.3, [1, 2, 3, 4])),
+                  f_eff=g3a_predate_catchability_effortfleet(
+                      g3_parameterized("catchability", by_stock=True, by_predator=True, value=0.02),
+                      table("e_f_eff", 5, 10, [3, 4])))
+    actions = [
+        g3a_time(2000, 2003, [3, 3, 3, 3]),
+        g3a_initialconditions_normalcv(fish), g3a_naturalmortality(fish),
+        g3a_growmature(fish, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3)),
+        g3a_renewal_normalcv(fish), g3a_age(fish),
+        g3l_understocking([fish]),
+    ]
+    for fname, cat in fleets.items():
+        fl = g3s_livesonareas(g3_fleet(fname), areas)
+        actions.append(g3a_predate_fleet(fl, [fish], suitabilities=g3_suitability_exponentiall50(), catchability_f=cat))
+        ld = dict(year=[y for y in yrs for _ in range(3)], step=[2 if fname == "f_num" else 3] * 12,
+                  length=["[5,20)", "[20,35)", "[35,Inf)"] * 4, number=list(rng.uniform(10, 100, 12)))
+        actions.append(g3l_catchdistribution("ldist_" + fname, ld, fleets=[fl], stocks=[fish],
+                                             function_f=g3l_distribution_sumofsquares(), area_group=None))
+    actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "*.Linf", 60, spread=0.2)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.05, upper=1)
+    p = g3_init_val(p, "*.t0", -0.5, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.15, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, lower=0.01, upper=1)
+    p = g3_init_val(p, "init.F", 0.3, lower=0.1, upper=1)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.bbin", 10, lower=1, upper=100)
+    p = g3_init_val(p, "*.rec.#", 5, lower=0.1, upper=20)
+    p = g3_init_val(p, "*.rec.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.rec.proj", 1)
+    p = g3_init_val(p, "*.*.alpha", 0.2, lower=0.05, upper=0.5)
+    p = g3_init_val(p, "*.*.l50", 25, lower=15, upper=35)
+    p = g3_init_val(p, "*.*.catchability", 0.02, lower=0.005, upper=0.05)
+    return model, p
+
+
 LING_IMM_STDDEV = [8.25, 10.5644599516659, 12.4081745588022, 11.5741565728647, 11.0523508874244,
                    11.3447991170274, 11.7721342759715, 13.6152275606449]
 LING_MAT_STDDEV = [12.4081745588022, 11.5741565728647, 11.0523508874244, 11.3447991170274, 11.7721342759715,
@@ -598,5 +657,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True),
+CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
            "LING": build_ling}

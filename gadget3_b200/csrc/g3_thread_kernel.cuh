@@ -421,6 +421,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                         const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
                         const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
                         const bool spred = P[G3P_KIND] == G3PRED_STOCK;
+                        const bool by_number = P[G3P_KIND] == G3PRED_NUMBERFLEET;       // suit = S * num (R/action_predate.R:7-11)
+                        if (P[G3P_KIND] == G3PRED_LINEARFLEET || P[G3P_KIND] == G3PRED_EFFORTFLEET) continue;     // no total needed
                         const int PL = spred ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1;
                         const T energy = spred ? SLOT(Q[G3PP_ENERGY]) : T(1.0);
                         for (int col = 0; col < ncol; col++) {
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                 T cs(0.0);
                                 for (int l = 0; l < L; l++) {
                                     const int cell = c0 + col * L + l;
-                                    cs = cs + W(A.t_suitq[q] + pl * L + l) * (W(A.t_num + cell) * W(A.t_wgt + cell));
+                                    cs = cs + W(A.t_suitq[q] + pl * L + l) * (by_number ? W(A.t_num + cell) : W(A.t_num + cell) * W(A.t_wgt + cell));
                                 }
                                 if (spred) W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) = W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) + cs * energy;
                                 else EOT(ts) = EOT(ts) + cs;
@@ -441,7 +443,12 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 // landings over total suitable biomass: cons = E * (suit / totalsuit)
 #pragma unroll
                 for (int k = 0; k < MAXTS; k++)
-                    if (k < A.NTS) EOT(k) = R[A.w_ts_eoff[k] + (size_t)t * A.w_ts_estr[k]] / EOT(k);
+                    if (k < A.NTS) {
+                        const double E = R[A.w_ts_eoff[k] + (size_t)t * A.w_ts_estr[k]];
+                        if (A.w_ts_kind[k] == G3PRED_LINEARFLEET || A.w_ts_kind[k] == G3PRED_EFFORTFLEET)
+                            EOT(k) = T(E * (A.w_dt_len[idt] / 12.0));       // harvest rate x step length (R/action_predate.R:13-18,117-126)
+                        else EOT(k) = E / EOT(k);
+                    }
                 // stock predators: predN * max_consumption * feeding_level / total_predsuit per (area, predator length)
                 // (R/action_predate.R:207-238; energycontent cancels between suit and cons)
                 for (int pi = 0; pi < I[G3H_NPRED]; pi++) {
@@ -516,7 +523,10 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             eotk[k] = T(0.0); tsk[k] = -1;
                             if (k < nq) {
                                 tsk[k] = A.pp_tsid[A.stock_pp[A.stock_pp_off[s] + k] * A.maxnarea + ridx];
-                                if (tsk[k] >= 0 && kpl[k] == 0) eotk[k] = EOT(tsk[k]);
+                                if (tsk[k] >= 0 && kpl[k] == 0) {
+                                    eotk[k] = EOT(tsk[k]);
+                                    if (A.w_ts_kind[tsk[k]] == G3PRED_EFFORTFLEET) eotk[k] = eotk[k] * SLOT(I[I[G3H_PP_OFF] + kq[k] * G3PP_LEN + G3PP_ENERGY]);
+                                }
                             }
                         }
                         unsigned lN = 0;
@@ -562,7 +572,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                         T cf;
                                         if (kpl[k] == 0) {
                                             cf = ws[ksuit[k] + lN] * eotk[k];
-                                            A.report[base + ci] = val(ws[ksuit[k] + lN] * num * *pw_);
+                                            A.report[base + ci] = val(A.w_ts_kind[tsk[k]] == G3PRED_NUMBERFLEET ? ws[ksuit[k] + lN] * num : ws[ksuit[k] + lN] * num * *pw_);
                                         } else {
                                             cf = T(0.0);
                                             for (int pl = 0; pl < kpl[k]; pl++)
@@ -583,12 +593,14 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                     for (int k = 0; k < nq; k++) {
                         const int q = A.stock_pp[A.stock_pp_off[s] + k];
                         const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
-                        if (I[I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN + G3P_KIND] == G3PRED_STOCK) continue;
+                        const int pk = I[I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN + G3P_KIND];
+                        if (pk == G3PRED_STOCK) continue;
                         for (int col = 0; col < ncol; col++) {
                             if (A.pp_tsid[q * A.maxnarea + col / nage] < 0) continue;
                             for (int l = 0; l < L; l++) {
                                 const int cell = c0 + col * L + l;
-                                A.report[A.rep_pp[q] + L + ((size_t)t * ncol + col) * L + l] = val(W(A.t_suitq[q] + l) * W(A.t_num + cell) * W(A.t_wgt + cell));
+                                const T sn = W(A.t_suitq[q] + l) * W(A.t_num + cell);
+                                A.report[A.rep_pp[q] + L + ((size_t)t * ncol + col) * L + l] = val(pk == G3PRED_NUMBERFLEET ? sn : sn * W(A.t_wgt + cell));
                             }
                         }
                     }

@@ -574,7 +574,9 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     for (int p = 0; p < I[G3H_NPRED]; p++) {
         const int32_t* P = I + I[G3H_PRED_OFF] + p * G3P_LEN;
         if (P[G3P_KIND] == G3PRED_STOCK) { m->only_thread = true; pred_ts_base[p] = -1; continue; }     // stock predator: thread kernel only
-        if (P[G3P_KIND] != G3PRED_TOTALFLEET) return bail(fail(G3CUDA_EUNSUPP, "predator kind %d is not supported yet", P[G3P_KIND]));
+        if (P[G3P_KIND] == G3PRED_NUMBERFLEET || P[G3P_KIND] == G3PRED_LINEARFLEET || P[G3P_KIND] == G3PRED_EFFORTFLEET)
+            m->only_thread = true;      // the CTA / warp kernels know the totalfleet form only
+        else if (P[G3P_KIND] != G3PRED_TOTALFLEET) return bail(fail(G3CUDA_EUNSUPP, "predator kind %d is not supported", P[G3P_KIND]));
         pred_ts_base[p] = nts; nts += P[G3P_NAREA];
     }
     if (nts > MAXTS) return bail(fail(G3CUDA_EUNSUPP, "more than %d (predator, area) pairs", MAXTS));
@@ -658,6 +660,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
             for (int k = 0; k < P[G3P_NAREA]; k++) {
                 A.w_ts_eoff[pred_ts_base[p] + k] = P[G3P_E_ROFF] + k;
                 A.w_ts_estr[pred_ts_base[p] + k] = P[G3P_NAREA];
+                A.w_ts_kind[pred_ts_base[p] + k] = P[G3P_KIND];
                 for (int t = 0; t < A.NT; t++) if (R[P[G3P_E_ROFF] + (size_t)t * P[G3P_NAREA] + k] != 0.0) pact[t] = 1;
             }
         }

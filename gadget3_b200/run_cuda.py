@@ -239,10 +239,10 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         if ps.areas is None:
             raise G3Unsupported(f"predator {pname} must live on areas")
         cat = a.catchability_f
-        if cat.kind == "totalfleet":
+        if cat.kind in ("totalfleet", "numberfleet", "linearfleet", "effortfleet"):
             if ps.lengthgroups is not None:
-                raise G3Unsupported("totalfleet catchability on a stock predator")
-            pr[K["G3P_KIND"]] = K["G3PRED_TOTALFLEET"]
+                raise G3Unsupported(f"{cat.kind} catchability on a stock predator")
+            pr[K["G3P_KIND"]] = K["G3PRED_" + cat.kind.upper()]
             E = []
             for t in range(NT):
                 y, st = tm.start_year + t // S, t % S + 1
@@ -282,7 +282,10 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             q[K["G3PP_ENERGY"]] = q[K["G3PP_PREF"]] = -1
             if cat.kind == "predator":
                 q[K["G3PP_ENERGY"]] = low.slot(cat.kw["energycontent"], c)
-            elif su.kind in ("andersen", "exponential", "richards"):
+            elif cat.kind == "effortfleet":
+                cf = cat.kw["catchability_fs"]
+                q[K["G3PP_ENERGY"]] = low.slot(wrap(cf[prey.name] if isinstance(cf, dict) else cf), c)
+            if cat.kind != "predator" and su.kind in ("andersen", "exponential", "richards"):
                 raise G3Unsupported(f"g3_suitability_{su.kind} needs a stock predator (predator_length)")
             pp_index[(pname, prey.name)] = len(pp_recs)
             pp_recs.append(q)

@@ -121,15 +121,17 @@
 #define G3P_LEN            8
 
 #define G3PRED_TOTALFLEET  0   /* g3a_predate_catchability_totalfleet (R/action_predate.R:1) */
-#define G3PRED_NUMBERFLEET 1
+#define G3PRED_NUMBERFLEET 1   /* suit = S * num; cons = E * (suit / total) * wgt (R/action_predate.R:7-11) */
 #define G3PRED_STOCK       2   /* g3a_predate_catchability_predator (R/action_predate.R:207) */
+#define G3PRED_LINEARFLEET 3   /* cons = suit * E * cur_step_size (R/action_predate.R:13-18) */
+#define G3PRED_EFFORTFLEET 4   /* cons = catchability_fs[prey] * E * cur_step_size * suit (R/action_predate.R:117-126) */
 
 /* ---- predator-prey pair record ------------------------------------------ */
 #define G3PP_PRED          0
 #define G3PP_PREY          1   /* stock index */
 #define G3PP_SUIT_KIND     2   /* G3SUIT_* */
 #define G3PP_SUIT_OFF      3   /* ints[6]: slots */
-#define G3PP_ENERGY        4   /* stock predators: slot energycontent, else -1 */
+#define G3PP_ENERGY        4   /* stock predators: slot energycontent; effort fleets: slot catchability_fs of this prey; else -1 */
 #define G3PP_PREF          5   /* stock predators: slot prey_preference, else -1 */
 #define G3PP_LEN           6
 

@@ -455,7 +455,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                     T colsum(0.0);
                     for (int l = 0; l < L; l++) {
                         int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
-                        suit[q][c] = suitab[l] * num[c] * wgt[c];
+                        suit[q][c] = P[G3P_KIND] == G3PRED_NUMBERFLEET ? suitab[l] * num[c] : suitab[l] * num[c] * wgt[c];
                         colsum = colsum + suit[q][c];
                     }
                     totalsuit[Q[G3PP_PRED]][pr] = totalsuit[Q[G3PP_PRED]][pr] + colsum;
@@ -504,7 +504,11 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                 double E = S.R[P[G3P_E_ROFF] + (size_t)cur_time * P[G3P_NAREA] + pr];
                 for (int a = 0; a < St[G3S_NAGE]; a++) for (int l = 0; l < L; l++) {
                     int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
-                    cons[q][c] = E * (suit[q][c] / totalsuit[Q[G3PP_PRED]][pr]);
+                    // g3a_predate_catchability_project / _effortfleet (R/action_predate.R:1-126)
+                    if (P[G3P_KIND] == G3PRED_TOTALFLEET) cons[q][c] = E * (suit[q][c] / totalsuit[Q[G3PP_PRED]][pr]);
+                    else if (P[G3P_KIND] == G3PRED_NUMBERFLEET) cons[q][c] = E * (suit[q][c] / totalsuit[Q[G3PP_PRED]][pr]) * wgt[c];
+                    else if (P[G3P_KIND] == G3PRED_LINEARFLEET) cons[q][c] = suit[q][c] * E * cur_step_size;
+                    else cons[q][c] = slot(Q[G3PP_ENERGY]) * E * cur_step_size * suit[q][c];
                     totalpredate[c] = totalpredate[c] + cons[q][c];
                 }
             }

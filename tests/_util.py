@@ -17,11 +17,13 @@ def us_tolerance(model, params, comp_us):
     for pr in range(ints[K["G3H_NPRED"]]):
         rec = ints[K["G3H_PRED_OFF"]] + pr * K["G3P_LEN"]
         n = ints[K["G3H_NT"]] * ints[rec + K["G3P_NAREA"]]
-        if ints[rec + K["G3P_E_ROFF"]] >= 0 and ints[rec + K["G3P_KIND"]] != K["G3PRED_STOCK"]:
+        if ints[rec + K["G3P_E_ROFF"]] >= 0 and ints[rec + K["G3P_KIND"]] == K["G3PRED_TOTALFLEET"]:
             emax = max(emax, np.abs(reals[ints[rec + K["G3P_E_ROFF"]]:ints[rec + K["G3P_E_ROFF"]] + n]).max())
-    # a stock predator's consumption is not a data table: bound it by the prey biomass it can take
-    # (0.95 x biomass, R/action_predate.R:383), from the oracle's own state history at the template values
-    if any(ints[ints[K["G3H_PRED_OFF"]] + pr * K["G3P_LEN"] + K["G3P_KIND"]] == K["G3PRED_STOCK"]
+    # only a totalfleet's table is the consumed biomass itself (a stock predator's consumption is no data
+    # table; numberfleet / linearfleet / effortfleet tables are individuals, rates, effort): bound the others by
+    # the prey biomass they can take (0.95 x biomass, R/action_predate.R:383), from the oracle's own state
+    # history at the template values
+    if any(ints[ints[K["G3H_PRED_OFF"]] + pr * K["G3P_LEN"] + K["G3P_KIND"]] != K["G3PRED_TOTALFLEET"]
            for pr in range(ints[K["G3H_NPRED"]])):
         from gadget3_b200.run_cuda import unpack_report
         from oracle.oracle_lib import Oracle

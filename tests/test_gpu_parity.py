@@ -283,10 +283,11 @@ def test_against_reference_generated_code(setups, name, kernel):
     assert np.median(_rel(nll, g["nll"])) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_SUITS"])
+@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_SUITS", "MINI_FLEETS"])
 def test_andersen_predator_model(oracle_lib, name):
     """g3_suitability_andersen (predator-length dependent), one-step-only migration: thread kernel vs oracle.
-    MINI_SUITS: richards for the predator, gamma / andersenfleet / straightline fleets, reports included."""
+    MINI_SUITS: richards for the predator, gamma / andersenfleet / straightline fleets, reports included.
+    MINI_FLEETS: numberfleet, linearfleet and effortfleet catchabilities."""
     model, p = CONFIGS[name]()
     fn = g3_cuda_adfun(model, p, device=0)
     orc = Oracle(*model.pack(p))
