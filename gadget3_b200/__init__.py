@@ -21,7 +21,7 @@ from .actions import (g3_action_order, g3_suitability_andersen, g3_suitability_a
                       g3a_renewal_normalparam, g3a_renewal_vonb, g3a_renewal_vonb_recl,
                       g3a_renewal_vonb_t0, g3a_report_detail, g3a_time)
 from .likelihood import (g3l_abundancedistribution, g3l_bounds_penalty, g3l_catchdistribution,
-                         g3l_distribution, g3l_distribution_multinomial, g3l_distribution_sumofsquares,
+                         g3l_distribution, g3l_distribution_multinomial, g3l_distribution_sumofsquaredlogratios, g3l_distribution_sumofsquares,
                          g3l_distribution_surveyindices_linear, g3l_distribution_surveyindices_log,
                          g3l_understocking)
 from .run_cuda import G3CudaADFun, G3CudaModel, g3_cuda_adfun, g3_to_cuda, unpack_report

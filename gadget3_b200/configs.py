@@ -521,6 +521,13 @@ def build_mini_fleets(seed=123):
         actions.append(g3a_predate_fleet(fl, [fish], suitabilities=g3_suitability_exponentiall50(), catchability_f=cat))
         ld = dict(year=[y for y in yrs for _ in range(3)], step=[2 if fname == "f_num" else 3] * 12,
                   length=["[5,20)", "[20,35)", "[35,Inf)"] * 4, number=list(rng.uniform(10, 100, 12)))
+        if fname == "f_lin":        # catch in kilos per year and area: sum of squared log ratios (R/likelihood_distribution.R:127-136)
+            from . import g3l_distribution_sumofsquaredlogratios
+            kg = dict(year=[y for y in yrs for _ in range(2)], step=[3] * 8, area=["a", "b"] * 4,
+                      weight=list(rng.uniform(500, 5000, 8)))
+            actions.append(g3l_catchdistribution("kilos_" + fname, kg, fleets=[fl], stocks=[fish],
+                                                 function_f=g3l_distribution_sumofsquaredlogratios(), area_group=areas))
+            continue
         actions.append(g3l_catchdistribution("ldist_" + fname, ld, fleets=[fl], stocks=[fish],
                                              function_f=g3l_distribution_sumofsquares(), area_group=None))
     actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]

@@ -800,6 +800,14 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                     }
                     cnll = 2.0 * (-likely + A.obsconst[A.obsconst_off[c] + ti]);
                     scored = true;
+                } else if (func == G3F_SUMSQLOGRATIOS) {    // R/likelihood_distribution.R:127-136 (obsprop holds log(obs + eps))
+                    const double eps = R[C[G3C_PARAM_ROFF]];
+                    const double* op = A.obsprop + A.obs_off[c] + (size_t)ti * nd;
+                    for (int e = 0; e < nd; e++) {
+                        const T dlt = op[e] - xlog(W(ms + e) + eps);
+                        cnll = cnll + dlt * dlt;
+                    }
+                    scored = true;
                 } else if (ti == nt - 1) {              // surveyindices: R/likelihood_distribution.R:82-125
                     const double fa = R[C[G3C_PARAM_ROFF]], fb = R[C[G3C_PARAM_ROFF] + 1];
                     const int series = A.t_ms[c];

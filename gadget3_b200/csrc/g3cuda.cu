@@ -749,6 +749,8 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
         const double* obs = R + C[G3C_OBS_ROFF];
         bool si = C[G3C_FUNC] == G3F_SI_LOG || C[G3C_FUNC] == G3F_SI_LINEAR;
         if (si) maxnt = std::max(maxnt, nt);
+        if (C[G3C_FUNC] == G3F_SUMSQLOGRATIOS) m->only_thread = true;       // thread kernel only
+        else if (C[G3C_FUNC] < 0 || C[G3C_FUNC] > G3F_SUMSQLOGRATIOS) return bail(fail(G3CUDA_EUNSUPP, "likelihood function %d is not supported", C[G3C_FUNC]));
         if (C[G3C_MODE] == 1 && nd > 32) return bail(fail(G3CUDA_EUNSUPP, "reduce-mode component with %d destinations", nd));
         for (int t = 0; t < nt; t++) {
             double cst = 0.0;
@@ -761,6 +763,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
                     double v = o;
                     if (C[G3C_FUNC] == G3F_SUMOFSQUARES) v = o / az;                // R/likelihood_distribution.R:12-27
                     else if (C[G3C_FUNC] == G3F_SI_LOG) v = std::log(h_avoid_zero(o));  // R/likelihood_distribution.R:86
+                    else if (C[G3C_FUNC] == G3F_SUMSQLOGRATIOS) v = std::log(o + R[C[G3C_PARAM_ROFF]]);     // R/likelihood_distribution.R:131
                     obsprop.push_back(v);
                 }
                 if (C[G3C_FUNC] == G3F_MULTINOMIAL)

@@ -31,6 +31,11 @@ def g3l_distribution_multinomial(epsilon=10):
     return _DistFn("multinomial", epsilon=float(epsilon))
 
 
+def g3l_distribution_sumofsquaredlogratios(epsilon=10):
+    """R/likelihood_distribution.R:127-136 (catch-in-kilos style sum of squared log ratios)."""
+    return _DistFn("sumofsquaredlogratios", epsilon=float(epsilon))
+
+
 def g3l_distribution_surveyindices_log(alpha=None, beta=1):
     """R/likelihood_distribution.R:82-125."""
     return _DistFn("surveyindices_log", alpha=alpha, beta=beta)

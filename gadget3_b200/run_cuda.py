@@ -411,7 +411,8 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         fn = a.function_f
         q[K["G3C_FUNC"]] = {"sumofsquares": K["G3F_SUMOFSQUARES"], "multinomial": K["G3F_MULTINOMIAL"],
                             "surveyindices_log": K["G3F_SI_LOG"],
-                            "surveyindices_linear": K["G3F_SI_LINEAR"]}[fn.name]
+                            "surveyindices_linear": K["G3F_SI_LINEAR"],
+                            "sumofsquaredlogratios": K["G3F_SUMSQLOGRATIOS"]}[fn.name]
         q[K["G3C_WEIGHT_PAR"]] = wcode[1][1]
         st_sorted = sorted(a.stocks, key=lambda x: x.name)
         if a.fleets:
@@ -490,7 +491,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             al, be = fn.kw["alpha"], fn.kw["beta"]
             q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([float("nan") if al is None else float(al),
                                                     float("nan") if be is None else float(be)])
-        elif fn.name == "multinomial":
+        elif fn.name in ("multinomial", "sumofsquaredlogratios"):
             q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([fn.kw["epsilon"], 0.0])
         else:
             q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([0.0, 0.0])

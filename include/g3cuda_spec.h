@@ -170,7 +170,7 @@
 #define G3C_CMP_OFF       14   /* ints[NT]: done_aggregating_f at step t (R/likelihood_data.R:219) */
 #define G3C_N_TIMES       15
 #define G3C_OBS_ROFF      16   /* reals[N_TIMES*N_DEST] observations, canonical dest layout */
-#define G3C_PARAM_ROFF    17   /* reals[2]: surveyindices fixed alpha, beta (NaN = estimate); multinomial: epsilon */
+#define G3C_PARAM_ROFF    17   /* reals[2]: surveyindices fixed alpha, beta (NaN = estimate); multinomial, sumofsquaredlogratios: epsilon */
 #define G3C_NAREA_SEL_OFF 18   /* reserved */
 #define G3C_LEN           19
 
@@ -178,6 +178,7 @@
 #define G3F_MULTINOMIAL    1   /* R/likelihood_distribution.R:41 */
 #define G3F_SI_LOG         2   /* R/likelihood_distribution.R:82 (fit = 'log') */
 #define G3F_SI_LINEAR      3
+#define G3F_SUMSQLOGRATIOS 4   /* sum((log(obs + eps) - log(model + eps))^2), R/likelihood_distribution.R:127-136; PARAM[0] = eps */
 
 /* ---- slot programs: postfix code, one int per op, operands inline ------- */
 #define G3OP_CONST         1   /* next int: reals[] offset */

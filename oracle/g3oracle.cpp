@@ -769,6 +769,12 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                     for (int b = 0; b < nb; b++) likely = likely + oo[b] * xlog(dif_pmax(mm[b] / atm, 1.0 / (nb * eps), 1e4));
                     cnll = cnll + 2.0 * (-likely + (slg - std::lgamma(1 + so)));
                 }
+            } else if (C[G3C_FUNC] == G3F_SUMSQLOGRATIOS) {  // R/likelihood_distribution.R:127-136
+                double eps = S.R[C[G3C_PARAM_ROFF]];
+                for (int e = 0; e < nd; e++) {
+                    T dlt = std::log(obs[e] + eps) - xlog(m[e] + eps);
+                    cnll = cnll + dlt * dlt;
+                }
             } else if (ti == nt - 1) {                      // surveyindices: R/likelihood_distribution.R:82-125
                 double fa = S.R[C[G3C_PARAM_ROFF]], fb = S.R[C[G3C_PARAM_ROFF] + 1];
                 bool lg = C[G3C_FUNC] == G3F_SI_LOG;

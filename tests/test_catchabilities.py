@@ -55,3 +55,15 @@ def test_rate_fleets_take_a_share_of_the_suitable_biomass(run, fleet, scale):
             np.testing.assert_allclose(cons[:, :, r, t][big], (suit[:, :, r, t] * (c * E * 0.25))[big], rtol=1e-9)
             seen += int(big.sum())
     assert seen > 100
+
+
+def test_sumofsquaredlogratios_from_the_reported_model_array(run, oracle_lib):
+    """g3l_distribution_sumofsquaredlogratios (R/likelihood_distribution.R:127-136): the component total must equal
+    sum((log(obs + 10) - log(model + 10))^2) over the reported model array."""
+    model, p, rep, acts = run
+    name = "cdist_sumofsquaredlogratios_kilos_f_lin"
+    act = [a for a in model.actions if getattr(a, "nll_name", "") == name][0]
+    obs = np.asarray(act.ld.obs).reshape(rep[f"{name}_model__wgt"].shape)
+    want = ((np.log(obs + 10.0) - np.log(rep[f"{name}_model__wgt"] + 10.0)) ** 2).sum()
+    assert rep[f"nll_{name}__wgt"].sum() == pytest.approx(want, rel=1e-12)
+    assert want > 0
