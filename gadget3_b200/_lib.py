@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libg3cuda.so")
+LIB_PATH = os.environ.get("G3CUDA_LIBRARY") or os.path.join(_HERE, "csrc", "libg3cuda.so")
 _LIB = None
 
 
@@ -61,6 +61,9 @@ def load():
     lib.g3cuda_abi_version.restype = C.c_int32
     lib.g3cuda_set_kernel.argtypes = [vp, C.c_int]
     lib.g3cuda_set_kernel.restype = C.c_int
+    lib.g3cuda_math_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64,
+                                      C.POINTER(C.c_double)]
+    lib.g3cuda_math_probe.restype = C.c_int
     lib.g3cuda_fp64_peak_tflops.argtypes = [C.c_int]
     lib.g3cuda_fp64_peak_tflops.restype = C.c_double
     _LIB = lib
@@ -70,7 +73,7 @@ def load():
 EXPORTED = ["g3cuda_model_create", "g3cuda_model_free", "g3cuda_n_par", "g3cuda_n_nll", "g3cuda_n_steps",
             "g3cuda_report_len", "g3cuda_eval_batch", "g3cuda_eval_batch_device", "g3cuda_launch_count",
             "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version",
-            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel"]
+            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe"]
 
 
 def _dp(a):
@@ -152,3 +155,15 @@ class Handle:
         out = np.empty(self.lib.g3cuda_report_len(self.h))
         self._check(self.lib.g3cuda_report(self.h, _dp(par), _dp(out)), "g3cuda_report")
         return out
+
+
+def math_probe(which, x, y=None, device=0):
+    """The kernels' own logspace_add (0) / avoid_zero (1) / dif_pmin(., ., 1e3) (2) on HOST arrays (test hook)."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(x)
+    rc = lib.g3cuda_math_probe(int(device), int(which), _dp(x), _dp(y), x.size, _dp(out))
+    if rc != 0:
+        raise G3CudaError("g3cuda_math_probe: %s (code %d)" % (lib.g3cuda_last_error().decode(), rc))
+    return out

@@ -552,13 +552,13 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                         for (int x = 0; x < MAXX; x++) if ((kx[k] >> x) & 1) fx[x] = fx[x] + cf;
                                     }
                                 }
-                            T cr = tp / avoid_zero(B0);
+                            T cr = xdiv(tp, avoid_zero(B0));
                             cr = dif_pmax_c(cr, 0.95, -1e3);
                             const T tpn = B0 * cr;
                             *pn = num * (1.0 - cr);
                             if (is_us) { o1 = o1 + tp; o2 = o2 + tpn; }
                             if (catch_now) {
-                                const T cc = 1.0 / avoid_zero(tp) * tpn * B0;      // consconv * B0
+                                const T cc = xdiv(T(1.0), avoid_zero(tp)) * tpn * B0;      // consconv * B0
 #pragma unroll
                                 for (int x = 0; x < MAXX; x++)
                                     if (((xact >> x) & 1) && A.w_x_kind[x] == 0) W(A.t_x[x] + c0 + col * L + l) = fx[x] * cc;
@@ -677,9 +677,9 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                     }
                                 }
                             }
-                            num = bn; wgt = bw / avoid_zero(bn);
+                            num = bn; wgt = xdiv(bw, avoid_zero(bn));
                             if (trans_now) {
-                                *ptn = an; *ptw = aw / avoid_zero(an);
+                                *ptn = an; *ptw = xdiv(aw, avoid_zero(an));
                                 // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
                                 num = num + an * W(A.t_remf + A.t_colbase[s] + col);
                             }
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
 #pragma unroll
                             for (int x = 0; x < MAXX; x++)
                                 if ((xact >> x) & 1) {
-                                    if (A.w_x_kind[x] == 0) { if (A.w_x_unit[x] == 0 && nq > 0) W(A.t_x[x] + cell) = W(A.t_x[x] + cell) / avoid_zero(wgt); }
+                                    if (A.w_x_kind[x] == 0) { if (A.w_x_unit[x] == 0 && nq > 0) W(A.t_x[x] + cell) = xdiv(W(A.t_x[x] + cell), avoid_zero(wgt)); }
                                     else W(A.t_x[x] + cell) = A.w_x_unit[x] == 0 ? num : num * wgt;
                                 }
                         }

@@ -448,7 +448,34 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+__global__ void math_probe_kernel(int which, const double* x, const double* y, long long n, double* out) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (which == 0) out[i] = g3::lsa(x[i], y[i]);
+    else if (which == 1) out[i] = g3::avoid_zero(x[i]);
+    else out[i] = g3::lsa(x[i] * -1e3, y[i] * -1e3) / -1e3;
+}
+
 extern "C" {
+
+int g3cuda_math_probe(int device, int which, const double* x, const double* y, int64_t n, double* out) {
+    if (!x || !out || n < 0 || which < 0 || which > 2 || (which != 1 && !y)) return fail(G3CUDA_EINVAL, "bad argument");
+    if (n == 0) return G3CUDA_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)n;
+    if (cudaMalloc(&dx, bytes) != cudaSuccess || cudaMalloc(&dy, bytes) != cudaSuccess || cudaMalloc(&dout, bytes) != cudaSuccess) {
+        cudaFree(dx); cudaFree(dy); cudaFree(dout); cudaGetLastError();
+        return fail(G3CUDA_ENOMEM, "cudaMalloc failed");
+    }
+    cudaMemcpy(dx, x, bytes, cudaMemcpyHostToDevice);
+    if (y) cudaMemcpy(dy, y, bytes, cudaMemcpyHostToDevice); else cudaMemset(dy, 0, bytes);
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256>>>(which, dx, dy, (long long)n, dout);
+    cudaError_t e = cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    if (e != cudaSuccess) return fail(G3CUDA_ECUDA, "math probe failed: %s", cudaGetErrorString(e));
+    return G3CUDA_OK;
+}
 
 double g3cuda_fp64_peak_tflops(int device) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1.0; }

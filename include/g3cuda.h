@@ -121,6 +121,13 @@ int g3cuda_report(g3cuda_model* m, const double* par, double* out);
  * denominator bench.py reports against). Negative on failure. */
 double g3cuda_fp64_peak_tflops(int device);
 
+/* Device-math probe for the parity tests: evaluates, on `device`, the kernels' own implementation of
+ *   which = 0: logspace_add(x[i], y[i])          (R/aab_env.R:16-19)
+ *   which = 1: avoid_zero(x[i])                  (R/aab_env.R:24-31; y ignored)
+ *   which = 2: dif_pmin(x[i], y[i], 1e3)         (R/env_dif.R:37-47)
+ * for n HOST values into out (HOST). Returns 0 or a negative G3CUDA_E* code. */
+int g3cuda_math_probe(int device, int which, const double* x, const double* y, int64_t n, double* out);
+
 /* Last error message of the calling thread. */
 const char* g3cuda_last_error(void);
 
