@@ -39,8 +39,8 @@ WORKLOAD = {"C1": "introduction-single-stock, nll only", "C2": "multiple-substoc
             "C4": "ling-style: 2 stocks x 35 length groups, 3 fleets, constant maturity, 40 years quarterly, nll only",
             "C5": "4-area predator-prey with migration and a stock predator, 20 years quarterly, nll only"}
 # DRAM bytes per evaluation of the evaluation kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture / evaluations in that launch): profiles/r01_thread_kernel_final_C2_b65536.txt
-TRAFFIC_PER_EVAL = {"C2": (133.971749e9 + 91.770329e9) / 65536}
+# `ncu --set full` capture / evaluations in that launch): profiles/r01_thread_kernel_v7_unified_lsa_C2_b65536.txt
+TRAFFIC_PER_EVAL = {"C2": (134.498123e9 + 91.515235e9) / 65536}
 MODEL_OF = {"C1": "C1", "C2": "C2", "C3": "C2", "C4": "C4", "C5": "C5"}
 DEFAULT_BATCH = {"C1": 65536, "C2": 65536, "C3": 8192, "C4": 65536, "C5": 131072}
 
@@ -313,7 +313,7 @@ def main():
                      "hbm": {"achieved": hbm_bytes / (kms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                              "alg_bytes_per_eval": P * 8 + 8},
                      "traffic": (TRAFFIC_PER_EVAL[a.config] * B if a.config in TRAFFIC_PER_EVAL else None),
-                     "traffic_unit": "bytes per launch (workspace streaming; ncu capture in profiles/r01_thread_kernel_final_C2_b65536.txt)"},
+                     "traffic_unit": "bytes per launch (workspace streaming; ncu capture in profiles/r01_thread_kernel_v7_unified_lsa_C2_b65536.txt)"},
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb, orc = cpu_reference(model, params, a.config, batch_fn, tix=opt.astype(np.int32) if want_grad else None)
