@@ -618,19 +618,26 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 const T* pmort = ws + (unsigned)(A.t_mort[s] + idt * ncol) * NTH;
                 const int4* cinc = A.t_colinc + A.t_colbase[s];
                 for (int l = L - 1; l >= 0; l--, pg -= NTH, pgr -= NTH, ppw -= NTH) {
-                    T gt[NW], grt[NW], dwt[NW];
+                    // Narrow bands keep the band and the weight gains of this length in registers for all columns;
+                    // wide ones (maxlengthgroupgrowth > 7) would spill them, so they stream them per column instead.
+                    constexpr bool WINDOW = NW <= 8;
+                    constexpr int NWR = WINDOW ? NW : 1;
+                    T gt[NWR], grt[NWR], dwt[NWR];
+                    const T pw_l = ppw[0];
                     if (l > 0 && grow_n >= 0) {     // next length's band on its way
 #pragma unroll
                         for (int d = 0; d < NW; d++)
                             if (d <= grow_n && d < l) { prefetch_l1(pg - NTH + d * LWS); if (cont_now) prefetch_l1(pgr - NTH + d * LWS); }
                     }
+                    if constexpr (WINDOW) {
 #pragma unroll
-                    for (int d = 0; d < NW; d++) {
-                        gt[d] = T(0.0); grt[d] = T(0.0); dwt[d] = T(0.0);
-                        if (d <= grow_n && d <= l) {
-                            gt[d] = pg[d * LWS];
-                            if (cont_now) grt[d] = pgr[d * LWS];
-                            dwt[d] = wal * (ppw[0] - *(ppw - d * NTH));        // walpha (l^wbeta - (l-d)^wbeta), R/action_grow.R:58-71
+                        for (int d = 0; d < NW; d++) {
+                            gt[d] = T(0.0); grt[d] = T(0.0); dwt[d] = T(0.0);
+                            if (d <= grow_n && d <= l) {
+                                gt[d] = pg[d * LWS];
+                                if (cont_now) grt[d] = pgr[d * LWS];
+                                dwt[d] = wal * (pw_l - *(ppw - d * NTH));        // walpha (l^wbeta - (l-d)^wbeta), R/action_grow.R:58-71
+                            }
                         }
                     }
                     T* pn = ws + (unsigned)(A.t_num + c0 + l) * NTH;
@@ -660,19 +667,25 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             for (int d = 0; d < NW; d++) {
                                 if (d <= grow_n && d <= l) {
                                     const T ns = *(pn - d * NTH) * mortf;
-                                    const T wsrc = dwt[d] + *(pw_ - d * NTH);
+                                    T gd, grd, dwd;
+                                    if constexpr (WINDOW) { gd = gt[d]; grd = grt[d]; dwd = dwt[d]; }
+                                    else {
+                                        gd = pg[d * LWS]; grd = cont_now ? pgr[d * LWS] : T(0.0);
+                                        dwd = wal * (pw_l - *(ppw - d * NTH));
+                                    }
+                                    const T wsrc = dwd + *(pw_ - d * NTH);
                                     if (cont_now) {
                                         const T w = wsrc * ns;
-                                        an = an + grt[d] * ns; aw = aw + grt[d] * w;
-                                        bn = bn + gt[d] * ns; bw = bw + gt[d] * w;
+                                        an = an + grd * ns; aw = aw + grd * w;
+                                        bn = bn + gd * ns; bw = bw + gd * w;
                                     } else if (CONSTMAT && const_now) {
                                         // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
                                         const T ratio = W(A.t_cmat[s] + col * L + l - d);
-                                        const T n1 = (ns * ratio) * gt[d], n2 = (ns * (1.0 - ratio)) * gt[d];
+                                        const T n1 = (ns * ratio) * gd, n2 = (ns * (1.0 - ratio)) * gd;
                                         an = an + n1; aw = aw + wsrc * n1;
                                         bn = bn + n2; bw = bw + wsrc * n2;
                                     } else {
-                                        const T n2 = ns * gt[d];
+                                        const T n2 = ns * gd;
                                         bn = bn + n2; bw = bw + wsrc * n2;
                                     }
                                 }
