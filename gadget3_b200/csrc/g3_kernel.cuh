@@ -64,6 +64,7 @@ struct KArgs {
     int w_o_mort, w_o_tot, w_o_mv;
     int w_mort_off[MAXS], w_o_dw[MAXS], w_o_rw[MAXS], w_tr_off[MAXS], w_mv_off[MAXS], w_inc_steps[MAXS];
     int w_ts_eoff[MAXTS], w_ts_estr[MAXTS]; // landings table of each (predator, area) accumulator
+    int t_cblk;                             // thread kernel, wide bands: columns per growth sweep block
     int w_ts_kind[MAXTS];                   // G3PRED_* of the accumulator's fleet
     int w_x_kind[MAXX], w_x_unit[MAXX]; unsigned w_x_ppmask[MAXX];
     const int32_t* w_inc_tr;                // per cell: compact index of its maturation source in s_tn/s_tw, or -1

@@ -612,11 +612,17 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 // loop: the band P(l - d -> l) and the weight gains are loaded once per l for all columns.
                 const int gsz = (grow_n + 1) * L;
                 const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
+                const T* pmort = ws + (unsigned)(A.t_mort[s] + idt * ncol) * NTH;
+                const int4* cinc = A.t_colinc + A.t_colbase[s];
+                // Wide bands (streamed per column, below) sweep the columns in blocks of t_cblk: the n+1 rows a
+                // column re-reads while l walks down then stay in L1/L2 instead of coming back from HBM
+                // (65,536 threads x 19 columns x 16 rows x 2 x 8 B = 318 MB per length otherwise).
+                const int cper = NW <= 8 ? ncol : A.t_cblk;
+                for (int cb0 = 0; cb0 < ncol; cb0 += cper) {
+                const int cb1 = min(cb0 + cper, ncol);
                 const T* pg = ws + (unsigned)((cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz + (L - 1)) * NTH;     // staying part, [d][l]
                 const T* pgr = ws + (unsigned)(A.t_gr[s] + idt * gsz + (L - 1)) * NTH;                              // maturing part
                 const T* ppw = ws + (unsigned)(A.t_pw[s] + (L - 1)) * NTH;
-                const T* pmort = ws + (unsigned)(A.t_mort[s] + idt * ncol) * NTH;
-                const int4* cinc = A.t_colinc + A.t_colbase[s];
                 for (int l = L - 1; l >= 0; l--, pg -= NTH, pgr -= NTH, ppw -= NTH) {
                     // Narrow bands keep the band and the weight gains of this length in registers for all columns;
                     // wide ones (maxlengthgroupgrowth > 7) would spill them, so they stream them per column instead.
@@ -640,17 +646,17 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             }
                         }
                     }
-                    T* pn = ws + (unsigned)(A.t_num + c0 + l) * NTH;
-                    T* pw_ = ws + (unsigned)(A.t_wgt + c0 + l) * NTH;
-                    T* ptn = ws + (unsigned)(A.t_tn + A.w_tr_off[s] + l) * NTH;
-                    T* ptw = ws + (unsigned)(A.t_tw + A.w_tr_off[s] + l) * NTH;
-                    int aidx = 0, ridx = 0;
+                    T* pn = ws + (unsigned)(A.t_num + c0 + cb0 * L + l) * NTH;
+                    T* pw_ = ws + (unsigned)(A.t_wgt + c0 + cb0 * L + l) * NTH;
+                    T* ptn = ws + (unsigned)(A.t_tn + A.w_tr_off[s] + cb0 * L + l) * NTH;
+                    T* ptw = ws + (unsigned)(A.t_tw + A.w_tr_off[s] + cb0 * L + l) * NTH;
+                    int aidx = cb0 % nage, ridx = cb0 / nage;
                     T* const pn_first = pn; T* const pw_first = pw_;
-                    for (int col = 0; col < ncol; col++, pn += LWS, pw_ += LWS, ptn += LWS, ptw += LWS) {
+                    for (int col = cb0; col < cb1; col++, pn += LWS, pw_ += LWS, ptn += LWS, ptw += LWS) {
                         {   // the next column's (or, at the end of the sweep, the next length's first column's) sources on their way
-                            const T* qn = col + 1 < ncol ? pn + LWS : pn_first - NTH;
-                            const T* qw = col + 1 < ncol ? pw_ + LWS : pw_first - NTH;
-                            if (col + 1 < ncol || l > 0) {
+                            const T* qn = col + 1 < cb1 ? pn + LWS : pn_first - NTH;
+                            const T* qw = col + 1 < cb1 ? pw_ + LWS : pw_first - NTH;
+                            if (col + 1 < cb1 || l > 0) {
                                 if (grow_n >= 0) {
 #pragma unroll
                                     for (int d = 0; d < NW; d++)
@@ -733,6 +739,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                         }
                         if (++aidx == nage) { aidx = 0; ridx++; }
                     }
+                }
                 }
             }
 
