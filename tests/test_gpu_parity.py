@@ -212,6 +212,21 @@ def test_full_size_batch_properties(setups):
     assert (small == nll[1000:1100]).all()
 
 
+def test_ragged_batch_larger_than_one_wave(setups):
+    """More vectors than the thread kernel holds at once (152 x 1024 workspace slots), and not a multiple of the
+    warp size: the launch runs several waves; every row must still equal the same row evaluated in a small batch."""
+    model, p, fn, orc = setups["C1"]
+    B = 200003
+    full = fn.full_par(parameter_batch(p, B, seed=99))
+    nll, comp, _ = fn.handle.eval_batch(full, want_comp=True)
+    assert nll.shape == (B,) and np.isfinite(nll).all()
+    for lo in (0, 77777, 155640, B - 37):
+        small = fn.handle.eval_batch(full[lo:lo + 37], want_comp=True)
+        assert (small[0] == nll[lo:lo + 37]).all() and (small[1] == comp[lo:lo + 37]).all()
+    o, oc, _ = orc.eval_batch(full[B - 64:], want_comp=True, nthreads=8)
+    assert (np.abs(nll[B - 64:] - o) <= NLL_RTOL * np.abs(o) + US_WEIGHT * _us_tolerance(model, p, oc[:, -2])).all()
+
+
 def test_device_pointer_entry_point(setups):
     import torch
     model, p, fn, orc = setups["C2"]
