@@ -108,6 +108,23 @@ def test_unsupported_actions_raise():
         g3.g3_to_cuda([g3.g3a_naturalmortality(st)])                 # no g3a_time
 
 
+def test_predator_length_suitabilities_need_a_stock_predator():
+    """g3_suitability_exponential / richards / andersen read predator_length (R/suitability.R:15-30,69-94): a fleet
+    has none, so the lowering refuses them there, as the reference fails on the undefined variable."""
+    areas = {"a": 1}
+    st = g3.g3s_livesonareas(g3.g3s_age(g3.g3_stock("s", range(10, 51, 10)), 1, 3), areas)
+    fl = g3.g3s_livesonareas(g3.g3_fleet("f"), areas)
+    land = g3.g3_timeareadata("l", dict(year=[2000], step=[1], area=["a"], w=[1.0]), "w", areas=areas)
+    for su in (g3.g3_suitability_richards(1, 1, 1, 1, 1), g3.g3_suitability_exponential(1, 1, 1, 1),
+               g3.g3_suitability_andersen(0, 1, 1, 1, 1)):
+        acts = [g3.g3a_time(2000, 2001, [6, 6]), g3.g3a_naturalmortality(st), g3.g3a_initialconditions_normalcv(st),
+                g3.g3a_predate_fleet(fl, [st], suitabilities=su, catchability_f=g3.g3a_predate_catchability_linearfleet(land))]
+        with pytest.raises(g3.G3Unsupported, match="stock predator"):
+            g3.g3_to_cuda(acts)
+    with pytest.raises(g3.G3Unsupported, match="g3_timeareadata"):
+        g3.g3a_predate_catchability_effortfleet(0.1, 5.0)
+
+
 def test_pack_rejects_reordered_template(cfgs):
     """R/run_tmb.R:1156-1158: 'Parameters not in expected order'."""
     model, p = cfgs["C1"]
