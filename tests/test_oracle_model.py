@@ -126,3 +126,21 @@ def test_threads_do_not_change_results(setups):
     a = orc.eval_batch(full, nthreads=1)[0]
     b = orc.eval_batch(full, nthreads=4)[0]
     assert (a == b).all()
+
+
+def test_bounds_penalty_zero_inside_huge_outside(setups):
+    """tests/test-likelihood_bounds.R:20-41: inside its bounds a parameter adds exactly nothing; one unit outside a
+    60-wide range pushes nll beyond 1e8; a new bound that excludes the current value does the same."""
+    model, p, orc = setups["C1"]
+    full = p.values()[None, :].copy()
+    nll0, comp0, _ = orc.eval_batch(full, want_comp=True)
+    assert comp0[0, -1] == 0.0                                   # "nll: start off inside bounds"
+    i = p.index("fish.K")                                        # bounds 0.04 .. 1.2
+    out = full.copy(); out[0, i] = p.upper[i] + (p.upper[i] - p.lower[i]) / 60.0
+    nll1, comp1, _ = orc.eval_batch(out, want_comp=True)
+    assert nll1[0] - nll0[0] > 1e8 and comp1[0, -1] > 1e8        # "outside initial upper bound"
+    q = p.copy(); q.upper[i] = p.value[i] - 0.01                 # "outside new upper bound"
+    nll2, comp2, _ = Oracle(*model.pack(q)).eval_batch(full, want_comp=True)
+    assert comp2[0, -1] > 1e8 and nll2[0] > 1e8
+    q = p.copy(); q.lower[i] = p.value[i] + 0.01                 # "outside new lower bound"
+    assert Oracle(*model.pack(q)).eval_batch(full, want_comp=True)[1][0, -1] > 1e8
