@@ -877,17 +877,22 @@ int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B, co
     int rc;
     if (d_grad && K > 0) {
         if (!d_tangent_idx) return fail(G3CUDA_EINVAL, "grad requested without tangent_idx");
-        // value + per-component sums from the double kernel, gradients from the dual kernel
+        const long long ntiles = (K + NTAN - 1) / NTAN;
         call.tangent_idx = nullptr; call.K = 0; call.grad = nullptr;
-        rc = launch<double>(m, call, B, st);
-        if (rc) return rc;
         g3::KArgs g = call;
-        g.tangent_idx = d_tangent_idx; g.K = K; g.grad = d_grad; g.comp = nullptr;
-        // the dual kernel also writes nll (tile 0); keep the double kernel's value: write duals' nll into scratch
-        rc = ensure(&m->d_nll, &m->cap_nll, (size_t)B);
-        if (rc) return rc;
-        g.nll = m->d_nll;
-        long long ntiles = (K + NTAN - 1) / NTAN;
+        g.tangent_idx = d_tangent_idx; g.K = K; g.grad = d_grad;
+        // The thread kernel's dual pass carries the value: its first direction tile writes nll and the component
+        // sums, so no separate value launch is needed (it cost 6 % of a C3 step). The CTA kernel's dual pass
+        // does not write the components: there the value pass stays.
+        const bool dual_on_thread = m->thread_ok && (m->force_kernel == 0 || m->force_kernel == 3) &&
+                                    (m->force_kernel == 3 || B * ntiles >= 16384 || !m->cta_ok_dual);
+        if (!dual_on_thread) {
+            rc = launch<double>(m, call, B, st);
+            if (rc) return rc;
+            rc = ensure(&m->d_nll, &m->cap_nll, (size_t)B);     // (its tile 0 writes nll too: into scratch)
+            if (rc) return rc;
+            g.nll = m->d_nll; g.comp = nullptr;
+        }
         rc = launch<DualT>(m, g, B * ntiles, st);
     } else {
         call.tangent_idx = nullptr; call.K = 0; call.grad = nullptr;
