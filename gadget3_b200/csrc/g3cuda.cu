@@ -374,17 +374,23 @@ int launch_variant(g3cuda_model* m, const Layout& lay, int nblocks_hint, cudaStr
     return G3CUDA_OK;
 }
 
+// Below this many evaluations the CTA-per-evaluation kernel wins: one evaluation is one thread's whole life in
+// the thread kernel (C2: 67 ms whatever the batch), but 1.3 ms when a CTA shares it (an optimiser's single fn()
+// call). Measured crossover on B200: ~11 k vectors (C1), ~14 k (C2) -- tools/gpu_latency.py.
+static const long long SMALL_BATCH = 12288;
+
 template <class T>
 int launch(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStream_t st) {
     const bool is_double = std::is_same<T, double>::value;
     if (m->thread_ok && (m->force_kernel == 0 || m->force_kernel == 3) &&
-        (call.report ? true : (is_double || m->force_kernel == 3 || work >= 16384 || !m->cta_ok_dual))) {
+        (call.report ? true : (m->force_kernel == 3 ||
+                               (is_double ? (work >= SMALL_BATCH || !m->cta_ok_double) : (work >= 16384 || !m->cta_ok_dual))))) {
         g3::KArgs a = m->base;
         a.par = call.par; a.B = call.B; a.tangent_idx = call.tangent_idx; a.K = call.K;
         a.nll = call.nll; a.comp = call.comp; a.grad = call.grad; a.report = call.report;
         return launch_thread<T>(m, a, work, st);
     }
-    if (m->warp_ok && !call.report && m->force_kernel != 1 && (is_double || m->force_kernel == 2)) {
+    if (m->warp_ok && !call.report && m->force_kernel == 2) {       // (kept as measured evidence: never chosen automatically)
         Layout lay = make_wlayout(m, sizeof(T));
         lay.a.par = call.par; lay.a.B = call.B; lay.a.tangent_idx = call.tangent_idx; lay.a.K = call.K;
         lay.a.nll = call.nll; lay.a.comp = call.comp; lay.a.grad = call.grad; lay.a.report = nullptr;

@@ -86,8 +86,10 @@ int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B,
 
 /* Kernel selection, for tests and profiling: 0 = automatic (default), 1 = CTA-per-evaluation
  * kernel, 2 = warp-per-evaluation kernel, 3 = thread-per-evaluation kernel (G3CUDA_EUNSUPP if
- * the model does not fit the requested one).
- * Both are CUDA; there is no CPU path to select. */
+ * the model does not fit the requested one). Automatic: batches below 12,288 evaluations go to the
+ * CTA-per-evaluation kernel when the model fits it (latency: ~1 ms for one vector), larger ones to
+ * the thread-per-evaluation kernel (throughput); the two agree to rounding, not to the bit.
+ * All are CUDA; there is no CPU path to select. */
 int g3cuda_set_kernel(g3cuda_model* m, int which);
 
 /* Number of kernels launched by this handle so far (bench.py gpu_launches). */

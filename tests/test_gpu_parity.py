@@ -208,8 +208,16 @@ def test_full_size_batch_properties(setups):
     perm = np.random.default_rng(0).permutation(B)
     nll_p = fn.handle.eval_batch(full[perm])[0]
     assert (nll_p == nll[perm]).all()
-    small = fn.handle.eval_batch(full[1000:1100])[0]
+    fn.handle.set_kernel(3)          # same kernel, smaller batch: identical to the bit
+    try:
+        small = fn.handle.eval_batch(full[1000:1100])[0]
+    finally:
+        fn.handle.set_kernel(0)
     assert (small == nll[1000:1100]).all()
+    # automatic dispatch sends a batch this small to the CTA-per-evaluation kernel (latency): same values to rounding
+    auto = fn.handle.eval_batch(full[1000:1100], want_comp=True)
+    tol = NLL_RTOL * np.abs(small) + _us_weight(model) * _us_tolerance(model, p, auto[1][:, -2])
+    assert (np.abs(auto[0] - small) <= tol).all()
 
 
 def test_ragged_batch_larger_than_one_wave(setups):
@@ -220,9 +228,13 @@ def test_ragged_batch_larger_than_one_wave(setups):
     full = fn.full_par(parameter_batch(p, B, seed=99))
     nll, comp, _ = fn.handle.eval_batch(full, want_comp=True)
     assert nll.shape == (B,) and np.isfinite(nll).all()
-    for lo in (0, 77777, 155640, B - 37):
-        small = fn.handle.eval_batch(full[lo:lo + 37], want_comp=True)
-        assert (small[0] == nll[lo:lo + 37]).all() and (small[1] == comp[lo:lo + 37]).all()
+    fn.handle.set_kernel(3)
+    try:
+        for lo in (0, 77777, 155640, B - 37):
+            small = fn.handle.eval_batch(full[lo:lo + 37], want_comp=True)
+            assert (small[0] == nll[lo:lo + 37]).all() and (small[1] == comp[lo:lo + 37]).all()
+    finally:
+        fn.handle.set_kernel(0)
     o, oc, _ = orc.eval_batch(full[B - 64:], want_comp=True, nthreads=8)
     assert (np.abs(nll[B - 64:] - o) <= NLL_RTOL * np.abs(o) + US_WEIGHT * _us_tolerance(model, p, oc[:, -2])).all()
 
