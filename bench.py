@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--config", default="C2", choices=sorted(ALG_FLOP))
     ap.add_argument("--batch", type=int, default=0, help="parameter vectors per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel", type=int, default=0, help="0 = automatic dispatch, 3 = thread kernel, 4 = tile kernel (profiling)")
+    ap.add_argument("--tile-warps", type=int, default=0, help="warps per tile of the tile kernel (0 = planner's choice)")
     return ap.parse_args()
 
 
@@ -209,6 +211,10 @@ def main():
     from gadget3_b200.run_cuda import g3_cuda_adfun
     fn = g3_cuda_adfun(model, params, device=local)
     h = fn.handle
+    if a.kernel:
+        h.set_kernel(a.kernel)
+    if a.tile_warps:
+        h.set_tile_warps(a.tile_warps)
     B, P = a.batch, h.n_par
 
     # ---- inputs: NB distinct batches so that the parameter stream (NB x B x P x 8 B) exceeds the 126 MB L2

@@ -61,6 +61,10 @@ def load():
     lib.g3cuda_abi_version.restype = C.c_int32
     lib.g3cuda_set_kernel.argtypes = [vp, C.c_int]
     lib.g3cuda_set_kernel.restype = C.c_int
+    lib.g3cuda_set_tile_warps.argtypes = [vp, C.c_int]
+    lib.g3cuda_set_tile_warps.restype = C.c_int
+    lib.g3cuda_tile_info.argtypes = [vp, ip]
+    lib.g3cuda_tile_info.restype = C.c_int32
     lib.g3cuda_math_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64,
                                       C.POINTER(C.c_double)]
     lib.g3cuda_math_probe.restype = C.c_int
@@ -73,7 +77,7 @@ def load():
 EXPORTED = ["g3cuda_model_create", "g3cuda_model_free", "g3cuda_n_par", "g3cuda_n_nll", "g3cuda_n_steps",
             "g3cuda_report_len", "g3cuda_eval_batch", "g3cuda_eval_batch_device", "g3cuda_launch_count",
             "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version",
-            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe"]
+            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe", "g3cuda_set_tile_warps", "g3cuda_tile_info"]
 
 
 def _dp(a):
@@ -141,8 +145,17 @@ class Handle:
         self._check(rc, "g3cuda_eval_batch_device")
 
     def set_kernel(self, which: int):
-        """0 = automatic, 1 = CTA-, 2 = warp-, 3 = thread-per-evaluation kernel."""
+        """0 = automatic, 3 = thread-per-evaluation kernel, 4 = tile kernel (tests / profiling)."""
         self._check(self.lib.g3cuda_set_kernel(self.h, int(which)), "g3cuda_set_kernel")
+
+    def set_tile_warps(self, warps: int):
+        """Warps per tile of the tile kernel (0 = the planner's choice); tuning hook."""
+        self._check(self.lib.g3cuda_set_tile_warps(self.h, int(warps)), "g3cuda_set_tile_warps")
+
+    def tile_info(self) -> dict:
+        out = np.zeros(6, dtype=np.int32)
+        self._check(self.lib.g3cuda_tile_info(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))), "g3cuda_tile_info")
+        return dict(zip(("tile_ok", "warps", "table_entries", "state_entries", "state_in_smem", "thread_ok"), out.tolist()))
 
     def last_kernel_ms(self) -> float:
         return float(self.lib.g3cuda_last_kernel_ms(self.h))
@@ -158,7 +171,8 @@ class Handle:
 
 
 def math_probe(which, x, y=None, device=0):
-    """The kernels' own logspace_add (0) / avoid_zero (1) / dif_pmin(., ., 1e3) (2) on HOST arrays (test hook)."""
+    """The kernels' own logspace_add (0) / avoid_zero (1) / dif_pmin(., ., 1e3) (2) / exact-division avoid_zero (3) /
+    exact-division dif_pmin(., ., 1e3) (4) on HOST arrays (test hook)."""
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float64)
     y = None if y is None else np.ascontiguousarray(y, dtype=np.float64)

@@ -265,7 +265,7 @@ def build_c4(seed=123):
         yy = np.repeat(years, 4)
         st = np.tile([1, 2, 3, 4], len(years))
         landings = dict(year=[int(y) for y in yy], step=[int(x) for x in st], area=["area1"] * len(yy),
-                        total_weight=list((fi + 1) * 2e3 * np.tile([1.0, 2.0, 3.0, 4.0], len(years))
+                        total_weight=list((fi + 1) * 1e2 * np.tile([1.0, 2.0, 3.0, 4.0], len(years))
                                           * rng.uniform(0.8, 1.2, len(yy))))
         actions.append(g3a_predate_fleet(
             fleet, stocks, suitabilities=g3_suitability_exponentiall50(by_stock="species"),
@@ -376,7 +376,7 @@ def build_c5(seed=123):
     p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
     p = g3_init_val(p, "*.wbeta", 3, optimise=False)
     p = g3_init_val(p, "*.migrate.*", 0.2, lower=0, upper=0.5)
-    p = g3_init_val(p, "*.consumption.m0", 4e-6, optimise=False)
+    p = g3_init_val(p, "*.consumption.m0", 1e-6, optimise=False)
     p = g3_init_val(p, "*.consumption.m3", 2.0, optimise=False)
     p = g3_init_val(p, "*.halffeeding", 1e4, lower=1e2, upper=1e6)
     p = g3_init_val(p, "*.energycontent", 1, optimise=False)

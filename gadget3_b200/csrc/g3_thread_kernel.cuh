@@ -1,112 +1,31 @@
-// g3_thread_kernel.cuh -- one THREAD per parameter vector: the production evaluation kernel.
+// g3_thread_kernel.cuh -- one THREAD per parameter vector (round 1's production kernel). Today it serves the
+// single-vector report run (g3cuda_report: per-step nll rows, state histories, model arrays), forward-mode
+// gradient batches, and models the tile kernel (g3_tile.cuh) refuses.
 //
-// Mapping. A lane is an independent evaluation: the 32 lanes of a warp walk the SAME cell of the
-// SAME time step of 32 different parameter vectors. Everything the reference's objective
-// (baseline/multiple-substocks.cpp:692-2161) does for one vector becomes straight scalar code per
-// thread, so
-//   * control flow is warp-uniform by construction (every branch depends on model structure and
-//     the step, never on the lane) and no lane is ever padding;
-//   * nothing is exchanged between lanes: no shuffles, no barriers, no shared-memory staging;
-//     reductions over length/age/stock are serial sums in the reference's own order;
-//   * the data-dependent tiers of logspace_add (g3_math.cuh) rarely diverge, because the 32 lanes
-//     look at the same cell of near-identical populations.
-// State. The per-evaluation working set (stock state, transition buffers, growth/suitability
-// tables, likelihood slabs: a few thousand doubles) lives in a global-memory workspace laid out
-// [entry][thread], so that every access of a warp is one coalesced 256-byte line; it is streamed
-// once per time step: per cell and step the kernel moves ~6 doubles against ~150 fp64
-// instructions, i.e. it is bound by the fp64 pipe, not by HBM (DESIGN.md "roofline").
-// Per step there is ONE fused pass over the cells (predation -> natural mortality -> banded
-// growth with the maturing split -> maturation hand-over -> renewal -> likelihood collection),
-// possible because length growth only looks down the length axis (a register window of n+1
-// source cells per column) and maturation sources are processed before their destinations;
-// plus a totals pre-pass on steps with landings and the ageing pass at the end of a year.
+// Mapping. A lane is an independent evaluation: the 32 lanes of a warp walk the SAME cell of the SAME time step
+// of 32 different parameter vectors, so everything the reference's objective
+// (baseline/multiple-substocks.cpp:692-2161) does for one vector is straight scalar code per thread: control flow
+// is warp-uniform by construction, nothing is exchanged between lanes, sums are serial in the reference's order.
+// State. The per-evaluation working set (a few thousand values) lives in a global workspace [entry][thread]
+// (every warp access is one coalesced line). With tens of thousands of evaluations in flight that workspace is
+// far larger than L2, so every step streams it from HBM (measured: 3.45 MB of DRAM traffic per C2 evaluation,
+// the kernel is latency-bound on those loads, fp64 pipe 15 % busy -- profiles/r01_thread_kernel_v7_*): the
+// reason the tile kernel, which keeps the state in shared memory, replaced it for value batches.
+// Per step there is ONE fused pass over the cells (predation -> natural mortality -> banded growth with the
+// maturing split -> maturation hand-over -> renewal -> likelihood collection), possible because length growth
+// only looks down the length axis and maturation sources are processed before their destinations; plus a totals
+// pre-pass on steps with landings and the ageing pass at the end of a year.
 #pragma once
-#include "g3_kernel.cuh"
+#include "g3_kargs.cuh"
 
 namespace g3 {
 
-template <class T> __device__ __forceinline__ T mkpar_g(const double* __restrict__ prow, const int* seed, int i) {
-    T r(prow[i]);
-    if constexpr (Tan<T>::n > 0) {
-#pragma unroll
-        for (int k = 0; k < Tan<T>::n; k++) if (seed[k] == i) r.d[k] = 1.0;
-    }
-    return r;
-}
-
-// slot programs (include/g3cuda_spec.h G3OP_*), parameters read from the vector's row in global memory
-template <class T> __device__ __noinline__ T eval_slot_g(const int32_t* __restrict__ I, const double* __restrict__ R,
-                                                         const double* __restrict__ prow, const int* seed, int slot) {
-    const int32_t* tab = I + I[G3H_SLOT_OFF] + 2 * slot;
-    const int32_t* c = I + tab[0];
-    int n = tab[1];
-    T st[G3_SLOT_STACK];
-    int sp = 0;
-    for (int i = 0; i < n; i++) {
-        int op = c[i];
-        switch (op) {
-        case G3OP_CONST: st[sp++] = T(R[c[++i]]); break;
-        case G3OP_PARAM: st[sp++] = mkpar_g<T>(prow, seed, c[++i]); break;
-        case G3OP_NAN: st[sp++] = T(nan("")); break;
-        case G3OP_ADD: sp--; st[sp - 1] = st[sp - 1] + st[sp]; break;
-        case G3OP_SUB: sp--; st[sp - 1] = st[sp - 1] - st[sp]; break;
-        case G3OP_MUL: sp--; st[sp - 1] = st[sp - 1] * st[sp]; break;
-        case G3OP_DIV: sp--; st[sp - 1] = st[sp - 1] / st[sp]; break;
-        case G3OP_POW: sp--; st[sp - 1] = xpow(st[sp - 1], st[sp]); break;
-        case G3OP_NEG: st[sp - 1] = -st[sp - 1]; break;
-        case G3OP_EXP: st[sp - 1] = xexp(st[sp - 1]); break;
-        case G3OP_LOG: st[sp - 1] = xlog(st[sp - 1]); break;
-        case G3OP_SQRT: st[sp - 1] = xsqrt(st[sp - 1]); break;
-        case G3OP_AVOID_ZERO: st[sp - 1] = avoid_zero(st[sp - 1]); break;
-        default: break;
-        }
-    }
-    return st[0];
-}
-
-#ifndef G3_TPB
-#define G3_TPB 512
-#endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-// g3_suitability_* of prey length `ml` for predator length `pl` (R/suitability.R:5-30); p[] = the pair's slot values
-template <class T> __device__ __forceinline__ T suitability_of(int kind, const T* p, double ml, double pl) {
-    if (kind == G3SUIT_EXPL50) return 1.0 / (1.0 + xexp(-p[0] * (ml - p[1])));
-    if (kind == G3SUIT_ANDERSEN) {
-        const T x = xlog(avoid_zero(T(pl / ml)));
-        const T d = x - p[1];
-        const T lo = 1.0 / (1.0 + xexp(1000.0 * (p[1] - x)));        // bounded_vec(., 0, 1), R/aab_env.R:51-55
-        const T hi = 1.0 / (1.0 + xexp(1000.0 * (x - p[1])));
-        const T a2 = avoid_zero(p[2]);
-        return p[0] + a2 * xexp(-(d * d) / avoid_zero(p[3])) * lo + a2 * xexp(-(d * d) / avoid_zero(p[4])) * hi;
-    }
-    if (kind == G3SUIT_ANDERSENFLEET) {     // pl = the prey's largest midlen; R/suitability.R:32-58
-        const T x = xlog(T(pl / ml));
-        const T d = x - p[1];
-        const T lo = 1.0 / (1.0 + xexp(1000.0 * (p[1] - x)));
-        const T hi = 1.0 / (1.0 + xexp(1000.0 * (x - p[1])));
-        return p[0] + p[2] * xexp(-(d * d) / p[3]) * lo + p[2] * xexp(-(d * d) / p[4]) * hi;
-    }
-    if (kind == G3SUIT_GAMMA)               // R/suitability.R:60-67
-        return xpow(T(ml) / ((p[0] - 1.0) * p[1] * p[2]), p[0] - 1.0) * xexp(p[0] - 1.0 - T(ml) / (p[1] * p[2]));
-    if (kind == G3SUIT_EXPONENTIAL || kind == G3SUIT_RICHARDS) {       // R/suitability.R:69-75,90-94
-        const T e = p[3] / (1.0 + xexp(-p[0] - p[1] * ml - p[2] * pl));
-        return kind == G3SUIT_RICHARDS ? xpow(e, 1.0 / p[4]) : e;
-    }
-    if (kind == G3SUIT_STRAIGHTLINE) return p[0] + p[1] * ml;           // R/suitability.R:77-79
-    return p[0];
-}
-
-constexpr int MAXMIG = 4;       // areas a migrating stock may live on
-constexpr int TPB = G3_TPB;     // block-size cap of the default variant (one block per SM; the launch picks
-                                // blockDim <= the cap so that the batch splits into equally full waves)
-constexpr int TPB_BIG = 1024;   // cap of the high-occupancy variant (64 registers per thread), used for plain-double
-                                // batches larger than one 512-thread wave: more warps hide more latency
-constexpr unsigned WS_STRIDE = 152u * 1024u;    // workspace stride in threads: room for 152 SMs x the largest block
-
 // CB: block-size cap the variant is compiled for (__launch_bounds__); NW: growth window = maxlengthgroupgrowth + 1 source cells kept in registers per column
 // CONSTMAT: some stock matures with g3a_mature_constant (needs a third register window)
 // REPORT: single-vector report run (g3cuda_report): per-step nll rows, state histories, model arrays
-template <class T, int CB, int NW, bool CONSTMAT, bool REPORT = false>
+// STRIDE: thread stride of the workspace (>= launched threads); the report variant runs one warp
+template <class T, int CB, int NW, bool CONSTMAT, bool REPORT = false, unsigned STRIDE = WS_STRIDE>
 __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__ KArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int32_t* __restrict__ I = A.I;
@@ -115,7 +34,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
     // The thread stride of the workspace is a COMPILE-TIME constant (>= the launched threads), so that
     // neighbouring entries sit at immediate offsets from a running pointer: no address arithmetic
     // in the inner loops. (entries x WS_STRIDE < 2^32 is checked at launch.)
-    constexpr unsigned NTH = WS_STRIDE;
+    constexpr unsigned NTH = STRIDE;
     T* __restrict__ ws = reinterpret_cast<T*>(A.t_ws) + gtid;
 #define W(e) ws[(unsigned)(e) * NTH]
     T* s_eot = reinterpret_cast<T*>(smem_raw) + threadIdx.x;      // [MAXTS][blockDim]: landings / total suitable biomass
@@ -552,8 +471,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                         for (int x = 0; x < MAXX; x++) if ((kx[k] >> x) & 1) fx[x] = fx[x] + cf;
                                     }
                                 }
-                            T cr = xdiv(tp, avoid_zero(B0));
-                            cr = dif_pmax_c(cr, 0.95, -1e3);
+                            T cr = xdiv_x(tp, avoid_zero_x(B0));       // (exact-division forms: see g3_math.cuh)
+                            cr = dif_pmax_x(cr, 0.95, -1e3);
                             const T tpn = B0 * cr;
                             *pn = num * (1.0 - cr);
                             if (is_us) { o1 = o1 + tp; o2 = o2 + tpn; }

@@ -1,0 +1,909 @@
+// g3_tile.cuh -- the production evaluation kernel: one CTA owns a TILE of 32 parameter vectors for the
+// whole time loop, with the stock state resident in shared memory.
+//
+// Mapping (north_star item 1; baseline/multiple-substocks.cpp:692-2161 is the path it evaluates):
+//   lane  = evaluation. The 32 lanes of every warp are the same 32 parameter vectors, so the per-cell
+//           arithmetic is the straight-line scalar code of the reference and control flow is warp-uniform
+//           (branches depend on model structure and the step, never on the lane).
+//   warp  = age/area column(s) of a stock. Growth, mortality, predation, renewal are independent per
+//           column (length is the only coupled axis); what crosses columns goes through shared memory and
+//           one block barrier: fleet totals, the maturation hand-over, likelihood sums, ageing, migration.
+//   state = num/wgt of every stock cell (+ the maturing fish in flight) in shared memory, [cell][lane]:
+//           a warp access is one conflict-free 256-byte row. Models whose state does not fit 227 KB
+//           (and Dual<N> gradient runs) keep the same layout in the CTA's global slab instead (SMEM = false).
+//   tables (per evaluation, time-invariant: growth bands, suitability, mortality, renewal shape, likelihood
+//           slabs, collect vectors) live in a per-CTA global slab [entry][lane]; only gridDim x 32
+//           evaluations are in flight, so the slabs stay in L2/L1 instead of streaming from HBM.
+// Nothing is exchanged between lanes: no shuffles, no atomics; every sum has a fixed order.
+//
+// The body is written against a few macros (G3T_BAR, G3T_ANY) so that the same source also compiles under
+// g++ for tests/emu (kernel-logic tests on the CPU, one OS thread per warp) -- test infrastructure, never
+// loaded by the product library.
+#pragma once
+#include "g3_common.cuh"
+
+namespace g3t {
+using namespace g3;
+
+constexpr int NL = 32;      // lanes = evaluations per tile
+
+struct StockRec {
+    int L, nage, narea, ncol, c0, gcol0, minage;
+    int grow_n, mat_kind, has_out, trans_mask, inc_steps;
+    int mort_ioff, midlen_roff, plusdl_roff, grow_ioff, mat_ioff, init_ioff;
+    int n_renew, renew_ioff;
+    int g_mort;             // [idt][col] exp(-M dt)
+    int g_rd, g_rw;         // [k][l] renewal numbers shape (x 1e4) and weight
+    int g_pw;               // [l] midlen^wbeta
+    int g_band, g_bandr;    // growth band sets, staying (or whole) / maturing part: [set][idt][(L+1)*(n+1)]
+    int band_percol, bsz;   // one set per column (continuous maturity with an age term) or per stock
+    int g_cmat;             // [col][l] g3a_mature_constant ratio, or -1
+    int mig_ioff, g_mig, mig_steps;
+    int age_enable, age_n_out, s_mv;
+    int us_flag;
+    int pp_off, pp_n;       // tb: predator-prey pairs acting on this stock, run order
+    int cx_off, cx_n;       // tb: catch collect vectors those pairs feed
+};
+struct ColRec {
+    int s, col, aidx, ridx, cell0;
+    int s_tn, s_tw;         // S entries of this column's maturing fish, or -1 (no destination: only the remainder matters)
+    int inc_tn, inc_tw, inc_slot, inc_mask;     // maturing fish arriving INTO this column: source entries, ratio slot, step mask
+    int g_remf;             // share of the maturing fish no output stock claims
+    int rem_off;            // tb: -1 terminated list of ratio slots with a destination
+    int g_usp;              // (sum tp, sum tp') of this column at this step's predation
+};
+struct PairRec {
+    int pred, prey, suit_kind, suit_ioff, energy_slot, pred_kind, pred_stock, PL;
+    int g_suit;             // [PL][L]
+    int g_part;             // [prey column][PL] partial suitable biomass
+    int cxmask;             // bit j: feeds the prey stock's j-th catch collect vector
+    int tsid_off;           // tb: [prey narea] accumulator (fleet) / predator area index (stock predator), or -1
+};
+struct PredRec { int kind, stock, slot_ioff, narea, g_pts, g_pmc, list_off; };
+struct TsRec { int kind, eoff, estr, list_off, list_n; };
+struct CompRec {
+    int func, weight_par, xbuf, mode, n_dest, n_bins, n_slices, n_areag;
+    int csr_ptr_ioff, csr_idx_ioff, csr_coef_roff, cell_dest_ioff, cell_coef_roff, tidx_ioff, cmp_ioff;
+    int n_times, param_roff, g_ms, obs_off, obsconst_off;
+};
+struct XRec { int kind, unit, g_x; };
+
+struct TArgs {
+    const int32_t* I; const double* R; const int32_t* tb;
+    const StockRec* st; const ColRec* col; const PairRec* pp; const PredRec* pred; const TsRec* ts;
+    const CompRec* comp; const XRec* xb; const int4* agedst;
+    const double* obsprop; const double* obsconst; const unsigned char* pred_active;
+    const double* par; long long B; const int32_t* tangent_idx; int K;
+    double* nll; double* comp_out; double* grad;
+    double* gws; long long slab_doubles; int lanes_per_tile;
+    int NC, NS, NPP, NPRED, NTS, NCOMP, NX, NSLOT, NPAR, NT, NSTEPS, NNLL, NBOUND, NCOLS, maxL, n_agedst;
+    int ndt, dt_len[4], step_idt[32];
+    int n_g;                // G entries per lane; the state entries follow them when SMEM = false
+    int s_num, s_wgt;       // S entry bases
+    int g_slot, g_eot, g_cn, g_ctot, g_bterm, g_wscr, wscr_n;
+    int wcol_off;           // tb: [W + 1] offsets into tb, then each warp's global columns
+    int ax_off, ax_n;       // tb: abundance collect vectors
+    int agedst_l_off;       // tb: length group of each agedst entry
+    int inc_any_mask;       // bit (cur_step-1): some column receives maturing fish on that step
+    int W;
+};
+
+#ifdef __CUDACC__
+#define G3T_BAR() __syncthreads()
+#define G3T_ANY(p) __any_sync(0xffffffffu, (p))
+#define G3T_CTX_DECL
+#define G3T_CTX_ARG
+#else
+struct EmuCtx { void (*bar)(void*); void* arg; };
+#define G3T_BAR() ctx.bar(ctx.arg)
+#define G3T_ANY(p) (p)
+#define G3T_CTX_DECL , const EmuCtx& ctx
+#define G3T_CTX_ARG , ctx
+#endif
+
+// element access in the [entry][component][lane] layout (component 0 = value, 1.. = tangents)
+__device__ __forceinline__ void ldv(const double* p, double& r) { r = *p; }
+__device__ __forceinline__ void stv(double* p, const double& v) { *p = v; }
+template <int N> __device__ __forceinline__ void ldv(const double* p, Dual<N>& r) {
+    r.v = p[0];
+#pragma unroll
+    for (int k = 0; k < N; k++) r.d[k] = p[(k + 1) * NL];
+}
+template <int N> __device__ __forceinline__ void stv(double* p, const Dual<N>& v) {
+    p[0] = v.v;
+#pragma unroll
+    for (int k = 0; k < N; k++) p[(k + 1) * NL] = v.d[k];
+}
+
+// T: double or Dual<N>; NW: compiled width of the growth band (maxlengthgroupgrowth + 1 <= NW);
+// SMEM: stock state in shared memory (smem = its base) or in the global slab
+template <class T, int NW, bool SMEM>
+__device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const int warp, const int lane, const int cta,
+                                          const int ncta G3T_CTX_DECL) {
+    constexpr int NTAN = Tan<T>::n;
+    constexpr unsigned C = (unsigned)(NTAN + 1) * NL;       // doubles per entry
+    const int32_t* __restrict__ I = A.I;
+    const double* __restrict__ R = A.R;
+    const int32_t* __restrict__ tb = A.tb;
+    const int W = A.W;
+    double* const gl = A.gws + (size_t)cta * (size_t)A.slab_doubles + lane;
+    double* const sm = SMEM ? smem + lane : gl + (size_t)A.n_g * C;
+#define GP(e) (gl + (unsigned)(e) * C)
+#define SP(e) (sm + (unsigned)(e) * C)
+    auto G = [&](int e) { T r; ldv(GP(e), r); return r; };
+    auto GS = [&](int e, const T& v) { stv(GP(e), v); };
+    auto S = [&](int e) { T r; ldv(SP(e), r); return r; };
+    auto SS = [&](int e, const T& v) { stv(SP(e), v); };
+#define SLOT(i) G(A.g_slot + (i))
+
+    const int NS = A.NS, NSTEPS = A.NSTEPS, NT = A.NT;
+    const int ntan_tiles = NTAN > 0 ? (A.K + NTAN - 1) / NTAN : 1;
+    const long long total = A.B * ntan_tiles;
+    const int LPT = A.lanes_per_tile;
+    const long long ntile = (total + LPT - 1) / LPT;
+    const double us_power = R[I[G3H_US_ROFF]], us_weight = R[I[G3H_US_ROFF] + 1];
+    const bool have_us = I[G3H_US_N] > 0;
+    const int wc0 = tb[A.wcol_off + warp], wc1 = tb[A.wcol_off + warp + 1];     // this warp's columns: tb[wc0..wc1)
+
+    for (long long tile = cta; tile < ntile; tile += ncta) {
+        const long long work0 = tile * LPT + lane;
+        const bool live = lane < LPT && work0 < total;
+        const long long work = live ? work0 : tile * LPT;       // idle lanes redo the tile's first item without writing
+        const long long b = work / ntan_tiles;
+        const int tile_t = (int)(work - b * ntan_tiles);
+        int seed[NTAN > 0 ? NTAN : 1];
+#pragma unroll
+        for (int k = 0; k < (NTAN > 0 ? NTAN : 1); k++) {
+            const int g = tile_t * NTAN + k;
+            seed[k] = (NTAN > 0 && g < A.K) ? A.tangent_idx[g] : -1;
+        }
+        const double* __restrict__ prow = A.par + b * A.NPAR;
+
+        // ---- g3a_time (R/action_time.R:75-91)
+        const double retro = I[G3H_PAR_RETRO] >= 0 ? prow[I[G3H_PAR_RETRO]] : 0.0;
+        const double proj = I[G3H_PAR_PROJECT] >= 0 ? prow[I[G3H_PAR_PROJECT]] : 0.0;
+        const int total_steps = NSTEPS * (I[G3H_END_YEAR] - (int)floor(retro) - I[G3H_START_YEAR] + (int)floor(proj)) + NSTEPS - 1;
+        const bool bad_time = !(retro >= 0.0) || !(proj >= 0.0) || total_steps + 1 > NT;
+
+        G3T_BAR();      // the previous tile is fully retired before the slab and the state are reused
+
+        // ================= scalar formula slots, once per parameter vector
+        for (int i = warp; i < A.NSLOT; i += W) GS(A.g_slot + i, eval_slot_g<T>(I, R, prow, seed, i));
+        G3T_BAR();
+
+        // ================= per-evaluation tables. Work units are dealt round-robin to the warps.
+        int ucnt = 0;
+        auto mine = [&]() { const bool m = ucnt == warp; ucnt = ucnt + 1 == W ? 0 : ucnt + 1; return m; };
+
+        for (int q = 0; q < A.NPP; q++) {           // suitability (R/suitability.R:5-94): [predator length][prey length]
+            const PairRec& Q = A.pp[q];
+            const StockRec& Ps = A.st[Q.prey];
+            const bool spred = Q.pred_kind == G3PRED_STOCK;
+            const double* pml = R + Ps.midlen_roff;
+            for (int pl = 0; pl < Q.PL; pl++) {
+                if (!mine()) continue;
+                const int32_t* ss = I + Q.suit_ioff;
+                T sp[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
+                const double plen = spred && Q.suit_kind != G3SUIT_ANDERSENFLEET ? R[A.st[Q.pred_stock].midlen_roff + pl] : pml[Ps.L - 1];
+                for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, suitability_of<T>(Q.suit_kind, sp, pml[l], plen));
+            }
+        }
+        // stock predators: maximum consumption per predator length without the step length,
+        // m0 exp(m1 T - m2 T^3) l^m3 (R/action_predate.R:190-205)
+        for (int pi = 0; pi < A.NPRED; pi++) {
+            const PredRec& P = A.pred[pi];
+            if (P.kind != G3PRED_STOCK) continue;
+            const StockRec& Pp = A.st[P.stock];
+            for (int pl = 0; pl < Pp.L; pl++) {
+                if (!mine()) continue;
+                const int32_t* ps = I + P.slot_ioff;
+                const T m0 = SLOT(ps[0]), m1 = SLOT(ps[1]), m2 = SLOT(ps[2]), m3 = SLOT(ps[3]), temp = SLOT(ps[5]);
+                const T tf = m0 * xexp(m1 * temp - m2 * temp * temp * temp);
+                GS(P.g_pmc + pl, tf * xpow(T(R[Pp.midlen_roff + pl]), m3));
+            }
+        }
+        for (int s = 0; s < NS; s++) {
+            const StockRec& St = A.st[s];
+            const int L = St.L;
+            const double* midlen = R + St.midlen_roff;
+            // migration matrices per step of the year: proportion moving src -> dest (R/action_migrate.R:2-15,49-56)
+            if (St.mig_ioff >= 0) {
+                const int NR = St.narea;
+                for (int sy = 0; sy < NSTEPS; sy++) {
+                    if (!mine()) continue;
+                    const int32_t* mig = I + St.mig_ioff + sy * NR * NR;
+                    for (int src = 0; src < NR; src++) {
+                        T tot(0.0);
+                        for (int d = 0; d < NR; d++) {
+                            T v = (d != src && mig[d * NR + src] >= 0) ? SLOT(mig[d * NR + src]) : T(0.0);
+                            v = v * v;
+                            tot = tot + v;
+                            GS(St.g_mig + (sy * NR + d) * NR + src, v / 1.0);
+                        }
+                        GS(St.g_mig + (sy * NR + src) * NR + src, (1.0 - tot) / 1.0);
+                    }
+                }
+            }
+            // renewal length distribution, normalised, and weight (R/action_renewal.R:56-80)
+            for (int k = 0; k < St.n_renew; k++) {
+                if (!mine()) continue;
+                const int32_t* Rn = I + St.renew_ioff + k * G3R_LEN;
+                const T mean = SLOT(Rn[G3R_MEAN]), sd = avoid_zero(SLOT(Rn[G3R_SD]));
+                const T wa = SLOT(Rn[G3R_WALPHA]), wb = SLOT(Rn[G3R_WBETA]);
+                T tot(0.0);
+                for (int l = 0; l < L; l++) { const T d = dnorm(midlen[l], mean, sd); GS(St.g_rd + k * L + l, d); tot = tot + d; }
+                const T den = avoid_zero(tot);
+                for (int l = 0; l < L; l++) {
+                    GS(St.g_rd + k * L + l, G(St.g_rd + k * L + l) / den * 10000.0);
+                    GS(St.g_rw + k * L + l, wa * xpow(midlen[l], wb));
+                }
+            }
+            const int n2 = St.grow_n;
+            if (n2 < 0) continue;
+            const int32_t* gs = I + St.grow_ioff;
+            for (int l = 0; l < L; l++)
+                if (mine()) GS(St.g_pw + l, xpow(midlen[l], SLOT(gs[4])));
+            // ---- growth bands, source-oriented: row l holds P(l -> l + x), x = 0..n (growth_bbinom in product
+            // form, R/action_grow.R:155-213); row L holds the plus-group tail sums, [d] = sum_{x >= d} P(L-1-d -> .)
+            // (R/action_grow.R:233-271). Continuous maturity splits each row into the staying and the maturing
+            // part (R/action_mature.R:1-42, R/action_grow.R:420-437); with an age term there is a set per column.
+            const bool cont = St.mat_kind == G3MAT_CONTINUOUS && St.has_out;
+            const double pdl = R[St.plusdl_roff];
+            const int nset = St.band_percol ? St.ncol : 1;
+            const int n1 = n2 + 1;
+            for (int set = 0; set < nset; set++)
+                for (int idt = 0; idt < A.ndt; idt++)
+                    for (int l = 0; l < L; l++) {
+                        if (!mine()) continue;
+                        const double dt = A.dt_len[idt] / 12.0;
+                        const T linf = SLOT(gs[0]), kk = 1.0 - xexp(-(SLOT(gs[1])) * dt), beta = avoid_zero(SLOT(gs[2]));
+                        // g3a_grow_lengthvbsimple (R/action_grow.R:54) inside the bbinom wrapper (R/action_grow.R:220)
+                        const T dl = avoid_zero((linf - midlen[l]) * kk);
+                        const T delta = avoid_zero(dl / pdl);
+                        const T alpha = (beta * delta) / ((double)n2 - delta);
+                        T g = T(1.0);
+                        for (int j = 0; j < n2; j++) g = g * ((beta + (double)j) / xabs(alpha + beta + (double)j));
+                        T m0(0.0), malpha(0.0), mbeta(0.0);
+                        if (cont) {         // g3a_mature_constant as M0 (R/action_mature.R:44-74)
+                            const int32_t* ms = I + St.mat_ioff;
+                            T inner(0.0);
+                            if (ms[0] >= 0) { malpha = SLOT(ms[0]); inner = inner - malpha * (midlen[l] - SLOT(ms[1])); }
+                            if (ms[2] >= 0) { mbeta = SLOT(ms[2]); inner = inner - mbeta * ((double)(St.minage + set % St.nage) - SLOT(ms[3])); }
+                            m0 = 1.0 / (1.0 + xexp(inner));
+                        }
+                        const int row = (set * A.ndt + idt) * St.bsz + l * n1;
+                        const int tail = (set * A.ndt + idt) * St.bsz + L * n1;
+                        const int dtail = L - 1 - l;            // this row's entry of the tail row, if within the band
+                        T ta(0.0), tr(0.0);
+                        T gx[NW], rx[NW];
+#pragma unroll
+                        for (int x = 0; x < NW; x++) {
+                            gx[x] = T(0.0); rx[x] = T(0.0);
+                            if (x <= n2) {
+                                if (cont) {
+                                    const T ratio = dif_pminmax_c(m0 * (malpha * (pdl * x) + mbeta * dt), 0.0, 1.0, 1e5);
+                                    rx[x] = g * ratio; gx[x] = g * (1.0 - ratio);
+                                    GS(St.g_bandr + row + x, rx[x]);
+                                } else gx[x] = g;
+                                GS(St.g_band + row + x, gx[x]);
+                                if (x < n2)
+                                    g = g * ((double)(n2 - x) / (double)(x + 1)) * (xabs(alpha + (double)x) / (beta + (double)(n2 - x - 1)));
+                            }
+                        }
+                        if (dtail <= n2) {
+#pragma unroll
+                            for (int x = 0; x < NW; x++)
+                                if (x >= dtail && x <= n2) { ta = ta + gx[x]; tr = tr + rx[x]; }
+                            GS(St.g_band + tail + dtail, ta);
+                            if (cont) GS(St.g_bandr + tail + dtail, tr);
+                        }
+                    }
+        }
+        // ---- own columns: mortality factors, initial conditions, maturation remainder, constant-maturity ratios
+        for (int wi = wc0; wi < wc1; wi++) {
+            const ColRec& Cl = A.col[tb[wi]];
+            const StockRec& St = A.st[Cl.s];
+            const int L = St.L, col = Cl.col;
+            const double* midlen = R + St.midlen_roff;
+            if (St.mort_ioff >= 0)      // natural mortality factor per distinct step length (R/action_naturalmortality.R:26)
+                for (int idt = 0; idt < A.ndt; idt++)
+                    GS(St.g_mort + idt * St.ncol + col, xexp(-SLOT(I[St.mort_ioff + col]) * (A.dt_len[idt] / 12.0)));
+            // g3a_initialconditions (R/action_renewal.R:83-163)
+            if (St.init_ioff < 0) {
+                for (int l = 0; l < L; l++) { SS(A.s_num + Cl.cell0 + l, T(0.0)); SS(A.s_wgt + Cl.cell0 + l, T(1.0)); }
+            } else {
+                const int32_t* sl = I + St.init_ioff + col * 5;
+                const T mean = SLOT(sl[0]), sd = avoid_zero(SLOT(sl[1])), factor = SLOT(sl[2]), wa = SLOT(sl[3]), wb = SLOT(sl[4]);
+                T tot(0.0);
+                for (int l = 0; l < L; l++) { const T d = dnorm(midlen[l], mean, sd); SS(A.s_num + Cl.cell0 + l, d); tot = tot + d; }
+                const T den = avoid_zero(tot);                           // normalize_vec, R/aab_env.R:37-41
+                for (int l = 0; l < L; l++) {
+                    SS(A.s_num + Cl.cell0 + l, S(A.s_num + Cl.cell0 + l) / den * 10000.0 * factor);
+                    SS(A.s_wgt + Cl.cell0 + l, wa * xpow(midlen[l], wb));
+                }
+            }
+            if (St.grow_n >= 0 && St.has_out) {
+                // share of the maturing fish of this column that no output stock claims (R/action_mature.R:126-131)
+                T remf(1.0);
+                for (int k = Cl.rem_off; tb[k] >= 0; k++) remf = remf - SLOT(tb[k]);
+                GS(Cl.g_remf, remf);
+                if (St.mat_kind == G3MAT_CONSTANT) {        // ratio per (column, length) (R/action_mature.R:44-74)
+                    const int32_t* msl = I + St.mat_ioff;
+                    for (int l = 0; l < L; l++) {
+                        T inner(0.0);
+                        if (msl[0] >= 0) inner = inner - SLOT(msl[0]) * (midlen[l] - SLOT(msl[1]));
+                        if (msl[2] >= 0) inner = inner - SLOT(msl[2]) * ((double)(St.minage + Cl.aidx) - SLOT(msl[3]));
+                        GS(St.g_cmat + col * L + l, 1.0 / (1.0 + xexp(inner)));
+                    }
+                }
+            }
+        }
+        // ---- g3l_bounds_penalty terms (R/likelihood_bounds.R:13-16); warp 0 adds them in run order below
+        {
+            const double bs = A.NBOUND > 0 ? R[I[G3H_BOUND_WS_ROFF] + 1] : 0.0;
+            for (int i = 0; i < A.NBOUND; i++) {
+                if (!mine()) continue;
+                const T p = mkpar_g<T>(prow, seed, I[I[G3H_BOUND_OFF] + i]);
+                const double lo = R[I[G3H_BOUND_ROFF] + 2 * i], up = R[I[G3H_BOUND_ROFF] + 2 * i + 1];
+                const T a = lsa_c(bs * (p - up) / (up - lo), 0.0) + lsa_c(bs * (lo - p) / (up - lo), 0.0);
+                GS(A.g_bterm + i, a * a);
+            }
+        }
+        for (int c = 0; c < A.NCOMP; c++) {         // zero the likelihood slabs
+            const CompRec& Cm = A.comp[c];
+            const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
+            const int n = Cm.n_dest * (si ? Cm.n_times : 1);
+            for (int i = warp; i < n; i += W) GS(Cm.g_ms + i, T(0.0));
+        }
+        G3T_BAR();
+
+        // which components this tile evaluates: <name>_weight > 0 on some lane (R/likelihood_distribution.R:352)
+        unsigned cw_any = 0, cw_lane = 0;
+        for (int c = 0; c < A.NCOMP; c++) {
+            const bool on = prow[A.comp[c].weight_par] > 0.0;
+            if (on) cw_lane |= 1u << c;
+            if (G3T_ANY(on)) cw_any |= 1u << c;
+        }
+
+        T nll(0.0);         // warp 0 keeps the objective and the component sums
+        if (warp == 0) {
+            for (int i = 0; i < A.NNLL; i++) GS(A.g_ctot + i, T(0.0));
+            if (A.NBOUND > 0) {
+                T pen(0.0);
+                for (int i = 0; i < A.NBOUND; i++) pen = pen + G(A.g_bterm + i);
+                nll = nll + R[I[G3H_BOUND_WS_ROFF]] * pen;
+                GS(A.g_ctot + A.NNLL - 1, pen);
+            }
+        }
+
+        for (int t = 0; t < NT; t++) {
+            const bool lane_on = !bad_time && t <= total_steps;
+            if (!G3T_ANY(lane_on)) break;       // (every warp holds the same 32 evaluations: the decision is block-uniform)
+            const int step = t % NSTEPS, yidx = t / NSTEPS;
+            const int idt = A.step_idt[step];
+            const double dt = A.dt_len[idt] / 12.0;
+            const bool final_step = step == NSTEPS - 1;
+            const bool pred_now = A.pred_active[t] != 0;
+            // components collecting at this step (bit c), their collect vectors (bit x), and whether any reads a catch
+            unsigned cact = 0, xact = 0;
+            bool any_catch = false;
+            for (int c = 0; c < A.NCOMP; c++) {
+                const CompRec& Cm = A.comp[c];
+                if (I[Cm.tidx_ioff + t] >= 0 && ((cw_any >> c) & 1)) {
+                    cact |= 1u << c;
+                    xact |= 1u << Cm.xbuf;
+                    if (A.xb[Cm.xbuf].kind == 0) any_catch = true;
+                }
+            }
+
+            // ================= g3a_migrate (R/action_migrate.R:17-82): every (age, length) mixes its areas
+            {
+                bool mig_any = false;
+                ucnt = 0;
+                for (int s = 0; s < NS; s++) {
+                    const StockRec& St = A.st[s];
+                    if (!((St.mig_steps >> step) & 1)) continue;
+                    mig_any = true;
+                    const int L = St.L, nage = St.nage, NR = St.narea, c0 = St.c0;
+                    const int mo = St.g_mig + step * NR * NR;
+                    for (int a = 0; a < nage; a++) {
+                        if (!mine()) continue;
+                        for (int l = 0; l < L; l++) {
+                            const int i = a * L + l;
+                            // destination by destination; sources are read before any destination is written (wscr holds them)
+                            for (int r = 0; r < NR; r++) {
+                                GS(A.g_wscr + warp * A.wscr_n + 2 * r, S(A.s_num + c0 + r * nage * L + i));
+                                GS(A.g_wscr + warp * A.wscr_n + 2 * r + 1, S(A.s_wgt + c0 + r * nage * L + i));
+                            }
+                            for (int d = 0; d < NR; d++) {
+                                T pn(0.0), pw(0.0);
+                                for (int r = 0; r < NR; r++) {
+                                    const T moved = G(A.g_wscr + warp * A.wscr_n + 2 * r) * G(mo + d * NR + r);
+                                    pw = ratio_add_pop(pw, pn, G(A.g_wscr + warp * A.wscr_n + 2 * r + 1), moved);     // stock_combine_subpop
+                                    pn = pn + moved;
+                                }
+                                SS(A.s_num + c0 + d * nage * L + i, pn); SS(A.s_wgt + c0 + d * nage * L + i, pw);
+                            }
+                        }
+                    }
+                }
+                if (mig_any) G3T_BAR();
+            }
+
+            // ================= g3a_predate step 1: suitable biomass per (predator, area[, predator length]) (R/action_predate.R:314-333)
+            if (pred_now) {
+                for (int wi = wc0; wi < wc1; wi++) {        // partial sums of the own columns
+                    const ColRec& Cl = A.col[tb[wi]];
+                    const StockRec& St = A.st[Cl.s];
+                    const int L = St.L;
+                    for (int j = 0; j < St.pp_n; j++) {
+                        const int q = tb[St.pp_off + j];
+                        const PairRec& Q = A.pp[q];
+                        if (Q.pred_kind == G3PRED_LINEARFLEET || Q.pred_kind == G3PRED_EFFORTFLEET) continue;     // no total needed
+                        if (tb[Q.tsid_off + Cl.ridx] < 0) continue;
+                        const bool spred = Q.pred_kind == G3PRED_STOCK;
+                        const bool by_number = Q.pred_kind == G3PRED_NUMBERFLEET;       // suit = S * num (R/action_predate.R:7-11)
+                        for (int pl = 0; pl < Q.PL; pl++) {
+                            T cs(0.0);
+                            for (int l = 0; l < L; l++) {
+                                const T n = S(A.s_num + Cl.cell0 + l);
+                                cs = cs + G(Q.g_suit + pl * L + l) * (by_number ? n : n * S(A.s_wgt + Cl.cell0 + l));
+                            }
+                            GS(Q.g_part + Cl.col * Q.PL + pl, spred ? cs * SLOT(Q.energy_slot) : cs);
+                        }
+                    }
+                }
+                G3T_BAR();
+                ucnt = 0;
+                for (int k = 0; k < A.NTS; k++) {           // fleets: landings over total suitable biomass, cons = E * (suit / totalsuit)
+                    if (!mine()) continue;
+                    const TsRec& Ts = A.ts[k];
+                    const double E = R[Ts.eoff + (size_t)t * Ts.estr];
+                    if (Ts.kind == G3PRED_LINEARFLEET || Ts.kind == G3PRED_EFFORTFLEET) {
+                        GS(A.g_eot + k, T(E * dt));         // harvest rate x step length (R/action_predate.R:13-18,117-126)
+                    } else {
+                        T tot(0.0);
+                        for (int i = 0; i < Ts.list_n; i++) tot = tot + G(tb[Ts.list_off + i]);
+                        GS(A.g_eot + k, E / tot);
+                    }
+                }
+                // stock predators: predN * max_consumption * feeding_level / total_predsuit per (area, predator length)
+                // (R/action_predate.R:207-238; energycontent cancels between suit and cons)
+                for (int pi = 0; pi < A.NPRED; pi++) {
+                    const PredRec& P = A.pred[pi];
+                    if (P.kind != G3PRED_STOCK) continue;
+                    const StockRec& Pp = A.st[P.stock];
+                    const int PL = Pp.L, PA = Pp.nage;
+                    for (int pr = 0; pr < Pp.narea; pr++) {
+                        const int lo = tb[P.list_off + 2 * pr], ln = tb[P.list_off + 2 * pr + 1];
+                        for (int pl = 0; pl < PL; pl++) {
+                            if (!mine()) continue;
+                            T ts(0.0);
+                            for (int i = 0; i < ln; i++) ts = ts + G(tb[lo + i] + pl);
+                            T predn(0.0);
+                            for (int pa = 0; pa < PA; pa++) predn = predn + S(A.s_num + Pp.c0 + (pr * PA + pa) * PL + pl);
+                            const T hf = SLOT(I[P.slot_ioff + 4]);
+                            const T feeding = ts / (hf * dt + ts);
+                            GS(P.g_pts + pr * PL + pl, predn * (G(P.g_pmc + pl) * dt) * feeding / ts);
+                        }
+                    }
+                }
+                G3T_BAR();
+            }
+
+            // what a column does once its own growth is through: hand-over, renewal, store, collect vectors
+            auto finish_cell = [&](const ColRec& Cl, const StockRec& St, const int l, T num, T wgt, const bool inc_here,
+                                   const int ren_mask) {
+                const int L = St.L;
+                // ---- g3a_step_transition (R/action_mature.R:78-134): maturing fish arriving from their source column
+                if (inc_here) {
+                    const T moved = S(Cl.inc_tn + l) * SLOT(Cl.inc_slot);
+                    wgt = ratio_add_pop(wgt, num, S(Cl.inc_tw + l), moved);
+                    num = num + moved;
+                }
+                // ---- g3a_renewal (R/action_renewal.R:166-188)
+                if (ren_mask)
+                    for (int r = 0; r < St.n_renew; r++)
+                        if (((ren_mask >> r) & 1) && Cl.aidx == I[St.renew_ioff + r * G3R_LEN + G3R_AGE_IDX]) {
+                            const int fs = I[I[St.renew_ioff + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * St.narea + Cl.ridx];
+                            if (fs >= 0) {
+                                const T rn = G(St.g_rd + r * L + l) * SLOT(fs);
+                                wgt = ratio_add_pop(wgt, num, G(St.g_rw + r * L + l), rn);
+                                num = num + rn;
+                            }
+                        }
+                SS(A.s_num + Cl.cell0 + l, num); SS(A.s_wgt + Cl.cell0 + l, wgt);
+                // ---- collect vectors for g3l_distribution (R/likelihood_distribution.R:275-287)
+                if (xact) {
+                    const int cell = Cl.cell0 + l;
+                    for (int j = 0; j < St.cx_n; j++) {         // catch in numbers: cons / avoid_zero(wgt)
+                        const int x = tb[St.cx_off + j];
+                        if (((xact >> x) & 1) && A.xb[x].unit == 0) GS(A.xb[x].g_x + cell, xdiv(G(A.xb[x].g_x + cell), avoid_zero(wgt)));
+                    }
+                    for (int j = 0; j < A.ax_n; j++) {          // abundance
+                        const int x = tb[A.ax_off + j];
+                        if ((xact >> x) & 1) GS(A.xb[x].g_x + cell, A.xb[x].unit == 0 ? num : num * wgt);
+                    }
+                }
+            };
+
+            // ================= own columns: predation, natural mortality, growth (+ maturing split), and -- unless
+            // maturing fish are about to arrive -- renewal and the collect vectors
+            for (int wi = wc0; wi < wc1; wi++) {
+                const ColRec& Cl = A.col[tb[wi]];
+                const StockRec& St = A.st[Cl.s];
+                const int L = St.L, nq = St.pp_n, cell0 = Cl.cell0;
+                const bool prey_now = pred_now && nq > 0;
+                const int grow_n = St.grow_n;
+                const bool trans_now = grow_n >= 0 && St.has_out && ((St.trans_mask >> step) & 1);
+                const bool cont_now = trans_now && St.mat_kind == G3MAT_CONTINUOUS;
+                const bool const_now = trans_now && St.mat_kind == G3MAT_CONSTANT;
+                const bool has_mort = St.mort_ioff >= 0;
+                const bool inc_here = Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1);
+                int ren_mask = 0;       // renewal records that run at this step
+                for (int k = 0; k < St.n_renew; k++) {
+                    const int rs = I[St.renew_ioff + k * G3R_LEN + G3R_RUN_STEP];
+                    if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
+                }
+                const bool catch_now = any_catch && nq > 0;
+
+                // ---------- g3a_predate (R/action_predate.R:335-406)
+                if (prey_now) {
+                    const int ws0 = A.g_wscr + warp * A.wscr_n;
+                    for (int k = 0; k < nq; k++) {      // landings / total suitable biomass of each fleet in this column's area
+                        const PairRec& Q = A.pp[tb[St.pp_off + k]];
+                        const int ts = tb[Q.tsid_off + Cl.ridx];
+                        if (ts < 0 || Q.pred_kind == G3PRED_STOCK) continue;
+                        T e = G(A.g_eot + ts);
+                        if (Q.pred_kind == G3PRED_EFFORTFLEET) e = e * SLOT(Q.energy_slot);      // catchability_fs of this prey
+                        GS(ws0 + k, e);
+                    }
+                    // consumption per unit of biomass by predator k at length l
+                    auto cfac = [&](const PairRec& Q, const int k, const int ts, const int l) {
+                        if (Q.pred_kind != G3PRED_STOCK) return G(Q.g_suit + l) * G(ws0 + k);
+                        T cf(0.0);      // sum over the predator's length groups of suitability x consumption factor
+                        const int gp = A.pred[Q.pred].g_pts + ts * Q.PL;
+                        for (int pl = 0; pl < Q.PL; pl++) cf = cf + G(Q.g_suit + pl * L + l) * G(gp + pl);
+                        return cf;
+                    };
+                    T o1(0.0), o2(0.0);
+                    for (int l = 0; l < L; l++) {
+                        const T num = S(A.s_num + cell0 + l);
+                        const T B0 = num * S(A.s_wgt + cell0 + l);
+                        T tp(0.0);
+                        for (int k = 0; k < nq; k++) {
+                            const PairRec& Q = A.pp[tb[St.pp_off + k]];
+                            const int ts = tb[Q.tsid_off + Cl.ridx];
+                            if (ts >= 0) tp = tp + cfac(Q, k, ts, l) * B0;
+                        }
+                        T cr = xdiv_x(tp, avoid_zero_x(B0));       // (exact-division forms: see g3_math.cuh)
+                        cr = dif_pmax_x(cr, 0.95, -1e3);
+                        const T tpn = B0 * cr;
+                        SS(A.s_num + cell0 + l, num * (1.0 - cr));
+                        o1 = o1 + tp; o2 = o2 + tpn;
+                        if (catch_now) {
+                            const T cc = xdiv(T(1.0), avoid_zero(tp)) * tpn * B0;      // consconv * B0
+                            for (int j = 0; j < St.cx_n; j++) {
+                                const int x = tb[St.cx_off + j];
+                                if (!((xact >> x) & 1)) continue;
+                                T fx(0.0);
+                                for (int k = 0; k < nq; k++) {
+                                    const PairRec& Q = A.pp[tb[St.pp_off + k]];
+                                    const int ts = tb[Q.tsid_off + Cl.ridx];
+                                    if (ts >= 0 && ((Q.cxmask >> j) & 1)) fx = fx + cfac(Q, k, ts, l);
+                                }
+                                GS(A.xb[x].g_x + cell0 + l, fx * cc);
+                            }
+                        }
+                    }
+                    GS(Cl.g_usp, o1); GS(Cl.g_usp + 1, o2);
+                } else if (catch_now) {
+                    for (int j = 0; j < St.cx_n; j++) {
+                        const int x = tb[St.cx_off + j];
+                        if ((xact >> x) & 1)
+                            for (int l = 0; l < L; l++) GS(A.xb[x].g_x + cell0 + l, T(0.0));       // no landings: cons = 0
+                    }
+                }
+                if (!has_mort && grow_n < 0 && !inc_here && !ren_mask && xact == 0) continue;
+
+                // ---------- natural mortality and growth. Length growth only looks DOWN the length axis, so walking l
+                // from the top the update is in place: every source l - d is still the old value when l is rebuilt.
+                const T mortf = has_mort ? G(St.g_mort + idt * St.ncol + Cl.col) : T(1.0);
+                if (grow_n < 0) {
+                    for (int l = L - 1; l >= 0; l--) {
+                        const T num = S(A.s_num + cell0 + l) * mortf, wgt = S(A.s_wgt + cell0 + l);
+                        if (!inc_here) finish_cell(Cl, St, l, num, wgt, false, ren_mask);
+                        else SS(A.s_num + cell0 + l, num);
+                    }
+                    continue;
+                }
+                const int n1 = grow_n + 1;
+                const T wal = SLOT(I[St.grow_ioff + 3]);
+                const T remf = trans_now ? G(Cl.g_remf) : T(0.0);
+                const int bset = ((St.band_percol ? Cl.col : 0) * A.ndt + idt) * St.bsz;
+                const int gb = St.g_band + bset, gbr = St.g_bandr + bset;
+                const bool stash = trans_now && Cl.s_tn >= 0;
+                for (int l = L - 1; l >= 0; l--) {
+                    // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d
+                    const T pw_l = G(St.g_pw + l);
+                    const bool top = l == L - 1;
+                    T an(0.0), aw(0.0), bn(0.0), bw(0.0);
+#pragma unroll
+                    for (int d = 0; d < NW; d++) {
+                        if (d <= grow_n && d <= l) {
+                            const int src = l - d;
+                            const int be = top ? L * n1 + d : src * n1 + d;     // plus group: tail sums
+                            const T ns = S(A.s_num + cell0 + src) * mortf;
+                            const T gd = G(gb + be);
+                            const T dwd = wal * (pw_l - G(St.g_pw + src));      // walpha (l^wbeta - (l-d)^wbeta), R/action_grow.R:58-71
+                            const T wsrc = dwd + S(A.s_wgt + cell0 + src);
+                            if (cont_now) {
+                                const T grd = G(gbr + be);
+                                const T w = wsrc * ns;
+                                an = an + grd * ns; aw = aw + grd * w;
+                                bn = bn + gd * ns; bw = bw + gd * w;
+                            } else if (const_now) {
+                                // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
+                                const T ratio = G(St.g_cmat + Cl.col * L + src);
+                                const T m1 = (ns * ratio) * gd, m2 = (ns * (1.0 - ratio)) * gd;
+                                an = an + m1; aw = aw + wsrc * m1;
+                                bn = bn + m2; bw = bw + wsrc * m2;
+                            } else {
+                                const T m2 = ns * gd;
+                                bn = bn + m2; bw = bw + wsrc * m2;
+                            }
+                        }
+                    }
+                    T num = bn, wgt = xdiv(bw, avoid_zero(bn));
+                    if (trans_now) {
+                        if (stash) { SS(Cl.s_tn + l, an); SS(Cl.s_tw + l, xdiv(aw, avoid_zero(an))); }
+                        // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
+                        num = num + an * remf;
+                    }
+                    if (!inc_here) finish_cell(Cl, St, l, num, wgt, false, ren_mask);
+                    else { SS(A.s_num + cell0 + l, num); SS(A.s_wgt + cell0 + l, wgt); }
+                }
+            }
+
+            // ================= columns that receive maturing fish finish once every source column has grown
+            if ((A.inc_any_mask >> step) & 1) G3T_BAR();
+            for (int wi = wc0; wi < wc1; wi++) {
+                const ColRec& Cl = A.col[tb[wi]];
+                if (!(Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1))) continue;
+                const StockRec& St = A.st[Cl.s];
+                int ren_mask = 0;
+                for (int k = 0; k < St.n_renew; k++) {
+                    const int rs = I[St.renew_ioff + k * G3R_LEN + G3R_RUN_STEP];
+                    if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
+                }
+                for (int l = St.L - 1; l >= 0; l--)
+                    finish_cell(Cl, St, l, S(A.s_num + Cl.cell0 + l), S(A.s_wgt + Cl.cell0 + l), true, ren_mask);
+            }
+
+            // ================= g3l_distribution collect: model[dest] += lgmatrix . x (R/likelihood_distribution.R:288-364)
+            if (cact) {
+                G3T_BAR();
+                ucnt = 0;
+                for (int c = 0; c < A.NCOMP; c++) {
+                    if (!((cact >> c) & 1)) continue;
+                    const CompRec& Cm = A.comp[c];
+                    const int nd = Cm.n_dest;
+                    const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
+                    const int ms = Cm.g_ms + (si ? I[Cm.tidx_ioff + t] * nd : 0);
+                    const int xs = A.xb[Cm.xbuf].g_x;
+                    if (Cm.mode == 0) {
+                        const int32_t* ptr = I + Cm.csr_ptr_ioff;
+                        const int32_t* idx = I + Cm.csr_idx_ioff;
+                        const double* cf = R + Cm.csr_coef_roff;
+                        for (int e = 0; e < nd; e++) {
+                            if (!mine()) continue;
+                            T acc = G(ms + e);
+                            for (int j = ptr[e]; j < ptr[e + 1]; j++) acc = acc + cf[j] * G(xs + idx[j]);
+                            GS(ms + e, acc);
+                        }
+                    } else {
+                        const int32_t* cd = I + Cm.cell_dest_ioff;
+                        const double* cf = R + Cm.cell_coef_roff;
+                        for (int e = 0; e < nd; e++) {
+                            if (!mine()) continue;
+                            T acc = G(ms + e);
+                            for (int i = 0; i < A.NC; i++) if (cd[i] == e) acc = acc + cf[i] * G(xs + i);
+                            GS(ms + e, acc);
+                        }
+                    }
+                }
+                G3T_BAR();
+                // ================= g3l_distribution compare (R/likelihood_distribution.R:375-394): one warp per component
+                ucnt = 0;
+                for (int c = 0; c < A.NCOMP; c++) {
+                    if (!((cact >> c) & 1)) continue;
+                    const CompRec& Cm = A.comp[c];
+                    if (!I[Cm.cmp_ioff + t]) continue;
+                    if (!mine()) continue;
+                    const int ti = I[Cm.tidx_ioff + t];
+                    const int func = Cm.func, nd = Cm.n_dest, nt = Cm.n_times;
+                    const bool si = func == G3F_SI_LOG || func == G3F_SI_LINEAR;
+                    const int ms = Cm.g_ms + (si ? ti * nd : 0);
+                    const int nb = Cm.n_bins, nsl = Cm.n_slices, nag = Cm.n_areag;
+                    T cnll(0.0);
+                    if (func == G3F_SUMOFSQUARES) {     // R/likelihood_distribution.R:3-39
+                        const int per = nsl * nb;
+                        const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
+                        for (int ag = 0; ag < nag; ag++) {
+                            T tot(0.0);
+                            for (int e = 0; e < per; e++) tot = tot + G(ms + ag * per + e);
+                            const T rt = 1.0 / avoid_zero(tot);
+                            for (int sl = 0; sl < nsl; sl++) {
+                                T v(0.0);
+                                for (int e = 0; e < nb; e++) {
+                                    const int i = ag * per + sl * nb + e;
+                                    const T dlt = G(ms + i) * rt - op[i];
+                                    v = v + dlt * dlt;
+                                }
+                                cnll = cnll + v;
+                            }
+                        }
+                    } else if (func == G3F_MULTINOMIAL) {   // R/likelihood_distribution.R:41-60
+                        const double eps = R[Cm.param_roff];
+                        const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
+                        T likely(0.0);
+                        for (int sl = 0; sl < nag * nsl; sl++) {
+                            T tot(0.0);
+                            for (int e = 0; e < nb; e++) tot = tot + G(ms + sl * nb + e);
+                            const T at = avoid_zero(tot);
+                            for (int e = 0; e < nb; e++)
+                                likely = likely + op[sl * nb + e] * xlog(dif_pmax_c(G(ms + sl * nb + e) / at, 1.0 / (nb * eps), 1e4));
+                        }
+                        cnll = 2.0 * (-likely + A.obsconst[Cm.obsconst_off + ti]);
+                    } else if (func == G3F_SUMSQLOGRATIOS) {    // R/likelihood_distribution.R:127-136 (obsprop holds log(obs + eps))
+                        const double eps = R[Cm.param_roff];
+                        const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
+                        for (int e = 0; e < nd; e++) {
+                            const T dlt = op[e] - xlog(G(ms + e) + eps);
+                            cnll = cnll + dlt * dlt;
+                        }
+                    } else if (ti == nt - 1) {              // surveyindices: R/likelihood_distribution.R:82-125
+                        const double fa = R[Cm.param_roff], fb = R[Cm.param_roff + 1];
+                        const int series = Cm.g_ms;
+                        const double* op = A.obsprop + Cm.obs_off;
+                        for (int e = 0; e < nd; e++) {
+                            T sN(0.0); double sI = 0.0;
+                            for (int i = 0; i < nt; i++) {
+                                const T mv = G(series + i * nd + e);
+                                sN = sN + (func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv);
+                                sI += op[(size_t)i * nd + e];
+                            }
+                            const T mN = sN / (double)nt;
+                            const double mI = sI / (double)nt;
+                            T beta(fb), alpha(fa);
+                            if (isnan(fb)) {
+                                T sxy(0.0), sxx(0.0);
+                                for (int i = 0; i < nt; i++) {
+                                    const T mv = G(series + i * nd + e);
+                                    const T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
+                                    sxy = sxy + (op[(size_t)i * nd + e] - mI) * (N - mN); sxx = sxx + (N - mN) * (N - mN);
+                                }
+                                beta = sxy / avoid_zero(sxx);
+                            }
+                            if (isnan(fa)) alpha = mI - beta * mN;
+                            for (int i = 0; i < nt; i++) {
+                                const T mv = G(series + i * nd + e);
+                                const T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
+                                const T r = alpha + beta * N - op[(size_t)i * nd + e];
+                                cnll = cnll + r * r;
+                            }
+                        }
+                    }
+                    GS(A.g_cn + c, cnll);
+                    if (!si) for (int e = 0; e < nd; e++) GS(ms + e, T(0.0));     // zero counters for the next period
+                }
+            }
+            G3T_BAR();          // the step's state, collect sums and component values are complete
+
+            // ================= warp 0: the objective, in the reference's summation order
+            if (warp == 0) {
+                for (int c = 0; c < A.NCOMP; c++) {
+                    if (!((cact >> c) & 1)) continue;
+                    const CompRec& Cm = A.comp[c];
+                    if (!I[Cm.cmp_ioff + t]) continue;
+                    const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
+                    if (si && I[Cm.tidx_ioff + t] != Cm.n_times - 1) continue;      // survey indices score once, at their last time
+                    if (lane_on && ((cw_lane >> c) & 1)) {
+                        const T cnll = G(A.g_cn + c);
+                        nll = nll + mkpar_g<T>(prow, seed, Cm.weight_par) * cnll;
+                        GS(A.g_ctot + c, G(A.g_ctot + c) + cnll);
+                    }
+                }
+                // ---- g3l_understocking (R/likelihood_understocking.R:36-46)
+                if (have_us) {
+                    T us_tot(0.0);
+                    if (pred_now)
+                        for (int s = 0; s < NS; s++) {
+                            const StockRec& St = A.st[s];
+                            if (!St.us_flag || St.pp_n == 0) continue;
+                            T o1(0.0), o2(0.0);
+                            for (int col = 0; col < St.ncol; col++) { o1 = o1 + G(A.col[St.gcol0 + col].g_usp); o2 = o2 + G(A.col[St.gcol0 + col].g_usp + 1); }
+                            us_tot = us_tot + (o1 - o2);
+                        }
+                    const T u = (us_power == 2.0) ? us_tot * us_tot : xpow(us_tot, T(us_power));
+                    if (lane_on) {
+                        nll = nll + us_weight * u;
+                        GS(A.g_ctot + A.NNLL - 2, G(A.g_ctot + A.NNLL - 2) + u);
+                    }
+                }
+            }
+
+            // ================= g3a_age (R/action_age.R:51-85) + movement hand-off: length group by length group
+            if (final_step) {
+                bool age_any = false;
+                for (int s = 0; s < NS; s++) age_any = age_any || A.st[s].age_enable;
+                if (age_any) {
+                    for (int l = warp; l < A.maxL; l += W) {
+                        for (int s = 0; s < NS; s++) {
+                            const StockRec& St = A.st[s];
+                            if (!St.age_enable || l >= St.L) continue;
+                            const int L = St.L, nage = St.nage, narea = St.narea;
+                            for (int r = 0; r < narea; r++) {
+                                const int i = r * L + l;
+                                const int base = St.c0 + r * nage * L + l;
+                                const int top = base + (nage - 1) * L;
+                                const int nb_ = A.s_num, wb_ = A.s_wgt;
+                                if (St.age_n_out > 0) { SS(St.s_mv + i, S(nb_ + top)); SS(St.s_mv + narea * L + i, S(wb_ + top)); }
+                                if (nage == 1) {
+                                    if (St.age_n_out > 0) SS(nb_ + top, T(0.0));
+                                    continue;
+                                }
+                                if (St.age_n_out > 0) { SS(nb_ + top, S(nb_ + top - L)); SS(wb_ + top, S(wb_ + top - L)); }
+                                else {
+                                    const T n0 = S(nb_ + top), n1_ = S(nb_ + top - L);
+                                    SS(wb_ + top, ratio_add_pop(S(wb_ + top), n0, S(wb_ + top - L), n1_));
+                                    SS(nb_ + top, n0 + n1_);
+                                }
+                                for (int a = nage - 2; a >= 1; a--) {
+                                    SS(nb_ + base + a * L, S(nb_ + base + (a - 1) * L));
+                                    SS(wb_ + base + a * L, S(wb_ + base + (a - 1) * L));
+                                }
+                                SS(nb_ + base, T(0.0));
+                            }
+                        }
+                        for (int i = 0; i < A.n_agedst; i++) {
+                            const int4 e = A.agedst[i];     // (destination cell, stash entry num, stash entry wgt, ratio slot); same l
+                            if (e.x < 0 || tb[A.agedst_l_off + i] != l) continue;
+                            const T n0 = S(A.s_num + e.x);
+                            const T moved = S(e.y) * SLOT(e.w);
+                            SS(A.s_wgt + e.x, ratio_add_pop(S(A.s_wgt + e.x), n0, S(e.z), moved));
+                            SS(A.s_num + e.x, n0 + moved);
+                        }
+                    }
+                    G3T_BAR();
+                }
+            }
+        }   // time loop
+
+        if (warp == 0 && live) {
+            const T out = bad_time ? T(nan("")) : nll;
+            if (tile_t == 0) {
+                A.nll[b] = val(out);
+                if (A.comp_out) for (int c = 0; c < A.NNLL; c++) A.comp_out[b * A.NNLL + c] = bad_time ? nan("") : val(G(A.g_ctot + c));
+            }
+            if (NTAN > 0 && A.grad)
+                for (int k = 0; k < NTAN; k++)
+                    if (tile_t * NTAN + k < A.K) A.grad[b * A.K + tile_t * NTAN + k] = tan_of(out, k);
+        }
+    }
+#undef GP
+#undef SP
+#undef SLOT
+}
+
+#ifdef __CUDACC__
+template <class T, int NW, bool SMEM, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) eval_tile_kernel(const __grid_constant__ TArgs A) {
+    extern __shared__ __align__(16) double g3t_smem[];
+    tile_body<T, NW, SMEM>(A, g3t_smem, threadIdx.x >> 5, threadIdx.x & 31, blockIdx.x, gridDim.x);
+}
+#endif
+
+}  // namespace g3t

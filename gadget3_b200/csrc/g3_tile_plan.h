@@ -1,0 +1,451 @@
+// g3_tile_plan.h -- host-side planner of the tile kernel (g3_tile.cuh): turns the packed model spec
+// (include/g3cuda_spec.h) into the kernel's record tables, entry layouts (shared-memory state, per-CTA global
+// slab) and the column -> warp assignment. Pure C++ (no CUDA API): g3cuda.cu uploads the result, tests/emu
+// runs the kernel body on it on the CPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "g3_tile.cuh"
+
+namespace g3t {
+
+struct TilePlan {
+    bool ok = false;
+    std::string why;            // why the model does not fit the tile kernel
+    TArgs a{};                  // scalars and entry offsets; pointers are filled by whoever places the tables
+    std::vector<StockRec> st; std::vector<ColRec> col; std::vector<PairRec> pp; std::vector<PredRec> pred;
+    std::vector<TsRec> ts; std::vector<CompRec> comp; std::vector<XRec> xb; std::vector<int4> agedst;
+    std::vector<int32_t> tb;
+    std::vector<double> obsprop, obsconst;
+    std::vector<unsigned char> pred_active;
+    int n_s = 0;                // state entries per lane (shared memory, or after the G entries in the slab)
+    int maxn = 0;               // widest growth band (maxlengthgroupgrowth)
+    std::vector<double> col_cost;
+};
+
+inline double plan_avoid_zero(double a) {       // R/aab_env.R:24-31, for parameter-independent terms
+    const double p = a * 1000.0;
+    return (std::fmax(p, 0.0) + std::log1p(std::exp(-std::fabs(p)))) / 1000.0;
+}
+
+// column -> warp assignment for W warps: longest-processing-time greedy; returns the efficiency sum / (W * max load)
+inline double assign_columns(const std::vector<double>& cost, int W, std::vector<std::vector<int>>* out) {
+    std::vector<int> order(cost.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    std::vector<double> load(W, 0.0);
+    std::vector<std::vector<int>> cols(W);
+    double sum = 0.0;
+    for (int c : order) {
+        int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        load[w] += cost[c]; cols[w].push_back(c); sum += cost[c];
+    }
+    for (auto& v : cols) std::sort(v.begin(), v.end());
+    if (out) *out = cols;
+    const double mx = *std::max_element(load.begin(), load.end());
+    return mx > 0 ? sum / (W * mx) : 1.0;
+}
+
+// (re)build the warp lists of a plan for W warps; they live at the end of tb
+inline void plan_set_warps(TilePlan& P, int W) {
+    std::vector<std::vector<int>> cols;
+    assign_columns(P.col_cost, W, &cols);
+    P.tb.resize(P.a.wcol_off);
+    const int base = P.a.wcol_off;
+    P.tb.resize(base + W + 1);
+    for (int w = 0; w < W; w++) {
+        P.tb[base + w] = (int)P.tb.size();
+        for (int c : cols[w]) P.tb.push_back(c);
+    }
+    P.tb[base + W] = (int)P.tb.size();
+    P.a.W = W;
+    // per-warp scratch follows the other G entries
+    P.a.n_g = P.a.g_wscr + W * P.a.wscr_n;
+}
+
+inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0) {
+    TilePlan P;
+    TArgs& A = P.a;
+    auto fail = [&](const std::string& w) { P.ok = false; P.why = w; return P; };
+    A.NC = I[G3H_NCELL]; A.NS = I[G3H_NSTOCK]; A.NPP = I[G3H_NPP]; A.NPRED = I[G3H_NPRED]; A.NCOMP = I[G3H_NCOMP];
+    A.NX = I[G3H_NXBUF]; A.NSLOT = I[G3H_NSLOT]; A.NPAR = I[G3H_NPAR]; A.NT = I[G3H_NT]; A.NSTEPS = I[G3H_NSTEPS];
+    A.NNLL = I[G3H_NNLL]; A.NBOUND = I[G3H_NBOUND]; A.maxL = I[G3H_MAXL];
+    if (A.NCOMP > 32) return fail("more than 32 likelihood components");
+    if (A.NX > 32) return fail("more than 32 collect vectors");
+    if (A.NSTEPS > 31) return fail("more than 31 steps per year");
+    auto stock = [&](int s) { return I + I[G3H_STOCK_OFF] + s * G3S_LEN; };
+
+    // ---- distinct step lengths
+    A.ndt = 0;
+    for (int sy = 0; sy < A.NSTEPS; sy++) {
+        const int len = I[I[G3H_STEPLEN_OFF] + sy];
+        int k = 0;
+        while (k < A.ndt && A.dt_len[k] != len) k++;
+        if (k == A.ndt) { if (A.ndt == 4) return fail("more than 4 distinct step lengths"); A.dt_len[A.ndt++] = len; }
+        A.step_idt[sy] = k;
+    }
+
+    int ng = 0, ns = 0;
+    auto takeg = [&](int n) { int o = ng; ng += n; return o; };
+    auto takes = [&](int n) { int o = ns; ns += n; return o; };
+    A.g_slot = takeg(A.NSLOT);
+    A.s_num = takes(A.NC); A.s_wgt = takes(A.NC);
+
+    // ---- stocks and columns
+    P.st.resize(A.NS);
+    int maxnarea = 1, ncols = 0;
+    std::vector<int> stock_of_cell(A.NC), col_of_cell(A.NC), l_of_cell(A.NC);
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = stock(s);
+        StockRec& r = P.st[s];
+        r.L = St[G3S_L]; r.nage = St[G3S_NAGE]; r.narea = St[G3S_NAREA]; r.ncol = r.nage * r.narea; r.c0 = St[G3S_CELL_OFF];
+        r.gcol0 = ncols; ncols += r.ncol; r.minage = St[G3S_MINAGE];
+        r.grow_n = St[G3S_GROW_N]; r.mat_kind = St[G3S_MAT_KIND]; r.has_out = St[G3S_N_OUT] > 0; r.trans_mask = St[G3S_TRANS_MASK];
+        r.inc_steps = 0;
+        r.mort_ioff = St[G3S_MORT_OFF]; r.midlen_roff = St[G3S_MIDLEN_ROFF]; r.plusdl_roff = St[G3S_PLUSDL_ROFF];
+        r.grow_ioff = St[G3S_GROW_OFF]; r.mat_ioff = St[G3S_MAT_OFF]; r.init_ioff = St[G3S_INIT_OFF];
+        r.n_renew = St[G3S_N_RENEW]; r.renew_ioff = St[G3S_RENEW_OFF];
+        if (r.n_renew > 30) return fail("more than 30 renewal actions on one stock");
+        maxnarea = std::max(maxnarea, r.narea);
+        P.maxn = std::max(P.maxn, r.grow_n);
+        r.g_mort = takeg(r.mort_ioff >= 0 ? r.ncol * A.ndt : 0);
+        r.g_rd = takeg(r.n_renew * r.L); r.g_rw = takeg(r.n_renew * r.L);
+        r.g_pw = takeg(r.grow_n >= 0 ? r.L : 0);
+        const bool trans = r.grow_n >= 0 && r.has_out;
+        const bool cont = trans && r.mat_kind == G3MAT_CONTINUOUS;
+        r.band_percol = cont && I[r.mat_ioff + 2] >= 0;         // age term: M0 differs per column (R/action_mature.R:18,44-74)
+        r.bsz = r.grow_n >= 0 ? (r.L + 1) * (r.grow_n + 1) : 0;
+        const int nset = r.band_percol ? r.ncol : 1;
+        r.g_band = takeg(nset * A.ndt * r.bsz);
+        r.g_bandr = cont ? takeg(nset * A.ndt * r.bsz) : r.g_band;
+        r.g_cmat = (trans && r.mat_kind == G3MAT_CONSTANT) ? takeg(r.ncol * r.L) : -1;
+        r.mig_ioff = St[G3S_MIGRATE_OFF]; r.mig_steps = 0;
+        r.g_mig = r.mig_ioff >= 0 ? takeg(A.NSTEPS * r.narea * r.narea) : 0;
+        if (r.mig_ioff >= 0)
+            for (int sy = 0; sy < A.NSTEPS; sy++) for (int i = 0; i < r.narea * r.narea; i++)
+                if (I[r.mig_ioff + sy * r.narea * r.narea + i] >= 0) r.mig_steps |= 1 << sy;
+        r.age_enable = St[G3S_AGE_ENABLE]; r.age_n_out = St[G3S_AGE_N_OUT]; r.s_mv = -1;
+        r.us_flag = 0;
+        for (int col = 0; col < r.ncol; col++) for (int l = 0; l < r.L; l++) {
+            const int c = r.c0 + col * r.L + l;
+            stock_of_cell[c] = s; col_of_cell[c] = col; l_of_cell[c] = l;
+        }
+    }
+    for (int i = 0; i < I[G3H_US_N]; i++) P.st[I[I[G3H_US_OFF] + i]].us_flag = 1;
+    if (P.maxn > 15) return fail("maxlengthgroupgrowth above 15");
+    A.NCOLS = ncols;
+
+    // ---- maturation hand-over (R/action_mature.R:78-134) per cell, then per column
+    std::vector<int> inc_src(A.NC, -1), inc_slot(A.NC, -1), inc_mask(A.NC, 0);
+    std::vector<std::vector<int>> rem(A.NC);
+    for (int s = 0; s < A.NS; s++) {
+        const int32_t* St = stock(s);
+        const StockRec& r = P.st[s];
+        if (!(r.grow_n >= 0 && r.has_out)) continue;
+        const int ncell = r.L * r.ncol;
+        for (int i = 0; i < ncell; i++)
+            for (int o = 0; o < St[G3S_N_OUT]; o++) {
+                const int d = I[St[G3S_OUT_MAP_OFF] + o * ncell + i];
+                if (d < 0) continue;
+                const int slot = I[St[G3S_OUT_OFF] + 2 * o + 1];
+                if (inc_src[d] >= 0) return fail("a cell receives maturing fish from more than one source");
+                inc_src[d] = r.c0 + i; inc_slot[d] = slot; inc_mask[d] = r.trans_mask;
+                rem[r.c0 + i].push_back(slot);
+            }
+    }
+    P.col.resize(ncols);
+    A.inc_any_mask = 0;
+    int ntr = 0;        // S entries of the maturing fish in flight (tn then tw per stashing column)
+    const int s_x0 = ns;        // start of the transient region (tn/tw; reused by the ageing movement stash)
+    for (int s = 0; s < A.NS; s++) {
+        const StockRec& r = P.st[s];
+        for (int col = 0; col < r.ncol; col++) {
+            ColRec& c = P.col[r.gcol0 + col];
+            c.s = s; c.col = col; c.aidx = col % r.nage; c.ridx = col / r.nage; c.cell0 = r.c0 + col * r.L;
+            c.s_tn = c.s_tw = -1; c.inc_tn = c.inc_tw = c.inc_slot = -1; c.inc_mask = 0;
+            c.g_remf = takeg(1); c.g_usp = takeg(2);
+            // remainder ratios must be the same down a column
+            for (int l = 1; l < r.L; l++)
+                if (rem[c.cell0 + l] != rem[c.cell0]) return fail("maturation outputs differ between the lengths of one column");
+            c.rem_off = (int)P.tb.size();
+            for (int sl : rem[c.cell0]) P.tb.push_back(sl);
+            P.tb.push_back(-1);
+            if (!rem[c.cell0].empty()) { c.s_tn = s_x0 + ntr; c.s_tw = s_x0 + ntr + r.L; ntr += 2 * r.L; }
+        }
+    }
+    for (int gc = 0; gc < ncols; gc++) {        // arrivals: every cell of a destination column is fed by the same length of ONE source column
+        ColRec& c = P.col[gc];
+        const StockRec& r = P.st[c.s];
+        const int c00 = c.cell0;
+        if (inc_src[c00] >= 0) {
+            const int src = inc_src[c00];
+            if (l_of_cell[src] != 0) return fail("maturing fish change length group on hand-over");
+            const ColRec& sc = P.col[P.st[stock_of_cell[src]].gcol0 + col_of_cell[src]];
+            if (P.st[sc.s].L != r.L) return fail("maturation between stocks of different length grids");
+            c.inc_tn = sc.s_tn; c.inc_tw = sc.s_tw; c.inc_slot = inc_slot[c00]; c.inc_mask = inc_mask[c00];
+            A.inc_any_mask |= c.inc_mask;
+        }
+        for (int l = 0; l < r.L; l++) {
+            const int cc = c00 + l;
+            const bool ok = inc_src[c00] < 0 ? inc_src[cc] < 0
+                                             : (inc_src[cc] == inc_src[c00] + l && inc_slot[cc] == inc_slot[c00] && inc_mask[cc] == inc_mask[c00]);
+            if (!ok) return fail("maturation hand-over is not column to column");
+        }
+    }
+    // one renewal per (column, step) is what finish_cell applies in a defined order
+    for (int s = 0; s < A.NS; s++) {
+        const StockRec& r = P.st[s];
+        for (int k = 0; k < r.n_renew; k++) for (int k2 = k + 1; k2 < r.n_renew; k2++) {
+            const int32_t* Ra = I + r.renew_ioff + k * G3R_LEN; const int32_t* Rb = I + r.renew_ioff + k2 * G3R_LEN;
+            if (Ra[G3R_AGE_IDX] == Rb[G3R_AGE_IDX] && (Ra[G3R_RUN_STEP] == 0 || Rb[G3R_RUN_STEP] == 0 || Ra[G3R_RUN_STEP] == Rb[G3R_RUN_STEP]))
+                return fail("two renewals into the same age at the same step");
+        }
+    }
+    // ---- ageing movement (R/action_age.R:16-20,57-63): stash of the oldest column per (area, l), destinations
+    int nmv = 0;
+    for (int s = 0; s < A.NS; s++) {
+        StockRec& r = P.st[s];
+        if (r.age_enable && r.age_n_out > 0) { r.s_mv = s_x0 + nmv; nmv += 2 * r.narea * r.L; }
+    }
+    takes(std::max(ntr, nmv));
+    {
+        std::vector<int> age_src(A.NC, -1);
+        std::vector<int32_t> agedst_l;
+        for (int s = 0; s < A.NS; s++) {
+            const int32_t* St = stock(s);
+            const StockRec& r = P.st[s];
+            if (!r.age_enable) continue;
+            for (int o = 0; o < r.age_n_out; o++) for (int ar = 0; ar < r.narea; ar++) for (int l = 0; l < r.L; l++) {
+                const int d = I[St[G3S_AGE_MAP_OFF] + (o * r.narea + ar) * r.L + l];
+                if (d < 0) continue;
+                if (age_src[d] >= 0) return fail("a cell receives ageing fish from more than one source");
+                if (l_of_cell[d] != l) return fail("ageing fish change length group on hand-over");
+                age_src[d] = 1;
+                const int i = ar * r.L + l;
+                P.agedst.push_back(make_int4(d, r.s_mv + i, r.s_mv + r.narea * r.L + i, I[St[G3S_AGE_OUT_OFF] + 2 * o + 1]));
+                agedst_l.push_back(l);
+            }
+        }
+        // the kernel walks destinations in cell order within a length group (the thread kernel's order)
+        std::vector<int> ord(P.agedst.size());
+        for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return P.agedst[x].x < P.agedst[y].x; });
+        std::vector<int4> ad2; std::vector<int32_t> al2;
+        for (int i : ord) { ad2.push_back(P.agedst[i]); al2.push_back(agedst_l[i]); }
+        P.agedst = ad2;
+        A.n_agedst = (int)P.agedst.size();
+        A.agedst_l_off = (int)P.tb.size();
+        for (int v : al2) P.tb.push_back(v);
+        if (P.agedst.empty()) P.agedst.push_back(make_int4(-1, 0, 0, 0));
+    }
+
+    // ---- collect vectors
+    P.xb.resize(std::max(A.NX, 1));
+    std::vector<unsigned> x_ppmask(std::max(A.NX, 1), 0);
+    for (int x = 0; x < A.NX; x++) {
+        const int32_t* X = I + I[G3H_XBUF_OFF] + x * G3X_LEN;
+        P.xb[x].kind = X[G3X_KIND]; P.xb[x].unit = X[G3X_UNIT]; P.xb[x].g_x = takeg(A.NC);
+        for (int j = 0; j < X[G3X_N_PP]; j++) {
+            const int q = I[X[G3X_PP_OFF] + j];
+            if (q >= 32) return fail("more than 32 predator-prey pairs feed collect vectors");
+            x_ppmask[x] |= 1u << q;
+        }
+    }
+    A.ax_off = (int)P.tb.size(); A.ax_n = 0;
+    for (int x = 0; x < A.NX; x++) if (P.xb[x].kind != 0) { P.tb.push_back(x); A.ax_n++; }
+
+    // ---- predators, pairs, total-suitability accumulators
+    P.pred.resize(std::max(A.NPRED, 1));
+    std::vector<int> pred_ts_base(std::max(A.NPRED, 1), -1);
+    int nts = 0;
+    for (int p = 0; p < A.NPRED; p++) {
+        const int32_t* Pr = I + I[G3H_PRED_OFF] + p * G3P_LEN;
+        PredRec& r = P.pred[p];
+        r.kind = Pr[G3P_KIND]; r.stock = Pr[G3P_STOCK]; r.slot_ioff = Pr[G3P_SLOT_OFF]; r.narea = Pr[G3P_NAREA];
+        r.g_pts = r.g_pmc = 0; r.list_off = 0;
+        if (r.kind == G3PRED_STOCK) {
+            const StockRec& Pp = P.st[r.stock];
+            r.g_pts = takeg(Pp.narea * Pp.L); r.g_pmc = takeg(Pp.L);
+            continue;
+        }
+        if (r.kind != G3PRED_TOTALFLEET && r.kind != G3PRED_NUMBERFLEET && r.kind != G3PRED_LINEARFLEET && r.kind != G3PRED_EFFORTFLEET)
+            return fail("predator kind " + std::to_string(r.kind) + " is not supported");
+        pred_ts_base[p] = nts;
+        for (int k = 0; k < r.narea; k++) P.ts.push_back(TsRec{r.kind, Pr[G3P_E_ROFF] + k, r.narea, 0, 0});
+        nts += r.narea;
+    }
+    A.NTS = nts;
+    A.g_eot = takeg(nts);
+    P.pp.resize(std::max(A.NPP, 1));
+    std::vector<std::vector<int>> pp_of_stock(A.NS);
+    for (int q = 0; q < A.NPP; q++) {
+        const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
+        const PredRec& Pr = P.pred[Q[G3PP_PRED]];
+        const StockRec& Ps = P.st[Q[G3PP_PREY]];
+        PairRec& r = P.pp[q];
+        r.pred = Q[G3PP_PRED]; r.prey = Q[G3PP_PREY]; r.suit_kind = Q[G3PP_SUIT_KIND]; r.suit_ioff = Q[G3PP_SUIT_OFF];
+        r.energy_slot = Q[G3PP_ENERGY]; r.pred_kind = Pr.kind; r.pred_stock = Pr.kind == G3PRED_STOCK ? Pr.stock : -1;
+        r.PL = Pr.kind == G3PRED_STOCK ? P.st[Pr.stock].L : 1;
+        const int sk = r.suit_kind;
+        if (sk == G3SUIT_ANDERSEN || sk == G3SUIT_EXPONENTIAL || sk == G3SUIT_RICHARDS) {
+            if (Pr.kind != G3PRED_STOCK) return fail("suitability kind " + std::to_string(sk) + " reads predator_length: it needs a stock predator");
+        } else if (sk < 0 || sk > G3SUIT_RICHARDS) return fail("suitability kind " + std::to_string(sk) + " is not supported");
+        r.g_suit = takeg(r.PL * Ps.L);
+        r.g_part = takeg(Ps.ncol * r.PL);
+        r.cxmask = 0;
+        r.tsid_off = (int)P.tb.size();
+        for (int ar = 0; ar < Ps.narea; ar++) {
+            const int area = I[stock(r.prey)[G3S_AREA_OFF] + ar];
+            int id = -1;
+            const int32_t* Prr = I + I[G3H_PRED_OFF] + r.pred * G3P_LEN;
+            for (int k = 0; k < Pr.narea; k++)
+                if (I[Prr[G3P_AREA_OFF] + k] == area) id = Pr.kind == G3PRED_STOCK ? k : pred_ts_base[r.pred] + k;
+            P.tb.push_back(id);
+        }
+        pp_of_stock[r.prey].push_back(q);
+    }
+    int max_nq = 1;
+    for (int s = 0; s < A.NS; s++) {
+        StockRec& r = P.st[s];
+        r.pp_off = (int)P.tb.size(); r.pp_n = (int)pp_of_stock[s].size();
+        max_nq = std::max(max_nq, r.pp_n);
+        for (int q : pp_of_stock[s]) P.tb.push_back(q);
+        // catch collect vectors fed by this stock's pairs
+        r.cx_off = (int)P.tb.size(); r.cx_n = 0;
+        for (int x = 0; x < A.NX; x++) {
+            if (P.xb[x].kind != 0) continue;
+            bool fed = false;
+            for (int q : pp_of_stock[s]) if ((x_ppmask[x] >> q) & 1) fed = true;
+            if (!fed) continue;
+            if (r.cx_n == 32) return fail("more than 32 catch collect vectors on one stock");
+            for (int q : pp_of_stock[s]) if ((x_ppmask[x] >> q) & 1) P.pp[q].cxmask |= 1 << r.cx_n;
+            P.tb.push_back(x); r.cx_n++;
+        }
+    }
+    // summation lists of the totals, in the reference's order: prey stock, pair, column
+    for (int k = 0; k < nts; k++) {
+        TsRec& T = P.ts[k];
+        T.list_off = (int)P.tb.size(); T.list_n = 0;
+        for (int s = 0; s < A.NS; s++)
+            for (int q : pp_of_stock[s]) {
+                const PairRec& r = P.pp[q];
+                if (r.pred_kind != G3PRED_TOTALFLEET && r.pred_kind != G3PRED_NUMBERFLEET) continue;
+                for (int col = 0; col < P.st[s].ncol; col++)
+                    if (P.tb[r.tsid_off + col / P.st[s].nage] == k) { P.tb.push_back(r.g_part + col); T.list_n++; }
+            }
+    }
+    if (P.ts.empty()) P.ts.push_back(TsRec{0, 0, 0, 0, 0});
+    for (int p = 0; p < A.NPRED; p++) {
+        PredRec& Pr = P.pred[p];
+        if (Pr.kind != G3PRED_STOCK) continue;
+        const StockRec& Pp = P.st[Pr.stock];
+        std::vector<std::vector<int>> lists(Pp.narea);
+        for (int s = 0; s < A.NS; s++)
+            for (int q : pp_of_stock[s]) {
+                const PairRec& r = P.pp[q];
+                if (r.pred != p) continue;
+                for (int col = 0; col < P.st[s].ncol; col++) {
+                    const int pr = P.tb[r.tsid_off + col / P.st[s].nage];
+                    if (pr >= 0) lists[pr].push_back(r.g_part + col * r.PL);
+                }
+            }
+        Pr.list_off = (int)P.tb.size();
+        P.tb.resize(P.tb.size() + 2 * Pp.narea);
+        for (int pr = 0; pr < Pp.narea; pr++) {
+            P.tb[Pr.list_off + 2 * pr] = (int)P.tb.size();
+            P.tb[Pr.list_off + 2 * pr + 1] = (int)lists[pr].size();
+            for (int e : lists[pr]) P.tb.push_back(e);
+        }
+    }
+    // steps with predation: some landing is non-zero, or a stock predator exists (it eats every step)
+    P.pred_active.assign(A.NT, 0);
+    for (int p = 0; p < A.NPRED; p++) {
+        const int32_t* Pr = I + I[G3H_PRED_OFF] + p * G3P_LEN;
+        if (Pr[G3P_KIND] == G3PRED_STOCK) { std::fill(P.pred_active.begin(), P.pred_active.end(), 1); continue; }
+        for (int k = 0; k < Pr[G3P_NAREA]; k++)
+            for (int t = 0; t < A.NT; t++)
+                if (R[Pr[G3P_E_ROFF] + (size_t)t * Pr[G3P_NAREA] + k] != 0.0) P.pred_active[t] = 1;
+    }
+
+    // ---- likelihood components and their parameter-independent observation terms
+    P.comp.resize(std::max(A.NCOMP, 1));
+    for (int c = 0; c < A.NCOMP; c++) {
+        const int32_t* Cm = I + I[G3H_COMP_OFF] + c * G3C_LEN;
+        CompRec& r = P.comp[c];
+        r.func = Cm[G3C_FUNC]; r.weight_par = Cm[G3C_WEIGHT_PAR]; r.xbuf = Cm[G3C_XBUF]; r.mode = Cm[G3C_MODE];
+        r.n_dest = Cm[G3C_N_DEST]; r.n_bins = Cm[G3C_N_BINS]; r.n_slices = Cm[G3C_N_SLICES]; r.n_areag = Cm[G3C_N_AREAG];
+        r.csr_ptr_ioff = Cm[G3C_CSR_PTR_OFF]; r.csr_idx_ioff = Cm[G3C_CSR_IDX_OFF]; r.csr_coef_roff = Cm[G3C_CSR_COEF_ROFF];
+        r.cell_dest_ioff = Cm[G3C_CELL_DEST_OFF]; r.cell_coef_roff = Cm[G3C_CELL_COEF_ROFF];
+        r.tidx_ioff = Cm[G3C_TIDX_OFF]; r.cmp_ioff = Cm[G3C_CMP_OFF]; r.n_times = Cm[G3C_N_TIMES]; r.param_roff = Cm[G3C_PARAM_ROFF];
+        if (r.func < 0 || r.func > G3F_SUMSQLOGRATIOS) return fail("likelihood function " + std::to_string(r.func) + " is not supported");
+        const bool si = r.func == G3F_SI_LOG || r.func == G3F_SI_LINEAR;
+        r.g_ms = takeg(r.n_dest * (si ? r.n_times : 1));
+        r.obs_off = (int)P.obsprop.size(); r.obsconst_off = (int)P.obsconst.size();
+        const double* obs = R + Cm[G3C_OBS_ROFF];
+        const int nd = r.n_dest, nb = r.n_bins, nsl = r.n_slices, nag = r.n_areag;
+        for (int t = 0; t < r.n_times; t++) {
+            double cst = 0.0;
+            for (int ag = 0; ag < nag; ag++) {
+                double tot = 0.0;
+                for (int i = 0; i < nsl * nb; i++) tot += obs[(size_t)t * nd + ag * nsl * nb + i];
+                const double az = plan_avoid_zero(tot);
+                for (int i = 0; i < nsl * nb; i++) {
+                    const double o = obs[(size_t)t * nd + ag * nsl * nb + i];
+                    double v = o;
+                    if (r.func == G3F_SUMOFSQUARES) v = o / az;                          // R/likelihood_distribution.R:12-27
+                    else if (r.func == G3F_SI_LOG) v = std::log(plan_avoid_zero(o));     // R/likelihood_distribution.R:86
+                    else if (r.func == G3F_SUMSQLOGRATIOS) v = std::log(o + R[r.param_roff]);    // R/likelihood_distribution.R:131
+                    P.obsprop.push_back(v);
+                }
+                if (r.func == G3F_MULTINOMIAL)
+                    for (int sl = 0; sl < nsl; sl++) {      // sum(lgamma(1 + data)) - lgamma(1 + sum(data))
+                        double so = 0, slg = 0;
+                        for (int b = 0; b < nb; b++) { const double o = obs[(size_t)t * nd + (ag * nsl + sl) * nb + b]; so += o; slg += std::lgamma(1 + o); }
+                        cst += slg - std::lgamma(1 + so);
+                    }
+            }
+            P.obsconst.push_back(cst);
+        }
+    }
+    if (P.obsprop.empty()) P.obsprop.push_back(0.0);
+    if (P.obsconst.empty()) P.obsconst.push_back(0.0);
+    A.g_cn = takeg(std::max(A.NCOMP, 1));
+    A.g_ctot = takeg(A.NNLL);
+    A.g_bterm = takeg(A.NBOUND);
+    A.wscr_n = std::max({2 * maxnarea, max_nq, 1});
+    A.g_wscr = ng;
+    P.n_s = ns;
+
+    // ---- column costs (relative): growth with its avoid_zero per cell dominates; the maturing split doubles it
+    P.col_cost.resize(ncols);
+    for (int gc = 0; gc < ncols; gc++) {
+        const StockRec& r = P.st[P.col[gc].s];
+        const bool cont = r.grow_n >= 0 && r.has_out && r.mat_kind != G3MAT_NONE;
+        double c = r.grow_n >= 0 ? (1.0 + 0.08 * (r.grow_n + 1)) * (cont && P.col[gc].s_tn >= 0 ? 2.0 : (cont ? 1.5 : 1.0)) : 0.15;
+        if (P.col[gc].inc_tn >= 0) c += 0.7;
+        if (r.pp_n > 0) c += 0.4;
+        P.col_cost[gc] = c * r.L;
+    }
+    A.wcol_off = (int)P.tb.size();
+    int W = want_W;
+    if (W <= 0) {
+        // as many warps as columns up to 16; beyond that the best-balanced count in 8..16
+        if (ncols <= 16) W = ncols;
+        else {
+            double best = -1.0;
+            for (int w = 8; w <= 16; w++) {
+                const double e = assign_columns(P.col_cost, w, nullptr) * (0.75 + 0.25 * w / 16.0);
+                if (e > best + 1e-12) { best = e; W = w; }
+            }
+        }
+    }
+    W = std::max(1, std::min({W, ncols, 32}));
+    plan_set_warps(P, W);
+    P.ok = true;
+    return P;
+}
+
+}  // namespace g3t

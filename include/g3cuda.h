@@ -84,13 +84,24 @@ int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B,
                              double* d_nll, double* d_nll_comp, double* d_grad,
                              void* stream);
 
-/* Kernel selection, for tests and profiling: 0 = automatic (default), 1 = CTA-per-evaluation
- * kernel, 2 = warp-per-evaluation kernel, 3 = thread-per-evaluation kernel (G3CUDA_EUNSUPP if
- * the model does not fit the requested one). Automatic: batches below 12,288 evaluations go to the
- * CTA-per-evaluation kernel when the model fits it (latency: ~1 ms for one vector), larger ones to
- * the thread-per-evaluation kernel (throughput); the two agree to rounding, not to the bit.
+/* Kernel selection, for tests and profiling: 0 = automatic (default), 3 = thread-per-evaluation kernel,
+ * 4 = tile kernel (G3CUDA_EUNSUPP if the model does not fit the requested one; other values: G3CUDA_EINVAL).
+ * Automatic: value batches of any size run on the tile kernel (one CTA owns 32 evaluations for the whole time
+ * loop, stock state in shared memory; few vectors are spread over the SMs, so a single fn(par) is a ~ms call);
+ * gradient batches run on the tile kernel when small and on the thread kernel when large; g3cuda_report always
+ * runs on the thread kernel. The kernels agree to rounding, not to the bit.
  * All are CUDA; there is no CPU path to select. */
 int g3cuda_set_kernel(g3cuda_model* m, int which);
+
+/* Tuning hook: warps per tile of the tile kernel (columns of the stocks are dealt to the warps); 0 restores the
+ * planner's choice. Results do not depend on it to the bit except through the order of per-column partial sums,
+ * which is fixed (column order), i.e. they do not depend on it at all. */
+int g3cuda_set_tile_warps(g3cuda_model* m, int warps);
+
+/* Introspection for tests and bench.py: out[0] = the model fits the tile kernel, out[1] = warps per tile,
+ * out[2] = per-evaluation table entries in the CTA's global slab, out[3] = per-evaluation state entries,
+ * out[4] = the state of a value run fits shared memory, out[5] = the model fits the thread kernel. */
+int32_t g3cuda_tile_info(const g3cuda_model* m, int32_t* out);
 
 /* Number of kernels launched by this handle so far (bench.py gpu_launches). */
 int64_t g3cuda_launch_count(const g3cuda_model* m);
@@ -108,8 +119,7 @@ float g3cuda_last_kernel_ms(g3cuda_model* m);
  *   of g3a_report_detail, R/action_report.R:177-213)
  *   then per component: model array [n_times][n_dest] (canonical dest layout)
  *   then per component: 2 doubles (surveyindices alpha, beta; NaN otherwise)
- *   then the rest of g3a_report_detail (R/action_report.R:177-213), written by the
- *   thread-per-evaluation kernel (NaN if the report was forced onto the CTA kernel):
+ *   then the rest of g3a_report_detail (R/action_report.R:177-213):
  *     per stock: renewalnum [NT][cells]                       (detail_<stock>__renewalnum)
  *     per predator-prey pair, in packed pair order:
  *       suitability [predator length groups (1 for a fleet)][prey L]   (suit_<prey>_<pred>__report)
@@ -127,6 +137,8 @@ double g3cuda_fp64_peak_tflops(int device);
  *   which = 0: logspace_add(x[i], y[i])          (R/aab_env.R:16-19)
  *   which = 1: avoid_zero(x[i])                  (R/aab_env.R:24-31; y ignored)
  *   which = 2: dif_pmin(x[i], y[i], 1e3)         (R/env_dif.R:37-47)
+ *   which = 3: avoid_zero(x[i]) in the exact-division form the predation step uses
+ *   which = 4: dif_pmin(x[i], y[i], 1e3) in the exact-division form
  * for n HOST values into out (HOST). Returns 0 or a negative G3CUDA_E* code. */
 int g3cuda_math_probe(int device, int which, const double* x, const double* y, int64_t n, double* out);
 

@@ -1,0 +1,81 @@
+"""Kernel-logic tests of the tile kernel WITHOUT a GPU: the body of gadget3_b200/csrc/g3_tile.cuh compiled by g++
+(tests/emu/g3emu.cpp), one OS thread per warp with a real barrier, on the tables the product's planner builds,
+against the CPU oracle. This checks barrier placement, table layouts, the column -> warp assignment and the index
+arithmetic; the device arithmetic itself (exp, reciprocal, FMA contraction) is what the `-m gpu` tests pin.
+The harness is test infrastructure: the product library never loads it."""
+import numpy as np
+import pytest
+
+from gadget3_b200.configs import CONFIGS, parameter_batch
+from oracle.oracle_lib import Oracle
+from _util import US_WEIGHT, us_tolerance
+
+emu = pytest.importorskip("emu.emu_lib")
+
+
+def _setup(name, B, seed=2026):
+    model, p = CONFIGS[name]()
+    ints, reals = model.pack(p)
+    opt = p.optimised_indices()
+    full = np.tile(p.values(), (B, 1))
+    full[:, opt] = parameter_batch(p, B, seed=seed)
+    return model, p, ints, reals, full, opt
+
+
+@pytest.mark.parametrize("smem", [True, False], ids=["state_in_smem", "state_in_slab"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C4", "C5", "LING", "MINI_ANDERSEN", "MINI_SUITS", "MINI_FLEETS"])
+def test_values_and_components(oracle_lib, name, smem):
+    model, p, ints, reals, full, _ = _setup(name, 6)
+    o_nll, o_comp, _ = Oracle(ints, reals).eval_batch(full, want_comp=True, nthreads=4)
+    g_nll, g_comp, _ = emu.eval_batch(ints, reals, full, want_comp=True, smem_state=smem, lanes_per_tile=4, ncta=2)
+    ncomp = len(model.comp_names)
+    assert (np.abs(g_comp[:, :ncomp] - o_comp[:, :ncomp]) <= 1e-10 * np.abs(o_comp[:, :ncomp])).all()
+    assert (np.abs(g_comp[:, -1] - o_comp[:, -1]) <= 1e-10 * np.abs(o_comp[:, -1])).all()
+    us_tol = us_tolerance(model, p, o_comp[:, -2])
+    assert (np.abs(g_comp[:, -2] - o_comp[:, -2]) <= us_tol).all()
+    assert (np.abs(g_nll - o_nll) <= 1e-10 * np.abs(o_nll) + US_WEIGHT * us_tol).all()
+    if name in ("C1", "C2", "C4", "C5", "LING"):
+        assert (np.abs(g_nll - o_nll) / np.abs(o_nll)).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C5", "LING"])
+def test_gradients(oracle_lib, name):
+    model, p, ints, reals, full, opt = _setup(name, 2, seed=77)
+    tidx = opt[:6].astype(np.int32) if name != "C1" else opt[:10].astype(np.int32)       # 2-3 direction tiles
+    o_nll, _, o_grad = Oracle(ints, reals).eval_batch(full, tangent_idx=tidx, nthreads=4)
+    g_nll, g_comp, g_grad = emu.eval_batch(ints, reals, full, tangent_idx=tidx, want_comp=True, smem_state=False,
+                                           lanes_per_tile=3, ncta=2)
+    assert (np.abs(g_nll - o_nll) / np.abs(o_nll)).max() < 1e-10
+    scale = np.abs(o_grad).max(axis=1, keepdims=True)
+    assert (np.abs(g_grad - o_grad) / scale).max() < 1e-8
+
+
+def test_warp_count_does_not_change_a_bit(oracle_lib):
+    """Columns are dealt to the warps differently, but every sum has a fixed (column) order."""
+    model, p, ints, reals, full, _ = _setup("C2", 3)
+    ref = emu.eval_batch(ints, reals, full, want_comp=True)
+    for W in (1, 4, 9):
+        got = emu.eval_batch(ints, reals, full, want_comp=True, W=W)
+        assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all()
+    info = emu.plan_info(ints, reals)
+    assert info["W"] == 13 and info["ncols"] == 13 and info["n_s"] == 2 * 260 + 2 * 3 * 20
+
+
+def test_tiles_lanes_and_ragged_end(oracle_lib):
+    """Lane, tile and CTA indexing: 7 vectors in tiles of 3 over 2 persistent CTAs == the same vectors alone."""
+    model, p, ints, reals, full, _ = _setup("C1", 7)
+    ref = emu.eval_batch(ints, reals, full, lanes_per_tile=1, ncta=1)[0]
+    got = emu.eval_batch(ints, reals, full, lanes_per_tile=3, ncta=2)[0]
+    assert (got == ref).all()
+
+
+def test_nan_for_negative_retro_years_is_per_lane(oracle_lib):
+    """R/action_time.R:78-79: a vector with retro_years < 0 returns NaN; its neighbours in the tile do not."""
+    model, p, ints, reals, full, _ = _setup("C1", 4)
+    full[2, p.index("retro_years")] = -1
+    full[3, p.index("retro_years")] = 2          # a shorter run in the same tile
+    o = Oracle(ints, reals).eval_batch(full)[0]
+    g = emu.eval_batch(ints, reals, full, lanes_per_tile=4, ncta=1)[0]
+    assert np.isnan(g[2]) and np.isnan(o[2])
+    ok = [0, 1, 3]
+    assert (np.abs(g[ok] - o[ok]) / np.abs(o[ok])).max() < 1e-10
