@@ -15,7 +15,8 @@ from . import (g3_areas, g3_fleet, g3_init_val, g3_parameterized, g3_stock, g3_t
                g3a_predate_catchability_totalfleet, g3a_predate_fleet, g3a_renewal_normalcv,
                g3a_renewal_normalparam, g3a_renewal_vonb_recl, g3a_report_detail, g3a_time,
                g3l_abundancedistribution, g3l_bounds_penalty, g3l_catchdistribution,
-               g3l_distribution_sumofsquares, g3l_distribution_surveyindices_log, g3l_understocking,
+               g3l_distribution_multinomial, g3l_distribution_sumofsquares, g3l_distribution_surveyindices_linear,
+               g3l_distribution_surveyindices_log, g3l_understocking,
                g3s_age, g3s_livesonareas, g3_suitability_exponentiall50)
 
 
@@ -80,10 +81,13 @@ def _fleet_data(rng, years, landings_mean, landings_sd, n_ldist, len_breaks, n_a
     return out
 
 
-def build_c1(seed=123, data=None):
+def build_c1(seed=123, data=None, likelihood="sumofsquares"):
     """introduction-single-stock (vignettes/introduction-single-stock.Rmd:116-596, 666-701).
     `data`: the fleet tables (landings, ldist, aldist, si as column dicts) to use instead of the synthetic
-    draws -- tools/replay_tmb_bundle.py feeds the tables an R session dumped."""
+    draws -- tools/replay_tmb_bundle.py feeds the tables an R session dumped.
+    `likelihood = "multinomial"`: the same model scored with g3l_distribution_multinomial for the two catch
+    distributions and g3l_distribution_surveyindices_linear (slope and intercept estimated) for the index
+    (R/likelihood_distribution.R:41-60,82-125)."""
     rng = np.random.default_rng(seed)
     years = list(range(1990, 2024))
     area_names = g3_areas(["IXa", "IXb"])
@@ -92,6 +96,10 @@ def build_c1(seed=123, data=None):
     d = data or _fleet_data(rng, years, 1000, 100, 100, range(0, 81, 20), 10000,
                             lambda r, n: np.floor(r.uniform(1, 5, n)), lambda a: 30 + a * 10)
     f_surv = g3s_livesonareas(g3_fleet("f_surv"), ixa)
+    if likelihood == "multinomial":
+        dist_f, si_f = g3l_distribution_multinomial, g3l_distribution_surveyindices_linear(alpha=None, beta=None)
+    else:
+        dist_f, si_f = g3l_distribution_sumofsquares, g3l_distribution_surveyindices_log(alpha=None, beta=1)
     actions = [
         g3a_time(1990, 2023, [3, 3, 3, 3]),
         g3a_growmature(fish, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4)),
@@ -104,14 +112,13 @@ def build_c1(seed=123, data=None):
                           catchability_f=g3a_predate_catchability_totalfleet(
                               g3_timeareadata("landings_f_surv", d["landings"], "weight", areas=area_names))),
         g3l_catchdistribution("ldist_f_surv", d["ldist"], fleets=[f_surv], stocks=[fish],
-                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              function_f=dist_f(), area_group=area_names,
                               report=True, nll_breakdown=True),
         g3l_catchdistribution("aldist_f_surv", d["aldist"], fleets=[f_surv], stocks=[fish],
-                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              function_f=dist_f(), area_group=area_names,
                               report=True, nll_breakdown=True),
         g3l_abundancedistribution("dist_si_cpue", d["si"], stocks=[fish],
-                                  function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
-                                  area_group=area_names, report=True, nll_breakdown=True),
+                                  function_f=si_f, area_group=area_names, report=True, nll_breakdown=True),
     ]
     actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
     model = g3_to_cuda(actions)
@@ -134,11 +141,14 @@ def build_c1(seed=123, data=None):
     p = g3_init_val(p, "*.*.alpha", 0.07, lower=0.01, upper=0.2)
     p = g3_init_val(p, "*.*.l50", est_l50, spread=0.25)
     p = g3_init_val(p, "*.bbin", 1, lower=1e-05, upper=10)
+    if likelihood == "multinomial":     # a linear index is scored in squared numbers: weigh it down to the size of the others
+        p = g3_init_val(p, "adist_surveyindices_linear_dist_si_cpue_weight", 1e-8, optimise=False)
     return model, p
 
 
-def build_c2(seed=123, data=None):
-    """multiple-substocks (vignettes/multiple-substocks.Rmd:59-439). `data`: as build_c1, plus matp."""
+def build_c2(seed=123, data=None, mat_age=False):
+    """multiple-substocks (vignettes/multiple-substocks.Rmd:59-439). `data`: as build_c1, plus matp.
+    `mat_age`: g3a_mature_continuous with its age term, beta * cur_step_size and a50 (R/action_mature.R:18,44-74)."""
     rng = np.random.default_rng(seed)
     years = list(range(1990, 2024))
     area_names = g3_areas(["IXa", "IXb"])
@@ -153,7 +163,9 @@ def build_c2(seed=123, data=None):
     actions = [
         g3a_time(1990, 2023, [3, 3, 3, 3]),
         g3a_growmature(st_imm, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4),
-                       maturity_f=g3a_mature_continuous(), output_stocks=[st_mat], transition_f=True),
+                       maturity_f=(g3a_mature_continuous(beta=g3_parameterized("mat.beta", by_stock=True),
+                                                         a50=g3_parameterized("mat.a50", by_stock=True))
+                                   if mat_age else g3a_mature_continuous()), output_stocks=[st_mat], transition_f=True),
         g3a_naturalmortality(st_imm),
         g3a_initialconditions_normalcv(st_imm),
         g3a_renewal_normalcv(st_imm),
@@ -203,6 +215,9 @@ def build_c2(seed=123, data=None):
     p = g3_init_val(p, "*.mat.alpha", 0.07, lower=0.0001, upper=1.8)
     p = g3_init_val(p, "*.mat.l50", est_l50, spread=3.5)
     p = g3_init_val(p, "*.bbin", 100, lower=1e-05, upper=1500)
+    if mat_age:
+        p = g3_init_val(p, "*.mat.beta", 0.4, lower=0.01, upper=2)
+        p = g3_init_val(p, "*.mat.a50", 3, lower=1, upper=6)
     return model, p
 
 
@@ -664,5 +679,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C2": build_c2, "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
            "LING": build_ling}

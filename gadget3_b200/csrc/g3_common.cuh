@@ -17,7 +17,7 @@ template <class T> __device__ __forceinline__ T mkpar_g(const double* __restrict
 }
 
 // slot programs (include/g3cuda_spec.h G3OP_*), parameters read from the vector's row in global memory
-template <class T> __device__ __noinline__ T eval_slot_g(const int32_t* __restrict__ I, const double* __restrict__ R,
+template <class T> __device__ G3_NOINLINE T eval_slot_g(const int32_t* __restrict__ I, const double* __restrict__ R,
                                                          const double* __restrict__ prow, const int* seed, int slot) {
     const int32_t* tab = I + I[G3H_SLOT_OFF] + 2 * slot;
     const int32_t* c = I + tab[0];

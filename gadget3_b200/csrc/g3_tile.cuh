@@ -26,6 +26,9 @@ namespace g3t {
 using namespace g3;
 
 constexpr int NL = 32;      // lanes = evaluations per tile
+#ifndef __CUDACC__
+using std::max; using std::min;
+#endif
 
 struct StockRec {
     int L, nage, narea, ncol, c0, gcol0, minage;
@@ -115,6 +118,11 @@ template <int N> __device__ __forceinline__ void stv(double* p, const Dual<N>& v
     for (int k = 0; k < N; k++) p[(k + 1) * NL] = v.d[k];
 }
 
+template <class T> __device__ __forceinline__ T ldT(const double* p) { T r; ldv(p, r); return r; }
+template <class T> __device__ __forceinline__ void stT(double* p, const T& v) { stv(p, v); }
+
+constexpr int NB = 4;       // cells per block of the elementwise phases (interleaved avoid_zero / reciprocal chains)
+
 // T: double or Dual<N>; NW: compiled width of the growth band (maxlengthgroupgrowth + 1 <= NW);
 // SMEM: stock state in shared memory (smem = its base) or in the global slab
 template <class T, int NW, bool SMEM>
@@ -125,7 +133,10 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;
     const int32_t* __restrict__ tb = A.tb;
-    const int W = A.W;
+    // A.W column warps plus one KEEPER warp (the last): it owns no column; it keeps the objective (nll, component sums,
+    // understocking) in the reference's summation order while the column warps are already on the next step
+    const int W = A.W + 1;
+    const bool keeper = warp == A.W;
     double* const gl = A.gws + (size_t)cta * (size_t)A.slab_doubles + lane;
     double* const sm = SMEM ? smem + lane : gl + (size_t)A.n_g * C;
 #define GP(e) (gl + (unsigned)(e) * C)
@@ -143,7 +154,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
     const long long ntile = (total + LPT - 1) / LPT;
     const double us_power = R[I[G3H_US_ROFF]], us_weight = R[I[G3H_US_ROFF] + 1];
     const bool have_us = I[G3H_US_N] > 0;
-    const int wc0 = tb[A.wcol_off + warp], wc1 = tb[A.wcol_off + warp + 1];     // this warp's columns: tb[wc0..wc1)
+    const int wc0 = keeper ? 0 : tb[A.wcol_off + warp], wc1 = keeper ? 0 : tb[A.wcol_off + warp + 1];     // this warp's columns: tb[wc0..wc1)
 
     for (long long tile = cta; tile < ntile; tile += ncta) {
         const long long work0 = tile * LPT + lane;
@@ -367,8 +378,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
             if (G3T_ANY(on)) cw_any |= 1u << c;
         }
 
-        T nll(0.0);         // warp 0 keeps the objective and the component sums
-        if (warp == 0) {
+        T nll(0.0);         // the keeper warp holds the objective and the component sums
+        if (keeper) {
             for (int i = 0; i < A.NNLL; i++) GS(A.g_ctot + i, T(0.0));
             if (A.NBOUND > 0) {
                 T pen(0.0);
@@ -493,40 +504,83 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                 G3T_BAR();
             }
 
-            // what a column does once its own growth is through: hand-over, renewal, store, collect vectors
-            auto finish_cell = [&](const ColRec& Cl, const StockRec& St, const int l, T num, T wgt, const bool inc_here,
-                                   const int ren_mask) {
+            // ---- what a cell does once its growth is through: hand-over, renewal, store, collect vectors. Elementwise, so it
+            // runs on blocks of NB cells (l0 - b, b < nb) with the avoid_zero / reciprocal chains of the NB cells interleaved.
+            auto finish_block = [&](const ColRec& Cl, const StockRec& St, const int l0, const int nb, T (&num)[NB], T (&wgt)[NB],
+                                    const bool inc_here, const int ren_mask) {
                 const int L = St.L;
-                // ---- g3a_step_transition (R/action_mature.R:78-134): maturing fish arriving from their source column
+                // g3a_step_transition (R/action_mature.R:78-134): maturing fish arriving from their source column
                 if (inc_here) {
-                    const T moved = S(Cl.inc_tn + l) * SLOT(Cl.inc_slot);
-                    wgt = ratio_add_pop(wgt, num, S(Cl.inc_tw + l), moved);
-                    num = num + moved;
+                    const T ratio = SLOT(Cl.inc_slot);
+                    T nu[NB], de[NB], mv[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        const int l = max(l0 - b, 0);
+                        mv[b] = S(Cl.inc_tn + l) * ratio;
+                        nu[b] = wgt[b] * num[b] + S(Cl.inc_tw + l) * mv[b];     // ratio_add_pop, R/aab_env.R:133-153
+                        de[b] = num[b] + mv[b];
+                    }
+                    div_az_n(nu, de);
+#pragma unroll
+                    for (int b = 0; b < NB; b++) { wgt[b] = nu[b]; num[b] = num[b] + mv[b]; }
                 }
-                // ---- g3a_renewal (R/action_renewal.R:166-188)
+                // g3a_renewal (R/action_renewal.R:166-188)
                 if (ren_mask)
                     for (int r = 0; r < St.n_renew; r++)
                         if (((ren_mask >> r) & 1) && Cl.aidx == I[St.renew_ioff + r * G3R_LEN + G3R_AGE_IDX]) {
                             const int fs = I[I[St.renew_ioff + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * St.narea + Cl.ridx];
-                            if (fs >= 0) {
-                                const T rn = G(St.g_rd + r * L + l) * SLOT(fs);
-                                wgt = ratio_add_pop(wgt, num, G(St.g_rw + r * L + l), rn);
-                                num = num + rn;
+                            if (fs < 0) continue;
+                            const T factor = SLOT(fs);
+                            T nu[NB], de[NB], rn[NB];
+#pragma unroll
+                            for (int b = 0; b < NB; b++) {
+                                const int l = max(l0 - b, 0);
+                                rn[b] = G(St.g_rd + r * L + l) * factor;
+                                nu[b] = wgt[b] * num[b] + G(St.g_rw + r * L + l) * rn[b];
+                                de[b] = num[b] + rn[b];
                             }
+                            div_az_n(nu, de);
+#pragma unroll
+                            for (int b = 0; b < NB; b++) { wgt[b] = nu[b]; num[b] = num[b] + rn[b]; }
                         }
-                SS(A.s_num + Cl.cell0 + l, num); SS(A.s_wgt + Cl.cell0 + l, wgt);
-                // ---- collect vectors for g3l_distribution (R/likelihood_distribution.R:275-287)
+#pragma unroll
+                for (int b = 0; b < NB; b++)
+                    if (b < nb) { SS(A.s_num + Cl.cell0 + l0 - b, num[b]); SS(A.s_wgt + Cl.cell0 + l0 - b, wgt[b]); }
+                // collect vectors for g3l_distribution (R/likelihood_distribution.R:275-287)
                 if (xact) {
-                    const int cell = Cl.cell0 + l;
-                    for (int j = 0; j < St.cx_n; j++) {         // catch in numbers: cons / avoid_zero(wgt)
-                        const int x = tb[St.cx_off + j];
-                        if (((xact >> x) & 1) && A.xb[x].unit == 0) GS(A.xb[x].g_x + cell, xdiv(G(A.xb[x].g_x + cell), avoid_zero(wgt)));
+                    const int cell0 = Cl.cell0;
+                    bool any_cn = false;        // catch in numbers: cons / avoid_zero(wgt)
+                    for (int j = 0; j < St.cx_n; j++) { const int x = tb[St.cx_off + j]; any_cn = any_cn || (((xact >> x) & 1) && A.xb[x].unit == 0); }
+                    if (any_cn) {
+                        T iw[NB], de[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; b++) { iw[b] = T(1.0); de[b] = wgt[b]; }
+                        div_az_n(iw, de);
+                        for (int j = 0; j < St.cx_n; j++) {
+                            const int x = tb[St.cx_off + j];
+                            if (!(((xact >> x) & 1) && A.xb[x].unit == 0)) continue;
+                            const int gx = A.xb[x].g_x + cell0;
+#pragma unroll
+                            for (int b = 0; b < NB; b++) if (b < nb) GS(gx + l0 - b, G(gx + l0 - b) * iw[b]);
+                        }
                     }
                     for (int j = 0; j < A.ax_n; j++) {          // abundance
                         const int x = tb[A.ax_off + j];
-                        if ((xact >> x) & 1) GS(A.xb[x].g_x + cell, A.xb[x].unit == 0 ? num : num * wgt);
+                        if (!((xact >> x) & 1)) continue;
+                        const int gx = A.xb[x].g_x + cell0;
+                        const bool by_num = A.xb[x].unit == 0;
+#pragma unroll
+                        for (int b = 0; b < NB; b++) if (b < nb) GS(gx + l0 - b, by_num ? num[b] : num[b] * wgt[b]);
                     }
                 }
+            };
+            auto renewals_now = [&](const StockRec& St) {
+                int ren_mask = 0;       // renewal records that run at this step
+                for (int k = 0; k < St.n_renew; k++) {
+                    const int rs = I[St.renew_ioff + k * G3R_LEN + G3R_RUN_STEP];
+                    if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
+                }
+                return ren_mask;
             };
 
             // ================= own columns: predation, natural mortality, growth (+ maturing split), and -- unless
@@ -542,14 +596,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                 const bool const_now = trans_now && St.mat_kind == G3MAT_CONSTANT;
                 const bool has_mort = St.mort_ioff >= 0;
                 const bool inc_here = Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1);
-                int ren_mask = 0;       // renewal records that run at this step
-                for (int k = 0; k < St.n_renew; k++) {
-                    const int rs = I[St.renew_ioff + k * G3R_LEN + G3R_RUN_STEP];
-                    if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
-                }
+                const int ren_mask = renewals_now(St);
                 const bool catch_now = any_catch && nq > 0;
+                double* const pNum = SP(A.s_num + cell0);
+                double* const pWgt = SP(A.s_wgt + cell0);
 
-                // ---------- g3a_predate (R/action_predate.R:335-406)
+                // ---------- g3a_predate (R/action_predate.R:335-406): blocks of NB cells, ascending (the order of the sums)
                 if (prey_now) {
                     const int ws0 = A.g_wscr + warp * A.wscr_n;
                     for (int k = 0; k < nq; k++) {      // landings / total suitable biomass of each fleet in this column's area
@@ -569,32 +621,58 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                         return cf;
                     };
                     T o1(0.0), o2(0.0);
-                    for (int l = 0; l < L; l++) {
-                        const T num = S(A.s_num + cell0 + l);
-                        const T B0 = num * S(A.s_wgt + cell0 + l);
-                        T tp(0.0);
+                    for (int l0 = 0; l0 < L; l0 += NB) {
+                        const int nb = min(NB, L - l0);
+                        T num[NB], B0[NB], tp[NB], cr[NB], de[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            const int l = min(l0 + b, L - 1);
+                            num[b] = ldT<T>(pNum + (unsigned)l * C);
+                            B0[b] = num[b] * ldT<T>(pWgt + (unsigned)l * C);
+                            tp[b] = T(0.0);
+                        }
                         for (int k = 0; k < nq; k++) {
                             const PairRec& Q = A.pp[tb[St.pp_off + k]];
                             const int ts = tb[Q.tsid_off + Cl.ridx];
-                            if (ts >= 0) tp = tp + cfac(Q, k, ts, l) * B0;
+                            if (ts < 0) continue;
+#pragma unroll
+                            for (int b = 0; b < NB; b++) tp[b] = tp[b] + cfac(Q, k, ts, min(l0 + b, L - 1)) * B0[b];
                         }
-                        T cr = xdiv_x(tp, avoid_zero_x(B0));       // (exact-division forms: see g3_math.cuh)
-                        cr = dif_pmax_x(cr, 0.95, -1e3);
-                        const T tpn = B0 * cr;
-                        SS(A.s_num + cell0 + l, num * (1.0 - cr));
-                        o1 = o1 + tp; o2 = o2 + tpn;
+#pragma unroll
+                        for (int b = 0; b < NB; b++) { cr[b] = tp[b]; de[b] = B0[b]; }
+                        div_azx_n(cr, de);                      // consratio = tp / avoid_zero(B0)   (exact-division forms: g3_math.cuh)
+                        dif_pmax_x_n(cr, 0.95, -1e3);           // dif_pmin(consratio, 0.95, 1e3)
+                        T tpn[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            tpn[b] = B0[b] * cr[b];
+                            if (b < nb) {
+                                stT<T>(pNum + (unsigned)(l0 + b) * C, num[b] * (1.0 - cr[b]));
+                                o1 = o1 + tp[b]; o2 = o2 + tpn[b];
+                            }
+                        }
                         if (catch_now) {
-                            const T cc = xdiv(T(1.0), avoid_zero(tp)) * tpn * B0;      // consconv * B0
+                            T cc[NB];
+#pragma unroll
+                            for (int b = 0; b < NB; b++) { cc[b] = T(1.0); de[b] = tp[b]; }
+                            div_az_n(cc, de);
+#pragma unroll
+                            for (int b = 0; b < NB; b++) cc[b] = cc[b] * tpn[b] * B0[b];        // consconv * B0
                             for (int j = 0; j < St.cx_n; j++) {
                                 const int x = tb[St.cx_off + j];
                                 if (!((xact >> x) & 1)) continue;
-                                T fx(0.0);
+                                T fx[NB];
+#pragma unroll
+                                for (int b = 0; b < NB; b++) fx[b] = T(0.0);
                                 for (int k = 0; k < nq; k++) {
                                     const PairRec& Q = A.pp[tb[St.pp_off + k]];
                                     const int ts = tb[Q.tsid_off + Cl.ridx];
-                                    if (ts >= 0 && ((Q.cxmask >> j) & 1)) fx = fx + cfac(Q, k, ts, l);
+                                    if (ts < 0 || !((Q.cxmask >> j) & 1)) continue;
+#pragma unroll
+                                    for (int b = 0; b < NB; b++) fx[b] = fx[b] + cfac(Q, k, ts, min(l0 + b, L - 1));
                                 }
-                                GS(A.xb[x].g_x + cell0 + l, fx * cc);
+#pragma unroll
+                                for (int b = 0; b < NB; b++) if (b < nb) GS(A.xb[x].g_x + cell0 + l0 + b, fx[b] * cc[b]);
                             }
                         }
                     }
@@ -612,10 +690,19 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                 // from the top the update is in place: every source l - d is still the old value when l is rebuilt.
                 const T mortf = has_mort ? G(St.g_mort + idt * St.ncol + Cl.col) : T(1.0);
                 if (grow_n < 0) {
-                    for (int l = L - 1; l >= 0; l--) {
-                        const T num = S(A.s_num + cell0 + l) * mortf, wgt = S(A.s_wgt + cell0 + l);
-                        if (!inc_here) finish_cell(Cl, St, l, num, wgt, false, ren_mask);
-                        else SS(A.s_num + cell0 + l, num);
+                    for (int l0 = L - 1; l0 >= 0; l0 -= NB) {
+                        const int nb = min(NB, l0 + 1);
+                        T num[NB], wgt[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            const int l = max(l0 - b, 0);
+                            num[b] = ldT<T>(pNum + (unsigned)l * C) * mortf; wgt[b] = ldT<T>(pWgt + (unsigned)l * C);
+                        }
+                        if (!inc_here) finish_block(Cl, St, l0, nb, num, wgt, false, ren_mask);
+                        else {
+#pragma unroll
+                            for (int b = 0; b < NB; b++) if (b < nb) stT<T>(pNum + (unsigned)(l0 - b) * C, num[b]);
+                        }
                     }
                     continue;
                 }
@@ -623,63 +710,97 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                 const T wal = SLOT(I[St.grow_ioff + 3]);
                 const T remf = trans_now ? G(Cl.g_remf) : T(0.0);
                 const int bset = ((St.band_percol ? Cl.col : 0) * A.ndt + idt) * St.bsz;
-                const int gb = St.g_band + bset, gbr = St.g_bandr + bset;
+                const double* const pB = GP(St.g_band + bset);
+                const double* const pBr = GP(St.g_bandr + bset);
+                const double* const pPw = GP(St.g_pw);
+                const double* const pCm = St.g_cmat >= 0 ? GP(St.g_cmat + Cl.col * L) : pPw;
                 const bool stash = trans_now && Cl.s_tn >= 0;
-                for (int l = L - 1; l >= 0; l--) {
-                    // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d
-                    const T pw_l = G(St.g_pw + l);
-                    const bool top = l == L - 1;
-                    T an(0.0), aw(0.0), bn(0.0), bw(0.0);
+                const unsigned bstep = (unsigned)(n1 - 1) * C;      // band entry of (source l - d, jump d) sits d * bstep below entry (l, 0)
+                for (int l0 = L - 1; l0 >= 0; l0 -= NB) {
+                    const int nb = min(NB, l0 + 1);
+                    // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d, NB cells
+                    T an[NB], aw[NB], bn[NB], bw[NB];
 #pragma unroll
-                    for (int d = 0; d < NW; d++) {
-                        if (d <= grow_n && d <= l) {
-                            const int src = l - d;
-                            const int be = top ? L * n1 + d : src * n1 + d;     // plus group: tail sums
-                            const T ns = S(A.s_num + cell0 + src) * mortf;
-                            const T gd = G(gb + be);
-                            const T dwd = wal * (pw_l - G(St.g_pw + src));      // walpha (l^wbeta - (l-d)^wbeta), R/action_grow.R:58-71
-                            const T wsrc = dwd + S(A.s_wgt + cell0 + src);
-                            if (cont_now) {
-                                const T grd = G(gbr + be);
-                                const T w = wsrc * ns;
-                                an = an + grd * ns; aw = aw + grd * w;
-                                bn = bn + gd * ns; bw = bw + gd * w;
-                            } else if (const_now) {
-                                // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
-                                const T ratio = G(St.g_cmat + Cl.col * L + src);
-                                const T m1 = (ns * ratio) * gd, m2 = (ns * (1.0 - ratio)) * gd;
-                                an = an + m1; aw = aw + wsrc * m1;
-                                bn = bn + m2; bw = bw + wsrc * m2;
-                            } else {
-                                const T m2 = ns * gd;
-                                bn = bn + m2; bw = bw + wsrc * m2;
+                    for (int b = 0; b < NB; b++) {
+                        const int l = max(l0 - b, 0);
+                        const T pw_l = ldT<T>(pPw + (unsigned)l * C);
+                        // row l of the band, or the plus group's tail sums
+                        const bool top = l == L - 1;
+                        const unsigned brow = (top ? (unsigned)(L * n1) : (unsigned)(l * n1)) * C;
+                        T a_n(0.0), a_w(0.0), b_n(0.0), b_w(0.0);
+#pragma unroll
+                        for (int d = 0; d < NW; d++) {
+                            if (d <= grow_n && d <= l) {
+                                const unsigned so = (unsigned)(l - d) * C;
+                                const unsigned be = top ? brow + (unsigned)d * C : brow - (unsigned)d * bstep;
+                                const T ns = ldT<T>(pNum + so) * mortf;
+                                const T gd = ldT<T>(pB + be);
+                                const T dwd = wal * (pw_l - ldT<T>(pPw + so));      // walpha (l^wbeta - (l-d)^wbeta), R/action_grow.R:58-71
+                                const T wsrc = dwd + ldT<T>(pWgt + so);
+                                if (cont_now) {
+                                    const T grd = ldT<T>(pBr + be);
+                                    const T w = wsrc * ns;
+                                    a_n = a_n + grd * ns; a_w = a_w + grd * w;
+                                    b_n = b_n + gd * ns; b_w = b_w + gd * w;
+                                } else if (const_now) {
+                                    // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
+                                    const T ratio = ldT<T>(pCm + so);
+                                    const T m1 = (ns * ratio) * gd, m2 = (ns * (1.0 - ratio)) * gd;
+                                    a_n = a_n + m1; a_w = a_w + wsrc * m1;
+                                    b_n = b_n + m2; b_w = b_w + wsrc * m2;
+                                } else {
+                                    const T m2 = ns * gd;
+                                    b_n = b_n + m2; b_w = b_w + wsrc * m2;
+                                }
                             }
                         }
+                        an[b] = a_n; aw[b] = a_w; bn[b] = b_n; bw[b] = b_w;
                     }
-                    T num = bn, wgt = xdiv(bw, avoid_zero(bn));
+                    // ---- mean weights (one avoid_zero + reciprocal per cell and part), interleaved over the block
+                    T num[NB], wgt[NB], de[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) { num[b] = bn[b]; wgt[b] = bw[b]; de[b] = bn[b]; }
+                    div_az_n(wgt, de);
                     if (trans_now) {
-                        if (stash) { SS(Cl.s_tn + l, an); SS(Cl.s_tw + l, xdiv(aw, avoid_zero(an))); }
+                        if (stash) {
+#pragma unroll
+                            for (int b = 0; b < NB; b++) de[b] = an[b];
+                            div_az_n(aw, de);
+#pragma unroll
+                            for (int b = 0; b < NB; b++) if (b < nb) { SS(Cl.s_tn + l0 - b, an[b]); SS(Cl.s_tw + l0 - b, aw[b]); }
+                        }
                         // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
-                        num = num + an * remf;
+#pragma unroll
+                        for (int b = 0; b < NB; b++) num[b] = num[b] + an[b] * remf;
                     }
-                    if (!inc_here) finish_cell(Cl, St, l, num, wgt, false, ren_mask);
-                    else { SS(A.s_num + cell0 + l, num); SS(A.s_wgt + cell0 + l, wgt); }
+                    if (!inc_here) finish_block(Cl, St, l0, nb, num, wgt, false, ren_mask);
+                    else {
+#pragma unroll
+                        for (int b = 0; b < NB; b++)
+                            if (b < nb) { stT<T>(pNum + (unsigned)(l0 - b) * C, num[b]); stT<T>(pWgt + (unsigned)(l0 - b) * C, wgt[b]); }
+                    }
                 }
             }
 
-            // ================= columns that receive maturing fish finish once every source column has grown
-            if ((A.inc_any_mask >> step) & 1) G3T_BAR();
-            for (int wi = wc0; wi < wc1; wi++) {
-                const ColRec& Cl = A.col[tb[wi]];
-                if (!(Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1))) continue;
-                const StockRec& St = A.st[Cl.s];
-                int ren_mask = 0;
-                for (int k = 0; k < St.n_renew; k++) {
-                    const int rs = I[St.renew_ioff + k * G3R_LEN + G3R_RUN_STEP];
-                    if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
+            // ================= columns that receive maturing fish finish once every source column has grown. That part is
+            // elementwise per cell, so its (column, block) units are dealt to ALL warps, not only to the owners.
+            if ((A.inc_any_mask >> step) & 1) {
+                G3T_BAR();
+                ucnt = 0;
+                for (int gc = 0; gc < A.NCOLS; gc++) {
+                    const ColRec& Cl = A.col[gc];
+                    if (!(Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1))) continue;
+                    const StockRec& St = A.st[Cl.s];
+                    const int ren_mask = renewals_now(St);
+                    for (int l0 = St.L - 1; l0 >= 0; l0 -= NB) {
+                        if (!mine()) continue;
+                        const int nb = min(NB, l0 + 1);
+                        T num[NB], wgt[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; b++) { const int l = max(l0 - b, 0); num[b] = S(A.s_num + Cl.cell0 + l); wgt[b] = S(A.s_wgt + Cl.cell0 + l); }
+                        finish_block(Cl, St, l0, nb, num, wgt, true, ren_mask);
+                    }
                 }
-                for (int l = St.L - 1; l >= 0; l--)
-                    finish_cell(Cl, St, l, S(A.s_num + Cl.cell0 + l), S(A.s_wgt + Cl.cell0 + l), true, ren_mask);
             }
 
             // ================= g3l_distribution collect: model[dest] += lgmatrix . x (R/likelihood_distribution.R:288-364)
@@ -802,8 +923,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
             }
             G3T_BAR();          // the step's state, collect sums and component values are complete
 
-            // ================= warp 0: the objective, in the reference's summation order
-            if (warp == 0) {
+            // ================= the keeper warp: the objective, in the reference's summation order (the column warps go on)
+            if (keeper) {
                 for (int c = 0; c < A.NCOMP; c++) {
                     if (!((cact >> c) & 1)) continue;
                     const CompRec& Cm = A.comp[c];
@@ -882,7 +1003,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
             }
         }   // time loop
 
-        if (warp == 0 && live) {
+        if (keeper && live) {
             const T out = bad_time ? T(nan("")) : nll;
             if (tile_t == 0) {
                 A.nll[b] = val(out);

@@ -62,8 +62,8 @@ inline void plan_set_warps(TilePlan& P, int W) {
     }
     P.tb[base + W] = (int)P.tb.size();
     P.a.W = W;
-    // per-warp scratch follows the other G entries
-    P.a.n_g = P.a.g_wscr + W * P.a.wscr_n;
+    // per-warp scratch follows the other G entries (W column warps + the keeper warp)
+    P.a.n_g = P.a.g_wscr + (W + 1) * P.a.wscr_n;
 }
 
 inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0) {
@@ -432,17 +432,17 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     A.wcol_off = (int)P.tb.size();
     int W = want_W;
     if (W <= 0) {
-        // as many warps as columns up to 16; beyond that the best-balanced count in 8..16
-        if (ncols <= 16) W = ncols;
+        // as many column warps as columns up to 15 (+ the keeper warp = 512 threads); beyond that the best-balanced count in 8..15
+        if (ncols <= 15) W = ncols;
         else {
             double best = -1.0;
-            for (int w = 8; w <= 16; w++) {
-                const double e = assign_columns(P.col_cost, w, nullptr) * (0.75 + 0.25 * w / 16.0);
+            for (int w = 8; w <= 15; w++) {
+                const double e = assign_columns(P.col_cost, w, nullptr) * (0.75 + 0.25 * w / 15.0);
                 if (e > best + 1e-12) { best = e; W = w; }
             }
         }
     }
-    W = std::max(1, std::min({W, ncols, 32}));
+    W = std::max(1, std::min({W, ncols, 15}));
     plan_set_warps(P, W);
     P.ok = true;
     return P;

@@ -125,8 +125,8 @@ int tile_geom(g3cuda_model* m, TileGeom* g) {
     const bool wide = m->tplan.maxn > 4;
     g->fn = dual ? (wide ? g3i::tile_g16(g->in_smem) : g3i::tile_g5(g->in_smem)) : (wide ? g3i::tile_d16(g->in_smem) : g3i::tile_d5(g->in_smem));
     CUDA_TRY(cudaFuncSetAttribute(g->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->per_sm, g->fn, m->targs.W * 32, g->smem));
-    if (g->per_sm < 1) return fail(G3CUDA_EUNSUPP, "tile kernel does not fit one SM (%d threads, %zu bytes of shared memory)", m->targs.W * 32, g->smem);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->per_sm, g->fn, (m->targs.W + 1) * 32, g->smem));
+    if (g->per_sm < 1) return fail(G3CUDA_EUNSUPP, "tile kernel does not fit one SM (%d threads, %zu bytes of shared memory)", (m->targs.W + 1) * 32, g->smem);
     g->slots = (long long)g->per_sm * m->num_sms;
     return G3CUDA_OK;
 }
@@ -156,7 +156,7 @@ int launch_tile(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStre
         m->t_gws_bytes = want;
     }
     A.gws = m->t_gws;
-    return launch_ptr(m, g.fn, (unsigned)grid, (unsigned)(A.W * 32), g.smem, st, &A);
+    return launch_ptr(m, g.fn, (unsigned)grid, (unsigned)((A.W + 1) * 32), g.smem, st, &A);       // column warps + the keeper warp
 }
 
 // ============================================================ thread kernel
@@ -510,8 +510,8 @@ std::string plan_thread(g3cuda_model* m, std::vector<int32_t>& rem_off, std::vec
         const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
         if (C[G3C_FUNC] < 0 || C[G3C_FUNC] > G3F_SUMSQLOGRATIOS) return "likelihood function " + std::to_string(C[G3C_FUNC]) + " is not supported";
     }
-    // 32-bit element indexing of the workspace: entries x stride x components must stay below 2^32
-    if ((double)m->t_entries * (double)WS_STRIDE * (NTAN + 1) >= 4294967295.0) return "evaluation workspace too large for 32-bit element indexing";
+    // 32-bit element indexing of the workspace (in units of T): entries x stride must stay below 2^32
+    if ((double)m->t_entries * (double)WS_STRIDE >= 4294967295.0) return "evaluation workspace too large for 32-bit element indexing";
     return "";
 }
 
@@ -812,7 +812,7 @@ int g3cuda_set_kernel(g3cuda_model* m, int which) {
 }
 
 int g3cuda_set_tile_warps(g3cuda_model* m, int warps) {
-    if (!m || warps < 0 || warps > 16) return fail(G3CUDA_EINVAL, "bad argument");
+    if (!m || warps < 0 || warps > 15) return fail(G3CUDA_EINVAL, "bad argument");
     if (!m->tile_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", m->tplan.why.c_str());
     CUDA_TRY(cudaSetDevice(m->device));
     int w = warps;
