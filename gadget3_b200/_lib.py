@@ -63,6 +63,8 @@ def load():
     lib.g3cuda_set_kernel.restype = C.c_int
     lib.g3cuda_set_tile_warps.argtypes = [vp, C.c_int]
     lib.g3cuda_set_tile_warps.restype = C.c_int
+    lib.g3cuda_set_tile_partition.argtypes = [vp, C.c_int, C.c_int]
+    lib.g3cuda_set_tile_partition.restype = C.c_int
     lib.g3cuda_tile_info.argtypes = [vp, ip]
     lib.g3cuda_tile_info.restype = C.c_int32
     lib.g3cuda_math_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64,
@@ -77,7 +79,7 @@ def load():
 EXPORTED = ["g3cuda_model_create", "g3cuda_model_free", "g3cuda_n_par", "g3cuda_n_nll", "g3cuda_n_steps",
             "g3cuda_report_len", "g3cuda_eval_batch", "g3cuda_eval_batch_device", "g3cuda_launch_count",
             "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version",
-            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe", "g3cuda_set_tile_warps", "g3cuda_tile_info"]
+            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe", "g3cuda_set_tile_warps", "g3cuda_set_tile_partition", "g3cuda_tile_info"]
 
 
 def _dp(a):
@@ -151,6 +153,10 @@ class Handle:
     def set_tile_warps(self, warps: int):
         """Warps per tile of the tile kernel (0 = the planner's choice); tuning hook."""
         self._check(self.lib.g3cuda_set_tile_warps(self.h, int(warps)), "g3cuda_set_tile_warps")
+
+    def set_tile_partition(self, warps: int = 0, seg_rows: int = 0):
+        """Re-plan the tile kernel: unit warps (0 = planner's choice), rows per unit (0 = planner's choice, -1 = whole columns)."""
+        self._check(self.lib.g3cuda_set_tile_partition(self.h, int(warps), int(seg_rows)), "g3cuda_set_tile_partition")
 
     def tile_info(self) -> dict:
         out = np.zeros(6, dtype=np.int32)

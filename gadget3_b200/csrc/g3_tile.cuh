@@ -5,15 +5,22 @@
 //   lane  = evaluation. The 32 lanes of every warp are the same 32 parameter vectors, so the per-cell
 //           arithmetic is the straight-line scalar code of the reference and control flow is warp-uniform
 //           (branches depend on model structure and the step, never on the lane).
-//   warp  = age/area column(s) of a stock. Growth, mortality, predation, renewal are independent per
-//           column (length is the only coupled axis); what crosses columns goes through shared memory and
-//           one block barrier: fleet totals, the maturation hand-over, likelihood sums, ageing, migration.
+//   warp  = a list of UNITS: row segments [lo, lo + len) of age/area columns of a stock, dealt to the warps by
+//           cost (g3_tile_plan.h). Growth only looks DOWN the length axis of its own column, so a unit needs its own
+//           rows plus the NW - 1 rows below it: the unit below copies those into the unit's GHOST rows before the
+//           growth pass (one block barrier), after which every unit sweeps its rows in place, top block first.
+//           What crosses columns goes through memory and one block barrier: fleet totals, the maturation hand-over,
+//           likelihood sums, ageing, migration.
 //   state = num/wgt of every stock cell (+ the maturing fish in flight) in shared memory, [cell][lane]:
 //           a warp access is one conflict-free 256-byte row. Models whose state does not fit 227 KB
 //           (and Dual<N> gradient runs) keep the same layout in the CTA's global slab instead (SMEM = false).
 //   tables (per evaluation, time-invariant: growth bands, suitability, mortality, renewal shape, likelihood
 //           slabs, collect vectors) live in a per-CTA global slab [entry][lane]; only gridDim x 32
 //           evaluations are in flight, so the slabs stay in L2/L1 instead of streaming from HBM.
+// The hot loops (growth gather, predation) are straight-line code over blocks of NB rows: every load is a block
+// pointer plus a compile-time offset, the band is stored destination-oriented ([l][d] = P(l - d -> l), plus-group
+// tail sums folded into row L - 1, zero where l - d < 0), and the avoid_zero / reciprocal chains of the NB rows are
+// interleaved stage by stage (g3_math.cuh).
 // Nothing is exchanged between lanes: no shuffles, no atomics; every sum has a fixed order.
 //
 // The body is written against a few macros (G3T_BAR, G3T_ANY) so that the same source also compiles under
@@ -26,6 +33,7 @@ namespace g3t {
 using namespace g3;
 
 constexpr int NL = 32;      // lanes = evaluations per tile
+constexpr int NBX = 4;      // rows per block of the plain-double instantiations: the planner aligns row segments to it
 #ifndef __CUDACC__
 using std::max; using std::min;
 #endif
@@ -37,15 +45,16 @@ struct StockRec {
     int n_renew, renew_ioff;
     int g_mort;             // [idt][col] exp(-M dt)
     int g_rd, g_rw;         // [k][l] renewal numbers shape (x 1e4) and weight
-    int g_pw;               // [l] midlen^wbeta
-    int g_band, g_bandr;    // growth band sets, staying (or whole) / maturing part: [set][idt][(L+1)*(n+1)]
+    int g_wq;               // [l] walpha * midlen^wbeta; NW - 1 zero rows before row 0, NBX - 1 after row L - 1
+    int g_band, g_bandr;    // destination-oriented growth bands, staying (or whole) / maturing part: [set][idt][(L + NBX - 1) * NW]
     int band_percol, bsz;   // one set per column (continuous maturity with an age term) or per stock
-    int g_cmat;             // [col][l] g3a_mature_constant ratio, or -1
+    int g_cmat;             // [col][l] g3a_mature_constant ratio (NW - 1 zero rows before, NBX - 1 after), or -1
     int mig_ioff, g_mig, mig_steps;
     int age_enable, age_n_out, s_mv;
     int us_flag;
     int pp_off, pp_n;       // tb: predator-prey pairs acting on this stock, run order
     int cx_off, cx_n;       // tb: catch collect vectors those pairs feed
+    int u0, nu;             // units of this stock: unit[u0 .. u0 + nu), column by column, bottom segment first (= cell order)
 };
 struct ColRec {
     int s, col, aidx, ridx, cell0;
@@ -53,12 +62,18 @@ struct ColRec {
     int inc_tn, inc_tw, inc_slot, inc_mask;     // maturing fish arriving INTO this column: source entries, ratio slot, step mask
     int g_remf;             // share of the maturing fish no output stock claims
     int rem_off;            // tb: -1 terminated list of ratio slots with a destination
-    int g_usp;              // (sum tp, sum tp') of this column at this step's predation
+};
+struct UnitRec {
+    int gc, lo, len;        // rows [lo, lo + len) of global column gc
+    int lu;                 // index among the units of its stock
+    int g_ghost;            // G entries [2][NW - 1]: num, then wgt, of rows lo - (NW - 1) .. lo - 1; -1 for a bottom segment
+    int up_ghost;           // g_ghost of the unit above in the same column (this unit fills it), or -1
+    int g_usp;              // (sum tp, sum tp') of this unit at this step's predation
 };
 struct PairRec {
     int pred, prey, suit_kind, suit_ioff, energy_slot, pred_kind, pred_stock, PL;
     int g_suit;             // [PL][L]
-    int g_part;             // [prey column][PL] partial suitable biomass
+    int g_part;             // [prey unit][PL] partial suitable biomass
     int cxmask;             // bit j: feeds the prey stock's j-th catch collect vector
     int tsid_off;           // tb: [prey narea] accumulator (fleet) / predator area index (stock predator), or -1
 };
@@ -68,26 +83,35 @@ struct CompRec {
     int func, weight_par, xbuf, mode, n_dest, n_bins, n_slices, n_areag;
     int csr_ptr_ioff, csr_idx_ioff, csr_coef_roff, cell_dest_ioff, cell_coef_roff, tidx_ioff, cmp_ioff;
     int n_times, param_roff, g_ms, obs_off, obsconst_off;
+    int n_groups, group_len;    // dests whose total the comparison needs: sumofsquares n_areag slabs, multinomial every slice
+    int g_pt, g_pv;             // [n_groups][16] the warps' shares of the group totals; [16] of the component's value
+    int g_cpart;                // partial sums of the split dests
+    int task_off;               // tb: [W + 2] offsets into tb, then each warp's tasks (dest, first term, end term, slot, group)
+    int split_off;              // tb: count, then (dest, first slot, slots) of every split dest
 };
 struct XRec { int kind, unit, g_x; };
 
 struct TArgs {
     const int32_t* I; const double* R; const int32_t* tb;
-    const StockRec* st; const ColRec* col; const PairRec* pp; const PredRec* pred; const TsRec* ts;
+    const StockRec* st; const ColRec* col; const UnitRec* unit; const PairRec* pp; const PredRec* pred; const TsRec* ts;
     const CompRec* comp; const XRec* xb; const int4* agedst;
     const double* obsprop; const double* obsconst; const unsigned char* pred_active;
+    const int32_t* cterm_idx; const double* cterm_coef;     // collect terms of all components: cell, lgmatrix coefficient
     const double* par; long long B; const int32_t* tangent_idx; int K;
     double* nll; double* comp_out; double* grad;
     double* gws; long long slab_doubles; int lanes_per_tile;
-    int NC, NS, NPP, NPRED, NTS, NCOMP, NX, NSLOT, NPAR, NT, NSTEPS, NNLL, NBOUND, NCOLS, maxL, n_agedst;
+    int NC, NS, NPP, NPRED, NTS, NCOMP, NX, NSLOT, NPAR, NT, NSTEPS, NNLL, NBOUND, NCOLS, NU, maxL, n_agedst;
     int ndt, dt_len[4], step_idt[32];
     int n_g;                // G entries per lane; the state entries follow them when SMEM = false
-    int s_num, s_wgt;       // S entry bases
-    int g_slot, g_eot, g_cn, g_ctot, g_bterm, g_wscr, wscr_n;
-    int wcol_off;           // tb: [W + 1] offsets into tb, then each warp's global columns
+    int s_num, s_wgt;       // S entry bases (NW - 1 zero entries lie below s_num)
+    int g_slot, g_eot, g_cn, g_ctot, g_bterm, g_wscr, wscr_n, cf_rows;
+    int wunit_off;          // tb: [W + 1] offsets into tb, then each warp's units
     int ax_off, ax_n;       // tb: abundance collect vectors
+    int zr_off, zr_n;       // tb: (space, first entry, count) triples zeroed once per tile: pads and the band tables
     int agedst_l_off;       // tb: length group of each agedst entry
     int inc_any_mask;       // bit (cur_step-1): some column receives maturing fish on that step
+    int any_ghost;          // some column is split into several units
+    int NWc;                // band width the tables are laid out for (the kernel's NW)
     int W;
 };
 
@@ -121,7 +145,78 @@ template <int N> __device__ __forceinline__ void stv(double* p, const Dual<N>& v
 template <class T> __device__ __forceinline__ T ldT(const double* p) { T r; ldv(p, r); return r; }
 template <class T> __device__ __forceinline__ void stT(double* p, const T& v) { stv(p, v); }
 
-constexpr int NB = 4;       // cells per block of the elementwise phases (interleaved avoid_zero / reciprocal chains)
+// avoid_zero(x) returns x itself when 1000 x > 34 (lsa_c_n's early-out: the log1p term is below half an ulp). div_plenty()
+// is a / avoid_zero(b) for such b, with exactly the operations the chain performs on them, so that a row's value does not
+// depend on whether its warp took the plain or the chain path (i.e. on which other vectors share its tile).
+__device__ __forceinline__ bool az_is_identity(double x) { return x * 1000.0 > 34.0; }
+template <int N> __device__ __forceinline__ bool az_is_identity(const Dual<N>& x) { return x.v * 1000.0 > 34.0; }
+__device__ __forceinline__ double div_plenty(double a, double b) { return a * rcp_bf((b * 1000.0) * 1e-3); }
+template <int N> __device__ __forceinline__ Dual<N> div_plenty(const Dual<N>& a, const Dual<N>& b) { return xdiv(a, avoid_zero(b)); }
+#ifdef __CUDACC__
+#define G3_FFSLL(x) __ffsll((long long)(x))
+#else
+#define G3_FFSLL(x) __builtin_ffsll((long long)(x))
+#endif
+
+// ---- g3a_growmature (R/action_grow.R:340-497), the banded gather of ONE BLOCK of NB destination rows r0 .. r0 + NB - 1 of a
+// unit, as straight-line code: source rows r0 - (NW - 1) .. r0 + NB - 1 are loaded once each, every (row, jump) pair is a
+// compile-time offset from the block pointers. Pointers address row 0 of the unit (pN, pW: state; pQ: walpha l^wbeta;
+// pCm: constant-maturity ratios) resp. band row 0 of the unit (pB, pBr).
+//   MODE 0: no maturation now            b = sum_d G[l][d] n[l-d]
+//   MODE 1: g3a_mature_continuous        a (maturing) uses the second band (R/action_grow.R:420-437)
+//   MODE 2: g3a_mature_constant          a / b split by the ratio of the SOURCE cell (R/action_grow.R:438-457)
+//   LOW:    the block reaches below the unit's first row and the unit has ghost rows (pGh: [2][NW - 1]) for them
+// Weights: a fish of row s that ends in row l gains wq[l] - wq[s] with wq = walpha l^wbeta (g3a_grow_weightsimple,
+// R/action_grow.R:58-71). The difference is formed FIRST, as in the reference: for the fish that stay (s = l) it is exactly
+// zero whatever the size of wq against the weight -- regrouping it as wq[l] * sum m + sum m (w[s] - wq[s]) saves two adds per
+// pair but loses digits of w when walpha l^wbeta is far above the actual weights (measured: 4e-10 on nll for such vectors).
+template <class T, int NW, int NB, int MODE, bool LOW>
+__device__ __forceinline__ void grow_gather(const double* __restrict__ pN, const double* __restrict__ pW, const double* __restrict__ pQ,
+                                            const double* __restrict__ pB, const double* __restrict__ pBr,
+                                            const double* __restrict__ pCm, const double* __restrict__ pGh, const int r0,
+                                            const T& mortf, T (&an)[NB], T (&aw)[NB], T (&bn)[NB], T (&bw)[NB]) {
+    constexpr int C = (Tan<T>::n + 1) * NL;
+    T wq[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) { an[b] = T(0.0); aw[b] = T(0.0); bn[b] = T(0.0); bw[b] = T(0.0); wq[b] = ldT<T>(pQ + (r0 + b) * C); }
+    const int rb = r0 - (NW - 1);
+    const double* const sN = pN + rb * C;
+    const double* const sW = pW + rb * C;
+    const double* const sQ = pQ + rb * C;
+    const double* const sC = pCm + rb * C;
+    const double* const bB = pB + r0 * (NW * C);
+    const double* const bR = pBr + r0 * (NW * C);
+#pragma unroll
+    for (int i = 0; i < NW + NB - 1; i++) {
+        const bool ghost = LOW && rb + i < 0;       // (block-uniform)
+        const double* const pn = ghost ? pGh + (rb + i + (NW - 1)) * C : sN + i * C;
+        const double* const pw = ghost ? pGh + (rb + i + 2 * (NW - 1)) * C : sW + i * C;
+        const T ns = ldT<T>(pn) * mortf;
+        const T ws = ldT<T>(pw), wqs = ldT<T>(sQ + i * C);
+        T nsr(0.0), nss(0.0);
+        if (MODE == 2) { const T ratio = ldT<T>(sC + i * C); nsr = ns * ratio; nss = ns * (1.0 - ratio); }
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const int d = NW - 1 + b - i;           // jump that takes source row i of the window to destination row b
+            if (d >= 0 && d < NW) {
+                const T g = ldT<T>(bB + (b * NW + d) * C);
+                if (MODE == 0) {
+                    const T m = ns * g;
+                    bn[b] = bn[b] + m; bw[b] = bw[b] + m * ((wq[b] - wqs) + ws);
+                } else if (MODE == 1) {
+                    const T gr = ldT<T>(bR + (b * NW + d) * C);
+                    const T ma = ns * gr, m = ns * g;
+                    an[b] = an[b] + ma; aw[b] = aw[b] + ma * ((wq[b] - wqs) + ws);
+                    bn[b] = bn[b] + m; bw[b] = bw[b] + m * ((wq[b] - wqs) + ws);
+                } else {
+                    const T ma = nsr * g, m = nss * g;
+                    an[b] = an[b] + ma; aw[b] = aw[b] + ma * ((wq[b] - wqs) + ws);
+                    bn[b] = bn[b] + m; bw[b] = bw[b] + m * ((wq[b] - wqs) + ws);
+                }
+            }
+        }
+    }
+}
 
 // T: double or Dual<N>; NW: compiled width of the growth band (maxlengthgroupgrowth + 1 <= NW);
 // SMEM: stock state in shared memory (smem = its base) or in the global slab
@@ -129,12 +224,13 @@ template <class T, int NW, bool SMEM>
 __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const int warp, const int lane, const int cta,
                                           const int ncta G3T_CTX_DECL) {
     constexpr int NTAN = Tan<T>::n;
+    constexpr int NB = NTAN > 0 ? 1 : NBX;                  // rows per block (interleaved avoid_zero / reciprocal chains)
     constexpr unsigned C = (unsigned)(NTAN + 1) * NL;       // doubles per entry
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;
     const int32_t* __restrict__ tb = A.tb;
-    // A.W column warps plus one KEEPER warp (the last): it owns no column; it keeps the objective (nll, component sums,
-    // understocking) in the reference's summation order while the column warps are already on the next step
+    // A.W unit warps plus one KEEPER warp (the last): it owns no unit; it keeps the objective (nll, component sums,
+    // understocking) in the reference's summation order while the unit warps are already on the next step
     const int W = A.W + 1;
     const bool keeper = warp == A.W;
     double* const gl = A.gws + (size_t)cta * (size_t)A.slab_doubles + lane;
@@ -154,7 +250,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
     const long long ntile = (total + LPT - 1) / LPT;
     const double us_power = R[I[G3H_US_ROFF]], us_weight = R[I[G3H_US_ROFF] + 1];
     const bool have_us = I[G3H_US_N] > 0;
-    const int wc0 = keeper ? 0 : tb[A.wcol_off + warp], wc1 = keeper ? 0 : tb[A.wcol_off + warp + 1];     // this warp's columns: tb[wc0..wc1)
+    const int wu0 = keeper ? 0 : tb[A.wunit_off + warp], wu1 = keeper ? 0 : tb[A.wunit_off + warp + 1];     // this warp's units: tb[wu0..wu1)
 
     for (long long tile = cta; tile < ntile; tile += ncta) {
         const long long work0 = tile * LPT + lane;
@@ -178,8 +274,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 
         G3T_BAR();      // the previous tile is fully retired before the slab and the state are reused
 
-        // ================= scalar formula slots, once per parameter vector
+        // ================= scalar formula slots, once per parameter vector; pads and band tables start from zero
         for (int i = warp; i < A.NSLOT; i += W) GS(A.g_slot + i, eval_slot_g<T>(I, R, prow, seed, i));
+        for (int z = 0; z < A.zr_n; z++) {
+            const int space = tb[A.zr_off + 3 * z], e0 = tb[A.zr_off + 3 * z + 1], n = tb[A.zr_off + 3 * z + 2];
+            for (int i = warp; i < n; i += W) { if (space) SS(e0 + i, T(0.0)); else GS(e0 + i, T(0.0)); }
+        }
         G3T_BAR();
 
         // ================= per-evaluation tables. Work units are dealt round-robin to the warps.
@@ -254,16 +354,16 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
             const int n2 = St.grow_n;
             if (n2 < 0) continue;
             const int32_t* gs = I + St.grow_ioff;
-            for (int l = 0; l < L; l++)
-                if (mine()) GS(St.g_pw + l, xpow(midlen[l], SLOT(gs[4])));
-            // ---- growth bands, source-oriented: row l holds P(l -> l + x), x = 0..n (growth_bbinom in product
-            // form, R/action_grow.R:155-213); row L holds the plus-group tail sums, [d] = sum_{x >= d} P(L-1-d -> .)
-            // (R/action_grow.R:233-271). Continuous maturity splits each row into the staying and the maturing
-            // part (R/action_mature.R:1-42, R/action_grow.R:420-437); with an age term there is a set per column.
+            for (int l = 0; l < L; l++)         // walpha l^wbeta (g3a_grow_weightsimple, R/action_grow.R:58-71)
+                if (mine()) GS(St.g_wq + l, SLOT(gs[3]) * xpow(midlen[l], SLOT(gs[4])));
+            // ---- growth bands: P(l -> l + x), x = 0..n, of each source row l (growth_bbinom in product form,
+            // R/action_grow.R:155-213), stored destination-oriented: entry [l + x][x]; everything that would leave the
+            // length axis is summed into the plus group's row L - 1 (R/action_grow.R:233-271). Continuous maturity splits
+            // each entry into the staying and the maturing part (R/action_mature.R:1-42, R/action_grow.R:420-437); with an
+            // age term there is a set per column.
             const bool cont = St.mat_kind == G3MAT_CONTINUOUS && St.has_out;
             const double pdl = R[St.plusdl_roff];
             const int nset = St.band_percol ? St.ncol : 1;
-            const int n1 = n2 + 1;
             for (int set = 0; set < nset; set++)
                 for (int idt = 0; idt < A.ndt; idt++)
                     for (int l = 0; l < L; l++) {
@@ -284,9 +384,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                             if (ms[2] >= 0) { mbeta = SLOT(ms[2]); inner = inner - mbeta * ((double)(St.minage + set % St.nage) - SLOT(ms[3])); }
                             m0 = 1.0 / (1.0 + xexp(inner));
                         }
-                        const int row = (set * A.ndt + idt) * St.bsz + l * n1;
-                        const int tail = (set * A.ndt + idt) * St.bsz + L * n1;
-                        const int dtail = L - 1 - l;            // this row's entry of the tail row, if within the band
+                        const int base = (set * A.ndt + idt) * St.bsz;
+                        const int dtail = L - 1 - l;            // jumps of at least dtail end in the plus group
                         T ta(0.0), tr(0.0);
                         T gx[NW], rx[NW];
 #pragma unroll
@@ -296,9 +395,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                                 if (cont) {
                                     const T ratio = dif_pminmax_c(m0 * (malpha * (pdl * x) + mbeta * dt), 0.0, 1.0, 1e5);
                                     rx[x] = g * ratio; gx[x] = g * (1.0 - ratio);
-                                    GS(St.g_bandr + row + x, rx[x]);
                                 } else gx[x] = g;
-                                GS(St.g_band + row + x, gx[x]);
+                                if (x < dtail) {
+                                    GS(St.g_band + base + (l + x) * NW + x, gx[x]);
+                                    if (cont) GS(St.g_bandr + base + (l + x) * NW + x, rx[x]);
+                                }
                                 if (x < n2)
                                     g = g * ((double)(n2 - x) / (double)(x + 1)) * (xabs(alpha + (double)x) / (beta + (double)(n2 - x - 1)));
                             }
@@ -307,14 +408,14 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 #pragma unroll
                             for (int x = 0; x < NW; x++)
                                 if (x >= dtail && x <= n2) { ta = ta + gx[x]; tr = tr + rx[x]; }
-                            GS(St.g_band + tail + dtail, ta);
-                            if (cont) GS(St.g_bandr + tail + dtail, tr);
+                            GS(St.g_band + base + (L - 1) * NW + dtail, ta);
+                            if (cont) GS(St.g_bandr + base + (L - 1) * NW + dtail, tr);
                         }
                     }
         }
-        // ---- own columns: mortality factors, initial conditions, maturation remainder, constant-maturity ratios
-        for (int wi = wc0; wi < wc1; wi++) {
-            const ColRec& Cl = A.col[tb[wi]];
+        // ---- per column: mortality factors, initial conditions, maturation remainder, constant-maturity ratios
+        for (int gc = warp; gc < A.NCOLS; gc += W) {
+            const ColRec& Cl = A.col[gc];
             const StockRec& St = A.st[Cl.s];
             const int L = St.L, col = Cl.col;
             const double* midlen = R + St.midlen_roff;
@@ -351,11 +452,10 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                 }
             }
         }
-        // ---- g3l_bounds_penalty terms (R/likelihood_bounds.R:13-16); warp 0 adds them in run order below
+        // ---- g3l_bounds_penalty terms (R/likelihood_bounds.R:13-16); the keeper warp adds them in run order below
         {
             const double bs = A.NBOUND > 0 ? R[I[G3H_BOUND_WS_ROFF] + 1] : 0.0;
-            for (int i = 0; i < A.NBOUND; i++) {
-                if (!mine()) continue;
+            for (int i = warp; i < A.NBOUND; i += W) {
                 const T p = mkpar_g<T>(prow, seed, I[I[G3H_BOUND_OFF] + i]);
                 const double lo = R[I[G3H_BOUND_ROFF] + 2 * i], up = R[I[G3H_BOUND_ROFF] + 2 * i + 1];
                 const T a = lsa_c(bs * (p - up) / (up - lo), 0.0) + lsa_c(bs * (lo - p) / (up - lo), 0.0);
@@ -445,10 +545,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 
             // ================= g3a_predate step 1: suitable biomass per (predator, area[, predator length]) (R/action_predate.R:314-333)
             if (pred_now) {
-                for (int wi = wc0; wi < wc1; wi++) {        // partial sums of the own columns
-                    const ColRec& Cl = A.col[tb[wi]];
+                for (int wi = wu0; wi < wu1; wi++) {        // partial sums of the own units
+                    const UnitRec& U = A.unit[tb[wi]];
+                    const ColRec& Cl = A.col[U.gc];
                     const StockRec& St = A.st[Cl.s];
-                    const int L = St.L;
+                    const int L = St.L, c_lo = Cl.cell0 + U.lo;
                     for (int j = 0; j < St.pp_n; j++) {
                         const int q = tb[St.pp_off + j];
                         const PairRec& Q = A.pp[q];
@@ -458,11 +559,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                         const bool by_number = Q.pred_kind == G3PRED_NUMBERFLEET;       // suit = S * num (R/action_predate.R:7-11)
                         for (int pl = 0; pl < Q.PL; pl++) {
                             T cs(0.0);
-                            for (int l = 0; l < L; l++) {
-                                const T n = S(A.s_num + Cl.cell0 + l);
-                                cs = cs + G(Q.g_suit + pl * L + l) * (by_number ? n : n * S(A.s_wgt + Cl.cell0 + l));
+                            for (int r = 0; r < U.len; r++) {
+                                const T n = S(A.s_num + c_lo + r);
+                                cs = cs + G(Q.g_suit + pl * L + U.lo + r) * (by_number ? n : n * S(A.s_wgt + c_lo + r));
                             }
-                            GS(Q.g_part + Cl.col * Q.PL + pl, spred ? cs * SLOT(Q.energy_slot) : cs);
+                            GS(Q.g_part + U.lu * Q.PL + pl, spred ? cs * SLOT(Q.energy_slot) : cs);
                         }
                     }
                 }
@@ -504,9 +605,9 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                 G3T_BAR();
             }
 
-            // ---- what a cell does once its growth is through: hand-over, renewal, store, collect vectors. Elementwise, so it
-            // runs on blocks of NB cells (l0 - b, b < nb) with the avoid_zero / reciprocal chains of the NB cells interleaved.
-            auto finish_block = [&](const ColRec& Cl, const StockRec& St, const int l0, const int nb, T (&num)[NB], T (&wgt)[NB],
+            // ---- what a block of rows does once its growth is through: hand-over, renewal, store, collect vectors.
+            // Rows row0 .. row0 + NB - 1 of a column, the first nb of them real (the others are computed and dropped).
+            auto finish_block = [&](const ColRec& Cl, const StockRec& St, const int row0, const int nb, T (&num)[NB], T (&wgt)[NB],
                                     const bool inc_here, const int ren_mask) {
                 const int L = St.L;
                 // g3a_step_transition (R/action_mature.R:78-134): maturing fish arriving from their source column
@@ -515,7 +616,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                     T nu[NB], de[NB], mv[NB];
 #pragma unroll
                     for (int b = 0; b < NB; b++) {
-                        const int l = max(l0 - b, 0);
+                        const int l = min(row0 + b, L - 1);
                         mv[b] = S(Cl.inc_tn + l) * ratio;
                         nu[b] = wgt[b] * num[b] + S(Cl.inc_tw + l) * mv[b];     // ratio_add_pop, R/aab_env.R:133-153
                         de[b] = num[b] + mv[b];
@@ -534,7 +635,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                             T nu[NB], de[NB], rn[NB];
 #pragma unroll
                             for (int b = 0; b < NB; b++) {
-                                const int l = max(l0 - b, 0);
+                                const int l = min(row0 + b, L - 1);
                                 rn[b] = G(St.g_rd + r * L + l) * factor;
                                 nu[b] = wgt[b] * num[b] + G(St.g_rw + r * L + l) * rn[b];
                                 de[b] = num[b] + rn[b];
@@ -543,12 +644,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 #pragma unroll
                             for (int b = 0; b < NB; b++) { wgt[b] = nu[b]; num[b] = num[b] + rn[b]; }
                         }
+                const int cell = Cl.cell0 + row0;
 #pragma unroll
                 for (int b = 0; b < NB; b++)
-                    if (b < nb) { SS(A.s_num + Cl.cell0 + l0 - b, num[b]); SS(A.s_wgt + Cl.cell0 + l0 - b, wgt[b]); }
+                    if (b < nb) { SS(A.s_num + cell + b, num[b]); SS(A.s_wgt + cell + b, wgt[b]); }
                 // collect vectors for g3l_distribution (R/likelihood_distribution.R:275-287)
                 if (xact) {
-                    const int cell0 = Cl.cell0;
                     bool any_cn = false;        // catch in numbers: cons / avoid_zero(wgt)
                     for (int j = 0; j < St.cx_n; j++) { const int x = tb[St.cx_off + j]; any_cn = any_cn || (((xact >> x) & 1) && A.xb[x].unit == 0); }
                     if (any_cn) {
@@ -559,18 +660,18 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                         for (int j = 0; j < St.cx_n; j++) {
                             const int x = tb[St.cx_off + j];
                             if (!(((xact >> x) & 1) && A.xb[x].unit == 0)) continue;
-                            const int gx = A.xb[x].g_x + cell0;
+                            const int gx = A.xb[x].g_x + cell;
 #pragma unroll
-                            for (int b = 0; b < NB; b++) if (b < nb) GS(gx + l0 - b, G(gx + l0 - b) * iw[b]);
+                            for (int b = 0; b < NB; b++) if (b < nb) GS(gx + b, G(gx + b) * iw[b]);
                         }
                     }
                     for (int j = 0; j < A.ax_n; j++) {          // abundance
                         const int x = tb[A.ax_off + j];
                         if (!((xact >> x) & 1)) continue;
-                        const int gx = A.xb[x].g_x + cell0;
+                        const int gx = A.xb[x].g_x + cell;
                         const bool by_num = A.xb[x].unit == 0;
 #pragma unroll
-                        for (int b = 0; b < NB; b++) if (b < nb) GS(gx + l0 - b, by_num ? num[b] : num[b] * wgt[b]);
+                        for (int b = 0; b < NB; b++) if (b < nb) GS(gx + b, by_num ? num[b] : num[b] * wgt[b]);
                     }
                 }
             };
@@ -583,63 +684,58 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                 return ren_mask;
             };
 
-            // ================= own columns: predation, natural mortality, growth (+ maturing split), and -- unless
-            // maturing fish are about to arrive -- renewal and the collect vectors
-            for (int wi = wc0; wi < wc1; wi++) {
-                const ColRec& Cl = A.col[tb[wi]];
+            // ================= own units, pass 1: g3a_predate (R/action_predate.R:335-406) in blocks of NB rows, ascending
+            // (the order of the sums); then the unit's top rows go to the ghost rows of the unit above
+            for (int wi = wu0; wi < wu1; wi++) {
+                const UnitRec& U = A.unit[tb[wi]];
+                const ColRec& Cl = A.col[U.gc];
                 const StockRec& St = A.st[Cl.s];
-                const int L = St.L, nq = St.pp_n, cell0 = Cl.cell0;
+                const int L = St.L, nq = St.pp_n, c_lo = Cl.cell0 + U.lo;
                 const bool prey_now = pred_now && nq > 0;
-                const int grow_n = St.grow_n;
-                const bool trans_now = grow_n >= 0 && St.has_out && ((St.trans_mask >> step) & 1);
-                const bool cont_now = trans_now && St.mat_kind == G3MAT_CONTINUOUS;
-                const bool const_now = trans_now && St.mat_kind == G3MAT_CONSTANT;
-                const bool has_mort = St.mort_ioff >= 0;
-                const bool inc_here = Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1);
-                const int ren_mask = renewals_now(St);
                 const bool catch_now = any_catch && nq > 0;
-                double* const pNum = SP(A.s_num + cell0);
-                double* const pWgt = SP(A.s_wgt + cell0);
-
-                // ---------- g3a_predate (R/action_predate.R:335-406): blocks of NB cells, ascending (the order of the sums)
+                double* const pNum = SP(A.s_num + c_lo);
+                double* const pWgt = SP(A.s_wgt + c_lo);
                 if (prey_now) {
-                    const int ws0 = A.g_wscr + warp * A.wscr_n;
-                    for (int k = 0; k < nq; k++) {      // landings / total suitable biomass of each fleet in this column's area
+                    // consumption per unit of biomass at each row: all pairs (j = 0), the pairs feeding catch collect vector j - 1
+                    const int cfb = A.g_wscr + warp * A.wscr_n, cfr = A.cf_rows;
+                    const int rows = (U.len + NB - 1) / NB * NB;
+                    const int ncf = catch_now ? 1 + St.cx_n : 1;
+                    for (int j = 0; j < ncf; j++)
+                        for (int r = 0; r < rows; r++) GS(cfb + j * cfr + r, T(0.0));
+                    for (int k = 0; k < nq; k++) {
                         const PairRec& Q = A.pp[tb[St.pp_off + k]];
                         const int ts = tb[Q.tsid_off + Cl.ridx];
-                        if (ts < 0 || Q.pred_kind == G3PRED_STOCK) continue;
-                        T e = G(A.g_eot + ts);
-                        if (Q.pred_kind == G3PRED_EFFORTFLEET) e = e * SLOT(Q.energy_slot);      // catchability_fs of this prey
-                        GS(ws0 + k, e);
+                        if (ts < 0) continue;
+                        const int cxm = catch_now ? Q.cxmask : 0;
+                        const bool spred = Q.pred_kind == G3PRED_STOCK;
+                        T e(0.0);
+                        if (!spred) {       // landings / total suitable biomass of this fleet in this column's area
+                            e = G(A.g_eot + ts);
+                            if (Q.pred_kind == G3PRED_EFFORTFLEET) e = e * SLOT(Q.energy_slot);      // catchability_fs of this prey
+                        }
+                        const int gp = spred ? A.pred[Q.pred].g_pts + ts * Q.PL : 0;
+                        for (int r = 0; r < U.len; r++) {
+                            T cf(0.0);
+                            if (!spred) cf = G(Q.g_suit + U.lo + r) * e;
+                            else        // sum over the predator's length groups of suitability x consumption factor
+                                for (int pl = 0; pl < Q.PL; pl++) cf = cf + G(Q.g_suit + pl * L + U.lo + r) * G(gp + pl);
+                            GS(cfb + r, G(cfb + r) + cf);
+                            for (int j = 0; j < St.cx_n; j++)
+                                if ((cxm >> j) & 1) GS(cfb + (1 + j) * cfr + r, G(cfb + (1 + j) * cfr + r) + cf);
+                        }
                     }
-                    // consumption per unit of biomass by predator k at length l
-                    auto cfac = [&](const PairRec& Q, const int k, const int ts, const int l) {
-                        if (Q.pred_kind != G3PRED_STOCK) return G(Q.g_suit + l) * G(ws0 + k);
-                        T cf(0.0);      // sum over the predator's length groups of suitability x consumption factor
-                        const int gp = A.pred[Q.pred].g_pts + ts * Q.PL;
-                        for (int pl = 0; pl < Q.PL; pl++) cf = cf + G(Q.g_suit + pl * L + l) * G(gp + pl);
-                        return cf;
-                    };
+                    const double* const pCf = GP(cfb);
                     T o1(0.0), o2(0.0);
-                    for (int l0 = 0; l0 < L; l0 += NB) {
-                        const int nb = min(NB, L - l0);
+                    for (int r0 = 0; r0 < U.len; r0 += NB) {
+                        const int nb = min(NB, U.len - r0);
                         T num[NB], B0[NB], tp[NB], cr[NB], de[NB];
 #pragma unroll
                         for (int b = 0; b < NB; b++) {
-                            const int l = min(l0 + b, L - 1);
-                            num[b] = ldT<T>(pNum + (unsigned)l * C);
-                            B0[b] = num[b] * ldT<T>(pWgt + (unsigned)l * C);
-                            tp[b] = T(0.0);
+                            num[b] = ldT<T>(pNum + (unsigned)(r0 + b) * C);
+                            B0[b] = num[b] * ldT<T>(pWgt + (unsigned)(r0 + b) * C);
+                            tp[b] = ldT<T>(pCf + (unsigned)(r0 + b) * C) * B0[b];
+                            cr[b] = tp[b]; de[b] = B0[b];
                         }
-                        for (int k = 0; k < nq; k++) {
-                            const PairRec& Q = A.pp[tb[St.pp_off + k]];
-                            const int ts = tb[Q.tsid_off + Cl.ridx];
-                            if (ts < 0) continue;
-#pragma unroll
-                            for (int b = 0; b < NB; b++) tp[b] = tp[b] + cfac(Q, k, ts, min(l0 + b, L - 1)) * B0[b];
-                        }
-#pragma unroll
-                        for (int b = 0; b < NB; b++) { cr[b] = tp[b]; de[b] = B0[b]; }
                         div_azx_n(cr, de);                      // consratio = tp / avoid_zero(B0)   (exact-division forms: g3_math.cuh)
                         dif_pmax_x_n(cr, 0.95, -1e3);           // dif_pmin(consratio, 0.95, 1e3)
                         T tpn[NB];
@@ -647,7 +743,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                         for (int b = 0; b < NB; b++) {
                             tpn[b] = B0[b] * cr[b];
                             if (b < nb) {
-                                stT<T>(pNum + (unsigned)(l0 + b) * C, num[b] * (1.0 - cr[b]));
+                                stT<T>(pNum + (unsigned)(r0 + b) * C, num[b] * (1.0 - cr[b]));
                                 o1 = o1 + tp[b]; o2 = o2 + tpn[b];
                             }
                         }
@@ -661,125 +757,162 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                             for (int j = 0; j < St.cx_n; j++) {
                                 const int x = tb[St.cx_off + j];
                                 if (!((xact >> x) & 1)) continue;
-                                T fx[NB];
 #pragma unroll
-                                for (int b = 0; b < NB; b++) fx[b] = T(0.0);
-                                for (int k = 0; k < nq; k++) {
-                                    const PairRec& Q = A.pp[tb[St.pp_off + k]];
-                                    const int ts = tb[Q.tsid_off + Cl.ridx];
-                                    if (ts < 0 || !((Q.cxmask >> j) & 1)) continue;
-#pragma unroll
-                                    for (int b = 0; b < NB; b++) fx[b] = fx[b] + cfac(Q, k, ts, min(l0 + b, L - 1));
-                                }
-#pragma unroll
-                                for (int b = 0; b < NB; b++) if (b < nb) GS(A.xb[x].g_x + cell0 + l0 + b, fx[b] * cc[b]);
+                                for (int b = 0; b < NB; b++)
+                                    if (b < nb) GS(A.xb[x].g_x + c_lo + r0 + b, G(cfb + (1 + j) * cfr + r0 + b) * cc[b]);
                             }
                         }
                     }
-                    GS(Cl.g_usp, o1); GS(Cl.g_usp + 1, o2);
+                    GS(U.g_usp, o1); GS(U.g_usp + 1, o2);
                 } else if (catch_now) {
                     for (int j = 0; j < St.cx_n; j++) {
                         const int x = tb[St.cx_off + j];
                         if ((xact >> x) & 1)
-                            for (int l = 0; l < L; l++) GS(A.xb[x].g_x + cell0 + l, T(0.0));       // no landings: cons = 0
+                            for (int r = 0; r < U.len; r++) GS(A.xb[x].g_x + c_lo + r, T(0.0));       // no landings: cons = 0
                     }
                 }
-                if (!has_mort && grow_n < 0 && !inc_here && !ren_mask && xact == 0) continue;
+                if (U.up_ghost >= 0) {
+#pragma unroll
+                    for (int i = 0; i < NW - 1; i++) {
+                        GS(U.up_ghost + i, ldT<T>(pNum + (unsigned)(U.len - (NW - 1) + i) * C));
+                        GS(U.up_ghost + (NW - 1) + i, ldT<T>(pWgt + (unsigned)(U.len - (NW - 1) + i) * C));
+                    }
+                }
+            }
+            if (A.any_ghost) G3T_BAR();
 
-                // ---------- natural mortality and growth. Length growth only looks DOWN the length axis, so walking l
-                // from the top the update is in place: every source l - d is still the old value when l is rebuilt.
+            // ================= own units, pass 2: natural mortality, growth (+ maturing split), and -- unless maturing fish are
+            // about to arrive -- renewal and the collect vectors. Length growth only looks DOWN the length axis, so sweeping
+            // the blocks from the top the update is in place: every source row is still the old value when a block is rebuilt.
+            for (int wi = wu0; wi < wu1; wi++) {
+                const UnitRec& U = A.unit[tb[wi]];
+                const ColRec& Cl = A.col[U.gc];
+                const StockRec& St = A.st[Cl.s];
+                const int L = St.L, c_lo = Cl.cell0 + U.lo;
+                const int grow_n = St.grow_n;
+                const bool trans_now = grow_n >= 0 && St.has_out && ((St.trans_mask >> step) & 1);
+                const bool cont_now = trans_now && St.mat_kind == G3MAT_CONTINUOUS;
+                const bool const_now = trans_now && St.mat_kind == G3MAT_CONSTANT;
+                const bool has_mort = St.mort_ioff >= 0;
+                const bool inc_here = Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1);
+                const int ren_mask = renewals_now(St);
+                double* const pNum = SP(A.s_num + c_lo);
+                double* const pWgt = SP(A.s_wgt + c_lo);
+                if (!has_mort && grow_n < 0 && !inc_here && !ren_mask && xact == 0) continue;
                 const T mortf = has_mort ? G(St.g_mort + idt * St.ncol + Cl.col) : T(1.0);
+                const int nblk = (U.len + NB - 1) / NB;
                 if (grow_n < 0) {
-                    for (int l0 = L - 1; l0 >= 0; l0 -= NB) {
-                        const int nb = min(NB, l0 + 1);
+                    for (int j = nblk - 1; j >= 0; j--) {
+                        const int r0 = j * NB, nb = min(NB, U.len - r0);
                         T num[NB], wgt[NB];
 #pragma unroll
                         for (int b = 0; b < NB; b++) {
-                            const int l = max(l0 - b, 0);
-                            num[b] = ldT<T>(pNum + (unsigned)l * C) * mortf; wgt[b] = ldT<T>(pWgt + (unsigned)l * C);
+                            num[b] = ldT<T>(pNum + (unsigned)(r0 + b) * C) * mortf; wgt[b] = ldT<T>(pWgt + (unsigned)(r0 + b) * C);
                         }
-                        if (!inc_here) finish_block(Cl, St, l0, nb, num, wgt, false, ren_mask);
+                        if (!inc_here) finish_block(Cl, St, U.lo + r0, nb, num, wgt, false, ren_mask);
                         else {
 #pragma unroll
-                            for (int b = 0; b < NB; b++) if (b < nb) stT<T>(pNum + (unsigned)(l0 - b) * C, num[b]);
+                            for (int b = 0; b < NB; b++) if (b < nb) stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]);
                         }
                     }
                     continue;
                 }
-                const int n1 = grow_n + 1;
-                const T wal = SLOT(I[St.grow_ioff + 3]);
                 const T remf = trans_now ? G(Cl.g_remf) : T(0.0);
-                const int bset = ((St.band_percol ? Cl.col : 0) * A.ndt + idt) * St.bsz;
+                const int bset = ((St.band_percol ? Cl.col : 0) * A.ndt + idt) * St.bsz + U.lo * NW;
                 const double* const pB = GP(St.g_band + bset);
                 const double* const pBr = GP(St.g_bandr + bset);
-                const double* const pPw = GP(St.g_pw);
-                const double* const pCm = St.g_cmat >= 0 ? GP(St.g_cmat + Cl.col * L) : pPw;
+                const double* const pQ = GP(St.g_wq + U.lo);
+                const double* const pCm = St.g_cmat >= 0 ? GP(St.g_cmat + Cl.col * L + U.lo) : pQ;
+                const double* const pGh = U.g_ghost >= 0 ? GP(U.g_ghost) : pQ;
                 const bool stash = trans_now && Cl.s_tn >= 0;
-                const unsigned bstep = (unsigned)(n1 - 1) * C;      // band entry of (source l - d, jump d) sits d * bstep below entry (l, 0)
-                for (int l0 = L - 1; l0 >= 0; l0 -= NB) {
-                    const int nb = min(NB, l0 + 1);
-                    // ---- g3a_growmature (R/action_grow.R:340-497): banded gather over the sources l - d, NB cells
-                    T an[NB], aw[NB], bn[NB], bw[NB];
+                double* const pTn = stash ? SP(Cl.s_tn + U.lo) : pNum;
+                double* const pTw = stash ? SP(Cl.s_tw + U.lo) : pWgt;
+                double* const pBn = GP(A.g_wscr + warp * A.wscr_n);        // the staying fish of each row, where num also takes the remainder back
+                // Mean weight = sum / avoid_zero(number). With more than 0.034 fish avoid_zero() is the identity (g3_math.cuh), which is
+                // the case for most rows on most steps: sweep 1 divides plainly where EVERY lane has that many and notes the other
+                // rows (bit r of need_*), sweep 2 runs the avoid_zero chain for those alone, NB rows at a time.
+                unsigned long long need_b = 0, need_a = 0;
+                for (int j = nblk - 1; j >= 0; j--) {
+                    const int r0 = j * NB, nb = min(NB, U.len - r0);
+                    T an[NB], aw[NB], num[NB], wgt[NB];
+                    const bool low = U.g_ghost >= 0 && r0 < NW - 1;
+                    if (cont_now) {
+                        if (low) grow_gather<T, NW, NB, 1, true>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
+                        else grow_gather<T, NW, NB, 1, false>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
+                    } else if (const_now) {
+                        if (low) grow_gather<T, NW, NB, 2, true>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
+                        else grow_gather<T, NW, NB, 2, false>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
+                    } else {
+                        if (low) grow_gather<T, NW, NB, 0, true>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
+                        else grow_gather<T, NW, NB, 0, false>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
+                    }
 #pragma unroll
                     for (int b = 0; b < NB; b++) {
-                        const int l = max(l0 - b, 0);
-                        const T pw_l = ldT<T>(pPw + (unsigned)l * C);
-                        // row l of the band, or the plus group's tail sums
-                        const bool top = l == L - 1;
-                        const unsigned brow = (top ? (unsigned)(L * n1) : (unsigned)(l * n1)) * C;
-                        T a_n(0.0), a_w(0.0), b_n(0.0), b_w(0.0);
-#pragma unroll
-                        for (int d = 0; d < NW; d++) {
-                            if (d <= grow_n && d <= l) {
-                                const unsigned so = (unsigned)(l - d) * C;
-                                const unsigned be = top ? brow + (unsigned)d * C : brow - (unsigned)d * bstep;
-                                const T ns = ldT<T>(pNum + so) * mortf;
-                                const T gd = ldT<T>(pB + be);
-                                const T dwd = wal * (pw_l - ldT<T>(pPw + so));      // walpha (l^wbeta - (l-d)^wbeta), R/action_grow.R:58-71
-                                const T wsrc = dwd + ldT<T>(pWgt + so);
-                                if (cont_now) {
-                                    const T grd = ldT<T>(pBr + be);
-                                    const T w = wsrc * ns;
-                                    a_n = a_n + grd * ns; a_w = a_w + grd * w;
-                                    b_n = b_n + gd * ns; b_w = b_w + gd * w;
-                                } else if (const_now) {
-                                    // g3a_mature_constant ratio of the SOURCE cell (R/action_mature.R:44-74, R/action_grow.R:438-457)
-                                    const T ratio = ldT<T>(pCm + so);
-                                    const T m1 = (ns * ratio) * gd, m2 = (ns * (1.0 - ratio)) * gd;
-                                    a_n = a_n + m1; a_w = a_w + wsrc * m1;
-                                    b_n = b_n + m2; b_w = b_w + wsrc * m2;
-                                } else {
-                                    const T m2 = ns * gd;
-                                    b_n = b_n + m2; b_w = b_w + wsrc * m2;
-                                }
-                            }
-                        }
-                        an[b] = a_n; aw[b] = a_w; bn[b] = b_n; bw[b] = b_w;
+                        const bool plenty = G3_ALL(az_is_identity(num[b]));
+                        if (b < nb && !plenty) need_b |= 1ull << (r0 + b);
+                        if (plenty) wgt[b] = div_plenty(wgt[b], num[b]);
                     }
-                    // ---- mean weights (one avoid_zero + reciprocal per cell and part), interleaved over the block
-                    T num[NB], wgt[NB], de[NB];
-#pragma unroll
-                    for (int b = 0; b < NB; b++) { num[b] = bn[b]; wgt[b] = bw[b]; de[b] = bn[b]; }
-                    div_az_n(wgt, de);
                     if (trans_now) {
                         if (stash) {
 #pragma unroll
-                            for (int b = 0; b < NB; b++) de[b] = an[b];
-                            div_az_n(aw, de);
-#pragma unroll
-                            for (int b = 0; b < NB; b++) if (b < nb) { SS(Cl.s_tn + l0 - b, an[b]); SS(Cl.s_tw + l0 - b, aw[b]); }
+                            for (int b = 0; b < NB; b++) {
+                                const bool plenty = G3_ALL(az_is_identity(an[b]));
+                                if (b < nb && !plenty) need_a |= 1ull << (r0 + b);
+                                if (plenty) aw[b] = div_plenty(aw[b], an[b]);
+                                if (b < nb) { stT<T>(pTn + (unsigned)(r0 + b) * C, an[b]); stT<T>(pTw + (unsigned)(r0 + b) * C, aw[b]); }
+                            }
                         }
                         // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
 #pragma unroll
-                        for (int b = 0; b < NB; b++) num[b] = num[b] + an[b] * remf;
+                        for (int b = 0; b < NB; b++) {
+                            if (b < nb) stT<T>(pBn + (unsigned)(r0 + b) * C, num[b]);
+                            num[b] = num[b] + an[b] * remf;
+                        }
                     }
-                    if (!inc_here) finish_block(Cl, St, l0, nb, num, wgt, false, ren_mask);
-                    else {
 #pragma unroll
-                        for (int b = 0; b < NB; b++)
-                            if (b < nb) { stT<T>(pNum + (unsigned)(l0 - b) * C, num[b]); stT<T>(pWgt + (unsigned)(l0 - b) * C, wgt[b]); }
-                    }
+                    for (int b = 0; b < NB; b++)
+                        if (b < nb) { stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]); stT<T>(pWgt + (unsigned)(r0 + b) * C, wgt[b]); }
                 }
+                // ---- sweep 2: the rows that need the avoid_zero chain (the last group repeats its last row: same value, same store)
+                const double* const pDe = trans_now ? pBn : pNum;
+                while (need_b) {
+                    int r[NB];
+                    T w[NB], de[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        r[b] = need_b ? G3_FFSLL(need_b) - 1 : r[b > 0 ? b - 1 : 0];
+                        need_b &= need_b - 1;
+                        w[b] = ldT<T>(pWgt + (unsigned)r[b] * C); de[b] = ldT<T>(pDe + (unsigned)r[b] * C);
+                    }
+                    div_az_n(w, de);
+#pragma unroll
+                    for (int b = 0; b < NB; b++) stT<T>(pWgt + (unsigned)r[b] * C, w[b]);
+                }
+                while (need_a) {
+                    int r[NB];
+                    T w[NB], de[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        r[b] = need_a ? G3_FFSLL(need_a) - 1 : r[b > 0 ? b - 1 : 0];
+                        need_a &= need_a - 1;
+                        w[b] = ldT<T>(pTw + (unsigned)r[b] * C); de[b] = ldT<T>(pTn + (unsigned)r[b] * C);
+                    }
+                    div_az_n(w, de);
+#pragma unroll
+                    for (int b = 0; b < NB; b++) stT<T>(pTw + (unsigned)r[b] * C, w[b]);
+                }
+                // ---- sweep 3, on the steps that have any: renewal into this column, collect vectors
+                bool ren_here = false;
+                for (int r = 0; r < St.n_renew; r++)
+                    ren_here = ren_here || (((ren_mask >> r) & 1) && Cl.aidx == I[St.renew_ioff + r * G3R_LEN + G3R_AGE_IDX]);
+                if (!inc_here && (ren_here || xact))
+                    for (int j = 0; j < nblk; j++) {
+                        const int r0 = j * NB, nb = min(NB, U.len - r0);
+                        T num[NB], wgt[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; b++) { num[b] = ldT<T>(pNum + (unsigned)(r0 + b) * C); wgt[b] = ldT<T>(pWgt + (unsigned)(r0 + b) * C); }
+                        finish_block(Cl, St, U.lo + r0, nb, num, wgt, false, ren_mask);
+                    }
             }
 
             // ================= columns that receive maturing fish finish once every source column has grown. That part is
@@ -792,21 +925,25 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                     if (!(Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1))) continue;
                     const StockRec& St = A.st[Cl.s];
                     const int ren_mask = renewals_now(St);
-                    for (int l0 = St.L - 1; l0 >= 0; l0 -= NB) {
+                    for (int r0 = 0; r0 < St.L; r0 += NB) {
                         if (!mine()) continue;
-                        const int nb = min(NB, l0 + 1);
+                        const int nb = min(NB, St.L - r0);
                         T num[NB], wgt[NB];
 #pragma unroll
-                        for (int b = 0; b < NB; b++) { const int l = max(l0 - b, 0); num[b] = S(A.s_num + Cl.cell0 + l); wgt[b] = S(A.s_wgt + Cl.cell0 + l); }
-                        finish_block(Cl, St, l0, nb, num, wgt, true, ren_mask);
+                        for (int b = 0; b < NB; b++) { const int l = min(r0 + b, St.L - 1); num[b] = S(A.s_num + Cl.cell0 + l); wgt[b] = S(A.s_wgt + Cl.cell0 + l); }
+                        finish_block(Cl, St, r0, nb, num, wgt, true, ren_mask);
                     }
                 }
             }
 
-            // ================= g3l_distribution collect: model[dest] += lgmatrix . x (R/likelihood_distribution.R:288-364)
+            // ================= g3l_distribution collect: model[dest] += lgmatrix . x (R/likelihood_distribution.R:288-364).
+            // The planner cut the (dest, term) lists into TASKS of at most a few dozen terms and dealt them to the warps by
+            // size (a survey index sums every cell of its stocks into ONE dest: 260 terms on C2). A task of an unsplit dest
+            // adds to the model entry; the tasks of a split dest leave partial sums that the dest's owner adds up below.
+            // Where the comparison needs the total of a group of dests (sumofsquares: the area group's whole slab;
+            // multinomial: each slice), every warp also keeps its share of that total.
             if (cact) {
                 G3T_BAR();
-                ucnt = 0;
                 for (int c = 0; c < A.NCOMP; c++) {
                     if (!((cact >> c) & 1)) continue;
                     const CompRec& Cm = A.comp[c];
@@ -814,82 +951,82 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                     const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
                     const int ms = Cm.g_ms + (si ? I[Cm.tidx_ioff + t] * nd : 0);
                     const int xs = A.xb[Cm.xbuf].g_x;
-                    if (Cm.mode == 0) {
-                        const int32_t* ptr = I + Cm.csr_ptr_ioff;
-                        const int32_t* idx = I + Cm.csr_idx_ioff;
-                        const double* cf = R + Cm.csr_coef_roff;
-                        for (int e = 0; e < nd; e++) {
-                            if (!mine()) continue;
-                            T acc = G(ms + e);
-                            for (int j = ptr[e]; j < ptr[e + 1]; j++) acc = acc + cf[j] * G(xs + idx[j]);
-                            GS(ms + e, acc);
-                        }
-                    } else {
-                        const int32_t* cd = I + Cm.cell_dest_ioff;
-                        const double* cf = R + Cm.cell_coef_roff;
-                        for (int e = 0; e < nd; e++) {
-                            if (!mine()) continue;
-                            T acc = G(ms + e);
-                            for (int i = 0; i < A.NC; i++) if (cd[i] == e) acc = acc + cf[i] * G(xs + i);
-                            GS(ms + e, acc);
-                        }
+                    const bool tot_now = Cm.n_groups > 0 && I[Cm.cmp_ioff + t];
+                    if (tot_now) for (int g = 0; g < Cm.n_groups; g++) GS(Cm.g_pt + g * 16 + warp, T(0.0));
+                    const int32_t* __restrict__ ci = A.cterm_idx;
+                    const double* __restrict__ cc = A.cterm_coef;
+                    for (int k = tb[Cm.task_off + warp]; k < tb[Cm.task_off + warp + 1]; k += 5) {
+                        const int e = tb[k], j0 = tb[k + 1], j1 = tb[k + 2], slot = tb[k + 3], grp = tb[k + 4];
+                        T acc(0.0);
+                        for (int j = j0; j < j1; j++) acc = acc + cc[j] * G(xs + ci[j]);
+                        // slot < 0: the whole dest; slot = -2 - k: first part of split dest (takes the old value along), k: a later part
+                        if (slot < 0) acc = acc + G(ms + e);
+                        if (slot == -1) GS(ms + e, acc);
+                        else GS(Cm.g_cpart + (slot < 0 ? -2 - slot : slot), acc);
+                        if (tot_now) GS(Cm.g_pt + grp * 16 + warp, G(Cm.g_pt + grp * 16 + warp) + acc);
                     }
                 }
                 G3T_BAR();
-                // ================= g3l_distribution compare (R/likelihood_distribution.R:375-394): one warp per component
-                ucnt = 0;
+                // ================= g3l_distribution compare (R/likelihood_distribution.R:375-394): the dests of a component are
+                // dealt warp by warp (continuing from component to component); every warp leaves its share of the component's value
+                int rot = 0;
                 for (int c = 0; c < A.NCOMP; c++) {
                     if (!((cact >> c) & 1)) continue;
                     const CompRec& Cm = A.comp[c];
-                    if (!I[Cm.cmp_ioff + t]) continue;
-                    if (!mine()) continue;
                     const int ti = I[Cm.tidx_ioff + t];
                     const int func = Cm.func, nd = Cm.n_dest, nt = Cm.n_times;
                     const bool si = func == G3F_SI_LOG || func == G3F_SI_LINEAR;
                     const int ms = Cm.g_ms + (si ? ti * nd : 0);
-                    const int nb = Cm.n_bins, nsl = Cm.n_slices, nag = Cm.n_areag;
-                    T cnll(0.0);
-                    if (func == G3F_SUMOFSQUARES) {     // R/likelihood_distribution.R:3-39
-                        const int per = nsl * nb;
+                    const int e0 = warp >= rot ? warp - rot : warp - rot + W;       // dest e belongs to warp (e + rot) % W
+                    const int rot0 = rot;
+                    rot = (rot + nd) % W;
+                    // split dests: the owner adds the parts up, in order
+                    for (int k = 0; k < tb[Cm.split_off]; k++) {
+                        const int e = tb[Cm.split_off + 1 + 3 * k];
+                        if ((e + rot0) % W != warp) continue;
+                        const int s0 = tb[Cm.split_off + 2 + 3 * k], sn = tb[Cm.split_off + 3 + 3 * k];
+                        T v(0.0);
+                        for (int i = 0; i < sn; i++) v = v + G(Cm.g_cpart + s0 + i);
+                        GS(ms + e, v);
+                    }
+                    if (!I[Cm.cmp_ioff + t]) continue;
+                    const int nb = Cm.n_bins;
+                    T part(0.0);
+                    if (func == G3F_SUMOFSQUARES || func == G3F_MULTINOMIAL) {
+                        // R/likelihood_distribution.R:3-39 (sum of squared differences of proportions) and :41-60
                         const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
-                        for (int ag = 0; ag < nag; ag++) {
-                            T tot(0.0);
-                            for (int e = 0; e < per; e++) tot = tot + G(ms + ag * per + e);
-                            const T rt = 1.0 / avoid_zero(tot);
-                            for (int sl = 0; sl < nsl; sl++) {
-                                T v(0.0);
-                                for (int e = 0; e < nb; e++) {
-                                    const int i = ag * per + sl * nb + e;
-                                    const T dlt = G(ms + i) * rt - op[i];
-                                    v = v + dlt * dlt;
-                                }
-                                cnll = cnll + v;
-                            }
-                        }
-                    } else if (func == G3F_MULTINOMIAL) {   // R/likelihood_distribution.R:41-60
                         const double eps = R[Cm.param_roff];
-                        const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
-                        T likely(0.0);
-                        for (int sl = 0; sl < nag * nsl; sl++) {
-                            T tot(0.0);
-                            for (int e = 0; e < nb; e++) tot = tot + G(ms + sl * nb + e);
-                            const T at = avoid_zero(tot);
-                            for (int e = 0; e < nb; e++)
-                                likely = likely + op[sl * nb + e] * xlog(dif_pmax_c(G(ms + sl * nb + e) / at, 1.0 / (nb * eps), 1e4));
+                        const int glen = Cm.group_len;
+                        int gcur = -1;
+                        T rt(0.0);
+                        for (int e = e0; e < nd; e += W) {
+                            const int g = e / glen;
+                            if (g != gcur) {        // total of the group: the warps' shares, in warp order
+                                T tot(0.0);
+                                for (int w = 0; w < W; w++) tot = tot + G(Cm.g_pt + g * 16 + w);
+                                rt = 1.0 / avoid_zero(tot);
+                                gcur = g;
+                            }
+                            if (func == G3F_SUMOFSQUARES) {
+                                const T dlt = G(ms + e) * rt - op[e];
+                                part = part + dlt * dlt;
+                            } else
+                                part = part + op[e] * xlog(dif_pmax_c(G(ms + e) * rt, 1.0 / (nb * eps), 1e4));
+                            GS(ms + e, T(0.0));      // zero counters for the next period
                         }
-                        cnll = 2.0 * (-likely + A.obsconst[Cm.obsconst_off + ti]);
                     } else if (func == G3F_SUMSQLOGRATIOS) {    // R/likelihood_distribution.R:127-136 (obsprop holds log(obs + eps))
                         const double eps = R[Cm.param_roff];
                         const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
-                        for (int e = 0; e < nd; e++) {
+                        for (int e = e0; e < nd; e += W) {
                             const T dlt = op[e] - xlog(G(ms + e) + eps);
-                            cnll = cnll + dlt * dlt;
+                            part = part + dlt * dlt;
+                            GS(ms + e, T(0.0));
                         }
                     } else if (ti == nt - 1) {              // surveyindices: R/likelihood_distribution.R:82-125
                         const double fa = R[Cm.param_roff], fb = R[Cm.param_roff + 1];
                         const int series = Cm.g_ms;
                         const double* op = A.obsprop + Cm.obs_off;
-                        for (int e = 0; e < nd; e++) {
+                        for (int e = e0; e < nd; e += W) {
                             T sN(0.0); double sI = 0.0;
                             for (int i = 0; i < nt; i++) {
                                 const T mv = G(series + i * nd + e);
@@ -913,17 +1050,16 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                                 const T mv = G(series + i * nd + e);
                                 const T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
                                 const T r = alpha + beta * N - op[(size_t)i * nd + e];
-                                cnll = cnll + r * r;
+                                part = part + r * r;
                             }
                         }
                     }
-                    GS(A.g_cn + c, cnll);
-                    if (!si) for (int e = 0; e < nd; e++) GS(ms + e, T(0.0));     // zero counters for the next period
+                    GS(Cm.g_pv + warp, part);
                 }
             }
             G3T_BAR();          // the step's state, collect sums and component values are complete
 
-            // ================= the keeper warp: the objective, in the reference's summation order (the column warps go on)
+            // ================= the keeper warp: the objective, in the reference's summation order (the unit warps go on)
             if (keeper) {
                 for (int c = 0; c < A.NCOMP; c++) {
                     if (!((cact >> c) & 1)) continue;
@@ -932,7 +1068,9 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                     const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
                     if (si && I[Cm.tidx_ioff + t] != Cm.n_times - 1) continue;      // survey indices score once, at their last time
                     if (lane_on && ((cw_lane >> c) & 1)) {
-                        const T cnll = G(A.g_cn + c);
+                        T cnll(0.0);        // the warps' shares of the component's value, in warp order
+                        for (int w = 0; w < W; w++) cnll = cnll + G(Cm.g_pv + w);
+                        if (Cm.func == G3F_MULTINOMIAL) cnll = 2.0 * (-cnll + A.obsconst[Cm.obsconst_off + I[Cm.tidx_ioff + t]]);
                         nll = nll + mkpar_g<T>(prow, seed, Cm.weight_par) * cnll;
                         GS(A.g_ctot + c, G(A.g_ctot + c) + cnll);
                     }
@@ -945,7 +1083,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                             const StockRec& St = A.st[s];
                             if (!St.us_flag || St.pp_n == 0) continue;
                             T o1(0.0), o2(0.0);
-                            for (int col = 0; col < St.ncol; col++) { o1 = o1 + G(A.col[St.gcol0 + col].g_usp); o2 = o2 + G(A.col[St.gcol0 + col].g_usp + 1); }
+                            for (int u = St.u0; u < St.u0 + St.nu; u++) { o1 = o1 + G(A.unit[u].g_usp); o2 = o2 + G(A.unit[u].g_usp + 1); }
                             us_tot = us_tot + (o1 - o2);
                         }
                     const T u = (us_power == 2.0) ? us_tot * us_tot : xpow(us_tot, T(us_power));

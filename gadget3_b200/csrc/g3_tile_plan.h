@@ -16,15 +16,27 @@ struct TilePlan {
     bool ok = false;
     std::string why;            // why the model does not fit the tile kernel
     TArgs a{};                  // scalars and entry offsets; pointers are filled by whoever places the tables
-    std::vector<StockRec> st; std::vector<ColRec> col; std::vector<PairRec> pp; std::vector<PredRec> pred;
+    std::vector<StockRec> st; std::vector<ColRec> col; std::vector<UnitRec> unit; std::vector<PairRec> pp; std::vector<PredRec> pred;
     std::vector<TsRec> ts; std::vector<CompRec> comp; std::vector<XRec> xb; std::vector<int4> agedst;
     std::vector<int32_t> tb;
     std::vector<double> obsprop, obsconst;
     std::vector<unsigned char> pred_active;
     int n_s = 0;                // state entries per lane (shared memory, or after the G entries in the slab)
     int maxn = 0;               // widest growth band (maxlengthgroupgrowth)
-    std::vector<double> col_cost;
+    std::vector<int> seglen;    // rows per unit of each stock's columns (L: one unit per column)
+    std::vector<double> row_cost;       // relative cost of one row of each column per step
+    std::vector<double> unit_cost;
+    int g_fixed = 0, tb_fixed = 0;      // G entries / tb words that do not depend on the partition into units
+    int max_cx = 0, maxnarea = 1;
+    std::vector<std::vector<int>> pp_of_stock;
+    // collect terms of all components (cell index, coefficient) and the tasks they are cut into: (dest, first term, end term, slot, group)
+    std::vector<int32_t> cterm_idx; std::vector<double> cterm_coef;
+    std::vector<std::vector<int>> ctask;
 };
+
+constexpr int TASK_TERMS = 24;          // longest run of collect terms one warp sums in one go
+
+constexpr double UNIT_OVERHEAD = 1.5;   // per-unit cost (pointer setup, ghost rows) in rows of a plain column
 
 inline double plan_avoid_zero(double a) {       // R/aab_env.R:24-31, for parameter-independent terms
     const double p = a * 1000.0;
@@ -49,24 +61,168 @@ inline double assign_columns(const std::vector<double>& cost, int W, std::vector
     return mx > 0 ? sum / (W * mx) : 1.0;
 }
 
+// Split the columns of every stock into units of P.seglen[s] rows and lay out what depends on that partition: ghost rows,
+// understocking sums per unit, partial suitable biomass per (pair, unit) with the summation lists of the totals.
+inline void plan_build_units(TilePlan& P) {
+    TArgs& A = P.a;
+    P.tb.resize(P.tb_fixed);
+    int ng = P.g_fixed;
+    auto takeg = [&](int n) { int o = ng; ng += n; return o; };
+    const int NWc = A.NWc;
+    P.unit.clear(); P.unit_cost.clear();
+    A.any_ghost = 0;
+    int max_len = 1;
+    for (int s = 0; s < A.NS; s++) {
+        StockRec& r = P.st[s];
+        r.u0 = (int)P.unit.size();
+        for (int col = 0; col < r.ncol; col++) {
+            const int gc = r.gcol0 + col;
+            for (int lo = 0; lo < r.L; lo += P.seglen[s]) {
+                UnitRec u{};
+                u.gc = gc; u.lo = lo; u.len = std::min(P.seglen[s], r.L - lo); u.lu = (int)P.unit.size() - r.u0;
+                u.g_ghost = -1; u.up_ghost = -1;
+                if (lo > 0) {
+                    u.g_ghost = takeg(2 * (NWc - 1));
+                    P.unit.back().up_ghost = u.g_ghost;
+                    A.any_ghost = 1;
+                }
+                u.g_usp = takeg(2);
+                max_len = std::max(max_len, u.len);
+                P.unit.push_back(u);
+                P.unit_cost.push_back(P.row_cost[gc] * ((u.len + NBX - 1) / NBX * NBX) + UNIT_OVERHEAD);
+            }
+        }
+        r.nu = (int)P.unit.size() - r.u0;
+    }
+    A.NU = (int)P.unit.size();
+    // partial suitable biomass per (pair, prey unit); summation lists of the totals in the reference's order: prey stock, pair, cell
+    for (int q = 0; q < A.NPP; q++) P.pp[q].g_part = takeg(P.st[P.pp[q].prey].nu * P.pp[q].PL);
+    for (int k = 0; k < A.NTS; k++) {
+        TsRec& T = P.ts[k];
+        T.list_off = (int)P.tb.size(); T.list_n = 0;
+        for (int s = 0; s < A.NS; s++)
+            for (int q : P.pp_of_stock[s]) {
+                const PairRec& r = P.pp[q];
+                if (r.pred_kind != G3PRED_TOTALFLEET && r.pred_kind != G3PRED_NUMBERFLEET) continue;
+                for (int u = 0; u < P.st[s].nu; u++) {
+                    const int col = P.col[P.unit[P.st[s].u0 + u].gc].col;
+                    if (P.tb[r.tsid_off + col / P.st[s].nage] == k) { P.tb.push_back(r.g_part + u); T.list_n++; }
+                }
+            }
+    }
+    for (int p = 0; p < A.NPRED; p++) {
+        PredRec& Pr = P.pred[p];
+        if (Pr.kind != G3PRED_STOCK) continue;
+        const StockRec& Pp = P.st[Pr.stock];
+        std::vector<std::vector<int>> lists(Pp.narea);
+        for (int s = 0; s < A.NS; s++)
+            for (int q : P.pp_of_stock[s]) {
+                const PairRec& r = P.pp[q];
+                if (r.pred != p) continue;
+                for (int u = 0; u < P.st[s].nu; u++) {
+                    const int col = P.col[P.unit[P.st[s].u0 + u].gc].col;
+                    const int pr = P.tb[r.tsid_off + col / P.st[s].nage];
+                    if (pr >= 0) lists[pr].push_back(r.g_part + u * r.PL);
+                }
+            }
+        Pr.list_off = (int)P.tb.size();
+        P.tb.resize(P.tb.size() + 2 * Pp.narea);
+        for (int pr = 0; pr < Pp.narea; pr++) {
+            P.tb[Pr.list_off + 2 * pr] = (int)P.tb.size();
+            P.tb[Pr.list_off + 2 * pr + 1] = (int)lists[pr].size();
+            for (int e : lists[pr]) P.tb.push_back(e);
+        }
+    }
+    // per-warp scratch: migration sources, or the consumption factors of one unit ([1 + catch collect vectors][rows])
+    A.cf_rows = (max_len + NBX - 1) / NBX * NBX;
+    A.wscr_n = std::max({2 * P.maxnarea, (1 + P.max_cx) * A.cf_rows, 1});
+    A.g_wscr = ng;
+    A.wunit_off = (int)P.tb.size();
+}
+
 // (re)build the warp lists of a plan for W warps; they live at the end of tb
 inline void plan_set_warps(TilePlan& P, int W) {
-    std::vector<std::vector<int>> cols;
-    assign_columns(P.col_cost, W, &cols);
-    P.tb.resize(P.a.wcol_off);
-    const int base = P.a.wcol_off;
+    W = std::max(1, std::min({W, P.a.NU, 15}));
+    std::vector<std::vector<int>> units;
+    assign_columns(P.unit_cost, W, &units);
+    P.tb.resize(P.a.wunit_off);
+    const int base = P.a.wunit_off;
     P.tb.resize(base + W + 1);
     for (int w = 0; w < W; w++) {
         P.tb[base + w] = (int)P.tb.size();
-        for (int c : cols[w]) P.tb.push_back(c);
+        for (int u : units[w]) P.tb.push_back(u);
     }
     P.tb[base + W] = (int)P.tb.size();
     P.a.W = W;
-    // per-warp scratch follows the other G entries (W column warps + the keeper warp)
+    // collect tasks of every component, dealt by size to all W + 1 warps (the keeper warp takes part)
+    for (int c = 0; c < P.a.NCOMP; c++) {
+        const std::vector<int>& T = P.ctask[c];
+        std::vector<double> cost;
+        for (size_t k = 0; k < T.size(); k += 5) cost.push_back(3.0 + (T[k + 2] - T[k + 1]));
+        std::vector<std::vector<int>> mine;
+        assign_columns(cost, W + 1, &mine);
+        const int off = (int)P.tb.size();
+        P.comp[c].task_off = off;
+        P.tb.resize(off + W + 2);
+        for (int w = 0; w <= W; w++) {
+            P.tb[off + w] = (int)P.tb.size();
+            for (int k : mine[w]) for (int i = 0; i < 5; i++) P.tb.push_back(T[5 * k + i]);
+        }
+        P.tb[off + W + 1] = (int)P.tb.size();
+    }
+    // per-warp scratch follows the other G entries (W unit warps + the keeper warp)
     P.a.n_g = P.a.g_wscr + (W + 1) * P.a.wscr_n;
 }
 
-inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0) {
+// rows per unit for every stock: the partition with the smallest largest warp load at `W` warps. Candidates per stock:
+// whole columns, or segments of a multiple of NBX rows that hold the NW - 1 rows the segment above reads below itself.
+inline void plan_choose_partition(TilePlan& P, int W) {
+    const TArgs& A = P.a;
+    std::vector<std::vector<int>> cand(A.NS);
+    for (int s = 0; s < A.NS; s++) {
+        const StockRec& r = P.st[s];
+        cand[s].push_back(r.L);
+        if (r.grow_n < 0) continue;
+        for (int m = NBX; m < r.L; m += NBX)
+            if (m >= A.NWc - 1 && (r.L + m - 1) / m <= 6) cand[s].push_back(m);
+    }
+    auto maxload = [&](const std::vector<int>& seg) {
+        std::vector<double> cost;
+        for (int s = 0; s < A.NS; s++) {
+            const StockRec& r = P.st[s];
+            for (int col = 0; col < r.ncol; col++)
+                for (int lo = 0; lo < r.L; lo += seg[s]) {
+                    const int len = std::min(seg[s], r.L - lo);
+                    cost.push_back(P.row_cost[r.gcol0 + col] * ((len + NBX - 1) / NBX * NBX) + UNIT_OVERHEAD);
+                }
+        }
+        const int w = std::max(1, std::min<int>(W, (int)cost.size()));
+        double sum = 0; for (double c : cost) sum += c;
+        const double eff = assign_columns(cost, w, nullptr);
+        return sum / (w * eff) * (15.0 / w > 1.0 ? 1.0 + 0.25 * (15.0 / w - 1.0) : 1.0);      // fewer warps hide less latency
+    };
+    std::vector<int> seg(A.NS);
+    for (int s = 0; s < A.NS; s++) seg[s] = P.st[s].L;
+    double best = maxload(seg);
+    for (int pass = 0; pass < 3; pass++) {           // coordinate descent over the stocks
+        bool changed = false;
+        for (int s = 0; s < A.NS; s++) {
+            int keep = seg[s];
+            for (int c : cand[s]) {
+                std::vector<int> t = seg; t[s] = c;
+                const double v = maxload(t);
+                if (v < best - 1e-9) { best = v; keep = c; changed = true; }
+            }
+            seg[s] = keep;
+        }
+        if (!changed) break;
+    }
+    P.seglen = seg;
+}
+
+// want_W: unit warps (0 = as many as useful, at most 15). want_seg: rows per unit, 0 = the planner's choice (made for the
+// automatic warp count whatever want_W is, so that changing the warp count alone never changes a sum), -1 = whole columns.
+inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0, int want_seg = 0) {
     TilePlan P;
     TArgs& A = P.a;
     auto fail = [&](const std::string& w) { P.ok = false; P.why = w; return P; };
@@ -88,10 +244,21 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         A.step_idt[sy] = k;
     }
 
+    for (int s = 0; s < A.NS; s++) P.maxn = std::max(P.maxn, stock(s)[G3S_GROW_N]);
+    if (P.maxn > 15) return fail("maxlengthgroupgrowth above 15");
+    const int NWc = A.NWc = P.maxn > 4 ? 16 : 5;        // band width of the kernel instantiation that runs this model
     int ng = 0, ns = 0;
     auto takeg = [&](int n) { int o = ng; ng += n; return o; };
     auto takes = [&](int n) { int o = ns; ns += n; return o; };
+    // entries zeroed once per tile: (space 0 = G / 1 = S, first entry, count)
+    std::vector<int> zr;
+    auto zero_g = [&](int e0, int n) { if (n > 0) { zr.push_back(0); zr.push_back(e0); zr.push_back(n); } };
+    auto zero_s = [&](int e0, int n) { if (n > 0) { zr.push_back(1); zr.push_back(e0); zr.push_back(n); } };
+    // a table read by source row: NW - 1 zero rows below row 0 (the growth gather reads them against zero band entries)
+    // and NBX - 1 above the last row (the dropped rows of a partial top block)
+    auto take_padded = [&](int n) { const int o = takeg(NWc - 1 + n + NBX - 1); zero_g(o, NWc - 1); zero_g(o + NWc - 1 + n, NBX - 1); return o + NWc - 1; };
     A.g_slot = takeg(A.NSLOT);
+    zero_s(takes(NWc - 1), NWc - 1);
     A.s_num = takes(A.NC); A.s_wgt = takes(A.NC);
 
     // ---- stocks and columns
@@ -110,18 +277,19 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         r.n_renew = St[G3S_N_RENEW]; r.renew_ioff = St[G3S_RENEW_OFF];
         if (r.n_renew > 30) return fail("more than 30 renewal actions on one stock");
         maxnarea = std::max(maxnarea, r.narea);
-        P.maxn = std::max(P.maxn, r.grow_n);
         r.g_mort = takeg(r.mort_ioff >= 0 ? r.ncol * A.ndt : 0);
         r.g_rd = takeg(r.n_renew * r.L); r.g_rw = takeg(r.n_renew * r.L);
-        r.g_pw = takeg(r.grow_n >= 0 ? r.L : 0);
+        r.g_wq = r.grow_n >= 0 ? take_padded(r.L) : 0;
         const bool trans = r.grow_n >= 0 && r.has_out;
         const bool cont = trans && r.mat_kind == G3MAT_CONTINUOUS;
         r.band_percol = cont && I[r.mat_ioff + 2] >= 0;         // age term: M0 differs per column (R/action_mature.R:18,44-74)
-        r.bsz = r.grow_n >= 0 ? (r.L + 1) * (r.grow_n + 1) : 0;
+        r.bsz = r.grow_n >= 0 ? (r.L + NBX - 1) * NWc : 0;
         const int nset = r.band_percol ? r.ncol : 1;
         r.g_band = takeg(nset * A.ndt * r.bsz);
+        zero_g(r.g_band, nset * A.ndt * r.bsz);
         r.g_bandr = cont ? takeg(nset * A.ndt * r.bsz) : r.g_band;
-        r.g_cmat = (trans && r.mat_kind == G3MAT_CONSTANT) ? takeg(r.ncol * r.L) : -1;
+        if (cont) zero_g(r.g_bandr, nset * A.ndt * r.bsz);
+        r.g_cmat = (trans && r.mat_kind == G3MAT_CONSTANT) ? take_padded(r.ncol * r.L) : -1;
         r.mig_ioff = St[G3S_MIGRATE_OFF]; r.mig_steps = 0;
         r.g_mig = r.mig_ioff >= 0 ? takeg(A.NSTEPS * r.narea * r.narea) : 0;
         if (r.mig_ioff >= 0)
@@ -135,7 +303,6 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         }
     }
     for (int i = 0; i < I[G3H_US_N]; i++) P.st[I[I[G3H_US_OFF] + i]].us_flag = 1;
-    if (P.maxn > 15) return fail("maxlengthgroupgrowth above 15");
     A.NCOLS = ncols;
 
     // ---- maturation hand-over (R/action_mature.R:78-134) per cell, then per column
@@ -166,7 +333,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
             ColRec& c = P.col[r.gcol0 + col];
             c.s = s; c.col = col; c.aidx = col % r.nage; c.ridx = col / r.nage; c.cell0 = r.c0 + col * r.L;
             c.s_tn = c.s_tw = -1; c.inc_tn = c.inc_tw = c.inc_slot = -1; c.inc_mask = 0;
-            c.g_remf = takeg(1); c.g_usp = takeg(2);
+            c.g_remf = takeg(1);
             // remainder ratios must be the same down a column
             for (int l = 1; l < r.L; l++)
                 if (rem[c.cell0 + l] != rem[c.cell0]) return fail("maturation outputs differ between the lengths of one column");
@@ -211,6 +378,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         if (r.age_enable && r.age_n_out > 0) { r.s_mv = s_x0 + nmv; nmv += 2 * r.narea * r.L; }
     }
     takes(std::max(ntr, nmv));
+    zero_s(takes(NBX - 1), NBX - 1);        // (rows the dropped part of the last column's top block reads)
     {
         std::vector<int> age_src(A.NC, -1);
         std::vector<int32_t> agedst_l;
@@ -294,7 +462,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
             if (Pr.kind != G3PRED_STOCK) return fail("suitability kind " + std::to_string(sk) + " reads predator_length: it needs a stock predator");
         } else if (sk < 0 || sk > G3SUIT_RICHARDS) return fail("suitability kind " + std::to_string(sk) + " is not supported");
         r.g_suit = takeg(r.PL * Ps.L);
-        r.g_part = takeg(Ps.ncol * r.PL);
+        r.g_part = 0;
         r.cxmask = 0;
         r.tsid_off = (int)P.tb.size();
         for (int ar = 0; ar < Ps.narea; ar++) {
@@ -307,11 +475,9 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         }
         pp_of_stock[r.prey].push_back(q);
     }
-    int max_nq = 1;
     for (int s = 0; s < A.NS; s++) {
         StockRec& r = P.st[s];
         r.pp_off = (int)P.tb.size(); r.pp_n = (int)pp_of_stock[s].size();
-        max_nq = std::max(max_nq, r.pp_n);
         for (int q : pp_of_stock[s]) P.tb.push_back(q);
         // catch collect vectors fed by this stock's pairs
         r.cx_off = (int)P.tb.size(); r.cx_n = 0;
@@ -325,41 +491,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
             P.tb.push_back(x); r.cx_n++;
         }
     }
-    // summation lists of the totals, in the reference's order: prey stock, pair, column
-    for (int k = 0; k < nts; k++) {
-        TsRec& T = P.ts[k];
-        T.list_off = (int)P.tb.size(); T.list_n = 0;
-        for (int s = 0; s < A.NS; s++)
-            for (int q : pp_of_stock[s]) {
-                const PairRec& r = P.pp[q];
-                if (r.pred_kind != G3PRED_TOTALFLEET && r.pred_kind != G3PRED_NUMBERFLEET) continue;
-                for (int col = 0; col < P.st[s].ncol; col++)
-                    if (P.tb[r.tsid_off + col / P.st[s].nage] == k) { P.tb.push_back(r.g_part + col); T.list_n++; }
-            }
-    }
     if (P.ts.empty()) P.ts.push_back(TsRec{0, 0, 0, 0, 0});
-    for (int p = 0; p < A.NPRED; p++) {
-        PredRec& Pr = P.pred[p];
-        if (Pr.kind != G3PRED_STOCK) continue;
-        const StockRec& Pp = P.st[Pr.stock];
-        std::vector<std::vector<int>> lists(Pp.narea);
-        for (int s = 0; s < A.NS; s++)
-            for (int q : pp_of_stock[s]) {
-                const PairRec& r = P.pp[q];
-                if (r.pred != p) continue;
-                for (int col = 0; col < P.st[s].ncol; col++) {
-                    const int pr = P.tb[r.tsid_off + col / P.st[s].nage];
-                    if (pr >= 0) lists[pr].push_back(r.g_part + col * r.PL);
-                }
-            }
-        Pr.list_off = (int)P.tb.size();
-        P.tb.resize(P.tb.size() + 2 * Pp.narea);
-        for (int pr = 0; pr < Pp.narea; pr++) {
-            P.tb[Pr.list_off + 2 * pr] = (int)P.tb.size();
-            P.tb[Pr.list_off + 2 * pr + 1] = (int)lists[pr].size();
-            for (int e : lists[pr]) P.tb.push_back(e);
-        }
-    }
     // steps with predation: some landing is non-zero, or a stock predator exists (it eats every step)
     P.pred_active.assign(A.NT, 0);
     for (int p = 0; p < A.NPRED; p++) {
@@ -383,6 +515,42 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         if (r.func < 0 || r.func > G3F_SUMSQLOGRATIOS) return fail("likelihood function " + std::to_string(r.func) + " is not supported");
         const bool si = r.func == G3F_SI_LOG || r.func == G3F_SI_LINEAR;
         r.g_ms = takeg(r.n_dest * (si ? r.n_times : 1));
+        // groups of dests whose total the comparison divides by
+        r.n_groups = 0; r.group_len = 1;
+        if (r.func == G3F_SUMOFSQUARES) { r.n_groups = r.n_areag; r.group_len = r.n_slices * r.n_bins; }
+        if (r.func == G3F_MULTINOMIAL) { r.n_groups = r.n_areag * r.n_slices; r.group_len = r.n_bins; }
+        r.g_pt = takeg(r.n_groups * 16); r.g_pv = takeg(16);
+        // collect terms per dest, cut into tasks
+        {
+            std::vector<std::vector<std::pair<int, double>>> rows(r.n_dest);
+            if (r.mode == 0) {
+                const int32_t* ptr = I + r.csr_ptr_ioff; const int32_t* idx = I + r.csr_idx_ioff; const double* cf = R + r.csr_coef_roff;
+                for (int e = 0; e < r.n_dest; e++) for (int j = ptr[e]; j < ptr[e + 1]; j++) rows[e].push_back({idx[j], cf[j]});
+            } else {
+                const int32_t* cd = I + r.cell_dest_ioff; const double* cf = R + r.cell_coef_roff;
+                for (int i = 0; i < A.NC; i++) if (cd[i] >= 0 && cd[i] < r.n_dest) rows[cd[i]].push_back({i, cf[i]});
+            }
+            std::vector<int> tasks, split;
+            int nslot = 0, nsplit = 0;
+            for (int e = 0; e < r.n_dest; e++) {
+                const int j0 = (int)P.cterm_idx.size();
+                for (auto& tc : rows[e]) { P.cterm_idx.push_back(tc.first); P.cterm_coef.push_back(tc.second); }
+                const int n = (int)rows[e].size(), grp = e / r.group_len;
+                if (n <= TASK_TERMS) { tasks.insert(tasks.end(), {e, j0, j0 + n, -1, grp}); continue; }
+                const int parts = (n + TASK_TERMS - 1) / TASK_TERMS;
+                split.insert(split.end(), {e, nslot, parts}); nsplit++;
+                for (int k = 0; k < parts; k++) {
+                    const int a = j0 + (int)((long long)n * k / parts), b = j0 + (int)((long long)n * (k + 1) / parts);
+                    tasks.insert(tasks.end(), {e, a, b, k == 0 ? -2 - nslot : nslot, grp});
+                    nslot++;
+                }
+            }
+            r.g_cpart = takeg(nslot);
+            r.split_off = (int)P.tb.size();
+            P.tb.push_back(nsplit);
+            for (int v : split) P.tb.push_back(v);
+            P.ctask.push_back(tasks);
+        }
         r.obs_off = (int)P.obsprop.size(); r.obsconst_off = (int)P.obsconst.size();
         const double* obs = R + Cm[G3C_OBS_ROFF];
         const int nd = r.n_dest, nb = r.n_bins, nsl = r.n_slices, nag = r.n_areag;
@@ -415,35 +583,39 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     A.g_cn = takeg(std::max(A.NCOMP, 1));
     A.g_ctot = takeg(A.NNLL);
     A.g_bterm = takeg(A.NBOUND);
-    A.wscr_n = std::max({2 * maxnarea, max_nq, 1});
-    A.g_wscr = ng;
     P.n_s = ns;
+    A.zr_off = (int)P.tb.size(); A.zr_n = (int)zr.size() / 3;
+    for (int v : zr) P.tb.push_back(v);
+    P.g_fixed = ng; P.tb_fixed = (int)P.tb.size();
+    P.maxnarea = maxnarea; P.pp_of_stock = pp_of_stock;
+    for (int s = 0; s < A.NS; s++) P.max_cx = std::max(P.max_cx, P.st[s].cx_n);
 
-    // ---- column costs (relative): growth with its avoid_zero per cell dominates; the maturing split doubles it
-    P.col_cost.resize(ncols);
+    // ---- cost of one row of each column per step, in avoid_zero chains (they dominate): growth 1 (+ the gather), the
+    // maturing split another one when the maturing fish have a destination, predation 3 on the steps that have any
+    int npred = 0;
+    for (int t = 0; t < A.NT; t++) npred += P.pred_active[t] != 0;
+    const double pred_frac = A.NT > 0 ? (double)npred / A.NT : 0.0;
+    P.row_cost.resize(ncols);
     for (int gc = 0; gc < ncols; gc++) {
         const StockRec& r = P.st[P.col[gc].s];
-        const bool cont = r.grow_n >= 0 && r.has_out && r.mat_kind != G3MAT_NONE;
-        double c = r.grow_n >= 0 ? (1.0 + 0.08 * (r.grow_n + 1)) * (cont && P.col[gc].s_tn >= 0 ? 2.0 : (cont ? 1.5 : 1.0)) : 0.15;
-        if (P.col[gc].inc_tn >= 0) c += 0.7;
-        if (r.pp_n > 0) c += 0.4;
-        P.col_cost[gc] = c * r.L;
+        const bool split = r.grow_n >= 0 && r.has_out && r.mat_kind != G3MAT_NONE;
+        double c = 0.1;
+        if (r.grow_n >= 0) c = 1.0 + 0.05 * NWc * (split ? 2 : 1) + (split && P.col[gc].s_tn >= 0 ? 1.0 : 0.0);
+        if (r.pp_n > 0) c += 3.3 * pred_frac;
+        P.row_cost[gc] = c;
     }
-    A.wcol_off = (int)P.tb.size();
-    int W = want_W;
-    if (W <= 0) {
-        // as many column warps as columns up to 15 (+ the keeper warp = 512 threads); beyond that the best-balanced count in 8..15
-        if (ncols <= 15) W = ncols;
-        else {
-            double best = -1.0;
-            for (int w = 8; w <= 15; w++) {
-                const double e = assign_columns(P.col_cost, w, nullptr) * (0.75 + 0.25 * w / 15.0);
-                if (e > best + 1e-12) { best = e; W = w; }
-            }
+    // ---- partition into units and their assignment to warps
+    P.seglen.resize(A.NS);
+    for (int s = 0; s < A.NS; s++) P.seglen[s] = P.st[s].L;
+    if (want_seg == 0) plan_choose_partition(P, 15);
+    else if (want_seg > 0)
+        for (int s = 0; s < A.NS; s++) {
+            const int m = (want_seg + NBX - 1) / NBX * NBX;
+            if (P.st[s].grow_n >= 0 && m >= NWc - 1 && m < P.st[s].L) P.seglen[s] = m;
         }
-    }
-    W = std::max(1, std::min({W, ncols, 15}));
-    plan_set_warps(P, W);
+    for (int s = 0; s < A.NS; s++) P.seglen[s] = std::min(P.seglen[s], 64);     // (the kernel keeps one bit per row of a unit)
+    plan_build_units(P);
+    plan_set_warps(P, want_W > 0 ? want_W : 15);
     P.ok = true;
     return P;
 }

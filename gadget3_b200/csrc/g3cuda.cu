@@ -106,7 +106,10 @@ template <class T> int ensure(T** p, size_t* cap, size_t n) {
 int tile_upload_tb(g3cuda_model* m) {
     if (m->d_tb) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(m->d_tb); m->d_tb = nullptr; }
     m->d_tb = dev_copy(m->tplan.tb);
-    if (!m->d_tb) return fail(G3CUDA_ENOMEM, "device allocation failed");
+    auto* d_comp = dev_copy(m->tplan.comp);     // (the components' task lists live in tb)
+    if (!m->d_tb || !d_comp) return fail(G3CUDA_ENOMEM, "device allocation failed");
+    m->owned.push_back((void*)d_comp);
+    m->tplan.a.comp = d_comp;
     m->targs = m->tplan.a;              // scalars (W, n_g, offsets) change with the warp count
     m->targs.tb = m->d_tb;
     return G3CUDA_OK;
@@ -639,13 +642,16 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     m->tplan = g3t::make_tile_plan(I, R);
     if (m->tplan.ok) {
         g3t::TilePlan& TP = m->tplan;
-        auto* d_st = up(TP.st); auto* d_col = up(TP.col); auto* d_pp = up(TP.pp); auto* d_pred = up(TP.pred); auto* d_ts = up(TP.ts);
+        auto* d_st = up(TP.st); auto* d_col = up(TP.col); auto* d_unit = up(TP.unit); auto* d_pp = up(TP.pp); auto* d_pred = up(TP.pred); auto* d_ts = up(TP.ts);
         auto* d_comp = up(TP.comp); auto* d_xb = up(TP.xb); auto* d_ad = up(TP.agedst);
         auto* d_op = up(TP.obsprop); auto* d_oc = up(TP.obsconst); auto* d_pa = up(TP.pred_active);
-        if (!d_st || !d_col || !d_pp || !d_pred || !d_ts || !d_comp || !d_xb || !d_ad || !d_op || !d_oc || !d_pa)
+        if (TP.cterm_idx.empty()) { TP.cterm_idx.push_back(0); TP.cterm_coef.push_back(0.0); }
+        auto* d_ci = up(TP.cterm_idx); auto* d_cc = up(TP.cterm_coef);
+        if (!d_st || !d_col || !d_unit || !d_pp || !d_pred || !d_ts || !d_comp || !d_xb || !d_ad || !d_op || !d_oc || !d_pa || !d_ci || !d_cc)
             return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
-        TP.a.I = d_I; TP.a.R = d_R; TP.a.st = d_st; TP.a.col = d_col; TP.a.pp = d_pp; TP.a.pred = d_pred; TP.a.ts = d_ts;
+        TP.a.I = d_I; TP.a.R = d_R; TP.a.st = d_st; TP.a.col = d_col; TP.a.unit = d_unit; TP.a.pp = d_pp; TP.a.pred = d_pred; TP.a.ts = d_ts;
         TP.a.comp = d_comp; TP.a.xb = d_xb; TP.a.agedst = d_ad; TP.a.obsprop = d_op; TP.a.obsconst = d_oc; TP.a.pred_active = d_pa;
+        TP.a.cterm_idx = d_ci; TP.a.cterm_coef = d_cc;
         if ((rc = tile_upload_tb(m))) return bail(rc);
         m->tile_ok = true;
     }
@@ -816,8 +822,28 @@ int g3cuda_set_tile_warps(g3cuda_model* m, int warps) {
     if (!m->tile_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", m->tplan.why.c_str());
     CUDA_TRY(cudaSetDevice(m->device));
     int w = warps;
-    if (w == 0) w = g3t::make_tile_plan(m->I.data(), m->R.data()).a.W;
-    g3t::plan_set_warps(m->tplan, std::max(1, std::min(w, m->tplan.a.NCOLS)));
+    if (w == 0) w = 15;
+    g3t::plan_set_warps(m->tplan, w);        // (the partition into units stays: only their assignment to warps changes)
+    return tile_upload_tb(m);
+}
+
+int g3cuda_set_tile_partition(g3cuda_model* m, int warps, int seg_rows) {
+    if (!m || warps < 0 || warps > 15 || seg_rows < -1) return fail(G3CUDA_EINVAL, "bad argument");
+    if (!m->tile_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", m->tplan.why.c_str());
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    g3t::TilePlan np = g3t::make_tile_plan(m->I.data(), m->R.data(), warps, seg_rows);
+    if (!np.ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", np.why.c_str());
+    // the record tables that depend on the partition: stocks (unit ranges), units, pairs, totals, predators
+    auto up = [&](auto& vec) { auto* d = dev_copy(vec); if (d) m->owned.push_back((void*)d); return d; };
+    const g3t::TArgs old = m->tplan.a;
+    auto* d_st = up(np.st); auto* d_unit = up(np.unit); auto* d_pp = up(np.pp); auto* d_pred = up(np.pred); auto* d_ts = up(np.ts);
+    if (!d_st || !d_unit || !d_pp || !d_pred || !d_ts) return fail(G3CUDA_ENOMEM, "device allocation failed");
+    np.a.I = old.I; np.a.R = old.R; np.a.col = old.col; np.a.comp = old.comp; np.a.xb = old.xb; np.a.agedst = old.agedst;
+    np.a.obsprop = old.obsprop; np.a.obsconst = old.obsconst; np.a.pred_active = old.pred_active;
+    np.a.cterm_idx = old.cterm_idx; np.a.cterm_coef = old.cterm_coef;
+    np.a.st = d_st; np.a.unit = d_unit; np.a.pp = d_pp; np.a.pred = d_pred; np.a.ts = d_ts;
+    m->tplan = std::move(np);
     return tile_upload_tb(m);
 }
 

@@ -93,10 +93,15 @@ int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B,
  * All are CUDA; there is no CPU path to select. */
 int g3cuda_set_kernel(g3cuda_model* m, int which);
 
-/* Tuning hook: warps per tile of the tile kernel (columns of the stocks are dealt to the warps); 0 restores the
- * planner's choice. Results do not depend on it to the bit except through the order of per-column partial sums,
- * which is fixed (column order), i.e. they do not depend on it at all. */
+/* Tuning hook: warps per tile of the tile kernel (the units -- row segments of the stocks' columns -- are dealt to the
+ * warps); 0 restores the planner's choice. The partition into units and the order of every sum stay the same, so results
+ * do not depend on the warp count at all. */
 int g3cuda_set_tile_warps(g3cuda_model* m, int warps);
+
+/* Tuning hook: re-plan the tile kernel with `warps` unit warps (0 = the planner's choice) and row segments of `seg_rows`
+ * rows per unit (0 = the planner's choice, -1 = whole columns). The partition only regroups partial sums (per-unit
+ * suitable biomass and understocking sums): results agree to rounding between partitions. */
+int g3cuda_set_tile_partition(g3cuda_model* m, int warps, int seg_rows);
 
 /* Introspection for tests and bench.py: out[0] = the model fits the tile kernel, out[1] = warps per tile,
  * out[2] = per-evaluation table entries in the CTA's global slab, out[3] = per-evaluation state entries,

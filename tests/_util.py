@@ -24,17 +24,20 @@ def consumed_biomass_per_step(model, params):
     return _US_CACHE[key]
 
 
-def us_tolerance(model, params, comp_us, ulps=16):
-    """Conditioning of g3l_understocking. Per step it adds weight * (sum(tp) - sum(tp'))^2 where both sums are the
+def us_tolerance(model, params, comp_us, ulps=16, rtol=1e-10):
+    """Allowed absolute difference of the (unweighted) g3l_understocking component: the contract's relative 1e-10
+    of the term itself, plus its conditioning. Per step it adds weight * (sum(tp) - sum(tp'))^2 where both sums are the
     biomass S_t consumed at that step (R/action_predate.R:393-398): the two sums are formed in floating point, so
     their DIFFERENCE carries an absolute error of a few ulps of S_t whatever its size -- the reference's own
     backends differ by as much (R sums in long double, TMB in Eigen's packet order), and so do two summation
     orders on the GPU. With delta_t = ulps * eps * S_t the squared term moves by 2 sqrt(u_t) delta_t + delta_t^2;
     over the steps, by Cauchy-Schwarz, sum_t 2 sqrt(u_t) delta_t <= 2 sqrt(sum_t u_t * sum_t delta_t^2).
-    `comp_us` is sum_t u_t (the unweighted understocking component). Typical sizes of the allowed slack on nll
-    (weight 1e8): C2 2e-12, C4 3e-11, C5 1e-12 relative -- observed errors are within a factor of ten of it."""
+    `comp_us` is sum_t u_t (the unweighted understocking component). Measured on a B200 (tools/gpu_parity_diag.py): the
+    conditioning part alone covers C2/C4/C5 with a margin of 30-100x (allowed slack on nll 1e-12 .. 3e-11 relative);
+    where overconsumption takes away half the landings (C1 has such vectors, u ~ 3e5) the term follows the state's own
+    relative error (observed 2e-13), which the relative part covers."""
     delta2 = float(((ulps * np.finfo(float).eps * consumed_biomass_per_step(model, params)) ** 2).sum())
-    return 2 * np.sqrt(np.abs(comp_us) * delta2) + delta2
+    return rtol * np.abs(comp_us) + 2 * np.sqrt(np.abs(comp_us) * delta2) + delta2
 
 
 def golden(name):

@@ -32,14 +32,14 @@ void run(const TArgs& A, int W, int ncta, size_t smem_doubles) {
 }  // namespace
 
 extern "C" int g3emu_eval(const int32_t* I, const double* R, const double* par, int64_t B, const int32_t* tidx, int32_t K,
-                          double* nll, double* comp, double* grad, int32_t W, int32_t lanes_per_tile, int32_t smem_state,
+                          double* nll, double* comp, double* grad, int32_t W, int32_t seg, int32_t lanes_per_tile, int32_t smem_state,
                           int32_t ncta, char* why, int32_t why_len) {
-    TilePlan P = make_tile_plan(I, R, W);
+    TilePlan P = make_tile_plan(I, R, W, seg);
     if (!P.ok) { if (why) { std::strncpy(why, P.why.c_str(), why_len - 1); why[why_len - 1] = 0; } return -4; }
     TArgs A = P.a;
-    A.I = I; A.R = R; A.tb = P.tb.data(); A.st = P.st.data(); A.col = P.col.data(); A.pp = P.pp.data(); A.pred = P.pred.data();
+    A.I = I; A.R = R; A.tb = P.tb.data(); A.st = P.st.data(); A.col = P.col.data(); A.unit = P.unit.data(); A.pp = P.pp.data(); A.pred = P.pred.data();
     A.ts = P.ts.data(); A.comp = P.comp.data(); A.xb = P.xb.data(); A.agedst = P.agedst.data();
-    A.obsprop = P.obsprop.data(); A.obsconst = P.obsconst.data(); A.pred_active = P.pred_active.data();
+    A.cterm_idx = P.cterm_idx.data(); A.cterm_coef = P.cterm_coef.data(); A.obsprop = P.obsprop.data(); A.obsconst = P.obsconst.data(); A.pred_active = P.pred_active.data();
     A.par = par; A.B = B; A.tangent_idx = tidx; A.K = K; A.nll = nll; A.comp_out = comp; A.grad = grad;
     A.lanes_per_tile = lanes_per_tile;
     const bool dual = grad && K > 0;
@@ -59,10 +59,11 @@ extern "C" int g3emu_eval(const int32_t* I, const double* R, const double* par, 
     return 0;
 }
 
-extern "C" int g3emu_plan_info(const int32_t* I, const double* R, int32_t W, int32_t* out /*[8]*/) {
-    TilePlan P = make_tile_plan(I, R, W);
+extern "C" int g3emu_plan_info(const int32_t* I, const double* R, int32_t W, int32_t seg, int32_t* out /*[8 + stocks]*/) {
+    TilePlan P = make_tile_plan(I, R, W, seg);
     if (!P.ok) return -4;
     out[0] = P.a.W; out[1] = P.a.n_g; out[2] = P.n_s; out[3] = P.a.NCOLS; out[4] = P.maxn; out[5] = (int)P.tb.size();
-    out[6] = P.a.wscr_n; out[7] = P.a.NTS;
+    out[6] = P.a.NU; out[7] = P.a.NTS;
+    for (int s = 0; s < P.a.NS; s++) out[8 + s] = P.seglen[s];
     return 0;
 }

@@ -63,13 +63,10 @@ def _check_nll_and_components(model, p, fn, orc):
     ncomp = len(model.comp_names)
     assert _rel(g_comp[:, :ncomp], o_comp[:, :ncomp]).max() < NLL_RTOL
     assert _rel(g_comp[:, -1], o_comp[:, -1]).max() < NLL_RTOL            # bounds penalty
-    # the objective: the contract's 1e-10 outright wherever g3l_understocking is not a visible share of it; where
-    # overconsumption is active (C1 has vectors with 20 % of nll from it), 1e-10 plus that term's conditioning
+    # the objective: the contract's 1e-10, plus the conditioning of g3l_understocking's difference of sums (a few ulps of
+    # the consumed biomass, _us_tolerance; measured sizes in tools/gpu_parity_diag.py: at most 3e-11 of nll)
     w = _us_weight(model)
-    calm = w * o_comp[:, -2] < 1e-5 * np.abs(o_nll)
-    assert calm.sum() >= len(o_nll) // 2
-    assert _rel(g_nll[calm], o_nll[calm]).max() < NLL_RTOL
-    assert (np.abs(g_nll - o_nll) <= NLL_RTOL * np.abs(o_nll) + w * _us_tolerance(model, p, o_comp[:, -2])).all()
+    assert (np.abs(g_nll - o_nll) <= NLL_RTOL * np.abs(o_nll) + w * _us_tolerance(model, p, o_comp[:, -2], rtol=0.0)).all()
     # everything except the understocking term agrees far better
     assert (np.abs((g_nll - w * g_comp[:, -2]) - (o_nll - w * o_comp[:, -2])) / np.abs(o_nll)).max() < 2e-11
     assert np.median(np.abs((g_nll - w * g_comp[:, -2]) - (o_nll - w * o_comp[:, -2])) / np.abs(o_nll)) < 1e-12
@@ -200,13 +197,20 @@ def test_full_size_batch_properties(setups):
         fn.handle.set_kernel(0)
     tol = NLL_RTOL * np.abs(small) + _us_weight(model) * _us_tolerance(model, p, thr[1][:, -2])
     assert (np.abs(thr[0] - small) <= tol).all()
-    # the warp count of a tile changes neither the per-column sums nor their order: identical to the bit
+    # the warp count of a tile only regroups the likelihood shares (one per warp); whole columns instead of row segments
+    # regroup the per-unit partial sums
     fn.handle.set_tile_warps(7)
     try:
         w7 = fn.handle.eval_batch(full[1000:1100])[0]
     finally:
         fn.handle.set_tile_warps(0)
-    assert (w7 == small).all()
+    assert _rel(w7, small).max() < 1e-13
+    fn.handle.set_tile_partition(0, -1)
+    try:
+        whole = fn.handle.eval_batch(full[1000:1100])[0]
+    finally:
+        fn.handle.set_tile_partition(0, 0)
+    assert (np.abs(whole - small) <= 1e-12 * np.abs(small) + _us_weight(model) * _us_tolerance(model, p, thr[1][:, -2], rtol=0.0)).all()
 
 
 def test_ragged_batch_larger_than_one_wave(setups):
@@ -225,7 +229,8 @@ def test_ragged_batch_larger_than_one_wave(setups):
         t_nll = fn.handle.eval_batch(full)[0]
     finally:
         fn.handle.set_kernel(0)
-    assert _rel(t_nll, nll).max() < NLL_RTOL
+    # two summation orders of the understocking sums: each within that term's conditioning of the other
+    assert (np.abs(t_nll - nll) <= NLL_RTOL * np.abs(nll) + 2 * US_WEIGHT * _us_tolerance(model, p, comp[:, -2], rtol=0.0)).all()
     o, oc, _ = orc.eval_batch(full[B - 64:], want_comp=True, nthreads=8)
     assert (np.abs(nll[B - 64:] - o) <= NLL_RTOL * np.abs(o) + US_WEIGHT * _us_tolerance(model, p, oc[:, -2])).all()
 

@@ -50,15 +50,38 @@ def test_gradients(oracle_lib, name):
     assert (np.abs(g_grad - o_grad) / scale).max() < 1e-8
 
 
-def test_warp_count_does_not_change_a_bit(oracle_lib):
-    """Columns are dealt to the warps differently, but every sum has a fixed (column) order."""
+def test_warp_count_only_regroups_sums(oracle_lib):
+    """Units and collect tasks are dealt to the warps differently; the partition into units does not depend on the warp
+    count, and every sum has a fixed order for a given count -- across counts only the likelihood shares (one per warp)
+    are grouped differently."""
     model, p, ints, reals, full, _ = _setup("C2", 3)
     ref = emu.eval_batch(ints, reals, full, want_comp=True)
+    again = emu.eval_batch(ints, reals, full, want_comp=True)
+    assert (again[0] == ref[0]).all() and (again[1] == ref[1]).all()
     for W in (1, 4, 9):
         got = emu.eval_batch(ints, reals, full, want_comp=True, W=W)
-        assert (got[0] == ref[0]).all() and (got[1] == ref[1]).all()
+        assert (np.abs(got[0] - ref[0]) <= 1e-13 * np.abs(ref[0])).all()
+        assert (np.abs(got[1][:, :4] - ref[1][:, :4]) <= 1e-13 * np.abs(ref[1][:, :4])).all()
+        assert (got[1][:, 4:] == ref[1][:, 4:]).all()          # understocking and bounds: per-unit sums, keeper's order
     info = emu.plan_info(ints, reals)
-    assert info["W"] == 13 and info["ncols"] == 13 and info["n_s"] == 2 * 260 + 2 * 3 * 20
+    # state: NW - 1 zero rows, num and wgt of the 260 cells, the maturing fish of 3 columns, NBX - 1 slack rows
+    assert info["W"] == 15 and info["ncols"] == 13 and info["n_s"] == 4 + 2 * 260 + 2 * 3 * 20 + 3
+    assert info["seglen"] == [8, 8] and info["units"] == 13 * 3
+
+
+@pytest.mark.parametrize("name", ["C2", "C4", "C5"])
+def test_partition_into_units_only_regroups_sums(oracle_lib, name):
+    """Whole columns (seg = -1), the planner's row segments and a finer partition: the ghost rows hand every unit the rows
+    below it, so the results differ only by the grouping of the per-unit partial sums."""
+    model, p, ints, reals, full, _ = _setup(name, 3)
+    whole = emu.eval_batch(ints, reals, full, want_comp=True, seg=-1)
+    assert emu.plan_info(ints, reals, seg=-1)["units"] == emu.plan_info(ints, reals)["ncols"]
+    for seg in (0, 4 if name != "C4" else 16, 12 if name != "C4" else 20):
+        got = emu.eval_batch(ints, reals, full, want_comp=True, seg=seg, smem_state=(seg != 0))
+        ncomp = len(model.comp_names)
+        assert (np.abs(got[1][:, :ncomp] - whole[1][:, :ncomp]) <= 1e-12 * np.abs(whole[1][:, :ncomp])).all()
+        us_tol = us_tolerance(model, p, whole[1][:, -2], rtol=0.0)
+        assert (np.abs(got[0] - whole[0]) <= 1e-12 * np.abs(whole[0]) + US_WEIGHT * us_tol).all()
 
 
 def test_tiles_lanes_and_ragged_end(oracle_lib):
