@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel", type=int, default=0, help="0 = automatic dispatch, 3 = thread kernel, 4 = tile kernel (profiling)")
     ap.add_argument("--tile-warps", type=int, default=0, help="warps per tile of the tile kernel (0 = planner's choice)")
+    ap.add_argument("--tile-seg", type=int, default=0, help="rows per unit of the tile kernel (0 = planner's choice, -1 = whole columns)")
     return ap.parse_args()
 
 
@@ -213,8 +214,8 @@ def main():
     h = fn.handle
     if a.kernel:
         h.set_kernel(a.kernel)
-    if a.tile_warps:
-        h.set_tile_warps(a.tile_warps)
+    if a.tile_warps or a.tile_seg:
+        h.set_tile_partition(a.tile_warps, a.tile_seg)
     B, P = a.batch, h.n_par
 
     # ---- inputs: NB distinct batches so that the parameter stream (NB x B x P x 8 B) exceeds the 126 MB L2

@@ -6,6 +6,8 @@ namespace g3i {
 constexpr unsigned REPORT_STRIDE = 32;      // workspace stride of the single-vector report variant
 // tile kernel (g3_tile.cuh): T = double | Dual<NTAN>, NW = 5 | 16, state in shared memory or in the slab
 const void* tile_d5(bool smem);
+const void* tile_d5_w24(bool smem);
+const void* tile_d5_w32(bool smem);
 const void* tile_d16(bool smem);
 const void* tile_g5(bool smem);
 const void* tile_g16(bool smem);

@@ -34,6 +34,7 @@ using namespace g3;
 
 constexpr int NL = 32;      // lanes = evaluations per tile
 constexpr int NBX = 4;      // rows per block of the plain-double instantiations: the planner aligns row segments to it
+constexpr int SHW = 32;     // most warps of a tile (unit warps + keeper): stride of the per-warp likelihood shares
 #ifndef __CUDACC__
 using std::max; using std::min;
 #endif
@@ -84,7 +85,7 @@ struct CompRec {
     int csr_ptr_ioff, csr_idx_ioff, csr_coef_roff, cell_dest_ioff, cell_coef_roff, tidx_ioff, cmp_ioff;
     int n_times, param_roff, g_ms, obs_off, obsconst_off;
     int n_groups, group_len;    // dests whose total the comparison needs: sumofsquares n_areag slabs, multinomial every slice
-    int g_pt, g_pv;             // [n_groups][16] the warps' shares of the group totals; [16] of the component's value
+    int g_pt, g_pv;             // [n_groups][SHW] the warps' shares of the group totals; [SHW] of the component's value
     int g_cpart;                // partial sums of the split dests
     int task_off;               // tb: [W + 2] offsets into tb, then each warp's tasks (dest, first term, end term, slot, group)
     int split_off;              // tb: count, then (dest, first slot, slots) of every split dest
@@ -105,10 +106,11 @@ struct TArgs {
     int n_g;                // G entries per lane; the state entries follow them when SMEM = false
     int s_num, s_wgt;       // S entry bases (NW - 1 zero entries lie below s_num)
     int g_slot, g_eot, g_cn, g_ctot, g_bterm, g_wscr, wscr_n, cf_rows;
-    int wunit_off;          // tb: [W + 1] offsets into tb, then each warp's units
     int ax_off, ax_n;       // tb: abundance collect vectors
     int zr_off, zr_n;       // tb: (space, first entry, count) triples zeroed once per tile: pads and the band tables
-    int agedst_l_off;       // tb: length group of each agedst entry
+    int agedst_l_off;       // tb: [maxL + 1] first agedst entry of each length group (they are sorted by length group, then cell)
+    int uorder_off;         // tb: the units, most expensive first (the work queues' order)
+    int inc_off, inc_n;     // tb: global columns that receive maturing fish
     int inc_any_mask;       // bit (cur_step-1): some column receives maturing fish on that step
     int any_ghost;          // some column is split into several units
     int NWc;                // band width the tables are laid out for (the kernel's NW)
@@ -120,7 +122,15 @@ struct TArgs {
 #define G3T_ANY(p) __any_sync(0xffffffffu, (p))
 #define G3T_CTX_DECL
 #define G3T_CTX_ARG
+// the next ticket of a work queue (a counter in shared memory), the same for every lane of the warp
+__device__ __forceinline__ int g3t_grab(int* ctr) {
+    int v = 0;
+    if ((threadIdx.x & 31) == 0) v = atomicAdd(ctr, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+#define G3T_GRAB(p) g3t_grab(p)
 #else
+#define G3T_GRAB(p) __atomic_fetch_add((p), 1, __ATOMIC_SEQ_CST)
 struct EmuCtx { void (*bar)(void*); void* arg; };
 #define G3T_BAR() ctx.bar(ctx.arg)
 #define G3T_ANY(p) (p)
@@ -220,11 +230,11 @@ __device__ __forceinline__ void grow_gather(const double* __restrict__ pN, const
 
 // T: double or Dual<N>; NW: compiled width of the growth band (maxlengthgroupgrowth + 1 <= NW);
 // SMEM: stock state in shared memory (smem = its base) or in the global slab
-template <class T, int NW, bool SMEM>
-__device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const int warp, const int lane, const int cta,
+template <class T, int NW, bool SMEM, int NBV = 0>
+__device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr, const int warp, const int lane, const int cta,
                                           const int ncta G3T_CTX_DECL) {
     constexpr int NTAN = Tan<T>::n;
-    constexpr int NB = NTAN > 0 ? 1 : NBX;                  // rows per block (interleaved avoid_zero / reciprocal chains)
+    constexpr int NB = NBV > 0 ? NBV : (NTAN > 0 ? 1 : NBX);    // rows per block (interleaved avoid_zero / reciprocal chains)
     constexpr unsigned C = (unsigned)(NTAN + 1) * NL;       // doubles per entry
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;
@@ -250,7 +260,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
     const long long ntile = (total + LPT - 1) / LPT;
     const double us_power = R[I[G3H_US_ROFF]], us_weight = R[I[G3H_US_ROFF] + 1];
     const bool have_us = I[G3H_US_N] > 0;
-    const int wu0 = keeper ? 0 : tb[A.wunit_off + warp], wu1 = keeper ? 0 : tb[A.wunit_off + warp + 1];     // this warp's units: tb[wu0..wu1)
+    // The units of a phase are a work queue: a counter in shared memory (ctr: one per phase and step parity) hands the next unit
+    // of the planner's list (most expensive first) to whichever unit warp is free -- the cost of a unit depends on the data
+    // (rows with plenty of fish skip the avoid_zero chain), so no static assignment balances. Every per-unit result is stored
+    // per unit and summed in unit order afterwards: which warp processed a unit changes nothing.
+    const int NU = A.NU;
+#define G3T_UNITS(q, k) for (int k = keeper ? NU : G3T_GRAB(ctr + (q)); k < NU; k = G3T_GRAB(ctr + (q)))
 
     for (long long tile = cta; tile < ntile; tile += ncta) {
         const long long work0 = tile * LPT + lane;
@@ -276,6 +291,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 
         // ================= scalar formula slots, once per parameter vector; pads and band tables start from zero
         for (int i = warp; i < A.NSLOT; i += W) GS(A.g_slot + i, eval_slot_g<T>(I, R, prow, seed, i));
+        if (keeper) for (int i = 0; i < 8; i++) ctr[i] = 0;
         for (int z = 0; z < A.zr_n; z++) {
             const int space = tb[A.zr_off + 3 * z], e0 = tb[A.zr_off + 3 * z + 1], n = tb[A.zr_off + 3 * z + 2];
             for (int i = warp; i < n; i += W) { if (space) SS(e0 + i, T(0.0)); else GS(e0 + i, T(0.0)); }
@@ -493,6 +509,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
             const bool lane_on = !bad_time && t <= total_steps;
             if (!G3T_ANY(lane_on)) break;       // (every warp holds the same 32 evaluations: the decision is block-uniform)
             const int step = t % NSTEPS, yidx = t / NSTEPS;
+            int* const qn = ctr + 4 * (t & 1);          // this step's queues; the keeper rewinds the next step's (idle since the step before)
+            if (keeper) for (int i = 0; i < 4; i++) ctr[4 * ((t + 1) & 1) + i] = 0;
             const int idt = A.step_idt[step];
             const double dt = A.dt_len[idt] / 12.0;
             const bool final_step = step == NSTEPS - 1;
@@ -545,8 +563,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 
             // ================= g3a_predate step 1: suitable biomass per (predator, area[, predator length]) (R/action_predate.R:314-333)
             if (pred_now) {
-                for (int wi = wu0; wi < wu1; wi++) {        // partial sums of the own units
-                    const UnitRec& U = A.unit[tb[wi]];
+                G3T_UNITS(qn - ctr + 0, uk) {              // partial sums per unit
+                    const UnitRec& U = A.unit[tb[A.uorder_off + uk]];
                     const ColRec& Cl = A.col[U.gc];
                     const StockRec& St = A.st[Cl.s];
                     const int L = St.L, c_lo = Cl.cell0 + U.lo;
@@ -686,8 +704,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 
             // ================= own units, pass 1: g3a_predate (R/action_predate.R:335-406) in blocks of NB rows, ascending
             // (the order of the sums); then the unit's top rows go to the ghost rows of the unit above
-            for (int wi = wu0; wi < wu1; wi++) {
-                const UnitRec& U = A.unit[tb[wi]];
+            G3T_UNITS(qn - ctr + 1, uk) {
+                const UnitRec& U = A.unit[tb[A.uorder_off + uk]];
                 const ColRec& Cl = A.col[U.gc];
                 const StockRec& St = A.st[Cl.s];
                 const int L = St.L, nq = St.pp_n, c_lo = Cl.cell0 + U.lo;
@@ -779,13 +797,13 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                     }
                 }
             }
-            if (A.any_ghost) G3T_BAR();
+            G3T_BAR();          // (pass 2 of a unit may run on another warp than its pass 1; ghost rows are in place)
 
             // ================= own units, pass 2: natural mortality, growth (+ maturing split), and -- unless maturing fish are
             // about to arrive -- renewal and the collect vectors. Length growth only looks DOWN the length axis, so sweeping
             // the blocks from the top the update is in place: every source row is still the old value when a block is rebuilt.
-            for (int wi = wu0; wi < wu1; wi++) {
-                const UnitRec& U = A.unit[tb[wi]];
+            G3T_UNITS(qn - ctr + 2, uk) {
+                const UnitRec& U = A.unit[tb[A.uorder_off + uk]];
                 const ColRec& Cl = A.col[U.gc];
                 const StockRec& St = A.st[Cl.s];
                 const int L = St.L, c_lo = Cl.cell0 + U.lo;
@@ -919,20 +937,28 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
             // elementwise per cell, so its (column, block) units are dealt to ALL warps, not only to the owners.
             if ((A.inc_any_mask >> step) & 1) {
                 G3T_BAR();
-                ucnt = 0;
-                for (int gc = 0; gc < A.NCOLS; gc++) {
-                    const ColRec& Cl = A.col[gc];
-                    if (!(Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1))) continue;
+                int nitem = 0;          // blocks of the receiving columns (tb: A.inc_n global columns)
+                for (int i = 0; i < A.inc_n; i++) {
+                    const ColRec& Cl = A.col[tb[A.inc_off + i]];
+                    if ((Cl.inc_mask >> step) & 1) nitem += (A.st[Cl.s].L + NB - 1) / NB;
+                }
+                for (int k = G3T_GRAB(qn + 3); k < nitem; k = G3T_GRAB(qn + 3)) {
+                    int i = 0, blk = k;
+                    for (;; i++) {
+                        const ColRec& Ci = A.col[tb[A.inc_off + i]];
+                        if (!((Ci.inc_mask >> step) & 1)) continue;
+                        const int n = (A.st[Ci.s].L + NB - 1) / NB;
+                        if (blk < n) break;
+                        blk -= n;
+                    }
+                    const ColRec& Cl = A.col[tb[A.inc_off + i]];
                     const StockRec& St = A.st[Cl.s];
                     const int ren_mask = renewals_now(St);
-                    for (int r0 = 0; r0 < St.L; r0 += NB) {
-                        if (!mine()) continue;
-                        const int nb = min(NB, St.L - r0);
-                        T num[NB], wgt[NB];
+                    const int r0 = blk * NB, nb = min(NB, St.L - r0);
+                    T num[NB], wgt[NB];
 #pragma unroll
-                        for (int b = 0; b < NB; b++) { const int l = min(r0 + b, St.L - 1); num[b] = S(A.s_num + Cl.cell0 + l); wgt[b] = S(A.s_wgt + Cl.cell0 + l); }
-                        finish_block(Cl, St, r0, nb, num, wgt, true, ren_mask);
-                    }
+                    for (int b = 0; b < NB; b++) { const int l = min(r0 + b, St.L - 1); num[b] = S(A.s_num + Cl.cell0 + l); wgt[b] = S(A.s_wgt + Cl.cell0 + l); }
+                    finish_block(Cl, St, r0, nb, num, wgt, true, ren_mask);
                 }
             }
 
@@ -952,7 +978,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                     const int ms = Cm.g_ms + (si ? I[Cm.tidx_ioff + t] * nd : 0);
                     const int xs = A.xb[Cm.xbuf].g_x;
                     const bool tot_now = Cm.n_groups > 0 && I[Cm.cmp_ioff + t];
-                    if (tot_now) for (int g = 0; g < Cm.n_groups; g++) GS(Cm.g_pt + g * 16 + warp, T(0.0));
+                    if (tot_now) for (int g = 0; g < Cm.n_groups; g++) GS(Cm.g_pt + g * SHW + warp, T(0.0));
                     const int32_t* __restrict__ ci = A.cterm_idx;
                     const double* __restrict__ cc = A.cterm_coef;
                     for (int k = tb[Cm.task_off + warp]; k < tb[Cm.task_off + warp + 1]; k += 5) {
@@ -963,7 +989,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                         if (slot < 0) acc = acc + G(ms + e);
                         if (slot == -1) GS(ms + e, acc);
                         else GS(Cm.g_cpart + (slot < 0 ? -2 - slot : slot), acc);
-                        if (tot_now) GS(Cm.g_pt + grp * 16 + warp, G(Cm.g_pt + grp * 16 + warp) + acc);
+                        if (tot_now) GS(Cm.g_pt + grp * SHW + warp, G(Cm.g_pt + grp * SHW + warp) + acc);
                     }
                 }
                 G3T_BAR();
@@ -1003,7 +1029,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                             const int g = e / glen;
                             if (g != gcur) {        // total of the group: the warps' shares, in warp order
                                 T tot(0.0);
-                                for (int w = 0; w < W; w++) tot = tot + G(Cm.g_pt + g * 16 + w);
+                                for (int w = 0; w < W; w++) tot = tot + G(Cm.g_pt + g * SHW + w);
                                 rt = 1.0 / avoid_zero(tot);
                                 gcur = g;
                             }
@@ -1127,9 +1153,9 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
                                 SS(nb_ + base, T(0.0));
                             }
                         }
-                        for (int i = 0; i < A.n_agedst; i++) {
+                        for (int i = tb[A.agedst_l_off + l]; i < tb[A.agedst_l_off + l + 1]; i++) {
                             const int4 e = A.agedst[i];     // (destination cell, stash entry num, stash entry wgt, ratio slot); same l
-                            if (e.x < 0 || tb[A.agedst_l_off + i] != l) continue;
+                            if (e.x < 0) continue;
                             const T n0 = S(A.s_num + e.x);
                             const T moved = S(e.y) * SLOT(e.w);
                             SS(A.s_wgt + e.x, ratio_add_pop(S(A.s_wgt + e.x), n0, S(e.z), moved));
@@ -1155,13 +1181,15 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, const in
 #undef GP
 #undef SP
 #undef SLOT
+#undef G3T_UNITS
 }
 
 #ifdef __CUDACC__
-template <class T, int NW, bool SMEM, int MAXT>
+template <class T, int NW, bool SMEM, int MAXT, int NBV = 0>
 __global__ void __launch_bounds__(MAXT, 1) eval_tile_kernel(const __grid_constant__ TArgs A) {
     extern __shared__ __align__(16) double g3t_smem[];
-    tile_body<T, NW, SMEM>(A, g3t_smem, threadIdx.x >> 5, threadIdx.x & 31, blockIdx.x, gridDim.x);
+    __shared__ int g3t_ctr[8];
+    tile_body<T, NW, SMEM, NBV>(A, g3t_smem, g3t_ctr, threadIdx.x >> 5, threadIdx.x & 31, blockIdx.x, gridDim.x);
 }
 #endif
 

@@ -27,7 +27,9 @@ struct TilePlan {
     std::vector<double> row_cost;       // relative cost of one row of each column per step
     std::vector<double> unit_cost;
     int g_fixed = 0, tb_fixed = 0;      // G entries / tb words that do not depend on the partition into units
+    int tb_units = 0;                   // tb words up to and including the partition's lists (the collect task lists follow)
     int max_cx = 0, maxnarea = 1;
+    int max_W = 15;             // most unit warps (15 + keeper = 512 threads at 128 registers; 23 + keeper = 768 at 80)
     std::vector<std::vector<int>> pp_of_stock;
     // collect terms of all components (cell index, coefficient) and the tasks they are cut into: (dest, first term, end term, slot, group)
     std::vector<int32_t> cterm_idx; std::vector<double> cterm_coef;
@@ -137,23 +139,23 @@ inline void plan_build_units(TilePlan& P) {
     A.cf_rows = (max_len + NBX - 1) / NBX * NBX;
     A.wscr_n = std::max({2 * P.maxnarea, (1 + P.max_cx) * A.cf_rows, 1});
     A.g_wscr = ng;
-    A.wunit_off = (int)P.tb.size();
+    // the work queues hand the units out most expensive first
+    std::vector<int> order(P.unit.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.unit_cost[x] > P.unit_cost[y]; });
+    A.uorder_off = (int)P.tb.size();
+    for (int u : order) P.tb.push_back(u);
+    P.tb_units = (int)P.tb.size();
 }
 
-// (re)build the warp lists of a plan for W warps; they live at the end of tb
+// set the warp count of a plan: W unit warps take units from the work queues; the collect tasks are dealt to all W + 1 warps
+// (lists at the end of tb)
 inline void plan_set_warps(TilePlan& P, int W) {
-    W = std::max(1, std::min({W, P.a.NU, 15}));
-    std::vector<std::vector<int>> units;
-    assign_columns(P.unit_cost, W, &units);
-    P.tb.resize(P.a.wunit_off);
-    const int base = P.a.wunit_off;
-    P.tb.resize(base + W + 1);
-    for (int w = 0; w < W; w++) {
-        P.tb[base + w] = (int)P.tb.size();
-        for (int u : units[w]) P.tb.push_back(u);
-    }
-    P.tb[base + W] = (int)P.tb.size();
+    W = std::max(1, std::min({W, P.a.NU, P.max_W}));
+    P.tb.resize(P.tb_units);
     P.a.W = W;
+    // per-warp scratch follows the other G entries (W unit warps + the keeper warp)
+    P.a.n_g = P.a.g_wscr + (W + 1) * P.a.wscr_n;
     // collect tasks of every component, dealt by size to all W + 1 warps (the keeper warp takes part)
     for (int c = 0; c < P.a.NCOMP; c++) {
         const std::vector<int>& T = P.ctask[c];
@@ -199,7 +201,7 @@ inline void plan_choose_partition(TilePlan& P, int W) {
         const int w = std::max(1, std::min<int>(W, (int)cost.size()));
         double sum = 0; for (double c : cost) sum += c;
         const double eff = assign_columns(cost, w, nullptr);
-        return sum / (w * eff) * (15.0 / w > 1.0 ? 1.0 + 0.25 * (15.0 / w - 1.0) : 1.0);      // fewer warps hide less latency
+        return sum / (w * eff) * ((double)W / w > 1.0 ? 1.0 + 0.25 * ((double)W / w - 1.0) : 1.0);      // fewer warps hide less latency
     };
     std::vector<int> seg(A.NS);
     for (int s = 0; s < A.NS; s++) seg[s] = P.st[s].L;
@@ -222,8 +224,9 @@ inline void plan_choose_partition(TilePlan& P, int W) {
 
 // want_W: unit warps (0 = as many as useful, at most 15). want_seg: rows per unit, 0 = the planner's choice (made for the
 // automatic warp count whatever want_W is, so that changing the warp count alone never changes a sum), -1 = whole columns.
-inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0, int want_seg = 0) {
+inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0, int want_seg = 0, int max_W = 15) {
     TilePlan P;
+    P.max_W = std::max(1, std::min(max_W, SHW - 1));
     TArgs& A = P.a;
     auto fail = [&](const std::string& w) { P.ok = false; P.why = w; return P; };
     A.NC = I[G3H_NCELL]; A.NS = I[G3H_NSTOCK]; A.NPP = I[G3H_NPP]; A.NPRED = I[G3H_NPRED]; A.NCOMP = I[G3H_NCOMP];
@@ -362,6 +365,8 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
             if (!ok) return fail("maturation hand-over is not column to column");
         }
     }
+    A.inc_off = (int)P.tb.size(); A.inc_n = 0;
+    for (int gc = 0; gc < ncols; gc++) if (P.col[gc].inc_tn >= 0) { P.tb.push_back(gc); A.inc_n++; }
     // one renewal per (column, step) is what finish_cell applies in a defined order
     for (int s = 0; s < A.NS; s++) {
         const StockRec& r = P.st[s];
@@ -400,13 +405,18 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         // the kernel walks destinations in cell order within a length group (the thread kernel's order)
         std::vector<int> ord(P.agedst.size());
         for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
-        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return P.agedst[x].x < P.agedst[y].x; });
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+            return agedst_l[x] != agedst_l[y] ? agedst_l[x] < agedst_l[y] : P.agedst[x].x < P.agedst[y].x; });
         std::vector<int4> ad2; std::vector<int32_t> al2;
         for (int i : ord) { ad2.push_back(P.agedst[i]); al2.push_back(agedst_l[i]); }
         P.agedst = ad2;
         A.n_agedst = (int)P.agedst.size();
-        A.agedst_l_off = (int)P.tb.size();
-        for (int v : al2) P.tb.push_back(v);
+        A.agedst_l_off = (int)P.tb.size();      // first entry of each length group
+        for (int l = 0; l <= A.maxL; l++) {
+            int k = 0;
+            while (k < (int)al2.size() && al2[k] < l) k++;
+            P.tb.push_back(k);
+        }
         if (P.agedst.empty()) P.agedst.push_back(make_int4(-1, 0, 0, 0));
     }
 
@@ -519,7 +529,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         r.n_groups = 0; r.group_len = 1;
         if (r.func == G3F_SUMOFSQUARES) { r.n_groups = r.n_areag; r.group_len = r.n_slices * r.n_bins; }
         if (r.func == G3F_MULTINOMIAL) { r.n_groups = r.n_areag * r.n_slices; r.group_len = r.n_bins; }
-        r.g_pt = takeg(r.n_groups * 16); r.g_pv = takeg(16);
+        r.g_pt = takeg(r.n_groups * SHW); r.g_pv = takeg(SHW);
         // collect terms per dest, cut into tasks
         {
             std::vector<std::vector<std::pair<int, double>>> rows(r.n_dest);
@@ -607,7 +617,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     // ---- partition into units and their assignment to warps
     P.seglen.resize(A.NS);
     for (int s = 0; s < A.NS; s++) P.seglen[s] = P.st[s].L;
-    if (want_seg == 0) plan_choose_partition(P, 15);
+    if (want_seg == 0) plan_choose_partition(P, P.max_W);
     else if (want_seg > 0)
         for (int s = 0; s < A.NS; s++) {
             const int m = (want_seg + NBX - 1) / NBX * NBX;
@@ -615,7 +625,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         }
     for (int s = 0; s < A.NS; s++) P.seglen[s] = std::min(P.seglen[s], 64);     // (the kernel keeps one bit per row of a unit)
     plan_build_units(P);
-    plan_set_warps(P, want_W > 0 ? want_W : 15);
+    plan_set_warps(P, want_W > 0 ? want_W : P.max_W);
     P.ok = true;
     return P;
 }

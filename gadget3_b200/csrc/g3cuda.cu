@@ -126,7 +126,10 @@ int tile_geom(g3cuda_model* m, TileGeom* g) {
     g->in_smem = state <= m->smem_optin;
     g->smem = g->in_smem ? state : 0;
     const bool wide = m->tplan.maxn > 4;
-    g->fn = dual ? (wide ? g3i::tile_g16(g->in_smem) : g3i::tile_g5(g->in_smem)) : (wide ? g3i::tile_d16(g->in_smem) : g3i::tile_d5(g->in_smem));
+    const int threads = (m->targs.W + 1) * 32;
+    if (threads > 512 && (dual || wide)) return fail(G3CUDA_EUNSUPP, "more than 16 warps per tile exist for plain values and narrow growth bands only");
+    g->fn = dual ? (wide ? g3i::tile_g16(g->in_smem) : g3i::tile_g5(g->in_smem))
+                 : (wide ? g3i::tile_d16(g->in_smem) : threads > 768 ? g3i::tile_d5_w32(g->in_smem) : threads > 512 ? g3i::tile_d5_w24(g->in_smem) : g3i::tile_d5(g->in_smem));
     CUDA_TRY(cudaFuncSetAttribute(g->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->per_sm, g->fn, (m->targs.W + 1) * 32, g->smem));
     if (g->per_sm < 1) return fail(G3CUDA_EUNSUPP, "tile kernel does not fit one SM (%d threads, %zu bytes of shared memory)", (m->targs.W + 1) * 32, g->smem);
@@ -828,11 +831,11 @@ int g3cuda_set_tile_warps(g3cuda_model* m, int warps) {
 }
 
 int g3cuda_set_tile_partition(g3cuda_model* m, int warps, int seg_rows) {
-    if (!m || warps < 0 || warps > 15 || seg_rows < -1) return fail(G3CUDA_EINVAL, "bad argument");
+    if (!m || warps < 0 || warps > g3t::SHW - 1 || seg_rows < -1) return fail(G3CUDA_EINVAL, "bad argument");
     if (!m->tile_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", m->tplan.why.c_str());
     CUDA_TRY(cudaSetDevice(m->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    g3t::TilePlan np = g3t::make_tile_plan(m->I.data(), m->R.data(), warps, seg_rows);
+    g3t::TilePlan np = g3t::make_tile_plan(m->I.data(), m->R.data(), warps, seg_rows, std::max(warps, 15));
     if (!np.ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", np.why.c_str());
     // the record tables that depend on the partition: stocks (unit ranges), units, pairs, totals, predators
     auto up = [&](auto& vec) { auto* d = dev_copy(vec); if (d) m->owned.push_back((void*)d); return d; };

@@ -20,12 +20,13 @@ void run(const TArgs& A, int W, int ncta, size_t smem_doubles) {
     for (int cta = 0; cta < ncta; cta++)
         for (int lane = 0; lane < A.lanes_per_tile; lane++) {
             std::vector<double> smem(smem_doubles + 64, 0.0);
+            int ctr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             std::barrier<> sync(W + 1);        // W column warps + the keeper warp
             Bar bar{&sync};
             EmuCtx ctx{bar_wait, &bar};
             std::vector<std::thread> th;
             for (int w = 0; w <= W; w++)
-                th.emplace_back([&, w]() { tile_body<T, NW, SMEM>(A, smem.data(), w, lane, cta, ncta, ctx); });
+                th.emplace_back([&, w]() { tile_body<T, NW, SMEM>(A, smem.data(), ctr, w, lane, cta, ncta, ctx); });
             for (auto& t : th) t.join();
         }
 }
