@@ -155,19 +155,6 @@ template <int N> __device__ __forceinline__ void stv(double* p, const Dual<N>& v
 template <class T> __device__ __forceinline__ T ldT(const double* p) { T r; ldv(p, r); return r; }
 template <class T> __device__ __forceinline__ void stT(double* p, const T& v) { stv(p, v); }
 
-// avoid_zero(x) returns x itself when 1000 x > 34 (lsa_c_n's early-out: the log1p term is below half an ulp). div_plenty()
-// is a / avoid_zero(b) for such b, with exactly the operations the chain performs on them, so that a row's value does not
-// depend on whether its warp took the plain or the chain path (i.e. on which other vectors share its tile).
-__device__ __forceinline__ bool az_is_identity(double x) { return x * 1000.0 > 34.0; }
-template <int N> __device__ __forceinline__ bool az_is_identity(const Dual<N>& x) { return x.v * 1000.0 > 34.0; }
-__device__ __forceinline__ double div_plenty(double a, double b) { return a * rcp_bf((b * 1000.0) * 1e-3); }
-template <int N> __device__ __forceinline__ Dual<N> div_plenty(const Dual<N>& a, const Dual<N>& b) { return xdiv(a, avoid_zero(b)); }
-#ifdef __CUDACC__
-#define G3_FFSLL(x) __ffsll((long long)(x))
-#else
-#define G3_FFSLL(x) __builtin_ffsll((long long)(x))
-#endif
-
 // ---- g3a_growmature (R/action_grow.R:340-497), the banded gather of ONE BLOCK of NB destination rows r0 .. r0 + NB - 1 of a
 // unit, as straight-line code: source rows r0 - (NW - 1) .. r0 + NB - 1 are loaded once each, every (row, jump) pair is a
 // compile-time offset from the block pointers. Pointers address row 0 of the unit (pN, pW: state; pQ: walpha l^wbeta;
@@ -845,14 +832,13 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 const bool stash = trans_now && Cl.s_tn >= 0;
                 double* const pTn = stash ? SP(Cl.s_tn + U.lo) : pNum;
                 double* const pTw = stash ? SP(Cl.s_tw + U.lo) : pWgt;
-                double* const pBn = GP(A.g_wscr + warp * A.wscr_n);        // the staying fish of each row, where num also takes the remainder back
-                // Mean weight = sum / avoid_zero(number). With more than 0.034 fish avoid_zero() is the identity (g3_math.cuh), which is
-                // the case for most rows on most steps: sweep 1 divides plainly where EVERY lane has that many and notes the other
-                // rows (bit r of need_*), sweep 2 runs the avoid_zero chain for those alone, NB rows at a time.
-                unsigned long long need_b = 0, need_a = 0;
+                bool ren_here = false;      // a renewal into this column at this step
+                for (int r = 0; r < St.n_renew; r++)
+                    ren_here = ren_here || (((ren_mask >> r) & 1) && Cl.aidx == I[St.renew_ioff + r * G3R_LEN + G3R_AGE_IDX]);
+                const bool finish_here = !inc_here && (ren_here || xact);
                 for (int j = nblk - 1; j >= 0; j--) {
                     const int r0 = j * NB, nb = min(NB, U.len - r0);
-                    T an[NB], aw[NB], num[NB], wgt[NB];
+                    T an[NB], aw[NB], num[NB], wgt[NB], de[NB];
                     const bool low = U.g_ghost >= 0 && r0 < NW - 1;
                     if (cont_now) {
                         if (low) grow_gather<T, NW, NB, 1, true>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
@@ -864,73 +850,32 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         if (low) grow_gather<T, NW, NB, 0, true>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
                         else grow_gather<T, NW, NB, 0, false>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
                     }
+                    // ---- mean weights: one avoid_zero + reciprocal per row and part, the chains of the block interleaved; where
+                    // every row of the block has more than 0.034 fish on every lane avoid_zero() is the identity and the chain is
+                    // skipped (div_az_n, g3_math.cuh) -- rows of that kind come in runs, so the blocks catch nearly all of them
 #pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        const bool plenty = G3_ALL(az_is_identity(num[b]));
-                        if (b < nb && !plenty) need_b |= 1ull << (r0 + b);
-                        if (plenty) wgt[b] = div_plenty(wgt[b], num[b]);
-                    }
+                    for (int b = 0; b < NB; b++) de[b] = num[b];
+                    div_az_n(wgt, de);
                     if (trans_now) {
                         if (stash) {
 #pragma unroll
-                            for (int b = 0; b < NB; b++) {
-                                const bool plenty = G3_ALL(az_is_identity(an[b]));
-                                if (b < nb && !plenty) need_a |= 1ull << (r0 + b);
-                                if (plenty) aw[b] = div_plenty(aw[b], an[b]);
+                            for (int b = 0; b < NB; b++) de[b] = an[b];
+                            div_az_n(aw, de);
+#pragma unroll
+                            for (int b = 0; b < NB; b++)
                                 if (b < nb) { stT<T>(pTn + (unsigned)(r0 + b) * C, an[b]); stT<T>(pTw + (unsigned)(r0 + b) * C, aw[b]); }
-                            }
                         }
                         // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
 #pragma unroll
-                        for (int b = 0; b < NB; b++) {
-                            if (b < nb) stT<T>(pBn + (unsigned)(r0 + b) * C, num[b]);
-                            num[b] = num[b] + an[b] * remf;
-                        }
+                        for (int b = 0; b < NB; b++) num[b] = num[b] + an[b] * remf;
                     }
+                    if (finish_here) finish_block(Cl, St, U.lo + r0, nb, num, wgt, false, ren_mask);
+                    else {
 #pragma unroll
-                    for (int b = 0; b < NB; b++)
-                        if (b < nb) { stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]); stT<T>(pWgt + (unsigned)(r0 + b) * C, wgt[b]); }
+                        for (int b = 0; b < NB; b++)
+                            if (b < nb) { stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]); stT<T>(pWgt + (unsigned)(r0 + b) * C, wgt[b]); }
+                    }
                 }
-                // ---- sweep 2: the rows that need the avoid_zero chain (the last group repeats its last row: same value, same store)
-                const double* const pDe = trans_now ? pBn : pNum;
-                while (need_b) {
-                    int r[NB];
-                    T w[NB], de[NB];
-#pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        r[b] = need_b ? G3_FFSLL(need_b) - 1 : r[b > 0 ? b - 1 : 0];
-                        need_b &= need_b - 1;
-                        w[b] = ldT<T>(pWgt + (unsigned)r[b] * C); de[b] = ldT<T>(pDe + (unsigned)r[b] * C);
-                    }
-                    div_az_n(w, de);
-#pragma unroll
-                    for (int b = 0; b < NB; b++) stT<T>(pWgt + (unsigned)r[b] * C, w[b]);
-                }
-                while (need_a) {
-                    int r[NB];
-                    T w[NB], de[NB];
-#pragma unroll
-                    for (int b = 0; b < NB; b++) {
-                        r[b] = need_a ? G3_FFSLL(need_a) - 1 : r[b > 0 ? b - 1 : 0];
-                        need_a &= need_a - 1;
-                        w[b] = ldT<T>(pTw + (unsigned)r[b] * C); de[b] = ldT<T>(pTn + (unsigned)r[b] * C);
-                    }
-                    div_az_n(w, de);
-#pragma unroll
-                    for (int b = 0; b < NB; b++) stT<T>(pTw + (unsigned)r[b] * C, w[b]);
-                }
-                // ---- sweep 3, on the steps that have any: renewal into this column, collect vectors
-                bool ren_here = false;
-                for (int r = 0; r < St.n_renew; r++)
-                    ren_here = ren_here || (((ren_mask >> r) & 1) && Cl.aidx == I[St.renew_ioff + r * G3R_LEN + G3R_AGE_IDX]);
-                if (!inc_here && (ren_here || xact))
-                    for (int j = 0; j < nblk; j++) {
-                        const int r0 = j * NB, nb = min(NB, U.len - r0);
-                        T num[NB], wgt[NB];
-#pragma unroll
-                        for (int b = 0; b < NB; b++) { num[b] = ldT<T>(pNum + (unsigned)(r0 + b) * C); wgt[b] = ldT<T>(pWgt + (unsigned)(r0 + b) * C); }
-                        finish_block(Cl, St, U.lo + r0, nb, num, wgt, false, ren_mask);
-                    }
             }
 
             // ================= columns that receive maturing fish finish once every source column has grown. That part is
@@ -1023,15 +968,14 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
                         const double eps = R[Cm.param_roff];
                         const int glen = Cm.group_len;
-                        int gcur = -1;
+                        int g = -1, gend = 0;       // group of dest e: [gend - glen, gend)
                         T rt(0.0);
                         for (int e = e0; e < nd; e += W) {
-                            const int g = e / glen;
-                            if (g != gcur) {        // total of the group: the warps' shares, in warp order
+                            if (e >= gend) {        // total of the group: the warps' shares, in warp order
+                                while (e >= gend) { g++; gend += glen; }
                                 T tot(0.0);
                                 for (int w = 0; w < W; w++) tot = tot + G(Cm.g_pt + g * SHW + w);
                                 rt = 1.0 / avoid_zero(tot);
-                                gcur = g;
                             }
                             if (func == G3F_SUMOFSQUARES) {
                                 const T dlt = G(ms + e) * rt - op[e];
