@@ -287,7 +287,7 @@ def measure(config, batch, steps, warmup, env, a, main_run):
     peak_tflops = env["peak_tflops"]
     achieved = flop * B / (kms * 1e-3) / 1e12
     info = h.tile_info()
-    on_tile = a.kernel == 4 or (a.kernel == 0 and info["tile_ok"] and (not want_grad or B * ((Kt + 3) // 4) < 4096 or not info["thread_ok"]))
+    on_tile = a.kernel == 4 or (a.kernel == 0 and info["tile_ok"])
     kname = ("g3t::eval_tile_kernel" if on_tile else "g3::eval_thread_kernel") + ("<Dual<4>> (the dual pass carries the value)" if want_grad else "<double>")
     tr, cap = traffic_of(config)
     out = {

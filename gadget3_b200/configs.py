@@ -238,7 +238,8 @@ def build_c4(seed=123):
     """Ling-style model (structure of inttest/codegeneration/run.R:17-183 as BASELINE.json config 4
     describes it): 2 stocks on 35 length groups, maxlengthgroupgrowth 15, constant maturity with the
     hand-over on the last step of the year, 3 total-catch fleets with exponentiall50 suitability,
-    one length distribution per fleet and two log survey indices, 40 years of quarterly steps."""
+    one length distribution per fleet (the lln fleet's is the reference's catchdistribution_ldist_lln.txt fixture) and
+    two log survey indices, 40 years of quarterly steps."""
     rng = np.random.default_rng(seed)
     years = list(range(1979, 2019))
     areas = g3_areas(["area1"])
@@ -292,6 +293,17 @@ def build_c4(seed=123):
         ln = np.clip(rng.normal(lmean, 25, len(yy2)), 20, 400)
         ld = _count(dict(year=[int(y) for y in yy2], step=[int(x) for x in st2], length=_cut(ln, edges)),
                     ["year", "step", "length"])
+        lln = ling_lln_table() if fname == "lln" else None
+        if lln is not None:
+            # the reference's own fixture for this fleet (inttest/codegeneration/catchdistribution_ldist_lln.txt, 1994-2018),
+            # its years wrapped onto the 40-year grid
+            rows = {}
+            for y, s_, l, n in zip(lln["year"], lln["step"], lln["length"], lln["number"]):
+                rows.setdefault(y, []).append((s_, l, n))
+            ld = dict(year=[], step=[], length=[], number=[])
+            for Y in years:
+                for s_, l, n in rows.get(1994 + (Y - years[0]) % 25, []):
+                    ld["year"].append(Y); ld["step"].append(s_); ld["length"].append(l); ld["number"].append(n)
         actions.append(g3l_catchdistribution("ldist_" + fname, ld, fleets=[fleet], stocks=stocks,
                                              function_f=g3l_distribution_sumofsquares(), nll_breakdown=True))
     for nm, lab in (("si_20_52", "[20,52)"), ("si_52_inf", "[52,Inf)")):
@@ -576,12 +588,25 @@ LING_MAT_STDDEV = [12.4081745588022, 11.5741565728647, 11.0523508874244, 11.3447
                    15.9776436358384]
 
 
+def ling_lln_table():
+    """The reference's length-distribution fixture as column dicts (igfs_obs_data of inttest/codegeneration/run.R:120-122:
+    read.table(...) plus area = 1), or None where the file is not shipped."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "catchdistribution_ldist_lln.txt")
+    if not os.path.exists(path):
+        return None
+    rows = [ln.split() for ln in open(path).read().strip().split("\n")[1:]]
+    return dict(year=[int(r[0]) for r in rows], step=[int(r[1]) for r in rows], area=["area1"] * len(rows),
+                length=[float(r[2]) for r in rows], number=[float(r[3]) for r in rows])
+
+
 def build_ling(seed=123):
     """The ling model of the reference's code-generation snapshot (inttest/codegeneration/run.R:17-183,
     generated C++ checked in as inttest/codegeneration/ling.cpp): same stocks, actions, formulas and
     parameter names, so that the oracle can be compared with that generated code (oracle/ref_lib.py).
-    The observation table is synthetic (same shape as catchdistribution_ldist_lln.txt); the numbers in
-    ling_*_stddev and the parameter values are model DATA quoted from run.R:32-40,92-103,161-183."""
+    The observation table is the reference's own fixture, inttest/codegeneration/catchdistribution_ldist_lln.txt
+    (2,270 rows of year, step, length, number; copied as data to tests/golden/, read as run.R:120-122 does); the numbers
+    in ling_*_stddev and the parameter values are model DATA quoted from run.R:32-40,92-103,161-183."""
     from .formula import Lookup, ParamExpr, age as AGE, g3_as_integer, g3_exp
     rng = np.random.default_rng(seed)
     areas = g3_areas(["area1"])
@@ -607,11 +632,13 @@ def build_ling(seed=123):
     st = np.tile([1, 2, 3, 4], len(years))
     totaldata = dict(year=[int(y) for y in yy], step=[int(x) for x in st], area=["area1"] * len(yy),
                      total_weight=[float(x) for x in st])
-    ns = 120
-    yl, sl = np.repeat(yy, ns), np.repeat(st, ns)
-    ln = np.clip(rng.normal(80, 25, len(yl)), 20, 400)
-    obs = _count(dict(year=[int(y) for y in yl], step=[int(x) for x in sl], area=["area1"] * len(yl),
-                      length=_cut(ln, list(range(20, 157, 4)))), ["year", "step", "area", "length"])
+    obs = ling_lln_table()
+    if obs is None:         # (the fixture is missing: a table of the same shape)
+        ns = 120
+        yl, sl = np.repeat(yy, ns), np.repeat(st, ns)
+        ln = np.clip(rng.normal(80, 25, len(yl)), 20, 400)
+        obs = _count(dict(year=[int(y) for y in yl], step=[int(x) for x in sl], area=["area1"] * len(yl),
+                          length=_cut(ln, list(range(20, 157, 4)))), ["year", "step", "area", "length"])
     actions = [
         g3a_time(1994, 2018, [3, 3, 3, 3]),
         # ling_mat_actions

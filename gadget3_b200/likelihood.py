@@ -53,9 +53,12 @@ _RANGE_RE = re.compile(r"^(.+):(.+)$")
 def _parse_levels(lvls):
     """R/likelihood_data.R:1-33: returns list of (name, lower, upper) and open_ended flag."""
     try:
-        m = [float(x) for x in lvls]
+        # numeric lower bounds: sorted, each group ends where the next begins, the last one is open-ended
+        # (parse_levels() on the sorted factor levels, R/likelihood_data.R:1-11,275-281)
+        order = sorted(range(len(lvls)), key=lambda i: float(lvls[i]))
+        m = [float(lvls[i]) for i in order]
         ups = m[1:] + [math.inf]
-        return [(str(n), lo, up) for n, lo, up in zip(lvls, m, ups)], True
+        return [(str(lvls[i]), lo, up) for i, lo, up in zip(order, m, ups)], True
     except (TypeError, ValueError):
         pass
     out = []
