@@ -210,3 +210,34 @@ def test_suitability_closed_forms(lib):
         assert _suit(lib, K["G3SUIT_EXPONENTIAL"], [a, b, g, d], ml, pl) == pytest.approx(e, rel=1e-14)
         assert _suit(lib, K["G3SUIT_RICHARDS"], [a, b, g, d, 1.7], ml, pl) == pytest.approx(e ** (1 / 1.7), rel=1e-13)
         assert _suit(lib, K["G3SUIT_STRAIGHTLINE"], [0.1, 0.004], ml) == pytest.approx(0.1 + 0.004 * ml, rel=1e-15)
+
+
+def test_mature_continuous_age_term_hand_value(oracle_lib):
+    """g3a_mature_continuous with its age term (R/action_mature.R:1-42): per step the share
+    dif_pminmax(m0 * (alpha * ldelta + beta * cur_step_size), 0, 1, 1e5), m0 = 1 / (1 + exp(-alpha (l - l50) - beta (age - a50)))
+    of every length jump matures. With alpha = 0 that share no longer depends on length or jump, so -- growth keeps every
+    fish (plus group), mortality switched off, no landings and no ageing inside the first steps of the year -- an age
+    column of the immature stock that has a destination loses exactly that share of its fish per step, and a column
+    without one (ages 1-2: mat starts at age 3) gets the remainder back and loses nothing. The expected numbers are
+    computed here from the formula, not by the oracle."""
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["C2_MATAGE"]()
+    v = p.values().copy()
+    beta, a50, dt = 0.4, 3.0, 0.25
+    v[p.index("fish_imm.mat.alpha")] = 0.0
+    v[p.index("fish_imm.mat.beta")] = beta
+    v[p.index("fish_imm.mat.a50")] = a50
+    for a in range(1, 6):
+        v[p.index(f"fish_imm.M.{a}")] = 0.0
+    rep = unpack_report(model, Oracle(*model.pack(p)).report(v))
+    num = np.asarray(rep["dstart_fish_imm__num"])          # length x age x area x time
+    tot = num.sum(axis=0)[:, 0, :]                         # age x time
+    for ai, age in enumerate(range(1, 6)):
+        m0 = 1.0 / (1.0 + math.exp(-beta * (age - a50)))
+        share = min(max(m0 * beta * dt, 0.0), 1.0) if age >= 3 else 0.0
+        if age == 1:
+            continue            # (the renewal lands in age 1 at step 1)
+        # the first step of the run: no landings (they come at step 2), no ageing (step 4)
+        assert tot[ai, 1] / tot[ai, 0] == pytest.approx(1.0 - share, rel=1e-9), age
