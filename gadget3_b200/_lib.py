@@ -65,6 +65,16 @@ def load():
     lib.g3cuda_set_tile_warps.restype = C.c_int
     lib.g3cuda_set_tile_partition.argtypes = [vp, C.c_int, C.c_int]
     lib.g3cuda_set_tile_partition.restype = C.c_int
+    lib.g3cuda_multi_create.argtypes = [C.POINTER(_Spec), ip, C.c_int32, C.POINTER(vp)]
+    lib.g3cuda_multi_create.restype = C.c_int
+    lib.g3cuda_multi_free.argtypes = [vp]
+    lib.g3cuda_multi_free.restype = None
+    lib.g3cuda_multi_n_devices.argtypes = [vp]
+    lib.g3cuda_multi_n_devices.restype = C.c_int32
+    lib.g3cuda_multi_model.argtypes = [vp, C.c_int32]
+    lib.g3cuda_multi_model.restype = vp
+    lib.g3cuda_multi_eval_batch.argtypes = [vp, dp, C.c_int64, ip, C.c_int32, dp, dp, dp]
+    lib.g3cuda_multi_eval_batch.restype = C.c_int
     lib.g3cuda_tile_info.argtypes = [vp, ip]
     lib.g3cuda_tile_info.restype = C.c_int32
     lib.g3cuda_math_probe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64,
@@ -79,7 +89,8 @@ def load():
 EXPORTED = ["g3cuda_model_create", "g3cuda_model_free", "g3cuda_n_par", "g3cuda_n_nll", "g3cuda_n_steps",
             "g3cuda_report_len", "g3cuda_eval_batch", "g3cuda_eval_batch_device", "g3cuda_launch_count",
             "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version",
-            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe", "g3cuda_set_tile_warps", "g3cuda_set_tile_partition", "g3cuda_tile_info"]
+            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe", "g3cuda_set_tile_warps", "g3cuda_set_tile_partition", "g3cuda_tile_info",
+            "g3cuda_multi_create", "g3cuda_multi_free", "g3cuda_multi_n_devices", "g3cuda_multi_model", "g3cuda_multi_eval_batch"]
 
 
 def _dp(a):
@@ -187,3 +198,68 @@ def math_probe(which, x, y=None, device=0):
     if rc != 0:
         raise G3CudaError("g3cuda_math_probe: %s (code %d)" % (lib.g3cuda_last_error().decode(), rc))
     return out
+
+
+class _Borrowed(Handle):
+    """A device's handle inside a MultiHandle: same calls, owned by the multi-device handle."""
+
+    def __init__(self, lib, h, device):
+        self.lib, self.h, self.device = lib, h, int(device)
+        self.n_par = lib.g3cuda_n_par(h)
+        self.n_nll = lib.g3cuda_n_nll(h)
+        self.n_steps = lib.g3cuda_n_steps(h)
+
+    def close(self):
+        self.h = None
+
+
+class MultiHandle:
+    """Owns one g3cuda_multi*: the model on several devices, batches cut into one row block per device."""
+
+    def __init__(self, ints, reals, devices):
+        self.lib = load()
+        self.ints = np.ascontiguousarray(ints, dtype=np.int32)
+        self.reals = np.ascontiguousarray(reals, dtype=np.float64)
+        from .spec import K
+        spec = _Spec(K["G3CUDA_SPEC_VERSION"], len(self.ints), self.ints.ctypes.data_as(C.POINTER(C.c_int32)),
+                     len(self.reals), self.reals.ctypes.data_as(C.POINTER(C.c_double)))
+        dv = np.ascontiguousarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        rc = self.lib.g3cuda_multi_create(C.byref(spec), dv.ctypes.data_as(C.POINTER(C.c_int32)), len(dv), C.byref(h))
+        if rc != 0:
+            raise G3CudaError("g3cuda_multi_create: %s (code %d)" % (self.lib.g3cuda_last_error().decode(), rc))
+        self.h = h
+        self.devices = [int(d) for d in dv]
+        self.handles = [_Borrowed(self.lib, C.c_void_p(self.lib.g3cuda_multi_model(h, i)), d) for i, d in enumerate(self.devices)]
+        self.n_par, self.n_nll = self.handles[0].n_par, self.handles[0].n_nll
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.g3cuda_multi_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval_batch(self, par, tangent_idx=None, want_comp=False):
+        """HOST buffers in, HOST buffers out; the devices work on their row blocks concurrently."""
+        par = np.ascontiguousarray(np.atleast_2d(par), dtype=np.float64)
+        B = par.shape[0]
+        if par.shape[1] != self.n_par:
+            raise ValueError(f"expected {self.n_par} parameters per vector, got {par.shape[1]}")
+        nll = np.empty(B)
+        comp = np.empty((B, self.n_nll)) if want_comp else None
+        grad, tidx, Kt = None, None, 0
+        if tangent_idx is not None:
+            tidx = np.ascontiguousarray(tangent_idx, dtype=np.int32)
+            Kt = len(tidx)
+            grad = np.empty((B, Kt))
+        rc = self.lib.g3cuda_multi_eval_batch(self.h, _dp(par), B,
+                                              None if tidx is None else tidx.ctypes.data_as(C.POINTER(C.c_int32)), Kt,
+                                              _dp(nll), _dp(comp), _dp(grad))
+        if rc != 0:
+            raise G3CudaError("g3cuda_multi_eval_batch: %s (code %d)" % (self.lib.g3cuda_last_error().decode(), rc))
+        return nll, comp, grad

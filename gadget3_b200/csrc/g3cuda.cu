@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -808,6 +809,66 @@ int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B, const int32
     std::memcpy(nll, h_nll, sizeof(double) * B);
     if (nll_comp) std::memcpy(nll_comp, h_comp, sizeof(double) * B * NN);
     if (want_grad) std::memcpy(grad, h_grad, sizeof(double) * B * K);
+    return G3CUDA_OK;
+}
+
+// ---- one handle over several devices ("copies all spec/obs data to every selected device"): the rows
+// of a batch are cut into contiguous blocks, one per device, evaluated concurrently by one host thread per device; no
+// device talks to another (the path has no exchange step), every block lands in the caller's buffers directly.
+struct g3cuda_multi {
+    std::vector<g3cuda_model*> m;
+};
+
+int g3cuda_multi_create(const g3cuda_spec* spec, const int32_t* devices, int32_t n_devices, g3cuda_multi** out) {
+    if (!out || !devices || n_devices < 1) return fail(G3CUDA_EINVAL, "bad argument");
+    *out = nullptr;
+    auto* mm = new g3cuda_multi;
+    for (int i = 0; i < n_devices; i++) {
+        g3cuda_model* h = nullptr;
+        const int rc = g3cuda_model_create(spec, devices[i], &h);
+        if (rc != G3CUDA_OK) {          // (the error text is the failing device's)
+            for (auto* x : mm->m) g3cuda_model_free(x);
+            delete mm;
+            return rc;
+        }
+        mm->m.push_back(h);
+    }
+    *out = mm;
+    return G3CUDA_OK;
+}
+
+void g3cuda_multi_free(g3cuda_multi* mm) {
+    if (!mm) return;
+    for (auto* x : mm->m) g3cuda_model_free(x);
+    delete mm;
+}
+
+int32_t g3cuda_multi_n_devices(const g3cuda_multi* mm) { return mm ? (int32_t)mm->m.size() : 0; }
+g3cuda_model* g3cuda_multi_model(g3cuda_multi* mm, int32_t i) { return (mm && i >= 0 && i < (int32_t)mm->m.size()) ? mm->m[i] : nullptr; }
+
+int g3cuda_multi_eval_batch(g3cuda_multi* mm, const double* par, int64_t B, const int32_t* tangent_idx, int32_t K,
+                            double* nll, double* nll_comp, double* grad) {
+    if (!mm || mm->m.empty() || !par || !nll || B < 0) return fail(G3CUDA_EINVAL, "bad argument");
+    const int n = (int)mm->m.size();
+    const int64_t P = mm->m[0]->NPAR, NN = mm->m[0]->NNLL;
+    std::vector<int> rcs(n, G3CUDA_OK);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> th;
+    const int64_t base = B / n, extra = B % n;      // the first B % n devices take one row more (gadget3_b200/shard.py)
+    int64_t lo = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t rows = base + (i < extra ? 1 : 0), at = lo;
+        lo += rows;
+        if (rows == 0) continue;
+        th.emplace_back([&, i, rows, at]() {
+            rcs[i] = g3cuda_eval_batch(mm->m[i], par + at * P, rows, tangent_idx, K, nll + at,
+                                       nll_comp ? nll_comp + at * NN : nullptr, (grad && K > 0) ? grad + at * (int64_t)K : nullptr);
+            if (rcs[i] != G3CUDA_OK) errs[i] = g_err;      // (the error text is thread-local)
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; i++)
+        if (rcs[i] != G3CUDA_OK) return fail(rcs[i], "device %d: %s", mm->m[i]->device, errs[i].c_str());
     return G3CUDA_OK;
 }
 

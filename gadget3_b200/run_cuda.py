@@ -93,6 +93,36 @@ class G3CudaModel:
         return b.finish()
 
 
+def save_spec(model: "G3CudaModel", path, parameters: ParameterTemplate = None, report_len=None):
+    """Write the packed spec for a consumer without this package -- the R glue (R/run_cuda.R: g3_cuda_load_spec()):
+    <path>.ints (int32), <path>.reals (float64), <path>.json (sizes, the parameter template, the report layout) and,
+    when ``report_len`` (g3cuda_report_len) is given, <path>.idx (int32): for every report array, in the model's own
+    dimension order (first index fastest, as R stores arrays), the position of each element in g3cuda_report()'s vector."""
+    import json
+    pt = model.parameter_template if parameters is None else parameters
+    ints, reals = model.pack(pt)
+    np.asarray(ints, dtype=np.int32).tofile(str(path) + ".ints")
+    np.asarray(reals, dtype=np.float64).tofile(str(path) + ".reals")
+    layout = []
+    if report_len:
+        pieces = unpack_report(model, np.arange(int(report_len), dtype=np.float64))
+        idx, pos = [], 0
+        for name, arr in pieces.items():
+            a = np.asarray(arr, dtype=np.float64)
+            flat = a.reshape(-1, order="F") if a.ndim > 1 else a.reshape(-1)
+            flat = np.nan_to_num(flat, nan=-1.0)
+            layout.append({"name": name, "dim": list(a.shape) if a.ndim else [1], "idx_offset": pos})
+            idx.append(flat.astype(np.int32)); pos += flat.size
+        np.concatenate(idx).tofile(str(path) + ".idx")
+    meta = {"n_ints": int(len(ints)), "n_reals": int(len(reals)), "report_layout": layout,
+            "parameter_template": {"switch": list(pt.switch), "value": [float(v) for v in pt.values()],
+                                   "optimise": [bool(i in set(pt.optimised_indices().tolist())) for i in range(len(pt.switch))],
+                                   "lower": [float(v) for v in pt.lower], "upper": [float(v) for v in pt.upper]}}
+    with open(str(path) + ".json", "w") as f:
+        json.dump(meta, f)
+    return meta
+
+
 def g3_to_cuda(actions, strict=False) -> G3CudaModel:
     acts = _flatten(actions)
     by_kind = {}
@@ -570,8 +600,8 @@ class G3CudaADFun:
     """Mirror of the list g3_tmb_adfun() returns (R/run_tmb.R:1254-1325): ``par``, ``fn``, ``gr``,
     ``report`` -- plus batched ``fn_batch`` / ``gr_batch`` / ``nll_components_batch``."""
 
-    def __init__(self, model: G3CudaModel, parameters: ParameterTemplate = None, device=0):
-        from ._lib import Handle
+    def __init__(self, model: G3CudaModel, parameters: ParameterTemplate = None, device=0, devices=None):
+        from ._lib import Handle, MultiHandle
         self.model = model
         self.parameters = (model.parameter_template if parameters is None else parameters).copy()
         ints, reals = model.pack(self.parameters)
@@ -581,7 +611,11 @@ class G3CudaADFun:
         self.par_names = [self.parameters.switch[i] for i in self.opt_idx]
         self.par = self.parameters.values()[self.opt_idx].copy()
         self._full = self.parameters.values()
-        self.handle = Handle(ints, reals, device)
+        # devices = [0, 1, ...]: one handle over several GPUs of the box, the rows of every batch cut into one block per
+        # device (g3cuda_multi_*); `handle` is then the first device's (report, single-vector calls, tuning hooks)
+        self.multi = MultiHandle(ints, reals, devices) if devices is not None and len(devices) > 1 else None
+        self.handle = self.multi.handles[0] if self.multi else Handle(ints, reals, devices[0] if devices else device)
+        self._batch = self.multi if self.multi else self.handle
         self.last_par = self.par.copy()
 
     # full PARAMETER matrix from optimiser-facing vectors
@@ -604,14 +638,14 @@ class G3CudaADFun:
         return self.gr_batch(par[None, :])[1]          # 1 x n matrix, like TMB
 
     def fn_batch(self, P) -> np.ndarray:
-        return self.handle.eval_batch(self.full_par(P))[0]
+        return self._batch.eval_batch(self.full_par(P))[0]
 
     def nll_components_batch(self, P):
-        nll, comp, _ = self.handle.eval_batch(self.full_par(P), want_comp=True)
+        nll, comp, _ = self._batch.eval_batch(self.full_par(P), want_comp=True)
         return nll, comp
 
     def gr_batch(self, P):
-        nll, _, grad = self.handle.eval_batch(self.full_par(P), tangent_idx=self.opt_idx)
+        nll, _, grad = self._batch.eval_batch(self.full_par(P), tangent_idx=self.opt_idx)
         return nll, grad
 
     def report(self, par=None) -> dict:
@@ -676,5 +710,6 @@ def unpack_report(model: G3CudaModel, raw: np.ndarray) -> dict:
     return out
 
 
-def g3_cuda_adfun(model: G3CudaModel, parameters: ParameterTemplate = None, device=0) -> G3CudaADFun:
-    return G3CudaADFun(model, parameters, device)
+def g3_cuda_adfun(model: G3CudaModel, parameters: ParameterTemplate = None, device=0, devices=None) -> G3CudaADFun:
+    """``device``: one CUDA ordinal; ``devices``: several (one process drives them all)."""
+    return G3CudaADFun(model, parameters, device, devices)

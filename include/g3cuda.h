@@ -84,6 +84,21 @@ int g3cuda_eval_batch_device(g3cuda_model* m, const double* d_par, int64_t B,
                              double* d_nll, double* d_nll_comp, double* d_grad,
                              void* stream);
 
+/* One handle over several devices of the box: the spec and observation data are copied to every device in `devices`
+ * (CUDA ordinals; one may appear twice), and g3cuda_multi_eval_batch() cuts the B rows into contiguous blocks, one per
+ * device, evaluated concurrently (one host thread and one stream set per device); results land in the caller's buffers.
+ * The path has no exchange step, so no device talks to another. Same arguments, same error conventions as the
+ * single-device calls. This is how ONE R session drives all 8 GPUs: obj <- g3_cuda_adfun(model, devices = 0:7);
+ * obj$fn_batch(P). */
+typedef struct g3cuda_multi g3cuda_multi;
+int g3cuda_multi_create(const g3cuda_spec* spec, const int32_t* devices, int32_t n_devices, g3cuda_multi** out);
+void g3cuda_multi_free(g3cuda_multi* mm);
+int32_t g3cuda_multi_n_devices(const g3cuda_multi* mm);
+g3cuda_model* g3cuda_multi_model(g3cuda_multi* mm, int32_t i);     /* the i-th device's handle (dimensions, report, tuning hooks) */
+int g3cuda_multi_eval_batch(g3cuda_multi* mm, const double* par, int64_t B,
+                            const int32_t* tangent_idx, int32_t K,
+                            double* nll, double* nll_comp, double* grad);
+
 /* Kernel selection, for tests and profiling: 0 = automatic (default), 3 = thread-per-evaluation kernel,
  * 4 = tile kernel (G3CUDA_EUNSUPP if the model does not fit the requested one; other values: G3CUDA_EINVAL).
  * Automatic: value batches of any size run on the tile kernel (one CTA owns 32 evaluations for the whole time

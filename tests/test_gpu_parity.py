@@ -364,3 +364,29 @@ def test_profile_sweep_c5(setups):
     assert (np.abs(nll[pick] - o) <= tol).all()
     alone = fn.handle.eval_batch(full[pick])[0]
     assert (alone == nll[pick]).all()
+
+
+def test_multi_device_handle(setups):
+    """One handle over several devices (g3cuda_multi_*): the rows of a batch are cut into one
+    contiguous block per device and evaluated concurrently, results land in the caller's buffers. With one GPU visible
+    the same device is listed twice (two handles, two host threads); with more, every device takes part. Values,
+    components and gradients must equal the single-device call to the bit (same kernels, same tiles of 32 rows or not:
+    a vector's result does not depend on its neighbours)."""
+    import torch
+    model, p, fn, orc = setups["C1"]
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    multi = g3_cuda_adfun(model, p, devices=devices)
+    assert multi.multi is not None and len(multi.multi.handles) == len(devices)
+    P = parameter_batch(p, 1003, seed=31)             # uneven split
+    nll1, comp1 = fn.nll_components_batch(P)
+    nllm, compm = multi.nll_components_batch(P)
+    assert (nllm == nll1).all() and (compm == comp1).all()
+    g1 = fn.gr_batch(P[:65])
+    gm = multi.gr_batch(P[:65])
+    assert (gm[0] == g1[0]).all() and (gm[1] == g1[1]).all()
+    assert multi.fn(P[3]) == fn.fn(P[3])
+    # an error on any device is the call's error
+    bad = fn.full_par(P[:10])[:, :-1]
+    with pytest.raises(ValueError):
+        multi.multi.eval_batch(bad)
