@@ -265,4 +265,10 @@ def g3l_bounds_penalty(actions_or_parameter_template=None, weight=1, scale=1e6):
     """R/likelihood_bounds.R:2-65, "fromactions" form: one penalty per parameter with finite
     lower & upper bound; the bounds are bound at g3_cuda_adfun() time like the __lower/__upper
     DATA_SCALARs (R/run_tmb.R:1234-1235)."""
+    from .formula import ParameterTemplate
+    if isinstance(actions_or_parameter_template, ParameterTemplate):
+        # the parameter_template form penalises only optimise = TRUE rows and bakes today's bounds into the action
+        # (R/likelihood_bounds.R:44-62): a different nll from the one this backend would compute
+        raise G3Unsupported("g3l_bounds_penalty(parameter_template): only the actions form is supported "
+                            "(bounds are bound at g3_cuda_adfun() time)")
     return BoundsPenaltyAction(weight, scale)

@@ -390,3 +390,14 @@ def test_multi_device_handle(setups):
     bad = fn.full_par(P[:10])[:, :-1]
     with pytest.raises(ValueError):
         multi.multi.eval_batch(bad)
+
+
+def test_projection_years_are_refused_not_nan(setups):
+    """project_years >= 1 would need tables beyond the model's years: G3CUDA_EUNSUPP, not a NaN that looks like a value."""
+    from gadget3_b200._lib import G3CudaError
+    model, p, fn, orc = setups["C1"]
+    full = fn.full_par(parameter_batch(p, 4, seed=1))
+    full[2, p.index("project_years")] = 1
+    with pytest.raises(G3CudaError, match="project_years"):
+        fn.handle.eval_batch(full)
+    assert np.isfinite(fn.handle.eval_batch(full[:2])[0]).all()

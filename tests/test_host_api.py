@@ -181,3 +181,14 @@ def test_malformed_spec_is_rejected():
     h = C.c_void_p()
     assert lib.g3cuda_model_create(C.byref(bad), 0, C.byref(h)) < 0
     assert lib.g3cuda_last_error()
+
+
+def test_bounds_penalty_parameter_template_form_refused():
+    """R/likelihood_bounds.R:44-62: the parameter_template form penalises optimise = TRUE rows with the bounds of the moment
+    baked in -- not what this backend computes, so it refuses instead of silently returning a different nll."""
+    from gadget3_b200 import g3l_bounds_penalty
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.formula import G3Unsupported
+    _, p = CONFIGS["C1"]()
+    with pytest.raises(G3Unsupported):
+        g3l_bounds_penalty(p)
