@@ -146,9 +146,11 @@ def build_c1(seed=123, data=None, likelihood="sumofsquares"):
     return model, p
 
 
-def build_c2(seed=123, data=None, mat_age=False):
+def build_c2(seed=123, data=None, mat_age=False, stratified=False):
     """multiple-substocks (vignettes/multiple-substocks.Rmd:59-439). `data`: as build_c1, plus matp.
-    `mat_age`: g3a_mature_continuous with its age term, beta * cur_step_size and a50 (R/action_mature.R:18,44-74)."""
+    `mat_age`: g3a_mature_continuous with its age term, beta * cur_step_size and a50 (R/action_mature.R:18,44-74).
+    `stratified`: the maturity data scored as proportions WITHIN each length group, g3l_distribution_sumofsquares(over =
+    c('area', 'length')) (R/likelihood_distribution.R:8-16) -- proportion mature at length."""
     rng = np.random.default_rng(seed)
     years = list(range(1990, 2024))
     area_names = g3_areas(["IXa", "IXb"])
@@ -186,7 +188,8 @@ def build_c2(seed=123, data=None, mat_age=False):
                               function_f=g3l_distribution_sumofsquares(), area_group=area_names,
                               report=True, nll_breakdown=True),
         g3l_catchdistribution("matp_f_surv", d["matp"], fleets=[f_surv], stocks=stocks,
-                              function_f=g3l_distribution_sumofsquares(), area_group=area_names,
+                              function_f=(g3l_distribution_sumofsquares(over=("area", "length")) if stratified
+                                          else g3l_distribution_sumofsquares()), area_group=area_names,
                               report=True, nll_breakdown=True),
         g3l_abundancedistribution("dist_si_cpue", d["si"], stocks=stocks,
                                   function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
@@ -706,5 +709,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
            "LING": build_ling}

@@ -84,7 +84,8 @@ struct CompRec {
     int func, weight_par, xbuf, mode, n_dest, n_bins, n_slices, n_areag;
     int csr_ptr_ioff, csr_idx_ioff, csr_coef_roff, cell_dest_ioff, cell_coef_roff, tidx_ioff, cmp_ioff;
     int n_times, param_roff, g_ms, obs_off, obsconst_off;
-    int n_groups, group_len;    // dests whose total the comparison needs: sumofsquares n_areag slabs, multinomial every slice
+    int n_groups, grp_off;      // dests that share a total (sumofsquares: the area group's slab, or -- stratified -- a length
+                                // group across the slices; multinomial: every slice); tb: [n_dest] group of each dest
     int g_pt, g_pv;             // [n_groups][SHW] the warps' shares of the group totals; [SHW] of the component's value
     int g_cpart;                // partial sums of the split dests
     int task_off;               // tb: [W + 2] offsets into tb, then each warp's tasks (dest, first term, end term, slot, group)
@@ -967,12 +968,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         // R/likelihood_distribution.R:3-39 (sum of squared differences of proportions) and :41-60
                         const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
                         const double eps = R[Cm.param_roff];
-                        const int glen = Cm.group_len;
-                        int g = -1, gend = 0;       // group of dest e: [gend - glen, gend)
+                        int gcur = -1;
                         T rt(0.0);
                         for (int e = e0; e < nd; e += W) {
-                            if (e >= gend) {        // total of the group: the warps' shares, in warp order
-                                while (e >= gend) { g++; gend += glen; }
+                            const int g = tb[Cm.grp_off + e];
+                            if (g != gcur) {        // total of the group: the warps' shares, in warp order
+                                gcur = g;
                                 T tot(0.0);
                                 for (int w = 0; w < W; w++) tot = tot + G(Cm.g_pt + g * SHW + w);
                                 rt = 1.0 / avoid_zero(tot);

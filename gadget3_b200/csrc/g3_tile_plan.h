@@ -527,9 +527,23 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         const bool si = r.func == G3F_SI_LOG || r.func == G3F_SI_LINEAR;
         r.g_ms = takeg(r.n_dest * (si ? r.n_times : 1));
         // groups of dests whose total the comparison divides by
-        r.n_groups = 0; r.group_len = 1;
-        if (r.func == G3F_SUMOFSQUARES) { r.n_groups = r.n_areag; r.group_len = r.n_slices * r.n_bins; }
-        if (r.func == G3F_MULTINOMIAL) { r.n_groups = r.n_areag * r.n_slices; r.group_len = r.n_bins; }
+        // groups of dests that share a total: sumofsquares the area group's whole slab, or -- stratified -- one length group
+        // across the slices; multinomial every slice
+        const bool strat = r.func == G3F_SUMOFSQUARES && R[r.param_roff] != 0.0;
+        std::vector<int> grp(r.n_dest, 0);
+        r.n_groups = 0;
+        if (strat) {
+            r.n_groups = r.n_areag * r.n_bins;
+            for (int e = 0; e < r.n_dest; e++) grp[e] = (e / (r.n_slices * r.n_bins)) * r.n_bins + e % r.n_bins;
+        } else if (r.func == G3F_SUMOFSQUARES) {
+            r.n_groups = r.n_areag;
+            for (int e = 0; e < r.n_dest; e++) grp[e] = e / (r.n_slices * r.n_bins);
+        } else if (r.func == G3F_MULTINOMIAL) {
+            r.n_groups = r.n_areag * r.n_slices;
+            for (int e = 0; e < r.n_dest; e++) grp[e] = e / r.n_bins;
+        }
+        r.grp_off = (int)P.tb.size();
+        for (int v : grp) P.tb.push_back(v);
         r.g_pt = takeg(r.n_groups * SHW); r.g_pv = takeg(SHW);
         // collect terms per dest, cut into tasks
         {
@@ -546,13 +560,13 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
             for (int e = 0; e < r.n_dest; e++) {
                 const int j0 = (int)P.cterm_idx.size();
                 for (auto& tc : rows[e]) { P.cterm_idx.push_back(tc.first); P.cterm_coef.push_back(tc.second); }
-                const int n = (int)rows[e].size(), grp = e / r.group_len;
-                if (n <= TASK_TERMS) { tasks.insert(tasks.end(), {e, j0, j0 + n, -1, grp}); continue; }
+                const int n = (int)rows[e].size(), ge = grp[e];
+                if (n <= TASK_TERMS) { tasks.insert(tasks.end(), {e, j0, j0 + n, -1, ge}); continue; }
                 const int parts = (n + TASK_TERMS - 1) / TASK_TERMS;
                 split.insert(split.end(), {e, nslot, parts}); nsplit++;
                 for (int k = 0; k < parts; k++) {
                     const int a = j0 + (int)((long long)n * k / parts), b = j0 + (int)((long long)n * (k + 1) / parts);
-                    tasks.insert(tasks.end(), {e, a, b, k == 0 ? -2 - nslot : nslot, grp});
+                    tasks.insert(tasks.end(), {e, a, b, k == 0 ? -2 - nslot : nslot, ge});
                     nslot++;
                 }
             }
@@ -570,9 +584,11 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
             for (int ag = 0; ag < nag; ag++) {
                 double tot = 0.0;
                 for (int i = 0; i < nsl * nb; i++) tot += obs[(size_t)t * nd + ag * nsl * nb + i];
-                const double az = plan_avoid_zero(tot);
+                std::vector<double> btot(nb, 0.0);          // stratified: totals per length group
+                for (int i = 0; i < nsl * nb; i++) btot[i % nb] += obs[(size_t)t * nd + ag * nsl * nb + i];
                 for (int i = 0; i < nsl * nb; i++) {
                     const double o = obs[(size_t)t * nd + ag * nsl * nb + i];
+                    const double az = plan_avoid_zero(strat ? btot[i % nb] : tot);
                     double v = o;
                     if (r.func == G3F_SUMOFSQUARES) v = o / az;                          // R/likelihood_distribution.R:12-27
                     else if (r.func == G3F_SI_LOG) v = std::log(plan_avoid_zero(o));     // R/likelihood_distribution.R:86

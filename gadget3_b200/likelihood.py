@@ -18,12 +18,12 @@ class _DistFn:
 
 
 def g3l_distribution_sumofsquares(over=("area", "predator", "predator_tag", "predator_age", "predator_length")):
-    """R/likelihood_distribution.R:31-39 (stratified form, 'length' in over, is not supported)."""
-    if "length" in over:
-        raise G3Unsupported("g3l_distribution_sumofsquares(over = 'length')")
+    """R/likelihood_distribution.R:3-39. With 'length' in ``over`` the sum of squares is STRATIFIED: proportions are taken
+    within each length group (total = avoid_zero(rowSums(...)) over the other dimensions, dist_prop() :8-16) -- the
+    usual form for maturity-at-length data."""
     if "area" not in over:
         raise G3Unsupported("g3l_distribution_sumofsquares: 'area' must be in over")
-    return _DistFn("sumofsquares")
+    return _DistFn("sumofsquares", stratified="length" in over)
 
 
 def g3l_distribution_multinomial(epsilon=10):

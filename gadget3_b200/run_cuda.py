@@ -523,8 +523,8 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                                                     float("nan") if be is None else float(be)])
         elif fn.name in ("multinomial", "sumofsquaredlogratios"):
             q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([fn.kw["epsilon"], 0.0])
-        else:
-            q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([0.0, 0.0])
+        else:       # sumofsquares: PARAM[0] = 1 for the stratified form (proportions within each length group)
+            q[K["G3C_PARAM_ROFF"]] = b.alloc_reals([1.0 if fn.kw.get("stratified") else 0.0, 0.0])
         if key not in xbuf_index:
             xbuf_index[key] = len(xbufs)
             xbufs.append(dict(kind=0 if key[0] == "catch" else 1, unit=0 if ld.unit == "num" else 1,

@@ -170,7 +170,8 @@
 #define G3C_CMP_OFF       14   /* ints[NT]: done_aggregating_f at step t (R/likelihood_data.R:219) */
 #define G3C_N_TIMES       15
 #define G3C_OBS_ROFF      16   /* reals[N_TIMES*N_DEST] observations, canonical dest layout */
-#define G3C_PARAM_ROFF    17   /* reals[2]: surveyindices fixed alpha, beta (NaN = estimate); multinomial, sumofsquaredlogratios: epsilon */
+#define G3C_PARAM_ROFF    17   /* reals[2]: surveyindices fixed alpha, beta (NaN = estimate); multinomial, sumofsquaredlogratios: epsilon;
+                                  sumofsquares: [0] != 0 = stratified (proportions within each length group, over = 'length') */
 #define G3C_NAREA_SEL_OFF 18   /* reserved */
 #define G3C_LEN           19
 

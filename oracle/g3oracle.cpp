@@ -743,7 +743,20 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             const double* obs = S.R + C[G3C_OBS_ROFF] + (size_t)ti * nd;
             int nb = C[G3C_N_BINS], nsl = C[G3C_N_SLICES], nag = C[G3C_N_AREAG];
             T cnll(0.0);
-            if (C[G3C_FUNC] == G3F_SUMOFSQUARES) {          // R/likelihood_distribution.R:3-39
+            if (C[G3C_FUNC] == G3F_SUMOFSQUARES && S.R[C[G3C_PARAM_ROFF]] != 0.0) {
+                // stratified (over includes 'length'): x / avoid_zero(rowSums(x))[length], R/likelihood_distribution.R:8-16
+                for (int ag = 0; ag < nag; ag++)
+                    for (int b = 0; b < nb; b++) {
+                        T tm(0.0); double to = 0.0;
+                        for (int sl = 0; sl < nsl; sl++) { tm = tm + m[(ag * nsl + sl) * nb + b]; to += obs[(ag * nsl + sl) * nb + b]; }
+                        T atm = avoid_zero(tm); double ato = avoid_zero(to);
+                        for (int sl = 0; sl < nsl; sl++) {
+                            int e = (ag * nsl + sl) * nb + b;
+                            T dlt = m[e] / atm - obs[e] / ato;
+                            cnll = cnll + dlt * dlt;
+                        }
+                    }
+            } else if (C[G3C_FUNC] == G3F_SUMOFSQUARES) {   // R/likelihood_distribution.R:3-39
                 for (int ag = 0; ag < nag; ag++) {
                     T tm(0.0); double to = 0.0;
                     for (int i = 0; i < nsl * nb; i++) { tm = tm + m[ag * nsl * nb + i]; to += obs[ag * nsl * nb + i]; }

@@ -19,7 +19,7 @@ GRAD_RTOL = 1e-8
 @pytest.fixture(scope="module")
 def setups(oracle_lib):
     out = {}
-    for n in ("C1", "C1_MULTI", "C2", "C2_MATAGE", "C4", "C5"):
+    for n in ("C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5"):
         model, p = CONFIGS[n]()
         fn = g3_cuda_adfun(model, p, device=0)
         out[n] = (model, p, fn, Oracle(*model.pack(p)))
@@ -41,10 +41,11 @@ KERNELS = pytest.mark.parametrize("kernel", [4, 3], ids=["tile_kernel", "thread_
 
 
 @KERNELS
-@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C4", "C5"])
+@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5"])
 def test_nll_and_components(setups, name, kernel):
     """C1_MULTI: g3l_distribution_multinomial + g3l_distribution_surveyindices_linear (R/likelihood_distribution.R:41-60,
     82-125; the oracle's versions are re-derived independently in tests/test_oracle_likelihoods.py).
+    C2_STRAT: stratified sumofsquares, proportions within each length group (R/likelihood_distribution.R:8-16).
     C2_MATAGE: g3a_mature_continuous with its age term, beta * cur_step_size and a50 (R/action_mature.R:18,44-74; the
     oracle's share against a hand value in tests/test_oracle_kat.py)."""
     model, p, fn, orc = setups[name]
@@ -79,7 +80,7 @@ def _check_nll_and_components(model, p, fn, orc):
 
 
 @KERNELS
-@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C4", "C5"])
+@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5"])
 def test_gradients(setups, name, kernel):
     model, p, fn, orc = setups[name]
     if kernel == 3 and not fn.handle.tile_info()["thread_ok"]:

@@ -89,3 +89,29 @@ def test_surveyindices_linear_regression_rederived(c1m):
                 for n in model.comp_names)
     total += 1e8 * np.asarray(rep["nll_understocking__wgt"]).sum()
     assert rep["nll"] == pytest.approx(total, rel=1e-9)
+
+
+def test_stratified_sumofsquares_rederived_from_the_reported_model_array(oracle_lib):
+    """g3l_distribution_sumofsquares(over = c('area', 'length')), R/likelihood_distribution.R:8-16: proportions within each
+    length group, x / avoid_zero(rowSums(x))[length], for the model and the observations alike (here: proportion mature at
+    length, two stock slices). Re-derived from the oracle's REPORTed model array; and it must differ from the plain form."""
+    model, p = CONFIGS["C2_STRAT"]()
+    ints, reals = model.pack(p)
+    rep = unpack_report(model, Oracle(ints, reals).report(p.values()))
+    name = [n for n in model.comp_names if "matp" in n][0]
+    c = model.comp_names.index(name)
+    obs, tidx, nb = _comp(ints, reals, c)
+    marr = np.asarray(rep[name + "_model__num"], dtype=float)
+    marr = marr.reshape(marr.shape[0], -1, nb)                      # [time][slice][length bin]
+    per_step = np.asarray(rep["nll_" + name + "__num"], dtype=float)
+    checked = 0
+    for t, ti in enumerate(tidx):
+        if ti < 0:
+            continue
+        m, o = marr[ti], obs[ti].reshape(-1, nb)
+        want = ((m / _avoid_zero(m.sum(axis=0)) - o / _avoid_zero(o.sum(axis=0))) ** 2).sum()
+        plain = ((m / _avoid_zero(m.sum()) - o / _avoid_zero(o.sum())) ** 2).sum()
+        assert per_step[t] == pytest.approx(want, rel=1e-11), t
+        assert abs(want - plain) > 1e-3 * abs(want)
+        checked += 1
+    assert checked == 34
