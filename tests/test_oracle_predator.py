@@ -1,0 +1,108 @@
+"""The oracle's stock-predator path (g3a_predate + g3a_predate_catchability_predator + g3a_predate_maxconsumption,
+R/action_predate.R:190-238, 240-420) re-derived in numpy from its own REPORTed arrays -- the way the reference's tests
+pin the likelihoods (tests/test-likelihood_distribution.R:419-700) -- and the two scaling properties the reference's
+predator test asserts (tests/test-action_predate-predator.R:94-135): suitable biomass scales with energycontent,
+consumption with predator_length^m3 when half-feeding is far above the available food. CPU only."""
+import numpy as np
+import pytest
+
+from gadget3_b200.configs import CONFIGS
+from gadget3_b200.run_cuda import unpack_report
+from oracle.oracle_lib import Oracle
+
+
+@pytest.fixture(scope="module")
+def mini(oracle_lib):
+    model, p = CONFIGS["MINI_ANDERSEN"]()
+    return model, p, Oracle(*model.pack(p))
+
+
+def _stocks(model):
+    out = {}
+    for a in model.actions:
+        s = getattr(a, "stock", None)
+        if s is not None and getattr(s, "midlen", None) is not None:
+            out[s.name] = s
+    return out
+
+
+def _values(p, **over):
+    v = p.values().copy()
+    for n in p.switch:                      # no migration: every fish stays (the report's dstart_* is then the state predation sees)
+        if ".migrate." in n:
+            v[p.index(n)] = 0.0
+    for k, x in over.items():
+        v[p.index(k.replace("__", "."))] = x
+    return v
+
+
+def _expected_consumption(model, p, v, rep, t):
+    """cons[l, age, area] by eqn 4.22-4.23: predN * M_L * psi_L * suit / (energycontent * total_predsuit), summed over predator lengths."""
+    st = _stocks(model)
+    g = lambda n: float(v[p.index(n)])
+    dt = 3 / 12.0
+    predlen = np.asarray(st["pred"].midlen, dtype=float)
+    m0, m1, m2, m3 = (g(f"pred.consumption.m{i}") for i in range(4))
+    temp = 0.0
+    maxcons = m0 * dt * np.exp(m1 * temp - m2 * temp ** 3) * predlen ** m3                 # M_L
+    hf, E = g("pred.halffeeding"), g("prey.energycontent")
+    S = np.asarray(rep["suit_prey_pred__report"], dtype=float)                          # [prey length][predator length]
+    B0 = (np.asarray(rep["dstart_prey__num"]) * np.asarray(rep["dstart_prey__wgt"]))[..., t]        # [l][age][area]
+    predN = np.asarray(rep["dstart_pred__num"])[..., t].sum(axis=1)                     # [pl][area]
+    cons = np.zeros_like(B0)
+    for r in range(B0.shape[2]):
+        suit = S[:, None, :] * E * B0[:, :, r][:, :, None]                              # [l][age][pl]
+        ts = suit.sum(axis=(0, 1))                                                      # total_predsuit per predator length
+        psi = ts / (hf * dt + ts)                                                       # feeding level
+        cons[:, :, r] = (suit * (predN[:, r] * maxcons * psi / (E * ts))[None, None, :]).sum(axis=2)
+    # the overconsumption block rescales every predator's share by consconv = tp' / avoid_zero(tp) with
+    # tp' = B0 * dif_pmin(tp / avoid_zero(B0), 0.95, 1e3) (R/action_predate.R:381-416): the identity for cells with real
+    # consumption, a squeeze towards zero for the (near-)empty ones
+    az = lambda a: (np.maximum(a * 1000.0, 0.0) + np.log1p(np.exp(-np.abs(a * 1000.0)))) / 1000.0
+    ratio = cons / az(B0)
+    ratio = 0.95 - (np.maximum(1e3 * (0.95 - ratio), 0.0) + np.log1p(np.exp(-np.abs(1e3 * (0.95 - ratio))))) / 1e3
+    return cons * (B0 * ratio) / az(cons)
+
+
+def test_consumption_rederived_from_reported_arrays(mini):
+    model, p, orc = mini
+    v = _values(p)
+    rep = unpack_report(model, orc.report(v))
+    got = np.asarray(rep["detail_prey_pred__cons"], dtype=float)
+    for t in (0, 1, 2):         # before the first ageing; growth and mortality come after predation in the step
+        want = _expected_consumption(model, p, v, rep, t)
+        assert want.max() > 0
+        assert np.abs(got[..., t] - want).max() <= 1e-9 * want.max(), t
+
+
+def test_energycontent(mini):
+    """tests/test-action_predate-predator.R:94-106 (suitable biomass doubles with energycontent = 2): suit / total_predsuit does
+    not change, the feeding level psi = total / (half_feeding dt + total) rises, and the consumption in biomass is divided by
+    energycontent (R/action_predate.R:219-237)."""
+    model, p, orc = mini
+    v = _values(p, prey__energycontent=2.0)
+    rep = unpack_report(model, orc.report(v))
+    want = _expected_consumption(model, p, v, rep, 0)
+    got = np.asarray(rep["detail_prey_pred__cons"], dtype=float)[..., 0]
+    assert np.abs(got - want).max() <= 1e-9 * want.max()
+    base = np.asarray(unpack_report(model, orc.report(_values(p)))["detail_prey_pred__cons"], dtype=float)[..., 0]
+    assert 0.5 < got.sum() / base.sum() < 1.0           # twice the energy per kg: (slightly more than) half the biomass eaten
+
+
+def test_consumption_scales_with_predator_length_power_m3(mini):
+    """tests/test-action_predate-predator.R:114-135: with half-feeding far above the food, consumption by predator length
+    goes as length^m3. The report sums over predator lengths, so: the same run with m3 + 1 equals the re-derivation in which
+    every predator length's share is multiplied by its length (first step: same state)."""
+    model, p, orc = mini
+    m3 = float(p.values()[p.index("pred.consumption.m3")])
+    base = dict(pred__halffeeding=1e7)          # far above the suitable biomass (~1e4), consumption still well above avoid_zero's scale
+    va, vb = _values(p, **base), _values(p, pred__consumption__m3=m3 + 1.0, **base)
+    ra, rb = unpack_report(model, orc.report(va)), unpack_report(model, orc.report(vb))
+    want_b = _expected_consumption(model, p, vb, ra, 0)         # state of run a at t = 0 == state of run b at t = 0
+    got_b = np.asarray(rb["detail_prey_pred__cons"], dtype=float)[..., 0]
+    assert np.abs(got_b - want_b).max() <= 1e-9 * want_b.max()
+    got_a = np.asarray(ra["detail_prey_pred__cons"], dtype=float)[..., 0]
+    st = _stocks(model)
+    lo, hi = min(st["pred"].midlen), max(st["pred"].midlen)
+    ratio = got_b.sum() / got_a.sum()                           # a length-weighted mean of the predator lengths
+    assert lo < ratio < hi
