@@ -44,6 +44,7 @@ struct StockRec {
     int grow_n, mat_kind, has_out, trans_mask, inc_steps;
     int mort_ioff, midlen_roff, plusdl_roff, grow_ioff, mat_ioff, init_ioff;
     int n_renew, renew_ioff;
+    int ren_off;            // tb: per renewal (run step or 0 = every step, age index it lands in, offset in I of its factor slots per year x area)
     int g_mort;             // [idt][col] exp(-M dt)
     int g_rd, g_rw;         // [k][l] renewal numbers shape (x 1e4) and weight
     int g_wq;               // [l] walpha * midlen^wbeta; NW - 1 zero rows before row 0, NBX - 1 after row L - 1
@@ -94,11 +95,14 @@ struct CompRec {
 struct XRec { int kind, unit, g_x; };
 
 struct TArgs {
-    const int32_t* I; const double* R; const int32_t* tb;
-    const StockRec* st; const ColRec* col; const UnitRec* unit; const PairRec* pp; const PredRec* pred; const TsRec* ts;
-    const CompRec* comp; const XRec* xb; const int4* agedst;
-    const double* obsprop; const double* obsconst; const unsigned char* pred_active;
-    const int32_t* cterm_idx; const double* cterm_coef;     // collect terms of all components: cell, lgmatrix coefficient
+    const int32_t* I; const double* R;
+    // every record table and index list of the plan in ONE block of ints (m_* = offsets of its sections), copied to shared
+    // memory when the kernel starts if it fits beside the state: the per-step control code of every warp walks these tables,
+    // and from global memory every hop is an L2 round trip (the bands and collect vectors stream through L1)
+    const int32_t* meta; int meta_n, meta_in_smem, n_s;
+    int m_st, m_col, m_unit, m_pp, m_pred, m_ts, m_comp, m_xb, m_agedst, m_tb, m_cidx, m_ccoef;
+    int tmask_off;          // tb: [3][NT] per step: components whose time index is set (bit c), that compare (bit c), predation on
+    const double* obsprop; const double* obsconst;
     const double* par; long long B; const int32_t* tangent_idx; int K;
     double* nll; double* comp_out; double* grad;
     double* gws; long long slab_doubles; int lanes_per_tile;
@@ -130,7 +134,11 @@ __device__ __forceinline__ int g3t_grab(int* ctr) {
     return __shfl_sync(0xffffffffu, v, 0);
 }
 #define G3T_GRAB(p) g3t_grab(p)
+#define G3T_TID(warp, lane) ((warp) * 32 + (lane))
+#define G3T_NTHREADS(warps) ((warps) * 32)
 #else
+#define G3T_TID(warp, lane) (warp)              /* one emulated lane at a time: its warps share the copy */
+#define G3T_NTHREADS(warps) (warps)
 #define G3T_GRAB(p) __atomic_fetch_add((p), 1, __ATOMIC_SEQ_CST)
 struct EmuCtx { void (*bar)(void*); void* arg; };
 #define G3T_BAR() ctx.bar(ctx.arg)
@@ -139,6 +147,17 @@ struct EmuCtx { void (*bar)(void*); void* arg; };
 #define G3T_CTX_ARG , ctx
 #endif
 
+#if defined(__CUDACC__) && defined(G3T_PHASE_CLOCKS)
+// profiling build only (tools/gpu_phase_clocks.py): cycles between phase boundaries as warp 0 sees them, summed per phase
+__device__ unsigned long long g3t_phase_cycles[16];
+#define G3T_PH_DECL long long ph_t0 = clock64(); unsigned long long ph_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define G3T_PH(k) { const long long ph_now = clock64(); ph_acc[k] += (unsigned long long)(ph_now - ph_t0); ph_t0 = ph_now; }
+#define G3T_PH_FLUSH() if (warp == 0 && lane == 0) { for (int k = 0; k < 12; k++) atomicAdd(&g3t_phase_cycles[k], ph_acc[k]); }
+#else
+#define G3T_PH_DECL
+#define G3T_PH(k)
+#define G3T_PH_FLUSH()
+#endif
 // element access in the [entry][component][lane] layout (component 0 = value, 1.. = tangents)
 __device__ __forceinline__ void ldv(const double* p, double& r) { r = *p; }
 __device__ __forceinline__ void stv(double* p, const double& v) { *p = v; }
@@ -226,13 +245,28 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
     constexpr unsigned C = (unsigned)(NTAN + 1) * NL;       // doubles per entry
     const int32_t* __restrict__ I = A.I;
     const double* __restrict__ R = A.R;
-    const int32_t* __restrict__ tb = A.tb;
     // A.W unit warps plus one KEEPER warp (the last): it owns no unit; it keeps the objective (nll, component sums,
     // understocking) in the reference's summation order while the unit warps are already on the next step
     const int W = A.W + 1;
     const bool keeper = warp == A.W;
     double* const gl = A.gws + (size_t)cta * (size_t)A.slab_doubles + lane;
     double* const sm = SMEM ? smem + lane : gl + (size_t)A.n_g * C;
+    const int32_t* M = A.meta;
+    if (A.meta_in_smem) {       // the plan's tables, once per CTA
+        int32_t* const ms = reinterpret_cast<int32_t*>(smem + (SMEM ? (size_t)A.n_s * C : 0));
+        for (int i = G3T_TID(warp, lane); i < A.meta_n; i += G3T_NTHREADS(A.W + 1)) ms[i] = A.meta[i];
+        G3T_BAR();
+        M = ms;
+    }
+    const StockRec* const Tst = reinterpret_cast<const StockRec*>(M + A.m_st);
+    const ColRec* const Tcol = reinterpret_cast<const ColRec*>(M + A.m_col);
+    const UnitRec* const Tunit = reinterpret_cast<const UnitRec*>(M + A.m_unit);
+    const PairRec* const Tpp = reinterpret_cast<const PairRec*>(M + A.m_pp);
+    const PredRec* const Tpred = reinterpret_cast<const PredRec*>(M + A.m_pred);
+    const TsRec* const Tts = reinterpret_cast<const TsRec*>(M + A.m_ts);
+    const CompRec* const Tcomp = reinterpret_cast<const CompRec*>(M + A.m_comp);
+    const XRec* const Txb = reinterpret_cast<const XRec*>(M + A.m_xb);
+    const int4* const Tagedst = reinterpret_cast<const int4*>(M + A.m_agedst);
 #define GP(e) (gl + (unsigned)(e) * C)
 #define SP(e) (sm + (unsigned)(e) * C)
     auto G = [&](int e) { T r; ldv(GP(e), r); return r; };
@@ -241,6 +275,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
     auto SS = [&](int e, const T& v) { stv(SP(e), v); };
 #define SLOT(i) G(A.g_slot + (i))
 
+    const int32_t* __restrict__ tb = M + A.m_tb;
     const int NS = A.NS, NSTEPS = A.NSTEPS, NT = A.NT;
     const int ntan_tiles = NTAN > 0 ? (A.K + NTAN - 1) / NTAN : 1;
     const long long total = A.B * ntan_tiles;
@@ -255,6 +290,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
     const int NU = A.NU;
 #define G3T_UNITS(q, k) for (int k = keeper ? NU : G3T_GRAB(ctr + (q)); k < NU; k = G3T_GRAB(ctr + (q)))
 
+    G3T_PH_DECL
     for (long long tile = cta; tile < ntile; tile += ncta) {
         const long long work0 = tile * LPT + lane;
         const bool live = lane < LPT && work0 < total;
@@ -291,8 +327,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
         auto mine = [&]() { const bool m = ucnt == warp; ucnt = ucnt + 1 == W ? 0 : ucnt + 1; return m; };
 
         for (int q = 0; q < A.NPP; q++) {           // suitability (R/suitability.R:5-94): [predator length][prey length]
-            const PairRec& Q = A.pp[q];
-            const StockRec& Ps = A.st[Q.prey];
+            const PairRec& Q = Tpp[q];
+            const StockRec& Ps = Tst[Q.prey];
             const bool spred = Q.pred_kind == G3PRED_STOCK;
             const double* pml = R + Ps.midlen_roff;
             for (int pl = 0; pl < Q.PL; pl++) {
@@ -301,16 +337,16 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 T sp[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
-                const double plen = spred && Q.suit_kind != G3SUIT_ANDERSENFLEET ? R[A.st[Q.pred_stock].midlen_roff + pl] : pml[Ps.L - 1];
+                const double plen = spred && Q.suit_kind != G3SUIT_ANDERSENFLEET ? R[Tst[Q.pred_stock].midlen_roff + pl] : pml[Ps.L - 1];
                 for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, suitability_of<T>(Q.suit_kind, sp, pml[l], plen));
             }
         }
         // stock predators: maximum consumption per predator length without the step length,
         // m0 exp(m1 T - m2 T^3) l^m3 (R/action_predate.R:190-205)
         for (int pi = 0; pi < A.NPRED; pi++) {
-            const PredRec& P = A.pred[pi];
+            const PredRec& P = Tpred[pi];
             if (P.kind != G3PRED_STOCK) continue;
-            const StockRec& Pp = A.st[P.stock];
+            const StockRec& Pp = Tst[P.stock];
             for (int pl = 0; pl < Pp.L; pl++) {
                 if (!mine()) continue;
                 const int32_t* ps = I + P.slot_ioff;
@@ -320,7 +356,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             }
         }
         for (int s = 0; s < NS; s++) {
-            const StockRec& St = A.st[s];
+            const StockRec& St = Tst[s];
             const int L = St.L;
             const double* midlen = R + St.midlen_roff;
             // migration matrices per step of the year: proportion moving src -> dest (R/action_migrate.R:2-15,49-56)
@@ -419,8 +455,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
         }
         // ---- per column: mortality factors, initial conditions, maturation remainder, constant-maturity ratios
         for (int gc = warp; gc < A.NCOLS; gc += W) {
-            const ColRec& Cl = A.col[gc];
-            const StockRec& St = A.st[Cl.s];
+            const ColRec& Cl = Tcol[gc];
+            const StockRec& St = Tst[Cl.s];
             const int L = St.L, col = Cl.col;
             const double* midlen = R + St.midlen_roff;
             if (St.mort_ioff >= 0)      // natural mortality factor per distinct step length (R/action_naturalmortality.R:26)
@@ -467,7 +503,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             }
         }
         for (int c = 0; c < A.NCOMP; c++) {         // zero the likelihood slabs
-            const CompRec& Cm = A.comp[c];
+            const CompRec& Cm = Tcomp[c];
             const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
             const int n = Cm.n_dest * (si ? Cm.n_times : 1);
             for (int i = warp; i < n; i += W) GS(Cm.g_ms + i, T(0.0));
@@ -477,7 +513,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
         // which components this tile evaluates: <name>_weight > 0 on some lane (R/likelihood_distribution.R:352)
         unsigned cw_any = 0, cw_lane = 0;
         for (int c = 0; c < A.NCOMP; c++) {
-            const bool on = prow[A.comp[c].weight_par] > 0.0;
+            const bool on = prow[Tcomp[c].weight_par] > 0.0;
             if (on) cw_lane |= 1u << c;
             if (G3T_ANY(on)) cw_any |= 1u << c;
         }
@@ -493,6 +529,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             }
         }
 
+        G3T_PH(0)       // tile set-up: slots, tables, initial conditions
         for (int t = 0; t < NT; t++) {
             const bool lane_on = !bad_time && t <= total_steps;
             if (!G3T_ANY(lane_on)) break;       // (every warp holds the same 32 evaluations: the decision is block-uniform)
@@ -502,25 +539,25 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             const int idt = A.step_idt[step];
             const double dt = A.dt_len[idt] / 12.0;
             const bool final_step = step == NSTEPS - 1;
-            const bool pred_now = A.pred_active[t] != 0;
-            // components collecting at this step (bit c), their collect vectors (bit x), and whether any reads a catch
-            unsigned cact = 0, xact = 0;
-            bool any_catch = false;
-            for (int c = 0; c < A.NCOMP; c++) {
-                const CompRec& Cm = A.comp[c];
-                if (I[Cm.tidx_ioff + t] >= 0 && ((cw_any >> c) & 1)) {
-                    cact |= 1u << c;
-                    xact |= 1u << Cm.xbuf;
-                    if (A.xb[Cm.xbuf].kind == 0) any_catch = true;
+            const bool pred_now = tb[A.tmask_off + 2 * NT + t] != 0;
+            // components collecting at this step (bit c) and the CATCH collect vectors they read (bit x; abundance components read
+            // the state itself when they collect)
+            const unsigned cact = (unsigned)tb[A.tmask_off + t] & cw_any;
+            const unsigned cmp_now = (unsigned)tb[A.tmask_off + NT + t];      // components that compare at this step (bit c)
+            unsigned xact = 0;
+            for (int c = 0; c < A.NCOMP; c++)
+                if ((cact >> c) & 1) {
+                    const CompRec& Cm = Tcomp[c];
+                    if (Txb[Cm.xbuf].kind == 0) xact |= 1u << Cm.xbuf;
                 }
-            }
+            const bool any_catch = xact != 0;
 
             // ================= g3a_migrate (R/action_migrate.R:17-82): every (age, length) mixes its areas
             {
                 bool mig_any = false;
                 ucnt = 0;
                 for (int s = 0; s < NS; s++) {
-                    const StockRec& St = A.st[s];
+                    const StockRec& St = Tst[s];
                     if (!((St.mig_steps >> step) & 1)) continue;
                     mig_any = true;
                     const int L = St.L, nage = St.nage, NR = St.narea, c0 = St.c0;
@@ -547,18 +584,19 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     }
                 }
                 if (mig_any) G3T_BAR();
+                G3T_PH(1)
             }
 
             // ================= g3a_predate step 1: suitable biomass per (predator, area[, predator length]) (R/action_predate.R:314-333)
             if (pred_now) {
                 G3T_UNITS(qn - ctr + 0, uk) {              // partial sums per unit
-                    const UnitRec& U = A.unit[tb[A.uorder_off + uk]];
-                    const ColRec& Cl = A.col[U.gc];
-                    const StockRec& St = A.st[Cl.s];
+                    const UnitRec& U = Tunit[tb[A.uorder_off + uk]];
+                    const ColRec& Cl = Tcol[U.gc];
+                    const StockRec& St = Tst[Cl.s];
                     const int L = St.L, c_lo = Cl.cell0 + U.lo;
                     for (int j = 0; j < St.pp_n; j++) {
                         const int q = tb[St.pp_off + j];
-                        const PairRec& Q = A.pp[q];
+                        const PairRec& Q = Tpp[q];
                         if (Q.pred_kind == G3PRED_LINEARFLEET || Q.pred_kind == G3PRED_EFFORTFLEET) continue;     // no total needed
                         if (tb[Q.tsid_off + Cl.ridx] < 0) continue;
                         const bool spred = Q.pred_kind == G3PRED_STOCK;
@@ -574,10 +612,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     }
                 }
                 G3T_BAR();
+                G3T_PH(2)
                 ucnt = 0;
                 for (int k = 0; k < A.NTS; k++) {           // fleets: landings over total suitable biomass, cons = E * (suit / totalsuit)
                     if (!mine()) continue;
-                    const TsRec& Ts = A.ts[k];
+                    const TsRec& Ts = Tts[k];
                     const double E = R[Ts.eoff + (size_t)t * Ts.estr];
                     if (Ts.kind == G3PRED_LINEARFLEET || Ts.kind == G3PRED_EFFORTFLEET) {
                         GS(A.g_eot + k, T(E * dt));         // harvest rate x step length (R/action_predate.R:13-18,117-126)
@@ -590,9 +629,9 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 // stock predators: predN * max_consumption * feeding_level / total_predsuit per (area, predator length)
                 // (R/action_predate.R:207-238; energycontent cancels between suit and cons)
                 for (int pi = 0; pi < A.NPRED; pi++) {
-                    const PredRec& P = A.pred[pi];
+                    const PredRec& P = Tpred[pi];
                     if (P.kind != G3PRED_STOCK) continue;
-                    const StockRec& Pp = A.st[P.stock];
+                    const StockRec& Pp = Tst[P.stock];
                     const int PL = Pp.L, PA = Pp.nage;
                     for (int pr = 0; pr < Pp.narea; pr++) {
                         const int lo = tb[P.list_off + 2 * pr], ln = tb[P.list_off + 2 * pr + 1];
@@ -634,8 +673,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 // g3a_renewal (R/action_renewal.R:166-188)
                 if (ren_mask)
                     for (int r = 0; r < St.n_renew; r++)
-                        if (((ren_mask >> r) & 1) && Cl.aidx == I[St.renew_ioff + r * G3R_LEN + G3R_AGE_IDX]) {
-                            const int fs = I[I[St.renew_ioff + r * G3R_LEN + G3R_FACTOR_OFF] + yidx * St.narea + Cl.ridx];
+                        if (((ren_mask >> r) & 1) && Cl.aidx == tb[St.ren_off + 3 * r + 1]) {
+                            const int fs = I[tb[St.ren_off + 3 * r + 2] + yidx * St.narea + Cl.ridx];
                             if (fs < 0) continue;
                             const T factor = SLOT(fs);
                             T nu[NB], de[NB], rn[NB];
@@ -657,7 +696,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 // collect vectors for g3l_distribution (R/likelihood_distribution.R:275-287)
                 if (xact) {
                     bool any_cn = false;        // catch in numbers: cons / avoid_zero(wgt)
-                    for (int j = 0; j < St.cx_n; j++) { const int x = tb[St.cx_off + j]; any_cn = any_cn || (((xact >> x) & 1) && A.xb[x].unit == 0); }
+                    for (int j = 0; j < St.cx_n; j++) { const int x = tb[St.cx_off + j]; any_cn = any_cn || (((xact >> x) & 1) && Txb[x].unit == 0); }
                     if (any_cn) {
                         T iw[NB], de[NB];
 #pragma unroll
@@ -665,26 +704,18 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         div_az_n(iw, de);
                         for (int j = 0; j < St.cx_n; j++) {
                             const int x = tb[St.cx_off + j];
-                            if (!(((xact >> x) & 1) && A.xb[x].unit == 0)) continue;
-                            const int gx = A.xb[x].g_x + cell;
+                            if (!(((xact >> x) & 1) && Txb[x].unit == 0)) continue;
+                            const int gx = Txb[x].g_x + cell;
 #pragma unroll
                             for (int b = 0; b < NB; b++) if (b < nb) GS(gx + b, G(gx + b) * iw[b]);
                         }
-                    }
-                    for (int j = 0; j < A.ax_n; j++) {          // abundance
-                        const int x = tb[A.ax_off + j];
-                        if (!((xact >> x) & 1)) continue;
-                        const int gx = A.xb[x].g_x + cell;
-                        const bool by_num = A.xb[x].unit == 0;
-#pragma unroll
-                        for (int b = 0; b < NB; b++) if (b < nb) GS(gx + b, by_num ? num[b] : num[b] * wgt[b]);
                     }
                 }
             };
             auto renewals_now = [&](const StockRec& St) {
                 int ren_mask = 0;       // renewal records that run at this step
                 for (int k = 0; k < St.n_renew; k++) {
-                    const int rs = I[St.renew_ioff + k * G3R_LEN + G3R_RUN_STEP];
+                    const int rs = tb[St.ren_off + 3 * k];
                     if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
                 }
                 return ren_mask;
@@ -693,55 +724,54 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             // ================= own units, pass 1: g3a_predate (R/action_predate.R:335-406) in blocks of NB rows, ascending
             // (the order of the sums); then the unit's top rows go to the ghost rows of the unit above
             G3T_UNITS(qn - ctr + 1, uk) {
-                const UnitRec& U = A.unit[tb[A.uorder_off + uk]];
-                const ColRec& Cl = A.col[U.gc];
-                const StockRec& St = A.st[Cl.s];
+                const UnitRec& U = Tunit[tb[A.uorder_off + uk]];
+                const ColRec& Cl = Tcol[U.gc];
+                const StockRec& St = Tst[Cl.s];
                 const int L = St.L, nq = St.pp_n, c_lo = Cl.cell0 + U.lo;
                 const bool prey_now = pred_now && nq > 0;
                 const bool catch_now = any_catch && nq > 0;
                 double* const pNum = SP(A.s_num + c_lo);
                 double* const pWgt = SP(A.s_wgt + c_lo);
                 if (prey_now) {
-                    // consumption per unit of biomass at each row: all pairs (j = 0), the pairs feeding catch collect vector j - 1
-                    const int cfb = A.g_wscr + warp * A.wscr_n, cfr = A.cf_rows;
-                    const int rows = (U.len + NB - 1) / NB * NB;
-                    const int ncf = catch_now ? 1 + St.cx_n : 1;
-                    for (int j = 0; j < ncf; j++)
-                        for (int r = 0; r < rows; r++) GS(cfb + j * cfr + r, T(0.0));
-                    for (int k = 0; k < nq; k++) {
-                        const PairRec& Q = A.pp[tb[St.pp_off + k]];
-                        const int ts = tb[Q.tsid_off + Cl.ridx];
-                        if (ts < 0) continue;
-                        const int cxm = catch_now ? Q.cxmask : 0;
-                        const bool spred = Q.pred_kind == G3PRED_STOCK;
-                        T e(0.0);
-                        if (!spred) {       // landings / total suitable biomass of this fleet in this column's area
-                            e = G(A.g_eot + ts);
+                    // consumption per unit of biomass by pair k at rows r0 .. r0 + NB - 1 of the unit (the plan's records are in
+                    // shared memory; the suitability rows and the fleets' landings / total suitable biomass are table loads)
+                    auto cfac = [&](const PairRec& Q, const int ts, const int r0, T (&cf)[NB]) {
+                        if (Q.pred_kind != G3PRED_STOCK) {
+                            T e = G(A.g_eot + ts);
                             if (Q.pred_kind == G3PRED_EFFORTFLEET) e = e * SLOT(Q.energy_slot);      // catchability_fs of this prey
+#pragma unroll
+                            for (int b = 0; b < NB; b++) cf[b] = G(Q.g_suit + U.lo + min(r0 + b, U.len - 1)) * e;
+                        } else {        // sum over the predator's length groups of suitability x consumption factor
+                            const int gp = Tpred[Q.pred].g_pts + ts * Q.PL;
+#pragma unroll
+                            for (int b = 0; b < NB; b++) cf[b] = T(0.0);
+                            for (int pl = 0; pl < Q.PL; pl++) {
+                                const T f = G(gp + pl);
+#pragma unroll
+                                for (int b = 0; b < NB; b++) cf[b] = cf[b] + G(Q.g_suit + pl * L + U.lo + min(r0 + b, U.len - 1)) * f;
+                            }
                         }
-                        const int gp = spred ? A.pred[Q.pred].g_pts + ts * Q.PL : 0;
-                        for (int r = 0; r < U.len; r++) {
-                            T cf(0.0);
-                            if (!spred) cf = G(Q.g_suit + U.lo + r) * e;
-                            else        // sum over the predator's length groups of suitability x consumption factor
-                                for (int pl = 0; pl < Q.PL; pl++) cf = cf + G(Q.g_suit + pl * L + U.lo + r) * G(gp + pl);
-                            GS(cfb + r, G(cfb + r) + cf);
-                            for (int j = 0; j < St.cx_n; j++)
-                                if ((cxm >> j) & 1) GS(cfb + (1 + j) * cfr + r, G(cfb + (1 + j) * cfr + r) + cf);
-                        }
-                    }
-                    const double* const pCf = GP(cfb);
+                    };
                     T o1(0.0), o2(0.0);
                     for (int r0 = 0; r0 < U.len; r0 += NB) {
                         const int nb = min(NB, U.len - r0);
-                        T num[NB], B0[NB], tp[NB], cr[NB], de[NB];
+                        T num[NB], B0[NB], tp[NB], cr[NB], de[NB], cf[NB];
 #pragma unroll
                         for (int b = 0; b < NB; b++) {
                             num[b] = ldT<T>(pNum + (unsigned)(r0 + b) * C);
                             B0[b] = num[b] * ldT<T>(pWgt + (unsigned)(r0 + b) * C);
-                            tp[b] = ldT<T>(pCf + (unsigned)(r0 + b) * C) * B0[b];
-                            cr[b] = tp[b]; de[b] = B0[b];
+                            tp[b] = T(0.0);
                         }
+                        for (int k = 0; k < nq; k++) {
+                            const PairRec& Q = Tpp[tb[St.pp_off + k]];
+                            const int ts = tb[Q.tsid_off + Cl.ridx];
+                            if (ts < 0) continue;
+                            cfac(Q, ts, r0, cf);
+#pragma unroll
+                            for (int b = 0; b < NB; b++) tp[b] = tp[b] + cf[b] * B0[b];
+                        }
+#pragma unroll
+                        for (int b = 0; b < NB; b++) { cr[b] = tp[b]; de[b] = B0[b]; }
                         div_azx_n(cr, de);                      // consratio = tp / avoid_zero(B0)   (exact-division forms: g3_math.cuh)
                         dif_pmax_x_n(cr, 0.95, -1e3);           // dif_pmin(consratio, 0.95, 1e3)
                         T tpn[NB];
@@ -763,9 +793,19 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             for (int j = 0; j < St.cx_n; j++) {
                                 const int x = tb[St.cx_off + j];
                                 if (!((xact >> x) & 1)) continue;
+                                T fx[NB];
 #pragma unroll
-                                for (int b = 0; b < NB; b++)
-                                    if (b < nb) GS(A.xb[x].g_x + c_lo + r0 + b, G(cfb + (1 + j) * cfr + r0 + b) * cc[b]);
+                                for (int b = 0; b < NB; b++) fx[b] = T(0.0);
+                                for (int k = 0; k < nq; k++) {
+                                    const PairRec& Q = Tpp[tb[St.pp_off + k]];
+                                    const int ts = tb[Q.tsid_off + Cl.ridx];
+                                    if (ts < 0 || !((Q.cxmask >> j) & 1)) continue;
+                                    cfac(Q, ts, r0, cf);
+#pragma unroll
+                                    for (int b = 0; b < NB; b++) fx[b] = fx[b] + cf[b];
+                                }
+#pragma unroll
+                                for (int b = 0; b < NB; b++) if (b < nb) GS(Txb[x].g_x + c_lo + r0 + b, fx[b] * cc[b]);
                             }
                         }
                     }
@@ -774,7 +814,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     for (int j = 0; j < St.cx_n; j++) {
                         const int x = tb[St.cx_off + j];
                         if ((xact >> x) & 1)
-                            for (int r = 0; r < U.len; r++) GS(A.xb[x].g_x + c_lo + r, T(0.0));       // no landings: cons = 0
+                            for (int r = 0; r < U.len; r++) GS(Txb[x].g_x + c_lo + r, T(0.0));       // no landings: cons = 0
                     }
                 }
                 if (U.up_ghost >= 0) {
@@ -785,15 +825,17 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     }
                 }
             }
+            G3T_PH(3)           // (totals of the predation steps, if any)
             G3T_BAR();          // (pass 2 of a unit may run on another warp than its pass 1; ghost rows are in place)
+            G3T_PH(4)           // pass 1: predation, ghost rows
 
             // ================= own units, pass 2: natural mortality, growth (+ maturing split), and -- unless maturing fish are
             // about to arrive -- renewal and the collect vectors. Length growth only looks DOWN the length axis, so sweeping
             // the blocks from the top the update is in place: every source row is still the old value when a block is rebuilt.
             G3T_UNITS(qn - ctr + 2, uk) {
-                const UnitRec& U = A.unit[tb[A.uorder_off + uk]];
-                const ColRec& Cl = A.col[U.gc];
-                const StockRec& St = A.st[Cl.s];
+                const UnitRec& U = Tunit[tb[A.uorder_off + uk]];
+                const ColRec& Cl = Tcol[U.gc];
+                const StockRec& St = Tst[Cl.s];
                 const int L = St.L, c_lo = Cl.cell0 + U.lo;
                 const int grow_n = St.grow_n;
                 const bool trans_now = grow_n >= 0 && St.has_out && ((St.trans_mask >> step) & 1);
@@ -835,7 +877,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 double* const pTw = stash ? SP(Cl.s_tw + U.lo) : pWgt;
                 bool ren_here = false;      // a renewal into this column at this step
                 for (int r = 0; r < St.n_renew; r++)
-                    ren_here = ren_here || (((ren_mask >> r) & 1) && Cl.aidx == I[St.renew_ioff + r * G3R_LEN + G3R_AGE_IDX]);
+                    ren_here = ren_here || (((ren_mask >> r) & 1) && Cl.aidx == tb[St.ren_off + 3 * r + 1]);
                 const bool finish_here = !inc_here && (ren_here || xact);
                 for (int j = nblk - 1; j >= 0; j--) {
                     const int r0 = j * NB, nb = min(NB, U.len - r0);
@@ -883,22 +925,23 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             // elementwise per cell, so its (column, block) units are dealt to ALL warps, not only to the owners.
             if ((A.inc_any_mask >> step) & 1) {
                 G3T_BAR();
+                G3T_PH(5)       // pass 2: growth
                 int nitem = 0;          // blocks of the receiving columns (tb: A.inc_n global columns)
                 for (int i = 0; i < A.inc_n; i++) {
-                    const ColRec& Cl = A.col[tb[A.inc_off + i]];
-                    if ((Cl.inc_mask >> step) & 1) nitem += (A.st[Cl.s].L + NB - 1) / NB;
+                    const ColRec& Cl = Tcol[tb[A.inc_off + i]];
+                    if ((Cl.inc_mask >> step) & 1) nitem += (Tst[Cl.s].L + NB - 1) / NB;
                 }
                 for (int k = G3T_GRAB(qn + 3); k < nitem; k = G3T_GRAB(qn + 3)) {
                     int i = 0, blk = k;
                     for (;; i++) {
-                        const ColRec& Ci = A.col[tb[A.inc_off + i]];
+                        const ColRec& Ci = Tcol[tb[A.inc_off + i]];
                         if (!((Ci.inc_mask >> step) & 1)) continue;
-                        const int n = (A.st[Ci.s].L + NB - 1) / NB;
+                        const int n = (Tst[Ci.s].L + NB - 1) / NB;
                         if (blk < n) break;
                         blk -= n;
                     }
-                    const ColRec& Cl = A.col[tb[A.inc_off + i]];
-                    const StockRec& St = A.st[Cl.s];
+                    const ColRec& Cl = Tcol[tb[A.inc_off + i]];
+                    const StockRec& St = Tst[Cl.s];
                     const int ren_mask = renewals_now(St);
                     const int r0 = blk * NB, nb = min(NB, St.L - r0);
                     T num[NB], wgt[NB];
@@ -916,35 +959,64 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             // multinomial: each slice), every warp also keeps its share of that total.
             if (cact) {
                 G3T_BAR();
+                G3T_PH(6)       // hand-over blocks (or pass 2 on steps without hand-over)
                 for (int c = 0; c < A.NCOMP; c++) {
                     if (!((cact >> c) & 1)) continue;
-                    const CompRec& Cm = A.comp[c];
+                    const CompRec& Cm = Tcomp[c];
                     const int nd = Cm.n_dest;
                     const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
                     const int ms = Cm.g_ms + (si ? I[Cm.tidx_ioff + t] * nd : 0);
-                    const int xs = A.xb[Cm.xbuf].g_x;
-                    const bool tot_now = Cm.n_groups > 0 && I[Cm.cmp_ioff + t];
+                    const int xs = Txb[Cm.xbuf].g_x, xkind = Txb[Cm.xbuf].kind, xunit = Txb[Cm.xbuf].unit;
+                    const bool tot_now = Cm.n_groups > 0 && ((cmp_now >> c) & 1);
                     if (tot_now) for (int g = 0; g < Cm.n_groups; g++) GS(Cm.g_pt + g * SHW + warp, T(0.0));
-                    const int32_t* __restrict__ ci = A.cterm_idx;
-                    const double* __restrict__ cc = A.cterm_coef;
+                    const int32_t* __restrict__ ci = M + A.m_cidx;
+                    const double* __restrict__ cc = reinterpret_cast<const double*>(M + A.m_ccoef);
+                    int gcur = -1;          // this warp's share of the current group's total stays in a register: its tasks
+                    T gsum(0.0);            // come sorted by group, so the slot in memory is touched once per group
                     for (int k = tb[Cm.task_off + warp]; k < tb[Cm.task_off + warp + 1]; k += 5) {
                         const int e = tb[k], j0 = tb[k + 1], j1 = tb[k + 2], slot = tb[k + 3], grp = tb[k + 4];
+                        const T old = slot < 0 ? G(ms + e) : T(0.0);        // (in flight with the terms' loads)
                         T acc(0.0);
-                        for (int j = j0; j < j1; j++) acc = acc + cc[j] * G(xs + ci[j]);
+                        // CU terms at a time: their loads are in flight together (a catch collect vector was written by other
+                        // warps: every read is an L2 round trip), the sum keeps its order. Abundance needs no collect vector:
+                        // it is the state itself, in shared memory, complete at this point of the step.
+                        constexpr int CU = NTAN > 0 ? 2 : 8;
+                        for (int j = j0; j < j1; j += CU) {
+                            int ix[CU]; double cf[CU]; T xv[CU];
+#pragma unroll
+                            for (int u = 0; u < CU; u++) { const int jj = min(j + u, j1 - 1); ix[u] = ci[jj]; cf[u] = j + u < j1 ? cc[jj] : 0.0; }
+                            if (xkind == 0) {
+#pragma unroll
+                                for (int u = 0; u < CU; u++) xv[u] = G(xs + ix[u]);
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < CU; u++) xv[u] = xunit == 0 ? S(A.s_num + ix[u]) : S(A.s_num + ix[u]) * S(A.s_wgt + ix[u]);
+                            }
+#pragma unroll
+                            for (int u = 0; u < CU; u++) if (j + u < j1) acc = acc + cf[u] * xv[u];
+                        }
                         // slot < 0: the whole dest; slot = -2 - k: first part of split dest (takes the old value along), k: a later part
-                        if (slot < 0) acc = acc + G(ms + e);
+                        if (slot < 0) acc = acc + old;
                         if (slot == -1) GS(ms + e, acc);
                         else GS(Cm.g_cpart + (slot < 0 ? -2 - slot : slot), acc);
-                        if (tot_now) GS(Cm.g_pt + grp * SHW + warp, G(Cm.g_pt + grp * SHW + warp) + acc);
+                        if (tot_now) {
+                            if (grp != gcur) {
+                                if (gcur >= 0) GS(Cm.g_pt + gcur * SHW + warp, G(Cm.g_pt + gcur * SHW + warp) + gsum);
+                                gcur = grp; gsum = T(0.0);
+                            }
+                            gsum = gsum + acc;
+                        }
                     }
+                    if (tot_now && gcur >= 0) GS(Cm.g_pt + gcur * SHW + warp, G(Cm.g_pt + gcur * SHW + warp) + gsum);
                 }
                 G3T_BAR();
+                G3T_PH(7)       // collect tasks
                 // ================= g3l_distribution compare (R/likelihood_distribution.R:375-394): the dests of a component are
                 // dealt warp by warp (continuing from component to component); every warp leaves its share of the component's value
                 int rot = 0;
                 for (int c = 0; c < A.NCOMP; c++) {
                     if (!((cact >> c) & 1)) continue;
-                    const CompRec& Cm = A.comp[c];
+                    const CompRec& Cm = Tcomp[c];
                     const int ti = I[Cm.tidx_ioff + t];
                     const int func = Cm.func, nd = Cm.n_dest, nt = Cm.n_times;
                     const bool si = func == G3F_SI_LOG || func == G3F_SI_LINEAR;
@@ -961,7 +1033,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         for (int i = 0; i < sn; i++) v = v + G(Cm.g_cpart + s0 + i);
                         GS(ms + e, v);
                     }
-                    if (!I[Cm.cmp_ioff + t]) continue;
+                    if (!((cmp_now >> c) & 1)) continue;
                     const int nb = Cm.n_bins;
                     T part(0.0);
                     if (func == G3F_SUMOFSQUARES || func == G3F_MULTINOMIAL) {
@@ -1028,14 +1100,16 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     GS(Cm.g_pv + warp, part);
                 }
             }
+            G3T_PH(8)           // compare (collect steps) / hand-over blocks (other steps)
             G3T_BAR();          // the step's state, collect sums and component values are complete
+            G3T_PH(9)           // waiting at the end-of-step barrier
 
             // ================= the keeper warp: the objective, in the reference's summation order (the unit warps go on)
             if (keeper) {
                 for (int c = 0; c < A.NCOMP; c++) {
                     if (!((cact >> c) & 1)) continue;
-                    const CompRec& Cm = A.comp[c];
-                    if (!I[Cm.cmp_ioff + t]) continue;
+                    const CompRec& Cm = Tcomp[c];
+                    if (!((cmp_now >> c) & 1)) continue;
                     const bool si = Cm.func == G3F_SI_LOG || Cm.func == G3F_SI_LINEAR;
                     if (si && I[Cm.tidx_ioff + t] != Cm.n_times - 1) continue;      // survey indices score once, at their last time
                     if (lane_on && ((cw_lane >> c) & 1)) {
@@ -1051,10 +1125,10 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     T us_tot(0.0);
                     if (pred_now)
                         for (int s = 0; s < NS; s++) {
-                            const StockRec& St = A.st[s];
+                            const StockRec& St = Tst[s];
                             if (!St.us_flag || St.pp_n == 0) continue;
                             T o1(0.0), o2(0.0);
-                            for (int u = St.u0; u < St.u0 + St.nu; u++) { o1 = o1 + G(A.unit[u].g_usp); o2 = o2 + G(A.unit[u].g_usp + 1); }
+                            for (int u = St.u0; u < St.u0 + St.nu; u++) { o1 = o1 + G(Tunit[u].g_usp); o2 = o2 + G(Tunit[u].g_usp + 1); }
                             us_tot = us_tot + (o1 - o2);
                         }
                     const T u = (us_power == 2.0) ? us_tot * us_tot : xpow(us_tot, T(us_power));
@@ -1068,11 +1142,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             // ================= g3a_age (R/action_age.R:51-85) + movement hand-off: length group by length group
             if (final_step) {
                 bool age_any = false;
-                for (int s = 0; s < NS; s++) age_any = age_any || A.st[s].age_enable;
+                for (int s = 0; s < NS; s++) age_any = age_any || Tst[s].age_enable;
                 if (age_any) {
                     for (int l = warp; l < A.maxL; l += W) {
                         for (int s = 0; s < NS; s++) {
-                            const StockRec& St = A.st[s];
+                            const StockRec& St = Tst[s];
                             if (!St.age_enable || l >= St.L) continue;
                             const int L = St.L, nage = St.nage, narea = St.narea;
                             for (int r = 0; r < narea; r++) {
@@ -1099,7 +1173,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             }
                         }
                         for (int i = tb[A.agedst_l_off + l]; i < tb[A.agedst_l_off + l + 1]; i++) {
-                            const int4 e = A.agedst[i];     // (destination cell, stash entry num, stash entry wgt, ratio slot); same l
+                            const int4 e = Tagedst[i];     // (destination cell, stash entry num, stash entry wgt, ratio slot); same l
                             if (e.x < 0) continue;
                             const T n0 = S(A.s_num + e.x);
                             const T moved = S(e.y) * SLOT(e.w);
@@ -1110,6 +1184,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     G3T_BAR();
                 }
             }
+            G3T_PH(10)          // keeper / ageing
         }   // time loop
 
         if (keeper && live) {
@@ -1123,6 +1198,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     if (tile_t * NTAN + k < A.K) A.grad[b * A.K + tile_t * NTAN + k] = tan_of(out, k);
         }
     }
+    G3T_PH_FLUSH()
 #undef GP
 #undef SP
 #undef SLOT

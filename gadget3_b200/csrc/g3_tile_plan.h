@@ -5,6 +5,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -19,6 +20,7 @@ struct TilePlan {
     std::vector<StockRec> st; std::vector<ColRec> col; std::vector<UnitRec> unit; std::vector<PairRec> pp; std::vector<PredRec> pred;
     std::vector<TsRec> ts; std::vector<CompRec> comp; std::vector<XRec> xb; std::vector<int4> agedst;
     std::vector<int32_t> tb;
+    std::vector<int32_t> meta;  // all of the above in one block (plan_pack_meta): what the kernel reads, from shared memory if it fits
     std::vector<double> obsprop, obsconst;
     std::vector<unsigned char> pred_active;
     int n_s = 0;                // state entries per lane (shared memory, or after the G entries in the slab)
@@ -148,6 +150,35 @@ inline void plan_build_units(TilePlan& P) {
     P.tb_units = (int)P.tb.size();
 }
 
+// every record table and tb in one block of ints, sections aligned to 16 bytes
+inline void plan_pack_meta(TilePlan& P) {
+    TArgs& A = P.a;
+    P.meta.clear();
+    auto put = [&](const void* data, size_t bytes) {
+        while (P.meta.size() % 4) P.meta.push_back(0);
+        const int off = (int)P.meta.size();
+        const size_t n = (bytes + 3) / 4;
+        P.meta.resize(off + std::max<size_t>(n, 1), 0);
+        if (bytes) std::memcpy(P.meta.data() + off, data, bytes);
+        return off;
+    };
+    A.m_st = put(P.st.data(), P.st.size() * sizeof(StockRec));
+    A.m_col = put(P.col.data(), P.col.size() * sizeof(ColRec));
+    A.m_unit = put(P.unit.data(), P.unit.size() * sizeof(UnitRec));
+    A.m_pp = put(P.pp.data(), P.pp.size() * sizeof(PairRec));
+    A.m_pred = put(P.pred.data(), P.pred.size() * sizeof(PredRec));
+    A.m_ts = put(P.ts.data(), P.ts.size() * sizeof(TsRec));
+    A.m_comp = put(P.comp.data(), P.comp.size() * sizeof(CompRec));
+    A.m_xb = put(P.xb.data(), P.xb.size() * sizeof(XRec));
+    A.m_agedst = put(P.agedst.data(), P.agedst.size() * sizeof(int4));
+    A.m_tb = put(P.tb.data(), P.tb.size() * sizeof(int32_t));
+    A.m_cidx = put(P.cterm_idx.data(), P.cterm_idx.size() * sizeof(int32_t));       // collect terms: cell, lgmatrix coefficient
+    A.m_ccoef = put(P.cterm_coef.data(), P.cterm_coef.size() * sizeof(double));
+    while (P.meta.size() % 4) P.meta.push_back(0);
+    A.meta_n = (int)P.meta.size();
+    A.n_s = P.n_s;
+}
+
 // set the warp count of a plan: W unit warps take units from the work queues; the collect tasks are dealt to all W + 1 warps
 // (lists at the end of tb)
 inline void plan_set_warps(TilePlan& P, int W) {
@@ -168,10 +199,12 @@ inline void plan_set_warps(TilePlan& P, int W) {
         P.tb.resize(off + W + 2);
         for (int w = 0; w <= W; w++) {
             P.tb[off + w] = (int)P.tb.size();
+            std::stable_sort(mine[w].begin(), mine[w].end(), [&](int x, int y) { return T[5 * x + 4] < T[5 * y + 4]; });   // by group
             for (int k : mine[w]) for (int i = 0; i < 5; i++) P.tb.push_back(T[5 * k + i]);
         }
         P.tb[off + W + 1] = (int)P.tb.size();
     }
+    plan_pack_meta(P);
     // per-warp scratch follows the other G entries (W unit warps + the keeper warp)
     P.a.n_g = P.a.g_wscr + (W + 1) * P.a.wscr_n;
 }
@@ -279,6 +312,11 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         r.mort_ioff = St[G3S_MORT_OFF]; r.midlen_roff = St[G3S_MIDLEN_ROFF]; r.plusdl_roff = St[G3S_PLUSDL_ROFF];
         r.grow_ioff = St[G3S_GROW_OFF]; r.mat_ioff = St[G3S_MAT_OFF]; r.init_ioff = St[G3S_INIT_OFF];
         r.n_renew = St[G3S_N_RENEW]; r.renew_ioff = St[G3S_RENEW_OFF];
+        r.ren_off = (int)P.tb.size();
+        for (int k = 0; k < r.n_renew; k++) {
+            const int32_t* Rn = I + r.renew_ioff + k * G3R_LEN;
+            P.tb.push_back(Rn[G3R_RUN_STEP]); P.tb.push_back(Rn[G3R_AGE_IDX]); P.tb.push_back(Rn[G3R_FACTOR_OFF]);
+        }
         if (r.n_renew > 30) return fail("more than 30 renewal actions on one stock");
         maxnarea = std::max(maxnarea, r.narea);
         r.g_mort = takeg(r.mort_ioff >= 0 ? r.ncol * A.ndt : 0);
@@ -605,6 +643,18 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
             P.obsconst.push_back(cst);
         }
     }
+    // per step: components with a time index (bit c), components that compare (bit c), predation on
+    A.tmask_off = (int)P.tb.size();
+    for (int which = 0; which < 2; which++)
+        for (int t = 0; t < A.NT; t++) {
+            unsigned mask = 0;
+            for (int c = 0; c < A.NCOMP; c++) {
+                const int v = which == 0 ? I[P.comp[c].tidx_ioff + t] : I[P.comp[c].cmp_ioff + t];
+                if (which == 0 ? v >= 0 : v != 0) mask |= 1u << c;
+            }
+            P.tb.push_back((int32_t)mask);
+        }
+    for (int t = 0; t < A.NT; t++) P.tb.push_back(P.pred_active[t]);
     if (P.obsprop.empty()) P.obsprop.push_back(0.0);
     if (P.obsconst.empty()) P.obsconst.push_back(0.0);
     A.g_cn = takeg(std::max(A.NCOMP, 1));

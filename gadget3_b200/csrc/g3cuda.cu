@@ -72,7 +72,8 @@ struct g3cuda_model {
     g3t::TilePlan tplan;
     g3t::TArgs targs{};
     bool tile_ok = false;
-    int32_t* d_tb = nullptr;            // re-uploaded when the warp count changes
+    int32_t* d_tb = nullptr;            // the plan's tables in one block; re-uploaded when the warp count or the partition changes
+    const unsigned char* d_pred_active = nullptr;
     double* t_gws = nullptr; size_t t_gws_bytes = 0;
     // ---- thread kernel (g3_thread_kernel.cuh)
     g3::KArgs base{};
@@ -105,19 +106,18 @@ template <class T> int ensure(T** p, size_t* cap, size_t n) {
 
 // ============================================================ tile kernel
 int tile_upload_tb(g3cuda_model* m) {
+    // the plan's record tables and index lists travel as one block (g3t::plan_pack_meta); re-uploaded when the warp count or
+    // the partition changes
     if (m->d_tb) { CUDA_TRY(cudaDeviceSynchronize()); cudaFree(m->d_tb); m->d_tb = nullptr; }
-    m->d_tb = dev_copy(m->tplan.tb);
-    auto* d_comp = dev_copy(m->tplan.comp);     // (the components' task lists live in tb)
-    if (!m->d_tb || !d_comp) return fail(G3CUDA_ENOMEM, "device allocation failed");
-    m->owned.push_back((void*)d_comp);
-    m->tplan.a.comp = d_comp;
+    m->d_tb = dev_copy(m->tplan.meta);
+    if (!m->d_tb) return fail(G3CUDA_ENOMEM, "device allocation failed");
+    m->tplan.a.meta = m->d_tb;
     m->targs = m->tplan.a;              // scalars (W, n_g, offsets) change with the warp count
-    m->targs.tb = m->d_tb;
     return G3CUDA_OK;
 }
 
 // tiles in flight and lanes per tile for `work` items
-struct TileGeom { const void* fn; size_t smem; int per_sm; long long slots; bool in_smem; };
+struct TileGeom { const void* fn; size_t smem; int per_sm; long long slots; bool in_smem, meta_in_smem; };
 
 template <class T>
 int tile_geom(g3cuda_model* m, TileGeom* g) {
@@ -126,6 +126,10 @@ int tile_geom(g3cuda_model* m, TileGeom* g) {
     const size_t state = (size_t)m->tplan.n_s * cpe * sizeof(double);
     g->in_smem = state <= m->smem_optin;
     g->smem = g->in_smem ? state : 0;
+    // the plan's tables beside the state, if they fit (else the kernel reads them from global memory)
+    const size_t meta_bytes = (size_t)m->targs.meta_n * sizeof(int32_t) + 16;
+    g->meta_in_smem = g->smem + meta_bytes + 64 <= m->smem_optin;
+    if (g->meta_in_smem) g->smem += meta_bytes;
     const bool wide = m->tplan.maxn > 4;
     const int threads = (m->targs.W + 1) * 32;
     if (threads > 512 && (dual || wide)) return fail(G3CUDA_EUNSUPP, "more than 16 warps per tile exist for plain values and narrow growth bands only");
@@ -146,6 +150,7 @@ int launch_tile(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStre
     g3t::TArgs A = m->targs;
     A.par = call.par; A.B = call.B; A.tangent_idx = call.tangent_idx; A.K = call.K;
     A.nll = call.nll; A.comp_out = call.comp; A.grad = call.grad;
+    A.meta_in_smem = g.meta_in_smem;
     // few evaluations: spread them over the SMs with partly filled tiles (latency); many: full 32-lane tiles
     const int lpt = (int)std::min<long long>(g3t::NL, std::max<long long>(1, (work + g.slots - 1) / g.slots));
     const long long ntile = (work + lpt - 1) / lpt;
@@ -646,16 +651,11 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     m->tplan = g3t::make_tile_plan(I, R);
     if (m->tplan.ok) {
         g3t::TilePlan& TP = m->tplan;
-        auto* d_st = up(TP.st); auto* d_col = up(TP.col); auto* d_unit = up(TP.unit); auto* d_pp = up(TP.pp); auto* d_pred = up(TP.pred); auto* d_ts = up(TP.ts);
-        auto* d_comp = up(TP.comp); auto* d_xb = up(TP.xb); auto* d_ad = up(TP.agedst);
         auto* d_op = up(TP.obsprop); auto* d_oc = up(TP.obsconst); auto* d_pa = up(TP.pred_active);
-        if (TP.cterm_idx.empty()) { TP.cterm_idx.push_back(0); TP.cterm_coef.push_back(0.0); }
-        auto* d_ci = up(TP.cterm_idx); auto* d_cc = up(TP.cterm_coef);
-        if (!d_st || !d_col || !d_unit || !d_pp || !d_pred || !d_ts || !d_comp || !d_xb || !d_ad || !d_op || !d_oc || !d_pa || !d_ci || !d_cc)
+        m->d_pred_active = d_pa;
+        if (!d_op || !d_oc || !d_pa)
             return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
-        TP.a.I = d_I; TP.a.R = d_R; TP.a.st = d_st; TP.a.col = d_col; TP.a.unit = d_unit; TP.a.pp = d_pp; TP.a.pred = d_pred; TP.a.ts = d_ts;
-        TP.a.comp = d_comp; TP.a.xb = d_xb; TP.a.agedst = d_ad; TP.a.obsprop = d_op; TP.a.obsconst = d_oc; TP.a.pred_active = d_pa;
-        TP.a.cterm_idx = d_ci; TP.a.cterm_coef = d_cc;
+        TP.a.I = d_I; TP.a.R = d_R; TP.a.obsprop = d_op; TP.a.obsconst = d_oc;
         if ((rc = tile_upload_tb(m))) return bail(rc);
         m->tile_ok = true;
     }
@@ -673,7 +673,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
             A.rem_off = up(rem_off); A.rem_slots = up(rem_slots); A.pp_tsid = up(tsid);
             A.w_agedst = up(agedst); A.t_colinc = up(colinc);
             if (!A.rem_off || !A.rem_slots || !A.pp_tsid || !A.w_agedst || !A.t_colinc) return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
-            A.obsprop = m->tplan.a.obsprop; A.obsconst = m->tplan.a.obsconst; A.w_pred_active = m->tplan.a.pred_active;
+            A.obsprop = m->tplan.a.obsprop; A.obsconst = m->tplan.a.obsconst; A.w_pred_active = m->d_pred_active;
             for (int c = 0; c < A.NCOMP; c++) { A.obs_off[c] = m->tplan.comp[c].obs_off; A.obsconst_off[c] = m->tplan.comp[c].obsconst_off; }
         }
     }
@@ -905,15 +905,8 @@ int g3cuda_set_tile_partition(g3cuda_model* m, int warps, int seg_rows) {
     CUDA_TRY(cudaDeviceSynchronize());
     g3t::TilePlan np = g3t::make_tile_plan(m->I.data(), m->R.data(), warps, seg_rows, std::max(warps, 15));
     if (!np.ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", np.why.c_str());
-    // the record tables that depend on the partition: stocks (unit ranges), units, pairs, totals, predators
-    auto up = [&](auto& vec) { auto* d = dev_copy(vec); if (d) m->owned.push_back((void*)d); return d; };
     const g3t::TArgs old = m->tplan.a;
-    auto* d_st = up(np.st); auto* d_unit = up(np.unit); auto* d_pp = up(np.pp); auto* d_pred = up(np.pred); auto* d_ts = up(np.ts);
-    if (!d_st || !d_unit || !d_pp || !d_pred || !d_ts) return fail(G3CUDA_ENOMEM, "device allocation failed");
-    np.a.I = old.I; np.a.R = old.R; np.a.col = old.col; np.a.comp = old.comp; np.a.xb = old.xb; np.a.agedst = old.agedst;
-    np.a.obsprop = old.obsprop; np.a.obsconst = old.obsconst; np.a.pred_active = old.pred_active;
-    np.a.cterm_idx = old.cterm_idx; np.a.cterm_coef = old.cterm_coef;
-    np.a.st = d_st; np.a.unit = d_unit; np.a.pp = d_pp; np.a.pred = d_pred; np.a.ts = d_ts;
+    np.a.I = old.I; np.a.R = old.R; np.a.obsprop = old.obsprop; np.a.obsconst = old.obsconst;
     m->tplan = std::move(np);
     return tile_upload_tb(m);
 }

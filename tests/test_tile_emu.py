@@ -102,3 +102,12 @@ def test_nan_for_negative_retro_years_is_per_lane(oracle_lib):
     assert np.isnan(g[2]) and np.isnan(o[2])
     ok = [0, 1, 3]
     assert (np.abs(g[ok] - o[ok]) / np.abs(o[ok])).max() < 1e-10
+
+
+def test_plan_tables_from_global_memory(oracle_lib):
+    """The plan's record tables are read from shared memory when they fit beside the state and from global memory otherwise:
+    same tables, same results to the bit."""
+    model, p, ints, reals, full, _ = _setup("C5", 2)
+    a = emu.eval_batch(ints, reals, full, want_comp=True, meta_smem=True)
+    b = emu.eval_batch(ints, reals, full, want_comp=True, meta_smem=False)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
