@@ -562,26 +562,43 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     mig_any = true;
                     const int L = St.L, nage = St.nage, NR = St.narea, c0 = St.c0;
                     const int mo = St.g_mig + step * NR * NR;
-                    for (int a = 0; a < nage; a++) {
-                        if (!mine()) continue;
-                        for (int l = 0; l < L; l++) {
-                            const int i = a * L + l;
-                            // destination by destination; sources are read before any destination is written (wscr holds them)
-                            for (int r = 0; r < NR; r++) {
-                                GS(A.g_wscr + warp * A.wscr_n + 2 * r, S(A.s_num + c0 + r * nage * L + i));
-                                GS(A.g_wscr + warp * A.wscr_n + 2 * r + 1, S(A.s_wgt + c0 + r * nage * L + i));
-                            }
-                            for (int d = 0; d < NR; d++) {
-                                T pn(0.0), pw(0.0);
-                                for (int r = 0; r < NR; r++) {
-                                    const T moved = G(A.g_wscr + warp * A.wscr_n + 2 * r) * G(mo + d * NR + r);
-                                    pw = ratio_add_pop(pw, pn, G(A.g_wscr + warp * A.wscr_n + 2 * r + 1), moved);     // stock_combine_subpop
-                                    pn = pn + moved;
+                    // work items: NB length groups of one age, dealt to the warps. Destination by destination; the sources are
+                    // read before any destination is written (the warp's scratch holds them); the ratio_add_pop chains
+                    // (stock_combine_subpop: one avoid_zero + reciprocal per source area) of the NB rows run interleaved
+                    const int ws = A.g_wscr + warp * A.wscr_n;
+                    for (int a = 0; a < nage; a++)
+                        for (int l0 = 0; l0 < L; l0 += NB) {
+                            if (!mine()) continue;
+                            const int nb = min(NB, L - l0);
+                            for (int r = 0; r < NR; r++)
+#pragma unroll
+                                for (int b = 0; b < NB; b++) {
+                                    const int i = a * L + min(l0 + b, L - 1);
+                                    GS(ws + (2 * r) * NB + b, S(A.s_num + c0 + r * nage * L + i));
+                                    GS(ws + (2 * r + 1) * NB + b, S(A.s_wgt + c0 + r * nage * L + i));
                                 }
-                                SS(A.s_num + c0 + d * nage * L + i, pn); SS(A.s_wgt + c0 + d * nage * L + i, pw);
+                            for (int d = 0; d < NR; d++) {
+                                T pn[NB], pw[NB];
+#pragma unroll
+                                for (int b = 0; b < NB; b++) { pn[b] = T(0.0); pw[b] = T(0.0); }
+                                for (int r = 0; r < NR; r++) {
+                                    const T prop = G(mo + d * NR + r);
+                                    T nu[NB], de[NB], moved[NB];
+#pragma unroll
+                                    for (int b = 0; b < NB; b++) {
+                                        moved[b] = G(ws + (2 * r) * NB + b) * prop;
+                                        nu[b] = pw[b] * pn[b] + G(ws + (2 * r + 1) * NB + b) * moved[b];      // ratio_add_pop, R/aab_env.R:133-153
+                                        de[b] = pn[b] + moved[b];
+                                    }
+                                    div_az_n(nu, de);
+#pragma unroll
+                                    for (int b = 0; b < NB; b++) { pw[b] = nu[b]; pn[b] = pn[b] + moved[b]; }
+                                }
+#pragma unroll
+                                for (int b = 0; b < NB; b++)
+                                    if (b < nb) { const int i = a * L + l0 + b; SS(A.s_num + c0 + d * nage * L + i, pn[b]); SS(A.s_wgt + c0 + d * nage * L + i, pw[b]); }
                             }
                         }
-                    }
                 }
                 if (mig_any) G3T_BAR();
                 G3T_PH(1)
@@ -601,13 +618,22 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         if (tb[Q.tsid_off + Cl.ridx] < 0) continue;
                         const bool spred = Q.pred_kind == G3PRED_STOCK;
                         const bool by_number = Q.pred_kind == G3PRED_NUMBERFLEET;       // suit = S * num (R/action_predate.R:7-11)
-                        for (int pl = 0; pl < Q.PL; pl++) {
-                            T cs(0.0);
+                        // four predator length groups at a time: the unit's biomass is read once per four, their loads in flight together
+                        for (int pl0 = 0; pl0 < Q.PL; pl0 += 4) {
+                            T cs[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) cs[u] = T(0.0);
                             for (int r = 0; r < U.len; r++) {
                                 const T n = S(A.s_num + c_lo + r);
-                                cs = cs + G(Q.g_suit + pl * L + U.lo + r) * (by_number ? n : n * S(A.s_wgt + c_lo + r));
+                                const T bm = by_number ? n : n * S(A.s_wgt + c_lo + r);
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    cs[u] = cs[u] + G(Q.g_suit + min(pl0 + u, Q.PL - 1) * L + U.lo + r) * bm;
                             }
-                            GS(Q.g_part + U.lu * Q.PL + pl, spred ? cs * SLOT(Q.energy_slot) : cs);
+                            const T en = spred ? SLOT(Q.energy_slot) : T(1.0);
+#pragma unroll
+                            for (int u = 0; u < 4; u++)
+                                if (pl0 + u < Q.PL) GS(Q.g_part + U.lu * Q.PL + pl0 + u, spred ? cs[u] * en : cs[u]);
                         }
                     }
                 }

@@ -137,9 +137,9 @@ inline void plan_build_units(TilePlan& P) {
             for (int e : lists[pr]) P.tb.push_back(e);
         }
     }
-    // per-warp scratch: migration sources, or the consumption factors of one unit ([1 + catch collect vectors][rows])
+    // per-warp scratch: the sources of a block of migrating rows
     A.cf_rows = (max_len + NBX - 1) / NBX * NBX;
-    A.wscr_n = std::max({2 * P.maxnarea, (1 + P.max_cx) * A.cf_rows, 1});
+    A.wscr_n = std::max(2 * P.maxnarea * NBX, 1);
     A.g_wscr = ng;
     // the work queues hand the units out most expensive first
     std::vector<int> order(P.unit.size());

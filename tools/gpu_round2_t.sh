@@ -1,0 +1,4 @@
+python tools/gpu_tile_sweep.py C5 37888 "0:0"
+python tools/gpu_tile_sweep.py C2 37888 "0:0"
+python tools/gpu_phase_clocks.py gadget3_b200/csrc/variants/libg3cuda_phase.so C5 4736
+python -m pytest tests -m gpu -q --timeout 1200 -x 2>&1 | tail -4
