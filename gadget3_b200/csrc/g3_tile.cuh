@@ -49,6 +49,8 @@ struct StockRec {
     int g_rd, g_rw;         // [k][l] renewal numbers shape (x 1e4) and weight
     int g_wq;               // [l] walpha * midlen^wbeta; NW - 1 zero rows before row 0, NBX - 1 after row L - 1
     int g_band, g_bandr;    // destination-oriented growth bands, staying (or whole) / maturing part: [set][idt][(L + NBX - 1) * NW]
+    int h_wq, h_band, h_bandr;      // the same tables in the H entries (shared memory beside the state), or -1: the planner puts
+                                    // the hottest tables there as far as room allows (plain-double runs only)
     int band_percol, bsz;   // one set per column (continuous maturity with an age term) or per stock
     int g_cmat;             // [col][l] g3a_mature_constant ratio (NW - 1 zero rows before, NBX - 1 after), or -1
     int mig_ioff, g_mig, mig_steps;
@@ -100,6 +102,7 @@ struct TArgs {
     // memory when the kernel starts if it fits beside the state: the per-step control code of every warp walks these tables,
     // and from global memory every hop is an L2 round trip (the bands and collect vectors stream through L1)
     const int32_t* meta; int meta_n, meta_in_smem, n_s;
+    int n_h, use_h;         // H entries: hot per-evaluation tables in shared memory (after the state, before the plan's tables)
     int m_st, m_col, m_unit, m_pp, m_pred, m_ts, m_comp, m_xb, m_agedst, m_tb, m_cidx, m_ccoef;
     int tmask_off;          // tb: [3][NT] per step: components whose time index is set (bit c), that compare (bit c), predation on
     const double* obsprop; const double* obsconst;
@@ -112,7 +115,7 @@ struct TArgs {
     int s_num, s_wgt;       // S entry bases (NW - 1 zero entries lie below s_num)
     int g_slot, g_eot, g_cn, g_ctot, g_bterm, g_wscr, wscr_n, cf_rows;
     int ax_off, ax_n;       // tb: abundance collect vectors
-    int zr_off, zr_n;       // tb: (space, first entry, count) triples zeroed once per tile: pads and the band tables
+    int zr_off, zr_n;       // tb: (space 0 = G / 1 = S, first entry, count) triples zeroed once per tile: pads and the band tables
     int agedst_l_off;       // tb: [maxL + 1] first agedst entry of each length group (they are sorted by length group, then cell)
     int uorder_off;         // tb: the units, most expensive first (the work queues' order)
     int inc_off, inc_n;     // tb: global columns that receive maturing fish
@@ -251,9 +254,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
     const bool keeper = warp == A.W;
     double* const gl = A.gws + (size_t)cta * (size_t)A.slab_doubles + lane;
     double* const sm = SMEM ? smem + lane : gl + (size_t)A.n_g * C;
+    double* const hs = smem + (SMEM ? (size_t)A.n_s * C : 0) + lane;
+#define HP(e) (hs + (unsigned)(e) * C)
     const int32_t* M = A.meta;
     if (A.meta_in_smem) {       // the plan's tables, once per CTA
-        int32_t* const ms = reinterpret_cast<int32_t*>(smem + (SMEM ? (size_t)A.n_s * C : 0));
+        int32_t* const ms = reinterpret_cast<int32_t*>(smem + (SMEM ? (size_t)A.n_s * C : 0) + (A.use_h ? (size_t)A.n_h * C : 0));
         for (int i = G3T_TID(warp, lane); i < A.meta_n; i += G3T_NTHREADS(A.W + 1)) ms[i] = A.meta[i];
         G3T_BAR();
         M = ms;
@@ -316,6 +321,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
         // ================= scalar formula slots, once per parameter vector; pads and band tables start from zero
         for (int i = warp; i < A.NSLOT; i += W) GS(A.g_slot + i, eval_slot_g<T>(I, R, prow, seed, i));
         if (keeper) for (int i = 0; i < 8; i++) ctr[i] = 0;
+        if (A.use_h) for (int i = warp; i < A.n_h; i += W) stT<T>(HP(i), T(0.0));       // (pads and the band tables start from zero)
         for (int z = 0; z < A.zr_n; z++) {
             const int space = tb[A.zr_off + 3 * z], e0 = tb[A.zr_off + 3 * z + 1], n = tb[A.zr_off + 3 * z + 2];
             for (int i = warp; i < n; i += W) { if (space) SS(e0 + i, T(0.0)); else GS(e0 + i, T(0.0)); }
@@ -394,8 +400,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             const int n2 = St.grow_n;
             if (n2 < 0) continue;
             const int32_t* gs = I + St.grow_ioff;
+            // where these tables live: the H entries (shared memory) if the planner found room for them, else the slab
+            const bool hwq = A.use_h && St.h_wq >= 0;
+            double* const bandp = A.use_h && St.h_band >= 0 ? HP(St.h_band) : GP(St.g_band);
+            double* const bandrp = A.use_h && St.h_bandr >= 0 ? HP(St.h_bandr) : GP(St.g_bandr);
             for (int l = 0; l < L; l++)         // walpha l^wbeta (g3a_grow_weightsimple, R/action_grow.R:58-71)
-                if (mine()) GS(St.g_wq + l, SLOT(gs[3]) * xpow(midlen[l], SLOT(gs[4])));
+                if (mine()) stT<T>(hwq ? HP(St.h_wq + l) : GP(St.g_wq + l), SLOT(gs[3]) * xpow(midlen[l], SLOT(gs[4])));
             // ---- growth bands: P(l -> l + x), x = 0..n, of each source row l (growth_bbinom in product form,
             // R/action_grow.R:155-213), stored destination-oriented: entry [l + x][x]; everything that would leave the
             // length axis is summed into the plus group's row L - 1 (R/action_grow.R:233-271). Continuous maturity splits
@@ -437,8 +447,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                                     rx[x] = g * ratio; gx[x] = g * (1.0 - ratio);
                                 } else gx[x] = g;
                                 if (x < dtail) {
-                                    GS(St.g_band + base + (l + x) * NW + x, gx[x]);
-                                    if (cont) GS(St.g_bandr + base + (l + x) * NW + x, rx[x]);
+                                    stT<T>(bandp + (unsigned)(base + (l + x) * NW + x) * C, gx[x]);
+                                    if (cont) stT<T>(bandrp + (unsigned)(base + (l + x) * NW + x) * C, rx[x]);
                                 }
                                 if (x < n2)
                                     g = g * ((double)(n2 - x) / (double)(x + 1)) * (xabs(alpha + (double)x) / (beta + (double)(n2 - x - 1)));
@@ -448,8 +458,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 #pragma unroll
                             for (int x = 0; x < NW; x++)
                                 if (x >= dtail && x <= n2) { ta = ta + gx[x]; tr = tr + rx[x]; }
-                            GS(St.g_band + base + (L - 1) * NW + dtail, ta);
-                            if (cont) GS(St.g_bandr + base + (L - 1) * NW + dtail, tr);
+                            stT<T>(bandp + (unsigned)(base + (L - 1) * NW + dtail) * C, ta);
+                            if (cont) stT<T>(bandrp + (unsigned)(base + (L - 1) * NW + dtail) * C, tr);
                         }
                     }
         }
@@ -893,9 +903,9 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 }
                 const T remf = trans_now ? G(Cl.g_remf) : T(0.0);
                 const int bset = ((St.band_percol ? Cl.col : 0) * A.ndt + idt) * St.bsz + U.lo * NW;
-                const double* const pB = GP(St.g_band + bset);
-                const double* const pBr = GP(St.g_bandr + bset);
-                const double* const pQ = GP(St.g_wq + U.lo);
+                const double* const pB = A.use_h && St.h_band >= 0 ? HP(St.h_band + bset) : GP(St.g_band + bset);
+                const double* const pBr = A.use_h && St.h_bandr >= 0 ? HP(St.h_bandr + bset) : GP(St.g_bandr + bset);
+                const double* const pQ = A.use_h && St.h_wq >= 0 ? HP(St.h_wq + U.lo) : GP(St.g_wq + U.lo);
                 const double* const pCm = St.g_cmat >= 0 ? GP(St.g_cmat + Cl.col * L + U.lo) : pQ;
                 const double* const pGh = U.g_ghost >= 0 ? GP(U.g_ghost) : pQ;
                 const bool stash = trans_now && Cl.s_tn >= 0;
@@ -1225,6 +1235,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
         }
     }
     G3T_PH_FLUSH()
+#undef HP
 #undef GP
 #undef SP
 #undef SLOT

@@ -31,6 +31,7 @@ struct TilePlan {
     int g_fixed = 0, tb_fixed = 0;      // G entries / tb words that do not depend on the partition into units
     int tb_units = 0;                   // tb words up to and including the partition's lists (the collect task lists follow)
     int max_cx = 0, maxnarea = 1;
+    int ctas_per_sm = 1;        // CTAs the plan wants resident per SM (small models: 4): the shared-memory budget of one is 1 / that
     int max_W = 15;             // most unit warps (15 + keeper = 512 threads at 128 registers; 23 + keeper = 768 at 80)
     std::vector<std::vector<int>> pp_of_stock;
     // collect terms of all components (cell index, coefficient) and the tasks they are cut into: (dest, first term, end term, slot, group)
@@ -177,6 +178,40 @@ inline void plan_pack_meta(TilePlan& P) {
     while (P.meta.size() % 4) P.meta.push_back(0);
     A.meta_n = (int)P.meta.size();
     A.n_s = P.n_s;
+}
+
+// Hot per-evaluation tables in shared memory: what is left of `smem_bytes` beside the state (if it lives there) and the plan's
+// own tables takes walpha l^wbeta of every growing stock first, then growth bands, the stocks with most columns first. (The L1
+// cache does not help here: the tables of the 15 warps stream through it -- measured: the same speed with 28 KB of L1 as with 60.)
+inline void plan_place_hot(TilePlan& P, size_t smem_bytes) {
+    TArgs& A = P.a;
+    const size_t entry = (size_t)NL * sizeof(double);
+    const size_t state = (size_t)P.n_s * entry;
+    size_t used = 4096 + (size_t)A.meta_n * sizeof(int32_t) + (state + 4096 <= smem_bytes ? state : 0);
+    smem_bytes /= (size_t)std::max(1, P.ctas_per_sm);
+    int nh = 0;
+    auto room = [&](int n) { return used + (size_t)(nh + n) * entry <= smem_bytes; };
+    for (auto& r : P.st) r.h_wq = r.h_band = r.h_bandr = -1;
+    // Only where the state itself does not fit shared memory (which then stands empty): C4 + 7 %, C5 + 5 %. Beside a resident
+    // state the tables bring nothing (C2: 806 k with, 830 k without): its growth pass waits on the fp64 pipe, not on these loads.
+    const bool state_resident = state + 4096 <= smem_bytes * (size_t)std::max(1, P.ctas_per_sm);
+    for (auto& r : P.st) {
+        if (r.grow_n < 0 || state_resident) continue;
+        const int n = A.NWc - 1 + r.L + NBX - 1;
+        if (room(n)) { r.h_wq = nh + A.NWc - 1; nh += n; }
+    }
+    std::vector<int> order(P.st.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.st[x].ncol > P.st[y].ncol; });
+    for (int s : order) {
+        StockRec& r = P.st[s];
+        if (r.grow_n < 0 || state_resident) continue;
+        const int n = (r.band_percol ? r.ncol : 1) * A.ndt * r.bsz;
+        if (room(n)) { r.h_band = nh; nh += n; }
+        if (r.g_bandr != r.g_band && r.h_band >= 0 && room(n)) { r.h_bandr = nh; nh += n; }
+    }
+    A.n_h = nh;
+    plan_pack_meta(P);          // (the stock records changed)
 }
 
 // set the warp count of a plan: W unit warps take units from the work queues; the collect tasks are dealt to all W + 1 warps
@@ -689,7 +724,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     for (int s = 0; s < A.NS; s++) P.seglen[s] = P.st[s].L;
     const size_t state_bytes = (size_t)ns * NL * sizeof(double) + 1024;
     const int fit = (int)(smem_bytes / state_bytes);
-    if (want_W == 0 && want_seg == 0 && max_W <= 15 && fit >= 4) { want_W = 3; want_seg = -1; }
+    if (want_W == 0 && want_seg == 0 && max_W <= 15 && fit >= 4) { want_W = 3; want_seg = -1; P.ctas_per_sm = 4; }
     if (want_seg == 0) plan_choose_partition(P, P.max_W);
     else if (want_seg > 0)
         for (int s = 0; s < A.NS; s++) {
@@ -698,6 +733,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         }
     plan_build_units(P);
     plan_set_warps(P, want_W > 0 ? want_W : P.max_W);
+    plan_place_hot(P, smem_bytes);
     P.ok = true;
     return P;
 }

@@ -117,7 +117,7 @@ int tile_upload_tb(g3cuda_model* m) {
 }
 
 // tiles in flight and lanes per tile for `work` items
-struct TileGeom { const void* fn; size_t smem; int per_sm; long long slots; bool in_smem, meta_in_smem; };
+struct TileGeom { const void* fn; size_t smem; int per_sm; long long slots; bool in_smem, meta_in_smem, use_h; };
 
 template <class T>
 int tile_geom(g3cuda_model* m, TileGeom* g) {
@@ -127,8 +127,12 @@ int tile_geom(g3cuda_model* m, TileGeom* g) {
     g->in_smem = state <= m->smem_optin;
     g->smem = g->in_smem ? state : 0;
     // the plan's tables beside the state, if they fit (else the kernel reads them from global memory)
+    // ... and, for plain values, the hot per-evaluation tables the planner chose (g3t::plan_place_hot)
     const size_t meta_bytes = (size_t)m->targs.meta_n * sizeof(int32_t) + 16;
-    g->meta_in_smem = g->smem + meta_bytes + 64 <= m->smem_optin;
+    const size_t hot_bytes = dual ? 0 : (size_t)m->targs.n_h * cpe * sizeof(double);
+    g->use_h = hot_bytes > 0 && g->smem + hot_bytes + meta_bytes + 4096 <= m->smem_optin;
+    if (g->use_h) g->smem += hot_bytes;
+    g->meta_in_smem = g->smem + meta_bytes + 4096 <= m->smem_optin;
     if (g->meta_in_smem) g->smem += meta_bytes;
     const bool wide = m->tplan.maxn > 4;
     const int threads = (m->targs.W + 1) * 32;
@@ -150,7 +154,7 @@ int launch_tile(g3cuda_model* m, const g3::KArgs& call, long long work, cudaStre
     g3t::TArgs A = m->targs;
     A.par = call.par; A.B = call.B; A.tangent_idx = call.tangent_idx; A.K = call.K;
     A.nll = call.nll; A.comp_out = call.comp; A.grad = call.grad;
-    A.meta_in_smem = g.meta_in_smem;
+    A.meta_in_smem = g.meta_in_smem; A.use_h = g.use_h;
     // few evaluations: spread them over the SMs with partly filled tiles (latency); many: full 32-lane tiles
     const int lpt = (int)std::min<long long>(g3t::NL, std::max<long long>(1, (work + g.slots - 1) / g.slots));
     const long long ntile = (work + lpt - 1) / lpt;
@@ -648,7 +652,7 @@ int g3cuda_model_create(const g3cuda_spec* spec, int device, g3cuda_model** out)
     if (!d_I || !d_R) return bail(fail(G3CUDA_ENOMEM, "device allocation failed"));
 
     // ---- tile kernel: the planner's tables
-    m->tplan = g3t::make_tile_plan(I, R);
+    m->tplan = g3t::make_tile_plan(I, R, 0, 0, 15, m->smem_optin);
     if (m->tplan.ok) {
         g3t::TilePlan& TP = m->tplan;
         auto* d_op = up(TP.obsprop); auto* d_oc = up(TP.obsconst); auto* d_pa = up(TP.pred_active);
@@ -895,6 +899,7 @@ int g3cuda_set_tile_warps(g3cuda_model* m, int warps) {
     int w = warps;
     if (w == 0) w = 15;
     g3t::plan_set_warps(m->tplan, w);        // (the partition into units stays: only their assignment to warps changes)
+    g3t::plan_place_hot(m->tplan, m->smem_optin);
     return tile_upload_tb(m);
 }
 
@@ -903,7 +908,7 @@ int g3cuda_set_tile_partition(g3cuda_model* m, int warps, int seg_rows) {
     if (!m->tile_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", m->tplan.why.c_str());
     CUDA_TRY(cudaSetDevice(m->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    g3t::TilePlan np = g3t::make_tile_plan(m->I.data(), m->R.data(), warps, seg_rows, std::max(warps, 15));
+    g3t::TilePlan np = g3t::make_tile_plan(m->I.data(), m->R.data(), warps, seg_rows, std::max(warps, 15), m->smem_optin);
     if (!np.ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", np.why.c_str());
     const g3t::TArgs old = m->tplan.a;
     np.a.I = old.I; np.a.R = old.R; np.a.obsprop = old.obsprop; np.a.obsconst = old.obsconst;

@@ -30,7 +30,7 @@ def load():
         lib = C.CDLL(build())
         ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
         lib.g3emu_eval.argtypes = [ip, dp, dp, C.c_int64, ip, C.c_int32, dp, dp, dp, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                   C.c_int32, C.c_char_p, C.c_int32, C.c_int32]
+                                   C.c_int32, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]
         lib.g3emu_eval.restype = C.c_int
         lib.g3emu_plan_info.argtypes = [ip, dp, C.c_int32, C.c_int32, ip]
         lib.g3emu_plan_info.restype = C.c_int
@@ -58,7 +58,7 @@ def plan_info(ints, reals, W=0, seg=0):
 
 
 def eval_batch(ints, reals, par, tangent_idx=None, want_comp=False, W=0, seg=0, lanes_per_tile=4, smem_state=True, ncta=2,
-               meta_smem=True):
+               meta_smem=True, hot_tables=True):
     ints = np.ascontiguousarray(ints, dtype=np.int32); reals = np.ascontiguousarray(reals, dtype=np.float64)
     par = np.ascontiguousarray(np.atleast_2d(par), dtype=np.float64)
     B = par.shape[0]
@@ -71,7 +71,7 @@ def eval_batch(ints, reals, par, tangent_idx=None, want_comp=False, W=0, seg=0, 
         grad = np.full((B, K), np.nan)
     why = C.create_string_buffer(256)
     rc = load().g3emu_eval(_ip(ints), _dp(reals), _dp(par), B, None if tidx is None else _ip(tidx), K, _dp(nll), _dp(comp),
-                           _dp(grad), W, seg, lanes_per_tile, int(smem_state), ncta, why, 256, int(meta_smem))
+                           _dp(grad), W, seg, lanes_per_tile, int(smem_state), ncta, why, 256, int(meta_smem), int(hot_tables))
     if rc:
         raise RuntimeError("g3emu_eval: " + why.value.decode())
     return nll, comp, grad

@@ -34,7 +34,7 @@ void run(const TArgs& A, int W, int ncta, size_t smem_doubles) {
 
 extern "C" int g3emu_eval(const int32_t* I, const double* R, const double* par, int64_t B, const int32_t* tidx, int32_t K,
                           double* nll, double* comp, double* grad, int32_t W, int32_t seg, int32_t lanes_per_tile, int32_t smem_state,
-                          int32_t ncta, char* why, int32_t why_len, int32_t meta_smem) {
+                          int32_t ncta, char* why, int32_t why_len, int32_t meta_smem, int32_t use_h) {
     TilePlan P = make_tile_plan(I, R, W, seg);
     if (!P.ok) { if (why) { std::strncpy(why, P.why.c_str(), why_len - 1); why[why_len - 1] = 0; } return -4; }
     TArgs A = P.a;
@@ -47,7 +47,8 @@ extern "C" int g3emu_eval(const int32_t* I, const double* R, const double* par, 
     A.slab_doubles = (long long)((size_t)(A.n_g + (smem_state ? 0 : P.n_s)) * cpe);
     std::vector<double> gws((size_t)A.slab_doubles * ncta + 64, 0.0);
     A.gws = gws.data();
-    const size_t sd = (size_t)P.n_s * cpe + (size_t)(A.meta_n + 1) / 2 + 8;       // state, then the plan's tables
+    A.use_h = !dual && use_h;
+    const size_t sd = (size_t)P.n_s * cpe + (size_t)A.n_h * cpe + (size_t)(A.meta_n + 1) / 2 + 8;       // state, hot tables, the plan's tables
     const bool wide = P.maxn > 4;
     if (!dual) {
         if (wide) { if (smem_state) run<double, 16, true>(A, A.W, ncta, sd); else run<double, 16, false>(A, A.W, ncta, sd); }

@@ -111,3 +111,13 @@ def test_plan_tables_from_global_memory(oracle_lib):
     a = emu.eval_batch(ints, reals, full, want_comp=True, meta_smem=True)
     b = emu.eval_batch(ints, reals, full, want_comp=True, meta_smem=False)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+@pytest.mark.parametrize("name", ["C2", "C4"])
+def test_hot_tables_in_shared_memory_or_in_the_slab(oracle_lib, name):
+    """Growth bands and walpha l^wbeta live in shared memory where the planner found room and in the slab otherwise (always
+    for gradient runs): same values either way."""
+    model, p, ints, reals, full, _ = _setup(name, 2)
+    a = emu.eval_batch(ints, reals, full, want_comp=True, hot_tables=True)
+    b = emu.eval_batch(ints, reals, full, want_comp=True, hot_tables=False)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
