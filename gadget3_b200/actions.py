@@ -162,6 +162,28 @@ def g3a_renewal_normalcv(stock, factor_f=None, mean_f=None, cv_f=None, alpha_f=N
 
 
 # ------------------------------------------------------------------ natural mortality
+class OtherfoodAction(Action):
+    """g3a_otherfood (R/action_renewal.R:276-308): at the start of every step num and wgt of the whole stock are
+    ASSIGNED from formulas -- a prey without dynamics of its own."""
+    kind = "otherfood"
+
+    def __init__(self, stock, num_f, wgt_f):
+        self.stock, self.num_f, self.wgt_f = stock, wrap(num_f), wrap(wgt_f)
+
+
+def g3a_otherfood(stock, num_f=None, wgt_f=None, by_stock=True):
+    """R/action_renewal.R:276-308. Defaults as the reference's: abundance ``of_abund`` by year, scaled by
+    ``of_abund.step`` by step (``of_abund.proj`` outside the model's years), mean weight ``of_meanwgt``. The number is
+    the same in every length group (force_lengthvector: ``n + 0 * stock__midlen``)."""
+    if num_f is None:
+        num_f = g3_parameterized("of_abund", by_year=True, by_stock=by_stock,
+                                 scale=g3_parameterized("of_abund.step", value=1, by_step=True, by_stock=by_stock),
+                                 ifmissing=g3_parameterized("of_abund.proj", by_stock=by_stock))
+    if wgt_f is None:
+        wgt_f = g3_parameterized("of_meanwgt", by_stock=by_stock)
+    return OtherfoodAction(stock, num_f, wgt_f)
+
+
 class MortalityAction(Action):
     kind = "naturalmortality"
 

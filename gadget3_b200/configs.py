@@ -423,10 +423,12 @@ def build_c5(seed=123):
     return model, p
 
 
-def build_mini_andersen(seed=123, suits=False):
+def build_mini_andersen(seed=123, suits=False, otherfood=False):
     """Small 2-area test model: a stock predator with g3_suitability_andersen (predator-length dependent
     suitability), migration on one step only for the predator, renewal, ageing -- exercises the code
-    paths config 5 does not (used by the parity tests, not by bench.py)."""
+    paths config 5 does not (used by the parity tests, not by bench.py). `otherfood`: the predator also eats an
+    otherfood stock (g3a_otherfood, R/action_renewal.R:276-308; one length group, abundance by year x step) with a
+    constant suitability, as in the reference's tests/test-action_predate-predator.R:8,39-45."""
     from . import (g3_suitability_andersen, g3_suitability_andersenfleet, g3_suitability_gamma,
                    g3_suitability_richards, g3_suitability_straightline)
     areas = g3_areas(["a", "b"])
@@ -451,9 +453,16 @@ def build_mini_andersen(seed=123, suits=False):
         g3a_growmature(pred, g3a_grow_impl_bbinom(maxlengthgroupgrowth=2)),
         g3a_renewal_normalcv(prey), g3a_age(prey), g3a_age(pred),
         g3a_migrate(prey, mig), g3a_migrate(pred, mig, run_steps=[2]),
-        g3a_predate(pred, [prey], suitabilities=su, catchability_f=g3a_predate_catchability_predator()),
         g3l_understocking([prey]),
     ]
+    if otherfood:
+        from . import g3a_otherfood, g3_suitability_constant
+        of = g3s_livesonareas(g3s_age(g3_stock("otherfood", [0]), 0, 0), areas)
+        actions += [g3a_otherfood(of),
+                    g3a_predate(pred, [prey, of], suitabilities={"prey": su, "otherfood": g3_suitability_constant(0.02)},
+                                catchability_f=g3a_predate_catchability_predator())]
+    else:
+        actions.append(g3a_predate(pred, [prey], suitabilities=su, catchability_f=g3a_predate_catchability_predator()))
     rng = np.random.default_rng(seed)
     yrs = [2000, 2001, 2002, 2003]
     if suits:
@@ -515,6 +524,11 @@ def build_mini_andersen(seed=123, suits=False):
     p = g3_init_val(p, "and.p1", 1.2, lower=0.5, upper=2)
     p = g3_init_val(p, "and.p3", 0.5, lower=0.1, upper=2)
     p = g3_init_val(p, "and.p4", 0.8, lower=0.1, upper=2)
+    if otherfood:
+        p = g3_init_val(p, "otherfood.of_abund.#", 5e4, lower=1e3, upper=1e6)
+        p = g3_init_val(p, "otherfood.of_abund.step.#", 1.0, lower=0.5, upper=2)
+        p = g3_init_val(p, "otherfood.of_abund.proj", 5e4, optimise=False)
+        p = g3_init_val(p, "otherfood.of_meanwgt", 0.05, lower=0.01, upper=0.2)
     return model, p
 
 
@@ -709,5 +723,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
            "LING": build_ling}

@@ -270,6 +270,16 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             const int idt = A.w_step_idt[step];
             const bool final_step = step == NSTEPS - 1;
             const bool pred_now = A.w_pred_active[t] != 0;
+            // g3a_otherfood (R/action_renewal.R:276-308): number and mean weight assigned from formulas, every step
+            for (int s = 0; s < NS; s++) {
+                const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+                if (St[G3S_OTHERFOOD_OFF] < 0) continue;
+                const int per = St[G3S_NAGE] * St[G3S_L];
+                for (int i = 0; i < St[G3S_NAREA] * per; i++) {
+                    const int32_t* sl = I + St[G3S_OTHERFOOD_OFF] + ((size_t)t * St[G3S_NAREA] + i / per) * 2;
+                    W(A.t_num + St[G3S_CELL_OFF] + i) = SLOT(sl[0]); W(A.t_wgt + St[G3S_CELL_OFF] + i) = SLOT(sl[1]);
+                }
+            }
             if (REPORT && live)         // dstart_<stock>__num/wgt (R/action_report.R:177-213)
                 for (int s = 0; s < NS; s++) {
                     const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;

@@ -54,6 +54,7 @@ struct StockRec {
     int band_percol, bsz;   // one set per column (continuous maturity with an age term) or per stock
     int g_cmat;             // [col][l] g3a_mature_constant ratio (NW - 1 zero rows before, NBX - 1 after), or -1
     int mig_ioff, g_mig, mig_steps;
+    int of_ioff;            // I: g3a_otherfood (num slot, wgt slot) per (step, area), or -1
     int age_enable, age_n_out, s_mv;
     int us_flag;
     int pp_off, pp_n;       // tb: predator-prey pairs acting on this stock, run order
@@ -562,9 +563,21 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 }
             const bool any_catch = xact != 0;
 
+            // ================= g3a_otherfood (R/action_renewal.R:276-308): number and mean weight assigned from formulas
+            bool of_any = false;
+            for (int s = 0; s < NS; s++) {
+                const StockRec& St = Tst[s];
+                if (St.of_ioff < 0) continue;
+                of_any = true;
+                const int per = St.nage * St.L;
+                for (int i = warp; i < St.narea * per; i += W) {
+                    const int32_t* sl = I + St.of_ioff + ((size_t)t * St.narea + i / per) * 2;
+                    SS(A.s_num + St.c0 + i, SLOT(sl[0])); SS(A.s_wgt + St.c0 + i, SLOT(sl[1]));
+                }
+            }
             // ================= g3a_migrate (R/action_migrate.R:17-82): every (age, length) mixes its areas
             {
-                bool mig_any = false;
+                bool mig_any = of_any;      // (one barrier for both)
                 ucnt = 0;
                 for (int s = 0; s < NS; s++) {
                     const StockRec& St = Tst[s];

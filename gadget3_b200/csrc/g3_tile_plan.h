@@ -368,6 +368,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         if (cont) zero_g(r.g_bandr, nset * A.ndt * r.bsz);
         r.g_cmat = (trans && r.mat_kind == G3MAT_CONSTANT) ? take_padded(r.ncol * r.L) : -1;
         r.mig_ioff = St[G3S_MIGRATE_OFF]; r.mig_steps = 0;
+        r.of_ioff = St[G3S_OTHERFOOD_OFF];
         r.g_mig = r.mig_ioff >= 0 ? takeg(A.NSTEPS * r.narea * r.narea) : 0;
         if (r.mig_ioff >= 0)
             for (int sy = 0; sy < A.NSTEPS; sy++) for (int i = 0; i < r.narea * r.narea; i++)

@@ -153,7 +153,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             raise G3Unsupported(f"stock {s.name} must have age and area dimensions")
         stocks.setdefault(s.name, s)
 
-    for k in ("init", "renewal", "naturalmortality", "growmature", "age", "migrate"):
+    for k in ("init", "otherfood", "renewal", "naturalmortality", "growmature", "age", "migrate"):
         for a in by_kind.get(k, []):
             note_stock(a.stock)
     for a in by_kind.get("growmature", []) + by_kind.get("age", []):
@@ -202,7 +202,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         r[K["G3S_CELL_OFF"]] = cell_off
         r[K["G3S_MIDLEN_ROFF"]] = b.alloc_reals(s.midlen)
         r[K["G3S_PLUSDL_ROFF"]] = b.alloc_reals([s.plusdl])
-        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF"):
+        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF", "G3S_OTHERFOOD_OFF"):
             r[K[f]] = -1
         dims = [d for d in s.dims if d != "length"]
         r[K["G3S_DIMORDER"]] = 0 if dims == ["age", "area"] else 1
@@ -238,6 +238,20 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             tab += [low.slot(a.mean_f, c), low.slot(a.stddev_f, c), low.slot(a.factor_f, c),
                     low.slot(a.alpha_f, c), low.slot(a.beta_f, c)]
         srec[name][K["G3S_INIT_OFF"]] = b.alloc_ints(tab)
+
+    # ---- g3a_otherfood (order -1, after the initial conditions in step-id order): (num, wgt) slots per step and area
+    for name, a in one_per_stock("otherfood", "g3a_otherfood").items():
+        s = stocks[name]
+        if inits.get(name) is not None or any(x.stock.name == name for k in ("renewal", "growmature", "age", "migrate", "naturalmortality")
+                                               for x in by_kind.get(k, [])):
+            raise G3Unsupported(f"g3a_otherfood({name}): an otherfood stock has no other actions of its own")
+        tab = []
+        for t in range(NT):
+            for an, aid in s.areas.items():
+                c = Ctx(stock=s, age=s.minage, area=aid, area_name=an, cur_year=tm.start_year + t // S, cur_step=t % S + 1,
+                        cur_step_size=tm.step_lengths[t % S] / 12.0)
+                tab += [low.slot(a.num_f, c), low.slot(a.wgt_f, c)]
+        srec[name][K["G3S_OTHERFOOD_OFF"]] = b.alloc_ints(tab)
 
     if by_kind.get("report_detail"):
         tmpl.add("report_detail", 1.0, optimise=False)

@@ -26,7 +26,7 @@
 #ifndef G3CUDA_SPEC_H
 #define G3CUDA_SPEC_H
 
-#define G3CUDA_SPEC_VERSION 3
+#define G3CUDA_SPEC_VERSION 4
 
 /* ---- header: ints[0..G3H_LEN) ------------------------------------------ */
 #define G3H_VERSION        0
@@ -93,7 +93,9 @@
                                   local cell (same length, age, area) or -1 (R/action_mature.R:100-112) */
 #define G3S_AGE_MAP_OFF   25   /* ints[AGE_N_OUT*NAREA*L]: destination global cell (age maxage+1) of the
                                   oldest column per (area idx, l) or -1 (R/action_age.R:16-20,57-63) */
-#define G3S_LEN           26
+#define G3S_OTHERFOOD_OFF 26   /* g3a_otherfood (R/action_renewal.R:276-308): ints[NT*NAREA*2]: (num slot, wgt slot) per (step t, area idx),
+                                  assigned to every cell of the stock at the start of step t; -1 = not an otherfood stock */
+#define G3S_LEN           27
 
 #define G3MAT_NONE         0
 #define G3MAT_CONSTANT     1   /* g3a_mature_constant (R/action_mature.R:44) */

@@ -368,6 +368,20 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                 }
             }
         }
+        // ---- g3a_otherfood (R/action_renewal.R:276-308): number and mean weight assigned from formulas, every step
+        if (cur_time <= total_steps) for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            if (St[G3S_OTHERFOOD_OFF] < 0) continue;
+            int L = St[G3S_L], A = St[G3S_NAGE], NR = St[G3S_NAREA];
+            for (int r = 0; r < NR; r++) {
+                const int32_t* sl = S.I + St[G3S_OTHERFOOD_OFF] + ((size_t)cur_time * NR + r) * 2;
+                T n = slot(sl[0]), w = slot(sl[1]);
+                for (int a = 0; a < A; a++) for (int l = 0; l < L; l++) {
+                    int c = St[G3S_CELL_OFF] + (r * A + a) * L + l;
+                    num[c] = n; wgt[c] = w;
+                }
+            }
+        }
         // ---- report dstart_* (R/action_report.R:177-213)
         if (rep && cur_time <= total_steps) for (int s = 0; s < NS; s++) {
             const int32_t* St = S.stock(s);

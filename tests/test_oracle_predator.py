@@ -58,6 +58,10 @@ def _expected_consumption(model, p, v, rep, t):
     # the overconsumption block rescales every predator's share by consconv = tp' / avoid_zero(tp) with
     # tp' = B0 * dif_pmin(tp / avoid_zero(B0), 0.95, 1e3) (R/action_predate.R:381-416): the identity for cells with real
     # consumption, a squeeze towards zero for the (near-)empty ones
+    return _overconsumption_squeeze(cons, B0)
+
+
+def _overconsumption_squeeze(cons, B0):
     az = lambda a: (np.maximum(a * 1000.0, 0.0) + np.log1p(np.exp(-np.abs(a * 1000.0)))) / 1000.0
     ratio = cons / az(B0)
     ratio = 0.95 - (np.maximum(1e3 * (0.95 - ratio), 0.0) + np.log1p(np.exp(-np.abs(1e3 * (0.95 - ratio))))) / 1e3
@@ -106,3 +110,74 @@ def test_consumption_scales_with_predator_length_power_m3(mini):
     lo, hi = min(st["pred"].midlen), max(st["pred"].midlen)
     ratio = got_b.sum() / got_a.sum()                           # a length-weighted mean of the predator lengths
     assert lo < ratio < hi
+
+
+# ---------------------------------------------------------------- g3a_otherfood (R/action_renewal.R:276-308)
+@pytest.fixture(scope="module")
+def mini_of(oracle_lib):
+    model, p = CONFIGS["MINI_OTHERFOOD"]()
+    return model, p, Oracle(*model.pack(p))
+
+
+def test_otherfood_is_assigned_every_step(mini_of):
+    """tests/test-action_predate-predator.R:39-45 sets up g3a_otherfood(num_f = of_abund by year x of_abund.step by step,
+    wgt_f = of_meanwgt): the state at the start of EVERY step is the formula's value in every cell, whatever was eaten in
+    the step before (the stock has no dynamics of its own)."""
+    model, p, orc = mini_of
+    v = _values(p)
+    years = [2000, 2001, 2002, 2003]
+    for i, y in enumerate(years):
+        v[p.index(f"otherfood.of_abund.{y}")] = 4e4 + 1e4 * i
+    for s in range(1, 5):
+        v[p.index(f"otherfood.of_abund.step.{s}")] = 0.5 + 0.25 * s
+    v[p.index("otherfood.of_meanwgt")] = 0.07
+    rep = unpack_report(model, orc.report(v))
+    num, wgt = np.asarray(rep["dstart_otherfood__num"]), np.asarray(rep["dstart_otherfood__wgt"])
+    assert num.shape[-1] == 16
+    for t in range(16):
+        want = (4e4 + 1e4 * (t // 4)) * (0.5 + 0.25 * (t % 4 + 1))
+        assert (num[..., t] == want).all(), t
+        assert (wgt[..., t] == 0.07).all()
+    assert np.asarray(rep["detail_otherfood_pred__cons"]).min() > 0          # and it IS eaten, every step, in both areas
+
+
+def _expected_two_prey_consumption(model, p, v, rep, t):
+    """As _expected_consumption, with the otherfood stock in the predator's total suitable biomass (R/action_predate.R:314-333:
+    total_predsuit sums over every prey of the predator) -- returns the consumption of `prey` and of `otherfood`."""
+    st = _stocks(model)
+    g = lambda n: float(v[p.index(n)])
+    dt = 3 / 12.0
+    predlen = np.asarray(st["pred"].midlen, dtype=float)
+    m0, m1, m2, m3 = (g(f"pred.consumption.m{i}") for i in range(4))
+    maxcons = m0 * dt * predlen ** m3
+    hf = g("pred.halffeeding")
+    E = {"prey": g("prey.energycontent"), "otherfood": g("otherfood.energycontent")}
+    S = {k: np.asarray(rep[f"suit_{k}_pred__report"], dtype=float) for k in E}
+    B0 = {k: (np.asarray(rep[f"dstart_{k}__num"]) * np.asarray(rep[f"dstart_{k}__wgt"]))[..., t] for k in E}
+    predN = np.asarray(rep["dstart_pred__num"])[..., t].sum(axis=1)
+    cons = {k: np.zeros_like(B0[k]) for k in E}
+    for r in range(predN.shape[1]):
+        suit = {k: S[k][:, None, :] * E[k] * B0[k][:, :, r][:, :, None] for k in E}
+        ts = sum(suit[k].sum(axis=(0, 1)) for k in E)
+        psi = ts / (hf * dt + ts)
+        for k in E:
+            cons[k][:, :, r] = (suit[k] * (predN[:, r] * maxcons * psi / (E[k] * ts))[None, None, :]).sum(axis=2)
+    return {k: _overconsumption_squeeze(cons[k], B0[k]) for k in E}
+
+
+def test_otherfood_shares_the_predators_appetite(mini_of):
+    model, p, orc = mini_of
+    v = _values(p)
+    rep = unpack_report(model, orc.report(v))
+    for t in (0, 1, 2):
+        want = _expected_two_prey_consumption(model, p, v, rep, t)
+        for k in ("prey", "otherfood"):
+            got = np.asarray(rep[f"detail_{k}_pred__cons"], dtype=float)[..., t]
+            assert want[k].max() > 0
+            assert np.abs(got - want[k]).max() <= 1e-9 * want[k].max(), (k, t)
+    # more other food => less of the prey eaten (same predators, same appetite)
+    v2 = v.copy()
+    for y in (2000, 2001, 2002, 2003):
+        v2[p.index(f"otherfood.of_abund.{y}")] *= 10
+    rep2 = unpack_report(model, orc.report(v2))
+    assert np.asarray(rep2["detail_prey_pred__cons"])[..., 0].sum() < np.asarray(rep["detail_prey_pred__cons"])[..., 0].sum()
