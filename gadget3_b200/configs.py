@@ -6,6 +6,7 @@ the vignettes' own data are unstored R ``rnorm``/``runif`` draws (SURVEY.md sect
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 import numpy as np
 
 from . import (g3_areas, g3_fleet, g3_init_val, g3_parameterized, g3_stock, g3_timeareadata, g3_to_cuda,
@@ -423,7 +424,7 @@ def build_c5(seed=123):
     return model, p
 
 
-def build_mini_andersen(seed=123, suits=False, otherfood=False):
+def build_mini_andersen(seed=123, suits=False, otherfood=False, prefs=False):
     """Small 2-area test model: a stock predator with g3_suitability_andersen (predator-length dependent
     suitability), migration on one step only for the predator, renewal, ageing -- exercises the code
     paths config 5 does not (used by the parity tests, not by bench.py). `otherfood`: the predator also eats an
@@ -451,16 +452,25 @@ def build_mini_andersen(seed=123, suits=False, otherfood=False):
         g3a_naturalmortality(prey), g3a_naturalmortality(pred),
         g3a_growmature(prey, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3)),
         g3a_growmature(pred, g3a_grow_impl_bbinom(maxlengthgroupgrowth=2)),
-        g3a_renewal_normalcv(prey), g3a_age(prey), g3a_age(pred),
-        g3a_migrate(prey, mig), g3a_migrate(pred, mig, run_steps=[2]),
+        g3a_renewal_normalcv(prey), g3a_age(pred),
         g3l_understocking([prey]),
     ]
+    # `prefs`: no ageing of the prey and no migration. Ageing leaves the youngest column exactly empty until the renewal, and
+    # 0^p has no derivative (NaN in the reference's tape as well); migration passes every weight through ratio_add_pop's
+    # avoid_zero, which moves the near-empty cells that biomass^p (p < 1) makes visible -- the re-derivation from the
+    # state at the start of the step (tests/test_oracle_predator.py) would not see that.
+    if not prefs:
+        actions += [g3a_age(prey), g3a_migrate(prey, mig), g3a_migrate(pred, mig, run_steps=[2])]
+    if prefs:       # a suitability that is never exactly zero: 0^p has no derivative (NaN in the reference's tape as well)
+        su = g3_suitability_exponentiall50(g3_parameterized("pl.alpha", value=0.1), g3_parameterized("pl.l50", value=25))
     if otherfood:
         from . import g3a_otherfood, g3_suitability_constant
         of = g3s_livesonareas(g3s_age(g3_stock("otherfood", [0]), 0, 0), areas)
         actions += [g3a_otherfood(of),
                     g3a_predate(pred, [prey, of], suitabilities={"prey": su, "otherfood": g3_suitability_constant(0.02)},
-                                catchability_f=g3a_predate_catchability_predator())]
+                                catchability_f=g3a_predate_catchability_predator(
+                                    # `prefs`: prey_preferences other than 1 (R/action_predate.R:208,220-225), one by prey name
+                                    prey_preferences={"prey": g3_parameterized("pref.prey", value=0.9), "otherfood": 1.3} if prefs else 1))]
     else:
         actions.append(g3a_predate(pred, [prey], suitabilities=su, catchability_f=g3a_predate_catchability_predator()))
     rng = np.random.default_rng(seed)
@@ -502,7 +512,8 @@ def build_mini_andersen(seed=123, suits=False, otherfood=False):
     p = g3_init_val(p, "recage", 1, optimise=False)
     p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
     p = g3_init_val(p, "*.wbeta", 3, optimise=False)
-    p = g3_init_val(p, "*.migrate.*", 0.3, lower=0, upper=0.7)
+    if not prefs:
+        p = g3_init_val(p, "*.migrate.*", 0.3, lower=0, upper=0.7)
     p = g3_init_val(p, "*.consumption.m0", 1e-5, optimise=False)
     p = g3_init_val(p, "*.consumption.m3", 1.5, optimise=False)
     p = g3_init_val(p, "*.halffeeding", 1e3, lower=10, upper=1e5)
@@ -521,14 +532,109 @@ def build_mini_andersen(seed=123, suits=False, otherfood=False):
         p = g3_init_val(p, "*.andersen.p3_exp", 0.1, lower=-1, upper=1)
         p = g3_init_val(p, "*.andersen.p4_exp", 0.1, lower=-1, upper=1)
         return model, p
-    p = g3_init_val(p, "and.p1", 1.2, lower=0.5, upper=2)
-    p = g3_init_val(p, "and.p3", 0.5, lower=0.1, upper=2)
-    p = g3_init_val(p, "and.p4", 0.8, lower=0.1, upper=2)
+    if prefs:
+        p = g3_init_val(p, "pl.alpha", 0.1, lower=0.05, upper=0.3)
+        p = g3_init_val(p, "pl.l50", 25, lower=15, upper=35)
+    else:
+        p = g3_init_val(p, "and.p1", 1.2, lower=0.5, upper=2)
+        p = g3_init_val(p, "and.p3", 0.5, lower=0.1, upper=2)
+        p = g3_init_val(p, "and.p4", 0.8, lower=0.1, upper=2)
     if otherfood:
         p = g3_init_val(p, "otherfood.of_abund.#", 5e4, lower=1e3, upper=1e6)
         p = g3_init_val(p, "otherfood.of_abund.step.#", 1.0, lower=0.5, upper=2)
         p = g3_init_val(p, "otherfood.of_abund.proj", 5e4, optimise=False)
         p = g3_init_val(p, "otherfood.of_meanwgt", 0.05, lower=0.01, upper=0.2)
+    if prefs:
+        p = g3_init_val(p, "pref.prey", 0.9, lower=0.7, upper=1.2)
+    return model, p
+
+
+def build_mini_migrate(seed=123):
+    """The set-up of the reference's migration test (tests/test-action_migrate.R:6-52): a stock on areas a, c, d of
+    (a, b, c, d) -- it does not live in b --, ages 3-7, a spring migration d -> a on step 2 and a winter migration
+    a -> c, c -> d on step 4 (two g3a_migrate actions), nothing else moving the fish. Initial numbers and weights differ
+    by area (abundance factor and walpha by area) so that ratio_add_pop has something to mix."""
+    allareas = g3_areas(["a", "b", "c", "d"])
+    areas = OrderedDict((k, allareas[k]) for k in ("a", "c", "d"))
+    st = g3s_livesonareas(g3s_age(g3_stock("stock_acd", range(10, 50, 10)), 3, 7), areas)
+    gp = g3_parameterized
+
+    def spring(src, dst):
+        return gp("migrate_spring", value=0.6324555320336759) if (src, dst) == ("d", "a") else 0
+
+    def winter(src, dst):
+        return gp("migrate_winter", value=0.7745966692414834) if (src, dst) in (("a", "c"), ("c", "d")) else 0
+
+    actions = [
+        g3a_time(2000, 2004, [3, 3, 3, 3]),
+        g3a_initialconditions_normalparam(st, factor_f=gp("init.fac", by_stock=True, by_area=True, value=100),
+                                          mean_f=gp("init.mean", by_stock=True, value=25),
+                                          stddev_f=gp("init.sd", by_stock=True, value=10),
+                                          alpha_f=gp("walpha", by_stock=True, by_area=True, value=1e-5),
+                                          beta_f=gp("wbeta", by_stock=True, value=3)),
+        g3a_migrate(st, spring, run_steps=[2]),
+        g3a_migrate(st, winter, run_steps=[4]),
+    ]
+    rng = np.random.default_rng(seed)
+    yrs = [2000, 2001, 2002, 2003, 2004]
+    si = dict(year=[y for y in yrs for _ in range(3)], step=[3] * 15, area=["a", "c", "d"] * 5,
+              number=list(rng.uniform(1e2, 1e3, 15)))
+    actions.append(g3l_abundancedistribution("si_acd", si, stocks=[st], area_group=areas,
+                                             function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    actions += [g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    for i, a in enumerate(("a", "c", "d")):
+        p = g3_init_val(p, f"stock_acd.init.fac.{a}", 100.0 * (i + 1), lower=10, upper=1000)
+        p = g3_init_val(p, f"stock_acd.walpha.{a}", 1e-5 * (i + 1), optimise=False)
+    p = g3_init_val(p, "stock_acd.init.mean", 25, lower=15, upper=35)
+    p = g3_init_val(p, "stock_acd.init.sd", 10, optimise=False)
+    p = g3_init_val(p, "stock_acd.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "migrate_spring", 0.6324555320336759, lower=0.1, upper=0.8)
+    p = g3_init_val(p, "migrate_winter", 0.7745966692414834, lower=0.1, upper=0.8)
+    return model, p
+
+
+READER_MATRIX = np.array([[0.5, 0.25, 0.25, 0, 0], [0, 0.75, 0.25, 0, 0], [0, 0, 1, 0, 0], [0, 0, 0, 1, 0], [0, 0, 0, 0, 1.0]])
+
+
+def build_mini_transform(seed=123, reader=READER_MATRIX):
+    """The set-up of the reference's transform_fs test (tests/test-likelihood_distribution.R:143-232): a stock with five
+    length groups and ages 1-5 on two areas, and four abundance distributions by length x age over the same observations --
+    `nt` plain, `wt` with an age-reading error matrix (age 1 smeared over three age groups, age 2 over two: the test's second
+    parameter set), `wtperstock` the same matrix given by stock name, `len` with the length transform diag(10 * midlen).
+    Here the fish also die and grow, so the four model arrays are collected from a state that moves."""
+    areas = g3_areas(["1", "2"])
+    st = g3s_livesonareas(g3s_age(g3_stock("prey_a", range(1, 6)), 1, 5), areas)
+    rng = np.random.default_rng(seed)
+    obs = dict(year=[y for y in (2000, 2001) for _ in range(25)], length=[l for _ in range(2) for l in range(1, 6) for _ in range(5)],
+               age=[a for _ in range(10) for a in range(1, 6)], number=list(rng.uniform(0.0, 1.0, 50) * 1e4))
+    ss = g3l_distribution_sumofsquares
+    actions = [
+        g3a_time(2000, 2001, [6, 6]),
+        g3a_initialconditions_normalcv(st),
+        g3a_naturalmortality(st),
+        g3a_growmature(st, g3a_grow_impl_bbinom(maxlengthgroupgrowth=2)),
+        g3l_abundancedistribution("nt", obs, stocks=[st], function_f=ss()),
+        g3l_abundancedistribution("wt", obs, stocks=[st], function_f=ss(), transform_fs={"age": reader}),
+        g3l_abundancedistribution("wtperstock", obs, stocks=[st], function_f=ss(), transform_fs={"age": {"prey_a": reader}}),
+        g3l_abundancedistribution("len", obs, stocks=[st], function_f=ss(), transform_fs={"length": np.diag(10.0 * np.asarray(st.midlen))}),
+    ]
+    actions += [g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "*.Linf", 6, lower=4, upper=9)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.05, upper=1)
+    p = g3_init_val(p, "*.t0", -0.5, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.3, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, lower=0.01, upper=1)
+    p = g3_init_val(p, "init.F", 0.3, lower=0.1, upper=1)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-2, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.bbin", 10, lower=1, upper=100)
     return model, p
 
 
@@ -723,5 +829,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets,
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform,
            "LING": build_ling}

@@ -83,10 +83,17 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             const bool spred = P[G3P_KIND] == G3PRED_STOCK;
             const int32_t* Pp = I + I[G3H_STOCK_OFF] + (spred ? P[G3P_STOCK] : 0) * G3S_LEN;
             const int PL = spred ? Pp[G3S_L] : 1, L = Ps[G3S_L];
+            // prey_preference p (R/action_predate.R:220-225): (S E B)^p = S^p E^p B^p; the table then holds S^p E^(p-1) -- x E x B^p
+            // in the predator's total, x B^p in the consumption (one E cancels against cons' 1 / E)
+            const bool pref = Q[G3PP_PREF] >= 0;
+            const T pp_ = pref ? SLOT(Q[G3PP_PREF]) : T(1.0), ef = pref ? xpow(SLOT(Q[G3PP_ENERGY]), pp_ - 1.0) : T(1.0);
             for (int pl = 0; pl < PL; pl++)
-                for (int l = 0; l < L; l++)
-                    W(A.t_suitq[q] + pl * L + l) = suitability_of<T>(Q[G3PP_SUIT_KIND], sp, R[Ps[G3S_MIDLEN_ROFF] + l],
+                for (int l = 0; l < L; l++) {
+                    const T sv = suitability_of<T>(Q[G3PP_SUIT_KIND], sp, R[Ps[G3S_MIDLEN_ROFF] + l],
                         spred && Q[G3PP_SUIT_KIND] != G3SUIT_ANDERSENFLEET ? R[Pp[G3S_MIDLEN_ROFF] + pl] : R[Ps[G3S_MIDLEN_ROFF] + L - 1]);
+                    if (REPORT && live && pref) A.report[A.rep_pp[q] + pl * L + l] = val(sv);       // suit_<prey>_<pred>__report is S itself
+                    W(A.t_suitq[q] + pl * L + l) = pref ? xpow(sv, pp_) * ef : sv;
+                }
         }
         // stock predators: maximum consumption per predator length without the step length,
         // m0 exp(m1 T - m2 T^3) l^m3 (R/action_predate.R:190-205)
@@ -361,7 +368,9 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                 T cs(0.0);
                                 for (int l = 0; l < L; l++) {
                                     const int cell = c0 + col * L + l;
-                                    cs = cs + W(A.t_suitq[q] + pl * L + l) * (by_number ? W(A.t_num + cell) : W(A.t_num + cell) * W(A.t_wgt + cell));
+                                    T bm = by_number ? W(A.t_num + cell) : W(A.t_num + cell) * W(A.t_wgt + cell);
+                                    if (Q[G3PP_PREF] >= 0) bm = xpow(bm, SLOT(Q[G3PP_PREF]));
+                                    cs = cs + W(A.t_suitq[q] + pl * L + l) * bm;
                                 }
                                 if (spred) W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) = W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) + cs * energy;
                                 else EOT(ts) = EOT(ts) + cs;
@@ -475,7 +484,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                         for (int pl = 0; pl < kpl[k]; pl++)
                                             cf = cf + ws[ksuit[k] + (unsigned)(pl * L) * NTH + lN] * W(kpts[k] + tsk[k] * kpl[k] + pl);
                                     }
-                                    tp = tp + cf * B0;
+                                    const int pfs = kpl[k] ? I[I[G3H_PP_OFF] + kq[k] * G3PP_LEN + G3PP_PREF] : -1;
+                                    tp = tp + cf * (pfs >= 0 ? xpow(B0, SLOT(pfs)) : B0);        // biomass^prey_preference
                                     if (catch_now) {
 #pragma unroll
                                         for (int x = 0; x < MAXX; x++) if ((kx[k] >> x) & 1) fx[x] = fx[x] + cf;
@@ -506,6 +516,11 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                             cf = T(0.0);
                                             for (int pl = 0; pl < kpl[k]; pl++)
                                                 cf = cf + ws[ksuit[k] + (unsigned)(pl * L) * NTH + lN] * W(kpts[k] + tsk[k] * kpl[k] + pl);
+                                            const int pfs = I[I[G3H_PP_OFF] + kq[k] * G3PP_LEN + G3PP_PREF];
+                                            if (pfs >= 0) {
+                                                A.report[base + (size_t)NT * ncs + ci] = val(cf * xpow(B0, SLOT(pfs)) * (1.0 / avoid_zero(tp) * tpn));
+                                                continue;
+                                            }
                                         }
                                         A.report[base + (size_t)NT * ncs + ci] = val(cf * cc);
                                     }
@@ -855,6 +870,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
                 const int n = I[I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN + G3S_L] *
                               (P[G3P_KIND] == G3PRED_STOCK ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1);
+                if (Q[G3PP_PREF] >= 0) continue;        // (written when the table was filled: the table is not S itself)
                 for (int i = 0; i < n; i++) A.report[A.rep_pp[q] + i] = val(W(A.t_suitq[q] + i));
             }
         if (tile_t == 0) {

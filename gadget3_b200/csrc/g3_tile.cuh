@@ -76,7 +76,7 @@ struct UnitRec {
     int g_usp;              // (sum tp, sum tp') of this unit at this step's predation
 };
 struct PairRec {
-    int pred, prey, suit_kind, suit_ioff, energy_slot, pred_kind, pred_stock, PL;
+    int pred, prey, suit_kind, suit_ioff, energy_slot, pref_slot, pred_kind, pred_stock, PL;
     int g_suit;             // [PL][L]
     int g_part;             // [prey unit][PL] partial suitable biomass
     int cxmask;             // bit j: feeds the prey stock's j-th catch collect vector
@@ -345,7 +345,14 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 #pragma unroll
                 for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
                 const double plen = spred && Q.suit_kind != G3SUIT_ANDERSENFLEET ? R[Tst[Q.pred_stock].midlen_roff + pl] : pml[Ps.L - 1];
-                for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, suitability_of<T>(Q.suit_kind, sp, pml[l], plen));
+                if (Q.pref_slot < 0)
+                    for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, suitability_of<T>(Q.suit_kind, sp, pml[l], plen));
+                else {
+                    // prey_preference p (R/action_predate.R:220-225): (S E B)^p = S^p E^p B^p; the table holds S^p E^(p-1) -- x E x B^p
+                    // in the predator's total, x B^p in the consumption (where one E cancels against cons' 1 / E)
+                    const T p = SLOT(Q.pref_slot), ef = xpow(SLOT(Q.energy_slot), p - 1.0);
+                    for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, xpow(suitability_of<T>(Q.suit_kind, sp, pml[l], plen), p) * ef);
+                }
             }
         }
         // stock predators: maximum consumption per predator length without the step length,
@@ -648,7 +655,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             for (int u = 0; u < 4; u++) cs[u] = T(0.0);
                             for (int r = 0; r < U.len; r++) {
                                 const T n = S(A.s_num + c_lo + r);
-                                const T bm = by_number ? n : n * S(A.s_wgt + c_lo + r);
+                                T bm = by_number ? n : n * S(A.s_wgt + c_lo + r);
+                                if (Q.pref_slot >= 0) bm = xpow(bm, SLOT(Q.pref_slot));
 #pragma unroll
                                 for (int u = 0; u < 4; u++)
                                     cs[u] = cs[u] + G(Q.g_suit + min(pl0 + u, Q.PL - 1) * L + U.lo + r) * bm;
@@ -816,6 +824,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             const int ts = tb[Q.tsid_off + Cl.ridx];
                             if (ts < 0) continue;
                             cfac(Q, ts, r0, cf);
+                            if (Q.pref_slot >= 0) {             // biomass^prey_preference for this predator
+                                const T p = SLOT(Q.pref_slot);
+#pragma unroll
+                                for (int b = 0; b < NB; b++) tp[b] = tp[b] + cf[b] * xpow(B0[b], p);
+                                continue;
+                            }
 #pragma unroll
                             for (int b = 0; b < NB; b++) tp[b] = tp[b] + cf[b] * B0[b];
                         }

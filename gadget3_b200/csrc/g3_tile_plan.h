@@ -540,7 +540,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         const StockRec& Ps = P.st[Q[G3PP_PREY]];
         PairRec& r = P.pp[q];
         r.pred = Q[G3PP_PRED]; r.prey = Q[G3PP_PREY]; r.suit_kind = Q[G3PP_SUIT_KIND]; r.suit_ioff = Q[G3PP_SUIT_OFF];
-        r.energy_slot = Q[G3PP_ENERGY]; r.pred_kind = Pr.kind; r.pred_stock = Pr.kind == G3PRED_STOCK ? Pr.stock : -1;
+        r.energy_slot = Q[G3PP_ENERGY]; r.pref_slot = Q[G3PP_PREF]; r.pred_kind = Pr.kind; r.pred_stock = Pr.kind == G3PRED_STOCK ? Pr.stock : -1;
         r.PL = Pr.kind == G3PRED_STOCK ? P.st[Pr.stock].L : 1;
         const int sk = r.suit_kind;
         if (sk == G3SUIT_ANDERSEN || sk == G3SUIT_EXPONENTIAL || sk == G3SUIT_RICHARDS) {

@@ -200,12 +200,39 @@ def _is_num(x):
         return False
 
 
+def _check_transforms(transform_fs, stocks):
+    """transform_fs (R/likelihood_distribution.R:184,298-347): 'length' -- the collected vector of a stock is multiplied by an
+    L x L matrix before it is reshaped onto the observation's length groups; 'age' -- what is collected at age `preage`
+    lands in age `age` with the factor matrix[preage_idx, age_idx] (an age-reading error matrix). One matrix, or one by
+    stock name (list_to_stock_switch; a stock without an entry is not transformed). The matrices are DATA here: they
+    are folded into the gather coefficients at lowering time; a matrix of parameters (g3_param_array) is refused.
+    Returns {stock name: {'length': ndarray | None, 'age': ndarray | None}}."""
+    out = {s.name: {"length": None, "age": None} for s in stocks}
+    for dim, tf in (transform_fs or {}).items():
+        if dim not in ("length", "age"):
+            raise G3Unsupported(f"Transforms for {dim} dimensions not supported yet")
+        for s in stocks:
+            m = tf.get(s.name) if isinstance(tf, dict) else tf
+            if m is None:
+                continue
+            try:
+                m = np.asarray(m, dtype=float)
+            except (TypeError, ValueError):
+                raise G3Unsupported("g3l_distribution(transform_fs = ...): only constant matrices are supported") from None
+            n = s.L if dim == "length" else s.nage
+            if m.shape != (n, n):
+                raise ValueError(f"transform_fs${dim} for {s.name} must be a {n} x {n} matrix, got {m.shape}")
+            out[s.name][dim] = m
+    return out
+
+
 class DistributionAction(Action):
     kind = "distribution"
 
     def __init__(self, nll_name, obs_data, fleets, stocks, function_f, area_group, report, nll_breakdown,
-                 weight, missing_val):
+                 weight, missing_val, transform_fs=None):
         self.fleets, self.stocks = list(fleets), list(stocks)
+        self.transform_fs = _check_transforms(transform_fs, self.stocks)
         self.function_f = function_f
         self.report, self.nll_breakdown = report, nll_breakdown
         # R/likelihood_distribution.R:266-271
@@ -219,14 +246,12 @@ def g3l_distribution(nll_name, obs_data, fleets=(), stocks=(), function_f=None, 
                      report=False, nll_breakdown=False, weight=None, missing_val=0, transform_fs=None,
                      predators=()):
     """R/likelihood_distribution.R:177-440."""
-    if transform_fs:
-        raise G3Unsupported("g3l_distribution(transform_fs = ...)")
     if predators:
         raise G3Unsupported("g3l_distribution(predators = ...)")
     if not isinstance(function_f, _DistFn):
         raise G3Unsupported("g3l_distribution: unsupported function_f")
     return DistributionAction(nll_name, obs_data, fleets, stocks, function_f, area_group, report,
-                              nll_breakdown, weight, missing_val)
+                              nll_breakdown, weight, missing_val, transform_fs)
 
 
 def g3l_catchdistribution(nll_name, obs_data, fleets=(), stocks=(), function_f=None, **kw):

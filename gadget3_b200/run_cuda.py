@@ -256,13 +256,18 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
     if by_kind.get("report_detail"):
         tmpl.add("report_detail", 1.0, optimise=False)
 
-    # ---- migration (order 2)
-    for name, a in one_per_stock("migrate", "g3a_migrate").items():
-        s = stocks[name]
+    # ---- migration (order 2). Several g3a_migrate actions on one stock are allowed when they run on different steps
+    # (tests/test-action_migrate.R:41-52: a spring and a winter migration): the table is per step.
+    mig_tabs = {}
+    for a in by_kind.get("migrate", []):
+        s = stocks[a.stock.name]
         anames = list(s.areas.keys())
         NR = len(anames)
-        run_steps = range(1, S + 1) if a.run_steps is None else [int(x) for x in a.run_steps]
-        tab = [-1] * (S * NR * NR)
+        tab, taken = mig_tabs.setdefault(s.name, ([-1] * (S * NR * NR), set()))
+        run_steps = list(range(1, S + 1)) if a.run_steps is None else [int(x) for x in a.run_steps]
+        if taken & set(run_steps):
+            raise G3Unsupported(f"more than one g3a_migrate action for {s.name} on step(s) {sorted(taken & set(run_steps))}")
+        taken |= set(run_steps)
         for st in run_steps:
             for di, dn in enumerate(anames):
                 for si, sn in enumerate(anames):
@@ -273,6 +278,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                         continue
                     c = Ctx(stock=s, area=s.areas[sn], area_name=sn, cur_step=st)
                     tab[((st - 1) * NR + di) * NR + si] = low.slot(wrap(e), c)
+    for name, (tab, _) in mig_tabs.items():
         srec[name][K["G3S_MIGRATE_OFF"]] = b.alloc_ints(tab)
 
     # ---- predation (order 3): predators by name, prey by name
@@ -299,9 +305,6 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             # g3a_predate_catchability_predator (R/action_predate.R:207-238) for a stock predator
             if ps.lengthgroups is None or ps.name not in sidx:
                 raise G3Unsupported("g3a_predate_catchability_predator needs a stock predator with length groups")
-            pref = cat.kw["prey_preferences"]
-            if not (isinstance(pref, (int, float)) and pref == 1):
-                raise G3Unsupported("g3a_predate_catchability_predator: prey_preferences other than 1")
             pr[K["G3P_KIND"]] = K["G3PRED_STOCK"]
             pr[K["G3P_E_ROFF"]] = -1
             pr[K["G3P_STOCK"]] = sidx[ps.name]
@@ -326,6 +329,15 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             q[K["G3PP_ENERGY"]] = q[K["G3PP_PREF"]] = -1
             if cat.kind == "predator":
                 q[K["G3PP_ENERGY"]] = low.slot(cat.kw["energycontent"], c)
+                # prey_preferences: one value / formula, or a list by prey stock name (list_to_stock_switch,
+                # R/action_predate.R:208,225); the exponent 1 is not lowered at all
+                pref = cat.kw["prey_preferences"]
+                if isinstance(pref, dict):
+                    if prey.name not in pref:
+                        raise G3Unsupported(f"g3a_predate_catchability_predator: no prey_preferences entry for {prey.name}")
+                    pref = pref[prey.name]
+                if not (isinstance(pref, (int, float)) and pref == 1):
+                    q[K["G3PP_PREF"]] = low.slot(wrap(pref), c)
             elif cat.kind == "effortfleet":
                 cf = cat.kw["catchability_fs"]
                 q[K["G3PP_ENERGY"]] = low.slot(wrap(cf[prey.name] if isinstance(cf, dict) else cf), c)
@@ -472,6 +484,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             key = ("abund", ld.unit, tuple(sidx[p.name] for p in st_sorted))
         # destination of every cell
         entries = [[] for _ in range(ld.n_dest)]
+        multi_dest = False          # an age transform sends one cell to several destinations: CSR mode whatever n_bins
         cell_dest = [-1] * ncell
         cell_coef = [0.0] * ncell
         for p in st_sorted:
@@ -481,6 +494,12 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                 if sg < 0:
                     continue
             M = _lgmatrix(p, ld.lenstock)
+            # transform_fs (R/likelihood_distribution.R:298-347), constant matrices folded into the gather: the length
+            # matrix acts on the collected vector before the reshape (lgmatrix %*% (T %*% x)); what is collected at age
+            # `preage` lands in every age `a` with the factor Tage[preage_idx, a_idx]
+            Tl, Ta = a.transform_fs[p.name]["length"], a.transform_fs[p.name]["age"]
+            if Tl is not None:
+                M = (np.eye(p.L) if M is None else np.asarray(M, dtype=float)) @ Tl
             for ri, an, aid, ai, ag in columns(p):
                 if ld.area_group is not None:
                     hit = [i for i, v in enumerate(ld.area_group.values()) if int(v) == aid]
@@ -489,21 +508,28 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                     areag = hit[0]
                 else:
                     areag = 0
-                if ld.minage is not None:
-                    if not (ld.minage <= ag <= ld.maxage):
-                        continue
-                    ageg = ag - ld.minage
+                # (destination age group, factor) of what this column holds
+                if Ta is None:
+                    dests = [(ag, 1.0)]
                 else:
-                    ageg = 0
-                for l in range(p.L):
-                    cell = p._cell_off + (ri * p.nage + ai) * p.L + l
-                    for bi in range(ld.n_bins):
-                        coef = (1.0 if bi == l else 0.0) if M is None else M[bi, l]
-                        if coef != 0.0:
-                            e = ld.dest(areag, sg, ageg, bi)
-                            entries[e].append((cell, coef))
-                            cell_dest[cell], cell_coef[cell] = e, coef
-        mode = 1 if ld.n_bins == 1 else 0
+                    multi_dest = True
+                    dests = [(p.minage + k, float(Ta[ai, k])) for k in range(p.nage) if Ta[ai, k] != 0.0]
+                for dag, af in dests:
+                    if ld.minage is not None:
+                        if not (ld.minage <= dag <= ld.maxage):
+                            continue
+                        ageg = dag - ld.minage
+                    else:
+                        ageg = 0
+                    for l in range(p.L):
+                        cell = p._cell_off + (ri * p.nage + ai) * p.L + l
+                        for bi in range(ld.n_bins):
+                            coef = ((1.0 if bi == l else 0.0) if M is None else M[bi, l]) * af
+                            if coef != 0.0:
+                                e = ld.dest(areag, sg, ageg, bi)
+                                entries[e].append((cell, coef))
+                                cell_dest[cell], cell_coef[cell] = e, coef
+        mode = 1 if (ld.n_bins == 1 and not multi_dest) else 0
         q[K["G3C_MODE"]] = mode
         q[K["G3C_N_DEST"]], q[K["G3C_N_BINS"]] = ld.n_dest, ld.n_bins
         q[K["G3C_N_SLICES"]], q[K["G3C_N_AREAG"]] = ld.n_slices, ld.n_areag

@@ -448,7 +448,9 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                             T colsum(0.0);
                             for (int l = 0; l < L; l++) {
                                 int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
-                                colsum = colsum + suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSENFLEET ? midlen[L - 1] : pmid[pl], ok) * energy * num[c] * wgt[c];
+                                T su = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSENFLEET ? midlen[L - 1] : pmid[pl], ok) * energy * num[c] * wgt[c];
+                                if (Q[G3PP_PREF] >= 0) su = xpow(su, slot(Q[G3PP_PREF]));        // (...)^prey_preference, R/action_predate.R:220-225
+                                colsum = colsum + su;
                             }
                             ptotsuit[Q[G3PP_PRED]][pr * PL + pl] = ptotsuit[Q[G3PP_PRED]][pr * PL + pl] + colsum;
                         }
@@ -502,6 +504,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                             for (int a = 0; a < St[G3S_NAGE]; a++) for (int l = 0; l < L; l++) {
                                 int c = St[G3S_CELL_OFF] + (r * St[G3S_NAGE] + a) * L + l;
                                 T su = suitability<T>(Q[G3PP_SUIT_KIND], ss, slot, midlen[l], Q[G3PP_SUIT_KIND] == G3SUIT_ANDERSENFLEET ? midlen[L - 1] : pmid[pl], ok) * energy * num[c] * wgt[c];
+                                if (Q[G3PP_PREF] >= 0) su = xpow(su, slot(Q[G3PP_PREF]));
                                 T cn = (predn * maxcons * feeding * su) / (energy * ts);
                                 cons[q][c] = cons[q][c] + cn;
                                 totalpredate[c] = totalpredate[c] + cn;

@@ -241,3 +241,37 @@ def test_mature_continuous_age_term_hand_value(oracle_lib):
             continue            # (the renewal lands in age 1 at step 1)
         # the first step of the run: no landings (they come at step 2), no ageing (step 4)
         assert tot[ai, 1] / tot[ai, 0] == pytest.approx(1.0 - share, rel=1e-9), age
+
+
+def test_migrate_twelve_step_recurrence(oracle_lib):
+    """tests/test-action_migrate.R:63-102: a stock on areas a, c, d (not b) with a spring migration d -> a (0.4 = the
+    parameter squared) on step 2 and a winter migration c -> d, a -> c (0.6) on step 4; the test applies the moves by hand,
+    numbers and ratio_add_pop weights, step after step, and compares every step with the model. Same recurrence here on the
+    oracle's state at the start of the following step, for every (length, age) -- the reference checks one pair and that the
+    ages agree."""
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["MINI_MIGRATE"]()
+    rep = unpack_report(model, Oracle(*model.pack(p)).report(p.values()))
+    num, wgt = np.asarray(rep["dstart_stock_acd__num"]), np.asarray(rep["dstart_stock_acd__wgt"])     # [length][age][area a,c,d][t]
+    assert num.shape == (4, 5, 3, 20)
+    rap = lambda ov, oa, nv, na: (ov * oa + nv * na) / (oa + na)
+    a, c, d = 0, 1, 2
+    en, ew = num[..., 0].copy(), wgt[..., 0].copy()
+    assert en.min() > 0 and len({float(x) for x in ew[0, 0]}) == 3          # weights differ by area: the mixing is visible
+    for t in range(19):
+        if t % 4 == 1:          # spring
+            ew[:, :, a] = rap(ew[:, :, a], en[:, :, a], ew[:, :, d], en[:, :, d] * 0.4)
+            en[:, :, a] = en[:, :, a] + en[:, :, d] * 0.4
+            en[:, :, d] = en[:, :, d] - en[:, :, d] * 0.4
+        if t % 4 == 3:          # winter: c -> d, then a -> c; nothing goes a -> d directly
+            ew[:, :, d] = rap(ew[:, :, d], en[:, :, d], ew[:, :, c], en[:, :, c] * 0.6)
+            en[:, :, d] = en[:, :, d] + en[:, :, c] * 0.6
+            en[:, :, c] = en[:, :, c] - en[:, :, c] * 0.6
+            ew[:, :, c] = rap(ew[:, :, c], en[:, :, c], ew[:, :, a], en[:, :, a] * 0.6)
+            en[:, :, c] = en[:, :, c] + en[:, :, a] * 0.6
+            en[:, :, a] = en[:, :, a] - en[:, :, a] * 0.6
+        np.testing.assert_allclose(num[..., t + 1], en, rtol=1e-12, err_msg=f"numbers, t = {t}")
+        np.testing.assert_allclose(wgt[..., t + 1], ew, rtol=1e-12, err_msg=f"weights, t = {t}")
+    assert np.abs(num[..., 19] - num[..., 0]).max() > 1.0       # (the fish did move)

@@ -115,3 +115,41 @@ def test_stratified_sumofsquares_rederived_from_the_reported_model_array(oracle_
         assert abs(want - plain) > 1e-3 * abs(want)
         checked += 1
     assert checked == 34
+
+
+def test_transform_fs_age_reading_error_and_length_matrix(oracle_lib):
+    """tests/test-likelihood_distribution.R:143-232 (g3l_distribution:transform_fs): `wt` collects through an age-reading error
+    matrix, `nt` does not; the test applies the matrix by hand to nt -- wt[, dest age, ] = sum_k nt[, k, ] * m[k, dest age] --
+    for the identity and for 'age 1 smeared over three groups, age 2 over two', checks that a matrix given per stock is the
+    same thing, and that the length transform diag(10 * midlen) scales every length group of nt."""
+    from gadget3_b200 import configs
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    for m, msg in ((np.eye(5), "identity matrix"), (configs.READER_MATRIX, "age1, age2 smeared")):
+        model, p = configs.build_mini_transform(reader=m)
+        rep = unpack_report(model, Oracle(*model.pack(p)).report(p.values()))
+        nt = np.asarray(rep["adist_sumofsquares_nt_model__num"])                 # [time][area][stock][age][length]
+        wt = np.asarray(rep["adist_sumofsquares_wt_model__num"])
+        assert nt.shape == (2, 1, 1, 5, 5) and nt.min() > 0
+        np.testing.assert_array_equal(wt, np.asarray(rep["adist_sumofsquares_wtperstock_model__num"]), err_msg=msg)
+        for dest in range(5):
+            want = sum(nt[:, :, :, k, :] * m[k, dest] for k in range(5))
+            np.testing.assert_allclose(wt[:, :, :, dest, :], want, rtol=1e-13, err_msg=f"age{dest + 1}: {msg}")
+        if m is not configs.READER_MATRIX:
+            np.testing.assert_array_equal(wt, nt)
+        else:
+            assert np.abs(wt - nt).max() > 1e-3 * nt.max()
+        midlen = np.array([1.5, 2.5, 3.5, 4.5, 5.5])
+        np.testing.assert_allclose(np.asarray(rep["adist_sumofsquares_len_model__num"]), nt * (10 * midlen), rtol=1e-13,
+                                   err_msg="length vector applied")
+
+
+def test_transform_fs_refusals():
+    """A matrix of parameters (g3_param_array) cannot be folded into the gather at lowering time; other dimensions are the
+    reference's own error (R/likelihood_distribution.R:326)."""
+    from gadget3_b200 import configs
+    from gadget3_b200.formula import G3Unsupported, g3_parameterized
+    with pytest.raises(G3Unsupported, match="constant matrices"):
+        configs.build_mini_transform(reader=[[g3_parameterized("reader")] * 5] * 5)
+    with pytest.raises(ValueError, match="5 x 5"):
+        configs.build_mini_transform(reader=np.eye(4))

@@ -141,7 +141,7 @@ def test_otherfood_is_assigned_every_step(mini_of):
     assert np.asarray(rep["detail_otherfood_pred__cons"]).min() > 0          # and it IS eaten, every step, in both areas
 
 
-def _expected_two_prey_consumption(model, p, v, rep, t):
+def _expected_two_prey_consumption(model, p, v, rep, t, pref=None):
     """As _expected_consumption, with the otherfood stock in the predator's total suitable biomass (R/action_predate.R:314-333:
     total_predsuit sums over every prey of the predator) -- returns the consumption of `prey` and of `otherfood`."""
     st = _stocks(model)
@@ -158,6 +158,8 @@ def _expected_two_prey_consumption(model, p, v, rep, t):
     cons = {k: np.zeros_like(B0[k]) for k in E}
     for r in range(predN.shape[1]):
         suit = {k: S[k][:, None, :] * E[k] * B0[k][:, :, r][:, :, None] for k in E}
+        if pref is not None:            # (suit_f * energycontent * num * wgt)^prey_preference, R/action_predate.R:220-225
+            suit = {k: suit[k] ** pref[k] for k in E}
         ts = sum(suit[k].sum(axis=(0, 1)) for k in E)
         psi = ts / (hf * dt + ts)
         for k in E:
@@ -181,3 +183,22 @@ def test_otherfood_shares_the_predators_appetite(mini_of):
         v2[p.index(f"otherfood.of_abund.{y}")] *= 10
     rep2 = unpack_report(model, orc.report(v2))
     assert np.asarray(rep2["detail_prey_pred__cons"])[..., 0].sum() < np.asarray(rep["detail_prey_pred__cons"])[..., 0].sum()
+
+
+def test_prey_preferences(oracle_lib):
+    """R/action_predate.R:208,220-225: the suitable biomass of each prey is raised to its prey_preference before it enters the
+    predator's total and the split of the consumption. MINI_PREFS: 0.9 (a parameter) for the prey, the constant 1.3 for the
+    other food; consumption re-derived from the reported arrays, and preference 1 for both gives MINI_OTHERFOOD back."""
+    model, p = CONFIGS["MINI_PREFS"]()
+    orc = Oracle(*model.pack(p))
+    assert "pref.prey" in p.switch
+    v = _values(p)
+    rep = unpack_report(model, orc.report(v))
+    for t in (0, 1, 2):
+        want = _expected_two_prey_consumption(model, p, v, rep, t, pref={"prey": 0.9, "otherfood": 1.3})
+        for k in ("prey", "otherfood"):
+            got = np.asarray(rep[f"detail_{k}_pred__cons"], dtype=float)[..., t]
+            assert np.abs(got - want[k]).max() <= 1e-9 * want[k].max(), (k, t)
+    plain = _expected_two_prey_consumption(model, p, v, rep, 0)
+    want = _expected_two_prey_consumption(model, p, v, rep, 0, pref={"prey": 0.9, "otherfood": 1.3})
+    assert np.abs(plain["prey"] - want["prey"]).max() > 1e-3 * plain["prey"].max()          # the exponents do something
