@@ -13,7 +13,9 @@ from .actions import (g3_action_order, g3_suitability_andersen, g3_suitability_a
                       g3_suitability_gamma, g3_suitability_richards, g3_suitability_straightline, g3_timeareadata, g3a_age, g3a_grow_impl_bbinom,
                       g3a_grow_lengthvbsimple, g3a_grow_weightsimple, g3a_growmature,
                       g3a_initialconditions_normalcv, g3a_initialconditions_normalparam,
-                      g3a_mature_constant, g3a_mature_continuous, g3a_migrate, g3a_naturalmortality, g3a_otherfood,
+                      g3a_mature_constant, g3a_mature_continuous, g3a_migrate, g3a_naturalmortality, g3a_otherfood, g3a_spawn,
+                      g3a_spawn_recruitment_bevertonholt, g3a_spawn_recruitment_bevertonholt_ss3, g3a_spawn_recruitment_fecundity,
+                      g3a_spawn_recruitment_hockeystick, g3a_spawn_recruitment_ricker, g3a_spawn_recruitment_simplessb,
                       g3a_naturalmortality_exp, g3a_predate, g3a_predate_catchability_predator,
                       g3a_predate_catchability_effortfleet, g3a_predate_catchability_linearfleet,
                       g3a_predate_catchability_numberfleet, g3a_predate_catchability_totalfleet, g3a_predate_fleet,

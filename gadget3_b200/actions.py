@@ -509,6 +509,86 @@ def g3a_predate_fleet(fleet_stock, prey_stocks, suitabilities, catchability_f):
     return g3a_predate(fleet_stock, prey_stocks, suitabilities, catchability_f)
 
 
+# ------------------------------------------------------------------ spawning
+class _Recruitment:
+    def __init__(self, kind, s_args, r_args, R_by_year=None):
+        self.kind, self.s_args, self.r_args, self.R_by_year = kind, [wrap(x) for x in s_args], [wrap(x) for x in r_args], R_by_year
+
+
+def _sp(name, by_stock, value=0.0, **kw):
+    return g3_parameterized("spawn." + name, value=value, by_stock=by_stock, **kw)
+
+
+def g3a_spawn_recruitment_fecundity(p0=None, p1=None, p2=None, p3=None, p4=None, by_stock=True):
+    """R/action_spawn.R:1-17: s = sum(midlen^p1 * age^p2 * spawningnum^p3 * wgt^p4), r = p0 * s."""
+    ps = [_sp(f"p{i}", by_stock, 1) if x is None else x for i, x in enumerate((p0, p1, p2, p3, p4))]
+    return _Recruitment("fecundity", ps[1:], ps[:1])
+
+
+def g3a_spawn_recruitment_simplessb(mu=None, by_stock=True):
+    """R/action_spawn.R:19-28: s = sum(wgt * spawningnum), r = mu * s."""
+    return _Recruitment("simplessb", [], [_sp("mu", by_stock) if mu is None else mu])
+
+
+def g3a_spawn_recruitment_ricker(mu=None, lam=None, by_stock=True):
+    """R/action_spawn.R:32-43: r = mu * s * exp(-lambda * s)."""
+    return _Recruitment("ricker", [], [_sp("mu", by_stock) if mu is None else mu, _sp("lambda", by_stock) if lam is None else lam])
+
+
+def g3a_spawn_recruitment_bevertonholt(mu=None, lam=None, by_stock=True):
+    """R/action_spawn.R:45-56: r = mu * s / (lambda + s)."""
+    return _Recruitment("bevertonholt", [], [_sp("mu", by_stock) if mu is None else mu, _sp("lambda", by_stock) if lam is None else lam])
+
+
+def g3a_spawn_recruitment_bevertonholt_ss3(h=None, R=None, B0=None, by_stock=True):
+    """R/action_spawn.R:59-74: r = 4 h s R / (B0 (1 - h) + s (5 h - 1)); R = exp(spawn.R.<year>) * spawn.R0 by default."""
+    h = _sp("h", by_stock, 0.5, lower=0.1, upper=1) if h is None else h
+    R = (g3_parameterized("spawn.R", by_year=True, exponentiate=True, scale="spawn.R0", by_stock=by_stock) if R is None else R)
+    B0 = _sp("B0", by_stock) if B0 is None else B0
+    return _Recruitment("bevertonholt_ss3", [], [h, B0], R_by_year=wrap(R))
+
+
+def g3a_spawn_recruitment_hockeystick(r0=None, blim=None, by_stock=True):
+    """R/action_spawn.R:76-88: r = r0 * logspace_add(-1000 * s / blim, -1000) / -1000 (a differentiable r0 * pmin(s / blim, 1))."""
+    return _Recruitment("hockeystick", [], [_sp("r0", by_stock) if r0 is None else r0, _sp("blim", by_stock, 1) if blim is None else blim])
+
+
+class SpawnAction(Action):
+    kind = "spawn"
+
+    def __init__(self, stock, recruitment_f, proportion_f, mortality_f, output_stocks, output_ratios, mean_f, stddev_f,
+                 alpha_f, beta_f, run_step):
+        self.stock, self.recruitment_f, self.proportion_f, self.mortality_f = stock, recruitment_f, proportion_f, mortality_f
+        self.output_stocks, self.output_ratios = list(output_stocks), list(output_ratios)
+        self.mean_f, self.stddev_f, self.alpha_f, self.beta_f, self.run_step = mean_f, stddev_f, alpha_f, beta_f, run_step
+
+
+def g3a_spawn(stock, recruitment_f, proportion_f=1, mortality_f=0, weightloss_f=0, weightloss_args=None, output_stocks=(),
+              output_ratios=None, mean_f=None, stddev_f=None, alpha_f=None, beta_f=None, by_stock=True, wgt_by_stock=True,
+              run_step=None):
+    """R/action_spawn.R:86-233. ``proportion_f`` / ``mortality_f``: a formula, or a g3_suitability_*() of the parent's
+    length (as the reference's documentation uses them). mean_f .. beta_f are evaluated for each OUTPUT stock
+    (R/action_spawn.R:187-189). Spawning weight loss is not supported."""
+    if not isinstance(recruitment_f, _Recruitment):
+        raise G3Unsupported("g3a_spawn: recruitment_f must come from g3a_spawn_recruitment_*()")
+    if not (isinstance(weightloss_f, (int, float)) and weightloss_f == 0) or weightloss_args:
+        raise G3Unsupported("g3a_spawn(weightloss_f / weightloss_args = ...)")
+    output_stocks = list(output_stocks)
+    if output_ratios is None:
+        output_ratios = [1.0 / len(output_stocks)] * len(output_stocks) if output_stocks else []
+    output_ratios = list(output_ratios)
+    if len(output_stocks) != len(output_ratios):
+        raise ValueError("length(output_stocks) == length(output_ratios) is not TRUE")
+    if all(isinstance(x, (int, float)) for x in output_ratios) and output_ratios and abs(sum(output_ratios) - 1) >= 1e-4:
+        raise ValueError("output_ratios must sum to 1")
+    mean_f = g3a_renewal_vonb_t0(by_stock=by_stock) if mean_f is None else wrap(mean_f)
+    stddev_f = g3_parameterized("rec.sd", value=10, by_stock=by_stock) if stddev_f is None else wrap(stddev_f)
+    alpha_f = g3_parameterized("walpha", by_stock=wgt_by_stock) if alpha_f is None else wrap(alpha_f)
+    beta_f = g3_parameterized("wbeta", by_stock=wgt_by_stock) if beta_f is None else wrap(beta_f)
+    return SpawnAction(stock, recruitment_f, proportion_f, mortality_f, output_stocks, output_ratios, mean_f, stddev_f,
+                       alpha_f, beta_f, run_step)
+
+
 # ------------------------------------------------------------------ migration
 class MigrateAction(Action):
     kind = "migrate"

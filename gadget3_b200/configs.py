@@ -638,6 +638,134 @@ def build_mini_transform(seed=123, reader=READER_MATRIX):
     return model, p
 
 
+SPAWN_KINDS = ("fecundity", "simplessb", "ricker", "bevertonholt", "bevertonholt_ss3", "hockeystick")
+
+
+def build_spawn_rig(seed=123):
+    """The rig of the reference's spawning test (tests/test-action_spawn.R:41-88): for every recruitment function a
+    mature stock whose number and mean weight are assigned every step (g3a_otherfood: abundance by year x step) spawns
+    into an immature stock that nothing else touches, so what arrives in a step is that step's recruitment. One survey
+    index on all the immature stocks together gives the model a likelihood."""
+    from . import (g3a_otherfood, g3a_spawn, g3a_spawn_recruitment_bevertonholt, g3a_spawn_recruitment_bevertonholt_ss3,
+                   g3a_spawn_recruitment_fecundity, g3a_spawn_recruitment_hockeystick, g3a_spawn_recruitment_ricker,
+                   g3a_spawn_recruitment_simplessb)
+    gp = g3_parameterized
+    areas = g3_areas(["a"])
+    rf = dict(fecundity=g3a_spawn_recruitment_fecundity(*(gp(f"fecundity_p{i}", value=0.5) for i in range(5))),
+              simplessb=g3a_spawn_recruitment_simplessb(gp("simplessb_mu", value=0.5)),
+              ricker=g3a_spawn_recruitment_ricker(gp("ricker_mu", value=1.0), gp("ricker_lambda", value=5e-6)),
+              bevertonholt=g3a_spawn_recruitment_bevertonholt(gp("bevertonholt_mu", value=0.5), gp("bevertonholt_lambda", value=0.5)),
+              bevertonholt_ss3=g3a_spawn_recruitment_bevertonholt_ss3(),
+              hockeystick=g3a_spawn_recruitment_hockeystick(gp("hockeystick_r0", value=0.5), gp("hockeystick_blim", value=0.5)))
+    actions = [g3a_time(1982, 1985, [3, 3, 3, 3])]
+    imms = []
+    for k in SPAWN_KINDS:
+        mat = g3s_livesonareas(g3s_age(g3_stock("mat_" + k, range(10, 50, 10)), 5, 5), areas)
+        imm = g3s_livesonareas(g3s_age(g3_stock("imm_" + k, range(10, 50, 10)), 0, 0), areas)
+        imms.append(imm)
+        actions += [g3a_otherfood(mat, by_stock=False), g3a_spawn(mat, rf[k], output_stocks=[imm])]
+    rng = np.random.default_rng(seed)
+    yrs = [1982, 1983, 1984, 1985]
+    si = dict(year=yrs, step=[4] * 4, number=list(rng.uniform(1e3, 1e4, 4)))
+    actions.append(g3l_abundancedistribution("si_imm", si, stocks=imms, function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    actions += [g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "of_abund.#", 100.0, lower=50, upper=200)
+    for i, y in enumerate(yrs):
+        p = g3_init_val(p, f"of_abund.{y}", 100.0 + 40 * i, lower=50, upper=400)
+    for st in (1, 2, 3, 4):
+        p = g3_init_val(p, f"of_abund.step.{st}", 0.7 + 0.2 * st, lower=0.5, upper=2)
+    p = g3_init_val(p, "of_abund.proj", 100.0, optimise=False)
+    p = g3_init_val(p, "of_meanwgt", 10.0, lower=5, upper=20)
+    for i in range(5):
+        p = g3_init_val(p, f"fecundity_p{i}", 0.3 + 0.1 * i, lower=0.1, upper=0.9)
+    p = g3_init_val(p, "simplessb_mu", 0.4, lower=0.1, upper=0.9)
+    p = g3_init_val(p, "ricker_mu", 1.1, lower=0.9, upper=1.2)
+    p = g3_init_val(p, "ricker_lambda", 5e-6, lower=1e-6, upper=1e-5)
+    p = g3_init_val(p, "bevertonholt_mu", 0.45, lower=0.4, upper=0.6)
+    p = g3_init_val(p, "bevertonholt_lambda", 0.55, lower=0.4, upper=0.6)
+    p = g3_init_val(p, "hockeystick_r0", 0.5, lower=0.4, upper=0.6)
+    p = g3_init_val(p, "hockeystick_blim", 5000.0, lower=1000, upper=10000)      # (inside the range of s: both arms of the stick)
+    p = g3_init_val(p, "mat_*.spawn.h", 0.7, lower=0.3, upper=0.95)
+    p = g3_init_val(p, "mat_*.spawn.R0", 1e4, optimise=False)
+    p = g3_init_val(p, "mat_*.spawn.R_exp.#", 0.1, lower=-1, upper=1)
+    p = g3_init_val(p, "mat_*.spawn.B0", 1e3, lower=500, upper=2000)
+    p = g3_init_val(p, "*.Linf", 50, optimise=False)
+    p = g3_init_val(p, "*.K", 0.3, optimise=False)
+    p = g3_init_val(p, "*.t0", -2.0, optimise=False)
+    p = g3_init_val(p, "*.rec.sd", 10, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    return model, p
+
+
+def build_mini_spawn(seed=123):
+    """A closed life cycle on two areas: the immature stock grows, matures into the mature stock (continuous maturity,
+    every step) and ages into it; the mature stock spawns on step 2 -- proportion spawning by length
+    (g3_suitability_exponentiall50), Ricker recruitment, spawning mortality -- into the immature stock's youngest age
+    (g3a_spawn, R/action_spawn.R:86-233). A fleet, two likelihood components, understocking."""
+    from . import g3a_spawn, g3a_spawn_recruitment_ricker
+    areas = g3_areas(["a", "b"])
+    imm = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "imm"}, range(10, 60, 5)), 1, 3), areas)
+    mat = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "mat"}, range(10, 60, 5)), 2, 5), areas)
+    fl = g3s_livesonareas(g3_fleet("f_comm"), areas)
+    rng = np.random.default_rng(seed)
+    yrs = [2000, 2001, 2002, 2003, 2004]
+    land = dict(year=[y for y in yrs for _ in range(8)], step=[st for _ in yrs for st in (1, 2, 3, 4) for _ in range(2)],
+                area=["a", "b"] * 20, weight=list(rng.uniform(20, 60, 40)))
+    actions = [
+        g3a_time(2000, 2004, [3, 3, 3, 3]),
+        g3a_initialconditions_normalcv(imm), g3a_initialconditions_normalcv(mat),
+        g3a_naturalmortality(imm), g3a_naturalmortality(mat),
+        g3a_growmature(imm, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3), maturity_f=g3a_mature_continuous(),
+                       output_stocks=[mat], transition_f=True),
+        g3a_growmature(mat, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3)),
+        g3a_age(imm, output_stocks=[mat]), g3a_age(mat),
+        g3a_spawn(mat, g3a_spawn_recruitment_ricker(), proportion_f=g3_suitability_exponentiall50(),
+                  mortality_f=g3_parameterized("spawn.mort", by_stock=True, value=0.1), output_stocks=[imm], run_step=2,
+                  # (lighter than the fish already there: the mean weight of the cells they join moves)
+                  alpha_f=g3_parameterized("spawn.walpha", by_stock=True, value=0.8e-5, optimise=False)),
+        g3a_predate_fleet(fl, [imm, mat], suitabilities=g3_suitability_exponentiall50(by_stock="species"),
+                          catchability_f=g3a_predate_catchability_totalfleet(g3_timeareadata("landings", land, "weight", areas=areas))),
+        g3l_understocking([imm, mat]),
+    ]
+    ld = dict(year=[y for y in yrs for _ in range(5)], step=[2] * 25, length=["[10,20)", "[20,30)", "[30,40)", "[40,50)", "[50,Inf)"] * 5,
+              number=list(rng.uniform(10, 100, 25)))
+    actions.append(g3l_catchdistribution("ldist", ld, fleets=[fl], stocks=[imm, mat], function_f=g3l_distribution_sumofsquares(),
+                                         area_group=None))
+    si = dict(year=[y for y in yrs for _ in range(2)], step=[3] * 10, area=["a", "b"] * 5, number=list(rng.uniform(1e4, 1e5, 10)))
+    actions.append(g3l_abundancedistribution("si_imm", si, stocks=[imm], area_group=areas,
+                                             function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    actions += [g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "*.Linf", 60, spread=0.2)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.05, upper=1)
+    p = g3_init_val(p, "*.t0", -0.5, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.15, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, lower=0.01, upper=1)
+    p = g3_init_val(p, "init.F", 0.3, lower=0.1, upper=1)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.bbin", 10, lower=1, upper=100)
+    p = g3_init_val(p, "*.mat.alpha", 0.1, lower=0.01, upper=1)
+    p = g3_init_val(p, "*.mat.l50", 30, lower=20, upper=40)
+    p = g3_init_val(p, "*.spawn.alpha", 0.2, lower=0.05, upper=1)
+    p = g3_init_val(p, "*.spawn.l50", 35, lower=25, upper=45)
+    p = g3_init_val(p, "*.spawn.mort", 0.1, lower=0.01, upper=0.5)
+    p = g3_init_val(p, "*.spawn.walpha", 0.8e-5, optimise=False)
+    p = g3_init_val(p, "*.spawn.mu", 0.5, lower=0.05, upper=2)
+    p = g3_init_val(p, "*.spawn.lambda", 1e-6, lower=1e-7, upper=5e-6)
+    p = g3_init_val(p, "*.rec.sd", 3, lower=1, upper=6)
+    p = g3_init_val(p, "fish.f_comm.alpha", 0.1, lower=0.01, upper=1)
+    p = g3_init_val(p, "fish.f_comm.l50", 30, lower=15, upper=45)
+    return model, p
+
+
 def build_mini_fleets(seed=123):
     """One stock on two areas fished by a numberfleet, a linearfleet and an effortfleet
     (R/action_predate.R:7-18,117-126) -- parity-test model for the catchabilities bench configs do not use."""
@@ -829,5 +957,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform,
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn,
            "LING": build_ling}

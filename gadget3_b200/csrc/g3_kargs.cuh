@@ -6,7 +6,7 @@
 
 namespace g3 {
 
-constexpr int MAXS = 8;      // stocks
+constexpr int MAXS = 16;     // stocks
 constexpr int MAXC = 16;     // likelihood components
 constexpr int MAXQ = 4;      // predator-prey pairs acting on one stock
 constexpr int MAXTS = 8;     // (predator, area) total-suitability accumulators
@@ -51,6 +51,7 @@ struct KArgs {
     int t_suitq[32];                        // per predator-prey pair: suitability [predator length][prey length]
     int t_pts[MAXS], t_pmc[MAXS];           // per stock predator: totals / consumption factors [area][length]; max consumption [length]
     int t_mig[MAXS], t_mig_steps[MAXS];     // migration matrices [step][dest][src]; steps on which the stock migrates
+    int t_sps;                              // per stock: the recruitment sum s of a spawning stock at this step (g3a_spawn)
     int t_remf, t_colbase[MAXS], t_cmat[MAXS];      // per global column: unclaimed share; first global column; constant-maturity ratios
     const int4* t_colinc;                   // per global column: (compact index of the source column's first cell or -1, ratio slot, step mask, 0)
 };

@@ -428,7 +428,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                     if (rs == 0 || rs == step + 1) ren_mask |= 1 << k;
                 }
                 const bool catch_now = any_catch && nq > 0;
-                if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0) continue;
+                const bool spawns_now = St[G3S_SPAWN_OFF] >= 0 && (I[St[G3S_SPAWN_OFF] + G3SP_RUN_STEP] == 0 || I[St[G3S_SPAWN_OFF] + G3SP_RUN_STEP] == step + 1);
+                if (!prey_now && !has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0 && !spawns_now) continue;
                 const unsigned LWS = (unsigned)L * NTH;
 
                 // ---------- g3a_predate (R/action_predate.R:335-406): cell order, as the reference sums
@@ -548,7 +549,31 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             }
                         }
                     }
-                if (!has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0) continue;
+                // g3a_spawn, order 6 (R/action_spawn.R:121-168): does this stock spawn at this step? (This kernel serves the reports:
+                // proportion, mortality and fecundity weights are worked out cell by cell instead of from tables.)
+                bool spawn_here = false;
+                T sp_prop[5], sp_mort[5], sp_p[5], sp_acc(0.0);
+                int sp_kind = 0, sp_pk = 0, sp_mk = -1;
+                if (St[G3S_SPAWN_OFF] >= 0) {
+                    const int32_t* Sp = I + St[G3S_SPAWN_OFF];
+                    spawn_here = Sp[G3SP_RUN_STEP] == 0 || Sp[G3SP_RUN_STEP] == step + 1;
+                    sp_kind = Sp[G3SP_RECR_KIND]; sp_pk = Sp[G3SP_PROP_KIND]; sp_mk = Sp[G3SP_MORT_KIND];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) {
+                        sp_prop[k] = Sp[G3SP_PROP_SLOTS + k] >= 0 ? SLOT(Sp[G3SP_PROP_SLOTS + k]) : T(0.0);
+                        sp_mort[k] = sp_mk >= 0 && Sp[G3SP_MORT_SLOTS + k] >= 0 ? SLOT(Sp[G3SP_MORT_SLOTS + k]) : T(0.0);
+                        sp_p[k] = sp_kind == G3SPAWN_FECUNDITY ? SLOT(Sp[G3SP_RECR_SLOTS + k]) : T(0.0);
+                    }
+                }
+                auto spawn_cell = [&](const int l, const int aidx, T& num, const T& wgt) {
+                    const double ml = R[St[G3S_MIDLEN_ROFF] + l];
+                    const T spn = num * suitability_of<T>(sp_pk, sp_prop, ml, ml);
+                    if (sp_kind == G3SPAWN_FECUNDITY)
+                        sp_acc = sp_acc + xpow(T(ml), sp_p[1]) * xpow(T((double)(St[G3S_MINAGE] + aidx)), sp_p[2]) * xpow(spn, sp_p[3]) * xpow(wgt, sp_p[4]);
+                    else sp_acc = sp_acc + wgt * spn;
+                    if (sp_mk >= 0) num = num - spn * (1.0 - xexp(-suitability_of<T>(sp_mk, sp_mort, ml, ml)));
+                };
+                if (!has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0 && !spawn_here) continue;
 
                 // ---------- natural mortality, growth (+ maturing split), hand-over, renewal, collect vectors.
                 // Length growth only looks DOWN the length axis, so walking l from the top the update is in
@@ -641,6 +666,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                 }
                             }
                             num = bn; wgt = xdiv(bw, avoid_zero(bn));
+                            if (spawn_here) spawn_cell(l, aidx, num, wgt);        // (before the maturing fish move: order 6 < 7)
                             if (trans_now) {
                                 *ptn = an; *ptw = xdiv(aw, avoid_zero(an));
                                 // unclaimed remainder moves back (move_remainder = TRUE, R/action_mature.R:126-131)
@@ -648,6 +674,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             }
                         } else {
                             num = *pn * mortf; wgt = *pw_;
+                            if (spawn_here) spawn_cell(l, aidx, num, wgt);
                         }
                         // ---- g3a_step_transition (R/action_mature.R:78-134): maturing fish arriving from their source column
                         if (inc_now) {
@@ -684,6 +711,55 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                         if (++aidx == nage) { aidx = 0; ridx++; }
                     }
                 }
+                }
+                if (spawn_here) W(A.t_sps + s) = sp_acc;
+            }
+
+            // ================= g3a_spawn, order 8 (R/action_spawn.R:183-218): the offspring arrive in the youngest age of the output stocks
+            for (int s = 0; s < NS; s++) {
+                const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
+                if (St[G3S_SPAWN_OFF] < 0) continue;
+                const int32_t* Sp = I + St[G3S_SPAWN_OFF];
+                if (Sp[G3SP_RUN_STEP] != 0 && Sp[G3SP_RUN_STEP] != step + 1) continue;
+                const int32_t* rs = Sp + G3SP_RECR_SLOTS;
+                const int kind = Sp[G3SP_RECR_KIND];
+                const T sum = W(A.t_sps + s);
+                T r(0.0);
+                if (kind == G3SPAWN_FECUNDITY || kind == G3SPAWN_SIMPLESSB) r = SLOT(rs[0]) * sum;
+                else if (kind == G3SPAWN_RICKER) r = SLOT(rs[0]) * sum * xexp(-SLOT(rs[1]) * sum);
+                else if (kind == G3SPAWN_BEVERTONHOLT) r = SLOT(rs[0]) * sum / (SLOT(rs[1]) + sum);
+                else if (kind == G3SPAWN_BEVERTONHOLT_SS3) {
+                    const T h = SLOT(rs[0]), B0 = SLOT(rs[1]), Ry = SLOT(I[rs[2] + yidx]);
+                    r = 4.0 * h * sum * Ry / (B0 * (1.0 - h) + sum * (5.0 * h - 1.0));
+                } else r = SLOT(rs[0]) * lsa_c(-1000.0 * sum / SLOT(rs[1]), -1000.0) / -1000.0;
+                const double ncell = (double)(St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA]);
+                const T total = r * 1.0 / avoid_zero(T(ncell)) * ncell;     // sum of stock__offspringnum = r / avoid_zero(cells) per cell
+                for (int o = 0; o < Sp[G3SP_N_OUT]; o++) {
+                    const int32_t* Or = I + Sp[G3SP_OUT_OFF] + 6 * o;
+                    const int32_t* So = I + I[G3H_STOCK_OFF] + Or[0] * G3S_LEN;
+                    const int oL = So[G3S_L], oA = So[G3S_NAGE], oR = So[G3S_NAREA];
+                    const double* oml = R + So[G3S_MIDLEN_ROFF];
+                    const T mean = SLOT(Or[1]), isd = 1.0 / SLOT(Or[2]), wa = SLOT(Or[3]), wb = SLOT(Or[4]);
+                    T tot(0.0);
+                    for (int ar = 0; ar < oR; ar++)
+                        for (int l = 0; l < oL; l++) { const T z = (oml[l] - mean) * isd; tot = tot + xexp(-(z * z) * 0.5); }
+                    const T share = total * SLOT(Or[5]) / avoid_zero(tot);
+                    for (int ar = 0; ar < oR; ar++)
+                        for (int l = 0; l < oL; l++) {
+                            const int cell = So[G3S_CELL_OFF] + ar * oA * oL + l;
+                            const T z = (oml[l] - mean) * isd;
+                            const T spawned = xexp(-(z * z) * 0.5) * share;
+                            const T n0 = W(A.t_num + cell), w0 = W(A.t_wgt + cell);
+                            const T w1 = ratio_add_pop(w0, n0, wa * xpow(T(oml[l]), wb), spawned), n1 = n0 + spawned;
+                            W(A.t_num + cell) = n1; W(A.t_wgt + cell) = w1;
+                            // the collect vectors of these cells were filled when the stock's own step ended: bring them up to date
+#pragma unroll
+                            for (int x = 0; x < MAXX; x++)
+                                if ((xact >> x) & 1) {
+                                    if (A.w_x_kind[x] == 0) { if (A.w_x_unit[x] == 0) W(A.t_x[x] + cell) = W(A.t_x[x] + cell) * avoid_zero(w0) / avoid_zero(w1); }
+                                    else W(A.t_x[x] + cell) = A.w_x_unit[x] == 0 ? n1 : n1 * w1;
+                                }
+                        }
                 }
             }
 

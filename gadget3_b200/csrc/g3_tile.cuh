@@ -55,6 +55,9 @@ struct StockRec {
     int g_cmat;             // [col][l] g3a_mature_constant ratio (NW - 1 zero rows before, NBX - 1 after), or -1
     int mig_ioff, g_mig, mig_steps;
     int of_ioff;            // I: g3a_otherfood (num slot, wgt slot) per (step, area), or -1
+    int sp_ioff;            // I: g3a_spawn record of this (parent) stock, or -1
+    int g_sprop, g_smort, g_sfec;   // [l] proportion spawning; [l] 1 - exp(-spawning mortality) or -1; [age][l] midlen^p1 age^p2 or -1
+    int sp_out_off;         // tb: per output stock (stock, G [l] share of the offspring, G [l] their weight, ratio slot)
     int age_enable, age_n_out, s_mv;
     int us_flag;
     int pp_off, pp_n;       // tb: predator-prey pairs acting on this stock, run order
@@ -74,6 +77,7 @@ struct UnitRec {
     int g_ghost;            // G entries [2][NW - 1]: num, then wgt, of rows lo - (NW - 1) .. lo - 1; -1 for a bottom segment
     int up_ghost;           // g_ghost of the unit above in the same column (this unit fills it), or -1
     int g_usp;              // (sum tp, sum tp') of this unit at this step's predation
+    int g_sps;              // this unit's part of the spawning stock's recruitment sum s at this step, or -1
 };
 struct PairRec {
     int pred, prey, suit_kind, suit_ioff, energy_slot, pref_slot, pred_kind, pred_stock, PL;
@@ -121,6 +125,8 @@ struct TArgs {
     int uorder_off;         // tb: the units, most expensive first (the work queues' order)
     int inc_off, inc_n;     // tb: global columns that receive maturing fish
     int inc_any_mask;       // bit (cur_step-1): some column receives maturing fish on that step
+    int sp_off, sp_n;       // tb: the spawning stocks
+    int spawn_mask;         // bit (cur_step-1): some stock spawns on that step
     int any_ghost;          // some column is split into several units
     int NWc;                // band width the tables are laid out for (the kernel's NW)
     int W;
@@ -389,6 +395,44 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         }
                         GS(St.g_mig + (sy * NR + src) * NR + src, (1.0 - tot) / 1.0);
                     }
+                }
+            }
+            // g3a_spawn (R/action_spawn.R:86-233): proportion spawning and spawning mortality by length, fecundity weights
+            // midlen^p1 age^p2; per output stock the offspring's share by length group -- exp(-((midlen - mean) / sd)^2 / 2) over
+            // avoid_zero(its sum over the stock's areas and lengths) -- and their weight alpha midlen^beta
+            if (St.sp_ioff >= 0) {
+                const int32_t* Sp = I + St.sp_ioff;
+                for (int which = 0; which < 2; which++) {
+                    const int kind = Sp[which ? G3SP_MORT_KIND : G3SP_PROP_KIND];
+                    if (kind < 0 || !mine()) continue;
+                    const int32_t* ss = Sp + (which ? G3SP_MORT_SLOTS : G3SP_PROP_SLOTS);
+                    T sp[5];
+#pragma unroll
+                    for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
+                    for (int l = 0; l < L; l++) {
+                        const T v = suitability_of<T>(kind, sp, midlen[l], midlen[l]);
+                        if (which) GS(St.g_smort + l, 1.0 - xexp(-v)); else GS(St.g_sprop + l, v);
+                    }
+                }
+                if (St.g_sfec >= 0 && mine()) {
+                    const T p1 = SLOT(Sp[G3SP_RECR_SLOTS + 1]), p2 = SLOT(Sp[G3SP_RECR_SLOTS + 2]);
+                    for (int a = 0; a < St.nage; a++) {
+                        const T ap = xpow(T((double)(St.minage + a)), p2);
+                        for (int l = 0; l < L; l++) GS(St.g_sfec + a * L + l, xpow(T(midlen[l]), p1) * ap);
+                    }
+                }
+                for (int o = 0; o < Sp[G3SP_N_OUT]; o++) {
+                    if (!mine()) continue;
+                    const int32_t* Or = I + Sp[G3SP_OUT_OFF] + 6 * o;
+                    const StockRec& So = Tst[Or[0]];
+                    const double* oml = R + So.midlen_roff;
+                    const int gn = tb[St.sp_out_off + 4 * o + 1], gw = tb[St.sp_out_off + 4 * o + 2];
+                    const T mean = SLOT(Or[1]), isd = 1.0 / SLOT(Or[2]), wa = SLOT(Or[3]), wb = SLOT(Or[4]);
+                    T tot(0.0);
+                    for (int l = 0; l < So.L; l++) { const T z = (oml[l] - mean) * isd; GS(gn + l, xexp(-(z * z) * 0.5)); }
+                    for (int r = 0; r < So.narea; r++) for (int l = 0; l < So.L; l++) tot = tot + G(gn + l);
+                    const T den = avoid_zero(tot);
+                    for (int l = 0; l < So.L; l++) { GS(gn + l, G(gn + l) / den); GS(gw + l, wa * xpow(T(oml[l]), wb)); }
                 }
             }
             // renewal length distribution, normalised, and weight (R/action_renewal.R:56-80)
@@ -892,6 +936,25 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             G3T_BAR();          // (pass 2 of a unit may run on another warp than its pass 1; ghost rows are in place)
             G3T_PH(4)           // pass 1: predation, ghost rows
 
+            // g3a_spawn, order 6 (R/action_spawn.R:121-168), for the rows of a block once they have grown: spawningnum = num x
+            // proportion, the block's part of the recruitment sum s, spawning mortality of the parents
+            auto spawn_rows = [&](const StockRec& St, const ColRec& Cl, const int row0, const int nb, T (&num)[NB], const T (&wgt)[NB], T& acc) {
+                const int32_t* Sp = I + St.sp_ioff;
+                const bool fec = Sp[G3SP_RECR_KIND] == G3SPAWN_FECUNDITY;
+                T p3(0.0), p4(0.0);
+                if (fec) { p3 = SLOT(Sp[G3SP_RECR_SLOTS + 3]); p4 = SLOT(Sp[G3SP_RECR_SLOTS + 4]); }
+#pragma unroll
+                for (int b = 0; b < NB; b++) {
+                    if (b >= nb) continue;
+                    const int l = row0 + b;
+                    const T spn = num[b] * G(St.g_sprop + l);
+                    if (fec) acc = acc + G(St.g_sfec + Cl.aidx * St.L + l) * xpow(spn, p3) * xpow(wgt[b], p4);
+                    else acc = acc + wgt[b] * spn;
+                    if (St.g_smort >= 0) num[b] = num[b] - spn * G(St.g_smort + l);
+                }
+            };
+            const bool spawn_step = (A.spawn_mask >> step) & 1;
+
             // ================= own units, pass 2: natural mortality, growth (+ maturing split), and -- unless maturing fish are
             // about to arrive -- renewal and the collect vectors. Length growth only looks DOWN the length axis, so sweeping
             // the blocks from the top the update is in place: every source row is still the old value when a block is rebuilt.
@@ -909,9 +972,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 const int ren_mask = renewals_now(St);
                 double* const pNum = SP(A.s_num + c_lo);
                 double* const pWgt = SP(A.s_wgt + c_lo);
-                if (!has_mort && grow_n < 0 && !inc_here && !ren_mask && xact == 0) continue;
+                bool spawn_here = false;    // this stock spawns at this step
+                if (spawn_step && St.sp_ioff >= 0) { const int rs = I[St.sp_ioff + G3SP_RUN_STEP]; spawn_here = rs == 0 || rs == step + 1; }
+                if (!has_mort && grow_n < 0 && !inc_here && !ren_mask && xact == 0 && !spawn_here) continue;
                 const T mortf = has_mort ? G(St.g_mort + idt * St.ncol + Cl.col) : T(1.0);
                 const int nblk = (U.len + NB - 1) / NB;
+                T sp_acc(0.0);
                 if (grow_n < 0) {
                     for (int j = nblk - 1; j >= 0; j--) {
                         const int r0 = j * NB, nb = min(NB, U.len - r0);
@@ -920,12 +986,14 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         for (int b = 0; b < NB; b++) {
                             num[b] = ldT<T>(pNum + (unsigned)(r0 + b) * C) * mortf; wgt[b] = ldT<T>(pWgt + (unsigned)(r0 + b) * C);
                         }
+                        if (spawn_here) spawn_rows(St, Cl, U.lo + r0, nb, num, wgt, sp_acc);
                         if (!inc_here) finish_block(Cl, St, U.lo + r0, nb, num, wgt, false, ren_mask);
                         else {
 #pragma unroll
                             for (int b = 0; b < NB; b++) if (b < nb) stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]);
                         }
                     }
+                    if (spawn_here) GS(U.g_sps, sp_acc);
                     continue;
                 }
                 const T remf = trans_now ? G(Cl.g_remf) : T(0.0);
@@ -962,6 +1030,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 #pragma unroll
                     for (int b = 0; b < NB; b++) de[b] = num[b];
                     div_az_n(wgt, de);
+                    if (spawn_here) spawn_rows(St, Cl, U.lo + r0, nb, num, wgt, sp_acc);      // (before the maturing fish move: order 6 < 7)
                     if (trans_now) {
                         if (stash) {
 #pragma unroll
@@ -982,6 +1051,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             if (b < nb) { stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]); stT<T>(pWgt + (unsigned)(r0 + b) * C, wgt[b]); }
                     }
                 }
+                if (spawn_here) GS(U.g_sps, sp_acc);
             }
 
             // ================= columns that receive maturing fish finish once every source column has grown. That part is
@@ -1011,6 +1081,66 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 #pragma unroll
                     for (int b = 0; b < NB; b++) { const int l = min(r0 + b, St.L - 1); num[b] = S(A.s_num + Cl.cell0 + l); wgt[b] = S(A.s_wgt + Cl.cell0 + l); }
                     finish_block(Cl, St, r0, nb, num, wgt, true, ren_mask);
+                }
+            }
+
+            // ================= g3a_spawn, order 8 (R/action_spawn.R:183-218): the offspring arrive in the youngest age of the
+            // output stocks. s = the parent units' parts in unit order, r = the recruitment function, every (output stock, area,
+            // block of rows) is dealt to a warp; a warp works out r of a parent when its first block of that parent comes up.
+            if (spawn_step) {
+                G3T_BAR();
+                int kblk = 0;
+                for (int i = 0; i < A.sp_n; i++) {
+                    const StockRec& Pst = Tst[tb[A.sp_off + i]];
+                    const int32_t* Sp = I + Pst.sp_ioff;
+                    if (Sp[G3SP_RUN_STEP] != 0 && Sp[G3SP_RUN_STEP] != step + 1) continue;
+                    bool have_total = false;
+                    T total(0.0);
+                    for (int o = 0; o < Sp[G3SP_N_OUT]; o++) {
+                        const StockRec& So = Tst[tb[Pst.sp_out_off + 4 * o]];
+                        const int gn = tb[Pst.sp_out_off + 4 * o + 1], gw = tb[Pst.sp_out_off + 4 * o + 2];
+                        const int nblk = (So.L + NB - 1) / NB;
+                        for (int ab = 0; ab < So.narea * nblk; ab++, kblk++) {
+                            if (kblk % W != warp) continue;
+                            if (!have_total) {
+                                have_total = true;
+                                T sum(0.0);
+                                for (int u = Pst.u0; u < Pst.u0 + Pst.nu; u++) sum = sum + G(Tunit[u].g_sps);
+                                const int32_t* rs = Sp + G3SP_RECR_SLOTS;
+                                const int kind = Sp[G3SP_RECR_KIND];
+                                T r(0.0);
+                                if (kind == G3SPAWN_FECUNDITY || kind == G3SPAWN_SIMPLESSB) r = SLOT(rs[0]) * sum;
+                                else if (kind == G3SPAWN_RICKER) r = SLOT(rs[0]) * sum * xexp(-SLOT(rs[1]) * sum);
+                                else if (kind == G3SPAWN_BEVERTONHOLT) r = SLOT(rs[0]) * sum / (SLOT(rs[1]) + sum);
+                                else if (kind == G3SPAWN_BEVERTONHOLT_SS3) {
+                                    const T h = SLOT(rs[0]), B0 = SLOT(rs[1]), Ry = SLOT(I[rs[2] + yidx]);
+                                    r = 4.0 * h * sum * Ry / (B0 * (1.0 - h) + sum * (5.0 * h - 1.0));
+                                } else r = SLOT(rs[0]) * lsa_c(-1000.0 * sum / SLOT(rs[1]), -1000.0) / -1000.0;
+                                // stock__offspringnum = r / avoid_zero(number of cells) in every cell of the parent, summed again
+                                const double ncell = (double)(Pst.ncol * Pst.L);
+                                total = r * 1.0 / avoid_zero(T(ncell)) * ncell;
+                            }
+                            const int ar = ab / nblk, r0 = (ab - ar * nblk) * NB;
+                            const T share = total * SLOT(tb[Pst.sp_out_off + 4 * o + 3]);
+                            for (int b = 0; b < NB; b++) {
+                                const int l = r0 + b;
+                                if (l >= So.L) break;
+                                const int cell = So.c0 + ar * So.nage * So.L + l;
+                                const T n0 = S(A.s_num + cell), w0 = S(A.s_wgt + cell), spawned = G(gn + l) * share;
+                                const T w1 = ratio_add_pop(w0, n0, G(gw + l), spawned);
+                                SS(A.s_wgt + cell, w1);
+                                SS(A.s_num + cell, n0 + spawned);
+                                // a catch in numbers is cons / avoid_zero(wgt) with the weight the likelihood sees (order 10): the
+                                // block's finish divided by the weight before the offspring arrived
+                                if (xact)
+                                    for (int j = 0; j < So.cx_n; j++) {
+                                        const int x = tb[So.cx_off + j];
+                                        if (!(((xact >> x) & 1) && Txb[x].unit == 0)) continue;
+                                        GS(Txb[x].g_x + cell, G(Txb[x].g_x + cell) * avoid_zero(w0) / avoid_zero(w1));
+                                    }
+                            }
+                        }
+                    }
                 }
             }
 

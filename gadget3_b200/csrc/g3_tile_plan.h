@@ -92,6 +92,7 @@ inline void plan_build_units(TilePlan& P) {
                     A.any_ghost = 1;
                 }
                 u.g_usp = takeg(2);
+                u.g_sps = r.sp_ioff >= 0 ? takeg(1) : -1;
                 max_len = std::max(max_len, u.len);
                 P.unit.push_back(u);
                 P.unit_cost.push_back(P.row_cost[gc] * ((u.len + NBX - 1) / NBX * NBX) + UNIT_OVERHEAD);
@@ -301,6 +302,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     A.NC = I[G3H_NCELL]; A.NS = I[G3H_NSTOCK]; A.NPP = I[G3H_NPP]; A.NPRED = I[G3H_NPRED]; A.NCOMP = I[G3H_NCOMP];
     A.NX = I[G3H_NXBUF]; A.NSLOT = I[G3H_NSLOT]; A.NPAR = I[G3H_NPAR]; A.NT = I[G3H_NT]; A.NSTEPS = I[G3H_NSTEPS];
     A.NNLL = I[G3H_NNLL]; A.NBOUND = I[G3H_NBOUND]; A.maxL = I[G3H_MAXL];
+    A.spawn_mask = 0; A.sp_n = 0; A.sp_off = 0;
     if (A.NCOMP > 32) return fail("more than 32 likelihood components");
     if (A.NX > 32) return fail("more than 32 collect vectors");
     if (A.NSTEPS > 31) return fail("more than 31 steps per year");
@@ -369,6 +371,16 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         r.g_cmat = (trans && r.mat_kind == G3MAT_CONSTANT) ? take_padded(r.ncol * r.L) : -1;
         r.mig_ioff = St[G3S_MIGRATE_OFF]; r.mig_steps = 0;
         r.of_ioff = St[G3S_OTHERFOOD_OFF];
+        // g3a_spawn (R/action_spawn.R:86-233): proportion spawning and spawning mortality by length, the fecundity weights
+        r.sp_ioff = St[G3S_SPAWN_OFF]; r.g_sprop = r.g_smort = r.g_sfec = -1; r.sp_out_off = -1;
+        if (r.sp_ioff >= 0) {
+            const int32_t* Sp = I + r.sp_ioff;
+            r.g_sprop = takeg(r.L);
+            if (Sp[G3SP_MORT_KIND] >= 0) r.g_smort = takeg(r.L);
+            if (Sp[G3SP_RECR_KIND] == G3SPAWN_FECUNDITY) r.g_sfec = takeg(r.nage * r.L);
+            if (Sp[G3SP_RECR_KIND] < 0 || Sp[G3SP_RECR_KIND] > G3SPAWN_HOCKEYSTICK) return fail("unknown recruitment function");
+            A.spawn_mask |= Sp[G3SP_RUN_STEP] == 0 ? (1 << A.NSTEPS) - 1 : 1 << (Sp[G3SP_RUN_STEP] - 1);
+        }
         r.g_mig = r.mig_ioff >= 0 ? takeg(A.NSTEPS * r.narea * r.narea) : 0;
         if (r.mig_ioff >= 0)
             for (int sy = 0; sy < A.NSTEPS; sy++) for (int i = 0; i < r.narea * r.narea; i++)
@@ -442,6 +454,23 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     }
     A.inc_off = (int)P.tb.size(); A.inc_n = 0;
     for (int gc = 0; gc < ncols; gc++) if (P.col[gc].inc_tn >= 0) { P.tb.push_back(gc); A.inc_n++; }
+    // ---- spawning: the parents, and per output stock (stock, normalised length distribution, weights, ratio slot)
+    A.sp_off = (int)P.tb.size(); A.sp_n = 0;
+    for (int s = 0; s < A.NS; s++) if (P.st[s].sp_ioff >= 0) { P.tb.push_back(s); A.sp_n++; }
+    for (int s = 0; s < A.NS; s++) {
+        StockRec& r = P.st[s];
+        if (r.sp_ioff < 0) continue;
+        const int32_t* Sp = I + r.sp_ioff;
+        r.sp_out_off = (int)P.tb.size();
+        for (int o = 0; o < Sp[G3SP_N_OUT]; o++) {
+            const int32_t* Or = I + Sp[G3SP_OUT_OFF] + 6 * o;
+            const StockRec& So = P.st[Or[0]];
+            // the offspring land after the barrier that follows pass 2, beside the blocks that receive maturing fish: not the same cells
+            for (int ar = 0; ar < So.narea; ar++)
+                if (P.col[So.gcol0 + ar * So.nage].inc_tn >= 0) return fail("spawning into a column that also receives maturing fish");
+            P.tb.push_back(Or[0]); P.tb.push_back(takeg(So.L)); P.tb.push_back(takeg(So.L)); P.tb.push_back(Or[5]);
+        }
+    }
     // one renewal per (column, step) is what finish_cell applies in a defined order
     for (int s = 0; s < A.NS; s++) {
         const StockRec& r = P.st[s];

@@ -241,6 +241,7 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
         A.t_cmat[s] = (St[G3S_GROW_N] >= 0 && St[G3S_N_OUT] > 0 && St[G3S_MAT_KIND] == G3MAT_CONSTANT) ? take(St[G3S_L] * St[G3S_NAGE] * St[G3S_NAREA]) : 0;
     }
     A.t_remf = take(ncolg);
+    A.t_sps = take(A.NS);
     A.t_cblk = 2;       // wide bands: columns per growth sweep block (C4 on B200: 1: 48.9 k, 2: 51.9 k, 3: 50.4 k, all columns: 46.3 k evals/s)
     return off;
 }

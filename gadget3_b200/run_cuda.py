@@ -153,10 +153,10 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             raise G3Unsupported(f"stock {s.name} must have age and area dimensions")
         stocks.setdefault(s.name, s)
 
-    for k in ("init", "otherfood", "renewal", "naturalmortality", "growmature", "age", "migrate"):
+    for k in ("init", "otherfood", "renewal", "naturalmortality", "growmature", "age", "migrate", "spawn"):
         for a in by_kind.get(k, []):
             note_stock(a.stock)
-    for a in by_kind.get("growmature", []) + by_kind.get("age", []):
+    for a in by_kind.get("growmature", []) + by_kind.get("age", []) + by_kind.get("spawn", []):
         for o in a.output_stocks:
             note_stock(o)
     for a in by_kind.get("predate", []):
@@ -202,7 +202,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         r[K["G3S_CELL_OFF"]] = cell_off
         r[K["G3S_MIDLEN_ROFF"]] = b.alloc_reals(s.midlen)
         r[K["G3S_PLUSDL_ROFF"]] = b.alloc_reals([s.plusdl])
-        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF", "G3S_OTHERFOOD_OFF"):
+        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF", "G3S_OTHERFOOD_OFF", "G3S_SPAWN_OFF"):
             r[K[f]] = -1
         dims = [d for d in s.dims if d != "length"]
         r[K["G3S_DIMORDER"]] = 0 if dims == ["age", "area"] else 1
@@ -407,6 +407,40 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                         omap.append(base + l if ok else -1)
             r[K["G3S_OUT_MAP_OFF"]] = b.alloc_ints(omap)
 
+    # ---- spawning (order 6: proportion, recruitment, parent mortality)
+    def suit_slots(f, c, what):
+        """A formula (-> G3SUIT_CONSTANT) or a g3_suitability_*() of the stock's own length."""
+        if hasattr(f, "kind") and hasattr(f, "args"):
+            if f.kind in ("andersen", "exponential", "richards"):
+                raise G3Unsupported(f"{what}: g3_suitability_{f.kind} reads predator_length")
+            kind = K["G3SUIT_" + {"expl50": "EXPL50"}.get(f.kind, f.kind.upper())]
+            sl = [low.slot(x, c) for x in f.args]
+        else:
+            kind, sl = K["G3SUIT_CONSTANT"], [low.slot(wrap(f), c)]
+        return [kind] + sl + [-1] * (5 - len(sl))
+
+    spawn_recs = {}
+    for name, a in one_per_stock("spawn", "g3a_spawn").items():
+        s = stocks[name]
+        # by_predator names read "spawn" (proportion_f is substituted with predstock = 'spawn', R/action_spawn.R:165)
+        c = Ctx(stock=s, predstock=type("_SpawnName", (), {"name": "spawn", "name_parts": {}})())
+        rf = a.recruitment_f
+        q = [0] * K["G3SP_LEN"]
+        q[K["G3SP_RUN_STEP"]] = 0 if a.run_step is None else int(a.run_step)
+        q[K["G3SP_RECR_KIND"]] = K["G3SPAWN_" + rf.kind.upper()]
+        q[K["G3SP_PROP_KIND"]:K["G3SP_PROP_KIND"] + 6] = suit_slots(a.proportion_f, c, "g3a_spawn(proportion_f)")
+        rs = [low.slot(x, c) for x in rf.s_args] + [low.slot(x, c) for x in rf.r_args]
+        if rf.kind == "fecundity":
+            rs = rs[4:] + rs[:4]        # stored p0..p4; declared in the order the reference's code reads them (s, then r)
+        if rf.R_by_year is not None:
+            rs.append(b.alloc_ints([low.slot(rf.R_by_year, Ctx(stock=s, cur_year=y)) for y in range(tm.start_year, tm.end_year + 1)]))
+        q[K["G3SP_RECR_SLOTS"]:K["G3SP_RECR_SLOTS"] + 5] = rs + [-1] * (5 - len(rs))
+        if isinstance(a.mortality_f, (int, float)) and a.mortality_f == 0:
+            q[K["G3SP_MORT_KIND"]:K["G3SP_MORT_KIND"] + 6] = [-1] * 6
+        else:
+            q[K["G3SP_MORT_KIND"]:K["G3SP_MORT_KIND"] + 6] = suit_slots(a.mortality_f, c, "g3a_spawn(mortality_f)")
+        spawn_recs[name] = q
+
     # ---- renewal (order 8)
     for name, s in stocks.items():
         recs = []
@@ -434,6 +468,18 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             recs.append(q)
         srec[name][K["G3S_N_RENEW"]] = len(recs)
         srec[name][K["G3S_RENEW_OFF"]] = b.alloc_ints([x for q in recs for x in q])
+
+    # ---- spawning, the offspring (order 8, after the renewals in step-id order): formulas in the OUTPUT stock's context
+    for name, q in spawn_recs.items():
+        a = [x for x in by_kind["spawn"] if x.stock.name == name][0]
+        tab = []
+        for o, rt in zip(a.output_stocks, a.output_ratios):
+            co = Ctx(stock=o, age=o.minage)
+            tab += [sidx[o.name], low.slot(a.mean_f, co), low.slot(a.stddev_f, co)]
+            ratio = low.slot(wrap(rt), co)
+            tab += [low.slot(a.alpha_f, co), low.slot(a.beta_f, co), ratio]
+        q[K["G3SP_N_OUT"]], q[K["G3SP_OUT_OFF"]] = len(a.output_stocks), b.alloc_ints(tab)
+        srec[name][K["G3S_SPAWN_OFF"]] = b.alloc_ints(q)
 
     # ---- ageing (order 12)
     for name, a in one_per_stock("age", "g3a_age").items():

@@ -26,7 +26,7 @@
 #ifndef G3CUDA_SPEC_H
 #define G3CUDA_SPEC_H
 
-#define G3CUDA_SPEC_VERSION 4
+#define G3CUDA_SPEC_VERSION 5
 
 /* ---- header: ints[0..G3H_LEN) ------------------------------------------ */
 #define G3H_VERSION        0
@@ -95,7 +95,33 @@
                                   oldest column per (area idx, l) or -1 (R/action_age.R:16-20,57-63) */
 #define G3S_OTHERFOOD_OFF 26   /* g3a_otherfood (R/action_renewal.R:276-308): ints[NT*NAREA*2]: (num slot, wgt slot) per (step t, area idx),
                                   assigned to every cell of the stock at the start of step t; -1 = not an otherfood stock */
-#define G3S_LEN           27
+#define G3S_SPAWN_OFF     27   /* g3a_spawn (R/action_spawn.R:86-233): ints[G3SP_LEN] record of the PARENT stock, or -1 */
+#define G3S_LEN           28
+
+/* ---- spawning record (g3a_spawn, R/action_spawn.R:86-233) ----------------
+   At order 6 (after growth, before the maturing fish arrive and before renewal): spawningnum = num * proportion(l);
+   s = sum over the whole stock of the recruitment function's summand; parents lose spawningnum * (1 - exp(-mortality(l)));
+   r = R(s). At order 8: every output stock gets r * ratio fish at its youngest age, spread over all its areas and length
+   groups as exp(-((midlen - mean) / sd)^2 / 2) / avoid_zero(sum of that over the areas and lengths), mean weight
+   alpha * midlen^beta, combined with ratio_add_pop. */
+#define G3SP_RUN_STEP      0   /* cur_step == this (1-based); 0 = every step */
+#define G3SP_RECR_KIND     1   /* G3SPAWN_* */
+#define G3SP_RECR_SLOTS    2   /* ints[5]: fecundity p0..p4; simplessb mu; ricker / bevertonholt mu, lambda;
+                                  bevertonholt_ss3 h, B0, then the offset of ints[NYEARS] slots of R by year idx; hockeystick r0, blim */
+#define G3SP_PROP_KIND     7   /* proportion_f: G3SUIT_* of the parent's length (G3SUIT_CONSTANT: one formula) */
+#define G3SP_PROP_SLOTS    8   /* ints[5] */
+#define G3SP_MORT_KIND    13   /* mortality_f likewise; -1 = no spawning mortality */
+#define G3SP_MORT_SLOTS   14   /* ints[5] */
+#define G3SP_N_OUT        19
+#define G3SP_OUT_OFF      20   /* ints[N_OUT*6]: (output stock, mean slot, sd slot, alpha slot, beta slot, ratio slot) */
+#define G3SP_LEN          21
+
+#define G3SPAWN_FECUNDITY        0   /* s = sum midlen^p1 age^p2 spawningnum^p3 wgt^p4, r = p0 s (R/action_spawn.R:1-17) */
+#define G3SPAWN_SIMPLESSB        1   /* s = sum wgt spawningnum (this and all below), r = mu s (:19-28) */
+#define G3SPAWN_RICKER           2   /* r = mu s exp(-lambda s) (:32-43) */
+#define G3SPAWN_BEVERTONHOLT     3   /* r = mu s / (lambda + s) (:45-56) */
+#define G3SPAWN_BEVERTONHOLT_SS3 4   /* r = 4 h s R / (B0 (1 - h) + s (5 h - 1)) (:59-74) */
+#define G3SPAWN_HOCKEYSTICK      5   /* r = r0 logspace_add(-1000 s / blim, -1000) / -1000 (:76-88) */
 
 #define G3MAT_NONE         0
 #define G3MAT_CONSTANT     1   /* g3a_mature_constant (R/action_mature.R:44) */

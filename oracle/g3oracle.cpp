@@ -644,6 +644,49 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             }
             lastcalc[s] = calc;
         }
+        // ---- g3a_spawn, order 6 (R/action_spawn.R:121-168): spawning parents, total offspring, spawning mortality
+        std::vector<T> spawn_total(NS, T(0.0));
+        std::vector<char> spawn_now(NS, 0);
+        for (int s = 0; s < NS; s++) {
+            const int32_t* St = S.stock(s);
+            if (St[G3S_SPAWN_OFF] < 0) continue;
+            const int32_t* Sp = S.I + St[G3S_SPAWN_OFF];
+            if (Sp[G3SP_RUN_STEP] != 0 && Sp[G3SP_RUN_STEP] != cur_step) continue;
+            spawn_now[s] = 1;
+            int L = St[G3S_L], A = St[G3S_NAGE], NR = St[G3S_NAREA], ncell = L * A * NR;
+            const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
+            const int32_t* rs = Sp + G3SP_RECR_SLOTS;
+            const int kind = Sp[G3SP_RECR_KIND];
+            bool ok = true;
+            T sum(0.0);
+            for (int r = 0; r < NR; r++) for (int a = 0; a < A; a++) for (int l = 0; l < L; l++) {
+                int c = St[G3S_CELL_OFF] + (r * A + a) * L + l;
+                T prop = suitability<T>(Sp[G3SP_PROP_KIND], Sp + G3SP_PROP_SLOTS, slot, midlen[l], midlen[l], ok);
+                T spn = num[c] * prop;          // stock__spawningnum
+                if (kind == G3SPAWN_FECUNDITY)
+                    sum = sum + xpow(T(midlen[l]), slot(rs[1])) * xpow(T((double)(St[G3S_MINAGE] + a)), slot(rs[2])) * xpow(spn, slot(rs[3])) * xpow(wgt[c], slot(rs[4]));
+                else
+                    sum = sum + wgt[c] * spn;
+                if (Sp[G3SP_MORT_KIND] >= 0) {  // g3a_naturalmortality_exp(mortality_f, action_step_size_f = 1)
+                    T m = suitability<T>(Sp[G3SP_MORT_KIND], Sp + G3SP_MORT_SLOTS, slot, midlen[l], midlen[l], ok);
+                    num[c] = num[c] - spn * (1.0 - xexp(-m));
+                }
+            }
+            if (!ok) return T(NaN);
+            T r(0.0);
+            if (kind == G3SPAWN_FECUNDITY || kind == G3SPAWN_SIMPLESSB) r = slot(rs[0]) * sum;
+            else if (kind == G3SPAWN_RICKER) r = slot(rs[0]) * sum * xexp(-slot(rs[1]) * sum);
+            else if (kind == G3SPAWN_BEVERTONHOLT) r = slot(rs[0]) * sum / (slot(rs[1]) + sum);
+            else if (kind == G3SPAWN_BEVERTONHOLT_SS3) {
+                T h = slot(rs[0]), B0 = slot(rs[1]), Ry = slot(S.I[rs[2] + yidx]);
+                r = 4.0 * h * sum * Ry / (B0 * (1.0 - h) + sum * (5.0 * h - 1.0));
+            } else if (kind == G3SPAWN_HOCKEYSTICK) r = slot(rs[0]) * logspace_add(-1000.0 * sum / slot(rs[1]), T(-1000.0)) / -1000.0;
+            else return T(NaN);
+            // stock__offspringnum = r * 1 / avoid_zero(sum(1)) in every cell; the offspring step sums it again
+            T per = r * 1.0 / avoid_zero(T((double)ncell));
+            for (int i = 0; i < ncell; i++) spawn_total[s] = spawn_total[s] + per;
+        }
+
         // ---- g3a_step_transition after growth (R/action_mature.R:78-134)
         for (int s = 0; s < NS; s++) {
             const int32_t* St = S.stock(s);
@@ -687,6 +730,29 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                         wgt[c] = ratio_add_pop(wgt[c], num[c], rw, rn);
                         num[c] = num[c] + rn;
                     }
+                }
+            }
+        }
+
+        // ---- g3a_spawn, order 8 (R/action_spawn.R:183-218): the offspring arrive in the youngest age of the output stocks
+        for (int s = 0; s < NS; s++) {
+            if (!spawn_now[s]) continue;
+            const int32_t* Sp = S.I + S.stock(s)[G3S_SPAWN_OFF];
+            for (int o = 0; o < Sp[G3SP_N_OUT]; o++) {
+                const int32_t* Or = S.I + Sp[G3SP_OUT_OFF] + 6 * o;
+                const int32_t* So = S.stock(Or[0]);
+                int L = So[G3S_L], A = So[G3S_NAGE], NR = So[G3S_NAREA];
+                const double* midlen = S.R + So[G3S_MIDLEN_ROFF];
+                T mean = slot(Or[1]), sd = slot(Or[2]), wa = slot(Or[3]), wb = slot(Or[4]), ratio = slot(Or[5]);
+                std::vector<T> shape(L); T tot(0.0);
+                for (int l = 0; l < L; l++) { T z = (T(midlen[l]) - mean) * (1.0 / sd); shape[l] = xexp(-(z * z) * 0.5); }
+                for (int r = 0; r < NR; r++) for (int l = 0; l < L; l++) tot = tot + shape[l];
+                T den = avoid_zero(tot);
+                for (int r = 0; r < NR; r++) for (int l = 0; l < L; l++) {
+                    int c = So[G3S_CELL_OFF] + (r * A + 0) * L + l;
+                    T spawned = (shape[l] / den) * spawn_total[s] * ratio;
+                    wgt[c] = ratio_add_pop(wgt[c], num[c], wa * xpow(T(midlen[l]), wb), spawned);
+                    num[c] = num[c] + spawned;
                 }
             }
         }
