@@ -1,0 +1,7 @@
+// instantiation unit: tile kernel with the XF code (g3a_otherfood, g3a_spawn, prey_preferences), T = g3::Dual<G3_NTAN>, band width 16
+#include "g3_ntan.h"
+#include "g3_tile.cuh"
+#include "g3_launch.h"
+const void* g3i::tile_x_g16(bool smem) {
+    return smem ? (const void*)g3t::eval_tile_kernel<g3::Dual<G3_NTAN>, 16, true, 512, 0, true> : (const void*)g3t::eval_tile_kernel<g3::Dual<G3_NTAN>, 16, false, 512, 0, true>;
+}

@@ -11,6 +11,11 @@ const void* tile_d5_w32(bool smem);
 const void* tile_d16(bool smem);
 const void* tile_g5(bool smem);
 const void* tile_g16(bool smem);
+// ... the same with the XF code (models with g3a_otherfood, g3a_spawn or prey_preferences), 16 warps per tile
+const void* tile_x_d5(bool smem);
+const void* tile_x_d16(bool smem);
+const void* tile_x_g5(bool smem);
+const void* tile_x_g16(bool smem);
 // thread kernel (g3_thread_kernel.cuh): (big = 1024-thread variant, plain doubles only), constmat
 const void* thread_d5(bool big, bool constmat);
 const void* thread_d16(bool constmat);

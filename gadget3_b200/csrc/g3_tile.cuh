@@ -126,6 +126,7 @@ struct TArgs {
     int inc_off, inc_n;     // tb: global columns that receive maturing fish
     int inc_any_mask;       // bit (cur_step-1): some column receives maturing fish on that step
     int sp_off, sp_n;       // tb: the spawning stocks
+    int xf;                 // the model needs the XF instantiation (g3a_otherfood, g3a_spawn, prey_preferences)
     int spawn_mask;         // bit (cur_step-1): some stock spawns on that step
     int any_ghost;          // some column is split into several units
     int NWc;                // band width the tables are laid out for (the kernel's NW)
@@ -247,7 +248,9 @@ __device__ __forceinline__ void grow_gather(const double* __restrict__ pN, const
 
 // T: double or Dual<N>; NW: compiled width of the growth band (maxlengthgroupgrowth + 1 <= NW);
 // SMEM: stock state in shared memory (smem = its base) or in the global slab
-template <class T, int NW, bool SMEM, int NBV = 0>
+// XF: the model uses g3a_otherfood, g3a_spawn or prey_preferences (TArgs::xf, set by the planner). The kernels of the models
+// that do not are compiled without that code: beside the hot loops it cost 5-9 % (registers, instruction footprint).
+template <class T, int NW, bool SMEM, int NBV = 0, bool XF = true>
 __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr, const int warp, const int lane, const int cta,
                                           const int ncta G3T_CTX_DECL) {
     constexpr int NTAN = Tan<T>::n;
@@ -351,7 +354,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 #pragma unroll
                 for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
                 const double plen = spred && Q.suit_kind != G3SUIT_ANDERSENFLEET ? R[Tst[Q.pred_stock].midlen_roff + pl] : pml[Ps.L - 1];
-                if (Q.pref_slot < 0)
+                if (!XF || Q.pref_slot < 0)
                     for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, suitability_of<T>(Q.suit_kind, sp, pml[l], plen));
                 else {
                     // prey_preference p (R/action_predate.R:220-225): (S E B)^p = S^p E^p B^p; the table holds S^p E^(p-1) -- x E x B^p
@@ -400,7 +403,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             // g3a_spawn (R/action_spawn.R:86-233): proportion spawning and spawning mortality by length, fecundity weights
             // midlen^p1 age^p2; per output stock the offspring's share by length group -- exp(-((midlen - mean) / sd)^2 / 2) over
             // avoid_zero(its sum over the stock's areas and lengths) -- and their weight alpha midlen^beta
-            if (St.sp_ioff >= 0) {
+            if (XF && St.sp_ioff >= 0) {
                 const int32_t* Sp = I + St.sp_ioff;
                 for (int which = 0; which < 2; which++) {
                     const int kind = Sp[which ? G3SP_MORT_KIND : G3SP_PROP_KIND];
@@ -616,7 +619,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 
             // ================= g3a_otherfood (R/action_renewal.R:276-308): number and mean weight assigned from formulas
             bool of_any = false;
-            for (int s = 0; s < NS; s++) {
+            for (int s = 0; XF && s < NS; s++) {
                 const StockRec& St = Tst[s];
                 if (St.of_ioff < 0) continue;
                 of_any = true;
@@ -700,7 +703,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             for (int r = 0; r < U.len; r++) {
                                 const T n = S(A.s_num + c_lo + r);
                                 T bm = by_number ? n : n * S(A.s_wgt + c_lo + r);
-                                if (Q.pref_slot >= 0) bm = xpow(bm, SLOT(Q.pref_slot));
+                                if (XF && Q.pref_slot >= 0) bm = xpow(bm, SLOT(Q.pref_slot));
 #pragma unroll
                                 for (int u = 0; u < 4; u++)
                                     cs[u] = cs[u] + G(Q.g_suit + min(pl0 + u, Q.PL - 1) * L + U.lo + r) * bm;
@@ -868,7 +871,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             const int ts = tb[Q.tsid_off + Cl.ridx];
                             if (ts < 0) continue;
                             cfac(Q, ts, r0, cf);
-                            if (Q.pref_slot >= 0) {             // biomass^prey_preference for this predator
+                            if (XF && Q.pref_slot >= 0) {       // biomass^prey_preference for this predator
                                 const T p = SLOT(Q.pref_slot);
 #pragma unroll
                                 for (int b = 0; b < NB; b++) tp[b] = tp[b] + cf[b] * xpow(B0[b], p);
@@ -953,7 +956,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     if (St.g_smort >= 0) num[b] = num[b] - spn * G(St.g_smort + l);
                 }
             };
-            const bool spawn_step = (A.spawn_mask >> step) & 1;
+            const bool spawn_step = XF && ((A.spawn_mask >> step) & 1);
 
             // ================= own units, pass 2: natural mortality, growth (+ maturing split), and -- unless maturing fish are
             // about to arrive -- renewal and the collect vectors. Length growth only looks DOWN the length axis, so sweeping
@@ -973,7 +976,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 double* const pNum = SP(A.s_num + c_lo);
                 double* const pWgt = SP(A.s_wgt + c_lo);
                 bool spawn_here = false;    // this stock spawns at this step
-                if (spawn_step && St.sp_ioff >= 0) { const int rs = I[St.sp_ioff + G3SP_RUN_STEP]; spawn_here = rs == 0 || rs == step + 1; }
+                if (XF && spawn_step && St.sp_ioff >= 0) { const int rs = I[St.sp_ioff + G3SP_RUN_STEP]; spawn_here = rs == 0 || rs == step + 1; }
                 if (!has_mort && grow_n < 0 && !inc_here && !ren_mask && xact == 0 && !spawn_here) continue;
                 const T mortf = has_mort ? G(St.g_mort + idt * St.ncol + Cl.col) : T(1.0);
                 const int nblk = (U.len + NB - 1) / NB;
@@ -986,14 +989,14 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         for (int b = 0; b < NB; b++) {
                             num[b] = ldT<T>(pNum + (unsigned)(r0 + b) * C) * mortf; wgt[b] = ldT<T>(pWgt + (unsigned)(r0 + b) * C);
                         }
-                        if (spawn_here) spawn_rows(St, Cl, U.lo + r0, nb, num, wgt, sp_acc);
+                        if (XF && spawn_here) spawn_rows(St, Cl, U.lo + r0, nb, num, wgt, sp_acc);
                         if (!inc_here) finish_block(Cl, St, U.lo + r0, nb, num, wgt, false, ren_mask);
                         else {
 #pragma unroll
                             for (int b = 0; b < NB; b++) if (b < nb) stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]);
                         }
                     }
-                    if (spawn_here) GS(U.g_sps, sp_acc);
+                    if (XF && spawn_here) GS(U.g_sps, sp_acc);
                     continue;
                 }
                 const T remf = trans_now ? G(Cl.g_remf) : T(0.0);
@@ -1030,7 +1033,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 #pragma unroll
                     for (int b = 0; b < NB; b++) de[b] = num[b];
                     div_az_n(wgt, de);
-                    if (spawn_here) spawn_rows(St, Cl, U.lo + r0, nb, num, wgt, sp_acc);      // (before the maturing fish move: order 6 < 7)
+                    if (XF && spawn_here) spawn_rows(St, Cl, U.lo + r0, nb, num, wgt, sp_acc);      // (before the maturing fish move: order 6 < 7)
                     if (trans_now) {
                         if (stash) {
 #pragma unroll
@@ -1051,7 +1054,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             if (b < nb) { stT<T>(pNum + (unsigned)(r0 + b) * C, num[b]); stT<T>(pWgt + (unsigned)(r0 + b) * C, wgt[b]); }
                     }
                 }
-                if (spawn_here) GS(U.g_sps, sp_acc);
+                if (XF && spawn_here) GS(U.g_sps, sp_acc);
             }
 
             // ================= columns that receive maturing fish finish once every source column has grown. That part is
@@ -1087,7 +1090,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             // ================= g3a_spawn, order 8 (R/action_spawn.R:183-218): the offspring arrive in the youngest age of the
             // output stocks. s = the parent units' parts in unit order, r = the recruitment function, every (output stock, area,
             // block of rows) is dealt to a warp; a warp works out r of a parent when its first block of that parent comes up.
-            if (spawn_step) {
+            if (XF && spawn_step) {
                 G3T_BAR();
                 int kblk = 0;
                 for (int i = 0; i < A.sp_n; i++) {
@@ -1400,11 +1403,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 }
 
 #ifdef __CUDACC__
-template <class T, int NW, bool SMEM, int MAXT, int NBV = 0>
+template <class T, int NW, bool SMEM, int MAXT, int NBV = 0, bool XF = false>
 __global__ void __launch_bounds__(MAXT, 1) eval_tile_kernel(const __grid_constant__ TArgs A) {
     extern __shared__ __align__(16) double g3t_smem[];
     __shared__ int g3t_ctr[8];
-    tile_body<T, NW, SMEM, NBV>(A, g3t_smem, g3t_ctr, threadIdx.x >> 5, threadIdx.x & 31, blockIdx.x, gridDim.x);
+    tile_body<T, NW, SMEM, NBV, XF>(A, g3t_smem, g3t_ctr, threadIdx.x >> 5, threadIdx.x & 31, blockIdx.x, gridDim.x);
 }
 #endif
 

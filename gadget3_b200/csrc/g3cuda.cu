@@ -137,6 +137,10 @@ int tile_geom(g3cuda_model* m, TileGeom* g) {
     const bool wide = m->tplan.maxn > 4;
     const int threads = (m->targs.W + 1) * 32;
     if (threads > 512 && (dual || wide)) return fail(G3CUDA_EUNSUPP, "more than 16 warps per tile exist for plain values and narrow growth bands only");
+    const bool xf = m->targs.xf != 0;
+    if (xf && threads > 512) return fail(G3CUDA_EUNSUPP, "more than 16 warps per tile: not for models with g3a_otherfood, g3a_spawn or prey_preferences");
+    if (xf) g->fn = dual ? (wide ? g3i::tile_x_g16(g->in_smem) : g3i::tile_x_g5(g->in_smem)) : (wide ? g3i::tile_x_d16(g->in_smem) : g3i::tile_x_d5(g->in_smem));
+    else
     g->fn = dual ? (wide ? g3i::tile_g16(g->in_smem) : g3i::tile_g5(g->in_smem))
                  : (wide ? g3i::tile_d16(g->in_smem) : threads > 768 ? g3i::tile_d5_w32(g->in_smem) : threads > 512 ? g3i::tile_d5_w24(g->in_smem) : g3i::tile_d5(g->in_smem));
     CUDA_TRY(cudaFuncSetAttribute(g->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));

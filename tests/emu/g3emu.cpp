@@ -15,8 +15,8 @@ using namespace g3t;
 struct Bar { std::barrier<>* b; };
 void bar_wait(void* p) { static_cast<Bar*>(p)->b->arrive_and_wait(); }
 
-template <class T, int NW, bool SMEM>
-void run(const TArgs& A, int W, int ncta, size_t smem_doubles) {
+template <class T, int NW, bool SMEM, bool XF>
+void run_xf(const TArgs& A, int W, int ncta, size_t smem_doubles) {
     for (int cta = 0; cta < ncta; cta++)
         for (int lane = 0; lane < A.lanes_per_tile; lane++) {
             std::vector<double> smem(smem_doubles + 64, 0.0);
@@ -26,9 +26,14 @@ void run(const TArgs& A, int W, int ncta, size_t smem_doubles) {
             EmuCtx ctx{bar_wait, &bar};
             std::vector<std::thread> th;
             for (int w = 0; w <= W; w++)
-                th.emplace_back([&, w]() { tile_body<T, NW, SMEM>(A, smem.data(), ctr, w, lane, cta, ncta, ctx); });
+                th.emplace_back([&, w]() { tile_body<T, NW, SMEM, 0, XF>(A, smem.data(), ctr, w, lane, cta, ncta, ctx); });
             for (auto& t : th) t.join();
         }
+}
+// the instantiation the product's dispatch picks (TArgs::xf)
+template <class T, int NW, bool SMEM>
+void run(const TArgs& A, int W, int ncta, size_t smem_doubles) {
+    if (A.xf) run_xf<T, NW, SMEM, true>(A, W, ncta, smem_doubles); else run_xf<T, NW, SMEM, false>(A, W, ncta, smem_doubles);
 }
 }  // namespace
 
