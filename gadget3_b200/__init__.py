@@ -6,7 +6,8 @@ reference's ``g3_to_r()`` / ``g3_to_tmb()`` (R/run_r.R, R/run_tmb.R). The comput
 hand-written CUDA library in ``csrc/`` reached through the C ABI in ``include/g3cuda.h``.
 """
 from .formula import (G3Unsupported, ParameterTemplate, Lookup, age, area, cur_step, cur_step_size,
-                      cur_year, g3_as_integer, g3_avoid_zero, g3_exp, g3_init_val, g3_log, g3_parameterized, g3_sqrt)
+                      cur_year, g3_as_integer, g3_avoid_zero, g3_exp, g3_init_val, g3_log, g3_parameterized, g3_sqrt,
+                      g3_timevariable)
 from .stock import (g3_areas, g3_fleet, g3_stock, g3_stock_def, g3s_age, g3s_length, g3s_livesonareas)
 from .actions import (g3_action_order, g3_suitability_andersen, g3_suitability_andersenfleet,
                       g3_suitability_constant, g3_suitability_exponential, g3_suitability_exponentiall50,

@@ -700,12 +700,15 @@ def build_spawn_rig(seed=123):
     return model, p
 
 
-def build_mini_spawn(seed=123):
+def build_mini_spawn(seed=123, timevar=False):
     """A closed life cycle on two areas: the immature stock grows, matures into the mature stock (continuous maturity,
     every step) and ages into it; the mature stock spawns on step 2 -- proportion spawning by length
     (g3_suitability_exponentiall50), Ricker recruitment, spawning mortality -- into the immature stock's youngest age
-    (g3a_spawn, R/action_spawn.R:86-233). A fleet, two likelihood components, understocking."""
-    from . import g3a_spawn, g3a_spawn_recruitment_ricker
+    (g3a_spawn, R/action_spawn.R:86-233). A fleet, two likelihood components, understocking.
+    `timevar`: time-varying natural mortality -- the immature stock's M by age AND year
+    (g3_parameterized(by_year = TRUE), R/params.R:122-129), the mature stock's M a g3_timevariable that steps up in
+    2002 step 3 and again in 2004 (R/timevariable.R:1-31)."""
+    from . import g3a_spawn, g3a_spawn_recruitment_ricker, g3_timevariable, g3a_naturalmortality_exp
     areas = g3_areas(["a", "b"])
     imm = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "imm"}, range(10, 60, 5)), 1, 3), areas)
     mat = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "mat"}, range(10, 60, 5)), 2, 5), areas)
@@ -717,7 +720,13 @@ def build_mini_spawn(seed=123):
     actions = [
         g3a_time(2000, 2004, [3, 3, 3, 3]),
         g3a_initialconditions_normalcv(imm), g3a_initialconditions_normalcv(mat),
-        g3a_naturalmortality(imm), g3a_naturalmortality(mat),
+        (g3a_naturalmortality(imm, g3a_naturalmortality_exp(g3_parameterized("Mt", by_stock=True, by_age=True, by_year=True)))
+         if timevar else g3a_naturalmortality(imm)),
+        (g3a_naturalmortality(mat, g3a_naturalmortality_exp(g3_timevariable("matM", OrderedDict([
+            ("init", g3_parameterized("M.early", by_stock=True, value=0.2)),
+            ("2002-03", g3_parameterized("M.mid", by_stock=True, value=0.3)),
+            ("2004", g3_parameterized("M.late", by_stock=True, value=0.15))]))))
+         if timevar else g3a_naturalmortality(mat)),
         g3a_growmature(imm, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3), maturity_f=g3a_mature_continuous(),
                        output_stocks=[mat], transition_f=True),
         g3a_growmature(mat, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3)),
@@ -726,7 +735,11 @@ def build_mini_spawn(seed=123):
                   mortality_f=g3_parameterized("spawn.mort", by_stock=True, value=0.1), output_stocks=[imm], run_step=2,
                   # (lighter than the fish already there: the mean weight of the cells they join moves)
                   alpha_f=g3_parameterized("spawn.walpha", by_stock=True, value=0.8e-5, optimise=False)),
-        g3a_predate_fleet(fl, [imm, mat], suitabilities=g3_suitability_exponentiall50(by_stock="species"),
+        g3a_predate_fleet(fl, [imm, mat],
+                          # `timevar`: the fleet's l50 by year (a selectivity that changes over time)
+                          suitabilities=(g3_suitability_exponentiall50(l50=g3_parameterized("l50", by_stock="species", by_predator=True, by_year=True),
+                                                                       by_stock="species") if timevar
+                                         else g3_suitability_exponentiall50(by_stock="species")),
                           catchability_f=g3a_predate_catchability_totalfleet(g3_timeareadata("landings", land, "weight", areas=areas))),
         g3l_understocking([imm, mat]),
     ]
@@ -746,7 +759,16 @@ def build_mini_spawn(seed=123):
     p = g3_init_val(p, "*.lencv", 0.15, optimise=False)
     p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
     p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
-    p = g3_init_val(p, "*.M.#", 0.2, lower=0.01, upper=1)
+    if timevar:
+        for y in yrs:
+            for a in (1, 2, 3):
+                p = g3_init_val(p, f"fish_imm.Mt.{y}.{a}", 0.15 + 0.02 * a + 0.03 * (y - 2000), lower=0.01, upper=1)
+        p = g3_init_val(p, "fish_mat.M.early", 0.2, lower=0.05, upper=0.5)
+        p = g3_init_val(p, "fish_mat.M.mid", 0.3, lower=0.05, upper=0.6)
+        p = g3_init_val(p, "fish_mat.M.late", 0.15, lower=0.05, upper=0.5)
+        p = g3_init_val(p, "*.M.#", 0.2, optimise=False)                # (the initial conditions' M-based abundance)
+    else:
+        p = g3_init_val(p, "*.M.#", 0.2, lower=0.01, upper=1)
     p = g3_init_val(p, "init.F", 0.3, lower=0.1, upper=1)
     p = g3_init_val(p, "recage", 1, optimise=False)
     p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
@@ -762,7 +784,57 @@ def build_mini_spawn(seed=123):
     p = g3_init_val(p, "*.spawn.lambda", 1e-6, lower=1e-7, upper=5e-6)
     p = g3_init_val(p, "*.rec.sd", 3, lower=1, upper=6)
     p = g3_init_val(p, "fish.f_comm.alpha", 0.1, lower=0.01, upper=1)
-    p = g3_init_val(p, "fish.f_comm.l50", 30, lower=15, upper=45)
+    if timevar:
+        for y in yrs:
+            p = g3_init_val(p, f"fish.f_comm.l50.{y}", 26 + 2 * (y - 2000), lower=15, upper=45)
+    else:
+        p = g3_init_val(p, "fish.f_comm.l50", 30, lower=15, upper=45)
+    return model, p
+
+
+def build_timevar_rig(seed=123):
+    """Two stocks that only die, with time-varying natural mortality: `st_year` by age, year and
+    step (g3_parameterized(by_year = TRUE, by_step = TRUE), R/params.R:122-129), `st_tv` through a g3_timevariable that
+    switches in 2001 step 2 and in 2002 (R/timevariable.R:1-31). The numbers at the start of a step over those of the step
+    before must be exp(-M dt) of the M in force (tests/test_oracle_kat.py)."""
+    from . import g3_timevariable, g3a_naturalmortality_exp
+    gp = g3_parameterized
+    areas = g3_areas(["a"])
+    sy = g3s_livesonareas(g3s_age(g3_stock("st_year", range(10, 50, 10)), 1, 2), areas)
+    sv = g3s_livesonareas(g3s_age(g3_stock("st_tv", range(10, 50, 10)), 1, 1), areas)
+    tv = g3_timevariable("M", OrderedDict([("init", gp("tvM.init", value=0.1)), ("2001-02", gp("tvM.a", value=0.4)),
+                                           ("2002", gp("tvM.b", value=0.2) * 1.5)]))
+    actions = [
+        g3a_time(2000, 2002, [3, 3, 6]),
+        g3a_initialconditions_normalcv(sy), g3a_initialconditions_normalcv(sv),
+        g3a_naturalmortality(sy, g3a_naturalmortality_exp(gp("Mt", by_stock=True, by_age=True, by_year=True, by_step=True))),
+        g3a_naturalmortality(sv, g3a_naturalmortality_exp(tv)),
+    ]
+    rng = np.random.default_rng(seed)
+    yrs = [2000, 2001, 2002]
+    si = dict(year=yrs, step=[3] * 3, number=list(rng.uniform(1e3, 1e4, 3)))
+    actions.append(g3l_abundancedistribution("si", si, stocks=[sy, sv], function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    actions += [g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    for y in yrs:
+        for st in (1, 2, 3):
+            for a in (1, 2):
+                p = g3_init_val(p, f"st_year.Mt.{y}.{st}.{a}", 0.1 + 0.05 * (y - 2000) + 0.02 * st + 0.01 * a, lower=0.01, upper=1)
+    p = g3_init_val(p, "tvM.init", 0.1, lower=0.01, upper=1)
+    p = g3_init_val(p, "tvM.a", 0.4, lower=0.01, upper=1)
+    p = g3_init_val(p, "tvM.b", 0.2, lower=0.01, upper=1)
+    p = g3_init_val(p, "*.Linf", 50, optimise=False)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.1, upper=0.6)
+    p = g3_init_val(p, "*.t0", -1.0, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.3, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, optimise=False)
+    p = g3_init_val(p, "init.F", 0.3, optimise=False)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
     return model, p
 
 
@@ -957,5 +1029,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn,
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "TIMEVAR_RIG": build_timevar_rig,
            "LING": build_ling}

@@ -48,9 +48,11 @@ struct KArgs {
     int t_slot, t_num, t_wgt, t_tn, t_tw, t_mv, t_suit, t_scr, t_ctot;
     int t_mort[MAXS], t_pw[MAXS], t_g[MAXS], t_gr[MAXS], t_gn[MAXS], t_rd[MAXS], t_rw[MAXS], t_ms[MAXC];
     int t_x[MAXX];                          // collect vectors
-    int t_suitq[32];                        // per predator-prey pair: suitability [predator length][prey length]
+    int w_suit_nset[32];                    // per pair: sets of suitability parameters (1 unless the selectivity varies with time)
+    int t_suitq[32];                        // per predator-prey pair: suitability [set][predator length][prey length]
     int t_pts[MAXS], t_pmc[MAXS];           // per stock predator: totals / consumption factors [area][length]; max consumption [length]
     int t_mig[MAXS], t_mig_steps[MAXS];     // migration matrices [step][dest][src]; steps on which the stock migrates
+    int w_mort_nset[MAXS];                  // slot sets of a time-varying M (1 otherwise)
     int t_sps;                              // per stock: the recruitment sum s of a spawning stock at this step (g3a_spawn)
     int t_remf, t_colbase[MAXS], t_cmat[MAXS];      // per global column: unclaimed share; first global column; constant-maturity ratios
     const int4* t_colinc;                   // per global column: (compact index of the source column's first cell or -1, ratio slot, step mask, 0)

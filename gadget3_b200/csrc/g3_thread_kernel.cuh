@@ -71,15 +71,13 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
         for (int i = 0; i < A.NSLOT; i++) W(A.t_slot + i) = eval_slot_g<T>(I, R, prow, seed, i);
 #define SLOT(i) W(A.t_slot + (i))
 
+        // the set of suitability parameters in force at step t (time-varying selectivity), 0 where there is one
+        auto suit_set = [&](const int32_t* Q, const int t) { return Q[G3PP_SUIT_TMAP] >= 0 ? I[Q[G3PP_SUIT_TMAP] + t] : 0; };
         // ================= per-evaluation tables
         for (int q = 0; q < A.NPP; q++) {           // suitability (R/suitability.R:5-30): [predator length][prey length]
             const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
             const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
             const int32_t* Ps = I + I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN;
-            const int32_t* ss = I + Q[G3PP_SUIT_OFF];
-            T sp[5];
-#pragma unroll
-            for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
             const bool spred = P[G3P_KIND] == G3PRED_STOCK;
             const int32_t* Pp = I + I[G3H_STOCK_OFF] + (spred ? P[G3P_STOCK] : 0) * G3S_LEN;
             const int PL = spred ? Pp[G3S_L] : 1, L = Ps[G3S_L];
@@ -87,13 +85,22 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             // in the predator's total, x B^p in the consumption (one E cancels against cons' 1 / E)
             const bool pref = Q[G3PP_PREF] >= 0;
             const T pp_ = pref ? SLOT(Q[G3PP_PREF]) : T(1.0), ef = pref ? xpow(SLOT(Q[G3PP_ENERGY]), pp_ - 1.0) : T(1.0);
-            for (int pl = 0; pl < PL; pl++)
-                for (int l = 0; l < L; l++) {
-                    const T sv = suitability_of<T>(Q[G3PP_SUIT_KIND], sp, R[Ps[G3S_MIDLEN_ROFF] + l],
-                        spred && Q[G3PP_SUIT_KIND] != G3SUIT_ANDERSENFLEET ? R[Pp[G3S_MIDLEN_ROFF] + pl] : R[Ps[G3S_MIDLEN_ROFF] + L - 1]);
-                    if (REPORT && live && pref) A.report[A.rep_pp[q] + pl * L + l] = val(sv);       // suit_<prey>_<pred>__report is S itself
-                    W(A.t_suitq[q] + pl * L + l) = pref ? xpow(sv, pp_) * ef : sv;
-                }
+            // one table per set of suitability parameters: one set, unless the selectivity varies with time (by_year / by_step
+            // tables, g3_timevariable); the report shows the set of the last step
+            const int last_set = Q[G3PP_SUIT_TMAP] >= 0 ? I[Q[G3PP_SUIT_TMAP] + min(total_steps, NT - 1)] : 0;
+            for (int sset = 0; sset < A.w_suit_nset[q]; sset++) {
+                const int32_t* ss = I + Q[G3PP_SUIT_OFF] + 6 * sset;
+                T sp[5];
+#pragma unroll
+                for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
+                for (int pl = 0; pl < PL; pl++)
+                    for (int l = 0; l < L; l++) {
+                        const T sv = suitability_of<T>(Q[G3PP_SUIT_KIND], sp, R[Ps[G3S_MIDLEN_ROFF] + l],
+                            spred && Q[G3PP_SUIT_KIND] != G3SUIT_ANDERSENFLEET ? R[Pp[G3S_MIDLEN_ROFF] + pl] : R[Ps[G3S_MIDLEN_ROFF] + L - 1]);
+                        if (REPORT && live && pref && sset == last_set) A.report[A.rep_pp[q] + pl * L + l] = val(sv);       // suit_<prey>_<pred>__report is S itself
+                        W(A.t_suitq[q] + (sset * PL + pl) * L + l) = pref ? xpow(sv, pp_) * ef : sv;
+                    }
+            }
         }
         // stock predators: maximum consumption per predator length without the step length,
         // m0 exp(m1 T - m2 T^3) l^m3 (R/action_predate.R:190-205)
@@ -132,9 +139,10 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             const double pdl = R[St[G3S_PLUSDL_ROFF]];
             // natural mortality factor per column and distinct step length (R/action_naturalmortality.R:26)
             if (St[G3S_MORT_OFF] >= 0)
-                for (int idt = 0; idt < A.w_ndt; idt++)
-                    for (int col = 0; col < ncol; col++)
-                        W(A.t_mort[s] + idt * ncol + col) = xexp(-SLOT(I[St[G3S_MORT_OFF] + col]) * (A.w_dt_len[idt] / 12.0));
+                for (int ms = 0; ms < A.w_mort_nset[s]; ms++)       // (one set unless M varies with time)
+                    for (int idt = 0; idt < A.w_ndt; idt++)
+                        for (int col = 0; col < ncol; col++)
+                            W(A.t_mort[s] + (ms * A.w_ndt + idt) * ncol + col) = xexp(-SLOT(I[St[G3S_MORT_OFF] + ms * ncol + col]) * (A.w_dt_len[idt] / 12.0));
             // renewal length distribution, normalised, and weight (R/action_renewal.R:56-80)
             for (int k = 0; k < St[G3S_N_RENEW]; k++) {
                 const int32_t* Rn = I + St[G3S_RENEW_OFF] + k * G3R_LEN;
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                     const int cell = c0 + col * L + l;
                                     T bm = by_number ? W(A.t_num + cell) : W(A.t_num + cell) * W(A.t_wgt + cell);
                                     if (Q[G3PP_PREF] >= 0) bm = xpow(bm, SLOT(Q[G3PP_PREF]));
-                                    cs = cs + W(A.t_suitq[q] + pl * L + l) * bm;
+                                    cs = cs + W(A.t_suitq[q] + suit_set(Q, t) * PL * L + pl * L + l) * bm;
                                 }
                                 if (spred) W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) = W(A.t_pts[Q[G3PP_PRED]] + ts * PL + pl) + cs * energy;
                                 else EOT(ts) = EOT(ts) + cs;
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             kq[k] = q;
                             const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
                             const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
-                            ksuit[k] = (unsigned)A.t_suitq[q] * NTH;
+                            ksuit[k] = (unsigned)(A.t_suitq[q] + suit_set(Q, t) * (P[G3P_KIND] == G3PRED_STOCK ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1) * L) * NTH;
                             if (P[G3P_KIND] == G3PRED_STOCK) { kpl[k] = I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L]; kpts[k] = A.t_pts[Q[G3PP_PRED]]; }
                             for (int x = 0; x < A.NX; x++) if ((A.w_x_ppmask[x] >> q) & 1) kx[k] |= 1u << x;
                         }
@@ -544,7 +552,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             if (A.pp_tsid[q * A.maxnarea + col / nage] < 0) continue;
                             for (int l = 0; l < L; l++) {
                                 const int cell = c0 + col * L + l;
-                                const T sn = W(A.t_suitq[q] + l) * W(A.t_num + cell);
+                                const T sn = W(A.t_suitq[q] + suit_set(Q, t) * L + l) * W(A.t_num + cell);
                                 A.report[A.rep_pp[q] + L + ((size_t)t * ncol + col) * L + l] = val(pk == G3PRED_NUMBERFLEET ? sn : sn * W(A.t_wgt + cell));
                             }
                         }
@@ -581,7 +589,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 // loop: the band P(l - d -> l) and the weight gains are loaded once per l for all columns.
                 const int gsz = (grow_n + 1) * L;
                 const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
-                const T* pmort = ws + (unsigned)(A.t_mort[s] + idt * ncol) * NTH;
+                const int mset = St[G3S_MORT_TMAP_OFF] >= 0 ? I[St[G3S_MORT_TMAP_OFF] + t] : 0;        // time-varying M: this step's table
+                const T* pmort = ws + (unsigned)(A.t_mort[s] + (mset * A.w_ndt + idt) * ncol) * NTH;
                 const int4* cinc = A.t_colinc + A.t_colbase[s];
                 // Wide bands (streamed per column, below) sweep the columns in blocks of t_cblk: the n+1 rows a
                 // column re-reads while l walks down then stay in L1/L2 instead of coming back from HBM
@@ -947,7 +956,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 const int n = I[I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN + G3S_L] *
                               (P[G3P_KIND] == G3PRED_STOCK ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1);
                 if (Q[G3PP_PREF] >= 0) continue;        // (written when the table was filled: the table is not S itself)
-                for (int i = 0; i < n; i++) A.report[A.rep_pp[q] + i] = val(W(A.t_suitq[q] + i));
+                for (int i = 0; i < n; i++) A.report[A.rep_pp[q] + i] = val(W(A.t_suitq[q] + suit_set(Q, min(total_steps, NT - 1)) * n + i));
             }
         if (tile_t == 0) {
             A.nll[b] = val(out);

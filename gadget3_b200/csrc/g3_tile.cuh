@@ -45,7 +45,8 @@ struct StockRec {
     int mort_ioff, midlen_roff, plusdl_roff, grow_ioff, mat_ioff, init_ioff;
     int n_renew, renew_ioff;
     int ren_off;            // tb: per renewal (run step or 0 = every step, age index it lands in, offset in I of its factor slots per year x area)
-    int g_mort;             // [idt][col] exp(-M dt)
+    int g_mort;             // [set][idt][col] exp(-M dt)
+    int mort_tmap, mort_nset;   // I: the slot set of M each step uses (time-varying M), or -1; number of sets
     int g_rd, g_rw;         // [k][l] renewal numbers shape (x 1e4) and weight
     int g_wq;               // [l] walpha * midlen^wbeta; NW - 1 zero rows before row 0, NBX - 1 after row L - 1
     int g_band, g_bandr;    // destination-oriented growth bands, staying (or whole) / maturing part: [set][idt][(L + NBX - 1) * NW]
@@ -81,7 +82,8 @@ struct UnitRec {
 };
 struct PairRec {
     int pred, prey, suit_kind, suit_ioff, energy_slot, pref_slot, pred_kind, pred_stock, PL;
-    int g_suit;             // [PL][L]
+    int g_suit;             // [set][PL][L]
+    int suit_tmap, suit_nset;   // I: the slot set of the suitability each step uses (time-varying selectivity), or -1; number of sets
     int g_part;             // [prey unit][PL] partial suitable biomass
     int cxmask;             // bit j: feeds the prey stock's j-th catch collect vector
     int tsid_off;           // tb: [prey narea] accumulator (fleet) / predator area index (stock predator), or -1
@@ -248,6 +250,12 @@ __device__ __forceinline__ void grow_gather(const double* __restrict__ pN, const
 
 // T: double or Dual<N>; NW: compiled width of the growth band (maxlengthgroupgrowth + 1 <= NW);
 // SMEM: stock state in shared memory (smem = its base) or in the global slab
+// Experiment switch (variant builds only, tools/build_variant.sh): G3T_LEAN bit 0 = no migration, bit 1 = totalfleet predation
+// only, bit 2 = no constant maturity, bit 3 = sumofsquares / log survey indices only -- the code is compiled out.
+#ifndef G3T_LEAN
+#define G3T_LEAN 0
+#endif
+constexpr bool F_MIG = !(G3T_LEAN & 1), F_PRED = !(G3T_LEAN & 2), F_CMAT = !(G3T_LEAN & 4), F_LIKE = !(G3T_LEAN & 8);
 // XF: the model uses g3a_otherfood, g3a_spawn or prey_preferences (TArgs::xf, set by the planner). The kernels of the models
 // that do not are compiled without that code: beside the hot loops it cost 5-9 % (registers, instruction footprint).
 template <class T, int NW, bool SMEM, int NBV = 0, bool XF = true>
@@ -347,20 +355,22 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             const StockRec& Ps = Tst[Q.prey];
             const bool spred = Q.pred_kind == G3PRED_STOCK;
             const double* pml = R + Ps.midlen_roff;
+            for (int sset = 0; sset < Q.suit_nset; sset++)        // (one set unless the selectivity varies with time)
             for (int pl = 0; pl < Q.PL; pl++) {
                 if (!mine()) continue;
-                const int32_t* ss = I + Q.suit_ioff;
+                const int32_t* ss = I + Q.suit_ioff + 6 * sset;
+                const int gsu = Q.g_suit + sset * Q.PL * Ps.L;
                 T sp[5];
 #pragma unroll
                 for (int k = 0; k < 5; k++) sp[k] = ss[k] >= 0 ? SLOT(ss[k]) : T(0.0);
                 const double plen = spred && Q.suit_kind != G3SUIT_ANDERSENFLEET ? R[Tst[Q.pred_stock].midlen_roff + pl] : pml[Ps.L - 1];
                 if (!XF || Q.pref_slot < 0)
-                    for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, suitability_of<T>(Q.suit_kind, sp, pml[l], plen));
+                    for (int l = 0; l < Ps.L; l++) GS(gsu + pl * Ps.L + l, suitability_of<T>(Q.suit_kind, sp, pml[l], plen));
                 else {
                     // prey_preference p (R/action_predate.R:220-225): (S E B)^p = S^p E^p B^p; the table holds S^p E^(p-1) -- x E x B^p
                     // in the predator's total, x B^p in the consumption (where one E cancels against cons' 1 / E)
                     const T p = SLOT(Q.pref_slot), ef = xpow(SLOT(Q.energy_slot), p - 1.0);
-                    for (int l = 0; l < Ps.L; l++) GS(Q.g_suit + pl * Ps.L + l, xpow(suitability_of<T>(Q.suit_kind, sp, pml[l], plen), p) * ef);
+                    for (int l = 0; l < Ps.L; l++) GS(gsu + pl * Ps.L + l, xpow(suitability_of<T>(Q.suit_kind, sp, pml[l], plen), p) * ef);
                 }
             }
         }
@@ -525,8 +535,9 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             const int L = St.L, col = Cl.col;
             const double* midlen = R + St.midlen_roff;
             if (St.mort_ioff >= 0)      // natural mortality factor per distinct step length (R/action_naturalmortality.R:26)
-                for (int idt = 0; idt < A.ndt; idt++)
-                    GS(St.g_mort + idt * St.ncol + col, xexp(-SLOT(I[St.mort_ioff + col]) * (A.dt_len[idt] / 12.0)));
+                for (int ms = 0; ms < St.mort_nset; ms++)       // (one set unless M varies with time)
+                    for (int idt = 0; idt < A.ndt; idt++)
+                        GS(St.g_mort + (ms * A.ndt + idt) * St.ncol + col, xexp(-SLOT(I[St.mort_ioff + ms * St.ncol + col]) * (A.dt_len[idt] / 12.0)));
             // g3a_initialconditions (R/action_renewal.R:83-163)
             if (St.init_ioff < 0) {
                 for (int l = 0; l < L; l++) { SS(A.s_num + Cl.cell0 + l, T(0.0)); SS(A.s_wgt + Cl.cell0 + l, T(1.0)); }
@@ -633,7 +644,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             {
                 bool mig_any = of_any;      // (one barrier for both)
                 ucnt = 0;
-                for (int s = 0; s < NS; s++) {
+                for (int s = 0; F_MIG && s < NS; s++) {
                     const StockRec& St = Tst[s];
                     if (!((St.mig_steps >> step) & 1)) continue;
                     mig_any = true;
@@ -691,10 +702,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     for (int j = 0; j < St.pp_n; j++) {
                         const int q = tb[St.pp_off + j];
                         const PairRec& Q = Tpp[q];
-                        if (Q.pred_kind == G3PRED_LINEARFLEET || Q.pred_kind == G3PRED_EFFORTFLEET) continue;     // no total needed
+                        if (F_PRED && (Q.pred_kind == G3PRED_LINEARFLEET || Q.pred_kind == G3PRED_EFFORTFLEET)) continue;     // no total needed
                         if (tb[Q.tsid_off + Cl.ridx] < 0) continue;
-                        const bool spred = Q.pred_kind == G3PRED_STOCK;
-                        const bool by_number = Q.pred_kind == G3PRED_NUMBERFLEET;       // suit = S * num (R/action_predate.R:7-11)
+                        const bool spred = F_PRED && Q.pred_kind == G3PRED_STOCK;
+                        const bool by_number = F_PRED && Q.pred_kind == G3PRED_NUMBERFLEET;       // suit = S * num (R/action_predate.R:7-11)
+                        const int gsu = Q.g_suit + (XF && Q.suit_tmap >= 0 ? I[Q.suit_tmap + t] * Q.PL * L : 0);      // this step's table
                         // four predator length groups at a time: the unit's biomass is read once per four, their loads in flight together
                         for (int pl0 = 0; pl0 < Q.PL; pl0 += 4) {
                             T cs[4];
@@ -706,7 +718,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                                 if (XF && Q.pref_slot >= 0) bm = xpow(bm, SLOT(Q.pref_slot));
 #pragma unroll
                                 for (int u = 0; u < 4; u++)
-                                    cs[u] = cs[u] + G(Q.g_suit + min(pl0 + u, Q.PL - 1) * L + U.lo + r) * bm;
+                                    cs[u] = cs[u] + G(gsu + min(pl0 + u, Q.PL - 1) * L + U.lo + r) * bm;
                             }
                             const T en = spred ? SLOT(Q.energy_slot) : T(1.0);
 #pragma unroll
@@ -722,7 +734,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     if (!mine()) continue;
                     const TsRec& Ts = Tts[k];
                     const double E = R[Ts.eoff + (size_t)t * Ts.estr];
-                    if (Ts.kind == G3PRED_LINEARFLEET || Ts.kind == G3PRED_EFFORTFLEET) {
+                    if (F_PRED && (Ts.kind == G3PRED_LINEARFLEET || Ts.kind == G3PRED_EFFORTFLEET)) {
                         GS(A.g_eot + k, T(E * dt));         // harvest rate x step length (R/action_predate.R:13-18,117-126)
                     } else {
                         T tot(0.0);
@@ -732,7 +744,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 }
                 // stock predators: predN * max_consumption * feeding_level / total_predsuit per (area, predator length)
                 // (R/action_predate.R:207-238; energycontent cancels between suit and cons)
-                for (int pi = 0; pi < A.NPRED; pi++) {
+                for (int pi = 0; F_PRED && pi < A.NPRED; pi++) {
                     const PredRec& P = Tpred[pi];
                     if (P.kind != G3PRED_STOCK) continue;
                     const StockRec& Pp = Tst[P.stock];
@@ -840,11 +852,12 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     // consumption per unit of biomass by pair k at rows r0 .. r0 + NB - 1 of the unit (the plan's records are in
                     // shared memory; the suitability rows and the fleets' landings / total suitable biomass are table loads)
                     auto cfac = [&](const PairRec& Q, const int ts, const int r0, T (&cf)[NB]) {
-                        if (Q.pred_kind != G3PRED_STOCK) {
+                        const int gsu = Q.g_suit + (XF && Q.suit_tmap >= 0 ? I[Q.suit_tmap + t] * Q.PL * L : 0);      // this step's table
+                        if (!F_PRED || Q.pred_kind != G3PRED_STOCK) {
                             T e = G(A.g_eot + ts);
-                            if (Q.pred_kind == G3PRED_EFFORTFLEET) e = e * SLOT(Q.energy_slot);      // catchability_fs of this prey
+                            if (F_PRED && Q.pred_kind == G3PRED_EFFORTFLEET) e = e * SLOT(Q.energy_slot);      // catchability_fs of this prey
 #pragma unroll
-                            for (int b = 0; b < NB; b++) cf[b] = G(Q.g_suit + U.lo + min(r0 + b, U.len - 1)) * e;
+                            for (int b = 0; b < NB; b++) cf[b] = G(gsu + U.lo + min(r0 + b, U.len - 1)) * e;
                         } else {        // sum over the predator's length groups of suitability x consumption factor
                             const int gp = Tpred[Q.pred].g_pts + ts * Q.PL;
 #pragma unroll
@@ -852,7 +865,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             for (int pl = 0; pl < Q.PL; pl++) {
                                 const T f = G(gp + pl);
 #pragma unroll
-                                for (int b = 0; b < NB; b++) cf[b] = cf[b] + G(Q.g_suit + pl * L + U.lo + min(r0 + b, U.len - 1)) * f;
+                                for (int b = 0; b < NB; b++) cf[b] = cf[b] + G(gsu + pl * L + U.lo + min(r0 + b, U.len - 1)) * f;
                             }
                         }
                     };
@@ -969,7 +982,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 const int grow_n = St.grow_n;
                 const bool trans_now = grow_n >= 0 && St.has_out && ((St.trans_mask >> step) & 1);
                 const bool cont_now = trans_now && St.mat_kind == G3MAT_CONTINUOUS;
-                const bool const_now = trans_now && St.mat_kind == G3MAT_CONSTANT;
+                const bool const_now = F_CMAT && trans_now && St.mat_kind == G3MAT_CONSTANT;
                 const bool has_mort = St.mort_ioff >= 0;
                 const bool inc_here = Cl.inc_tn >= 0 && ((Cl.inc_mask >> step) & 1);
                 const int ren_mask = renewals_now(St);
@@ -978,7 +991,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 bool spawn_here = false;    // this stock spawns at this step
                 if (XF && spawn_step && St.sp_ioff >= 0) { const int rs = I[St.sp_ioff + G3SP_RUN_STEP]; spawn_here = rs == 0 || rs == step + 1; }
                 if (!has_mort && grow_n < 0 && !inc_here && !ren_mask && xact == 0 && !spawn_here) continue;
-                const T mortf = has_mort ? G(St.g_mort + idt * St.ncol + Cl.col) : T(1.0);
+                const int mset = XF && St.mort_tmap >= 0 ? I[St.mort_tmap + t] : 0;       // time-varying M: this step's table
+                const T mortf = has_mort ? G(St.g_mort + (mset * A.ndt + idt) * St.ncol + Cl.col) : T(1.0);
                 const int nblk = (U.len + NB - 1) / NB;
                 T sp_acc(0.0);
                 if (grow_n < 0) {
@@ -1232,7 +1246,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     if (!((cmp_now >> c) & 1)) continue;
                     const int nb = Cm.n_bins;
                     T part(0.0);
-                    if (func == G3F_SUMOFSQUARES || func == G3F_MULTINOMIAL) {
+                    if (func == G3F_SUMOFSQUARES || (F_LIKE && func == G3F_MULTINOMIAL)) {
                         // R/likelihood_distribution.R:3-39 (sum of squared differences of proportions) and :41-60
                         const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
                         const double eps = R[Cm.param_roff];
@@ -1246,14 +1260,14 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                                 for (int w = 0; w < W; w++) tot = tot + G(Cm.g_pt + g * SHW + w);
                                 rt = 1.0 / avoid_zero(tot);
                             }
-                            if (func == G3F_SUMOFSQUARES) {
+                            if (!F_LIKE || func == G3F_SUMOFSQUARES) {
                                 const T dlt = G(ms + e) * rt - op[e];
                                 part = part + dlt * dlt;
                             } else
                                 part = part + op[e] * xlog(dif_pmax_c(G(ms + e) * rt, 1.0 / (nb * eps), 1e4));
                             GS(ms + e, T(0.0));      // zero counters for the next period
                         }
-                    } else if (func == G3F_SUMSQLOGRATIOS) {    // R/likelihood_distribution.R:127-136 (obsprop holds log(obs + eps))
+                    } else if (F_LIKE && func == G3F_SUMSQLOGRATIOS) {    // R/likelihood_distribution.R:127-136 (obsprop holds log(obs + eps))
                         const double eps = R[Cm.param_roff];
                         const double* op = A.obsprop + Cm.obs_off + (size_t)ti * nd;
                         for (int e = e0; e < nd; e += W) {
@@ -1269,7 +1283,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             T sN(0.0); double sI = 0.0;
                             for (int i = 0; i < nt; i++) {
                                 const T mv = G(series + i * nd + e);
-                                sN = sN + (func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv);
+                                sN = sN + (!F_LIKE || func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv);
                                 sI += op[(size_t)i * nd + e];
                             }
                             const T mN = sN / (double)nt;
@@ -1279,7 +1293,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                                 T sxy(0.0), sxx(0.0);
                                 for (int i = 0; i < nt; i++) {
                                     const T mv = G(series + i * nd + e);
-                                    const T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
+                                    const T N = !F_LIKE || func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
                                     sxy = sxy + (op[(size_t)i * nd + e] - mI) * (N - mN); sxx = sxx + (N - mN) * (N - mN);
                                 }
                                 beta = sxy / avoid_zero(sxx);
@@ -1287,7 +1301,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             if (isnan(fa)) alpha = mI - beta * mN;
                             for (int i = 0; i < nt; i++) {
                                 const T mv = G(series + i * nd + e);
-                                const T N = func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
+                                const T N = !F_LIKE || func == G3F_SI_LOG ? xlog(avoid_zero(mv)) : mv;
                                 const T r = alpha + beta * N - op[(size_t)i * nd + e];
                                 part = part + r * r;
                             }

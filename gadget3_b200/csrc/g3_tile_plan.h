@@ -356,7 +356,11 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         }
         if (r.n_renew > 30) return fail("more than 30 renewal actions on one stock");
         maxnarea = std::max(maxnarea, r.narea);
-        r.g_mort = takeg(r.mort_ioff >= 0 ? r.ncol * A.ndt : 0);
+        // time-varying M: one table per (slot set, step length)
+        r.mort_tmap = St[G3S_MORT_TMAP_OFF]; r.mort_nset = 1;
+        if (r.mort_ioff >= 0 && r.mort_tmap >= 0) for (int t = 0; t < A.NT; t++) r.mort_nset = std::max(r.mort_nset, I[r.mort_tmap + t] + 1);
+        r.g_mort = takeg(r.mort_ioff >= 0 ? r.mort_nset * r.ncol * A.ndt : 0);
+        if (r.mort_ioff >= 0 && r.mort_tmap >= 0) A.xf = 1;
         r.g_rd = takeg(r.n_renew * r.L); r.g_rw = takeg(r.n_renew * r.L);
         r.g_wq = r.grow_n >= 0 ? take_padded(r.L) : 0;
         const bool trans = r.grow_n >= 0 && r.has_out;
@@ -576,7 +580,9 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         if (sk == G3SUIT_ANDERSEN || sk == G3SUIT_EXPONENTIAL || sk == G3SUIT_RICHARDS) {
             if (Pr.kind != G3PRED_STOCK) return fail("suitability kind " + std::to_string(sk) + " reads predator_length: it needs a stock predator");
         } else if (sk < 0 || sk > G3SUIT_RICHARDS) return fail("suitability kind " + std::to_string(sk) + " is not supported");
-        r.g_suit = takeg(r.PL * Ps.L);
+        r.suit_tmap = Q[G3PP_SUIT_TMAP]; r.suit_nset = 1;
+        if (r.suit_tmap >= 0) { A.xf = 1; for (int t = 0; t < A.NT; t++) r.suit_nset = std::max(r.suit_nset, I[r.suit_tmap + t] + 1); }
+        r.g_suit = takeg(r.suit_nset * r.PL * Ps.L);
         r.g_part = 0;
         r.cxmask = 0;
         r.tsid_off = (int)P.tb.size();

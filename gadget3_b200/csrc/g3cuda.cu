@@ -203,7 +203,9 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
         const int32_t* Q = I + I[G3H_PP_OFF] + q * G3PP_LEN;
         const int32_t* P = I + I[G3H_PRED_OFF] + Q[G3PP_PRED] * G3P_LEN;
         int PL = P[G3P_KIND] == G3PRED_STOCK ? I[I[G3H_STOCK_OFF] + P[G3P_STOCK] * G3S_LEN + G3S_L] : 1;
-        A.t_suitq[q] = take(PL * I[I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN + G3S_L]);
+        A.w_suit_nset[q] = 1;
+        if (Q[G3PP_SUIT_TMAP] >= 0) for (int t = 0; t < I[G3H_NT]; t++) A.w_suit_nset[q] = std::max(A.w_suit_nset[q], I[Q[G3PP_SUIT_TMAP] + t] + 1);
+        A.t_suitq[q] = take(A.w_suit_nset[q] * PL * I[I[G3H_STOCK_OFF] + Q[G3PP_PREY] * G3S_LEN + G3S_L]);
     }
     for (int p = 0; p < I[G3H_NPRED] && p < MAXS; p++) {
         const int32_t* P = I + I[G3H_PRED_OFF] + p * G3P_LEN;
@@ -220,7 +222,10 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
     for (int s = 0; s < A.NS; s++) {
         const int32_t* St = I + I[G3H_STOCK_OFF] + s * G3S_LEN;
         int n = St[G3S_GROW_N], L = St[G3S_L];
-        A.t_mort[s] = take(St[G3S_MORT_OFF] >= 0 ? St[G3S_NAGE] * St[G3S_NAREA] * A.w_ndt : 0);
+        A.w_mort_nset[s] = 1;
+        if (St[G3S_MORT_OFF] >= 0 && St[G3S_MORT_TMAP_OFF] >= 0)
+            for (int t = 0; t < I[G3H_NT]; t++) A.w_mort_nset[s] = std::max(A.w_mort_nset[s], I[St[G3S_MORT_TMAP_OFF] + t] + 1);
+        A.t_mort[s] = take(St[G3S_MORT_OFF] >= 0 ? A.w_mort_nset[s] * St[G3S_NAGE] * St[G3S_NAREA] * A.w_ndt : 0);
         A.t_rd[s] = take(St[G3S_N_RENEW] * L);
         A.t_rw[s] = take(St[G3S_N_RENEW] * L);
         A.t_pw[s] = take(n >= 0 ? L : 0);

@@ -74,6 +74,13 @@ class Lookup(Expr):
         self.values, self.key, self.base = list(values), wrap(key), base
 
 
+class TimeVar(Expr):
+    """g3_timevariable (R/timevariable.R:1-31): the value of `init` until the first (year, step) listed, then each entry's
+    formula from its (year, step) on."""
+    def __init__(self, name, init, entries):
+        self.name, self.init, self.entries = name, init, entries       # entries: [(year, step, Expr)] in time order
+
+
 class ParamExpr(Expr):
     """Result of :func:`g3_parameterized` before scale/offset wrapping: one ``g3_param`` or
     ``g3_param_table`` call (R/params.R:170-186)."""
@@ -99,6 +106,22 @@ area = Var("area")
 cur_year = Var("cur_year")
 cur_step = Var("cur_step")
 cur_step_size = Var("cur_step_size")
+
+
+def g3_timevariable(lookup_name, fs) -> Expr:
+    """Mirror of ``g3_timevariable()`` (R/timevariable.R:1-31). ``fs``: an ordered mapping; the first key must be 'init', the
+    others 'YYYY' (step 1) or 'YYYY-SS'."""
+    import re as _re
+    items = list(fs.items())
+    if not items or items[0][0] != "init":
+        raise ValueError("First formula should be named 'init'")
+    entries = []
+    for k, f in items[1:]:
+        m = _re.match(r"^([0-9]{4})-?([0-9]{1,2})?$", str(k))
+        if not m:
+            raise ValueError(f"Invalid formula identifier(s): {k}")
+        entries.append((int(m.group(1)), int(m.group(2)) if m.group(2) else 1, wrap(f)))
+    return TimeVar("tv_" + lookup_name, wrap(items[0][1]), entries)
 
 
 def g3_parameterized(name, by_stock=False, by_predator=False, by_year=False, by_step=False,
@@ -374,6 +397,16 @@ class Lowerer:
             if not (0 <= i < len(e.values)):
                 raise G3Unsupported(f"data lookup index {i} out of range")
             return ("c", float(e.values[i]))
+        if isinstance(e, TimeVar):
+            # every formula is lowered (its parameters are declared whatever the step), the step picks one: the global formula
+            # is re-evaluated every step and keeps its last value (R/timevariable.R:20-29)
+            now = (int(self._var("cur_year", ctx)), int(self._var("cur_step", ctx)))
+            out = self._lower(e.init, ctx)
+            for y, st, f in e.entries:
+                v = self._lower(f, ctx)
+                if (y, st) <= now:
+                    out = v
+            return out
         if isinstance(e, ParamExpr):
             base = self._base_name(e, ctx)
             is_table = (e.by_year is not False) or e.by_step or e.by_age or e.by_area

@@ -202,7 +202,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         r[K["G3S_CELL_OFF"]] = cell_off
         r[K["G3S_MIDLEN_ROFF"]] = b.alloc_reals(s.midlen)
         r[K["G3S_PLUSDL_ROFF"]] = b.alloc_reals([s.plusdl])
-        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF", "G3S_OTHERFOOD_OFF", "G3S_SPAWN_OFF"):
+        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF", "G3S_OTHERFOOD_OFF", "G3S_SPAWN_OFF", "G3S_MORT_TMAP_OFF"):
             r[K[f]] = -1
         dims = [d for d in s.dims if d != "length"]
         r[K["G3S_DIMORDER"]] = 0 if dims == ["age", "area"] else 1
@@ -281,6 +281,20 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
     for name, (tab, _) in mig_tabs.items():
         srec[name][K["G3S_MIGRATE_OFF"]] = b.alloc_ints(tab)
 
+    def time_sets(slots_at):
+        """Time-varying formulas (by_year / by_step tables, g3_timevariable -- R/params.R:122-129, R/timevariable.R:1-31): the
+        slots of every step, deduplicated into sets. Returns (flat list of the sets' slots, per-step set index or None when one
+        set serves every step)."""
+        sets, index, tmap = [], {}, []
+        for t in range(NT):
+            key = tuple(slots_at(dict(cur_year=tm.start_year + t // S, cur_step=t % S + 1,
+                                      cur_step_size=tm.step_lengths[t % S] / 12.0)))
+            if key not in index:
+                index[key] = len(sets)
+                sets.append(key)
+            tmap.append(index[key])
+        return [x for k in sets for x in k], (tmap if len(sets) > 1 else None)
+
     # ---- predation (order 3): predators by name, prey by name
     pred_recs, pp_recs, pp_index, pp_info = [], [], {}, []
     for pname, a in preds.items():
@@ -324,8 +338,9 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             q = [0] * K["G3PP_LEN"]
             q[K["G3PP_PRED"]], q[K["G3PP_PREY"]] = len(pred_recs), sidx[prey.name]
             q[K["G3PP_SUIT_KIND"]] = K["G3SUIT_" + {"expl50": "EXPL50"}.get(su.kind, su.kind.upper())]
-            slots = [low.slot(x, c) for x in su.args]
-            q[K["G3PP_SUIT_OFF"]] = b.alloc_ints(slots + [-1] * (6 - len(slots)))
+            slots, stmap = time_sets(lambda tc: (lambda sl: sl + [-1] * (6 - len(sl)))([low.slot(x, c.replace(**tc)) for x in su.args]))
+            q[K["G3PP_SUIT_OFF"]] = b.alloc_ints(slots)
+            q[K["G3PP_SUIT_TMAP"]] = -1 if stmap is None else b.alloc_ints(stmap)
             q[K["G3PP_ENERGY"]] = q[K["G3PP_PREF"]] = -1
             if cat.kind == "predator":
                 q[K["G3PP_ENERGY"]] = low.slot(cat.kw["energycontent"], c)
@@ -352,9 +367,11 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
     # ---- natural mortality (order 4)
     for name, a in one_per_stock("naturalmortality", "g3a_naturalmortality").items():
         s = stocks[name]
-        tab = [low.slot(a.param_f, Ctx(stock=s, age=ag, area=aid, area_name=an))
-               for ri, an, aid, ai, ag in columns(s)]
+        tab, tmap = time_sets(lambda tc: [low.slot(a.param_f, Ctx(stock=s, age=ag, area=aid, area_name=an, **tc))
+                                          for ri, an, aid, ai, ag in columns(s)])
         srec[name][K["G3S_MORT_OFF"]] = b.alloc_ints(tab)
+        if tmap is not None:
+            srec[name][K["G3S_MORT_TMAP_OFF"]] = b.alloc_ints(tmap)
 
     # ---- growth + maturity (order 5 / 7)
     maxn = 0

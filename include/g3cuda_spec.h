@@ -26,7 +26,7 @@
 #ifndef G3CUDA_SPEC_H
 #define G3CUDA_SPEC_H
 
-#define G3CUDA_SPEC_VERSION 5
+#define G3CUDA_SPEC_VERSION 6
 
 /* ---- header: ints[0..G3H_LEN) ------------------------------------------ */
 #define G3H_VERSION        0
@@ -96,7 +96,10 @@
 #define G3S_OTHERFOOD_OFF 26   /* g3a_otherfood (R/action_renewal.R:276-308): ints[NT*NAREA*2]: (num slot, wgt slot) per (step t, area idx),
                                   assigned to every cell of the stock at the start of step t; -1 = not an otherfood stock */
 #define G3S_SPAWN_OFF     27   /* g3a_spawn (R/action_spawn.R:86-233): ints[G3SP_LEN] record of the PARENT stock, or -1 */
-#define G3S_LEN           28
+#define G3S_MORT_TMAP_OFF 28   /* time-varying natural mortality (by_year / by_step tables, g3_timevariable; R/params.R:122-129,
+                                  R/timevariable.R:1-31): ints[NT]: which set of MORT_OFF's ints[NSET*NAGE*NAREA] slots step t uses;
+                                  -1 = one set for every step */
+#define G3S_LEN           29
 
 /* ---- spawning record (g3a_spawn, R/action_spawn.R:86-233) ----------------
    At order 6 (after growth, before the maturing fish arrive and before renewal): spawningnum = num * proportion(l);
@@ -161,7 +164,9 @@
 #define G3PP_SUIT_OFF      3   /* ints[6]: slots */
 #define G3PP_ENERGY        4   /* stock predators: slot energycontent; effort fleets: slot catchability_fs of this prey; else -1 */
 #define G3PP_PREF          5   /* stock predators: slot prey_preference, else -1 */
-#define G3PP_LEN           6
+#define G3PP_SUIT_TMAP     6   /* time-varying suitability parameters (selectivity blocks: by_year / by_step tables, g3_timevariable):
+                                  ints[NT]: which set of SUIT_OFF's ints[NSET*6] slots step t uses; -1 = one set for every step */
+#define G3PP_LEN           7
 
 #define G3SUIT_EXPL50      0   /* alpha, l50 (R/suitability.R:5) */
 #define G3SUIT_ANDERSEN    1   /* p0..p4, p5 = predator length (R/suitability.R:15) */

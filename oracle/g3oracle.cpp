@@ -433,7 +433,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             const int32_t* Q = S.pp(q); const int32_t* P = S.pred(Q[G3PP_PRED]); const int32_t* St = S.stock(Q[G3PP_PREY]);
             is_prey[Q[G3PP_PREY]] = 1;
             int L = St[G3S_L]; const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
-            const int32_t* ss = S.I + Q[G3PP_SUIT_OFF];
+            const int32_t* ss = S.I + Q[G3PP_SUIT_OFF] + 6 * (Q[G3PP_SUIT_TMAP] >= 0 ? S.I[Q[G3PP_SUIT_TMAP] + cur_time] : 0);       // (time-varying selectivity: this step's set)
             bool ok = true;
             if (P[G3P_KIND] == G3PRED_STOCK) {
                 const int32_t* Sp = S.stock(P[G3P_STOCK]);
@@ -487,7 +487,8 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                 const int32_t* Sp = S.stock(P[G3P_STOCK]);
                 int PL = Sp[G3S_L], PA = Sp[G3S_NAGE]; const double* pmid = S.R + Sp[G3S_MIDLEN_ROFF];
                 const double* midlen = S.R + St[G3S_MIDLEN_ROFF];
-                const int32_t* ss = S.I + Q[G3PP_SUIT_OFF]; const int32_t* ps = S.I + P[G3P_SLOT_OFF];
+                const int32_t* ss = S.I + Q[G3PP_SUIT_OFF] + 6 * (Q[G3PP_SUIT_TMAP] >= 0 ? S.I[Q[G3PP_SUIT_TMAP] + cur_time] : 0);
+                const int32_t* ps = S.I + P[G3P_SLOT_OFF];
                 T energy = slot(Q[G3PP_ENERGY]);
                 T m0 = slot(ps[0]), m1 = slot(ps[1]), m2 = slot(ps[2]), m3 = slot(ps[3]), hf = slot(ps[4]), temp = slot(ps[5]);
                 bool ok = true;
@@ -561,9 +562,11 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
         for (int s = 0; s < NS; s++) {
             const int32_t* St = S.stock(s);
             if (St[G3S_MORT_OFF] < 0) continue;
-            int L = St[G3S_L];
-            for (int col = 0; col < St[G3S_NAREA] * St[G3S_NAGE]; col++) {
-                T f = xexp(-slot(S.I[St[G3S_MORT_OFF] + col]) * cur_step_size);
+            int L = St[G3S_L], ncol = St[G3S_NAREA] * St[G3S_NAGE];
+            // time-varying M (by_year / by_step tables, g3_timevariable): the slot set of this step
+            int mset = St[G3S_MORT_TMAP_OFF] >= 0 ? S.I[St[G3S_MORT_TMAP_OFF] + cur_time] : 0;
+            for (int col = 0; col < ncol; col++) {
+                T f = xexp(-slot(S.I[St[G3S_MORT_OFF] + mset * ncol + col]) * cur_step_size);
                 for (int l = 0; l < L; l++) { int c = St[G3S_CELL_OFF] + col * L + l; num[c] = num[c] * f; }
             }
         }
@@ -980,7 +983,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             int L = St[G3S_L], PL = sp ? Sp[G3S_L] : 1;
             bool ok = true;
             for (int pl = 0; pl < PL; pl++) for (int l = 0; l < L; l++)
-                rep->suit_report[q][pl * L + l] = val(suitability<T>(Q[G3PP_SUIT_KIND], S.I + Q[G3PP_SUIT_OFF], slot,
+                rep->suit_report[q][pl * L + l] = val(suitability<T>(Q[G3PP_SUIT_KIND], S.I + Q[G3PP_SUIT_OFF] + 6 * (Q[G3PP_SUIT_TMAP] >= 0 ? S.I[Q[G3PP_SUIT_TMAP] + std::min(total_steps, S.h(G3H_NT) - 1)] : 0), slot,      // (the last step's set)
                     (S.R + St[G3S_MIDLEN_ROFF])[l],
                     sp && Q[G3PP_SUIT_KIND] != G3SUIT_ANDERSENFLEET ? (S.R + Sp[G3S_MIDLEN_ROFF])[pl] : (S.R + St[G3S_MIDLEN_ROFF])[L - 1], ok));
         }

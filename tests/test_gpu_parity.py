@@ -313,7 +313,7 @@ def test_against_reference_generated_code(setups, name, kernel):
 
 
 @KERNELS
-@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN"])
+@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG"])
 def test_andersen_predator_model(oracle_lib, name, kernel):
     """g3_suitability_andersen (predator-length dependent), one-step-only migration: CUDA vs oracle.
     MINI_SUITS: richards for the predator, gamma / andersenfleet / straightline fleets, reports included.

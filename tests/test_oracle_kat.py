@@ -275,3 +275,60 @@ def test_migrate_twelve_step_recurrence(oracle_lib):
         np.testing.assert_allclose(num[..., t + 1], en, rtol=1e-12, err_msg=f"numbers, t = {t}")
         np.testing.assert_allclose(wgt[..., t + 1], ew, rtol=1e-12, err_msg=f"weights, t = {t}")
     assert np.abs(num[..., 19] - num[..., 0]).max() > 1.0       # (the fish did move)
+
+
+def test_time_varying_natural_mortality(oracle_lib):
+    """SURVEY section 8f rank 4, first slice: M from a by_year x by_step x by_age g3_param_table (R/params.R:122-129) and from a
+    g3_timevariable (R/timevariable.R:1-31: 'init' until 2001 step 2, the second formula until 2002 step 1, then the third).
+    The stocks of TIMEVAR_RIG only die, so num(t + 1) / num(t) = exp(-M(t) * cur_step_size) (R/action_naturalmortality.R:1-9)
+    with the M in force at step t, for every length group."""
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["TIMEVAR_RIG"]()
+    v = p.values()
+    g = lambda n: float(v[p.index(n)])
+    rep = unpack_report(model, Oracle(*model.pack(p)).report(v))
+    dt = [3 / 12, 3 / 12, 6 / 12]
+    ny = np.asarray(rep["dstart_st_year__num"])          # [length][age][area][t], 9 steps
+    nv = np.asarray(rep["dstart_st_tv__num"])
+    assert ny.shape == (4, 2, 1, 9) and ny.min() > 0
+    for t in range(8):
+        y, st = 2000 + t // 3, t % 3 + 1
+        for a in (1, 2):
+            want = np.exp(-g(f"st_year.Mt.{y}.{st}.{a}") * dt[st - 1])
+            np.testing.assert_allclose(ny[:, a - 1, 0, t + 1] / ny[:, a - 1, 0, t], want, rtol=1e-13, err_msg=f"by_year/by_step, t = {t}")
+        m = g("tvM.init") if (y, st) < (2001, 2) else g("tvM.a") if (y, st) < (2002, 1) else g("tvM.b") * 1.5
+        np.testing.assert_allclose(nv[:, 0, 0, t + 1] / nv[:, 0, 0, t], np.exp(-m * dt[st - 1]), rtol=1e-13, err_msg=f"g3_timevariable, t = {t}")
+    # all three formulas of the time variable are parameters of the model, whatever step they come into force at
+    assert {"tvM.init", "tvM.a", "tvM.b"} <= set(p.switch)
+    # g3_timevariable's own checks (R/timevariable.R:8,16)
+    from gadget3_b200 import g3_timevariable
+    with pytest.raises(ValueError, match="init"):
+        g3_timevariable("x", {"2000": 1})
+    with pytest.raises(ValueError, match="Invalid formula identifier"):
+        g3_timevariable("x", {"init": 1, "20x0": 2})
+
+
+def test_time_varying_selectivity(oracle_lib):
+    """a by_year table inside a suitability function (R/params.R:122-129). MINI_TIMEVAR's fleet has
+    l50 by year; the suitable biomass the oracle reports for a step, over the biomass at the start of that step, must be
+    g3_suitability_exponentiall50 (R/suitability.R:5-13) with THAT year's l50 -- and the final suit report the last year's."""
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["MINI_TIMEVAR"]()
+    v = p.values()
+    g = lambda n: float(v[p.index(n)])
+    rep = unpack_report(model, Oracle(*model.pack(p)).report(v))
+    midlen = np.arange(12.5, 60, 5.0)
+    alpha = g("fish.f_comm.alpha")
+    suit = np.asarray(rep["detail_fish_mat_f_comm__suit"])        # [length][age][area][t]
+    bio = np.asarray(rep["dstart_fish_mat__num"]) * np.asarray(rep["dstart_fish_mat__wgt"])
+    for t in range(20):
+        want = 1 / (1 + np.exp(-alpha * (midlen - g(f"fish.f_comm.l50.{2000 + t // 4}"))))
+        got = suit[:, 1, 0, t] / bio[:, 1, 0, t]
+        np.testing.assert_allclose(got, want, rtol=1e-12, err_msg=f"t = {t}")
+    last = 1 / (1 + np.exp(-alpha * (midlen - g("fish.f_comm.l50.2004"))))
+    np.testing.assert_allclose(np.asarray(rep["suit_fish_mat_f_comm__report"]).ravel(), last, rtol=1e-13)
+    assert len({g(f"fish.f_comm.l50.{y}") for y in range(2000, 2005)}) == 5
