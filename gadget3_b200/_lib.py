@@ -158,7 +158,7 @@ class Handle:
         self._check(rc, "g3cuda_eval_batch_device")
 
     def set_kernel(self, which: int):
-        """0 = automatic, 3 = thread-per-evaluation kernel, 4 = tile kernel (tests / profiling)."""
+        """0 = automatic, 3 = thread-per-evaluation kernel, 4 = tile kernel, 5 = tile kernel in its full instantiation (tests / profiling)."""
         self._check(self.lib.g3cuda_set_kernel(self.h, int(which)), "g3cuda_set_kernel")
 
     def set_tile_warps(self, warps: int):

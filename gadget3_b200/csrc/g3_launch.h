@@ -16,6 +16,11 @@ const void* tile_x_d5(bool smem);
 const void* tile_x_d16(bool smem);
 const void* tile_x_g5(bool smem);
 const void* tile_x_g16(bool smem);
+// ... plain values with the features a model does not use compiled out (LEAN masks of g3_tile.cuh), 16 warps per tile
+const void* tile_l15_d5(bool smem);
+const void* tile_l12_d5(bool smem);
+const void* tile_l15_d16(bool smem);
+const void* tile_l11_d16(bool smem);
 // thread kernel (g3_thread_kernel.cuh): (big = 1024-thread variant, plain doubles only), constmat
 const void* thread_d5(bool big, bool constmat);
 const void* thread_d16(bool constmat);

@@ -129,6 +129,7 @@ struct TArgs {
     int inc_any_mask;       // bit (cur_step-1): some column receives maturing fish on that step
     int sp_off, sp_n;       // tb: the spawning stocks
     int xf;                 // the model needs the XF instantiation (g3a_otherfood, g3a_spawn, prey_preferences)
+    int need;               // features the model uses, in the bits of LEAN (an instantiation with LEAN & need == 0 can run it)
     int spawn_mask;         // bit (cur_step-1): some stock spawns on that step
     int any_ghost;          // some column is split into several units
     int NWc;                // band width the tables are laid out for (the kernel's NW)
@@ -250,17 +251,16 @@ __device__ __forceinline__ void grow_gather(const double* __restrict__ pN, const
 
 // T: double or Dual<N>; NW: compiled width of the growth band (maxlengthgroupgrowth + 1 <= NW);
 // SMEM: stock state in shared memory (smem = its base) or in the global slab
-// Experiment switch (variant builds only, tools/build_variant.sh): G3T_LEAN bit 0 = no migration, bit 1 = totalfleet predation
-// only, bit 2 = no constant maturity, bit 3 = sumofsquares / log survey indices only -- the code is compiled out.
-#ifndef G3T_LEAN
-#define G3T_LEAN 0
-#endif
-constexpr bool F_MIG = !(G3T_LEAN & 1), F_PRED = !(G3T_LEAN & 2), F_CMAT = !(G3T_LEAN & 4), F_LIKE = !(G3T_LEAN & 8);
 // XF: the model uses g3a_otherfood, g3a_spawn or prey_preferences (TArgs::xf, set by the planner). The kernels of the models
 // that do not are compiled without that code: beside the hot loops it cost 5-9 % (registers, instruction footprint).
-template <class T, int NW, bool SMEM, int NBV = 0, bool XF = true>
+// LEAN: features the model does NOT use, compiled out (TArgs::need is what it does use; the dispatch picks the leanest instantiation
+// that covers it): bit 0 migration, bit 1 anything but totalfleet predation (stock predators, number- / linear- / effort-fleets),
+// bit 2 constant maturity, bit 3 likelihood functions other than sumofsquares and log survey indices. Never-taken branches
+// beside the hot loops are not free here (registers, code layout): C2 +6 %, C1 +4 %, C4 / C5 +2 % (variant A/B on a B200).
+template <class T, int NW, bool SMEM, int NBV = 0, bool XF = true, int LEAN = 0>
 __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr, const int warp, const int lane, const int cta,
                                           const int ncta G3T_CTX_DECL) {
+    constexpr bool F_MIG = !(LEAN & 1), F_PRED = !(LEAN & 2), F_CMAT = !(LEAN & 4), F_LIKE = !(LEAN & 8);
     constexpr int NTAN = Tan<T>::n;
     constexpr int NB = NBV > 0 ? NBV : (NTAN > 0 ? 1 : NBX);    // rows per block (interleaved avoid_zero / reciprocal chains)
     constexpr unsigned C = (unsigned)(NTAN + 1) * NL;       // doubles per entry
@@ -1417,11 +1417,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 }
 
 #ifdef __CUDACC__
-template <class T, int NW, bool SMEM, int MAXT, int NBV = 0, bool XF = false>
+template <class T, int NW, bool SMEM, int MAXT, int NBV = 0, bool XF = false, int LEAN = 0>
 __global__ void __launch_bounds__(MAXT, 1) eval_tile_kernel(const __grid_constant__ TArgs A) {
     extern __shared__ __align__(16) double g3t_smem[];
     __shared__ int g3t_ctr[8];
-    tile_body<T, NW, SMEM, NBV, XF>(A, g3t_smem, g3t_ctr, threadIdx.x >> 5, threadIdx.x & 31, blockIdx.x, gridDim.x);
+    tile_body<T, NW, SMEM, NBV, XF, LEAN>(A, g3t_smem, g3t_ctr, threadIdx.x >> 5, threadIdx.x & 31, blockIdx.x, gridDim.x);
 }
 #endif
 

@@ -302,7 +302,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     A.NC = I[G3H_NCELL]; A.NS = I[G3H_NSTOCK]; A.NPP = I[G3H_NPP]; A.NPRED = I[G3H_NPRED]; A.NCOMP = I[G3H_NCOMP];
     A.NX = I[G3H_NXBUF]; A.NSLOT = I[G3H_NSLOT]; A.NPAR = I[G3H_NPAR]; A.NT = I[G3H_NT]; A.NSTEPS = I[G3H_NSTEPS];
     A.NNLL = I[G3H_NNLL]; A.NBOUND = I[G3H_NBOUND]; A.maxL = I[G3H_MAXL];
-    A.spawn_mask = 0; A.sp_n = 0; A.sp_off = 0; A.xf = 0;
+    A.spawn_mask = 0; A.sp_n = 0; A.sp_off = 0; A.xf = 0; A.need = 0;
     if (A.NCOMP > 32) return fail("more than 32 likelihood components");
     if (A.NX > 32) return fail("more than 32 collect vectors");
     if (A.NSTEPS > 31) return fail("more than 31 steps per year");
@@ -374,6 +374,8 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         if (cont) zero_g(r.g_bandr, nset * A.ndt * r.bsz);
         r.g_cmat = (trans && r.mat_kind == G3MAT_CONSTANT) ? take_padded(r.ncol * r.L) : -1;
         r.mig_ioff = St[G3S_MIGRATE_OFF]; r.mig_steps = 0;
+        if (r.mig_ioff >= 0) A.need |= 1;
+        if (r.grow_n >= 0 && r.has_out && r.mat_kind == G3MAT_CONSTANT) A.need |= 4;
         r.of_ioff = St[G3S_OTHERFOOD_OFF];
         // g3a_spawn (R/action_spawn.R:86-233): proportion spawning and spawning mortality by length, the fecundity weights
         r.sp_ioff = St[G3S_SPAWN_OFF]; r.g_sprop = r.g_smort = r.g_sfec = -1; r.sp_out_off = -1;
@@ -574,7 +576,8 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         const StockRec& Ps = P.st[Q[G3PP_PREY]];
         PairRec& r = P.pp[q];
         r.pred = Q[G3PP_PRED]; r.prey = Q[G3PP_PREY]; r.suit_kind = Q[G3PP_SUIT_KIND]; r.suit_ioff = Q[G3PP_SUIT_OFF];
-        r.energy_slot = Q[G3PP_ENERGY]; r.pref_slot = Q[G3PP_PREF]; if (r.pref_slot >= 0) A.xf = 1; r.pred_kind = Pr.kind; r.pred_stock = Pr.kind == G3PRED_STOCK ? Pr.stock : -1;
+        r.energy_slot = Q[G3PP_ENERGY]; r.pref_slot = Q[G3PP_PREF]; if (r.pref_slot >= 0) A.xf = 1;
+        if (Pr.kind != G3PRED_TOTALFLEET) A.need |= 2; r.pred_kind = Pr.kind; r.pred_stock = Pr.kind == G3PRED_STOCK ? Pr.stock : -1;
         r.PL = Pr.kind == G3PRED_STOCK ? P.st[Pr.stock].L : 1;
         const int sk = r.suit_kind;
         if (sk == G3SUIT_ANDERSEN || sk == G3SUIT_EXPONENTIAL || sk == G3SUIT_RICHARDS) {
@@ -628,6 +631,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     for (int c = 0; c < A.NCOMP; c++) {
         const int32_t* Cm = I + I[G3H_COMP_OFF] + c * G3C_LEN;
         CompRec& r = P.comp[c];
+        if (Cm[G3C_FUNC] != G3F_SUMOFSQUARES && Cm[G3C_FUNC] != G3F_SI_LOG) A.need |= 8;
         r.func = Cm[G3C_FUNC]; r.weight_par = Cm[G3C_WEIGHT_PAR]; r.xbuf = Cm[G3C_XBUF]; r.mode = Cm[G3C_MODE];
         r.n_dest = Cm[G3C_N_DEST]; r.n_bins = Cm[G3C_N_BINS]; r.n_slices = Cm[G3C_N_SLICES]; r.n_areag = Cm[G3C_N_AREAG];
         r.csr_ptr_ioff = Cm[G3C_CSR_PTR_OFF]; r.csr_idx_ioff = Cm[G3C_CSR_IDX_OFF]; r.csr_coef_roff = Cm[G3C_CSR_COEF_ROFF];

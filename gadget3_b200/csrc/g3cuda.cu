@@ -68,6 +68,7 @@ struct g3cuda_model {
     cudaEvent_t ws_free = nullptr;      // recorded after every launch that uses a workspace: the next one waits for it,
                                         // whichever stream it is on (the workspaces are per handle, not per stream)
     int force_kernel = 0;               // 0 = automatic, 3 = thread kernel, 4 = tile kernel
+    int no_lean = 0;                    // set_kernel(5): the tile kernel's full instantiation even where a leaner one covers the model
     // ---- tile kernel (g3_tile.cuh): plan, device tables, per-CTA slabs
     g3t::TilePlan tplan;
     g3t::TArgs targs{};
@@ -139,7 +140,13 @@ int tile_geom(g3cuda_model* m, TileGeom* g) {
     if (threads > 512 && (dual || wide)) return fail(G3CUDA_EUNSUPP, "more than 16 warps per tile exist for plain values and narrow growth bands only");
     const bool xf = m->targs.xf != 0;
     if (xf && threads > 512) return fail(G3CUDA_EUNSUPP, "more than 16 warps per tile: not for models with g3a_otherfood, g3a_spawn or prey_preferences");
+    const int need = m->targs.need;     // features the model uses: the leanest instantiation that covers them (plain values, 16 warps)
+    const bool lean_ok = !dual && !xf && threads <= 512 && !m->no_lean;
     if (xf) g->fn = dual ? (wide ? g3i::tile_x_g16(g->in_smem) : g3i::tile_x_g5(g->in_smem)) : (wide ? g3i::tile_x_d16(g->in_smem) : g3i::tile_x_d5(g->in_smem));
+    else if (lean_ok && !wide && (need & 15) == 0) g->fn = g3i::tile_l15_d5(g->in_smem);
+    else if (lean_ok && !wide && (need & 12) == 0) g->fn = g3i::tile_l12_d5(g->in_smem);
+    else if (lean_ok && wide && (need & 15) == 0) g->fn = g3i::tile_l15_d16(g->in_smem);
+    else if (lean_ok && wide && (need & 11) == 0) g->fn = g3i::tile_l11_d16(g->in_smem);
     else
     g->fn = dual ? (wide ? g3i::tile_g16(g->in_smem) : g3i::tile_g5(g->in_smem))
                  : (wide ? g3i::tile_d16(g->in_smem) : threads > 768 ? g3i::tile_d5_w32(g->in_smem) : threads > 512 ? g3i::tile_d5_w24(g->in_smem) : g3i::tile_d5(g->in_smem));
@@ -895,7 +902,9 @@ int g3cuda_multi_eval_batch(g3cuda_multi* mm, const double* par, int64_t B, cons
 }
 
 int g3cuda_set_kernel(g3cuda_model* m, int which) {
-    if (!m || (which != 0 && which != 3 && which != 4)) return fail(G3CUDA_EINVAL, "bad argument: kernel must be 0 (automatic), 3 (thread) or 4 (tile)");
+    if (!m || (which != 0 && which != 3 && which != 4 && which != 5)) return fail(G3CUDA_EINVAL, "bad argument: kernel must be 0 (automatic), 3 (thread), 4 (tile) or 5 (tile, full instantiation)");
+    m->no_lean = which == 5;
+    if (which == 5) which = 4;
     if (which == 3 && !m->thread_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the thread-per-evaluation kernel: %s", m->thread_why.c_str());
     if (which == 4 && !m->tile_ok) return fail(G3CUDA_EUNSUPP, "model does not fit the tile kernel: %s", m->tplan.why.c_str());
     m->force_kernel = which;

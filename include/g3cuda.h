@@ -103,7 +103,10 @@ int g3cuda_multi_eval_batch(g3cuda_multi* mm, const double* par, int64_t B,
                             double* nll, double* nll_comp, double* grad);
 
 /* Kernel selection, for tests and profiling: 0 = automatic (default), 3 = thread-per-evaluation kernel,
- * 4 = tile kernel (G3CUDA_EUNSUPP if the model does not fit the requested one; other values: G3CUDA_EINVAL).
+ * 4 = tile kernel, 5 = tile kernel in its full instantiation (by default a model runs on the instantiation that has the
+ * features it does not use -- migration, stock predators, constant maturity, the rarer likelihood functions -- compiled out;
+ * the same source for what remains; the two compilations agree to rounding) (G3CUDA_EUNSUPP if the model does not fit the requested one;
+ * other values: G3CUDA_EINVAL).
  * Automatic: value batches of any size run on the tile kernel (one CTA owns 32 evaluations for the whole time
  * loop, stock state in shared memory; few vectors are spread over the SMs, so a single fn(par) is a ~ms call);
  * gradient batches run on the tile kernel when small and on the thread kernel when large; g3cuda_report always

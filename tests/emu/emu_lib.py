@@ -58,7 +58,9 @@ def plan_info(ints, reals, W=0, seg=0):
 
 
 def eval_batch(ints, reals, par, tangent_idx=None, want_comp=False, W=0, seg=0, lanes_per_tile=4, smem_state=True, ncta=2,
-               meta_smem=True, hot_tables=True):
+               meta_smem=True, hot_tables=True, lean=True):
+    """`lean`: as the product's dispatch, the instantiation with the model's unused features compiled out (False: the full one)."""
+    load().g3emu_set_no_lean(0 if lean else 1)
     ints = np.ascontiguousarray(ints, dtype=np.int32); reals = np.ascontiguousarray(reals, dtype=np.float64)
     par = np.ascontiguousarray(np.atleast_2d(par), dtype=np.float64)
     B = par.shape[0]

@@ -6,16 +6,18 @@
 #include <barrier>
 #include <cstring>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../gadget3_b200/csrc/g3_tile_plan.h"
 
 namespace {
 using namespace g3t;
+bool g_no_lean = false;     // g3emu_set_no_lean: the full instantiation even where a leaner one covers the model
 struct Bar { std::barrier<>* b; };
 void bar_wait(void* p) { static_cast<Bar*>(p)->b->arrive_and_wait(); }
 
-template <class T, int NW, bool SMEM, bool XF>
+template <class T, int NW, bool SMEM, bool XF, int LEAN = 0>
 void run_xf(const TArgs& A, int W, int ncta, size_t smem_doubles) {
     for (int cta = 0; cta < ncta; cta++)
         for (int lane = 0; lane < A.lanes_per_tile; lane++) {
@@ -26,16 +28,27 @@ void run_xf(const TArgs& A, int W, int ncta, size_t smem_doubles) {
             EmuCtx ctx{bar_wait, &bar};
             std::vector<std::thread> th;
             for (int w = 0; w <= W; w++)
-                th.emplace_back([&, w]() { tile_body<T, NW, SMEM, 0, XF>(A, smem.data(), ctr, w, lane, cta, ncta, ctx); });
+                th.emplace_back([&, w]() { tile_body<T, NW, SMEM, 0, XF, LEAN>(A, smem.data(), ctr, w, lane, cta, ncta, ctx); });
             for (auto& t : th) t.join();
         }
 }
 // the instantiation the product's dispatch picks (TArgs::xf)
 template <class T, int NW, bool SMEM>
 void run(const TArgs& A, int W, int ncta, size_t smem_doubles) {
-    if (A.xf) run_xf<T, NW, SMEM, true>(A, W, ncta, smem_doubles); else run_xf<T, NW, SMEM, false>(A, W, ncta, smem_doubles);
+    if (A.xf) { run_xf<T, NW, SMEM, true>(A, W, ncta, smem_doubles); return; }
+    // plain values: the leanest instantiation the product compiles that covers the model (g3cuda.cu: tile_geom)
+    if constexpr (std::is_same<T, double>::value) {
+        if (!g_no_lean) {
+            if ((A.need & 15) == 0) { run_xf<T, NW, SMEM, false, 15>(A, W, ncta, smem_doubles); return; }
+            if (NW == 5 && (A.need & 12) == 0) { run_xf<T, NW, SMEM, false, 12>(A, W, ncta, smem_doubles); return; }
+            if (NW == 16 && (A.need & 11) == 0) { run_xf<T, NW, SMEM, false, 11>(A, W, ncta, smem_doubles); return; }
+        }
+    }
+    run_xf<T, NW, SMEM, false>(A, W, ncta, smem_doubles);
 }
 }  // namespace
+
+extern "C" void g3emu_set_no_lean(int32_t v) { g_no_lean = v != 0; }
 
 extern "C" int g3emu_eval(const int32_t* I, const double* R, const double* par, int64_t B, const int32_t* tidx, int32_t K,
                           double* nll, double* comp, double* grad, int32_t W, int32_t seg, int32_t lanes_per_tile, int32_t smem_state,

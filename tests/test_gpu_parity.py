@@ -403,3 +403,25 @@ def test_projection_years_are_refused_not_nan(setups):
     with pytest.raises(G3CudaError, match="project_years"):
         fn.handle.eval_batch(full)
     assert np.isfinite(fn.handle.eval_batch(full[:2])[0]).all()
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C4", "C5"])
+def test_lean_instantiations_are_bit_identical(setups, name):
+    """By default a model runs on the instantiation of the tile kernel that has the features it does not use compiled out
+    (LEAN masks, g3_tile.cuh); g3cuda_set_kernel(m, 5) selects the full instantiation. The same source for what remains (the
+    CPU emulation gives identical bits, tests/test_tile_emu.py); on the device the two compilations contract and order a few
+    operations differently, so they agree to rounding."""
+    model, p, fn, orc = setups[name]
+    full = fn.full_par(parameter_batch(p, 96, seed=44))
+    try:
+        fn.handle.set_kernel(4)
+        a = fn.handle.eval_batch(full, want_comp=True)
+        fn.handle.set_kernel(5)
+        b = fn.handle.eval_batch(full, want_comp=True)
+    finally:
+        fn.handle.set_kernel(0)
+    ncomp = len(model.comp_names)
+    assert _rel(a[1][:, :ncomp], b[1][:, :ncomp]).max() < 1e-12
+    tol = 1e-12 * np.abs(b[0]) + US_WEIGHT * _us_tolerance(model, p, b[1][:, -2])
+    assert (np.abs(a[0] - b[0]) <= tol).all()
+    assert np.median(_rel(a[0], b[0])) < 1e-14

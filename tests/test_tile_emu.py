@@ -121,3 +121,14 @@ def test_hot_tables_in_shared_memory_or_in_the_slab(oracle_lib, name):
     a = emu.eval_batch(ints, reals, full, want_comp=True, hot_tables=True)
     b = emu.eval_batch(ints, reals, full, want_comp=True, hot_tables=False)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C4", "C5"])
+def test_lean_instantiations_are_bit_identical(oracle_lib, name):
+    """A model runs on the instantiation of the kernel that has the features it does not use compiled out (LEAN masks of
+    g3_tile.cuh: C1 / C2 everything, C4 all but constant maturity, C5 constant maturity and the rarer likelihood functions);
+    the arithmetic that remains is the same code: identical results."""
+    model, p, ints, reals, full, _ = _setup(name, 3)
+    a = emu.eval_batch(ints, reals, full, want_comp=True, lean=True)
+    b = emu.eval_batch(ints, reals, full, want_comp=True, lean=False)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
