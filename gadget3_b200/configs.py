@@ -804,16 +804,24 @@ def build_timevar_rig(seed=123):
     sv = g3s_livesonareas(g3s_age(g3_stock("st_tv", range(10, 50, 10)), 1, 1), areas)
     tv = g3_timevariable("M", OrderedDict([("init", gp("tvM.init", value=0.1)), ("2001-02", gp("tvM.a", value=0.4)),
                                            ("2002", gp("tvM.b", value=0.2) * 1.5)]))
+    # a third stock that only grows: Linf by year, K a g3_timevariable (the growth matrices follow the parameters in force)
+    sg = g3s_livesonareas(g3s_age(g3_stock("st_grow", range(10, 60, 5)), 1, 2), areas)
+    tk = g3_timevariable("K", OrderedDict([("init", gp("tvK.init", value=0.2)), ("2001", gp("tvK.a", value=0.5)), ("2002-03", gp("tvK.b", value=0.1))]))
     actions = [
         g3a_time(2000, 2002, [3, 3, 6]),
-        g3a_initialconditions_normalcv(sy), g3a_initialconditions_normalcv(sv),
+        g3a_initialconditions_normalcv(sy), g3a_initialconditions_normalcv(sv), g3a_initialconditions_normalcv(sg),
         g3a_naturalmortality(sy, g3a_naturalmortality_exp(gp("Mt", by_stock=True, by_age=True, by_year=True, by_step=True))),
         g3a_naturalmortality(sv, g3a_naturalmortality_exp(tv)),
+        g3a_growmature(sg, g3a_grow_impl_bbinom(g3a_grow_lengthvbsimple(gp("Linf_t", by_stock=True, by_year=True), tk),
+                                                g3a_grow_weightsimple(), maxlengthgroupgrowth=3)),
     ]
     rng = np.random.default_rng(seed)
     yrs = [2000, 2001, 2002]
     si = dict(year=yrs, step=[3] * 3, number=list(rng.uniform(1e3, 1e4, 3)))
     actions.append(g3l_abundancedistribution("si", si, stocks=[sy, sv], function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    ld = dict(year=[y for y in yrs for _ in range(5)], step=[3] * 15, length=["[10,20)", "[20,30)", "[30,40)", "[40,50)", "[50,Inf)"] * 3,
+              number=list(rng.uniform(10, 100, 15)))
+    actions.append(g3l_abundancedistribution("ldist_grow", ld, stocks=[sg], function_f=g3l_distribution_sumofsquares()))
     actions += [g3l_bounds_penalty(actions)]
     model = g3_to_cuda(actions)
     p = model.parameter_template
@@ -821,6 +829,12 @@ def build_timevar_rig(seed=123):
         for st in (1, 2, 3):
             for a in (1, 2):
                 p = g3_init_val(p, f"st_year.Mt.{y}.{st}.{a}", 0.1 + 0.05 * (y - 2000) + 0.02 * st + 0.01 * a, lower=0.01, upper=1)
+    for i, y in enumerate(yrs):
+        p = g3_init_val(p, f"st_grow.Linf_t.{y}", 55 + 10 * i, lower=40, upper=90)
+    p = g3_init_val(p, "tvK.init", 0.2, lower=0.05, upper=1)
+    p = g3_init_val(p, "tvK.a", 0.5, lower=0.05, upper=1)
+    p = g3_init_val(p, "tvK.b", 0.1, lower=0.05, upper=1)
+    p = g3_init_val(p, "*.bbin", 10, lower=1, upper=100)
     p = g3_init_val(p, "tvM.init", 0.1, lower=0.01, upper=1)
     p = g3_init_val(p, "tvM.a", 0.4, lower=0.01, upper=1)
     p = g3_init_val(p, "tvM.b", 0.2, lower=0.01, upper=1)

@@ -52,6 +52,7 @@ struct KArgs {
     int t_suitq[32];                        // per predator-prey pair: suitability [set][predator length][prey length]
     int t_pts[MAXS], t_pmc[MAXS];           // per stock predator: totals / consumption factors [area][length]; max consumption [length]
     int t_mig[MAXS], t_mig_steps[MAXS];     // migration matrices [step][dest][src]; steps on which the stock migrates
+    int w_grow_nset[MAXS];                  // slot sets of time-varying growth parameters (1 otherwise)
     int w_mort_nset[MAXS];                  // slot sets of a time-varying M (1 otherwise)
     int t_sps;                              // per stock: the recruitment sum s of a spawning stock at this step (g3a_spawn)
     int t_remf, t_colbase[MAXS], t_cmat[MAXS];      // per global column: unclaimed share; first global column; constant-maturity ratios

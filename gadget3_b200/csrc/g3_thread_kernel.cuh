@@ -158,12 +158,13 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             }
             const int n2 = St[G3S_GROW_N];
             if (n2 < 0) continue;
-            const int32_t* gs = I + St[G3S_GROW_OFF];
             const bool cont = St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0;
             const int gsz = (n2 + 1) * L;
+            for (int gset = 0; gset < A.w_grow_nset[s]; gset++) {       // (one set unless the growth parameters vary with time)
+            const int32_t* gs = I + St[G3S_GROW_OFF] + 5 * gset;
             {
                 const T wb = SLOT(gs[4]);
-                for (int l = 0; l < L; l++) W(A.t_pw[s] + l) = xpow(midlen[l], wb);
+                for (int l = 0; l < L; l++) W(A.t_pw[s] + gset * L + l) = xpow(midlen[l], wb);
             }
             for (int idt = 0; idt < A.w_ndt; idt++) {
                 const double dt = A.w_dt_len[idt] / 12.0;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 }
                 // destination-oriented band [d][l] = P(l - d -> l), plus-group tail sums folded in (R/action_grow.R:233-271)
                 for (int v = 0; v < (cont ? 3 : 1); v++) {
-                    const int o = (v == 0 ? A.t_g[s] : (v == 1 ? A.t_gr[s] : A.t_gn[s])) + idt * gsz;
+                    const int o = (v == 0 ? A.t_g[s] : (v == 1 ? A.t_gr[s] : A.t_gn[s])) + (gset * A.w_ndt + idt) * gsz;
                     for (int d = 0; d <= n2; d++)
                         for (int j = 0; j < L; j++) {
                             const int src = j - d;
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                         }
                 }
             }
+            }   // gset
         }
 
         // ================= g3a_initialconditions (R/action_renewal.R:83-163)
@@ -588,7 +590,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 // place: every source l - d is still the old value when l is rebuilt. Columns are the inner
                 // loop: the band P(l - d -> l) and the weight gains are loaded once per l for all columns.
                 const int gsz = (grow_n + 1) * L;
-                const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 3]) : T(0.0);
+                const int gset = grow_n >= 0 && St[G3S_GROW_TMAP_OFF] >= 0 ? I[St[G3S_GROW_TMAP_OFF] + t] : 0;     // time-varying growth: this step's tables
+                const T wal = grow_n >= 0 ? SLOT(I[St[G3S_GROW_OFF] + 5 * gset + 3]) : T(0.0);
                 const int mset = St[G3S_MORT_TMAP_OFF] >= 0 ? I[St[G3S_MORT_TMAP_OFF] + t] : 0;        // time-varying M: this step's table
                 const T* pmort = ws + (unsigned)(A.t_mort[s] + (mset * A.w_ndt + idt) * ncol) * NTH;
                 const int4* cinc = A.t_colinc + A.t_colbase[s];
@@ -598,9 +601,9 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 const int cper = NW <= 8 ? ncol : A.t_cblk;
                 for (int cb0 = 0; cb0 < ncol; cb0 += cper) {
                 const int cb1 = min(cb0 + cper, ncol);
-                const T* pg = ws + (unsigned)((cont_now ? A.t_gn[s] : A.t_g[s]) + idt * gsz + (L - 1)) * NTH;     // staying part, [d][l]
-                const T* pgr = ws + (unsigned)(A.t_gr[s] + idt * gsz + (L - 1)) * NTH;                              // maturing part
-                const T* ppw = ws + (unsigned)(A.t_pw[s] + (L - 1)) * NTH;
+                const T* pg = ws + (unsigned)((cont_now ? A.t_gn[s] : A.t_g[s]) + (gset * A.w_ndt + idt) * gsz + (L - 1)) * NTH;     // staying part, [d][l]
+                const T* pgr = ws + (unsigned)(A.t_gr[s] + (gset * A.w_ndt + idt) * gsz + (L - 1)) * NTH;                              // maturing part
+                const T* ppw = ws + (unsigned)(A.t_pw[s] + gset * L + (L - 1)) * NTH;
                 for (int l = L - 1; l >= 0; l--, pg -= NTH, pgr -= NTH, ppw -= NTH) {
                     // Narrow bands keep the band and the weight gains of this length in registers for all columns;
                     // wide ones (maxlengthgroupgrowth > 7) would spill them, so they stream them per column instead.

@@ -48,8 +48,9 @@ struct StockRec {
     int g_mort;             // [set][idt][col] exp(-M dt)
     int mort_tmap, mort_nset;   // I: the slot set of M each step uses (time-varying M), or -1; number of sets
     int g_rd, g_rw;         // [k][l] renewal numbers shape (x 1e4) and weight
-    int g_wq;               // [l] walpha * midlen^wbeta; NW - 1 zero rows before row 0, NBX - 1 after row L - 1
-    int g_band, g_bandr;    // destination-oriented growth bands, staying (or whole) / maturing part: [set][idt][(L + NBX - 1) * NW]
+    int g_wq;               // [gset][l] walpha * midlen^wbeta; NW - 1 zero rows before row 0, NBX - 1 after row L - 1 (wq_stride apart)
+    int grow_tmap, grow_nset, wq_stride;    // I: the set of growth parameters each step uses (time-varying growth), or -1; sets
+    int g_band, g_bandr;    // destination-oriented growth bands, staying (or whole) / maturing part: [gset][set][idt][(L + NBX - 1) * NW]
     int h_wq, h_band, h_bandr;      // the same tables in the H entries (shared memory beside the state), or -1: the planner puts
                                     // the hottest tables there as far as room allows (plain-double runs only)
     int band_percol, bsz;   // one set per column (continuous maturity with an age term) or per stock
@@ -464,13 +465,15 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             }
             const int n2 = St.grow_n;
             if (n2 < 0) continue;
-            const int32_t* gs = I + St.grow_ioff;
             // where these tables live: the H entries (shared memory) if the planner found room for them, else the slab
             const bool hwq = A.use_h && St.h_wq >= 0;
             double* const bandp = A.use_h && St.h_band >= 0 ? HP(St.h_band) : GP(St.g_band);
             double* const bandrp = A.use_h && St.h_bandr >= 0 ? HP(St.h_bandr) : GP(St.g_bandr);
+            const int ncset = St.band_percol ? St.ncol : 1;
+            for (int gset = 0; gset < (XF ? St.grow_nset : 1); gset++) {       // (one set unless the growth parameters vary with time)
+            const int32_t* gs = I + St.grow_ioff + 5 * gset;
             for (int l = 0; l < L; l++)         // walpha l^wbeta (g3a_grow_weightsimple, R/action_grow.R:58-71)
-                if (mine()) stT<T>(hwq ? HP(St.h_wq + l) : GP(St.g_wq + l), SLOT(gs[3]) * xpow(midlen[l], SLOT(gs[4])));
+                if (mine()) stT<T>(hwq ? HP(St.h_wq + l) : GP(St.g_wq + gset * St.wq_stride + l), SLOT(gs[3]) * xpow(midlen[l], SLOT(gs[4])));
             // ---- growth bands: P(l -> l + x), x = 0..n, of each source row l (growth_bbinom in product form,
             // R/action_grow.R:155-213), stored destination-oriented: entry [l + x][x]; everything that would leave the
             // length axis is summed into the plus group's row L - 1 (R/action_grow.R:233-271). Continuous maturity splits
@@ -478,8 +481,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
             // age term there is a set per column.
             const bool cont = St.mat_kind == G3MAT_CONTINUOUS && St.has_out;
             const double pdl = R[St.plusdl_roff];
-            const int nset = St.band_percol ? St.ncol : 1;
-            for (int set = 0; set < nset; set++)
+            for (int set = 0; set < ncset; set++)
                 for (int idt = 0; idt < A.ndt; idt++)
                     for (int l = 0; l < L; l++) {
                         if (!mine()) continue;
@@ -499,7 +501,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             if (ms[2] >= 0) { mbeta = SLOT(ms[2]); inner = inner - mbeta * ((double)(St.minage + set % St.nage) - SLOT(ms[3])); }
                             m0 = 1.0 / (1.0 + xexp(inner));
                         }
-                        const int base = (set * A.ndt + idt) * St.bsz;
+                        const int base = ((gset * ncset + set) * A.ndt + idt) * St.bsz;
                         const int dtail = L - 1 - l;            // jumps of at least dtail end in the plus group
                         T ta(0.0), tr(0.0);
                         T gx[NW], rx[NW];
@@ -527,6 +529,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             if (cont) stT<T>(bandrp + (unsigned)(base + (L - 1) * NW + dtail) * C, tr);
                         }
                     }
+            }   // gset
         }
         // ---- per column: mortality factors, initial conditions, maturation remainder, constant-maturity ratios
         for (int gc = warp; gc < A.NCOLS; gc += W) {
@@ -1014,10 +1017,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     continue;
                 }
                 const T remf = trans_now ? G(Cl.g_remf) : T(0.0);
-                const int bset = ((St.band_percol ? Cl.col : 0) * A.ndt + idt) * St.bsz + U.lo * NW;
+                const int gset = XF && St.grow_tmap >= 0 ? I[St.grow_tmap + t] : 0;       // time-varying growth: this step's tables
+                const int bset = (((XF ? gset * (St.band_percol ? St.ncol : 1) : 0) + (St.band_percol ? Cl.col : 0)) * A.ndt + idt) * St.bsz + U.lo * NW;
                 const double* const pB = A.use_h && St.h_band >= 0 ? HP(St.h_band + bset) : GP(St.g_band + bset);
                 const double* const pBr = A.use_h && St.h_bandr >= 0 ? HP(St.h_bandr + bset) : GP(St.g_bandr + bset);
-                const double* const pQ = A.use_h && St.h_wq >= 0 ? HP(St.h_wq + U.lo) : GP(St.g_wq + U.lo);
+                const double* const pQ = A.use_h && St.h_wq >= 0 ? HP(St.h_wq + U.lo) : GP(St.g_wq + (XF ? gset * St.wq_stride : 0) + U.lo);
                 const double* const pCm = St.g_cmat >= 0 ? GP(St.g_cmat + Cl.col * L + U.lo) : pQ;
                 const double* const pGh = U.g_ghost >= 0 ? GP(U.g_ghost) : pQ;
                 const bool stash = trans_now && Cl.s_tn >= 0;

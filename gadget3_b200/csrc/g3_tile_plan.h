@@ -197,7 +197,7 @@ inline void plan_place_hot(TilePlan& P, size_t smem_bytes) {
     // state the tables bring nothing (C2: 806 k with, 830 k without): its growth pass waits on the fp64 pipe, not on these loads.
     const bool state_resident = state + 4096 <= smem_bytes * (size_t)std::max(1, P.ctas_per_sm);
     for (auto& r : P.st) {
-        if (r.grow_n < 0 || state_resident) continue;
+        if (r.grow_n < 0 || state_resident || r.grow_nset > 1) continue;
         const int n = A.NWc - 1 + r.L + NBX - 1;
         if (room(n)) { r.h_wq = nh + A.NWc - 1; nh += n; }
     }
@@ -206,7 +206,7 @@ inline void plan_place_hot(TilePlan& P, size_t smem_bytes) {
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.st[x].ncol > P.st[y].ncol; });
     for (int s : order) {
         StockRec& r = P.st[s];
-        if (r.grow_n < 0 || state_resident) continue;
+        if (r.grow_n < 0 || state_resident || r.grow_nset > 1) continue;
         const int n = (r.band_percol ? r.ncol : 1) * A.ndt * r.bsz;
         if (room(n)) { r.h_band = nh; nh += n; }
         if (r.g_bandr != r.g_band && r.h_band >= 0 && room(n)) { r.h_bandr = nh; nh += n; }
@@ -362,12 +362,17 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         r.g_mort = takeg(r.mort_ioff >= 0 ? r.mort_nset * r.ncol * A.ndt : 0);
         if (r.mort_ioff >= 0 && r.mort_tmap >= 0) A.xf = 1;
         r.g_rd = takeg(r.n_renew * r.L); r.g_rw = takeg(r.n_renew * r.L);
-        r.g_wq = r.grow_n >= 0 ? take_padded(r.L) : 0;
+        // time-varying growth parameters: one copy of walpha l^wbeta and of the bands per slot set
+        r.grow_tmap = St[G3S_GROW_TMAP_OFF]; r.grow_nset = 1;
+        if (r.grow_n >= 0 && r.grow_tmap >= 0) { A.xf = 1; for (int t = 0; t < A.NT; t++) r.grow_nset = std::max(r.grow_nset, I[r.grow_tmap + t] + 1); }
+        r.wq_stride = NWc - 1 + r.L + NBX - 1;
+        r.g_wq = 0;
+        if (r.grow_n >= 0) for (int gsn = 0; gsn < r.grow_nset; gsn++) { const int o = take_padded(r.L); if (gsn == 0) r.g_wq = o; }
         const bool trans = r.grow_n >= 0 && r.has_out;
         const bool cont = trans && r.mat_kind == G3MAT_CONTINUOUS;
         r.band_percol = cont && I[r.mat_ioff + 2] >= 0;         // age term: M0 differs per column (R/action_mature.R:18,44-74)
         r.bsz = r.grow_n >= 0 ? (r.L + NBX - 1) * NWc : 0;
-        const int nset = r.band_percol ? r.ncol : 1;
+        const int nset = (r.band_percol ? r.ncol : 1) * r.grow_nset;
         r.g_band = takeg(nset * A.ndt * r.bsz);
         zero_g(r.g_band, nset * A.ndt * r.bsz);
         r.g_bandr = cont ? takeg(nset * A.ndt * r.bsz) : r.g_band;

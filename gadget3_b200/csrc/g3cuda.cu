@@ -235,11 +235,15 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
         A.t_mort[s] = take(St[G3S_MORT_OFF] >= 0 ? A.w_mort_nset[s] * St[G3S_NAGE] * St[G3S_NAREA] * A.w_ndt : 0);
         A.t_rd[s] = take(St[G3S_N_RENEW] * L);
         A.t_rw[s] = take(St[G3S_N_RENEW] * L);
-        A.t_pw[s] = take(n >= 0 ? L : 0);
+        A.w_grow_nset[s] = 1;
+        if (n >= 0 && St[G3S_GROW_TMAP_OFF] >= 0)
+            for (int t = 0; t < I[G3H_NT]; t++) A.w_grow_nset[s] = std::max(A.w_grow_nset[s], I[St[G3S_GROW_TMAP_OFF] + t] + 1);
+        const int gn = A.w_grow_nset[s];
+        A.t_pw[s] = take(n >= 0 ? gn * L : 0);
         if (n < 0) { A.t_g[s] = A.t_gr[s] = A.t_gn[s] = 0; continue; }
         int g = (n + 1) * L; maxg = std::max(maxg, g);
-        A.t_g[s] = take(g * A.w_ndt);
-        if (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0) { A.t_gr[s] = take(g * A.w_ndt); A.t_gn[s] = take(g * A.w_ndt); }
+        A.t_g[s] = take(gn * g * A.w_ndt);
+        if (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0) { A.t_gr[s] = take(gn * g * A.w_ndt); A.t_gn[s] = take(gn * g * A.w_ndt); }
         else { A.t_gr[s] = A.t_gn[s] = A.t_g[s]; }
     }
     A.t_scr = take(3 * maxg);

@@ -202,7 +202,8 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         r[K["G3S_CELL_OFF"]] = cell_off
         r[K["G3S_MIDLEN_ROFF"]] = b.alloc_reals(s.midlen)
         r[K["G3S_PLUSDL_ROFF"]] = b.alloc_reals([s.plusdl])
-        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF", "G3S_OTHERFOOD_OFF", "G3S_SPAWN_OFF", "G3S_MORT_TMAP_OFF"):
+        for f in ("G3S_INIT_OFF", "G3S_MORT_OFF", "G3S_GROW_N", "G3S_MIGRATE_OFF", "G3S_OTHERFOOD_OFF", "G3S_SPAWN_OFF", "G3S_MORT_TMAP_OFF",
+                  "G3S_GROW_TMAP_OFF"):
             r[K[f]] = -1
         dims = [d for d in s.dims if d != "length"]
         r[K["G3S_DIMORDER"]] = 0 if dims == ["age", "area"] else 1
@@ -389,9 +390,11 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         c = Ctx(stock=s)
         r[K["G3S_GROW_N"]] = im.maxlengthgroupgrowth
         maxn = max(maxn, im.maxlengthgroupgrowth)
-        r[K["G3S_GROW_OFF"]] = b.alloc_ints([
-            low.slot(im.delta_len_f.linf_f, c), low.slot(im.delta_len_f.kappa_f, c),
-            low.slot(im.beta_f, c), low.slot(im.delta_wgt_f.alpha_f, c), low.slot(im.delta_wgt_f.beta_f, c)])
+        gtab, gtmap = time_sets(lambda tc: [low.slot(f, c.replace(**tc)) for f in (
+            im.delta_len_f.linf_f, im.delta_len_f.kappa_f, im.beta_f, im.delta_wgt_f.alpha_f, im.delta_wgt_f.beta_f)])
+        r[K["G3S_GROW_OFF"]] = b.alloc_ints(gtab)
+        if gtmap is not None:
+            r[K["G3S_GROW_TMAP_OFF"]] = b.alloc_ints(gtmap)
         m = a.maturity_f
         if m is not None:
             r[K["G3S_MAT_KIND"]] = K["G3MAT_CONTINUOUS"] if m.kind == "continuous" else K["G3MAT_CONSTANT"]

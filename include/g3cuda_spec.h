@@ -26,7 +26,7 @@
 #ifndef G3CUDA_SPEC_H
 #define G3CUDA_SPEC_H
 
-#define G3CUDA_SPEC_VERSION 6
+#define G3CUDA_SPEC_VERSION 7
 
 /* ---- header: ints[0..G3H_LEN) ------------------------------------------ */
 #define G3H_VERSION        0
@@ -99,7 +99,10 @@
 #define G3S_MORT_TMAP_OFF 28   /* time-varying natural mortality (by_year / by_step tables, g3_timevariable; R/params.R:122-129,
                                   R/timevariable.R:1-31): ints[NT]: which set of MORT_OFF's ints[NSET*NAGE*NAREA] slots step t uses;
                                   -1 = one set for every step */
-#define G3S_LEN           29
+#define G3S_GROW_TMAP_OFF 29   /* time-varying growth parameters (Linf, K, bbin, walpha, wbeta by year / step, g3_timevariable): ints[NT]:
+                                  which set of GROW_OFF's ints[NSET*5] slots step t uses; -1 = one set for every step. The reference
+                                  recomputes its growth matrices whenever their inputs change (R/action_grow.R:391-410) */
+#define G3S_LEN           30
 
 /* ---- spawning record (g3a_spawn, R/action_spawn.R:86-233) ----------------
    At order 6 (after growth, before the maturing fish arrive and before renewal): spawningnum = num * proportion(l);

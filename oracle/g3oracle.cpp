@@ -584,8 +584,11 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                 trans_num[s].assign(ncell, T(0.0));
                 trans_wgt[s].assign(wgt.begin() + c0, wgt.begin() + c0 + ncell);
             }
-            const int32_t* gs = S.I + St[G3S_GROW_OFF];
-            int calc = (int)std::floor(cur_step_size * 12);
+            // time-varying growth parameters: the slot set of this step; the matrices are recomputed when the step length
+            // OR the set changes (the reference keys its cache on what the formulas depend on, R/action_grow.R:391-410)
+            const int gset = St[G3S_GROW_TMAP_OFF] >= 0 ? S.I[St[G3S_GROW_TMAP_OFF] + cur_time] : 0;
+            const int32_t* gs = S.I + St[G3S_GROW_OFF] + 5 * gset;
+            int calc = (int)std::floor(cur_step_size * 12) + 100 * gset;
             if (lastcalc[s] != calc) {
                 T linf = slot(gs[0]), kappa = slot(gs[1]), beta = slot(gs[2]), wa = slot(gs[3]), wb = slot(gs[4]);
                 std::vector<T> dl(L);

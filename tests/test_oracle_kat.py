@@ -332,3 +332,40 @@ def test_time_varying_selectivity(oracle_lib):
     last = 1 / (1 + np.exp(-alpha * (midlen - g("fish.f_comm.l50.2004"))))
     np.testing.assert_allclose(np.asarray(rep["suit_fish_mat_f_comm__report"]).ravel(), last, rtol=1e-13)
     assert len({g(f"fish.f_comm.l50.{y}") for y in range(2000, 2005)}) == 5
+
+
+def test_time_varying_growth(oracle_lib):
+    """growth parameters that vary with time (Linf by year, K a g3_timevariable). The reference
+    recomputes its growth matrices when their inputs change (R/action_grow.R:391-410). st_grow of TIMEVAR_RIG only grows,
+    so its numbers after a step are the beta-binomial redistribution (growth_bbinom, R/action_grow.R:155-213, nine-lgamma
+    form; delta from g3a_grow_lengthvbsimple, R/action_grow.R:44-55) of the numbers before it -- with THAT step's Linf and K --
+    re-derived here with scipy's gammaln."""
+    from scipy.special import gammaln
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["TIMEVAR_RIG"]()
+    v = p.values()
+    g = lambda n: float(v[p.index(n)])
+    rep = unpack_report(model, Oracle(*model.pack(p)).report(v))
+    num = np.asarray(rep["dstart_st_grow__num"])          # [length][age][area][t]
+    L, n, dl = num.shape[0], 3, 5.0
+    midlen = np.arange(12.5, 60, 5.0)
+    az = lambda a: (np.maximum(a * 1000.0, 0.0) + np.log1p(np.exp(-np.abs(a * 1000.0)))) / 1000.0
+    dt = [3 / 12, 3 / 12, 6 / 12]
+    beta = az(g("st_grow.bbin"))
+    for t in range(8):
+        y, st = 2000 + t // 3, t % 3 + 1
+        K = g("tvK.init") if (y, st) < (2001, 1) else g("tvK.a") if (y, st) < (2002, 3) else g("tvK.b")
+        delta = az(az((g(f"st_grow.Linf_t.{y}") - midlen) * (1 - np.exp(-K * dt[st - 1]))) / dl)
+        alpha = (beta * delta) / (n - delta)
+        P = np.zeros((L, L))
+        for x in range(n + 1):
+            pm = np.exp(gammaln(n + 1) + gammaln(alpha + beta) + gammaln(n - x + beta) + gammaln(x + alpha) - gammaln(n - x + 1)
+                        - gammaln(x + 1) - gammaln(n + alpha + beta) - gammaln(beta) - gammaln(alpha))
+            for l in range(L):
+                P[min(l + x, L - 1), l] += pm[l]
+        for a in range(2):
+            want = P @ num[:, a, 0, t]
+            np.testing.assert_allclose(num[:, a, 0, t + 1], want, rtol=1e-9, atol=1e-12 * want.max(), err_msg=f"t = {t}, age idx {a}")
+    assert len({g(f"st_grow.Linf_t.{y}") for y in (2000, 2001, 2002)}) == 3
