@@ -425,3 +425,24 @@ def test_lean_instantiations_are_bit_identical(setups, name):
     tol = 1e-12 * np.abs(b[0]) + US_WEIGHT * _us_tolerance(model, p, b[1][:, -2])
     assert (np.abs(a[0] - b[0]) <= tol).all()
     assert np.median(_rel(a[0], b[0])) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["C2", "MINI_SPAWN", "SPAWN_RIG", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_TIMEVAR", "TIMEVAR_RIG"])
+def test_results_do_not_depend_on_scheduling(oracle_lib, name):
+    """The work queues hand units to whichever warp is free and the spawning / hand-over phases run beside each other: every
+    sum has a fixed order all the same, so repeated launches, and a vector alone or among 300 others, give identical bits
+    (a missing barrier or a racing update would show here)."""
+    model, p = CONFIGS[name]()
+    fn = g3_cuda_adfun(model, p, device=0)
+    full = fn.full_par(parameter_batch(p, 300, seed=9))
+    ref = fn.handle.eval_batch(full, want_comp=True)
+    for _ in range(4):
+        again = fn.handle.eval_batch(full, want_comp=True)
+        assert (again[0] == ref[0]).all() and (again[1] == ref[1]).all()
+    for i in (0, 131, 299):
+        alone = fn.handle.eval_batch(full[i:i + 1], want_comp=True)
+        assert alone[0][0] == ref[0][i] and (alone[1][0] == ref[1][i]).all()
+    tidx = fn.opt_idx[:5].astype(np.int32)
+    g1 = fn.handle.eval_batch(full[:40], tangent_idx=tidx)
+    g2 = fn.handle.eval_batch(full[:40], tangent_idx=tidx)
+    assert (g1[2] == g2[2]).all() or (np.isnan(g1[2]) == np.isnan(g2[2])).all() and np.array_equal(np.nan_to_num(g1[2]), np.nan_to_num(g2[2]))
