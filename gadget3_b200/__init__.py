@@ -26,7 +26,7 @@ from .actions import (g3_action_order, g3_suitability_andersen, g3_suitability_a
 from .likelihood import (g3l_abundancedistribution, g3l_bounds_penalty, g3l_catchdistribution,
                          g3l_distribution, g3l_distribution_multinomial, g3l_distribution_sumofsquaredlogratios, g3l_distribution_sumofsquares,
                          g3l_distribution_surveyindices_linear, g3l_distribution_surveyindices_log,
-                         g3l_understocking)
+                         g3l_random_dnorm, g3l_random_walk, g3l_understocking)
 from .run_cuda import G3CudaADFun, G3CudaModel, g3_cuda_adfun, g3_to_cuda, unpack_report
 
 __version__ = "0.1.0"

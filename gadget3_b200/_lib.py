@@ -63,6 +63,8 @@ def load():
     lib.g3cuda_set_kernel.restype = C.c_int
     lib.g3cuda_set_tile_warps.argtypes = [vp, C.c_int]
     lib.g3cuda_set_tile_warps.restype = C.c_int
+    lib.g3cuda_set_tile_slots.argtypes = [vp, C.c_int]
+    lib.g3cuda_set_tile_slots.restype = C.c_int
     lib.g3cuda_set_tile_partition.argtypes = [vp, C.c_int, C.c_int]
     lib.g3cuda_set_tile_partition.restype = C.c_int
     lib.g3cuda_multi_create.argtypes = [C.POINTER(_Spec), ip, C.c_int32, C.POINTER(vp)]
@@ -89,7 +91,7 @@ def load():
 EXPORTED = ["g3cuda_model_create", "g3cuda_model_free", "g3cuda_n_par", "g3cuda_n_nll", "g3cuda_n_steps",
             "g3cuda_report_len", "g3cuda_eval_batch", "g3cuda_eval_batch_device", "g3cuda_launch_count",
             "g3cuda_last_kernel_ms", "g3cuda_report", "g3cuda_last_error", "g3cuda_abi_version",
-            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe", "g3cuda_set_tile_warps", "g3cuda_set_tile_partition", "g3cuda_tile_info",
+            "g3cuda_fp64_peak_tflops", "g3cuda_set_kernel", "g3cuda_math_probe", "g3cuda_set_tile_warps", "g3cuda_set_tile_slots", "g3cuda_set_tile_partition", "g3cuda_tile_info",
             "g3cuda_multi_create", "g3cuda_multi_free", "g3cuda_multi_n_devices", "g3cuda_multi_model", "g3cuda_multi_eval_batch"]
 
 
@@ -168,6 +170,10 @@ class Handle:
     def set_tile_partition(self, warps: int = 0, seg_rows: int = 0):
         """Re-plan the tile kernel: unit warps (0 = planner's choice), rows per unit (0 = planner's choice, -1 = whole columns)."""
         self._check(self.lib.g3cuda_set_tile_partition(self.h, int(warps), int(seg_rows)), "g3cuda_set_tile_partition")
+
+    def set_tile_slots(self, tiles: int):
+        """At most `tiles` tiles of the tile kernel in flight (0 = every slot of the device)."""
+        self._check(self.lib.g3cuda_set_tile_slots(self.h, int(tiles)), "g3cuda_set_tile_slots")
 
     def tile_info(self) -> dict:
         out = np.zeros(6, dtype=np.int32)

@@ -82,13 +82,14 @@ def _fleet_data(rng, years, landings_mean, landings_sd, n_ldist, len_breaks, n_a
     return out
 
 
-def build_c1(seed=123, data=None, likelihood="sumofsquares"):
+def build_c1(seed=123, data=None, likelihood="sumofsquares", random=False):
     """introduction-single-stock (vignettes/introduction-single-stock.Rmd:116-596, 666-701).
     `data`: the fleet tables (landings, ldist, aldist, si as column dicts) to use instead of the synthetic
     draws -- tools/replay_tmb_bundle.py feeds the tables an R session dumped.
     `likelihood = "multinomial"`: the same model scored with g3l_distribution_multinomial for the two catch
     distributions and g3l_distribution_surveyindices_linear (slope and intercept estimated) for the index
-    (R/likelihood_distribution.R:41-60,82-125)."""
+    (R/likelihood_distribution.R:41-60,82-125).
+    `random`: plus a g3l_random_dnorm and a g3l_random_walk on the yearly recruitment parameters."""
     rng = np.random.default_rng(seed)
     years = list(range(1990, 2024))
     area_names = g3_areas(["IXa", "IXb"])
@@ -121,6 +122,13 @@ def build_c1(seed=123, data=None, likelihood="sumofsquares"):
         g3l_abundancedistribution("dist_si_cpue", d["si"], stocks=[fish],
                                   function_f=si_f, area_group=area_names, report=True, nll_breakdown=True),
     ]
+    if random:      # recruitment deviations penalised as a random effect would be (R/likelihood_random.R:14-109)
+        from . import g3l_random_dnorm, g3l_random_walk
+        rec = g3_parameterized("rec", by_stock=[fish], by_year=True, scale=1e4)
+        actions += [g3l_random_dnorm("rec_dnorm", rec, mean_f=g3_parameterized("rec_mean", value=1.0, lower=0.1, upper=10),
+                                     sigma_f=g3_parameterized("rec_sigma", value=2.0, lower=0.5, upper=5), period="year"),
+                    g3l_random_walk("rec_walk", rec, sigma_f=g3_parameterized("rec_sigma", value=2.0, lower=0.5, upper=5),
+                                    period="year")]
     actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
     model = g3_to_cuda(actions)
     midlen = fish.midlen
@@ -852,6 +860,64 @@ def build_timevar_rig(seed=123):
     return model, p
 
 
+def build_random_rig(seed=123):
+    """The rig of the reference's random-effect test (tests/test-likelihood_random.R:6-34): 1990-1994 in quarters, a
+    g3l_random_dnorm on the log scale and one on the linear scale (single parameters: scored once, at the last step), a
+    g3l_random_walk over a by-year table and one over a by-year-by-step table, each switched on by its own weight
+    parameter. The reference's rig has no stock at all; here one stock that only dies keeps the planner busy (it adds
+    nothing to the objective)."""
+    from . import g3a_naturalmortality_exp, g3l_random_dnorm, g3l_random_walk
+    gp = g3_parameterized
+    areas = g3_areas(["a"])
+    st = g3s_livesonareas(g3s_age(g3_stock("st", range(10, 50, 10)), 1, 2), areas)
+    actions = [
+        g3a_time(1990, 1994, [3, 3, 3, 3]),
+        g3a_initialconditions_normalcv(st),
+        g3a_naturalmortality(st, g3a_naturalmortality_exp(gp("M", by_stock=True))),
+        g3l_random_dnorm("dnorm_log", gp("dnorm_log", value=0.0), mean_f=gp("dnorm_log_mean", value=0.0, optimise=False),
+                         sigma_f=gp("dnorm_log_sigma", value=1.0, optimise=False),
+                         weight=gp("dnorm_log_enabled", value=0.0, optimise=False)),
+        g3l_random_dnorm("dnorm_lin", gp("dnorm_lin", value=0.0), mean_f=gp("dnorm_lin_mean", value=0.0, optimise=False),
+                         sigma_f=gp("dnorm_lin_sigma", value=1.0, optimise=False), log_f=False,
+                         weight=gp("dnorm_lin_enabled", value=0.0, optimise=False)),
+        g3l_random_walk("walk_year", gp("walk_year", by_year=True, value=0.0),
+                        sigma_f=gp("walk_year_sigma", value=1.0, optimise=False),
+                        weight=gp("walk_year_enabled", value=0.0, optimise=False)),
+        g3l_random_walk("walk_step", gp("walk_step", by_year=True, by_step=True, value=0.0),
+                        sigma_f=gp("walk_step_sigma", value=1.0, optimise=False),
+                        weight=gp("walk_step_enabled", value=0.0, optimise=False)),
+    ]
+    model = g3_to_cuda(actions)
+    rng = np.random.default_rng(seed)
+    p = model.parameter_template
+    for n in ("dnorm_log", "dnorm_lin"):
+        p = g3_init_val(p, n, float(rng.uniform(0, 10)), lower=0, upper=10)
+        p = g3_init_val(p, n + "_mean", float(rng.uniform(0, 10)), optimise=False)
+        p = g3_init_val(p, n + "_sigma", float(rng.uniform(0.5, 10)), optimise=False)
+        p = g3_init_val(p, n + "_enabled", 1, optimise=False)
+    for y in range(1990, 1995):
+        p = g3_init_val(p, f"walk_year.{y}", float(rng.uniform(1, 10)), lower=1, upper=10)
+        for stp in range(1, 5):
+            p = g3_init_val(p, f"walk_step.{y}.{stp}", float(rng.uniform(1, 10)), lower=1, upper=10)
+    p = g3_init_val(p, "walk_year_sigma", 1.7, optimise=False)
+    p = g3_init_val(p, "walk_step_sigma", 0.6, optimise=False)
+    p = g3_init_val(p, "walk_year_enabled", 1, optimise=False)
+    p = g3_init_val(p, "walk_step_enabled", 1, optimise=False)
+    p = g3_init_val(p, "st.M", 0.2, lower=0.05, upper=0.5)
+    p = g3_init_val(p, "*.Linf", 50, optimise=False)
+    p = g3_init_val(p, "*.K", 0.3, optimise=False)
+    p = g3_init_val(p, "*.t0", -1.0, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.3, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, optimise=False)
+    p = g3_init_val(p, "init.F", 0.3, optimise=False)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    return model, p
+
+
 def build_mini_fleets(seed=123):
     """One stock on two areas fished by a numberfleet, a linearfleet and an effortfleet
     (R/action_predate.R:7-18,117-126) -- parity-test model for the catchabilities bench configs do not use."""
@@ -1043,5 +1109,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "TIMEVAR_RIG": build_timevar_rig,
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "C1_RANDOM": lambda: build_c1(random=True),
            "LING": build_ling}

@@ -901,6 +901,18 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 }
                 if (!si) for (int e = 0; e < nd; e++) W(ms + e) = T(0.0);     // zero counters for the next period
             }
+            // ================= g3l_random_dnorm / g3l_random_walk (R/likelihood_random.R:14-109)
+            for (int r = 0; r < I[G3H_NRAND]; r++) {
+                const int32_t* Rn = I + I[G3H_RAND_OFF] + r * G3RN_LEN;
+                if (!I[Rn[G3RN_RUN_OFF] + t]) continue;
+                const T sd = SLOT(I[Rn[G3RN_SIGMA_OFF] + t]);
+                const T resid = (SLOT(I[Rn[G3RN_PARAM_OFF] + t]) - SLOT(I[Rn[G3RN_MEAN_OFF] + t])) / sd;
+                const T logans = T(-0.91893853320467274178) - xlog(sd) - 0.5 * resid * resid;     // TMB dnorm
+                const T n = Rn[G3RN_LOG] ? T(0.0) - logans : xexp(logans);
+                nll = nll + SLOT(Rn[G3RN_WEIGHT]) * n;
+                W(A.t_ctot + A.NCOMP + r) = W(A.t_ctot + A.NCOMP + r) + n;
+                if (REPORT && live) A.report[1 + (size_t)(A.NCOMP + r) * NT + t] = val(n);
+            }
             // ================= g3l_understocking (R/likelihood_understocking.R:36-46)
             if (have_us) {
                 T u = (us_power == 2.0) ? us_tot * us_tot : xpow(us_tot, T(us_power));

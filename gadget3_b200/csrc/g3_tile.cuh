@@ -1334,6 +1334,20 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         GS(A.g_ctot + c, G(A.g_ctot + c) + cnll);
                     }
                 }
+                // ---- g3l_random_dnorm / g3l_random_walk (R/likelihood_random.R:14-109): formulas of parameters only
+                if (F_LIKE)
+                    for (int r = 0; r < I[G3H_NRAND]; r++) {
+                        const int32_t* const Rn = I + I[G3H_RAND_OFF] + r * G3RN_LEN;
+                        if (!I[Rn[G3RN_RUN_OFF] + t]) continue;
+                        const T sd = SLOT(I[Rn[G3RN_SIGMA_OFF] + t]);
+                        const T resid = (SLOT(I[Rn[G3RN_PARAM_OFF] + t]) - SLOT(I[Rn[G3RN_MEAN_OFF] + t])) / sd;
+                        const T logans = T(-0.91893853320467274178) - xlog(sd) - 0.5 * resid * resid;     // TMB dnorm
+                        const T n = Rn[G3RN_LOG] ? T(0.0) - logans : xexp(logans);
+                        if (lane_on) {
+                            nll = nll + SLOT(Rn[G3RN_WEIGHT]) * n;
+                            GS(A.g_ctot + A.NCOMP + r, G(A.g_ctot + A.NCOMP + r) + n);
+                        }
+                    }
                 // ---- g3l_understocking (R/likelihood_understocking.R:36-46)
                 if (have_us) {
                     T us_tot(0.0);

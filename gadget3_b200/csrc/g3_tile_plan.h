@@ -302,7 +302,7 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
     A.NC = I[G3H_NCELL]; A.NS = I[G3H_NSTOCK]; A.NPP = I[G3H_NPP]; A.NPRED = I[G3H_NPRED]; A.NCOMP = I[G3H_NCOMP];
     A.NX = I[G3H_NXBUF]; A.NSLOT = I[G3H_NSLOT]; A.NPAR = I[G3H_NPAR]; A.NT = I[G3H_NT]; A.NSTEPS = I[G3H_NSTEPS];
     A.NNLL = I[G3H_NNLL]; A.NBOUND = I[G3H_NBOUND]; A.maxL = I[G3H_MAXL];
-    A.spawn_mask = 0; A.sp_n = 0; A.sp_off = 0; A.xf = 0; A.need = 0;
+    A.spawn_mask = 0; A.sp_n = 0; A.sp_off = 0; A.xf = 0; A.need = I[G3H_NRAND] > 0 ? 8 : 0;      // random terms: with the rarer likelihood code
     if (A.NCOMP > 32) return fail("more than 32 likelihood components");
     if (A.NX > 32) return fail("more than 32 collect vectors");
     if (A.NSTEPS > 31) return fail("more than 31 steps per year");

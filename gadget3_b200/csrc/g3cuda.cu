@@ -68,6 +68,7 @@ struct g3cuda_model {
     cudaEvent_t ws_free = nullptr;      // recorded after every launch that uses a workspace: the next one waits for it,
                                         // whichever stream it is on (the workspaces are per handle, not per stream)
     int force_kernel = 0;               // 0 = automatic, 3 = thread kernel, 4 = tile kernel
+    int max_tiles = 0;                  // tuning hook: at most this many tiles in flight (0 = every slot of the device)
     int no_lean = 0;                    // set_kernel(5): the tile kernel's full instantiation even where a leaner one covers the model
     // ---- tile kernel (g3_tile.cuh): plan, device tables, per-CTA slabs
     g3t::TilePlan tplan;
@@ -154,6 +155,7 @@ int tile_geom(g3cuda_model* m, TileGeom* g) {
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g->per_sm, g->fn, (m->targs.W + 1) * 32, g->smem));
     if (g->per_sm < 1) return fail(G3CUDA_EUNSUPP, "tile kernel does not fit one SM (%d threads, %zu bytes of shared memory)", (m->targs.W + 1) * 32, g->smem);
     g->slots = (long long)g->per_sm * m->num_sms;
+    if (m->max_tiles > 0) g->slots = std::min<long long>(g->slots, m->max_tiles);
     return G3CUDA_OK;
 }
 
@@ -924,6 +926,12 @@ int g3cuda_set_tile_warps(g3cuda_model* m, int warps) {
     g3t::plan_set_warps(m->tplan, w);        // (the partition into units stays: only their assignment to warps changes)
     g3t::plan_place_hot(m->tplan, m->smem_optin);
     return tile_upload_tb(m);
+}
+
+int g3cuda_set_tile_slots(g3cuda_model* m, int tiles) {
+    if (!m || tiles < 0) return fail(G3CUDA_EINVAL, "bad argument");
+    m->max_tiles = tiles;
+    return G3CUDA_OK;
 }
 
 int g3cuda_set_tile_partition(g3cuda_model* m, int warps, int seg_rows) {

@@ -324,7 +324,7 @@ class Lowerer:
         for ex in reversed(p.prepend_extra):
             parts.append(str(ex))
         if p.by_stock is not False:
-            if ctx.stock is None:
+            if ctx.stock is None and (p.by_stock is True or isinstance(p.by_stock, str)):    # explicit stocks name themselves
                 raise G3Unsupported(f"parameter {p.name}: by_stock used outside a stock context")
             parts.append(self._stock_part(ctx.stock, p.by_stock))
         if p.by_predator is not False:

@@ -297,3 +297,77 @@ def g3l_bounds_penalty(actions_or_parameter_template=None, weight=1, scale=1e6):
         raise G3Unsupported("g3l_bounds_penalty(parameter_template): only the actions form is supported "
                             "(bounds are bound at g3_cuda_adfun() time)")
     return BoundsPenaltyAction(weight, scale)
+
+
+# --------------------------------------------------------------------------- random-effect penalties
+def _param_columns(e):
+    """The table columns of the g3_parameterized() calls inside ``e`` (what g3_parameterized_breakdown reports,
+    R/likelihood_random.R:1-12)."""
+    from .formula import BinOp, ParamExpr, UnOp
+    cols = set()
+
+    def walk(x):
+        if isinstance(x, ParamExpr):
+            for flag, col in ((x.by_stock, "stock"), (x.by_predator, "predator"), (x.by_year, "cur_year"),
+                              (x.by_step, "cur_step"), (x.by_age, "age"), (x.by_area, "area")):
+                if flag:
+                    cols.add(col)
+            if x.ifmissing is not None and not isinstance(x.ifmissing, (int, float)):
+                walk(x.ifmissing)
+        elif isinstance(x, BinOp):
+            walk(x.a), walk(x.b)
+        elif isinstance(x, UnOp):
+            walk(x.a)
+    walk(e)
+    return sorted(cols)
+
+
+def _guess_period(param_f):
+    """R/likelihood_random.R:1-12."""
+    cols = _param_columns(param_f)
+    if not cols:
+        return "single"
+    if "stock" in cols:
+        raise ValueError("Per-stock random parameters not supported yet")
+    if cols == ["cur_step", "cur_year"]:
+        return "step"
+    if cols == ["cur_year"]:
+        return "year"
+    if cols == ["cur_step"]:
+        raise ValueError("Seasonal random parameters not supported yet")
+    raise ValueError("Cannot use period='auto', set period manually: %s" % ", ".join(cols))
+
+
+class RandomAction(Action):
+    kind = "random"
+
+    def __init__(self, walk, nll_name, param_f, mean_f, sigma_f, log_f, period, nll_breakdown, weight):
+        from .formula import g3_parameterized, wrap
+        if period not in ("year", "step", "single", "auto"):
+            raise ValueError("period must be one of 'year', 'step', 'single', 'auto'")
+        if not isinstance(log_f, bool):
+            raise ValueError("log_f must be logical")
+        self.walk, self.nll_name = bool(walk), nll_name
+        self.param_f, self.sigma_f = wrap(param_f), wrap(sigma_f)
+        self.mean_f = None if walk else wrap(mean_f)
+        self.log_f = log_f
+        self.period = _guess_period(self.param_f) if period == "auto" else period
+        self.nll_breakdown = nll_breakdown
+        self.weight = wrap(g3_parameterized(nll_name + "_weight", optimise=False, value=1) if weight is None else weight)
+
+    @property
+    def report_name(self):
+        return ("nll_random_walk_" if self.walk else "nll_random_dnorm_") + self.nll_name
+
+
+def g3l_random_dnorm(nll_name, param_f, mean_f=0, sigma_f=1, log_f=True, period="auto", nll_breakdown=False, weight=None):
+    """R/likelihood_random.R:14-60: on every step of the period, nll += weight * -dnorm(param_f, mean_f, sigma_f, log)
+    (the sign is +1 when log_f is FALSE). The Laplace machinery of a random effect stays in TMB; this is the term the
+    objective function itself adds. weight defaults to the fixed parameter <nll_name>_weight = 1."""
+    return RandomAction(False, nll_name, param_f, mean_f, sigma_f, log_f, period, nll_breakdown, weight)
+
+
+def g3l_random_walk(nll_name, param_f, sigma_f=1, log_f=True, period="auto", nll_breakdown=False, weight=None):
+    """R/likelihood_random.R:62-109: as g3l_random_dnorm with the mean = param_f on the previous step of the period;
+    the first step only remembers the value."""
+    return RandomAction(True, nll_name, param_f, None, sigma_f, log_f, period, nll_breakdown, weight)

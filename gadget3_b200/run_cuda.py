@@ -60,6 +60,7 @@ class G3CudaModel:
         self._builder = None
         self.stock_names, self.stock_shapes, self.stock_dims = [], [], []
         self.comp_names, self.comp_shapes, self.comp_units = [], [], []
+        self.random_names = []      # report names of the g3l_random_dnorm / g3l_random_walk terms, packed order
         self.pp_info = []           # (predator name, prey name, predator length groups or 1), packed pair order
         self.nll_names = []
         self.n_steps = 0
@@ -646,6 +647,35 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         model.comp_shapes.append(dict(n_times=len(ld.times), n_areag=ld.n_areag, n_stockg=ld.n_stockg,
                                       n_age=ld.n_age, n_bins=ld.n_bins, times=list(ld.times)))
 
+    # ---- random-effect penalties (order 10, after the distributions by step id): g3l_random_dnorm / g3l_random_walk
+    # (R/likelihood_random.R:14-109). Everything they read is a formula of parameters: per step, the slots of param_f,
+    # mean_f (walk: param_f of the period's previous step) and sigma_f.
+    rand_recs = []
+    model.random_names = []
+    rands = sorted(by_kind.get("random", []), key=lambda a: ("g3l_random_walk" if a.walk else "g3l_random_dnorm", a.nll_name))
+    for a in rands:
+        run, ps, ms, ss = [0] * NT, [0] * NT, [0] * NT, [0] * NT
+        prev = -1
+        for t in range(NT):
+            c = Ctx(cur_year=tm.start_year + t // S, cur_step=t % S + 1, cur_step_size=tm.step_lengths[t % S] / 12.0)
+            ps[t], ss[t] = low.slot(a.param_f, c), low.slot(a.sigma_f, c)
+            on = {"step": True, "year": t % S == S - 1, "single": t == NT - 1}[a.period]
+            if a.walk:
+                ms[t] = prev if prev >= 0 else ps[t]
+                run[t] = 1 if (on and prev >= 0) else 0
+                if on:
+                    prev = ps[t]
+            else:
+                ms[t] = low.slot(a.mean_f, c)
+                run[t] = 1 if on else 0
+        q = [0] * K["G3RN_LEN"]
+        q[K["G3RN_RUN_OFF"]], q[K["G3RN_PARAM_OFF"]] = b.alloc_ints(run), b.alloc_ints(ps)
+        q[K["G3RN_MEAN_OFF"]], q[K["G3RN_SIGMA_OFF"]] = b.alloc_ints(ms), b.alloc_ints(ss)
+        q[K["G3RN_WEIGHT"]] = low.slot(a.weight, Ctx())
+        q[K["G3RN_LOG"]] = 1 if a.log_f else 0
+        rand_recs.append(q)
+        model.random_names.append(a.report_name)
+
     xrecs = []
     for xb in xbufs:
         x = [0] * K["G3X_LEN"]
@@ -683,7 +713,9 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
     H[K["G3H_NPAR"]] = len(tmpl)
     H[K["G3H_MAXL"]] = max(s.L for s in stocks.values())
     H[K["G3H_MAXN"]] = maxn
-    H[K["G3H_NNLL"]] = len(comp_recs) + 2
+    H[K["G3H_NRAND"]] = len(rand_recs)
+    H[K["G3H_RAND_OFF"]] = b.alloc_ints([x for r in rand_recs for x in r])
+    H[K["G3H_NNLL"]] = len(comp_recs) + len(rand_recs) + 2
 
     model.actions = acts
     model.parameter_template = tmpl
@@ -695,7 +727,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         model.stock_shapes.append((s.L, s.nage, len(s.areas)))
         model.stock_dims.append(list(s.dims))
     model.pp_info = pp_info
-    model.nll_names = list(model.comp_names) + ["understocking", "bounds"]
+    model.nll_names = list(model.comp_names) + list(model.random_names) + ["understocking", "bounds"]
     model.n_steps = NT
     model.time_labels = ["%d-%02d" % (tm.start_year + t // S, t % S + 1) for t in range(NT)]
     return model
@@ -771,6 +803,8 @@ def unpack_report(model: G3CudaModel, raw: np.ndarray) -> dict:
     br = raw[pos:pos + nn * NT].reshape(nn, NT); pos += nn * NT
     for i, n in enumerate(model.comp_names):
         out[f"nll_{n}__{model.comp_units[i]}"] = br[i].copy()
+    for i, n in enumerate(getattr(model, "random_names", [])):       # nll_random_dnorm_<name>__dnorm (R/likelihood_random.R:56-60)
+        out[f"{n}__dnorm"] = br[len(model.comp_names) + i].copy()
     out["nll_understocking__wgt"] = br[nn - 2].copy()
     out["nll_bounds"] = br[nn - 1].copy()
     for n, (L, A_, R), dims in zip(model.stock_names, model.stock_shapes, model.stock_dims):

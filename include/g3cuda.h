@@ -119,6 +119,10 @@ int g3cuda_set_kernel(g3cuda_model* m, int which);
  * do not depend on the warp count at all. */
 int g3cuda_set_tile_warps(g3cuda_model* m, int warps);
 
+/* Tuning hook: at most `tiles` tiles (CTAs) of the tile kernel in flight; 0 = every slot of the device. The per-tile slabs
+ * of the tiles in flight are the kernel's L2 working set. Results do not depend on it. */
+int g3cuda_set_tile_slots(g3cuda_model* m, int tiles);
+
 /* Tuning hook: re-plan the tile kernel with `warps` unit warps (0 = the planner's choice) and row segments of `seg_rows`
  * rows per unit (0 = the planner's choice, -1 = whole columns). The partition only regroups partial sums (per-unit
  * suitable biomass and understocking sums): results agree to rounding between partitions. */

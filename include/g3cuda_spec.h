@@ -26,7 +26,7 @@
 #ifndef G3CUDA_SPEC_H
 #define G3CUDA_SPEC_H
 
-#define G3CUDA_SPEC_VERSION 7
+#define G3CUDA_SPEC_VERSION 8
 
 /* ---- header: ints[0..G3H_LEN) ------------------------------------------ */
 #define G3H_VERSION        0
@@ -61,7 +61,9 @@
 #define G3H_NAREA         29   /* number of model areas */
 #define G3H_MAXL          30   /* max L over stocks */
 #define G3H_MAXN          31   /* max maxlengthgroupgrowth over stocks */
-#define G3H_NNLL          32   /* number of nll report rows = NCOMP + 2 (understocking, bounds) */
+#define G3H_NNLL          32   /* number of nll report rows = NCOMP + NRAND + 2: components, random terms, understocking, bounds */
+#define G3H_NRAND         33   /* g3l_random_dnorm / g3l_random_walk terms, run order (R/likelihood_random.R:14-109) */
+#define G3H_RAND_OFF      34   /* NRAND records of G3RN_LEN ints */
 #define G3H_LEN           40
 
 /* ---- stock record ------------------------------------------------------ */
@@ -216,6 +218,20 @@
 #define G3F_SI_LOG         2   /* R/likelihood_distribution.R:82 (fit = 'log') */
 #define G3F_SI_LINEAR      3
 #define G3F_SUMSQLOGRATIOS 4   /* sum((log(obs + eps) - log(model + eps))^2), R/likelihood_distribution.R:127-136; PARAM[0] = eps */
+
+/* ---- random-effect penalty record (g3l_random_dnorm, g3l_random_walk; R/likelihood_random.R:14-109) ----
+   On every step t with RUN[t] != 0:  n = sense * dnorm(slot PARAM[t], slot MEAN[t], slot SIGMA[t], log),
+   sense = -1 with LOG (the log density) else +1;  nll += slot WEIGHT * n;  report row NCOMP + r += n.
+   A random walk is the same record with MEAN[t] = the PARAM slot of the previous run step (its first run step only
+   remembers the value: RUN = 0 there). */
+#define G3RN_RUN_OFF       0   /* ints[NT]: 1 = the term is added on step t (period 'step': every step; 'year': the year's last
+                                  step; 'single': the model's last step) */
+#define G3RN_PARAM_OFF     1   /* ints[NT]: slot of param_f on step t */
+#define G3RN_MEAN_OFF      2   /* ints[NT]: slot of mean_f on step t (walk: of param_f on the previous run step) */
+#define G3RN_SIGMA_OFF     3   /* ints[NT]: slot of sigma_f on step t */
+#define G3RN_WEIGHT        4   /* slot of the weight formula (<nll_name>_weight) */
+#define G3RN_LOG           5   /* log_f */
+#define G3RN_LEN           6
 
 /* ---- slot programs: postfix code, one int per op, operands inline ------- */
 #define G3OP_CONST         1   /* next int: reals[] offset */

@@ -907,6 +907,19 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
             nllsteps[(size_t)c * NT + cur_time] += val(cnll);
             if (!si && !rep) std::fill(model[c].begin(), model[c].end(), T(0.0));
         }
+        // ---- g3l_random_dnorm / g3l_random_walk (R/likelihood_random.R:14-109): n = sense * dnorm(param, mean, sigma, log)
+        for (int r = 0; r < S.h(G3H_NRAND); r++) {
+            const int32_t* Rn = S.I + S.h(G3H_RAND_OFF) + r * G3RN_LEN;
+            if (!S.I[Rn[G3RN_RUN_OFF] + cur_time]) continue;
+            T x = slot(S.I[Rn[G3RN_PARAM_OFF] + cur_time]), mu = slot(S.I[Rn[G3RN_MEAN_OFF] + cur_time]);
+            T sd = slot(S.I[Rn[G3RN_SIGMA_OFF] + cur_time]);
+            T resid = (x - mu) / sd;
+            T logans = T(-std::log(std::sqrt(2 * M_PI))) - xlog(sd) - 0.5 * resid * resid;      // TMB dnorm
+            T n = Rn[G3RN_LOG] ? T(0.0) - logans : xexp(logans);
+            nll = nll + slot(Rn[G3RN_WEIGHT]) * n;
+            comp_tot[NCOMP + r] = comp_tot[NCOMP + r] + n;
+            nllsteps[(size_t)(NCOMP + r) * NT + cur_time] += val(n);
+        }
         // ---- g3l_understocking (R/likelihood_understocking.R:36-46)
         if (S.h(G3H_US_N) > 0) {
             T tot(0.0);

@@ -427,7 +427,7 @@ def test_lean_instantiations_are_bit_identical(setups, name):
     assert np.median(_rel(a[0], b[0])) < 1e-14
 
 
-@pytest.mark.parametrize("name", ["C2", "MINI_SPAWN", "SPAWN_RIG", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_TIMEVAR", "TIMEVAR_RIG"])
+@pytest.mark.parametrize("name", ["C2", "MINI_SPAWN", "SPAWN_RIG", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_TIMEVAR", "TIMEVAR_RIG", "C1_RANDOM"])
 def test_results_do_not_depend_on_scheduling(oracle_lib, name):
     """The work queues hand units to whichever warp is free and the spawning / hand-over phases run beside each other: every
     sum has a fixed order all the same, so repeated launches, and a vector alone or among 300 others, give identical bits
@@ -446,3 +446,45 @@ def test_results_do_not_depend_on_scheduling(oracle_lib, name):
     g1 = fn.handle.eval_batch(full[:40], tangent_idx=tidx)
     g2 = fn.handle.eval_batch(full[:40], tangent_idx=tidx)
     assert (g1[2] == g2[2]).all() or (np.isnan(g1[2]) == np.isnan(g2[2])).all() and np.array_equal(np.nan_to_num(g1[2]), np.nan_to_num(g2[2]))
+
+
+@KERNELS
+@pytest.mark.parametrize("name", ["RANDOM_RIG", "C1_RANDOM"])
+def test_random_effect_terms(oracle_lib, name, kernel):
+    """g3l_random_dnorm / g3l_random_walk (R/likelihood_random.R:14-109): the rig of the reference's own test
+    (tests/test-likelihood_random.R:6-34; the oracle's terms against the normal density by hand in
+    tests/test_oracle_random.py) and the vignette model with recruitment deviations: values, every nll row, gradients
+    and the reported per-step rows, CUDA vs oracle."""
+    model, p = CONFIGS[name]()
+    fn = g3_cuda_adfun(model, p, device=0)
+    orc = Oracle(*model.pack(p))
+    P = np.vstack([fn.par[None, :], parameter_batch(p, 63, seed=21)])
+    full = fn.full_par(P)
+    fn.handle.set_kernel(kernel)
+    g_nll, g_comp, _ = fn.handle.eval_batch(full, want_comp=True)
+    o_nll, o_comp, _ = orc.eval_batch(full, want_comp=True, nthreads=8)
+    ncomp, nrand = len(model.comp_names), len(model.random_names)
+    assert nrand >= 2 and g_comp.shape[1] == ncomp + nrand + 2
+    assert _rel(g_comp[:, ncomp:ncomp + nrand], o_comp[:, ncomp:ncomp + nrand]).max() < 1e-13
+    if ncomp:
+        assert _rel(g_comp[:, :ncomp], o_comp[:, :ncomp]).max() < NLL_RTOL
+    us_tol = _us_tolerance(model, p, o_comp[:, -2]) if model.pp_info else np.zeros(len(o_nll))
+    assert (np.abs(g_nll - o_nll) <= NLL_RTOL * np.abs(o_nll) + US_WEIGHT * us_tol).all()
+    if name == "RANDOM_RIG":        # by hand, as the reference's test does
+        import math
+        v = dict(zip(p.switch, full[5]))
+        ld = lambda x, mu, sd: -0.5 * math.log(2 * math.pi) - math.log(sd) - 0.5 * ((x - mu) / sd) ** 2
+        wy = [v[f"walk_year.{y}"] for y in range(1990, 1995)]
+        hand = (-ld(v["dnorm_log"], v["dnorm_log_mean"], v["dnorm_log_sigma"]) + math.exp(ld(v["dnorm_lin"], v["dnorm_lin_mean"], v["dnorm_lin_sigma"]))
+                + sum(-ld(wy[i + 1], wy[i], v["walk_year_sigma"]) for i in range(4)))
+        ws = [v[f"walk_step.{y}.{s}"] for y in range(1990, 1995) for s in range(1, 5)]
+        hand += sum(-ld(ws[i + 1], ws[i], v["walk_step_sigma"]) for i in range(19))
+        assert g_nll[5] == pytest.approx(hand, rel=1e-12)
+    g2, grad = fn.gr_batch(P[:4])
+    _, _, og = orc.eval_batch(full[:4], tangent_idx=fn.opt_idx.astype(np.int32))
+    scale = np.abs(og).max(axis=1, keepdims=True)
+    gtol = GRAD_RTOL + US_WEIGHT * us_tol[:4] / np.abs(o_nll[:4])
+    assert ((np.abs(grad - og) / scale).max(axis=1) < gtol).all()
+    rg, ro = fn.report(P[1]), unpack_report(model, orc.report(full[1]))
+    for n in model.random_names:
+        np.testing.assert_allclose(rg[n + "__dnorm"], ro[n + "__dnorm"], rtol=1e-13, atol=0.0, err_msg=n)

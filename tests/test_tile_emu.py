@@ -23,7 +23,7 @@ def _setup(name, B, seed=2026):
 
 
 @pytest.mark.parametrize("smem", [True, False], ids=["state_in_smem", "state_in_slab"])
-@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5", "LING", "MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG"])
+@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5", "LING", "MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "RANDOM_RIG", "C1_RANDOM"])
 def test_values_and_components(oracle_lib, name, smem):
     model, p, ints, reals, full, _ = _setup(name, 6)
     o_nll, o_comp, _ = Oracle(ints, reals).eval_batch(full, want_comp=True, nthreads=4)
@@ -31,6 +31,7 @@ def test_values_and_components(oracle_lib, name, smem):
     ncomp = len(model.comp_names)
     assert (np.abs(g_comp[:, :ncomp] - o_comp[:, :ncomp]) <= 1e-10 * np.abs(o_comp[:, :ncomp])).all()
     assert (np.abs(g_comp[:, -1] - o_comp[:, -1]) <= 1e-10 * np.abs(o_comp[:, -1])).all()
+    assert (np.abs(g_comp[:, ncomp:-2] - o_comp[:, ncomp:-2]) <= 1e-12 * np.abs(o_comp[:, ncomp:-2])).all()     # random-effect terms
     us_tol = us_tolerance(model, p, o_comp[:, -2])
     assert (np.abs(g_comp[:, -2] - o_comp[:, -2]) <= us_tol).all()
     assert (np.abs(g_nll - o_nll) <= 1e-10 * np.abs(o_nll) + US_WEIGHT * us_tol).all()
@@ -38,7 +39,7 @@ def test_values_and_components(oracle_lib, name, smem):
         assert (np.abs(g_nll - o_nll) / np.abs(o_nll)).max() < 1e-10
 
 
-@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C5", "LING", "MINI_SPAWN", "SPAWN_RIG", "MINI_TIMEVAR"])
+@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C5", "LING", "MINI_SPAWN", "SPAWN_RIG", "MINI_TIMEVAR", "RANDOM_RIG", "C1_RANDOM"])
 def test_gradients(oracle_lib, name):
     model, p, ints, reals, full, opt = _setup(name, 2, seed=77)
     tidx = opt[:6].astype(np.int32) if name != "C1" else opt[:10].astype(np.int32)       # 2-3 direction tiles
