@@ -918,6 +918,86 @@ def build_random_rig(seed=123):
     return model, p
 
 
+def build_six_fleets(seed=123):
+    """Three stocks and six fleets (the sizes real models reach -- gadget-models' ling and bling
+    run five to seven fleets): the imm / mat pair of multiple-substocks plus a second species, four commercial fleets on
+    the pair in different quarters, one on the second species, a survey on everything; a length and an age-length
+    distribution per fleet, maturity proportions, two survey indices: 15 likelihood components, 9 collect vectors, 5
+    predators on one stock. Ten years in quarters."""
+    rng = np.random.default_rng(seed)
+    years = list(range(1990, 2000))
+    area_names = g3_areas(["IXa", "IXb"])
+    ixa = {"IXa": area_names["IXa"]}
+    st_imm = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "imm"}, range(5, 101, 5)), 1, 5), ixa)
+    st_mat = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "mat"}, range(5, 101, 5)), 3, 10), ixa)
+    st_cod = g3s_livesonareas(g3s_age(g3_stock({"species": "cod", "maturity": "all"}, range(10, 131, 8)), 1, 8), ixa)
+    pair = [st_imm, st_mat]
+    actions = [
+        g3a_time(1990, 1999, [3, 3, 3, 3]),
+        g3a_growmature(st_imm, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4), maturity_f=g3a_mature_continuous(),
+                       output_stocks=[st_mat], transition_f=True),
+        g3a_naturalmortality(st_imm), g3a_initialconditions_normalcv(st_imm), g3a_renewal_normalcv(st_imm),
+        g3a_age(st_imm, output_stocks=[st_mat]),
+        g3a_growmature(st_mat, g3a_grow_impl_bbinom(maxlengthgroupgrowth=4)),
+        g3a_naturalmortality(st_mat), g3a_initialconditions_normalcv(st_mat), g3a_age(st_mat),
+        g3a_growmature(st_cod, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3)),
+        g3a_naturalmortality(st_cod), g3a_initialconditions_normalcv(st_cod), g3a_renewal_normalcv(st_cod), g3a_age(st_cod),
+        g3l_understocking(pair + [st_cod], nll_breakdown=True),
+    ]
+    fleets = [("f_comm1", pair, 1, 2e4), ("f_comm2", pair, 2, 3e4), ("f_comm3", pair, 3, 1e4), ("f_comm4", pair, 4, 2e4),
+              ("f_cod", [st_cod], 2, 1e4), ("f_surv", pair + [st_cod], 3, 500)]
+    for name, stocks, step, land in fleets:
+        d = _fleet_data(rng, years, land, land / 100, 300, range(0, 121, 10), 2000,
+                        lambda r, n: np.floor(np.minimum(r.normal(5, 1.5, n).clip(1), 10)), lambda a: 30 + a * 3,
+                        maturity=(name == "f_surv"))
+        for tab in d.values():
+            if "step" in tab:
+                tab["step"] = [step] * len(tab["step"])
+        fl = g3s_livesonareas(g3_fleet(name), ixa)
+        actions += [
+            g3a_predate_fleet(fl, stocks, suitabilities=g3_suitability_exponentiall50(by_stock="species"),
+                              catchability_f=g3a_predate_catchability_totalfleet(
+                                  g3_timeareadata("landings_" + name, d["landings"], "weight", areas=area_names))),
+            g3l_catchdistribution("ldist_" + name, d["ldist"], fleets=[fl], stocks=stocks,
+                                  function_f=g3l_distribution_sumofsquares(), area_group=area_names, nll_breakdown=True),
+            g3l_catchdistribution("aldist_" + name, d["aldist"], fleets=[fl], stocks=stocks,
+                                  function_f=g3l_distribution_sumofsquares(), area_group=area_names, nll_breakdown=True),
+        ]
+        if name == "f_surv":
+            matp = {k: [v for v, st_ in zip(vals, d["matp"]["stock"])] for k, vals in d["matp"].items()}
+            actions.append(g3l_catchdistribution("matp_f_surv", matp, fleets=[fl], stocks=pair,
+                                                 function_f=g3l_distribution_sumofsquares(), area_group=area_names, nll_breakdown=True))
+            actions.append(g3l_abundancedistribution("si_fish", d["si"], stocks=pair,
+                                                     function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
+                                                     area_group=area_names, nll_breakdown=True))
+            si2 = dict(d["si"]); si2["weight"] = list(rng.uniform(1e4, 1e5, len(years)))
+            actions.append(g3l_abundancedistribution("si_cod", si2, stocks=[st_cod],
+                                                     function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1),
+                                                     area_group=area_names, nll_breakdown=True))
+    actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "*.rec|init.scalar", 1000, optimise=False)
+    p = g3_init_val(p, "*.init.#", 10, lower=0.001, upper=10)
+    p = g3_init_val(p, "*.rec.#", 100, lower=1e-6, upper=1000)
+    p = g3_init_val(p, "*.rec.proj", 0.002)
+    p = g3_init_val(p, "*.M.#", 0.15, lower=0.001, upper=10)
+    p = g3_init_val(p, "init.F", 0.5, lower=0.1, upper=10)
+    p = g3_init_val(p, "fish*.Linf", 85, spread=0.2)
+    p = g3_init_val(p, "cod*.Linf", 120, spread=0.2)
+    p = g3_init_val(p, "*.K", 0.3, lower=0.04, upper=1.2)
+    p = g3_init_val(p, "fish*.t0", 0.2, optimise=False)
+    p = g3_init_val(p, "cod*.t0", 0.2, optimise=False)
+    p = g3_init_val(p, "*.walpha", 0.01, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.*.alpha", 0.07, lower=0.01, upper=1.8)
+    p = g3_init_val(p, "*.*.l50", 45, spread=0.5)
+    p = g3_init_val(p, "*.mat.alpha", 0.07, lower=0.0001, upper=1.8)
+    p = g3_init_val(p, "*.mat.l50", 50, spread=0.5)
+    p = g3_init_val(p, "*.bbin", 100, lower=1e-05, upper=1500)
+    return model, p
+
+
 def build_mini_fleets(seed=123):
     """One stock on two areas fished by a numberfleet, a linearfleet and an effortfleet
     (R/action_predate.R:7-18,117-126) -- parity-test model for the catchabilities bench configs do not use."""
@@ -1109,5 +1189,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "C1_RANDOM": lambda: build_c1(random=True),
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
            "LING": build_ling}

@@ -7,10 +7,10 @@
 namespace g3 {
 
 constexpr int MAXS = 16;     // stocks
-constexpr int MAXC = 16;     // likelihood components
-constexpr int MAXQ = 4;      // predator-prey pairs acting on one stock
+constexpr int MAXC = 32;     // likelihood components
+constexpr int MAXQ = 8;      // predator-prey pairs acting on one stock
 constexpr int MAXTS = 8;     // (predator, area) total-suitability accumulators
-constexpr int MAXX = 4;      // collect vectors
+constexpr int MAXX = 12;     // collect vectors
 constexpr int MAXRN = 4;     // renewal records per stock
 constexpr int MAXMIG = 4;    // areas a migrating stock may live on
 constexpr int TPB = 512;        // block-size cap of the default variant (one block per SM; the launch picks

@@ -313,12 +313,13 @@ def test_against_reference_generated_code(setups, name, kernel):
 
 
 @KERNELS
-@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG"])
+@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "SIX_FLEETS"])
 def test_andersen_predator_model(oracle_lib, name, kernel):
     """g3_suitability_andersen (predator-length dependent), one-step-only migration: CUDA vs oracle.
     MINI_SUITS: richards for the predator, gamma / andersenfleet / straightline fleets, reports included.
     MINI_FLEETS: numberfleet, linearfleet and effortfleet catchabilities.
-    MINI_OTHERFOOD: the predator also eats a g3a_otherfood stock (assigned every step, R/action_renewal.R:276-308)."""
+    MINI_OTHERFOOD: the predator also eats a g3a_otherfood stock (assigned every step, R/action_renewal.R:276-308).
+    SIX_FLEETS: three stocks, six fleets, 15 likelihood components, 9 collect vectors, five predators on one stock."""
     model, p = CONFIGS[name]()
     fn = g3_cuda_adfun(model, p, device=0)
     orc = Oracle(*model.pack(p))
