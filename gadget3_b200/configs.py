@@ -708,14 +708,15 @@ def build_spawn_rig(seed=123):
     return model, p
 
 
-def build_mini_spawn(seed=123, timevar=False):
+def build_mini_spawn(seed=123, timevar=False, matvar=False):
     """A closed life cycle on two areas: the immature stock grows, matures into the mature stock (continuous maturity,
     every step) and ages into it; the mature stock spawns on step 2 -- proportion spawning by length
     (g3_suitability_exponentiall50), Ricker recruitment, spawning mortality -- into the immature stock's youngest age
     (g3a_spawn, R/action_spawn.R:86-233). A fleet, two likelihood components, understocking.
     `timevar`: time-varying natural mortality -- the immature stock's M by age AND year
     (g3_parameterized(by_year = TRUE), R/params.R:122-129), the mature stock's M a g3_timevariable that steps up in
-    2002 step 3 and again in 2004 (R/timevariable.R:1-31)."""
+    2002 step 3 and again in 2004 (R/timevariable.R:1-31).
+    `matvar`: time-varying maturity parameters (g3a_mature_continuous's alpha by year, l50 a g3_timevariable)."""
     from . import g3a_spawn, g3a_spawn_recruitment_ricker, g3_timevariable, g3a_naturalmortality_exp
     areas = g3_areas(["a", "b"])
     imm = g3s_livesonareas(g3s_age(g3_stock({"species": "fish", "maturity": "imm"}, range(10, 60, 5)), 1, 3), areas)
@@ -735,7 +736,14 @@ def build_mini_spawn(seed=123, timevar=False):
             ("2002-03", g3_parameterized("M.mid", by_stock=True, value=0.3)),
             ("2004", g3_parameterized("M.late", by_stock=True, value=0.15))]))))
          if timevar else g3a_naturalmortality(mat)),
-        g3a_growmature(imm, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3), maturity_f=g3a_mature_continuous(),
+        g3a_growmature(imm, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3),
+                       # `matvar`: the maturation ogive moves -- l50 a g3_timevariable that switches in 2002 step 2, alpha by year
+                       maturity_f=(g3a_mature_continuous(
+                           alpha=g3_parameterized("mat.alpha", by_stock=True, by_year=True),
+                           l50=g3_timevariable("matl50", OrderedDict([
+                               ("init", g3_parameterized("mat.l50.early", by_stock=True, value=30)),
+                               ("2002-02", g3_parameterized("mat.l50.late", by_stock=True, value=30))])))
+                                   if matvar else g3a_mature_continuous()),
                        output_stocks=[mat], transition_f=True),
         g3a_growmature(mat, g3a_grow_impl_bbinom(maxlengthgroupgrowth=3)),
         g3a_age(imm, output_stocks=[mat]), g3a_age(mat),
@@ -782,8 +790,13 @@ def build_mini_spawn(seed=123, timevar=False):
     p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
     p = g3_init_val(p, "*.wbeta", 3, optimise=False)
     p = g3_init_val(p, "*.bbin", 10, lower=1, upper=100)
-    p = g3_init_val(p, "*.mat.alpha", 0.1, lower=0.01, upper=1)
-    p = g3_init_val(p, "*.mat.l50", 30, lower=20, upper=40)
+    if matvar:
+        p = g3_init_val(p, "*.mat.alpha.#", 0.1, lower=0.01, upper=1)
+        p = g3_init_val(p, "*.mat.l50.early", 28, lower=20, upper=40)
+        p = g3_init_val(p, "*.mat.l50.late", 34, lower=20, upper=40)
+    else:
+        p = g3_init_val(p, "*.mat.alpha", 0.1, lower=0.01, upper=1)
+        p = g3_init_val(p, "*.mat.l50", 30, lower=20, upper=40)
     p = g3_init_val(p, "*.spawn.alpha", 0.2, lower=0.05, upper=1)
     p = g3_init_val(p, "*.spawn.l50", 35, lower=25, upper=45)
     p = g3_init_val(p, "*.spawn.mort", 0.1, lower=0.01, upper=0.5)
@@ -998,6 +1011,54 @@ def build_six_fleets(seed=123):
     return model, p
 
 
+def build_renewal_rig(seed=123):
+    """A stock whose recruits change shape over the years: mean length a by-year table
+    (g3_parameterized(by_year = TRUE), R/params.R:122-129), standard deviation a g3_timevariable that switches in 2002
+    (R/timevariable.R:1-31), numbers by year as usual. The reported renewal (detail_st__renewalnum) of each year must be
+    the normal density of that year's parameters on the length grid, normalised, times 1e4 * rec (R/action_renewal.R:56-80)
+    -- tests/test_oracle_kat.py."""
+    from . import g3_timevariable, g3a_renewal_normalparam
+    gp = g3_parameterized
+    areas = g3_areas(["a"])
+    st = g3s_livesonareas(g3s_age(g3_stock("st", range(10, 55, 5)), 1, 3), areas)
+    sd = g3_timevariable("recsd", OrderedDict([("init", gp("recsd.early", value=4.0)), ("2002", gp("recsd.late", value=8.0))]))
+    actions = [
+        g3a_time(2000, 2003, [6, 6]),
+        g3a_initialconditions_normalcv(st),
+        g3a_naturalmortality(st),
+        g3a_renewal_normalparam(st, factor_f=gp("rec", by_stock=True, by_year=True), mean_f=gp("recl", by_stock=True, by_year=True),
+                                stddev_f=sd, run_step=1),
+        g3a_age(st),
+    ]
+    rng = np.random.default_rng(seed)
+    yrs = [2000, 2001, 2002, 2003]
+    si = dict(year=yrs, step=[2] * 4, number=list(rng.uniform(1e3, 1e4, 4)))
+    actions.append(g3l_abundancedistribution("si", si, stocks=[st], function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    ld = dict(year=[y for y in yrs for _ in range(4)], step=[2] * 16, length=["[10,20)", "[20,30)", "[30,40)", "[40,Inf)"] * 4,
+              number=list(rng.uniform(10, 100, 16)))
+    actions.append(g3l_abundancedistribution("ldist", ld, stocks=[st], function_f=g3l_distribution_sumofsquares()))
+    actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    for i, y in enumerate(yrs):
+        p = g3_init_val(p, f"st.rec.{y}", 1.0 + 0.5 * i, lower=0.1, upper=5)
+        p = g3_init_val(p, f"st.recl.{y}", 18.0 + 3.0 * i, lower=12, upper=35)
+    p = g3_init_val(p, "recsd.early", 4.0, lower=2, upper=10)
+    p = g3_init_val(p, "recsd.late", 8.0, lower=2, upper=12)
+    p = g3_init_val(p, "*.Linf", 50, optimise=False)
+    p = g3_init_val(p, "*.K", 0.3, optimise=False)
+    p = g3_init_val(p, "*.t0", -1.0, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.3, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, lower=0.05, upper=0.5)
+    p = g3_init_val(p, "init.F", 0.3, optimise=False)
+    p = g3_init_val(p, "recage", 1, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    return model, p
+
+
 def build_mini_fleets(seed=123):
     """One stock on two areas fished by a numberfleet, a linearfleet and an effortfleet
     (R/action_predate.R:7-18,117-126) -- parity-test model for the catchabilities bench configs do not use."""
@@ -1189,5 +1250,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "MINI_MATVAR": lambda: build_mini_spawn(matvar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "RENEWAL_RIG": build_renewal_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
            "LING": build_ling}

@@ -11,7 +11,7 @@ constexpr int MAXC = 32;     // likelihood components
 constexpr int MAXQ = 8;      // predator-prey pairs acting on one stock
 constexpr int MAXTS = 8;     // (predator, area) total-suitability accumulators
 constexpr int MAXX = 12;     // collect vectors
-constexpr int MAXRN = 4;     // renewal records per stock
+constexpr int MAXRN = 30;    // renewal records per stock (a bit each in the per-step mask)
 constexpr int MAXMIG = 4;    // areas a migrating stock may live on
 constexpr int TPB = 512;        // block-size cap of the default variant (one block per SM; the launch picks
                                 // blockDim <= the cap so that the batch splits into equally full waves)

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 const double dt = A.w_dt_len[idt] / 12.0;
                 const T linf = SLOT(gs[0]), kk = 1.0 - xexp(-(SLOT(gs[1])) * dt), beta = avoid_zero(SLOT(gs[2]));
                 T malpha(0.0), ml50(0.0);
-                if (cont) { const int32_t* ms = I + St[G3S_MAT_OFF]; malpha = SLOT(ms[0]); ml50 = SLOT(ms[1]); }
+                if (cont) { const int32_t* ms = I + St[G3S_MAT_OFF] + 4 * gset; malpha = SLOT(ms[0]); ml50 = SLOT(ms[1]); }
                 // source-oriented band in scratch: [v][x * L + l], v = 0 all, 1 maturing, 2 staying
                 for (int l = 0; l < L; l++) {
                     // g3a_grow_lengthvbsimple (R/action_grow.R:54) inside the bbinom wrapper (R/action_grow.R:220)

@@ -495,7 +495,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                         for (int j = 0; j < n2; j++) g = g * ((beta + (double)j) / xabs(alpha + beta + (double)j));
                         T m0(0.0), malpha(0.0), mbeta(0.0);
                         if (cont) {         // g3a_mature_constant as M0 (R/action_mature.R:44-74)
-                            const int32_t* ms = I + St.mat_ioff;
+                            const int32_t* ms = I + St.mat_ioff + 4 * gset;      // (the maturity parameters vary with the growth sets)
                             T inner(0.0);
                             if (ms[0] >= 0) { malpha = SLOT(ms[0]); inner = inner - malpha * (midlen[l] - SLOT(ms[1])); }
                             if (ms[2] >= 0) { mbeta = SLOT(ms[2]); inner = inner - mbeta * ((double)(St.minage + set % St.nage) - SLOT(ms[3])); }

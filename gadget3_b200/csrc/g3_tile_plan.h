@@ -488,8 +488,14 @@ inline TilePlan make_tile_plan(const int32_t* I, const double* R, int want_W = 0
         const StockRec& r = P.st[s];
         for (int k = 0; k < r.n_renew; k++) for (int k2 = k + 1; k2 < r.n_renew; k2++) {
             const int32_t* Ra = I + r.renew_ioff + k * G3R_LEN; const int32_t* Rb = I + r.renew_ioff + k2 * G3R_LEN;
-            if (Ra[G3R_AGE_IDX] == Rb[G3R_AGE_IDX] && (Ra[G3R_RUN_STEP] == 0 || Rb[G3R_RUN_STEP] == 0 || Ra[G3R_RUN_STEP] == Rb[G3R_RUN_STEP]))
-                return fail("two renewals into the same age at the same step");
+            if (Ra[G3R_AGE_IDX] == Rb[G3R_AGE_IDX] && (Ra[G3R_RUN_STEP] == 0 || Rb[G3R_RUN_STEP] == 0 || Ra[G3R_RUN_STEP] == Rb[G3R_RUN_STEP])) {
+                // ... unless they never run in the same year (one renewal whose shape parameters vary by year, split into a
+                // record per set of years: gadget3_b200/run_cuda.py)
+                bool together = false;
+                const int nya = (I[G3H_END_YEAR] - I[G3H_START_YEAR] + 1) * r.narea;
+                for (int i = 0; i < nya; i++) together = together || (I[Ra[G3R_FACTOR_OFF] + i] >= 0 && I[Rb[G3R_FACTOR_OFF] + i] >= 0);
+                if (together) return fail("two renewals into the same age at the same step");
+            }
         }
     }
     // ---- ageing movement (R/action_age.R:16-20,57-63): stash of the oldest column per (area, l), destinations

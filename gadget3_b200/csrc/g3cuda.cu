@@ -540,8 +540,13 @@ std::string plan_thread(g3cuda_model* m, std::vector<int32_t>& rem_off, std::vec
         const int32_t* St = stock(s);
         for (int k = 0; k < St[G3S_N_RENEW]; k++) for (int k2 = k + 1; k2 < St[G3S_N_RENEW]; k2++) {
             const int32_t* Ra = I + St[G3S_RENEW_OFF] + k * G3R_LEN; const int32_t* Rb = I + St[G3S_RENEW_OFF] + k2 * G3R_LEN;
-            if (Ra[G3R_AGE_IDX] == Rb[G3R_AGE_IDX] && (Ra[G3R_RUN_STEP] == 0 || Rb[G3R_RUN_STEP] == 0 || Ra[G3R_RUN_STEP] == Rb[G3R_RUN_STEP]))
-                return "two renewals into the same age at the same step";
+            if (Ra[G3R_AGE_IDX] == Rb[G3R_AGE_IDX] && (Ra[G3R_RUN_STEP] == 0 || Rb[G3R_RUN_STEP] == 0 || Ra[G3R_RUN_STEP] == Rb[G3R_RUN_STEP])) {
+                // ... unless they never run in the same year (a renewal whose shape varies by year, one record per set of years)
+                bool together = false;
+                const int nya = (I[G3H_END_YEAR] - I[G3H_START_YEAR] + 1) * St[G3S_NAREA];
+                for (int i = 0; i < nya; i++) together = together || (I[Ra[G3R_FACTOR_OFF] + i] >= 0 && I[Rb[G3R_FACTOR_OFF] + i] >= 0);
+                if (together) return "two renewals into the same age at the same step";
+            }
         }
     }
     for (int c = 0; c < A.NCOMP; c++) {

@@ -391,16 +391,23 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         c = Ctx(stock=s)
         r[K["G3S_GROW_N"]] = im.maxlengthgroupgrowth
         maxn = max(maxn, im.maxlengthgroupgrowth)
-        gtab, gtmap = time_sets(lambda tc: [low.slot(f, c.replace(**tc)) for f in (
-            im.delta_len_f.linf_f, im.delta_len_f.kappa_f, im.beta_f, im.delta_wgt_f.alpha_f, im.delta_wgt_f.beta_f)])
-        r[K["G3S_GROW_OFF"]] = b.alloc_ints(gtab)
+        m = a.maturity_f
+        mat_fs = () if m is None else (m.alpha, m.l50, m.beta, m.a50)
+        # the growth parameters and, with them, the maturity parameters of every step, deduplicated into sets: the maturing
+        # share is part of the growth bands (R/action_grow.R:420-437), so the two vary together
+        gmtab, gtmap = time_sets(lambda tc: [low.slot(f, c.replace(**tc)) for f in (
+            im.delta_len_f.linf_f, im.delta_len_f.kappa_f, im.beta_f, im.delta_wgt_f.alpha_f, im.delta_wgt_f.beta_f)]
+            + [(-1 if x is None else low.slot(x, c.replace(**tc))) for x in mat_fs])
+        w = 5 + len(mat_fs)
+        r[K["G3S_GROW_OFF"]] = b.alloc_ints([x for i in range(0, len(gmtab), w) for x in gmtab[i:i + 5]])
         if gtmap is not None:
             r[K["G3S_GROW_TMAP_OFF"]] = b.alloc_ints(gtmap)
-        m = a.maturity_f
         if m is not None:
             r[K["G3S_MAT_KIND"]] = K["G3MAT_CONTINUOUS"] if m.kind == "continuous" else K["G3MAT_CONSTANT"]
-            r[K["G3S_MAT_OFF"]] = b.alloc_ints(
-                [(-1 if x is None else low.slot(x, c)) for x in (m.alpha, m.l50, m.beta, m.a50)])
+            mtab = [x for i in range(0, len(gmtab), w) for x in gmtab[i + 5:i + 9]]
+            if m.kind != "continuous" and any(mtab[i:i + 4] != mtab[:4] for i in range(0, len(mtab), 4)):
+                raise G3Unsupported("g3a_mature_constant with time-varying parameters")
+            r[K["G3S_MAT_OFF"]] = b.alloc_ints(mtab)
             if m.kind == "continuous" and (m.alpha is None or m.l50 is None):
                 raise G3Unsupported("g3a_mature_continuous needs alpha and l50")
             if (m.alpha is None) != (m.l50 is None) or (m.beta is None) != (m.a50 is None):
@@ -472,21 +479,33 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                 raise G3Unsupported("g3a_renewal: run_age = NULL")
             if not (s.minage <= a.run_age <= s.maxage):
                 continue
-            q = [0] * K["G3R_LEN"]
-            q[K["G3R_RUN_STEP"]] = 0 if a.run_step is None else int(a.run_step)
-            q[K["G3R_AGE_IDX"]] = a.run_age - s.minage
             an0, aid0 = next(iter(s.areas.items()))
             c = Ctx(stock=s, age=a.run_age, area=aid0, area_name=an0)
-            q[K["G3R_MEAN"]], q[K["G3R_SD"]] = low.slot(a.mean_f, c), low.slot(a.stddev_f, c)
-            q[K["G3R_WALPHA"]], q[K["G3R_WBETA"]] = low.slot(a.alpha_f, c), low.slot(a.beta_f, c)
-            ftab = []
+            # Shape parameters that vary by year (mean length, sd, walpha, wbeta as by_year tables or g3_timevariable): one
+            # record per set of years that share their values, each with the factor slots of its own years only -- in any
+            # year one record of the family runs, the others skip (FACTOR_OFF = -1), so the kernels need nothing new.
+            run_steps = [int(a.run_step)] if a.run_step is not None else list(range(1, S + 1))
+            families = OrderedDict()
             for y in range(tm.start_year, tm.end_year + 1):
-                for an, aid in s.areas.items():
-                    cy = Ctx(stock=s, age=a.run_age, area=aid, area_name=an, cur_year=y,
-                             cur_step=(a.run_step or 1))
-                    ftab.append(low.slot(a.factor_f, cy))
-            q[K["G3R_FACTOR_OFF"]] = b.alloc_ints(ftab)
-            recs.append(q)
+                keys = {tuple(low.slot(f, c.replace(cur_year=y, cur_step=st, cur_step_size=tm.step_lengths[st - 1] / 12.0))
+                              for f in (a.mean_f, a.stddev_f, a.alpha_f, a.beta_f)) for st in run_steps}
+                if len(keys) > 1:
+                    raise G3Unsupported(f"g3a_renewal of {name}: shape parameters that change between the steps of a year")
+                families.setdefault(keys.pop(), set()).add(y)
+            for shape, fam_years in families.items():
+                q = [0] * K["G3R_LEN"]
+                q[K["G3R_RUN_STEP"]] = 0 if a.run_step is None else int(a.run_step)
+                q[K["G3R_AGE_IDX"]] = a.run_age - s.minage
+                q[K["G3R_MEAN"]], q[K["G3R_SD"]], q[K["G3R_WALPHA"]], q[K["G3R_WBETA"]] = shape
+                ftab = []
+                for y in range(tm.start_year, tm.end_year + 1):
+                    for an, aid in s.areas.items():
+                        cy = Ctx(stock=s, age=a.run_age, area=aid, area_name=an, cur_year=y,
+                                 cur_step=(a.run_step or 1))
+                        fslot = low.slot(a.factor_f, cy)         # (lowered for every year: the parameter order does not depend on the split)
+                        ftab.append(fslot if y in fam_years else -1)
+                q[K["G3R_FACTOR_OFF"]] = b.alloc_ints(ftab)
+                recs.append(q)
         srec[name][K["G3S_N_RENEW"]] = len(recs)
         srec[name][K["G3S_RENEW_OFF"]] = b.alloc_ints([x for q in recs for x in q])
 

@@ -80,7 +80,8 @@
 #define G3S_GROW_N        10   /* maxlengthgroupgrowth; -1 = no growth */
 #define G3S_GROW_OFF      11   /* ints[5]: slots linf, kappa, beta, walpha, wbeta */
 #define G3S_MAT_KIND      12   /* G3MAT_* */
-#define G3S_MAT_OFF       13   /* ints[4]: slots alpha, l50, beta, a50 (-1 = term absent) */
+#define G3S_MAT_OFF       13   /* ints[NSET*4]: slots alpha, l50, beta, a50 (-1 = term absent), one row per set of GROW_TMAP_OFF
+                                  (g3a_mature_constant: one set only) */
 #define G3S_TRANS_MASK    14   /* bit (cur_step-1) set: transition_f true on that step */
 #define G3S_N_OUT         15   /* maturation output stocks */
 #define G3S_OUT_OFF       16   /* ints[2*N_OUT]: (stock index, ratio slot) */
@@ -102,7 +103,7 @@
                                   R/timevariable.R:1-31): ints[NT]: which set of MORT_OFF's ints[NSET*NAGE*NAREA] slots step t uses;
                                   -1 = one set for every step */
 #define G3S_GROW_TMAP_OFF 29   /* time-varying growth parameters (Linf, K, bbin, walpha, wbeta by year / step, g3_timevariable): ints[NT]:
-                                  which set of GROW_OFF's ints[NSET*5] slots step t uses; -1 = one set for every step. The reference
+                                  which set of GROW_OFF's ints[NSET*5] (and MAT_OFF's ints[NSET*4]) slots step t uses; -1 = one set for every step. The reference
                                   recomputes its growth matrices whenever their inputs change (R/action_grow.R:391-410) */
 #define G3S_LEN           30
 

@@ -602,7 +602,7 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                     growth_w[s][l + L * x] = (pw[(l + x < L) ? l + x : L - 1] - pw[l]) * wa;
             }
             std::vector<T> Wm; grow_matrix_wgt(growth_w[s], L, D, Wm);
-            const int32_t* ms = St[G3S_MAT_KIND] != G3MAT_NONE ? S.I + St[G3S_MAT_OFF] : nullptr;
+            const int32_t* ms = St[G3S_MAT_KIND] != G3MAT_NONE ? S.I + St[G3S_MAT_OFF] + (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS ? 4 * gset : 0) : nullptr;
             std::vector<T> on, ow;
             for (int col = 0; col < St[G3S_NAREA] * St[G3S_NAGE]; col++) {
                 int age = St[G3S_MINAGE] + col % St[G3S_NAGE];

@@ -313,12 +313,15 @@ def test_against_reference_generated_code(setups, name, kernel):
 
 
 @KERNELS
-@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "SIX_FLEETS"])
+@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "SIX_FLEETS", "MINI_MATVAR", "RENEWAL_RIG"])
 def test_andersen_predator_model(oracle_lib, name, kernel):
     """g3_suitability_andersen (predator-length dependent), one-step-only migration: CUDA vs oracle.
     MINI_SUITS: richards for the predator, gamma / andersenfleet / straightline fleets, reports included.
     MINI_FLEETS: numberfleet, linearfleet and effortfleet catchabilities.
     MINI_OTHERFOOD: the predator also eats a g3a_otherfood stock (assigned every step, R/action_renewal.R:276-308).
+    MINI_MATVAR: time-varying maturity parameters (alpha by year, l50 a g3_timevariable; tests/test_oracle_matvar.py).
+    RENEWAL_RIG: renewal mean length by year, standard deviation a g3_timevariable (one record per shape; the oracle's
+    renewal against the normal density by hand in tests/test_oracle_kat.py).
     SIX_FLEETS: three stocks, six fleets, 15 likelihood components, 9 collect vectors, five predators on one stock."""
     model, p = CONFIGS[name]()
     fn = g3_cuda_adfun(model, p, device=0)
@@ -428,7 +431,7 @@ def test_lean_instantiations_are_bit_identical(setups, name):
     assert np.median(_rel(a[0], b[0])) < 1e-14
 
 
-@pytest.mark.parametrize("name", ["C2", "MINI_SPAWN", "SPAWN_RIG", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_TIMEVAR", "TIMEVAR_RIG", "C1_RANDOM"])
+@pytest.mark.parametrize("name", ["C2", "MINI_SPAWN", "SPAWN_RIG", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_TIMEVAR", "TIMEVAR_RIG", "C1_RANDOM", "MINI_MATVAR"])
 def test_results_do_not_depend_on_scheduling(oracle_lib, name):
     """The work queues hand units to whichever warp is free and the spawning / hand-over phases run beside each other: every
     sum has a fixed order all the same, so repeated launches, and a vector alone or among 300 others, give identical bits

