@@ -561,6 +561,7 @@ class SpawnAction(Action):
         self.stock, self.recruitment_f, self.proportion_f, self.mortality_f = stock, recruitment_f, proportion_f, mortality_f
         self.output_stocks, self.output_ratios = list(output_stocks), list(output_ratios)
         self.mean_f, self.stddev_f, self.alpha_f, self.beta_f, self.run_step = mean_f, stddev_f, alpha_f, beta_f, run_step
+        self.weightloss = None      # (rel_loss, min_weight) formulas
 
 
 def g3a_spawn(stock, recruitment_f, proportion_f=1, mortality_f=0, weightloss_f=0, weightloss_args=None, output_stocks=(),
@@ -568,11 +569,18 @@ def g3a_spawn(stock, recruitment_f, proportion_f=1, mortality_f=0, weightloss_f=
               run_step=None):
     """R/action_spawn.R:86-233. ``proportion_f`` / ``mortality_f``: a formula, or a g3_suitability_*() of the parent's
     length (as the reference's documentation uses them). mean_f .. beta_f are evaluated for each OUTPUT stock
-    (R/action_spawn.R:187-189). Spawning weight loss is not supported."""
+    (R/action_spawn.R:187-189). Spawning weight loss: the relative form (weightloss_f, or weightloss_args with rel_loss and
+    min_weight); abs_loss is not supported."""
     if not isinstance(recruitment_f, _Recruitment):
         raise G3Unsupported("g3a_spawn: recruitment_f must come from g3a_spawn_recruitment_*()")
-    if not (isinstance(weightloss_f, (int, float)) and weightloss_f == 0) or weightloss_args:
-        raise G3Unsupported("g3a_spawn(weightloss_f / weightloss_args = ...)")
+    # weightloss_f is rewritten as weightloss_args = list(rel_loss = weightloss_f, min_weight = 0) (R/action_spawn.R:166-171)
+    wl_args = dict(weightloss_args or {})
+    if not (isinstance(weightloss_f, (int, float)) and weightloss_f == 0):
+        wl_args = dict(rel_loss=weightloss_f, min_weight=0)
+    if wl_args.get("abs_loss") is not None:
+        raise G3Unsupported("g3a_spawn(weightloss_args = list(abs_loss = ...))")
+    if wl_args and wl_args.get("rel_loss") is None:
+        raise G3Unsupported("g3a_spawn(weightloss_args) without rel_loss")
     output_stocks = list(output_stocks)
     if output_ratios is None:
         output_ratios = [1.0 / len(output_stocks)] * len(output_stocks) if output_stocks else []
@@ -585,8 +593,11 @@ def g3a_spawn(stock, recruitment_f, proportion_f=1, mortality_f=0, weightloss_f=
     stddev_f = g3_parameterized("rec.sd", value=10, by_stock=by_stock) if stddev_f is None else wrap(stddev_f)
     alpha_f = g3_parameterized("walpha", by_stock=wgt_by_stock) if alpha_f is None else wrap(alpha_f)
     beta_f = g3_parameterized("wbeta", by_stock=wgt_by_stock) if beta_f is None else wrap(beta_f)
-    return SpawnAction(stock, recruitment_f, proportion_f, mortality_f, output_stocks, output_ratios, mean_f, stddev_f,
-                       alpha_f, beta_f, run_step)
+    act = SpawnAction(stock, recruitment_f, proportion_f, mortality_f, output_stocks, output_ratios, mean_f, stddev_f,
+                      alpha_f, beta_f, run_step)
+    if wl_args:     # g3a_weightloss applied to the spawning part of every cell (R/action_weightloss.R:19-44; min_weight defaults to 1e-7)
+        act.weightloss = (wrap(wl_args["rel_loss"]), wrap(wl_args.get("min_weight", 1e-7)))
+    return act
 
 
 # ------------------------------------------------------------------ migration

@@ -1059,6 +1059,58 @@ def build_renewal_rig(seed=123):
     return model, p
 
 
+def build_wloss_rig(seed=123):
+    """Spawning weight loss (R/action_spawn.R:166-181 -> g3a_weightloss, R/action_weightloss.R:19-44) where nothing else
+    touches the parents: two mature stocks that neither grow nor die spawn in step 2 with a length-dependent proportion
+    and a spawning mortality -- `mat_rel` loses a relative share of its weight (weightloss_f), `mat_min` the same down to
+    a floor (weightloss_args = list(rel_loss, min_weight)). Between the start of step 2 and the start of step 3 the
+    parents' number and mean weight change by the spawning formulas alone (tests/test_oracle_spawn.py)."""
+    from . import g3a_spawn, g3a_spawn_recruitment_simplessb
+    gp = g3_parameterized
+    areas = g3_areas(["a"])
+    actions = [g3a_time(2000, 2001, [3, 3, 3, 3])]
+    imms = []
+    for k in ("rel", "min"):
+        mat = g3s_livesonareas(g3s_age(g3_stock("mat_" + k, range(10, 60, 10)), 3, 4), areas)
+        imm = g3s_livesonareas(g3s_age(g3_stock("imm_" + k, range(10, 60, 10)), 0, 0), areas)
+        imms.append(imm)
+        wl = (dict(weightloss_f=gp("spawn.wloss", by_stock=True, value=0.15)) if k == "rel" else
+              dict(weightloss_args=dict(rel_loss=gp("spawn.wloss", by_stock=True, value=0.3), min_weight=gp("spawn.minwgt", by_stock=True, value=0.02))))
+        actions += [g3a_initialconditions_normalcv(mat),
+                    g3a_spawn(mat, g3a_spawn_recruitment_simplessb(gp("spawn.mu", by_stock=True, value=0.5)),
+                              proportion_f=g3_suitability_exponentiall50(), mortality_f=gp("spawn.mort", by_stock=True, value=0.2),
+                              output_stocks=[imm], run_step=2, **wl)]
+    rng = np.random.default_rng(seed)
+    si = dict(year=[2000, 2001], step=[4] * 2, number=list(rng.uniform(1e3, 1e4, 2)))
+    actions.append(g3l_abundancedistribution("si_imm", si, stocks=imms, function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
+    ld = dict(year=[y for y in (2000, 2001) for _ in range(5)], step=[3] * 10, length=["[10,20)", "[20,30)", "[30,40)", "[40,50)", "[50,Inf)"] * 2,
+              weight=list(rng.uniform(1, 10, 10)))
+    actions.append(g3l_abundancedistribution("wdist_mat", ld, stocks=[actions[1].stock, actions[3].stock], function_f=g3l_distribution_sumofsquares()))
+    actions += [g3l_bounds_penalty(actions)]
+    model = g3_to_cuda(actions)
+    p = model.parameter_template
+    p = g3_init_val(p, "*.Linf", 70, optimise=False)
+    p = g3_init_val(p, "*.K", 0.3, optimise=False)
+    p = g3_init_val(p, "*.t0", -1.0, optimise=False)
+    p = g3_init_val(p, "*.lencv", 0.3, optimise=False)
+    p = g3_init_val(p, "*.init.scalar", 10, optimise=False)
+    p = g3_init_val(p, "*.init.#", 1, lower=0.1, upper=5)
+    p = g3_init_val(p, "*.M.#", 0.2, optimise=False)
+    p = g3_init_val(p, "init.F", 0.3, optimise=False)
+    p = g3_init_val(p, "recage", 0, optimise=False)
+    p = g3_init_val(p, "*.walpha", 1e-5, optimise=False)
+    p = g3_init_val(p, "*.wbeta", 3, optimise=False)
+    p = g3_init_val(p, "*.rec.sd", 5, optimise=False)
+    p = g3_init_val(p, "*.spawn.alpha", 0.15, lower=0.05, upper=1)
+    p = g3_init_val(p, "*.spawn.l50", 35, lower=25, upper=45)
+    p = g3_init_val(p, "*.spawn.mort", 0.2, lower=0.01, upper=0.5)
+    p = g3_init_val(p, "*.spawn.mu", 0.5, lower=0.05, upper=2)
+    p = g3_init_val(p, "mat_rel.spawn.wloss", 0.15, lower=0.01, upper=0.5)
+    p = g3_init_val(p, "mat_min.spawn.wloss", 0.3, lower=0.01, upper=0.5)
+    p = g3_init_val(p, "mat_min.spawn.minwgt", 0.02, lower=0.001, upper=0.1)
+    return model, p
+
+
 def build_mini_fleets(seed=123):
     """One stock on two areas fished by a numberfleet, a linearfleet and an effortfleet
     (R/action_predate.R:7-18,117-126) -- parity-test model for the catchabilities bench configs do not use."""
@@ -1250,5 +1302,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "MINI_MATVAR": lambda: build_mini_spawn(matvar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "RENEWAL_RIG": build_renewal_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "MINI_MATVAR": lambda: build_mini_spawn(matvar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "WLOSS_RIG": build_wloss_rig, "RENEWAL_RIG": build_renewal_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
            "LING": build_ling}

@@ -575,13 +575,19 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                         sp_p[k] = sp_kind == G3SPAWN_FECUNDITY ? SLOT(Sp[G3SP_RECR_SLOTS + k]) : T(0.0);
                     }
                 }
-                auto spawn_cell = [&](const int l, const int aidx, T& num, const T& wgt) {
+                auto spawn_cell = [&](const int l, const int aidx, T& num, T& wgt) {
                     const double ml = R[St[G3S_MIDLEN_ROFF] + l];
                     const T spn = num * suitability_of<T>(sp_pk, sp_prop, ml, ml);
                     if (sp_kind == G3SPAWN_FECUNDITY)
                         sp_acc = sp_acc + xpow(T(ml), sp_p[1]) * xpow(T((double)(St[G3S_MINAGE] + aidx)), sp_p[2]) * xpow(spn, sp_p[3]) * xpow(wgt, sp_p[4]);
                     else sp_acc = sp_acc + wgt * spn;
                     if (sp_mk >= 0) num = num - spn * (1.0 - xexp(-suitability_of<T>(sp_mk, sp_mort, ml, ml)));
+                    const int32_t* Spw = I + St[G3S_SPAWN_OFF];
+                    if (Spw[G3SP_WLOSS] >= 0) {     // spawning weight loss (R/action_spawn.R:166-181, R/action_weightloss.R:19-44)
+                        const T mw = SLOT(Spw[G3SP_WLOSS + 1]);
+                        const T lost = ((wgt - mw) * (1.0 - SLOT(Spw[G3SP_WLOSS]))) + mw;
+                        wgt = ratio_add_pop(wgt, num - spn, lost, spn);
+                    }
                 };
                 if (!has_mort && grow_n < 0 && !inc_now && !ren_mask && xact == 0 && !spawn_here) continue;
 

@@ -957,7 +957,7 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
 
             // g3a_spawn, order 6 (R/action_spawn.R:121-168), for the rows of a block once they have grown: spawningnum = num x
             // proportion, the block's part of the recruitment sum s, spawning mortality of the parents
-            auto spawn_rows = [&](const StockRec& St, const ColRec& Cl, const int row0, const int nb, T (&num)[NB], const T (&wgt)[NB], T& acc) {
+            auto spawn_rows = [&](const StockRec& St, const ColRec& Cl, const int row0, const int nb, T (&num)[NB], T (&wgt)[NB], T& acc) {
                 const int32_t* Sp = I + St.sp_ioff;
                 const bool fec = Sp[G3SP_RECR_KIND] == G3SPAWN_FECUNDITY;
                 T p3(0.0), p4(0.0);
@@ -970,6 +970,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     if (fec) acc = acc + G(St.g_sfec + Cl.aidx * St.L + l) * xpow(spn, p3) * xpow(wgt[b], p4);
                     else acc = acc + wgt[b] * spn;
                     if (St.g_smort >= 0) num[b] = num[b] - spn * G(St.g_smort + l);
+                    if (Sp[G3SP_WLOSS] >= 0) {      // spawning weight loss (R/action_spawn.R:166-181, R/action_weightloss.R:19-44)
+                        const T mw = SLOT(Sp[G3SP_WLOSS + 1]);
+                        const T lost = ((wgt[b] - mw) * (1.0 - SLOT(Sp[G3SP_WLOSS]))) + mw;
+                        wgt[b] = ratio_add_pop(wgt[b], num[b] - spn, lost, spn);
+                    }
                 }
             };
             const bool spawn_step = XF && ((A.spawn_mask >> step) & 1);

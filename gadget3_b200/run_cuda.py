@@ -467,6 +467,8 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             q[K["G3SP_MORT_KIND"]:K["G3SP_MORT_KIND"] + 6] = [-1] * 6
         else:
             q[K["G3SP_MORT_KIND"]:K["G3SP_MORT_KIND"] + 6] = suit_slots(a.mortality_f, c, "g3a_spawn(mortality_f)")
+        wl = getattr(a, "weightloss", None)
+        q[K["G3SP_WLOSS"]:K["G3SP_WLOSS"] + 2] = [-1, -1] if wl is None else [low.slot(wl[0], c), low.slot(wl[1], c)]
         spawn_recs[name] = q
 
     # ---- renewal (order 8)

@@ -123,7 +123,11 @@
 #define G3SP_MORT_SLOTS   14   /* ints[5] */
 #define G3SP_N_OUT        19
 #define G3SP_OUT_OFF      20   /* ints[N_OUT*6]: (output stock, mean slot, sd slot, alpha slot, beta slot, ratio slot) */
-#define G3SP_LEN          21
+#define G3SP_WLOSS        21   /* spawning weight loss (g3a_weightloss on the spawning part, R/action_spawn.R:166-181, R/action_weightloss.R:19-44):
+                                  ints[2]: slots rel_loss, min_weight; after the spawning mortality
+                                  wgt = ratio_add_pop(wgt, num - spawningnum, (wgt - min_weight) (1 - rel_loss) + min_weight, spawningnum);
+                                  -1 in [0] = none */
+#define G3SP_LEN          23
 
 #define G3SPAWN_FECUNDITY        0   /* s = sum midlen^p1 age^p2 spawningnum^p3 wgt^p4, r = p0 s (R/action_spawn.R:1-17) */
 #define G3SPAWN_SIMPLESSB        1   /* s = sum wgt spawningnum (this and all below), r = mu s (:19-28) */

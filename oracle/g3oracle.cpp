@@ -677,6 +677,11 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
                     T m = suitability<T>(Sp[G3SP_MORT_KIND], Sp + G3SP_MORT_SLOTS, slot, midlen[l], midlen[l], ok);
                     num[c] = num[c] - spn * (1.0 - xexp(-m));
                 }
+                if (Sp[G3SP_WLOSS] >= 0) {      // g3a_weightloss on the spawning part (R/action_spawn.R:166-181, R/action_weightloss.R:19-44)
+                    T mw = slot(Sp[G3SP_WLOSS + 1]);
+                    T lost = ((wgt[c] - mw) * (1.0 - slot(Sp[G3SP_WLOSS]))) + mw;
+                    wgt[c] = ratio_add_pop(wgt[c], num[c] - spn, lost, spn);
+                }
             }
             if (!ok) return T(NaN);
             T r(0.0);

@@ -137,3 +137,35 @@ def test_spawn_api_errors():
         g3a_spawn(mat, rf, output_stocks=[i1, i2], output_ratios=[9, 9, 9])
     with pytest.raises(ValueError, match="output_ratios"):
         g3a_spawn(mat, rf, output_stocks=[i1, i2], output_ratios=[9, 9])
+
+
+def test_spawning_weight_loss_by_hand(oracle_lib):
+    """g3a_spawn(weightloss_f) / weightloss_args (R/action_spawn.R:166-181 -> g3a_weightloss with apply_to_pop =
+    stock__spawningnum, R/action_weightloss.R:19-44): on parents nothing else touches, number and mean weight at the start
+    of step 3 follow from those at the start of step 2 by the spawning formulas alone --
+    spawningnum = num * proportion(l); num' = num - spawningnum (1 - exp(-mortality));
+    wgt' = ratio_add_pop(wgt, num' - spawningnum, (wgt - min_weight) (1 - rel_loss) + min_weight, spawningnum)."""
+    import math
+    from gadget3_b200 import G3Unsupported, g3_parameterized, g3a_spawn, g3a_spawn_recruitment_simplessb
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["WLOSS_RIG"]()
+    rep = unpack_report(model, Oracle(*model.pack(p)).report(p.values()))
+    v = dict(zip(p.switch, p.values()))
+    mid = np.arange(15, 60, 10.0)
+    az = lambda x: np.logaddexp(1000 * x, 0) / 1000
+    for k in ("rel", "min"):
+        n, w = rep[f"dstart_mat_{k}__num"], rep[f"dstart_mat_{k}__wgt"]        # [length, age, area, time]
+        for t in (1, 5):                                                      # step 2 of both years
+            prop = (1 / (1 + np.exp(-v[f"mat_{k}.spawn.alpha"] * (mid - v[f"mat_{k}.spawn.l50"]))))[:, None, None]
+            spn = n[..., t] * prop
+            num2 = n[..., t] - spn * (1 - math.exp(-v[f"mat_{k}.spawn.mort"]))
+            mw = v.get(f"mat_{k}.spawn.minwgt", 0.0)
+            lost = (w[..., t] - mw) * (1 - v[f"mat_{k}.spawn.wloss"]) + mw
+            np.testing.assert_allclose(n[..., t + 1], num2, rtol=1e-14)
+            np.testing.assert_allclose(w[..., t + 1], (w[..., t] * (num2 - spn) + lost * spn) / az(num2), rtol=1e-14)
+            assert (w[..., t + 1] < w[..., t]).all()
+        assert np.array_equal(w[..., 1], w[..., 0]) and np.array_equal(w[..., 3], w[..., 2])      # no other step touches them
+    with pytest.raises(G3Unsupported, match="abs_loss"):
+        g3a_spawn(model.actions[1].stock, g3a_spawn_recruitment_simplessb(g3_parameterized("mu")), weightloss_args=dict(abs_loss=0.1))
