@@ -9,13 +9,15 @@ differ by as much (R sums in long double, TMB in Eigen's packet order)."""
 import numpy as np
 
 US_WEIGHT = 1e8      # g3l_understocking default weight (R/likelihood_understocking.R:7)
-_CACHE = {}
 
 
 def consumed_biomass_per_step(model, params):
     """Biomass consumed at each step, summed over predators and prey cells, at the template values
     (from the oracle's detail_<prey>_<pred>__cons report)."""
-    key = id(model)
+    # cached ON the model: a cache keyed by id(model) hands a freed model's numbers to the next object that gets its address
+    # (seen once as a spurious failure of a CPU test)
+    _CACHE = model.__dict__.setdefault("_parity_cache", {})
+    key = "consumed_biomass"
     if key not in _CACHE:
         from gadget3_b200.run_cuda import unpack_report
         from oracle.oracle_lib import Oracle
