@@ -432,7 +432,7 @@ def build_c5(seed=123):
     return model, p
 
 
-def build_mini_andersen(seed=123, suits=False, otherfood=False, prefs=False):
+def build_mini_andersen(seed=123, suits=False, otherfood=False, prefs=False, stomach=False):
     """Small 2-area test model: a stock predator with g3_suitability_andersen (predator-length dependent
     suitability), migration on one step only for the predator, renewal, ageing -- exercises the code
     paths config 5 does not (used by the parity tests, not by bench.py). `otherfood`: the predator also eats an
@@ -501,6 +501,14 @@ def build_mini_andersen(seed=123, suits=False, otherfood=False, prefs=False):
                       length=["[5,20)", "[20,35)", "[35,Inf)"] * 4, number=list(rng.uniform(10, 100, 12)))
             actions.append(g3l_catchdistribution("ldist_" + fname, ld, fleets=[fl], stocks=[prey],
                                                  function_f=g3l_distribution_sumofsquares(), area_group=None))
+    if stomach:     # stomach contents: what the predator ate, by prey length (g3l_catchdistribution(predators = ...))
+        sd = dict(year=[y for y in yrs for _ in range(3)], step=[2] * 12,
+                  length=["[5,20)", "[20,35)", "[35,Inf)"] * 4, weight=list(rng.uniform(1, 10, 12)))
+        actions.append(g3l_catchdistribution("stomach_pred", sd, predators=[pred], stocks=[prey],
+                                             function_f=g3l_distribution_sumofsquares(), area_group=None, report=True))
+        sn = dict(year=[y for y in yrs for _ in range(2)], step=[4] * 8, area=["a", "b"] * 4, number=list(rng.uniform(100, 1000, 8)))
+        actions.append(g3l_catchdistribution("eaten_num", sn, predators=[pred], stocks=[prey], area_group=areas,
+                                             function_f=g3l_distribution_surveyindices_log(alpha=None, beta=1)))
     for nm, stk in (("si_prey", prey), ("si_pred", pred)):
         si = dict(year=[y for y in yrs for _ in range(2)], step=[3] * 8, area=["a", "b"] * 4,
                   number=list(rng.uniform(1e4, 1e5, 8)))
@@ -1302,5 +1310,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "MINI_MATVAR": lambda: build_mini_spawn(matvar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "WLOSS_RIG": build_wloss_rig, "RENEWAL_RIG": build_renewal_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_STOMACH": lambda: build_mini_andersen(stomach=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "MINI_MATVAR": lambda: build_mini_spawn(matvar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "WLOSS_RIG": build_wloss_rig, "RENEWAL_RIG": build_renewal_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
            "LING": build_ling}

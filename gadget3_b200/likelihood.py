@@ -246,8 +246,15 @@ def g3l_distribution(nll_name, obs_data, fleets=(), stocks=(), function_f=None, 
                      report=False, nll_breakdown=False, weight=None, missing_val=0, transform_fs=None,
                      predators=()):
     """R/likelihood_distribution.R:177-440."""
+    # predators (stock predators) are collected exactly as fleets are (fleetpreds <- c(fleets, predators),
+    # R/likelihood_distribution.R:200,275-292): predprey__cons, summed over the predator's own dimensions unless the data
+    # carries predator_length / predator_age / predator_tag columns -- those are not supported
     if predators:
-        raise G3Unsupported("g3l_distribution(predators = ...)")
+        cols = obs_data.keys() if hasattr(obs_data, "keys") else ()
+        bad = [c for c in cols if str(c).startswith("predator_")]
+        if bad:
+            raise G3Unsupported("g3l_distribution(predators = ...) with %s columns in the data" % ", ".join(bad))
+        fleets = list(fleets) + list(predators)
     if not isinstance(function_f, _DistFn):
         raise G3Unsupported("g3l_distribution: unsupported function_f")
     return DistributionAction(nll_name, obs_data, fleets, stocks, function_f, area_group, report,
@@ -255,13 +262,13 @@ def g3l_distribution(nll_name, obs_data, fleets=(), stocks=(), function_f=None, 
 
 
 def g3l_catchdistribution(nll_name, obs_data, fleets=(), stocks=(), function_f=None, **kw):
-    if len(fleets) == 0:
+    if len(fleets) == 0 and len(kw.get("predators", ())) == 0:
         raise ValueError("fleets/predators must be supplied for g3l_catchdistribution")
     return g3l_distribution(nll_name, obs_data, fleets, stocks, function_f, **kw)
 
 
 def g3l_abundancedistribution(nll_name, obs_data, fleets=(), stocks=(), function_f=None, **kw):
-    if len(fleets) > 0:
+    if len(fleets) > 0 or len(kw.get("predators", ())) > 0:
         raise ValueError("fleets/predators must not be supplied for g3l_abundancedistribution")
     return g3l_distribution(nll_name, obs_data, (), stocks, function_f, **kw)
 

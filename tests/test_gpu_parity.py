@@ -313,7 +313,7 @@ def test_against_reference_generated_code(setups, name, kernel):
 
 
 @KERNELS
-@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "SIX_FLEETS", "MINI_MATVAR", "RENEWAL_RIG", "WLOSS_RIG"])
+@pytest.mark.parametrize("name", ["MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "SIX_FLEETS", "MINI_MATVAR", "RENEWAL_RIG", "WLOSS_RIG", "MINI_STOMACH"])
 def test_andersen_predator_model(oracle_lib, name, kernel):
     """g3_suitability_andersen (predator-length dependent), one-step-only migration: CUDA vs oracle.
     MINI_SUITS: richards for the predator, gamma / andersenfleet / straightline fleets, reports included.
@@ -323,6 +323,7 @@ def test_andersen_predator_model(oracle_lib, name, kernel):
     RENEWAL_RIG: renewal mean length by year, standard deviation a g3_timevariable (one record per shape; the oracle's
     renewal against the normal density by hand in tests/test_oracle_kat.py).
     WLOSS_RIG: spawning weight loss, relative and with a floor (by hand in tests/test_oracle_spawn.py).
+    MINI_STOMACH: stomach contents -- g3l_catchdistribution(predators = ...) on the stock predator's consumption.
     SIX_FLEETS: three stocks, six fleets, 15 likelihood components, 9 collect vectors, five predators on one stock."""
     model, p = CONFIGS[name]()
     fn = g3_cuda_adfun(model, p, device=0)

@@ -202,3 +202,29 @@ def test_prey_preferences(oracle_lib):
     plain = _expected_two_prey_consumption(model, p, v, rep, 0)
     want = _expected_two_prey_consumption(model, p, v, rep, 0, pref={"prey": 0.9, "otherfood": 1.3})
     assert np.abs(plain["prey"] - want["prey"]).max() > 1e-3 * plain["prey"].max()          # the exponents do something
+
+
+def test_stomach_content_distribution(oracle_lib):
+    """g3l_catchdistribution(predators = list(pred), stocks = list(prey)) (R/likelihood_distribution.R:200,275-292: stock
+    predators are collected exactly as fleets are, predprey__cons summed over the predator's own dimensions): the model
+    array in biomass is the reported consumption detail_prey_pred__cons of that step, summed into the data's length bins;
+    data with predator_length columns are refused."""
+    from gadget3_b200 import G3Unsupported, g3l_catchdistribution, g3l_distribution_sumofsquares
+    from gadget3_b200.configs import CONFIGS
+    from gadget3_b200.run_cuda import unpack_report
+    from oracle.oracle_lib import Oracle
+    model, p = CONFIGS["MINI_STOMACH"]()
+    rep = unpack_report(model, Oracle(*model.pack(p)).report(p.values()))
+    cons = rep["detail_prey_pred__cons"]                   # [length (5..50 by 5), age, area, time]
+    got = rep["cdist_sumofsquares_stomach_pred_model__wgt"]        # [time, areagroup, stockgroup, age, bin]
+    assert got.shape[0] == 4 and got.shape[-1] == 3
+    bins = [slice(0, 3), slice(3, 6), slice(6, 9)]          # [5,20) [20,35) [35,Inf)
+    for i in range(4):
+        t = 4 * i + 1                                       # step 2 of every year
+        hand = np.array([cons[b, :, :, t].sum() for b in bins])
+        assert hand.min() > 0
+        np.testing.assert_allclose(got[i].ravel(), hand, rtol=1e-12)
+    pred, prey = model.actions[2].stock, model.actions[1].stock
+    with pytest.raises(G3Unsupported, match="predator_length"):
+        g3l_catchdistribution("x", dict(year=[2000], step=[2], predator_length=["[20,30)"], weight=[1.0]), predators=[pred],
+                              stocks=[prey], function_f=g3l_distribution_sumofsquares())

@@ -23,7 +23,7 @@ def _setup(name, B, seed=2026):
 
 
 @pytest.mark.parametrize("smem", [True, False], ids=["state_in_smem", "state_in_slab"])
-@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5", "LING", "MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "RANDOM_RIG", "C1_RANDOM", "SIX_FLEETS", "MINI_MATVAR", "RENEWAL_RIG", "WLOSS_RIG"])
+@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5", "LING", "MINI_ANDERSEN", "MINI_OTHERFOOD", "MINI_PREFS", "MINI_SUITS", "MINI_FLEETS", "MINI_MIGRATE", "MINI_TRANSFORM", "SPAWN_RIG", "MINI_SPAWN", "MINI_TIMEVAR", "TIMEVAR_RIG", "RANDOM_RIG", "C1_RANDOM", "SIX_FLEETS", "MINI_MATVAR", "RENEWAL_RIG", "WLOSS_RIG", "MINI_STOMACH"])
 def test_values_and_components(oracle_lib, name, smem):
     model, p, ints, reals, full, _ = _setup(name, 6)
     o_nll, o_comp, _ = Oracle(ints, reals).eval_batch(full, want_comp=True, nthreads=4)
@@ -39,7 +39,7 @@ def test_values_and_components(oracle_lib, name, smem):
         assert (np.abs(g_nll - o_nll) / np.abs(o_nll)).max() < 1e-10
 
 
-@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C5", "LING", "MINI_SPAWN", "SPAWN_RIG", "MINI_TIMEVAR", "RANDOM_RIG", "C1_RANDOM", "MINI_MATVAR", "RENEWAL_RIG", "WLOSS_RIG"])
+@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C5", "LING", "MINI_SPAWN", "SPAWN_RIG", "MINI_TIMEVAR", "RANDOM_RIG", "C1_RANDOM", "MINI_MATVAR", "RENEWAL_RIG", "WLOSS_RIG", "MINI_STOMACH"])
 def test_gradients(oracle_lib, name):
     model, p, ints, reals, full, opt = _setup(name, 2, seed=77)
     tidx = opt[:6].astype(np.int32) if name != "C1" else opt[:10].astype(np.int32)       # 2-3 direction tiles
