@@ -53,6 +53,7 @@ struct KArgs {
     int t_pts[MAXS], t_pmc[MAXS];           // per stock predator: totals / consumption factors [area][length]; max consumption [length]
     int t_mig[MAXS], t_mig_steps[MAXS];     // migration matrices [step][dest][src]; steps on which the stock migrates
     int w_grow_nset[MAXS];                  // slot sets of time-varying growth parameters (1 otherwise)
+    int w_ncset[MAXS];                      // maturing / staying bands per column (g3a_mature_continuous with an age term), else 1
     int w_mort_nset[MAXS];                  // slot sets of a time-varying M (1 otherwise)
     int t_sps;                              // per stock: the recruitment sum s of a spawning stock at this step (g3a_spawn)
     int t_remf, t_colbase[MAXS], t_cmat[MAXS];      // per global column: unclaimed share; first global column; constant-maturity ratios

@@ -169,8 +169,14 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             for (int idt = 0; idt < A.w_ndt; idt++) {
                 const double dt = A.w_dt_len[idt] / 12.0;
                 const T linf = SLOT(gs[0]), kk = 1.0 - xexp(-(SLOT(gs[1])) * dt), beta = avoid_zero(SLOT(gs[2]));
-                T malpha(0.0), ml50(0.0);
-                if (cont) { const int32_t* ms = I + St[G3S_MAT_OFF] + 4 * gset; malpha = SLOT(ms[0]); ml50 = SLOT(ms[1]); }
+                T malpha(0.0), ml50(0.0), mbeta(0.0), ma50(0.0);
+                const int ncset = A.w_ncset[s];     // > 1: the maturing share has an age term, one pair of bands per column
+                if (cont) {
+                    const int32_t* ms = I + St[G3S_MAT_OFF] + 4 * gset; malpha = SLOT(ms[0]); ml50 = SLOT(ms[1]);
+                    if (ms[2] >= 0) { mbeta = SLOT(ms[2]); ma50 = SLOT(ms[3]); }
+                }
+                for (int cset = 0; cset < ncset; cset++) {
+                const double c_age = (double)(St[G3S_MINAGE] + cset % St[G3S_NAGE]);
                 // source-oriented band in scratch: [v][x * L + l], v = 0 all, 1 maturing, 2 staying
                 for (int l = 0; l < L; l++) {
                     // g3a_grow_lengthvbsimple (R/action_grow.R:54) inside the bbinom wrapper (R/action_grow.R:220)
@@ -181,11 +187,16 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                     T g = T(1.0);
                     for (int j = 0; j < n2; j++) g = g * ((beta + (double)j) / xabs(alpha + beta + (double)j));
                     T m0(0.0);
-                    if (cont) m0 = 1.0 / (1.0 + xexp(0.0 - malpha * (midlen[l] - ml50)));      // R/action_mature.R:46-72
+                    if (cont) {         // g3a_mature_constant as M0 (R/action_mature.R:46-72)
+                        T inner = 0.0 - malpha * (midlen[l] - ml50);
+                        if (ncset > 1) inner = inner - mbeta * (c_age - ma50);
+                        m0 = 1.0 / (1.0 + xexp(inner));
+                    }
                     for (int x = 0; x <= n2; x++) {
                         W(A.t_scr + x * L + l) = g;
-                        if (cont) {     // g3a_mature_continuous (R/action_mature.R:1-42), beta = 0
-                            T ratio = dif_pminmax_c(m0 * (malpha * (pdl * x)), 0.0, 1.0, 1e5);
+                        if (cont) {     // g3a_mature_continuous (R/action_mature.R:1-42): alpha ldelta + beta cur_step_size
+                            T ratio = ncset > 1 ? dif_pminmax_c(m0 * (malpha * (pdl * x) + mbeta * dt), 0.0, 1.0, 1e5)
+                                                : dif_pminmax_c(m0 * (malpha * (pdl * x)), 0.0, 1.0, 1e5);
                             W(A.t_scr + gsz + x * L + l) = g * ratio;
                             W(A.t_scr + 2 * gsz + x * L + l) = g * (1.0 - ratio);
                         }
@@ -194,8 +205,9 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                     }
                 }
                 // destination-oriented band [d][l] = P(l - d -> l), plus-group tail sums folded in (R/action_grow.R:233-271)
-                for (int v = 0; v < (cont ? 3 : 1); v++) {
-                    const int o = (v == 0 ? A.t_g[s] : (v == 1 ? A.t_gr[s] : A.t_gn[s])) + (gset * A.w_ndt + idt) * gsz;
+                for (int v = (cset == 0 ? 0 : 1); v < (cont ? 3 : 1); v++) {
+                    const int o = v == 0 ? A.t_g[s] + (gset * A.w_ndt + idt) * gsz
+                                         : (v == 1 ? A.t_gr[s] : A.t_gn[s]) + ((gset * ncset + cset) * A.w_ndt + idt) * gsz;
                     for (int d = 0; d <= n2; d++)
                         for (int j = 0; j < L; j++) {
                             const int src = j - d;
@@ -207,6 +219,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                             W(o + d * L + j) = g;
                         }
                 }
+                }   // cset
             }
             }   // gset
         }
@@ -607,8 +620,11 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 const int cper = NW <= 8 ? ncol : A.t_cblk;
                 for (int cb0 = 0; cb0 < ncol; cb0 += cper) {
                 const int cb1 = min(cb0 + cper, ncol);
-                const T* pg = ws + (unsigned)((cont_now ? A.t_gn[s] : A.t_g[s]) + (gset * A.w_ndt + idt) * gsz + (L - 1)) * NTH;     // staying part, [d][l]
-                const T* pgr = ws + (unsigned)(A.t_gr[s] + (gset * A.w_ndt + idt) * gsz + (L - 1)) * NTH;                              // maturing part
+                const int ncset = grow_n >= 0 ? A.w_ncset[s] : 1;       // > 1: bands per column (maturity with an age term)
+                const bool percol = cont_now && ncset > 1;
+                const T* pg = ws + (unsigned)((cont_now ? A.t_gn[s] + (gset * ncset * A.w_ndt + idt) * gsz : A.t_g[s] + (gset * A.w_ndt + idt) * gsz) + (L - 1)) * NTH;     // staying part, [d][l]
+                const T* pgr = ws + (unsigned)(A.t_gr[s] + (gset * ncset * A.w_ndt + idt) * gsz + (L - 1)) * NTH;                            // maturing part
+                const unsigned cset_stride = (unsigned)(A.w_ndt * gsz) * NTH;      // from one column's bands to the next
                 const T* ppw = ws + (unsigned)(A.t_pw[s] + gset * L + (L - 1)) * NTH;
                 for (int l = L - 1; l >= 0; l--, pg -= NTH, pgr -= NTH, ppw -= NTH) {
                     // Narrow bands keep the band and the weight gains of this length in registers for all columns;
@@ -666,6 +682,7 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                                         gd = pg[d * LWS]; grd = cont_now ? pgr[d * LWS] : T(0.0);
                                         dwd = wal * (pw_l - *(ppw - d * NTH));
                                     }
+                                    if (percol) { gd = (pg + col * cset_stride)[d * LWS]; grd = (pgr + col * cset_stride)[d * LWS]; }
                                     const T wsrc = dwd + *(pw_ - d * NTH);
                                     if (cont_now) {
                                         const T w = wsrc * ns;

@@ -245,8 +245,12 @@ int make_tlayout(g3cuda_model* m, g3::KArgs& A) {
         if (n < 0) { A.t_g[s] = A.t_gr[s] = A.t_gn[s] = 0; continue; }
         int g = (n + 1) * L; maxg = std::max(maxg, g);
         A.t_g[s] = take(gn * g * A.w_ndt);
-        if (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0) { A.t_gr[s] = take(gn * g * A.w_ndt); A.t_gn[s] = take(gn * g * A.w_ndt); }
-        else { A.t_gr[s] = A.t_gn[s] = A.t_g[s]; }
+        A.w_ncset[s] = 1;
+        if (St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0) {
+            // an age term (beta, a50: R/action_mature.R:18,44-74) makes the maturing share differ from column to column
+            if (I[St[G3S_MAT_OFF] + 2] >= 0) A.w_ncset[s] = St[G3S_NAGE] * St[G3S_NAREA];
+            A.t_gr[s] = take(gn * A.w_ncset[s] * g * A.w_ndt); A.t_gn[s] = take(gn * A.w_ncset[s] * g * A.w_ndt);
+        } else { A.t_gr[s] = A.t_gn[s] = A.t_g[s]; }
     }
     A.t_scr = take(3 * maxg);
     for (int c = 0; c < A.NCOMP; c++) {
@@ -379,8 +383,6 @@ std::string plan_thread(g3cuda_model* m, std::vector<int32_t>& rem_off, std::vec
         maxnarea = std::max(maxnarea, narea);
         if (St[G3S_N_RENEW] > MAXRN) return "more than " + std::to_string(MAXRN) + " renewal actions on one stock";
         if (St[G3S_GROW_N] >= 0 && St[G3S_MAT_KIND] == G3MAT_CONSTANT && St[G3S_N_OUT] > 0) A.any_const_mat = 1;
-        if (St[G3S_GROW_N] >= 0 && St[G3S_MAT_KIND] == G3MAT_CONTINUOUS && St[G3S_N_OUT] > 0 && I[St[G3S_MAT_OFF] + 2] >= 0)
-            return "g3a_mature_continuous with an age term (tile kernel only)";
         for (int r = 0; r < narea; r++) for (int a = 0; a < nage; a++) for (int l = 0; l < L; l++)
             cell[c0 + (r * nage + a) * L + l] = make_int4(s, l, r * nage + a, r);
         int ncell = L * nage * narea;
