@@ -844,7 +844,22 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
                 const int nb = C[G3C_N_BINS], nsl = C[G3C_N_SLICES], nag = C[G3C_N_AREAG];
                 T cnll(0.0);
                 bool scored = false;
-                if (func == G3F_SUMOFSQUARES) {     // R/likelihood_distribution.R:3-39
+                if (func == G3F_SUMOFSQUARES && R[C[G3C_PARAM_ROFF]] != 0.0) {
+                    // stratified (over includes 'length'): proportions within each length group, R/likelihood_distribution.R:8-16
+                    const double* op = A.obsprop + A.obs_off[c] + (size_t)ti * nd;     // (obs / avoid_zero(its length group's total))
+                    for (int ag = 0; ag < nag; ag++)
+                        for (int b = 0; b < nb; b++) {
+                            T tot(0.0);
+                            for (int sl = 0; sl < nsl; sl++) tot = tot + W(ms + (ag * nsl + sl) * nb + b);
+                            const T rt = 1.0 / avoid_zero(tot);
+                            for (int sl = 0; sl < nsl; sl++) {
+                                const int i = (ag * nsl + sl) * nb + b;
+                                T dlt = W(ms + i) * rt - op[i];
+                                cnll = cnll + dlt * dlt;
+                            }
+                        }
+                    scored = true;
+                } else if (func == G3F_SUMOFSQUARES) {     // R/likelihood_distribution.R:3-39
                     const int per = nsl * nb;
                     const double* op = A.obsprop + A.obs_off[c] + (size_t)ti * nd;
                     for (int ag = 0; ag < nag; ag++) {

@@ -554,7 +554,6 @@ std::string plan_thread(g3cuda_model* m, std::vector<int32_t>& rem_off, std::vec
     for (int c = 0; c < A.NCOMP; c++) {
         const int32_t* C = I + I[G3H_COMP_OFF] + c * G3C_LEN;
         if (C[G3C_FUNC] < 0 || C[G3C_FUNC] > G3F_SUMSQLOGRATIOS) return "likelihood function " + std::to_string(C[G3C_FUNC]) + " is not supported";
-        if (C[G3C_FUNC] == G3F_SUMOFSQUARES && m->R[C[G3C_PARAM_ROFF]] != 0.0) return "stratified sumofsquares (tile kernel only)";
     }
     // 32-bit element indexing of the workspace (in units of T): entries x stride must stay below 2^32
     if ((double)m->t_entries * (double)WS_STRIDE >= 4294967295.0) return "evaluation workspace too large for 32-bit element indexing";

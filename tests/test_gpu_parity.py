@@ -108,7 +108,7 @@ def _check_gradients(model, p, fn, orc):
     assert ((np.abs(g_grad - o_grad) / scale).max(axis=1) < gtol).all()
 
 
-@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C4", "C5"])
+@pytest.mark.parametrize("name", ["C1", "C1_MULTI", "C2", "C2_MATAGE", "C2_STRAT", "C4", "C5"])
 def test_report_arrays(setups, name):
     model, p, fn, orc = setups[name]
     par = parameter_batch(p, 1, seed=5)[0]
