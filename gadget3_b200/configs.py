@@ -82,7 +82,7 @@ def _fleet_data(rng, years, landings_mean, landings_sd, n_ldist, len_breaks, n_a
     return out
 
 
-def build_c1(seed=123, data=None, likelihood="sumofsquares", random=False):
+def build_c1(seed=123, data=None, likelihood="sumofsquares", random=False, max_project_years=0):
     """introduction-single-stock (vignettes/introduction-single-stock.Rmd:116-596, 666-701).
     `data`: the fleet tables (landings, ldist, aldist, si as column dicts) to use instead of the synthetic
     draws -- tools/replay_tmb_bundle.py feeds the tables an R session dumped.
@@ -130,7 +130,7 @@ def build_c1(seed=123, data=None, likelihood="sumofsquares", random=False):
                     g3l_random_walk("rec_walk", rec, sigma_f=g3_parameterized("rec_sigma", value=2.0, lower=0.5, upper=5),
                                     period="year")]
     actions += [g3a_report_detail(actions), g3l_bounds_penalty(actions)]
-    model = g3_to_cuda(actions)
+    model = g3_to_cuda(actions, max_project_years=max_project_years)
     midlen = fish.midlen
     est_l50 = midlen[len(midlen) // 2 - 1]
     est_linf = max(midlen)
@@ -1310,5 +1310,5 @@ def profile_sweep(params, names, n_per_axis):
     return P
 
 
-CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_STOMACH": lambda: build_mini_andersen(stomach=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "MINI_MATVAR": lambda: build_mini_spawn(matvar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "WLOSS_RIG": build_wloss_rig, "RENEWAL_RIG": build_renewal_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True),
+CONFIGS = {"C1": build_c1, "C1_MULTI": lambda: build_c1(likelihood="multinomial"), "C2": build_c2, "C2_MATAGE": lambda: build_c2(mat_age=True), "C2_STRAT": lambda: build_c2(stratified=True), "C4": build_c4, "C5": build_c5, "MINI_ANDERSEN": build_mini_andersen, "MINI_OTHERFOOD": lambda: build_mini_andersen(otherfood=True), "MINI_PREFS": lambda: build_mini_andersen(otherfood=True, prefs=True), "MINI_SUITS": lambda: build_mini_andersen(suits=True), "MINI_STOMACH": lambda: build_mini_andersen(stomach=True), "MINI_FLEETS": build_mini_fleets, "MINI_MIGRATE": build_mini_migrate, "MINI_TRANSFORM": build_mini_transform, "SPAWN_RIG": build_spawn_rig, "MINI_SPAWN": build_mini_spawn, "MINI_TIMEVAR": lambda: build_mini_spawn(timevar=True), "MINI_MATVAR": lambda: build_mini_spawn(matvar=True), "TIMEVAR_RIG": build_timevar_rig, "RANDOM_RIG": build_random_rig, "WLOSS_RIG": build_wloss_rig, "RENEWAL_RIG": build_renewal_rig, "SIX_FLEETS": build_six_fleets, "C1_RANDOM": lambda: build_c1(random=True), "C1_PROJ": lambda: build_c1(max_project_years=3),
            "LING": build_ling}

@@ -942,7 +942,8 @@ __global__ void __launch_bounds__(CB) eval_thread_kernel(const __grid_constant__
             // ================= g3l_random_dnorm / g3l_random_walk (R/likelihood_random.R:14-109)
             for (int r = 0; r < I[G3H_NRAND]; r++) {
                 const int32_t* Rn = I + I[G3H_RAND_OFF] + r * G3RN_LEN;
-                if (!I[Rn[G3RN_RUN_OFF] + t]) continue;
+                const int run = I[Rn[G3RN_RUN_OFF] + t];
+                if (!run || (run == 2 && t != total_steps)) continue;
                 const T sd = SLOT(I[Rn[G3RN_SIGMA_OFF] + t]);
                 const T resid = (SLOT(I[Rn[G3RN_PARAM_OFF] + t]) - SLOT(I[Rn[G3RN_MEAN_OFF] + t])) / sd;
                 const T logans = T(-0.91893853320467274178) - xlog(sd) - 0.5 * resid * resid;     // TMB dnorm

@@ -1343,12 +1343,13 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                 if (F_LIKE)
                     for (int r = 0; r < I[G3H_NRAND]; r++) {
                         const int32_t* const Rn = I + I[G3H_RAND_OFF] + r * G3RN_LEN;
-                        if (!I[Rn[G3RN_RUN_OFF] + t]) continue;
+                        const int run = I[Rn[G3RN_RUN_OFF] + t];
+                        if (!run) continue;
                         const T sd = SLOT(I[Rn[G3RN_SIGMA_OFF] + t]);
                         const T resid = (SLOT(I[Rn[G3RN_PARAM_OFF] + t]) - SLOT(I[Rn[G3RN_MEAN_OFF] + t])) / sd;
                         const T logans = T(-0.91893853320467274178) - xlog(sd) - 0.5 * resid * resid;     // TMB dnorm
                         const T n = Rn[G3RN_LOG] ? T(0.0) - logans : xexp(logans);
-                        if (lane_on) {
+                        if (lane_on && (run != 2 || t == total_steps)) {        // (2: on the last step of this vector's run)
                             nll = nll + SLOT(Rn[G3RN_WEIGHT]) * n;
                             GS(A.g_ctot + A.NCOMP + r, G(A.g_ctot + A.NCOMP + r) + n);
                         }

@@ -794,13 +794,16 @@ int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B, const int32
     const int P = m->NPAR, NN = m->NNLL;
     const bool want_grad = grad && K > 0;
     if (want_grad && !tangent_idx) return fail(G3CUDA_EINVAL, "grad requested without tangent_idx");
-    // Projections are outside the supported subset: the reference would run project_years more years (R/action_time.R:21-106),
-    // the kernels hold tables for the model's own years only. Say so instead of returning a NaN that looks like a value
-    // (NaN stays a VALUE for the reference's own NaN case, retro_years < 0).
-    if (const int pj = m->I[G3H_PAR_PROJECT]; pj >= 0)
+    // Projections: the reference runs project_years more years (R/action_time.R:21-106); the kernels hold tables for the years
+    // the model was lowered for. Beyond them, say so instead of returning a NaN that looks like a value (NaN stays a VALUE for
+    // the reference's own NaN case, retro_years < 0).
+    if (const int pj = m->I[G3H_PAR_PROJECT]; pj >= 0) {
+        // the per-step tables reach max_project_years past end_year (g3_to_cuda(max_project_years = ...))
+        const int room = m->I[G3H_NT] / m->I[G3H_NSTEPS] - (m->I[G3H_END_YEAR] - m->I[G3H_START_YEAR] + 1);
         for (int64_t b = 0; b < B; b++)
-            if (par[b * P + pj] >= 1.0)
-                return fail(G3CUDA_EUNSUPP, "vector %lld sets project_years = %g: projections are outside the supported subset", (long long)b, par[b * P + pj]);
+            if (par[b * P + pj] >= (double)(room + 1))
+                return fail(G3CUDA_EUNSUPP, "vector %lld sets project_years = %g: the model was lowered with room for %d projection year(s) (max_project_years)", (long long)b, par[b * P + pj], room);
+    }
     int rc;
     if ((rc = ensure(&m->d_par, &m->cap_par, (size_t)B * P))) return rc;
     if ((rc = ensure(&m->d_out, &m->cap_out, (size_t)B))) return rc;

@@ -124,7 +124,12 @@ def save_spec(model: "G3CudaModel", path, parameters: ParameterTemplate = None, 
     return meta
 
 
-def g3_to_cuda(actions, strict=False) -> G3CudaModel:
+def g3_to_cuda(actions, strict=False, max_project_years=0) -> G3CudaModel:
+    """``max_project_years``: how many years past end_year a parameter vector may run (its project_years, R/action_time.R:21-78).
+    The reference grows its loop at run time; here every per-step table is laid out at lowering time, so the lowering
+    needs the bound. In those years no observation has a time index and no landing is recorded (g3_timeareadata: missing =
+    0), by-year parameter tables answer with their `ifmissing` (rec.proj) or NaN (R/run_tmb.R:1047-1054) -- as in the
+    reference. Projection fleets / quotas / g3_param_project are outside the supported subset."""
     acts = _flatten(actions)
     by_kind = {}
     for a in acts:
@@ -139,7 +144,11 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
     S = len(tm.step_lengths)
     if S > 31:
         raise G3Unsupported("more than 31 steps per year")
-    n_years = tm.end_year - tm.start_year + 1
+    max_project_years = int(max_project_years)
+    if max_project_years < 0:
+        raise ValueError("max_project_years must be >= 0")
+    last_year = tm.end_year + max_project_years        # every per-year / per-step table reaches this far
+    n_years = last_year - tm.start_year + 1
     NT = S * n_years
     dt0 = tm.step_lengths[0] / 12.0
 
@@ -461,7 +470,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         if rf.kind == "fecundity":
             rs = rs[4:] + rs[:4]        # stored p0..p4; declared in the order the reference's code reads them (s, then r)
         if rf.R_by_year is not None:
-            rs.append(b.alloc_ints([low.slot(rf.R_by_year, Ctx(stock=s, cur_year=y)) for y in range(tm.start_year, tm.end_year + 1)]))
+            rs.append(b.alloc_ints([low.slot(rf.R_by_year, Ctx(stock=s, cur_year=y)) for y in range(tm.start_year, last_year + 1)]))
         q[K["G3SP_RECR_SLOTS"]:K["G3SP_RECR_SLOTS"] + 5] = rs + [-1] * (5 - len(rs))
         if isinstance(a.mortality_f, (int, float)) and a.mortality_f == 0:
             q[K["G3SP_MORT_KIND"]:K["G3SP_MORT_KIND"] + 6] = [-1] * 6
@@ -479,6 +488,8 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                 continue
             if a.run_age is None:
                 raise G3Unsupported("g3a_renewal: run_age = NULL")
+            if max_project_years > 0 and not a.run_projection:
+                raise G3Unsupported("g3a_renewal(run_projection = FALSE) in a model lowered with max_project_years > 0")
             if not (s.minage <= a.run_age <= s.maxage):
                 continue
             an0, aid0 = next(iter(s.areas.items()))
@@ -488,7 +499,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
             # year one record of the family runs, the others skip (FACTOR_OFF = -1), so the kernels need nothing new.
             run_steps = [int(a.run_step)] if a.run_step is not None else list(range(1, S + 1))
             families = OrderedDict()
-            for y in range(tm.start_year, tm.end_year + 1):
+            for y in range(tm.start_year, last_year + 1):
                 keys = {tuple(low.slot(f, c.replace(cur_year=y, cur_step=st, cur_step_size=tm.step_lengths[st - 1] / 12.0))
                               for f in (a.mean_f, a.stddev_f, a.alpha_f, a.beta_f)) for st in run_steps}
                 if len(keys) > 1:
@@ -500,7 +511,7 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
                 q[K["G3R_AGE_IDX"]] = a.run_age - s.minage
                 q[K["G3R_MEAN"]], q[K["G3R_SD"]], q[K["G3R_WALPHA"]], q[K["G3R_WBETA"]] = shape
                 ftab = []
-                for y in range(tm.start_year, tm.end_year + 1):
+                for y in range(tm.start_year, last_year + 1):
                     for an, aid in s.areas.items():
                         cy = Ctx(stock=s, age=a.run_age, area=aid, area_name=an, cur_year=y,
                                  cur_step=(a.run_step or 1))
@@ -680,15 +691,17 @@ def g3_to_cuda(actions, strict=False) -> G3CudaModel:
         for t in range(NT):
             c = Ctx(cur_year=tm.start_year + t // S, cur_step=t % S + 1, cur_step_size=tm.step_lengths[t % S] / 12.0)
             ps[t], ss[t] = low.slot(a.param_f, c), low.slot(a.sigma_f, c)
-            on = {"step": True, "year": t % S == S - 1, "single": t == NT - 1}[a.period]
+            # 'single' scores once, at the last step of the RUN (cur_time == total_steps, R/likelihood_random.R:46,97): that
+            # step moves with retro_years, so the flag says "the run's last step" (2) and the kernels compare with total_steps
+            on = {"step": True, "year": t % S == S - 1, "single": True}[a.period]
             if a.walk:
                 ms[t] = prev if prev >= 0 else ps[t]
-                run[t] = 1 if (on and prev >= 0) else 0
+                run[t] = 1 if (on and prev >= 0 and a.period != "single") else 0       # (a 'single' walk has no previous value: never scores)
                 if on:
                     prev = ps[t]
             else:
                 ms[t] = low.slot(a.mean_f, c)
-                run[t] = 1 if on else 0
+                run[t] = (2 if a.period == "single" else 1) if on else 0
         q = [0] * K["G3RN_LEN"]
         q[K["G3RN_RUN_OFF"]], q[K["G3RN_PARAM_OFF"]] = b.alloc_ints(run), b.alloc_ints(ps)
         q[K["G3RN_MEAN_OFF"]], q[K["G3RN_SIGMA_OFF"]] = b.alloc_ints(ms), b.alloc_ints(ss)

@@ -68,8 +68,9 @@ int64_t g3cuda_report_len(const g3cuda_model* m); /* doubles written by g3cuda_r
  *               understocking = sum of nll_understocking__wgt; bounds = penalty sum), or NULL
  *   grad        out, B x K forward-mode d nll / d par[tangent_idx[k]], or NULL
  * A vector with retro_years < 0 yields NaN (a value, as in the reference: R/action_time.R:78-79); a vector with
- * project_years >= 1 is refused with G3CUDA_EUNSUPP (projections are outside the supported subset; the
- * device-pointer entry point cannot look at the values and returns NaN for such rows).
+ * project_years beyond the years the spec's per-step tables cover (NT / NSTEPS - (END_YEAR - START_YEAR + 1): the
+ * max_project_years the model was lowered with, 0 by default) is refused with G3CUDA_EUNSUPP; the device-pointer entry
+ * point cannot look at the values and returns NaN for such rows.
  * Replaces: obj$fn(par), obj$gr(par) of the TMB ADFun (R/run_tmb.R:1254-1260,
  * man/run_tmb.Rd:233-242), called once per vector by nlminb/optim. */
 int g3cuda_eval_batch(g3cuda_model* m, const double* par, int64_t B,

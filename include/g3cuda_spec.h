@@ -230,7 +230,8 @@
    A random walk is the same record with MEAN[t] = the PARAM slot of the previous run step (its first run step only
    remembers the value: RUN = 0 there). */
 #define G3RN_RUN_OFF       0   /* ints[NT]: 1 = the term is added on step t (period 'step': every step; 'year': the year's last
-                                  step; 'single': the model's last step) */
+                                  step); 2 = added on step t if t is the last step of this parameter vector's run, cur_time ==
+                                  total_steps (period 'single': it moves with retro_years) */
 #define G3RN_PARAM_OFF     1   /* ints[NT]: slot of param_f on step t */
 #define G3RN_MEAN_OFF      2   /* ints[NT]: slot of mean_f on step t (walk: of param_f on the previous run step) */
 #define G3RN_SIGMA_OFF     3   /* ints[NT]: slot of sigma_f on step t */

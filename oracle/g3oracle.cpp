@@ -915,7 +915,8 @@ T run_model(const Spec& S, const ParVec<T>& pv, double* comp_out /*n_nll or null
         // ---- g3l_random_dnorm / g3l_random_walk (R/likelihood_random.R:14-109): n = sense * dnorm(param, mean, sigma, log)
         for (int r = 0; r < S.h(G3H_NRAND); r++) {
             const int32_t* Rn = S.I + S.h(G3H_RAND_OFF) + r * G3RN_LEN;
-            if (!S.I[Rn[G3RN_RUN_OFF] + cur_time]) continue;
+            const int run = S.I[Rn[G3RN_RUN_OFF] + cur_time];
+            if (!run || (run == 2 && cur_time != total_steps)) continue;
             T x = slot(S.I[Rn[G3RN_PARAM_OFF] + cur_time]), mu = slot(S.I[Rn[G3RN_MEAN_OFF] + cur_time]);
             T sd = slot(S.I[Rn[G3RN_SIGMA_OFF] + cur_time]);
             T resid = (x - mu) / sd;

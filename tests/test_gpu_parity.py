@@ -466,6 +466,7 @@ def test_random_effect_terms(oracle_lib, name, kernel):
     orc = Oracle(*model.pack(p))
     P = np.vstack([fn.par[None, :], parameter_batch(p, 63, seed=21)])
     full = fn.full_par(P)
+    full[7, p.index("retro_years")], full[9, p.index("retro_years")] = 2.0, 1.0      # 'single' terms score at the run's own last step
     fn.handle.set_kernel(kernel)
     g_nll, g_comp, _ = fn.handle.eval_batch(full, want_comp=True)
     o_nll, o_comp, _ = orc.eval_batch(full, want_comp=True, nthreads=8)
@@ -494,3 +495,40 @@ def test_random_effect_terms(oracle_lib, name, kernel):
     rg, ro = fn.report(P[1]), unpack_report(model, orc.report(full[1]))
     for n in model.random_names:
         np.testing.assert_allclose(rg[n + "__dnorm"], ro[n + "__dnorm"], rtol=1e-13, atol=0.0, err_msg=n)
+
+
+@KERNELS
+def test_projection_years(oracle_lib, kernel):
+    """project_years up to the room the model was lowered with (g3_to_cuda(max_project_years = 3); R/action_time.R:21-78; the
+    oracle's projected years by hand in tests/test_oracle_projection.py): vectors that project 0..3 years side by side, values,
+    gradients and the reported history against the oracle; one year more is refused, not answered with a NaN."""
+    from gadget3_b200._lib import G3CudaError
+    model, p = CONFIGS["C1_PROJ"]()
+    fn = g3_cuda_adfun(model, p, device=0)
+    orc = Oracle(*model.pack(p))
+    P = np.vstack([fn.par[None, :], parameter_batch(p, 63, seed=33)])
+    full = fn.full_par(P)
+    pj = p.index("project_years")
+    full[:, pj] = np.arange(64) % 4
+    full[4, p.index("retro_years")] = 1.0         # (with project_years = 0: a retro year that is projected again has its data back)
+    fn.handle.set_kernel(kernel)
+    g_nll, g_comp, _ = fn.handle.eval_batch(full, want_comp=True)
+    o_nll, o_comp, _ = orc.eval_batch(full, want_comp=True, nthreads=8)
+    ncomp = len(model.comp_names)
+    assert _rel(g_comp[:, :ncomp], o_comp[:, :ncomp]).max() < NLL_RTOL
+    us_tol = _us_tolerance(model, p, o_comp[:, -2])
+    assert (np.abs(g_nll - o_nll) <= NLL_RTOL * np.abs(o_nll) + US_WEIGHT * us_tol).all()
+    # no observation and no landing in the projected years: the objective does not move
+    full0 = full.copy(); full0[:, pj] = 0
+    assert np.array_equal(fn.handle.eval_batch(full0)[0], g_nll)
+    tix = fn.opt_idx.astype(np.int32)[:12]
+    _, _, gg = fn.handle.eval_batch(full[:4], tangent_idx=tix)
+    _, _, og = orc.eval_batch(full[:4], tangent_idx=tix)
+    assert ((np.abs(gg - og) / np.abs(og).max(axis=1, keepdims=True)).max(axis=1) < GRAD_RTOL + US_WEIGHT * us_tol[:4] / np.abs(o_nll[:4])).all()
+    rg, ro = unpack_report(model, fn.handle.report(full[3])), unpack_report(model, orc.report(full[3]))      # projects 3 years
+    for k in ("dstart_fish__num", "dstart_fish__wgt", "detail_fish__renewalnum"):
+        assert ro[k][..., -1].sum() > 0, k
+        np.testing.assert_allclose(rg[k], ro[k], rtol=1e-9, atol=1e-12 * np.abs(ro[k]).max(), err_msg=k)
+    full[2, pj] = 4
+    with pytest.raises(G3CudaError, match="max_project_years"):
+        fn.handle.eval_batch(full)

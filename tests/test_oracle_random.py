@@ -115,3 +115,22 @@ def test_period_guessing_and_argument_checks():
     with pytest.raises(ValueError):
         g3l_random_dnorm("a", gp("x"), log_f=1)
     assert g3l_random_walk("w", gp("x", by_year=True)).report_name == "nll_random_walk_w"
+
+
+def test_single_terms_follow_retro_years(oracle_lib):
+    """period = 'single' scores at cur_time == total_steps (R/likelihood_random.R:46): with retro_years = 2 the run ends
+    two years earlier and the term is still added, once, at ITS last step; the yearly walk loses its last two steps."""
+    model, p = CONFIGS["RANDOM_RIG"]()
+    orc = Oracle(*model.pack(p))
+    v = p.values().copy()
+    v[p.index("retro_years")] = 2.0
+    nll, comp, _ = orc.eval_batch(v[None, :], want_comp=True)
+    d = dict(zip(p.switch, v))
+    h = _hand(d)
+    assert comp[0, 1] == pytest.approx(h["dnorm_log"], rel=1e-12) and comp[0, 0] == pytest.approx(h["dnorm_lin"], rel=1e-12)
+    wy = [d[f"walk_year.{y}"] for y in range(1990, 1993)]
+    assert comp[0, 3] == pytest.approx(_walk(wy, d["walk_year_sigma"]), rel=1e-12)
+    ws = [d[f"walk_step.{y}.{s}"] for y in range(1990, 1993) for s in range(1, 5)]
+    assert comp[0, 2] == pytest.approx(_walk(ws, d["walk_step_sigma"]), rel=1e-12)
+    rep = unpack_report(model, orc.report(v))
+    assert np.flatnonzero(rep["nll_random_dnorm_dnorm_log__dnorm"]).tolist() == [11]

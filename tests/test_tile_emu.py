@@ -133,3 +133,25 @@ def test_lean_instantiations_are_bit_identical(oracle_lib, name):
     a = emu.eval_batch(ints, reals, full, want_comp=True, lean=True)
     b = emu.eval_batch(ints, reals, full, want_comp=True, lean=False)
     assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_random_terms_follow_retro_years(oracle_lib):
+    """g3l_random_dnorm with period 'single' scores at the last step of each vector's own run (retro_years differs by lane)."""
+    model, p, ints, reals, full, _ = _setup("RANDOM_RIG", 4)
+    full[1, p.index("retro_years")], full[2, p.index("retro_years")] = 2.0, 1.0
+    o_nll, o_comp, _ = Oracle(ints, reals).eval_batch(full, want_comp=True, nthreads=2)
+    g_nll, g_comp, _ = emu.eval_batch(ints, reals, full, want_comp=True, smem_state=True, lanes_per_tile=4, ncta=1)
+    assert (np.abs(g_comp[:, :4] - o_comp[:, :4]) <= 1e-12 * np.abs(o_comp[:, :4])).all() and (o_comp[:, :2] != 0).all()
+    assert (np.abs(g_nll - o_nll) <= 1e-12 * np.abs(o_nll)).all()
+
+
+def test_projection_years_differ_by_lane(oracle_lib):
+    """project_years is a parameter: the lanes of one tile run 0..3 years past end_year (g3_to_cuda(max_project_years = 3))."""
+    model, p, ints, reals, full, _ = _setup("C1_PROJ", 5)
+    pj, rt = p.index("project_years"), p.index("retro_years")
+    full[1, pj], full[2, pj], full[3, pj], full[4, rt] = 1.0, 2.0, 3.0, 1.0
+    o_nll, o_comp, _ = Oracle(ints, reals).eval_batch(full, want_comp=True, nthreads=2)
+    for smem in (True, False):
+        g_nll, g_comp, _ = emu.eval_batch(ints, reals, full, want_comp=True, smem_state=smem, lanes_per_tile=5, ncta=1)
+        assert (np.abs(g_nll - o_nll) / np.abs(o_nll)).max() < 1e-10
+        assert (np.abs(g_comp[:, :3] - o_comp[:, :3]) <= 1e-10 * np.abs(o_comp[:, :3])).all()
