@@ -31,14 +31,15 @@ g3_cuda_load_spec <- function(path) {
         parameter_template = pt)
 }
 
-g3_to_cuda <- function(actions, strict = FALSE, spec_file = NULL) {
+g3_to_cuda <- function(actions, strict = FALSE, spec_file = NULL, max_project_years = 0L) {
     if (!is.null(spec_file)) {
         model <- g3_cuda_load_spec(spec_file)
         attr(model, "actions") <- actions
         return(model)
     }
     collated <- g3_collate(actions)                       # same ordering contract as g3_to_tmb (R/run.R:31-72)
-    spec <- g3_cuda_lower(collated)                       # stop("g3_to_cuda: unsupported action ", name) outside the subset:
+    spec <- g3_cuda_lower(collated, max_project_years)    # per-step tables reach end_year + max_project_years (project_years runs);
+                                                          # stop("g3_to_cuda: unsupported action ", name) outside the subset:
                                                           # there is no CPU fallback
     structure(list(ints = spec$ints, reals = spec$reals, report_layout = spec$report_layout), class = "g3_cuda",
         actions = actions,
