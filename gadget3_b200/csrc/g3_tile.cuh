@@ -149,12 +149,14 @@ __device__ __forceinline__ int g3t_grab(int* ctr) {
     return __shfl_sync(0xffffffffu, v, 0);
 }
 #define G3T_GRAB(p) g3t_grab(p)
+__device__ __forceinline__ void g3t_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #define G3T_TID(warp, lane) ((warp) * 32 + (lane))
 #define G3T_NTHREADS(warps) ((warps) * 32)
 #else
 #define G3T_TID(warp, lane) (warp)              /* one emulated lane at a time: its warps share the copy */
 #define G3T_NTHREADS(warps) (warps)
 #define G3T_GRAB(p) __atomic_fetch_add((p), 1, __ATOMIC_SEQ_CST)
+inline void g3t_prefetch(const void*) {}
 struct EmuCtx { void (*bar)(void*); void* arg; };
 #define G3T_BAR() ctx.bar(ctx.arg)
 #define G3T_ANY(p) (p)
@@ -817,6 +819,15 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     bool any_cn = false;        // catch in numbers: cons / avoid_zero(wgt)
                     for (int j = 0; j < St.cx_n; j++) { const int x = tb[St.cx_off + j]; any_cn = any_cn || (((xact >> x) & 1) && Txb[x].unit == 0); }
                     if (any_cn) {
+                        // (the collect values were written by the predation pass: where the slabs do not fit the L2 every one of
+                        // these loads is a DRAM round trip -- get them on their way before the reciprocal chain, and read a block's
+                        // rows together instead of load - store - load)
+                        for (int j = 0; j < St.cx_n; j++) {
+                            const int x = tb[St.cx_off + j];
+                            if (!(((xact >> x) & 1) && Txb[x].unit == 0)) continue;
+#pragma unroll
+                            for (int b = 0; b < NB; b++) if (b < nb) g3t_prefetch(GP(Txb[x].g_x + cell + b));
+                        }
                         T iw[NB], de[NB];
 #pragma unroll
                         for (int b = 0; b < NB; b++) { iw[b] = T(1.0); de[b] = wgt[b]; }
@@ -825,8 +836,11 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             const int x = tb[St.cx_off + j];
                             if (!(((xact >> x) & 1) && Txb[x].unit == 0)) continue;
                             const int gx = Txb[x].g_x + cell;
+                            T xv[NB];
 #pragma unroll
-                            for (int b = 0; b < NB; b++) if (b < nb) GS(gx + b, G(gx + b) * iw[b]);
+                            for (int b = 0; b < NB; b++) xv[b] = G(gx + min(b, nb - 1));
+#pragma unroll
+                            for (int b = 0; b < NB; b++) if (b < nb) GS(gx + b, xv[b] * iw[b]);
                         }
                     }
                 }
@@ -1040,6 +1054,13 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     const int r0 = j * NB, nb = min(NB, U.len - r0);
                     T an[NB], aw[NB], num[NB], wgt[NB], de[NB];
                     const bool low = U.g_ghost >= 0 && r0 < NW - 1;
+                    if (!SMEM && j > 0) {       // state in the slab: the rows the NEXT block adds to the window, on their way now
+#pragma unroll
+                        for (int b = 0; b < NB; b++) {
+                            const int rr = r0 - NB - (NW - 1) + b;
+                            if (rr >= 0) { g3t_prefetch(pNum + (unsigned)rr * C); g3t_prefetch(pWgt + (unsigned)rr * C); }
+                        }
+                    }
                     if (cont_now) {
                         if (low) grow_gather<T, NW, NB, 1, true>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
                         else grow_gather<T, NW, NB, 1, false>(pNum, pWgt, pQ, pB, pBr, pCm, pGh, r0, mortf, an, aw, num, wgt);
