@@ -704,6 +704,8 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                     const ColRec& Cl = Tcol[U.gc];
                     const StockRec& St = Tst[Cl.s];
                     const int L = St.L, c_lo = Cl.cell0 + U.lo;
+                    if (!SMEM && St.pp_n > 0)       // state in the slab: the unit's rows on their way (this loop and the predation pass read them)
+                        for (int r = 0; r < U.len; r++) { g3t_prefetch(SP(A.s_num + c_lo + r)); g3t_prefetch(SP(A.s_wgt + c_lo + r)); }
                     for (int j = 0; j < St.pp_n; j++) {
                         const int q = tb[St.pp_off + j];
                         const PairRec& Q = Tpp[q];
@@ -1228,6 +1230,10 @@ __device__ __forceinline__ void tile_body(const TArgs& A, double* smem, int* ctr
                             if (xkind == 0) {
 #pragma unroll
                                 for (int u = 0; u < CU; u++) xv[u] = G(xs + ix[u]);
+                                if (!SMEM && j + CU < j1) {     // (slabs larger than the L2: the next terms on their way under this sum)
+#pragma unroll
+                                    for (int u = 0; u < CU; u++) g3t_prefetch(GP(xs + ci[min(j + CU + u, j1 - 1)]));
+                                }
                             } else {
 #pragma unroll
                                 for (int u = 0; u < CU; u++) xv[u] = xunit == 0 ? S(A.s_num + ix[u]) : S(A.s_num + ix[u]) * S(A.s_wgt + ix[u]);
